@@ -1,0 +1,246 @@
+/*
+ * kbgpu.h — C ABI of libkbgpu.so, the B200-native engine for kube-batch's per-cycle
+ * `allocate` hot path.
+ *
+ * The reference (kubernetes-sigs/kube-batch @ 86b2ba2, pure Go) has NO FFI boundary; the
+ * boundary below is what a cgo binding inside `allocateAction.Execute`
+ * (pkg/scheduler/actions/allocate/allocate.go:43-194) would call instead of running the
+ * queue→job→task loop in Go.  Each entry point cites the reference code it replaces.
+ *
+ * Conventions: plain C, caller-allocated outputs, no torch / C++ types, return 0 on
+ * success or a negative kb_status.  Never throws, never aborts.  One session in flight
+ * per engine; thread-compatible, not thread-safe (matches the single `runOnce`
+ * goroutine, pkg/scheduler/scheduler.go:85-102).  kb_session_load copies everything it
+ * needs before returning (cgo forbids retaining Go pointers).
+ *
+ * There is NO CPU fallback: if no CUDA device is usable kb_engine_create fails with
+ * KB_E_CUDA.
+ */
+#ifndef KBGPU_H_
+#define KBGPU_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KB_ABI_VERSION 1u
+
+/* Compile-time capacity of the dense encodings. */
+#define KB_MAX_R 8          /* resource dims: 0 = cpu (milli), 1 = memory (bytes), 2.. = scalar resources (milli) */
+#define KB_MAX_W 4          /* 64-bit words per label / taint / host-port bitmask */
+#define KB_MAX_AFF_TERMS 4  /* OR-ed required node-affinity terms carried per task */
+#define KB_MAX_Q 256        /* queues */
+
+typedef enum kb_status {
+  KB_OK = 0,
+  KB_E_BADARG = -1,
+  KB_E_UNSUPPORTED_PLUGIN = -2, /* a non built-in plugin / closure the GPU path cannot honour */
+  KB_E_CUDA = -3,
+  KB_E_NCCL = -4,
+  KB_E_STATE = -5,              /* call order violated (e.g. kb_allocate before kb_session_load) */
+  KB_E_UNSUPPORTED_FEATURE = -6 /* snapshot uses a feature outside this build (inter-pod affinity, preferred affinity) */
+} kb_status;
+
+/* node_flags bits — evaluated once by the flattener from v1.Node
+ * (vendor/k8s.io/kubernetes/pkg/scheduler/algorithm/predicates/predicates.go:1675-1698, 1633-1671). */
+#define KB_NODE_NOT_READY        (1u << 0) /* a NodeReady condition with Status != True            */
+#define KB_NODE_NET_UNAVAILABLE  (1u << 1) /* a NodeNetworkUnavailable condition with Status != False */
+#define KB_NODE_UNSCHEDULABLE    (1u << 2) /* node.Spec.Unschedulable                               */
+#define KB_NODE_MEM_PRESSURE     (1u << 3)
+#define KB_NODE_DISK_PRESSURE    (1u << 4)
+#define KB_NODE_PID_PRESSURE     (1u << 5)
+
+/* task_flags bits */
+#define KB_TASK_BEST_EFFORT_QOS  (1u << 0) /* v1qos.GetPodQOS(pod) == BestEffort (memory-pressure predicate only) */
+#define KB_TASK_HAS_POD_AFFINITY (1u << 1) /* pod (anti)affinity terms present -> KB_E_UNSUPPORTED_FEATURE        */
+#define KB_TASK_HAS_PREFERRED_NODE_AFFINITY (1u << 2) /* -> KB_E_UNSUPPORTED_FEATURE                               */
+
+/* kb_decision.kind */
+#define KB_KIND_NONE      0 /* task was never placed this cycle                                   */
+#define KB_KIND_ALLOCATED 1 /* ssn.Allocate (framework/session.go:235)  — consumed node.Idle       */
+#define KB_KIND_PIPELINED 2 /* ssn.Pipeline (framework/session.go:194)  — consumed node.Releasing  */
+#define KB_KIND_SKIPPED   3 /* Resreq.IsEmpty(): skipped by allocate (allocate.go:113-118)         */
+
+/*
+ * Flattened Session snapshot (SoA).  Replaces the Go maps ssn.Jobs / ssn.Nodes / ssn.Queues
+ * (framework/session.go:37-46) as input of the cycle.  All arrays are caller-owned and only
+ * read during kb_session_load.
+ *
+ * Canonical orders (they replace Go's random map iteration, SURVEY.md §8c rules 1-4):
+ *   nodes  : index == rank in ascending node Name      (allocate.go:71 GetNodeList)
+ *   jobs   : index == rank in ascending JobID (UID)    (allocate.go:50)
+ *   queues : index == rank in ascending QueueID (UID)
+ *   tasks  : grouped by job (job_task_off); any order inside a job — the engine orders them
+ *            by TaskOrderFn (session_plugins.go:318-331); task_uid_rank = rank of TaskInfo.UID.
+ * Only Pending tasks are listed (allocate.go:112 iterates TaskStatusIndex[Pending]).
+ */
+typedef struct kb_snapshot {
+  uint32_t abi_version;     /* KB_ABI_VERSION */
+  uint32_t R;               /* 2..KB_MAX_R */
+  uint32_t W;               /* 1..KB_MAX_W */
+  uint32_t N, T, J, Q;
+  uint32_t reserved0;       /* 0 */
+
+  /* ---- nodes (api.NodeInfo, api/node_info.go:28-47) ---- */
+  const double*   node_idle;          /* [R][N] NodeInfo.Idle                                        */
+  const double*   node_releasing;     /* [R][N] NodeInfo.Releasing                                   */
+  const double*   node_used;          /* [R][N] NodeInfo.Used (bookkeeping; returned by kb_node_state) */
+  const double*   node_allocatable;   /* [R][N] NodeInfo.Allocatable as float64 (drf.go:62-64, proportion.go:60-62) */
+  const uint32_t* node_alloc_present; /* [N] bit r (r>=2): scalar r present in Allocatable.ScalarResources */
+  const int64_t*  node_alloc_cpu;     /* [N] k8s nodeinfo allocatableResource.MilliCPU (resource_allocation.go:100-110) */
+  const int64_t*  node_alloc_mem;     /* [N] k8s nodeinfo allocatableResource.Memory                 */
+  const int64_t*  node_nz_cpu;        /* [N] nonzeroRequest.MilliCPU over every task in NodeInfo.Tasks (nodeinfo/node_info.go:513) */
+  const int64_t*  node_nz_mem;        /* [N]                                                         */
+  const int32_t*  node_pods;          /* [N] len(NodeInfo.Tasks)  (predicates.go:127)                */
+  const int32_t*  node_max_pods;      /* [N] Allocatable.MaxTaskNum                                  */
+  const uint32_t* node_flags;         /* [N] KB_NODE_*                                               */
+  const uint64_t* node_labels;        /* [W][N] bit a: selector-requirement atom a holds on the node */
+  const uint64_t* node_taints;        /* [W][N] bit a: node carries NoSchedule/NoExecute taint a     */
+  const uint64_t* node_ports;         /* [W][N] bit a: host-port atom (ip,proto,port) a is in use    */
+
+  /* ---- pending tasks (api.TaskInfo, api/job_info.go:36-54) ---- */
+  const double*   task_initreq;       /* [R][T] TaskInfo.InitResreq (predicate / fit)                */
+  const double*   task_resreq;        /* [R][T] TaskInfo.Resreq (bookkeeping); must be <= initreq per dim */
+  const uint32_t* task_res_present;   /* [T] bit r (r>=2): scalar r present in Resreq.ScalarResources */
+  const int64_t*  task_nz_cpu;        /* [T] calculatePodResourceRequest(pod, cpu) (resource_allocation.go:127) */
+  const int64_t*  task_nz_mem;        /* [T]                                                         */
+  const uint64_t* task_sel_req;       /* [W][T] nodeSelector atoms that must ALL hold                */
+  const uint64_t* task_aff_terms;     /* [KB_MAX_AFF_TERMS][W][T] required node-affinity terms (OR of AND-masks) */
+  const uint32_t* task_n_aff_terms;   /* [T] 0 = no required node affinity                           */
+  const uint64_t* task_tol;           /* [W][T] taint atoms tolerated by some toleration             */
+  const uint64_t* task_port_own;      /* [W][T] host-port atoms the pod occupies once placed         */
+  const uint64_t* task_port_conflict; /* [W][T] host-port atoms that conflict with a wanted port (host_ports.go:96-125) */
+  const uint32_t* task_flags;         /* [T] KB_TASK_*                                               */
+  const int32_t*  task_prio;          /* [T] TaskInfo.Priority                                       */
+  const int64_t*  task_ctime;         /* [T] Pod.CreationTimestamp (any monotone integer)            */
+  const uint32_t* task_uid_rank;      /* [T] rank of TaskInfo.UID (string order), unique             */
+
+  /* ---- jobs (api.JobInfo, api/job_info.go:127-154) ---- */
+  const uint32_t* job_task_off;       /* [J+1] task range of job j                                   */
+  const int32_t*  job_min_avail;      /* [J] JobInfo.MinAvailable                                    */
+  const int32_t*  job_ready0;         /* [J] ReadyTaskNum() at session open (job_info.go:383)        */
+  const double*   job_alloc0;         /* [R][J] sum Resreq of AllocatedStatus tasks (drf.go:71-77)   */
+  const uint32_t* job_alloc0_present; /* [J] scalar presence of that sum                             */
+  const uint32_t* job_queue;          /* [J] queue index                                             */
+  const int32_t*  job_prio;           /* [J] JobInfo.Priority                                        */
+  const int64_t*  job_ctime;          /* [J] JobInfo.CreationTimestamp                               */
+
+  /* ---- queues (api.QueueInfo, api/queue_info.go:74-81) ---- */
+  const int32_t*  queue_weight;       /* [Q]                                                         */
+  const int64_t*  queue_ctime;        /* [Q]                                                         */
+} kb_snapshot;
+
+/* Mirrors conf.PluginOption (pkg/scheduler/conf/scheduler_conf.go:33-56).  The Enabled* tri-states
+ * are resolved by the caller: nil -> 0 (framework `isEnabled`, session_plugins.go:371) unless the
+ * caller applied plugins.ApplyPluginConfDefaults (plugins/defaults.go:22-52), which sets nil -> 1. */
+typedef struct kb_plugin_option {
+  const char* name; /* "priority" "gang" "drf" "predicates" "proportion" "nodeorder" "conformance" */
+  uint8_t enabled_job_order;
+  uint8_t enabled_job_ready;
+  uint8_t enabled_job_pipelined;
+  uint8_t enabled_task_order;
+  uint8_t enabled_preemptable;
+  uint8_t enabled_reclaimable;
+  uint8_t enabled_queue_order;
+  uint8_t enabled_predicate;
+  uint8_t enabled_node_order;
+  uint32_t n_args;              /* framework.Arguments (framework/arguments.go:26) */
+  const char* const* arg_keys;
+  const char* const* arg_values;
+} kb_plugin_option;
+
+typedef struct kb_tier {
+  uint32_t n_plugins;
+  const kb_plugin_option* plugins;
+} kb_tier;
+
+typedef struct kb_plugin_conf {
+  uint32_t n_tiers;
+  const kb_tier* tiers;
+} kb_plugin_conf;
+
+typedef struct kb_engine_opts {
+  uint32_t abi_version;     /* KB_ABI_VERSION */
+  int32_t  device;          /* CUDA device ordinal */
+  /* Node-axis sharding.  world_size == 1: single GPU.  world_size > 1: this
+   * process is rank `rank`; `nccl_unique_id` (128 bytes, from ncclGetUniqueId on rank 0,
+   * distributed by the caller) bootstraps the communicator. */
+  int32_t  rank;
+  int32_t  world_size;
+  const void* nccl_unique_id;
+  uint32_t flags;           /* reserved, 0 */
+} kb_engine_opts;
+
+typedef struct kb_decision {
+  int32_t  node;          /* canonical node index, -1 if none                                  */
+  uint8_t  kind;          /* KB_KIND_*                                                         */
+  uint8_t  dispatched;    /* 1 if ssn.dispatch ran for the task (session.go:277-285): gang commit */
+  uint16_t reserved;
+  uint32_t step;          /* 0-based global order of the Allocate/Pipeline call, 0xFFFFFFFF if none */
+  uint32_t dispatch_step; /* step of the Allocate call whose JobReady triggered the dispatch    */
+} kb_decision;
+
+typedef struct kb_stats {
+  uint64_t pairs_logical;   /* sum over processed tasks of N  (BASELINE.md §3 work unit)        */
+  uint64_t pairs_scanned;   /* (class,node) pairs the scan kernels really evaluated             */
+  uint64_t pairs_replayed;  /* (task,node) pairs re-evaluated exactly during replay             */
+  uint32_t tasks_processed; /* tasks popped from a task queue (allocate.go:130)                 */
+  uint32_t tasks_allocated;
+  uint32_t tasks_pipelined;
+  uint32_t jobs_ready;      /* jobs with JobReady at cycle end that placed >= 1 task this cycle */
+  uint32_t visits;          /* job visits (allocate.go:109 pops)                                */
+  uint32_t kernel_launches; /* CUDA kernels launched by kb_allocate                             */
+  uint32_t n_classes;       /* task equivalence classes in the session                          */
+  float    gpu_ms;          /* device time of the cycle (CUDA events on the engine stream)      */
+  float    load_ms;         /* host time of kb_session_load (flatten->device)                   */
+} kb_stats;
+
+/* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,
+ * and (world_size > 1) the NCCL communicator used for the per-run best-candidate exchange. */
+int kb_engine_create(const kb_engine_opts* opts, struct kb_engine** out);
+void kb_engine_destroy(struct kb_engine* e);
+
+/* Replaces framework.OpenSession's in-memory wiring (framework/framework.go:30-52): the snapshot
+ * deep copy (cache/cache.go:627-683) arrives flattened, plugins are identified BY NAME + arguments
+ * (plugins/factory.go:31-42) and their OnSessionOpen precomputation (drf.go:60-83,
+ * proportion.go:58-154) is redone here.  Unknown plugin names -> KB_E_UNSUPPORTED_PLUGIN. */
+int kb_session_load(struct kb_engine* e, const kb_snapshot* snap, const kb_plugin_conf* conf);
+
+/* Replaces allocateAction.Execute (actions/allocate/allocate.go:43-194) and everything it calls
+ * (util.PredicateNodes / PrioritizeNodes / SelectBestNode, ssn.Allocate / ssn.Pipeline bookkeeping,
+ * JobReady gang commit).  `out` has T entries indexed like the snapshot's tasks.  The Go shim then
+ * replays `out` in `step` order through the unchanged ssn.Allocate / ssn.Pipeline. */
+int kb_allocate(struct kb_engine* e, kb_decision* out, kb_stats* stats);
+
+/* Debug / parity: predicate + score of tasks [task_lo, task_hi) against every node in the CURRENT
+ * device state (util.PredicateNodes + util.PrioritizeNodes for a task range, scheduler_helper.go:63-171).
+ * fit   [(task_hi-task_lo)][N] uint8 (1 = predicateFn returned nil), may be NULL
+ * score [(task_hi-task_lo)][N] double (HostPriority.Score; 0 where !fit), may be NULL */
+int kb_predicate_score(struct kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score);
+
+/* K1+K2+K3 in one launch over the whole task range: per task the packed best key
+ * (score << 32 | 0xFFFFFFFF - node) against the CURRENT device state, 0 if no node fits
+ * (util.SelectBestNode with the deterministic first-max rule, scheduler_helper.go:188-208). */
+int kb_best_nodes(struct kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint64_t* best_key);
+
+/* Current node bookkeeping after kb_allocate (NodeInfo.Idle/Releasing/Used, pod count, nonzero
+ * request, used host ports) — what node_info.go:172-212 AddTask left behind.  Any pointer may be NULL. */
+int kb_node_state(struct kb_engine* e, double* idle /*[R][N]*/, double* releasing /*[R][N]*/, double* used /*[R][N]*/,
+                  int32_t* pods /*[N]*/, int64_t* nz_cpu /*[N]*/, int64_t* nz_mem /*[N]*/, uint64_t* ports /*[W][N]*/);
+
+/* Job / queue ordering state at cycle end (drf.go:161-171 share, proportion.go:241-253 share + deserved). */
+int kb_order_state(struct kb_engine* e, double* job_share /*[J]*/, int32_t* job_ready /*[J]*/, double* queue_share /*[Q]*/,
+                   double* queue_deserved /*[R][Q]*/, double* queue_allocated /*[R][Q]*/);
+
+const char* kb_last_error(struct kb_engine* e);
+const char* kb_status_str(int status);
+/* "libkbgpu <version> sm_100a" — also proves which shared object is loaded. */
+const char* kb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBGPU_H_ */

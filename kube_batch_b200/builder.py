@@ -1,0 +1,408 @@
+"""Object-level session builder -> flattened Snapshot (the "flattener").
+
+Mirrors the in-memory harness of the reference's action tests
+(/root/reference/pkg/scheduler/actions/allocate/allocate_test.go:150-198: objects are fed through
+cache.AddNode / AddPod / AddPodGroup / AddQueue, then framework.OpenSession takes cache.Snapshot())
+and the helper constructors of /root/reference/pkg/scheduler/util/test_utils.go:34-93.  It is also the
+executable specification of what the Go shim's flattening must compute:
+
+  * canonical orders: nodes by Name, jobs by JobID "<ns>/<podgroup>", queues by QueueID (= Name),
+    task_uid_rank = rank of Pod.UID;
+  * selector / required-affinity requirements, NoSchedule|NoExecute taints and host ports are
+    interned per snapshot into bit "atoms";
+  * node aggregates (Idle / Used / Releasing, pod count, non-zero request sums, used ports) follow
+    api.NodeInfo.AddTask (api/node_info.go:172-212) and k8s nodeinfo.AddPod
+    (vendor/k8s.io/kubernetes/pkg/scheduler/nodeinfo/node_info.go:502-524).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import abi
+from .snapshot import Snapshot
+
+DEFAULT_MILLI_CPU_REQUEST = 100                 # priorities/util/non_zero.go:36
+DEFAULT_MEMORY_REQUEST = 200 * 1024 * 1024      # :38
+GPU = "nvidia.com/gpu"
+
+_SUFFIX = {"Ki": 1 << 10, "Mi": 1 << 20, "Gi": 1 << 30, "Ti": 1 << 40,
+           "k": 10 ** 3, "M": 10 ** 6, "G": 10 ** 9, "T": 10 ** 12}
+
+
+def parse_quantity(q) -> float:
+    """resource.MustParse for the forms the reference tests use ("1", "500m", "4Gi", "1G")."""
+    if isinstance(q, (int, float)):
+        return float(q)
+    s = str(q)
+    if s.endswith("m"):
+        return float(s[:-1]) / 1000.0
+    for suf in ("Ki", "Mi", "Gi", "Ti", "k", "M", "G", "T"):
+        if s.endswith(suf):
+            return float(s[: -len(suf)]) * _SUFFIX[suf]
+    return float(s)
+
+
+def build_resource_list(cpu, memory, gpu="0") -> Dict[str, float]:
+    """util.BuildResourceList / BuildResourceListWithGPU (util/test_utils.go:34-49):
+    cpu in cores, memory in bytes, nvidia.com/gpu always present."""
+    return {"cpu": parse_quantity(cpu), "memory": parse_quantity(memory), GPU: parse_quantity(gpu)}
+
+
+@dataclass
+class Node:
+    name: str
+    allocatable: Dict[str, float]                 # ResourceList: cpu (cores), memory (bytes), pods, scalars (units)
+    labels: Dict[str, str] = field(default_factory=dict)
+    taints: List[Tuple[str, str, str]] = field(default_factory=list)   # (key, value, effect)
+    unschedulable: bool = False
+    ready: Optional[bool] = None                  # NodeReady condition status; None = condition absent
+    network_unavailable: Optional[bool] = None
+    memory_pressure: bool = False
+    disk_pressure: bool = False
+    pid_pressure: bool = False
+
+
+@dataclass
+class Pod:
+    namespace: str
+    name: str
+    node_name: str = ""
+    phase: str = "Pending"                        # Pending | Running | Succeeded | Failed | Unknown
+    requests: Dict[str, float] = field(default_factory=dict)   # single container; keys may be absent
+    init_requests: List[Dict[str, float]] = field(default_factory=list)
+    group: str = ""
+    labels: Dict[str, str] = field(default_factory=dict)
+    node_selector: Dict[str, str] = field(default_factory=dict)
+    # required node affinity: OR over terms, each an AND of (key, op, values), op in In NotIn Exists DoesNotExist Gt Lt
+    affinity_terms: Optional[List[List[Tuple[str, str, Sequence[str]]]]] = None
+    tolerations: List[Tuple[str, str, str, str]] = field(default_factory=list)   # (key, operator, value, effect)
+    host_ports: List[Tuple[str, str, int]] = field(default_factory=list)          # (hostIP, protocol, hostPort)
+    priority: Optional[int] = None
+    creation: int = 0
+    deleting: bool = False
+    uid: Optional[str] = None
+    limits: Dict[str, float] = field(default_factory=dict)
+
+
+@dataclass
+class PodGroup:
+    namespace: str
+    name: str
+    queue: str
+    min_member: int = 0
+    priority: int = 0                             # resolved PriorityClass value (cache.go:664-674)
+    creation: int = 0
+
+
+@dataclass
+class Queue:
+    name: str
+    weight: int = 1
+    creation: int = 0
+
+
+def build_node(name, alloc: Dict[str, float], labels=None, pods: Optional[int] = None) -> Node:
+    """util.BuildNode (util/test_utils.go:52-63).  NB the reference helper sets no `pods` capacity, so
+    MaxTaskNum = 0 and the predicates plugin rejects every such node (predicates.go:127)."""
+    a = dict(alloc)
+    if pods is not None:
+        a["pods"] = pods
+    return Node(name, a, dict(labels or {}))
+
+
+def build_pod(namespace, name, nodename, phase, req, group_name, labels=None, selector=None) -> Pod:
+    """util.BuildPod (util/test_utils.go:66-93)."""
+    return Pod(namespace, name, nodename, phase, dict(req), group=group_name, labels=dict(labels or {}),
+               node_selector=dict(selector or {}), uid=f"{namespace}-{name}")
+
+
+def _match_requirement(labels: Dict[str, str], key: str, op: str, values: Sequence[str]) -> bool:
+    """labels.Requirement.Matches via v1helper.NodeSelectorRequirementsAsSelector
+    (vendor/k8s.io/kubernetes/pkg/apis/core/v1/helper/helpers.go:205-316)."""
+    if op == "In":
+        return key in labels and labels[key] in values
+    if op == "NotIn":
+        return key not in labels or labels[key] not in values
+    if op == "Exists":
+        return key in labels
+    if op == "DoesNotExist":
+        return key not in labels
+    if op in ("Gt", "Lt"):
+        if key not in labels:
+            return False
+        try:
+            lv, rv = int(labels[key]), int(values[0])
+        except (ValueError, IndexError):
+            return False
+        return lv > rv if op == "Gt" else lv < rv
+    raise ValueError(f"unknown operator {op}")
+
+
+def _tolerates(tol: Tuple[str, str, str, str], taint: Tuple[str, str, str]) -> bool:
+    """Toleration.ToleratesTaint (vendor/k8s.io/api/core/v1/toleration.go:37-56)."""
+    key, op, value, effect = tol
+    tkey, tvalue, teffect = taint
+    if effect and effect != teffect:
+        return False
+    if key and key != tkey:
+        return False
+    if op in ("", "Equal"):
+        return value == tvalue
+    if op == "Exists":
+        return True
+    return False
+
+
+def _sanitize_port(ip: str, proto: str, port: int):
+    return (ip or "0.0.0.0", proto or "TCP", int(port))   # HostPortInfo.sanitize (host_ports.go:127-135)
+
+
+def _ports_conflict(a, b) -> bool:
+    """HostPortInfo.CheckConflict (host_ports.go:96-125): same (proto, port) and equal IPs or a wildcard."""
+    if a[1] != b[1] or a[2] != b[2]:
+        return False
+    return a[0] == b[0] or a[0] == "0.0.0.0" or b[0] == "0.0.0.0"
+
+
+class SessionBuilder:
+    def __init__(self):
+        self.nodes: List[Node] = []
+        self.pods: List[Pod] = []
+        self.pod_groups: List[PodGroup] = []
+        self.queues: List[Queue] = []
+
+    def add_node(self, n: Node):
+        self.nodes.append(n)
+        return self
+
+    def add_pod(self, p: Pod):
+        self.pods.append(p)
+        return self
+
+    def add_pod_group(self, g: PodGroup):
+        self.pod_groups.append(g)
+        return self
+
+    def add_queue(self, q: Queue):
+        self.queues.append(q)
+        return self
+
+    # ---- api.NewResource (api/resource_info.go:73-90): cpu -> milli, memory -> bytes, scalars -> milli ----
+    @staticmethod
+    def _resource(rl: Dict[str, float], dims: List[str]):
+        v = np.zeros(len(dims))
+        present = 0
+        for k, q in rl.items():
+            if k == "cpu":
+                v[0] += round(q * 1000.0)
+            elif k == "memory":
+                v[1] += q
+            elif k == "pods":
+                continue
+            else:
+                r = dims.index(k)
+                v[r] += round(q * 1000.0)
+                present |= 1 << r
+        return v, present
+
+    @staticmethod
+    def _task_status(p: Pod) -> str:
+        """api.getTaskStatus (api/helpers.go:38-62)."""
+        if p.phase == "Running":
+            return "Releasing" if p.deleting else "Running"
+        if p.phase == "Pending":
+            if p.deleting:
+                return "Releasing"
+            return "Pending" if not p.node_name else "Bound"
+        return {"Succeeded": "Succeeded", "Failed": "Failed"}.get(p.phase, "Unknown")
+
+    def flatten(self, W: int = 1) -> Snapshot:
+        nodes = sorted(self.nodes, key=lambda n: n.name)
+        queues = sorted(self.queues, key=lambda q: q.name)
+        qidx = {q.name: i for i, q in enumerate(queues)}
+        groups = sorted(self.pod_groups, key=lambda g: f"{g.namespace}/{g.name}")
+        # cache.Snapshot drops jobs whose queue does not exist (cache/cache.go:652-656)
+        groups = [g for g in groups if g.queue in qidx]
+        jidx = {f"{g.namespace}/{g.name}": i for i, g in enumerate(groups)}
+        nidx = {n.name: i for i, n in enumerate(nodes)}
+
+        scalars = sorted({k for n in nodes for k in n.allocatable if k not in ("cpu", "memory", "pods")} |
+                         {k for p in self.pods for rl in [p.requests] + p.init_requests for k in rl if k not in ("cpu", "memory")})
+        dims = ["cpu", "memory"] + scalars
+        R = max(2, len(dims))
+        assert R <= abi.KB_MAX_R
+
+        pending = [p for p in self.pods if self._task_status(p) == "Pending" and f"{p.namespace}/{p.group}" in jidx]
+        uids = sorted((p.uid or f"{p.namespace}-{p.name}") for p in pending)
+        uid_rank = {u: i for i, u in enumerate(uids)}
+        assert len(uid_rank) == len(pending), "duplicate pod UIDs"
+        pending.sort(key=lambda p: jidx[f"{p.namespace}/{p.group}"])
+
+        # ---- atoms ----
+        req_atoms: Dict[Tuple, int] = {}
+
+        def atom_of(key, op, values):
+            k = (key, op, tuple(values))
+            if k not in req_atoms:
+                req_atoms[k] = len(req_atoms)
+            return req_atoms[k]
+
+        for p in pending:
+            for k, v in p.node_selector.items():
+                atom_of(k, "In", [v])
+            for term in (p.affinity_terms or []):
+                for (k, op, vals) in term:
+                    atom_of(k, op, vals)
+        taint_atoms: Dict[Tuple, int] = {}
+        for n in nodes:
+            for t in n.taints:
+                if t[2] in ("NoSchedule", "NoExecute") and t not in taint_atoms:
+                    taint_atoms[t] = len(taint_atoms)
+        port_atoms: Dict[Tuple, int] = {}
+        for p in self.pods:
+            for hp in p.host_ports:
+                if hp[2] <= 0:
+                    continue
+                sp = _sanitize_port(*hp)
+                if sp not in port_atoms:
+                    port_atoms[sp] = len(port_atoms)
+        need = max(len(req_atoms), len(taint_atoms), len(port_atoms), 1)
+        W = max(W, (need + 63) // 64)
+        assert W <= abi.KB_MAX_W, "too many atoms for KB_MAX_W words"
+
+        s = Snapshot(R, W, len(nodes), len(pending), len(groups), len(queues))
+
+        def setbit(arr, w_major_index, atom):
+            arr[atom // 64, w_major_index] |= np.uint64(1) << np.uint64(atom % 64)
+
+        # ---- nodes ----
+        for i, n in enumerate(nodes):
+            v, present = self._resource(n.allocatable, dims)
+            s.node_allocatable[:, i] = v
+            s.node_idle[:, i] = v
+            s.node_alloc_present[i] = present
+            s.node_alloc_cpu[i] = int(v[0])
+            s.node_alloc_mem[i] = int(v[1])
+            s.node_max_pods[i] = int(n.allocatable.get("pods", 0))
+            f = 0
+            if n.ready is not None and not n.ready:
+                f |= abi.KB_NODE_NOT_READY
+            if n.network_unavailable is not None and n.network_unavailable:
+                f |= abi.KB_NODE_NET_UNAVAILABLE
+            if n.unschedulable:
+                f |= abi.KB_NODE_UNSCHEDULABLE
+            if n.memory_pressure:
+                f |= abi.KB_NODE_MEM_PRESSURE
+            if n.disk_pressure:
+                f |= abi.KB_NODE_DISK_PRESSURE
+            if n.pid_pressure:
+                f |= abi.KB_NODE_PID_PRESSURE
+            s.node_flags[i] = f
+            for (k, op, vals), a in req_atoms.items():
+                if _match_requirement(n.labels, k, op, vals):
+                    setbit(s.node_labels, i, a)
+            for t in n.taints:
+                if t in taint_atoms:
+                    setbit(s.node_taints, i, taint_atoms[t])
+
+        # ---- pods already on nodes / counted in jobs ----
+        def pod_resreq(p: Pod):
+            return self._resource(p.requests, dims)
+
+        def pod_nz(p: Pod):
+            cpu = round(p.requests["cpu"] * 1000.0) if "cpu" in p.requests else DEFAULT_MILLI_CPU_REQUEST
+            mem = int(p.requests["memory"]) if "memory" in p.requests else DEFAULT_MEMORY_REQUEST
+            return int(cpu), int(mem)
+
+        for p in self.pods:
+            st = self._task_status(p)
+            key = f"{p.namespace}/{p.group}"
+            v, present = pod_resreq(p)
+            if st != "Pending" and key in jidx:
+                j = jidx[key]
+                if st in ("Bound", "Binding", "Running", "Allocated"):
+                    s.job_alloc0[:, j] += v
+                    s.job_alloc0_present[j] |= present
+                    s.job_ready0[j] += 1
+                elif st == "Succeeded":
+                    s.job_ready0[j] += 1
+            if p.node_name and p.node_name in nidx and st != "Pending":
+                i = nidx[p.node_name]
+                # api.NodeInfo.AddTask (node_info.go:172-212)
+                if st == "Releasing":
+                    s.node_idle[:, i] -= v
+                    s.node_releasing[:, i] += v
+                elif st == "Pipelined":
+                    s.node_releasing[:, i] -= v
+                else:
+                    s.node_idle[:, i] -= v
+                s.node_used[:, i] += v
+                s.node_pods[i] += 1
+                c, m = pod_nz(p)
+                s.node_nz_cpu[i] += c
+                s.node_nz_mem[i] += m
+                for hp in p.host_ports:
+                    if hp[2] > 0:
+                        setbit(s.node_ports, i, port_atoms[_sanitize_port(*hp)])
+
+        # ---- jobs / queues ----
+        for j, g in enumerate(groups):
+            s.job_min_avail[j] = g.min_member
+            s.job_queue[j] = qidx[g.queue]
+            s.job_prio[j] = g.priority
+            s.job_ctime[j] = g.creation
+        for q, qu in enumerate(queues):
+            s.queue_weight[q] = qu.weight
+            s.queue_ctime[q] = qu.creation
+
+        # ---- pending tasks ----
+        counts = np.zeros(len(groups) + 1, dtype=np.int64)
+        for t, p in enumerate(pending):
+            j = jidx[f"{p.namespace}/{p.group}"]
+            counts[j + 1] += 1
+            v, present = pod_resreq(p)
+            s.task_resreq[:, t] = v
+            s.task_res_present[t] = present
+            init = v.copy()
+            for rl in p.init_requests:          # api.GetPodResourceRequest (api/pod_info.go:53-73)
+                iv, _ = self._resource(rl, dims)
+                init = np.maximum(init, iv)
+            s.task_initreq[:, t] = init
+            c, m = pod_nz(p)
+            s.task_nz_cpu[t], s.task_nz_mem[t] = c, m
+            for k, val in p.node_selector.items():
+                setbit(s.task_sel_req, t, atom_of(k, "In", [val]))
+            terms = p.affinity_terms
+            if terms is not None:
+                assert 0 < len(terms) <= abi.KB_MAX_AFF_TERMS, "collapse the selector into one atom (DESIGN.md)"
+                s.task_n_aff_terms[t] = len(terms)
+                for ti, term in enumerate(terms):
+                    for (k, op, vals) in term:
+                        a = atom_of(k, op, vals)
+                        s.task_aff_terms[ti, a // 64, t] |= np.uint64(1) << np.uint64(a % 64)
+            for taint, a in taint_atoms.items():
+                if any(_tolerates(tol, taint) for tol in p.tolerations):
+                    setbit(s.task_tol, t, a)
+            for hp in p.host_ports:
+                if hp[2] <= 0:
+                    continue
+                sp = _sanitize_port(*hp)
+                setbit(s.task_port_own, t, port_atoms[sp])
+                for other, a in port_atoms.items():
+                    if _ports_conflict(sp, other):
+                        setbit(s.task_port_conflict, t, a)
+            fl = 0
+            if not p.requests and not p.limits:
+                fl |= abi.KB_TASK_BEST_EFFORT_QOS
+            s.task_flags[t] = fl
+            s.task_prio[t] = 1 if p.priority is None else p.priority    # api.NewTaskInfo (job_info.go:82-90)
+            s.task_ctime[t] = p.creation
+            s.task_uid_rank[t] = uid_rank[p.uid or f"{p.namespace}-{p.name}"]
+        s.job_task_off[:] = np.cumsum(counts).astype(np.uint32)
+        s.meta = {"nodes": [n.name for n in nodes], "tasks": [f"{p.namespace}/{p.name}" for p in pending],
+                  "jobs": list(jidx.keys()), "queues": [q.name for q in queues], "dims": dims}
+        s.validate()
+        return s

@@ -1,0 +1,91 @@
+/*
+ * kb_oracle.h — C API of the CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * The oracle is a C++17 restatement of kube-batch's allocate hot path
+ * (pkg/scheduler/actions/allocate/allocate.go:43-194 and everything it calls).  The reference
+ * is pure Go and there is no Go toolchain in this image, so the reference itself cannot be
+ * compiled or run here; this restatement is pinned against the reference's own golden
+ * vectors (tests/test_oracle_golden.py: allocate_test.go cases, resource_info_test.go,
+ * node_info_test.go known answers) — everything those tests do not pin (heap behaviour with
+ * stale keys, the rand tie-break, plugin arithmetic) is "parity unpinned" by the reference
+ * and defined by the deterministic rules of SURVEY.md §8c.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  libkbgpu.so never links or calls it.
+ */
+#ifndef KB_ORACLE_H_
+#define KB_ORACLE_H_
+
+#include "../include/kbgpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* mode: how the per-(task,node) work is organised (decisions are identical in both). */
+#define KBO_MODE_OPTIMISED 0 /* "mode B": cached node aggregates                                         */
+#define KBO_MODE_FAITHFUL  1 /* "mode A": reproduces the reference's cost pattern — rebuild the k8s
+                                NodeInfo aggregate from the node's pod list per pair
+                                (plugins/predicates/predicates.go:124, util/scheduler_helper.go:219-230)
+                                and scan every allocated task of every job for the anti-affinity
+                                check (plugins/util/util.go:62-85), deep-copying session-placed pods */
+
+typedef struct kbo_opts {
+  int32_t mode;          /* KBO_MODE_*                                                            */
+  int32_t threads;       /* workers of the PredicateNodes / PrioritizeNodes sweeps; the reference
+                            uses 16 (util/scheduler_helper.go:84,137); <=1 = serial                */
+  int64_t max_tasks;     /* >0: stop after this many tasks were popped (bounded timing sample)    */
+  double  max_seconds;   /* >0: stop once this much wall time has elapsed (bounded timing sample)  */
+} kbo_opts;
+
+typedef struct kbo_result {
+  uint64_t pairs_logical;    /* sum over processed tasks of N                                      */
+  uint32_t tasks_processed;
+  uint32_t tasks_allocated;
+  uint32_t tasks_pipelined;
+  uint32_t jobs_ready;
+  uint32_t visits;
+  uint32_t truncated;        /* 1 if max_tasks / max_seconds stopped the cycle early               */
+  double   seconds;          /* wall time of Execute                                               */
+} kbo_result;
+
+/* allocateAction.Execute on the flattened snapshot.  out: T decisions.  Optional final state outputs
+ * (any may be NULL): node_idle/releasing/used [R][N], node_pods [N], node_nz_cpu/mem [N],
+ * node_ports [W][N], job_share [J], job_ready [J], queue_share [Q], queue_deserved/allocated [R][Q]. */
+int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_opts* opts,
+                 kb_decision* out, kbo_result* res,
+                 double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                 int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                 double* job_share, int32_t* job_ready, double* queue_share,
+                 double* queue_deserved, double* queue_allocated);
+
+/* predicateFn + PrioritizeNodes of one task against the snapshot's initial node state. */
+int kbo_predicate_score(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t task,
+                        uint8_t* fit /*[N]*/, double* score /*[N]*/);
+
+/* ---- unit-level entry points used to pin the restatement against the reference's golden vectors ---- */
+/* api.Resource algebra (api/resource_info.go).  v[R] dense, present = scalar-map key mask (0 <=> nil map). */
+int  kbo_res_less_equal(uint32_t R, const double* l, uint32_t lp, const double* r, uint32_t rp);
+int  kbo_res_less(uint32_t R, const double* l, uint32_t lp, const double* r, uint32_t rp);
+int  kbo_res_is_empty(uint32_t R, const double* l, uint32_t lp);
+/* returns 0 ok, -1 if the reference would panic (Sub on insufficient resource, resource_info.go:158) */
+int  kbo_res_sub(uint32_t R, double* l, uint32_t* lp, const double* r, uint32_t rp);
+void kbo_res_add(uint32_t R, double* l, uint32_t* lp, const double* r, uint32_t rp);
+void kbo_res_set_max(uint32_t R, double* l, uint32_t* lp, const double* r, uint32_t rp);
+void kbo_res_fit_delta(uint32_t R, double* l, uint32_t* lp, const double* r, uint32_t rp);
+/* vendored k8s priorities */
+int64_t kbo_least_requested(int64_t req_cpu, int64_t alloc_cpu, int64_t req_mem, int64_t alloc_mem);
+int64_t kbo_most_requested(int64_t req_cpu, int64_t alloc_cpu, int64_t req_mem, int64_t alloc_mem);
+int64_t kbo_balanced(int64_t req_cpu, int64_t alloc_cpu, int64_t req_mem, int64_t alloc_mem);
+/* container/heap restated (util/priority_queue.go over Go's container/heap): pushes keys[0..n) in order
+ * with `less` = integer <, then pops all into out. */
+void kbo_heap_sort(const int64_t* keys, uint32_t n, int64_t* out);
+/* helpers.Share (api/helpers/helpers.go:47-60) */
+double kbo_share(double l, double r);
+
+const char* kbo_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

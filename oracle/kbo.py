@@ -1,0 +1,187 @@
+"""ctypes binding of the CPU oracle (oracle/libkboracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Importable from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs;
+the product package (kube_batch_b200) never imports this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from kube_batch_b200 import abi
+from kube_batch_b200.snapshot import PluginConf, Snapshot
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libkboracle.so")
+
+KBO_MODE_OPTIMISED = 0
+KBO_MODE_FAITHFUL = 1
+
+
+class kbo_opts(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("threads", C.c_int32), ("max_tasks", C.c_int64), ("max_seconds", C.c_double)]
+
+
+class kbo_result(C.Structure):
+    _fields_ = [
+        ("pairs_logical", C.c_uint64), ("tasks_processed", C.c_uint32), ("tasks_allocated", C.c_uint32),
+        ("tasks_pipelined", C.c_uint32), ("jobs_ready", C.c_uint32), ("visits", C.c_uint32),
+        ("truncated", C.c_uint32), ("seconds", C.c_double),
+    ]
+
+
+def build(force: bool = False) -> str:
+    src = os.path.join(_HERE, "kb_oracle.cpp")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "kb_oracle.h")),
+            os.path.getmtime(os.path.join(_HERE, "..", "include", "kbgpu.h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        L.kbo_last_error.restype = C.c_char_p
+        L.kbo_share.restype = C.c_double
+        L.kbo_share.argtypes = [C.c_double, C.c_double]
+        for f in ("kbo_least_requested", "kbo_most_requested", "kbo_balanced"):
+            getattr(L, f).restype = C.c_int64
+            getattr(L, f).argtypes = [C.c_int64] * 4
+        _lib = L
+    return _lib
+
+
+@dataclass
+class OracleOut:
+    decisions: np.ndarray      # structured, abi.DECISION_DTYPE
+    result: kbo_result
+    node_idle: np.ndarray
+    node_releasing: np.ndarray
+    node_used: np.ndarray
+    node_pods: np.ndarray
+    node_nz_cpu: np.ndarray
+    node_nz_mem: np.ndarray
+    node_ports: np.ndarray
+    job_share: np.ndarray
+    job_ready: np.ndarray
+    queue_share: np.ndarray
+    queue_deserved: np.ndarray
+    queue_allocated: np.ndarray
+
+    def bind_map(self):
+        """FakeBinder.Binds (util/test_utils.go:95-112): task -> node for dispatched tasks."""
+        d = self.decisions
+        return {int(t): int(d["node"][t]) for t in np.nonzero(d["dispatched"])[0]}
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def allocate(snap: Snapshot, conf: PluginConf, mode: int = KBO_MODE_OPTIMISED, threads: int = 1,
+             max_tasks: int = 0, max_seconds: float = 0.0) -> OracleOut:
+    L = lib()
+    cs, keep1 = snap.to_c()
+    cc, keep2 = conf.to_c()
+    o = kbo_opts(mode, threads, max_tasks, max_seconds)
+    R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
+    dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+    res = kbo_result()
+    out = OracleOut(
+        decisions=dec, result=res,
+        node_idle=np.zeros((R, N)), node_releasing=np.zeros((R, N)), node_used=np.zeros((R, N)),
+        node_pods=np.zeros(N, dtype=np.int32), node_nz_cpu=np.zeros(N, dtype=np.int64),
+        node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
+        job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
+        queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
+    rc = L.kbo_allocate(C.byref(cs), C.byref(cc), C.byref(o), dec.ctypes.data_as(C.c_void_p), C.byref(res),
+                        _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
+                        _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
+                        _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
+                        _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double),
+                        _p(out.queue_allocated, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"kbo_allocate rc={rc}: {L.kbo_last_error().decode()}")
+    out.decisions = dec[:T]
+    return out
+
+
+def predicate_score(snap: Snapshot, conf: PluginConf, task: int):
+    L = lib()
+    cs, keep1 = snap.to_c()
+    cc, keep2 = conf.to_c()
+    fit = np.zeros(snap.N, dtype=np.uint8)
+    score = np.zeros(snap.N, dtype=np.float64)
+    rc = L.kbo_predicate_score(C.byref(cs), C.byref(cc), C.c_uint32(task), _p(fit, C.c_uint8), _p(score, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"kbo_predicate_score rc={rc}: {L.kbo_last_error().decode()}")
+    return fit, score
+
+
+# ---- unit-level helpers (golden-vector tests) ----
+def _res(v, R):
+    a = np.zeros(R, dtype=np.float64)
+    a[: len(v)] = v
+    return a
+
+
+def res_less_equal(l, lp, r, rp, R=3) -> bool:
+    a, b = _res(l, R), _res(r, R)
+    return bool(lib().kbo_res_less_equal(R, _p(a, C.c_double), C.c_uint32(lp), _p(b, C.c_double), C.c_uint32(rp)))
+
+
+def res_less(l, lp, r, rp, R=3) -> bool:
+    a, b = _res(l, R), _res(r, R)
+    return bool(lib().kbo_res_less(R, _p(a, C.c_double), C.c_uint32(lp), _p(b, C.c_double), C.c_uint32(rp)))
+
+
+def res_is_empty(l, lp, R=3) -> bool:
+    a = _res(l, R)
+    return bool(lib().kbo_res_is_empty(R, _p(a, C.c_double), C.c_uint32(lp)))
+
+
+def _binop(fn, l, lp, r, rp, R):
+    a, b = _res(l, R), _res(r, R)
+    p = C.c_uint32(lp)
+    rc = fn(R, _p(a, C.c_double), C.byref(p), _p(b, C.c_double), C.c_uint32(rp))
+    return a, p.value, rc
+
+
+def res_add(l, lp, r, rp, R=3):
+    a, p, _ = _binop(lib().kbo_res_add, l, lp, r, rp, R)
+    return a, p
+
+
+def res_sub(l, lp, r, rp, R=3):
+    a, p, rc = _binop(lib().kbo_res_sub, l, lp, r, rp, R)
+    if rc != 0:
+        raise ArithmeticError("Resource is not sufficient to do operation")
+    return a, p
+
+
+def res_set_max(l, lp, r, rp, R=3):
+    a, p, _ = _binop(lib().kbo_res_set_max, l, lp, r, rp, R)
+    return a, p
+
+
+def res_fit_delta(l, lp, r, rp, R=3):
+    a, p, _ = _binop(lib().kbo_res_fit_delta, l, lp, r, rp, R)
+    return a, p
+
+
+def heap_sort(keys):
+    k = np.asarray(keys, dtype=np.int64)
+    out = np.zeros_like(k)
+    lib().kbo_heap_sort(_p(k, C.c_int64), C.c_uint32(len(k)), _p(out, C.c_int64))
+    return out
