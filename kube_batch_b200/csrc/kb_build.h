@@ -1,0 +1,494 @@
+// kb_build.h — CUDA-free host-side construction of a session from the C-ABI snapshot:
+// plugin resolution by name, task equivalence classes, TaskOrderFn order, TMA node tiles, drf /
+// proportion OnSessionOpen precomputation, per-queue job lists, the queue heap and the first visit.
+// Used by kb_engine.cu (which uploads the two slabs) and by tests/emu (which runs them on the CPU).
+#ifndef KB_BUILD_H_
+#define KB_BUILD_H_
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kb_ctl.h"
+
+namespace kb {
+
+struct Slab {                       // bump allocator over one byte buffer; offsets are 256-byte aligned
+  std::vector<unsigned char> host;
+  size_t alloc(size_t bytes) {
+    size_t off = (host.size() + 255) & ~(size_t)255;
+    host.resize(off + bytes, 0);
+    return off;
+  }
+};
+
+struct HostRes { double v[KB_MAX_R]; uint32_t present; HostRes() : present(0) { for (double& x : v) x = 0; } };
+
+struct BuildErr { int code = 0; std::string msg; };
+inline int bfail(BuildErr* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  e->code = code; e->msg = buf;
+  return code;
+}
+
+inline bool parse_int(const char* s, int* out) {
+  if (!s || !*s) return false;
+  char* end = nullptr;
+  long v = strtol(s, &end, 10);
+  if (end == s || *end != '\0') return false;     // strconv.Atoi error: keep the default (arguments.go:36-43)
+  *out = (int)v; return true;
+}
+inline bool parse_bool(const char* s, bool* out) {          // strconv.ParseBool (arguments.go:56-63)
+  if (!s) return false;
+  static const char* T[] = {"1", "t", "T", "TRUE", "true", "True"};
+  static const char* F[] = {"0", "f", "F", "FALSE", "false", "False"};
+  for (auto x : T) if (!strcmp(s, x)) { *out = true; return true; }
+  for (auto x : F) if (!strcmp(s, x)) { *out = false; return true; }
+  return false;
+}
+
+struct HostConf {
+  EvalConf cf{};
+  uint32_t jobcmp[4] = {0, 0, 0, 0};
+  bool task_order_priority = false, queue_order_proportion = false, proportion_present = false, drf_present = false,
+       gang_ready = false;
+};
+
+// plugins/factory.go:31-42 by name; OnSessionOpen registrations resolved in tier order (session_plugins.go)
+inline int resolve_conf(BuildErr* e, const kb_plugin_conf* conf, uint32_t R, uint32_t W, HostConf& hc) {
+  hc.cf.R = R; hc.cf.W = W;
+  int w_least = 1, w_most = 0, w_nodeaff = 1, w_podaff = 1, w_bal = 1;      // nodeorder.go:111-117
+  bool memp = false, diskp = false, pidp = false;                            // predicates.go:88-92
+  bool have[7] = {false};
+  enum { P_PRIORITY, P_GANG, P_DRF, P_PREDICATES, P_PROPORTION, P_NODEORDER, P_CONFORMANCE };
+  static const char* names[] = {"priority", "gang", "drf", "predicates", "proportion", "nodeorder", "conformance"};
+  auto id_of = [&](const char* n) { for (int i = 0; i < 7; ++i) if (n && !strcmp(n, names[i])) return i; return -1; };
+  if (conf) {
+    // pass 1: which plugins exist (every configured plugin's OnSessionOpen runs), arguments of the last occurrence win
+    for (uint32_t t = 0; t < conf->n_tiers; ++t)
+      for (uint32_t p = 0; p < conf->tiers[t].n_plugins; ++p) {
+        const kb_plugin_option& o = conf->tiers[t].plugins[p];
+        int id = id_of(o.name);
+        if (id < 0) return bfail(e, KB_E_UNSUPPORTED_PLUGIN, "plugin '%s' is not a built-in: the GPU path honours built-in plugins by name only", o.name ? o.name : "(null)");
+        have[id] = true;
+        if (id == P_NODEORDER) { w_least = 1; w_most = 0; w_nodeaff = 1; w_podaff = 1; w_bal = 1; }
+        if (id == P_PREDICATES) { memp = diskp = pidp = false; }
+        for (uint32_t a = 0; a < o.n_args; ++a) {
+          const char* k = o.arg_keys[a]; const char* v = o.arg_values[a];
+          if (!k) continue;
+          if (id == P_NODEORDER) {
+            if (!strcmp(k, "leastrequested.weight")) parse_int(v, &w_least);
+            else if (!strcmp(k, "mostrequested.weight")) parse_int(v, &w_most);
+            else if (!strcmp(k, "nodeaffinity.weight")) parse_int(v, &w_nodeaff);
+            else if (!strcmp(k, "podaffinity.weight")) parse_int(v, &w_podaff);
+            else if (!strcmp(k, "balancedresource.weight")) parse_int(v, &w_bal);
+          } else if (id == P_PREDICATES) {
+            if (!strcmp(k, "predicate.MemoryPressureEnable")) parse_bool(v, &memp);
+            else if (!strcmp(k, "predicate.DiskPressureEnable")) parse_bool(v, &diskp);
+            else if (!strcmp(k, "predicate.PIDPressureEnable")) parse_bool(v, &pidp);
+          }
+        }
+      }
+    // pass 2: dispatch chains in tier / plugin order
+    int nj = 0;
+    auto in_chain = [&](uint32_t c) { for (int i = 0; i < nj; ++i) if (hc.jobcmp[i] == c) return true; return false; };
+    for (uint32_t t = 0; t < conf->n_tiers; ++t)
+      for (uint32_t p = 0; p < conf->tiers[t].n_plugins; ++p) {
+        const kb_plugin_option& o = conf->tiers[t].plugins[p];
+        int id = id_of(o.name);
+        if (o.enabled_job_order) {
+          uint32_t c = id == P_PRIORITY ? JOBCMP_PRIORITY : id == P_GANG ? JOBCMP_GANG : id == P_DRF ? JOBCMP_DRF : JOBCMP_NONE;
+          if (c != JOBCMP_NONE && !in_chain(c) && nj < 3) hc.jobcmp[nj++] = c;
+        }
+        if (o.enabled_task_order && id == P_PRIORITY) hc.task_order_priority = true;
+        if (o.enabled_queue_order && id == P_PROPORTION) hc.queue_order_proportion = true;
+        if (o.enabled_job_ready && id == P_GANG) hc.gang_ready = true;
+        if (o.enabled_predicate && id == P_PREDICATES) hc.cf.predicates = 1;
+        if (o.enabled_node_order && id == P_NODEORDER) hc.cf.nodeorder = 1;
+      }
+  }
+  hc.proportion_present = have[P_PROPORTION];     // Overused ignores Enabled* (session_plugins.go:165-179)
+  hc.drf_present = have[P_DRF];
+  hc.cf.mem_pressure = memp; hc.cf.disk_pressure = diskp; hc.cf.pid_pressure = pidp;
+  hc.cf.w_least = w_least; hc.cf.w_most = w_most; hc.cf.w_balanced = w_bal;
+  (void)w_nodeaff; (void)w_podaff;    // their Map/Function results are identically 0 without preferred terms
+  const long lim = 1 << 20;
+  if (labs(w_least) > lim || labs(w_most) > lim || labs(w_bal) > lim) return bfail(e, KB_E_BADARG, "nodeorder weight out of range");
+  hc.cf.score_bias = 10ll * ((w_least < 0 ? -w_least : 0) + (w_most < 0 ? -w_most : 0) + (w_bal < 0 ? -w_bal : 0));
+  return KB_OK;
+}
+
+// ---- host-side Resource algebra with scalar-map presence, for proportion's OnSessionOpen only ----
+inline void hr_add(uint32_t R, HostRes& r, const HostRes& rr) {            // resource_info.go:128-140
+  r.v[0] += rr.v[0]; r.v[1] += rr.v[1];
+  for (uint32_t k = 2; k < R; ++k) if ((rr.present >> k) & 1u) { r.present |= 1u << k; r.v[k] += rr.v[k]; }
+}
+inline bool hr_le(uint32_t R, const HostRes& l, const HostRes& r) {        // :268-302
+  return res_less_equal(R, [&](uint32_t k) { return ((k < 2) || ((l.present >> k) & 1u)) ? l.v[k] : 0.0; },
+                        [&](uint32_t k) { return ((k < 2) || ((r.present >> k) & 1u)) ? r.v[k] : 0.0; });
+}
+inline bool hr_less(uint32_t R, const HostRes& r, const HostRes& rr) {     // :227-265
+  if (!(r.v[0] < rr.v[0])) return false;
+  if (!(r.v[1] < rr.v[1])) return false;
+  if (r.present == 0) {
+    if (rr.present != 0)
+      for (uint32_t k = 2; k < R; ++k) if (((rr.present >> k) & 1u) && rr.v[k] <= KB_MIN_MILLI_SCALAR) return false;
+    return true;
+  }
+  if (rr.present == 0) return false;
+  for (uint32_t k = 2; k < R; ++k) {
+    if (!((r.present >> k) & 1u)) continue;
+    double q = ((rr.present >> k) & 1u) ? rr.v[k] : 0.0;
+    if (!(r.v[k] < q)) return false;
+  }
+  return true;
+}
+inline HostRes hr_min(uint32_t R, const HostRes& l, const HostRes& r) {    // helpers.go:28-44
+  HostRes res;
+  res.v[0] = std::fmin(l.v[0], r.v[0]); res.v[1] = std::fmin(l.v[1], r.v[1]);
+  if (l.present == 0 || r.present == 0) return res;
+  for (uint32_t k = 2; k < R; ++k) if ((l.present >> k) & 1u) {
+    res.present |= 1u << k;
+    res.v[k] = std::fmin(l.v[k], ((r.present >> k) & 1u) ? r.v[k] : 0.0);
+  }
+  return res;
+}
+inline void hr_diff(uint32_t R, const HostRes& r, const HostRes& rr, HostRes& inc, HostRes& dec) {   // :305-337
+  inc = HostRes(); dec = HostRes();
+  for (uint32_t k = 0; k < 2; ++k) { if (r.v[k] > rr.v[k]) inc.v[k] += r.v[k] - rr.v[k]; else dec.v[k] += rr.v[k] - r.v[k]; }
+  for (uint32_t k = 2; k < R; ++k) {
+    if (!((r.present >> k) & 1u)) continue;
+    double q = ((rr.present >> k) & 1u) ? rr.v[k] : 0.0;
+    if (r.v[k] > q) { inc.present |= 1u << k; inc.v[k] += r.v[k] - q; }
+    else { dec.present |= 1u << k; dec.v[k] += q - r.v[k]; }
+  }
+}
+inline bool hr_sub(uint32_t R, HostRes& r, const HostRes& rr) {            // :143-160, false where the reference panics
+  if (!hr_le(R, rr, r)) return false;
+  r.v[0] -= rr.v[0]; r.v[1] -= rr.v[1];
+  for (uint32_t k = 2; k < R; ++k) {
+    if (!((rr.present >> k) & 1u)) continue;
+    if (r.present == 0) return true;
+    r.present |= 1u << k; r.v[k] -= rr.v[k];
+  }
+  return true;
+}
+inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :93-105
+  if (!(r.v[0] < KB_MIN_MILLI_CPU && r.v[1] < KB_MIN_MEMORY)) return false;
+  for (uint32_t k = 2; k < R; ++k) if (((r.present >> k) & 1u) && r.v[k] >= KB_MIN_MILLI_SCALAR) return false;
+  return true;
+}
+
+
+
+struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl; };
+struct OffImm { size_t classes, ord_task, ord_class, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
+
+struct BuiltSession {
+  Slab mut, imm;
+  OffMut om{};
+  OffImm oi{};
+  HostConf hc;
+  uint32_t R = 0, W = 0, N = 0, T = 0, J = 0, Q = 0, C = 0, NT = 0, ncols = 0, To = 0, grid = 1;
+  uint32_t total_dims_mask = 3;
+  double total[KB_MAX_R] = {0};
+  std::vector<int32_t> job_min_avail;
+
+  void bind(DevSession& D, unsigned char* mb, unsigned char* ib) const {
+    D.cf = hc.cf;
+    D.N = N; D.T = T; D.J = J; D.Q = Q; D.C = C; D.NT = NT; D.ncols = ncols; D.To = To;
+    D.gang_ready = hc.gang_ready ? 1 : 0;
+    for (int i = 0; i < 4; ++i) D.jobcmp[i] = hc.jobcmp[i];
+    D.queue_order_proportion = hc.queue_order_proportion; D.proportion_present = hc.proportion_present; D.drf_present = hc.drf_present;
+    D.total_dims_mask = total_dims_mask;
+    for (uint32_t r = 0; r < KB_MAX_R; ++r) D.total[r] = total[r];
+    D.tiles = (uint64_t*)(mb + om.tiles); D.node_used = (double*)(mb + om.used);
+    D.job_pos = (uint32_t*)(mb + om.job_pos); D.job_ready = (int32_t*)(mb + om.job_ready);
+    D.job_alloc = (double*)(mb + om.job_alloc); D.job_share = (double*)(mb + om.job_share);
+    D.job_placed = (uint32_t*)(mb + om.job_placed); D.q_static_head = (uint32_t*)(mb + om.q_head);
+    D.dyn_jobs = (uint32_t*)(mb + om.dyn); D.q_allocated = (double*)(mb + om.q_alloc); D.q_share = (double*)(mb + om.q_share);
+    D.qheap = (uint32_t*)(mb + om.qheap); D.dec = (kb_decision*)(mb + om.dec); D.cand = (uint64_t*)(mb + om.cand);
+    D.ctl = (Ctl*)(mb + om.ctl);
+    D.classes = (ClassRec*)(ib + oi.classes); D.ord_task = (uint32_t*)(ib + oi.ord_task); D.ord_class = (uint32_t*)(ib + oi.ord_class);
+    D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
+    D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
+    D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
+    D.q_deserved = (double*)(ib + oi.q_des); D.q_deserved_present = (uint32_t*)(ib + oi.q_des_p); D.q_ctime = (int64_t*)(ib + oi.q_ctime);
+  }
+};
+
+// Everything kb_session_load does before touching the device.  `max_grid` = scan CTAs (SM count).
+inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e) {
+  if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
+  if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
+  if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
+  if (s->Q > KB_MAX_Q) return bfail(e, KB_E_BADARG, "Q=%u > KB_MAX_Q", s->Q);
+  if (s->N >= 0xFFFFFFF0u) return bfail(e, KB_E_BADARG, "N too large for the packed key");
+  const uint32_t R = s->R, W = s->W, N = s->N, T = s->T, J = s->J, Q = s->Q;
+  HostConf& hc = B.hc;
+  int rc = resolve_conf(e, conf, R, W, hc);
+  if (rc) return rc;
+
+  // ---------------- validate + task classes ----------------
+  for (uint32_t j = 0; j < J; ++j) {
+    if (s->job_task_off[j] > s->job_task_off[j + 1] || s->job_task_off[j + 1] > T) return bfail(e, KB_E_BADARG, "job_task_off is not monotone at job %u", j);
+    if (s->job_queue[j] >= Q) return bfail(e, KB_E_BADARG, "job %u: queue %u does not exist (cache.Snapshot drops such jobs, cache.go:652-656)", j, s->job_queue[j]);
+  }
+  if (J && (s->job_task_off[0] != 0 || s->job_task_off[J] != T)) return bfail(e, KB_E_BADARG, "job_task_off must cover [0,T)");
+  std::vector<ClassRec> classes;
+  std::vector<uint32_t> task_class(T, 0);
+  std::vector<uint8_t> task_empty(T, 0);
+  {
+    std::unordered_map<std::string, uint32_t> dedup;
+    for (uint32_t t = 0; t < T; ++t) {
+      if (s->task_flags[t] & (KB_TASK_HAS_POD_AFFINITY | KB_TASK_HAS_PREFERRED_NODE_AFFINITY))
+        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod / preferred node affinity terms: outside this build (no CPU fallback)", t);
+      if (s->task_n_aff_terms[t] > KB_MAX_AFF_TERMS) return bfail(e, KB_E_BADARG, "task %u: n_aff_terms > KB_MAX_AFF_TERMS", t);
+      ClassRec c;
+      memset(&c, 0, sizeof c);
+      for (uint32_t r = 0; r < R; ++r) {
+        c.initreq[r] = s->task_initreq[(size_t)r * T + t];
+        c.resreq[r] = s->task_resreq[(size_t)r * T + t];
+        if (c.resreq[r] > c.initreq[r]) return bfail(e, KB_E_BADARG, "task %u: resreq > initreq in dim %u (violates api/pod_info.go:53-73)", t, r);
+      }
+      c.nz_cpu = s->task_nz_cpu[t]; c.nz_mem = s->task_nz_mem[t];
+      c.n_aff = s->task_n_aff_terms[t];
+      c.flags = s->task_flags[t] & KB_TASK_BEST_EFFORT_QOS;
+      for (uint32_t w = 0; w < W; ++w) {
+        c.sel_req[w] = s->task_sel_req[(size_t)w * T + t];
+        c.tol[w] = s->task_tol[(size_t)w * T + t];
+        c.port_own[w] = s->task_port_own[(size_t)w * T + t];
+        c.port_conflict[w] = s->task_port_conflict[(size_t)w * T + t];
+        for (uint32_t a = 0; a < c.n_aff; ++a) c.aff[a][w] = s->task_aff_terms[((size_t)a * W + w) * T + t];
+      }
+      task_empty[t] = res_is_empty(R, [&](uint32_t k) { return c.resreq[k]; }) ? 1 : 0;   // allocate.go:113-118
+      std::string key(reinterpret_cast<const char*>(&c), sizeof c);
+      auto it = dedup.find(key);
+      if (it == dedup.end()) { it = dedup.emplace(std::move(key), (uint32_t)classes.size()).first; classes.push_back(c); }
+      task_class[t] = it->second;
+    }
+  }
+  if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); }
+  const uint32_t C = (uint32_t)classes.size();
+
+  // ---------------- per-job TaskOrderFn order (session_plugins.go:318-331, priority.go:40-56) ----------------
+  std::vector<uint32_t> ord_task, ord_class, job_ord_off(J + 1, 0);
+  ord_task.reserve(T);
+  for (uint32_t j = 0; j < J; ++j) {
+    job_ord_off[j] = (uint32_t)ord_task.size();
+    size_t b = ord_task.size();
+    for (uint32_t t = s->job_task_off[j]; t < s->job_task_off[j + 1]; ++t) if (!task_empty[t]) ord_task.push_back(t);
+    std::sort(ord_task.begin() + b, ord_task.end(), [&](uint32_t l, uint32_t r) {
+      if (hc.task_order_priority && s->task_prio[l] != s->task_prio[r]) return s->task_prio[l] > s->task_prio[r];
+      if (s->task_ctime[l] != s->task_ctime[r]) return s->task_ctime[l] < s->task_ctime[r];
+      return s->task_uid_rank[l] < s->task_uid_rank[r];
+    });
+  }
+  job_ord_off[J] = (uint32_t)ord_task.size();
+  const uint32_t To = (uint32_t)ord_task.size();
+  ord_class.resize(To);
+  for (uint32_t i = 0; i < To; ++i) ord_class[i] = task_class[ord_task[i]];
+
+  // ---------------- slabs ----------------
+  const uint32_t NT = (N + TILE_NODES - 1) / TILE_NODES;
+  const uint32_t ncols = tile_ncols(R, W);
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  Slab& mut = B.mut; Slab& imm = B.imm;
+  mut.host.clear(); imm.host.clear();
+  DevSession H{};            // host view: pointers into the slabs' host buffers
+  OffMut& om = B.om; OffImm& oi = B.oi;
+  const uint32_t GMAX = std::max(1u, max_grid);
+  const uint32_t grid = std::max(1u, std::min(NT, GMAX));
+  om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
+  om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
+  om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
+  om.job_ready = mut.alloc((size_t)std::max(1u, J) * 4);
+  om.job_alloc = mut.alloc((size_t)R * std::max(1u, J) * 8);
+  om.job_share = mut.alloc((size_t)std::max(1u, J) * 8);
+  om.job_placed = mut.alloc((size_t)std::max(1u, J) * 4);
+  om.q_head = mut.alloc((size_t)std::max(1u, Q) * 4);
+  om.dyn = mut.alloc((size_t)std::max(1u, J) * 4);
+  om.q_alloc = mut.alloc((size_t)R * std::max(1u, Q) * 8);
+  om.q_share = mut.alloc((size_t)std::max(1u, Q) * 8);
+  om.qheap = mut.alloc((size_t)std::max(1u, J) * 4);
+  om.dec = mut.alloc((size_t)std::max(1u, T) * sizeof(kb_decision));
+  om.cand = mut.alloc((size_t)grid * KTOP * 8);
+  om.ctl = mut.alloc(sizeof(Ctl));
+  oi.classes = imm.alloc((size_t)C * sizeof(ClassRec));
+  oi.ord_task = imm.alloc((size_t)std::max(1u, To) * 4);
+  oi.ord_class = imm.alloc((size_t)std::max(1u, To) * 4);
+  oi.job_ord_off = imm.alloc((size_t)(J + 1) * 4);
+  oi.job_min = imm.alloc((size_t)std::max(1u, J) * 4);
+  oi.job_queue = imm.alloc((size_t)std::max(1u, J) * 4);
+  oi.job_prio = imm.alloc((size_t)std::max(1u, J) * 4);
+  oi.job_tb = imm.alloc((size_t)std::max(1u, J) * 4);
+  oi.q_static = imm.alloc((size_t)std::max(1u, J) * 4);
+  oi.q_static_off = imm.alloc((size_t)(Q + 1) * 4);
+  oi.q_des = imm.alloc((size_t)R * std::max(1u, Q) * 8);
+  oi.q_des_p = imm.alloc((size_t)std::max(1u, Q) * 4);
+  oi.q_ctime = imm.alloc((size_t)std::max(1u, Q) * 8);
+  oi.task_class = imm.alloc((size_t)std::max(1u, T) * 4);
+  oi.job_ready0 = imm.alloc((size_t)std::max(1u, J) * 4);
+  mut.host.resize((mut.host.size() + 255) & ~(size_t)255);
+  imm.host.resize((imm.host.size() + 255) & ~(size_t)255);
+
+  B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To;
+  B.bind(H, mut.host.data(), imm.host.data());
+
+  // ---------------- node tiles ----------------
+  for (uint32_t t = 0; t < NT; ++t) {
+    uint64_t* tb = H.tiles + (size_t)t * tile_u64;
+    for (uint32_t i = 0; i < TILE_NODES; ++i) {
+      const uint32_t n = t * TILE_NODES + i;
+      auto put = [&](uint32_t c, uint64_t v) { tb[(size_t)c * TILE_NODES + i] = v; };
+      if (n < N) {
+        for (uint32_t r = 0; r < R; ++r) {
+          put(col_idle(R, r), double_as_u64(s->node_idle[(size_t)r * N + n]));
+          put(col_rel(R, r), double_as_u64(s->node_releasing[(size_t)r * N + n]));
+          H.node_used[(size_t)r * N + n] = s->node_used[(size_t)r * N + n];
+        }
+        put(col_alloc_cpu(R), (uint64_t)s->node_alloc_cpu[n]); put(col_alloc_mem(R), (uint64_t)s->node_alloc_mem[n]);
+        put(col_nz_cpu(R), (uint64_t)s->node_nz_cpu[n]); put(col_nz_mem(R), (uint64_t)s->node_nz_mem[n]);
+        put(col_pods(R), (uint64_t)(uint32_t)s->node_pods[n] | ((uint64_t)(uint32_t)s->node_max_pods[n] << 32));
+        put(col_flags(R), (uint64_t)s->node_flags[n]);
+        for (uint32_t w = 0; w < W; ++w) {
+          put(col_labels(R, W, w), s->node_labels[(size_t)w * N + n]);
+          put(col_taints(R, W, w), s->node_taints[(size_t)w * N + n]);
+          put(col_ports(R, W, w), s->node_ports[(size_t)w * N + n]);
+        }
+      } else {                                   // padding node: can never fit (kernels also test node < N)
+        for (uint32_t r = 0; r < R; ++r) { put(col_idle(R, r), double_as_u64(-1e300)); put(col_rel(R, r), double_as_u64(-1e300)); }
+        put(col_flags(R), (uint64_t)KB_NODE_UNSCHEDULABLE);
+      }
+    }
+  }
+
+  // ---------------- immutable job / queue / class tables ----------------
+  memcpy(H.classes, classes.data(), (size_t)C * sizeof(ClassRec));
+  if (To) { memcpy(H.ord_task, ord_task.data(), (size_t)To * 4); memcpy(H.ord_class, ord_class.data(), (size_t)To * 4); }
+  memcpy(H.job_ord_off, job_ord_off.data(), (size_t)(J + 1) * 4);
+  if (T) memcpy(imm.host.data() + oi.task_class, task_class.data(), (size_t)T * 4);
+  std::vector<uint32_t> tb_order(J);
+  for (uint32_t j = 0; j < J; ++j) tb_order[j] = j;
+  std::sort(tb_order.begin(), tb_order.end(), [&](uint32_t l, uint32_t r) {
+    if (s->job_ctime[l] != s->job_ctime[r]) return s->job_ctime[l] < s->job_ctime[r];
+    return l < r;
+  });
+  for (uint32_t i = 0; i < J; ++i) H.job_tb_rank[tb_order[i]] = i;
+  int32_t* h_ready0 = (int32_t*)(imm.host.data() + oi.job_ready0);
+  for (uint32_t j = 0; j < J; ++j) {
+    H.job_min_avail[j] = s->job_min_avail[j];
+    H.job_queue[j] = s->job_queue[j];
+    H.job_prio[j] = s->job_prio[j];
+    H.job_ready[j] = s->job_ready0[j];
+    h_ready0[j] = s->job_ready0[j];
+    H.job_pos[j] = job_ord_off[j];
+    for (uint32_t r = 0; r < R; ++r) H.job_alloc[(size_t)r * J + j] = s->job_alloc0[(size_t)r * J + j];
+  }
+  for (uint32_t q = 0; q < Q; ++q) H.q_ctime[q] = s->queue_ctime[q];
+
+  // drf OnSessionOpen (drf.go:60-83): total = sum of node Allocatable; share per job
+  H.total_dims_mask = 3u;
+  for (uint32_t r = 0; r < R; ++r) H.total[r] = 0;
+  for (uint32_t n = 0; n < N; ++n) {
+    H.total_dims_mask |= s->node_alloc_present[n] & ~3u;
+    for (uint32_t r = 0; r < R; ++r)
+      if (r < 2 || ((s->node_alloc_present[n] >> r) & 1u)) H.total[r] += s->node_allocatable[(size_t)r * N + n];
+  }
+  H.total_dims_mask &= (R >= 32 ? 0xFFFFFFFFu : ((1u << R) - 1u));
+  B.total_dims_mask = H.total_dims_mask;
+  for (uint32_t r = 0; r < KB_MAX_R; ++r) B.total[r] = H.total[r];
+  for (uint32_t j = 0; j < J; ++j) { if (hc.drf_present) update_job_share(H, j); else H.job_share[j] = 0.0; }
+
+  // proportion OnSessionOpen (proportion.go:58-154)
+  if (hc.proportion_present) {
+    struct Attr { bool used = false; int32_t weight = 0; HostRes deserved, allocated, request; };
+    std::vector<Attr> qa(Q);
+    HostRes total; total.present = H.total_dims_mask & ~3u;
+    for (uint32_t r = 0; r < R; ++r) total.v[r] = H.total[r];
+    for (uint32_t j = 0; j < J; ++j) {                                   // :67-98
+      Attr& a = qa[s->job_queue[j]];
+      if (!a.used) { a.used = true; a.weight = s->queue_weight[s->job_queue[j]]; }
+      HostRes al; al.present = s->job_alloc0_present[j] & ~3u;
+      for (uint32_t r = 0; r < R; ++r) al.v[r] = (r < 2 || ((al.present >> r) & 1u)) ? s->job_alloc0[(size_t)r * J + j] : 0.0;
+      hr_add(R, a.allocated, al); hr_add(R, a.request, al);
+      for (uint32_t t = s->job_task_off[j]; t < s->job_task_off[j + 1]; ++t) {
+        HostRes rq; rq.present = s->task_res_present[t] & ~3u;
+        for (uint32_t r = 0; r < R; ++r) rq.v[r] = (r < 2 || ((rq.present >> r) & 1u)) ? s->task_resreq[(size_t)r * T + t] : 0.0;
+        hr_add(R, a.request, rq);
+      }
+    }
+    HostRes remaining = total;                                           // :100
+    std::vector<uint8_t> meet(Q, 0);
+    for (;;) {
+      int32_t totalWeight = 0;
+      for (uint32_t q = 0; q < Q; ++q) if (qa[q].used && !meet[q]) totalWeight += qa[q].weight;
+      if (totalWeight == 0) break;
+      HostRes incD, decD;
+      for (uint32_t q = 0; q < Q; ++q) {
+        Attr& a = qa[q];
+        if (!a.used || meet[q]) continue;
+        HostRes old = a.deserved;
+        HostRes part = remaining;
+        const double ratio = (double)a.weight / (double)totalWeight;
+        part.v[0] = part.v[0] * ratio; part.v[1] = part.v[1] * ratio;
+        for (uint32_t k = 2; k < R; ++k) if ((part.present >> k) & 1u) part.v[k] = part.v[k] * ratio;
+        hr_add(R, a.deserved, part);
+        if (hr_less(R, a.request, a.deserved)) { a.deserved = hr_min(R, a.deserved, a.request); meet[q] = 1; }
+        HostRes inc, dec;
+        hr_diff(R, a.deserved, old, inc, dec);
+        hr_add(R, incD, inc); hr_add(R, decD, dec);
+      }
+      if (!hr_sub(R, remaining, incD)) return bfail(e, KB_E_STATE, "proportion: remaining.Sub would panic in the reference (resource_info.go:158)");
+      hr_add(R, remaining, decD);
+      if (hr_is_empty(R, remaining)) break;
+    }
+    for (uint32_t q = 0; q < Q; ++q) {
+      H.q_deserved_present[q] = qa[q].deserved.present;
+      for (uint32_t r = 0; r < R; ++r) {
+        H.q_deserved[(size_t)r * Q + q] = (r < 2 || ((qa[q].deserved.present >> r) & 1u)) ? qa[q].deserved.v[r] : 0.0;
+        H.q_allocated[(size_t)r * Q + q] = (r < 2 || ((qa[q].allocated.present >> r) & 1u)) ? qa[q].allocated.v[r] : 0.0;
+      }
+      update_queue_share(H, q);
+    }
+  }
+
+  // ---------------- job lists per queue, queue heap, first visit (allocate.go:47-65, 89-126) ----------------
+  {
+    std::vector<uint32_t> cnt(Q + 1, 0);
+    for (uint32_t j = 0; j < J; ++j) cnt[s->job_queue[j] + 1]++;
+    for (uint32_t q = 0; q < Q; ++q) cnt[q + 1] += cnt[q];
+    memcpy(H.q_static_off, cnt.data(), (size_t)(Q + 1) * 4);
+    std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+    for (uint32_t j = 0; j < J; ++j) H.q_static[fill[s->job_queue[j]]++] = j;
+    for (uint32_t q = 0; q < Q; ++q) {
+      std::sort(H.q_static + cnt[q], H.q_static + cnt[q + 1], [&](uint32_t l, uint32_t r) { return job_before(H, l, r); });
+      H.q_static_head[q] = cnt[q];
+    }
+  }
+  Ctl& c0 = *H.ctl;
+  memset(&c0, 0, sizeof c0);
+  c0.cur_job = -1;
+  for (uint32_t j = 0; j < J; ++j) qheap_push(H, c0, s->job_queue[j]);      // one push PER JOB (allocate.go:52)
+  for (uint32_t t = 0; t < T; ++t) {
+    kb_decision d; d.node = -1; d.kind = task_empty[t] ? KB_KIND_SKIPPED : KB_KIND_NONE; d.dispatched = 0; d.reserved = 0;
+    d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu;
+    H.dec[t] = d;
+  }
+  select_next_visit(H, c0);
+
+
+  B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.grid = grid;
+  B.job_min_avail.assign(s->job_min_avail, s->job_min_avail + J);
+  return KB_OK;
+}
+
+}  // namespace kb
+#endif  // KB_BUILD_H_

@@ -1,0 +1,203 @@
+// kb_core.h — host/device-shared core of the engine: the exact per-(task,node) arithmetic
+// (K1 predicate bitmask + K2 fused score -> packed key) and the small resource algebra the
+// commit path needs.  Everything here is `KB_HD` so the very same code is compiled by nvcc
+// into the kernels and by g++ into tests/emu (logic tests without a GPU).
+//
+// Semantics follow the reference (paths relative to /root/reference/pkg/scheduler):
+//   resource fit      actions/allocate/allocate.go:73-87 + api/resource_info.go:268-302 (LessEqual)
+//   predicates        plugins/predicates/predicates.go:123-265 + vendored predicates.go
+//   node scores       vendor/k8s.io/kubernetes/pkg/scheduler/algorithm/priorities/{least_requested,
+//                     most_requested,balanced_resource_allocation,resource_allocation}.go
+//   score sum         util/scheduler_helper.go:162-168
+//   best node         util/scheduler_helper.go:188-208 with the deterministic first-max rule
+//
+// FP64 fidelity: Go on amd64 never fuses a*b+c, so every product / quotient that feeds a
+// decision goes through KB_DMUL / KB_DDIV / KB_DSUB (round-to-nearest intrinsics on device,
+// plain operators compiled with -ffp-contract=off on host).
+#ifndef KB_CORE_H_
+#define KB_CORE_H_
+
+#include <stdint.h>
+#include "../../include/kbgpu.h"
+
+#if defined(__CUDACC__)
+#define KB_HD __host__ __device__ __forceinline__
+#else
+#define KB_HD inline
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define KB_DSUB(a, b) __dsub_rn((a), (b))
+#define KB_DMUL(a, b) __dmul_rn((a), (b))
+#define KB_DDIV(a, b) __ddiv_rn((a), (b))
+#define KB_DADD(a, b) __dadd_rn((a), (b))
+#define KB_FABS(a) fabs(a)
+#define KB_LL2D(a) __ll2double_rn(a)
+#define KB_D2LL(a) __double2ll_rz(a)
+#else
+#include <math.h>
+#define KB_DSUB(a, b) ((a) - (b))
+#define KB_DMUL(a, b) ((a) * (b))
+#define KB_DDIV(a, b) ((a) / (b))
+#define KB_DADD(a, b) ((a) + (b))
+#define KB_FABS(a) fabs(a)
+#define KB_LL2D(a) ((double)(a))
+#define KB_D2LL(a) ((long long)(a))
+#endif
+
+namespace kb {
+
+// api/resource_info.go:68-70
+#define KB_MIN_MILLI_CPU 10.0
+#define KB_MIN_MILLI_SCALAR 10.0
+#define KB_MIN_MEMORY (10.0 * 1024.0 * 1024.0)
+
+constexpr int KTOP = 32;          // candidates kept per class per scan (one warp-wide sorted list)
+constexpr int DMAX = 32;          // dirty nodes a replay epilogue can hold
+constexpr int TILE_NODES = 128;   // nodes per TMA tile (== threads per scan CTA)
+
+// Job-order comparators in tier/plugin order (framework/session_plugins.go:243-267)
+enum JobCmp : uint32_t { JOBCMP_NONE = 0, JOBCMP_PRIORITY = 1, JOBCMP_GANG = 2, JOBCMP_DRF = 3 };
+
+// Resolved plugin configuration: what OnSessionOpen of the built-in plugins registers, by name.
+struct EvalConf {
+  uint32_t R, W;
+  uint32_t predicates;        // predicates plugin registered && EnabledPredicate
+  uint32_t mem_pressure, disk_pressure, pid_pressure;   // predicates.go:33-40 arguments
+  uint32_t nodeorder;         // nodeorder plugin registered && EnabledNodeOrder
+  int32_t  w_least, w_most, w_balanced;                 // nodeorder.go:107-131 (node/pod-affinity terms are 0 here)
+  int64_t  score_bias;        // makes the weighted sum non-negative so it packs into the key
+};
+
+// One task equivalence class: every field of a pending task that predicateFn / the prioritizers /
+// AddTask read.  Tasks of a PodGroup are normally one class.
+struct ClassRec {
+  double   initreq[KB_MAX_R];
+  double   resreq[KB_MAX_R];
+  int64_t  nz_cpu, nz_mem;
+  uint64_t sel_req[KB_MAX_W];
+  uint64_t aff[KB_MAX_AFF_TERMS][KB_MAX_W];
+  uint64_t tol[KB_MAX_W];
+  uint64_t port_own[KB_MAX_W];
+  uint64_t port_conflict[KB_MAX_W];
+  uint32_t n_aff;
+  uint32_t flags;             // KB_TASK_BEST_EFFORT_QOS only
+};
+
+// api/resource_info.go:268-274
+KB_HD bool le_func(double l, double r, double diff) { return l < r || KB_FABS(KB_DSUB(l, r)) < diff; }
+
+// Resource.LessEqual(l, r) on dense vectors (api/resource_info.go:268-302).  A nil scalar map and a
+// map of zeros are indistinguishable here: a scalar of l is only compared when l_k > 10, and then
+// `rr == nil -> false` and `l_k < 0 || |l_k - 0| < 10` both yield false (DESIGN.md §dense resources).
+template <class LAcc, class RAcc>
+KB_HD bool res_less_equal(uint32_t R, LAcc l, RAcc r) {
+  if (!le_func(l(0), r(0), KB_MIN_MILLI_CPU)) return false;
+  if (!le_func(l(1), r(1), KB_MIN_MEMORY)) return false;
+  for (uint32_t k = 2; k < R; ++k) {
+    double lq = l(k);
+    if (lq <= KB_MIN_MILLI_SCALAR) continue;
+    if (!le_func(lq, r(k), KB_MIN_MILLI_SCALAR)) return false;
+  }
+  return true;
+}
+
+// api/resource_info.go:93-105
+template <class Acc>
+KB_HD bool res_is_empty(uint32_t R, Acc v) {
+  if (!(v(0) < KB_MIN_MILLI_CPU && v(1) < KB_MIN_MEMORY)) return false;
+  for (uint32_t k = 2; k < R; ++k)
+    if (v(k) >= KB_MIN_MILLI_SCALAR) return false;
+  return true;
+}
+
+// api/helpers/helpers.go:47-60
+KB_HD double share_of(double l, double r) {
+  if (r == 0) return l == 0 ? 0.0 : 1.0;
+  return KB_DDIV(l, r);
+}
+
+// least_requested.go:49-58
+KB_HD int64_t least_requested_score(int64_t requested, int64_t capacity) {
+  if (capacity == 0) return 0;
+  if (requested > capacity) return 0;
+  return ((capacity - requested) * 10) / capacity;
+}
+// most_requested.go:52-61
+KB_HD int64_t most_requested_score(int64_t requested, int64_t capacity) {
+  if (capacity == 0) return 0;
+  if (requested > capacity) return 0;
+  return (requested * 10) / capacity;
+}
+// balanced_resource_allocation.go:42-79 (BalanceAttachedNodeVolumes gate off)
+KB_HD int64_t balanced_score(int64_t req_cpu, int64_t cap_cpu, int64_t req_mem, int64_t cap_mem) {
+  double cf = cap_cpu == 0 ? 1.0 : KB_DDIV(KB_LL2D(req_cpu), KB_LL2D(cap_cpu));
+  double mf = cap_mem == 0 ? 1.0 : KB_DDIV(KB_LL2D(req_mem), KB_LL2D(cap_mem));
+  if (cf >= 1.0 || mf >= 1.0) return 0;
+  double diff = KB_FABS(KB_DSUB(cf, mf));
+  return (int64_t)KB_D2LL(KB_DMUL(KB_DSUB(1.0, diff), 10.0));
+}
+
+// Packed candidate key: (biased score << 32) | (0xFFFFFFFF - node).  max over keys == highest score,
+// ties to the smallest canonical node index (== lexicographically smallest node name).  0 == infeasible.
+KB_HD uint64_t pack_key(int64_t biased_score, uint32_t node) {
+  return ((uint64_t)biased_score << 32) | (uint64_t)(0xFFFFFFFFu - node);
+}
+KB_HD uint32_t key_node(uint64_t key) { return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull); }
+KB_HD int64_t key_score(uint64_t key) { return (int64_t)(key >> 32); }
+
+// NodeAcc concept: idle(r) rel(r) -> double; alloc_cpu() alloc_mem() nz_cpu() nz_mem() -> int64_t;
+// pods() max_pods() -> int32_t; flags() -> uint32_t; labels(w) taints(w) ports(w) -> uint64_t.
+//
+// K1 (predicate bitmask) + K2 (fused score) for one (class, node) pair against the node's CURRENT state.
+// Returns the packed key, 0 if predicateFn would return an error.  `fits_idle` reports
+// InitResreq <= Idle, which decides Allocate vs Pipeline at commit (allocate.go:160).
+template <class NodeAcc>
+KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n, uint32_t node_idx, bool* fits_idle) {
+  const uint32_t R = cf.R, W = cf.W;
+  auto init = [&](uint32_t k) { return c.initreq[k]; };
+  // allocate.go:82: !InitResreq.LessEqual(Idle) && !InitResreq.LessEqual(Releasing) -> ResourceFit failed
+  bool fi = res_less_equal(R, init, [&](uint32_t k) { return n.idle(k); });
+  if (fits_idle) *fits_idle = fi;
+  if (!fi && !res_less_equal(R, init, [&](uint32_t k) { return n.rel(k); })) return 0;
+
+  if (cf.predicates) {
+    if (n.max_pods() <= n.pods()) return 0;                                                     // predicates.go:127
+    uint32_t fl = n.flags();
+    if (fl & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) return 0;   // vendored :1675-1698
+    uint64_t bad = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+      uint64_t lab = n.labels(w);
+      bad |= (lab & c.sel_req[w]) ^ c.sel_req[w];          // nodeSelector atoms missing        (:927-935)
+      bad |= n.ports(w) & c.port_conflict[w];              // host port conflict                 (:1153-1173)
+      bad |= n.taints(w) & ~c.tol[w];                      // untolerated NoSchedule/NoExecute   (:1596-1624)
+    }
+    if (bad) return 0;
+    if (c.n_aff) {                                         // required node affinity: OR of AND-terms (:944-968)
+      bool any = false;
+      for (uint32_t t = 0; t < c.n_aff; ++t) {
+        uint64_t miss = 0;
+        for (uint32_t w = 0; w < W; ++w) miss |= (n.labels(w) & c.aff[t][w]) ^ c.aff[t][w];
+        any = any || (miss == 0);
+      }
+      if (!any) return 0;
+    }
+    if (cf.mem_pressure && (c.flags & KB_TASK_BEST_EFFORT_QOS) && (fl & KB_NODE_MEM_PRESSURE)) return 0;   // :1633-1650
+    if (cf.disk_pressure && (fl & KB_NODE_DISK_PRESSURE)) return 0;                                         // :1654-1660
+    if (cf.pid_pressure && (fl & KB_NODE_PID_PRESSURE)) return 0;                                           // :1664-1671
+  }
+
+  int64_t score = cf.score_bias;
+  if (cf.nodeorder) {
+    // resource_allocation.go:100-123: req = nodeInfo.NonZeroRequest() + pod non-zero request
+    int64_t rc = n.nz_cpu() + c.nz_cpu, rm = n.nz_mem() + c.nz_mem;
+    int64_t ac = n.alloc_cpu(), am = n.alloc_mem();
+    if (cf.w_least)    score += ((least_requested_score(rc, ac) + least_requested_score(rm, am)) / 2) * (int64_t)cf.w_least;
+    if (cf.w_most)     score += ((most_requested_score(rc, ac) + most_requested_score(rm, am)) / 2) * (int64_t)cf.w_most;
+    if (cf.w_balanced) score += balanced_score(rc, ac, rm, am) * (int64_t)cf.w_balanced;
+  }
+  return pack_key(score, node_idx);
+}
+
+}  // namespace kb
+#endif  // KB_CORE_H_

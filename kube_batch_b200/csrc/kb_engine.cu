@@ -1,0 +1,328 @@
+// kb_engine.cu — libkbgpu.so: the C ABI of include/kbgpu.h over the sm_100a kernels.
+//
+// kb_session_load   flattens the caller's SoA snapshot into the device layout:
+//                     * node table -> TMA tiles [tile][column][128 nodes]  (kb_ctl.h tile_col_*)
+//                     * pending tasks -> equivalence classes (ClassRec) + per-job TaskOrderFn order
+//                     * built-in plugins resolved BY NAME into EvalConf / order chains; drf and
+//                       proportion OnSessionOpen precomputation redone on the host
+//                     * the first `queues.Pop()` .. `jobs.Pop()` is taken on the host so the device
+//                       starts with a ready run descriptor
+// kb_allocate       restores the pristine mutable slab (D2D), then pumps visit_kernel launches until
+//                   Ctl.done, runs the gang-commit prefix scan and copies the decisions back.
+// No CPU fallback exists: every decision is produced by the kernels.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "kb_build.h"
+#include "kb_kernels.cuh"
+
+using namespace kb;
+
+#define KB_VERSION_STRING "libkbgpu 0.1.0 sm_100a"
+
+namespace {
+
+}  // namespace
+
+struct kb_engine {
+  int device = 0;
+  int rank = 0, world = 1;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  bool loaded = false;
+
+  // session
+  uint32_t R = 0, W = 0, N = 0, T = 0, J = 0, Q = 0, C = 0, NT = 0, ncols = 0, To = 0;
+  unsigned char* d_mut = nullptr;      // mutable slab (current state)
+  unsigned char* d_pristine = nullptr; // copy of the mutable slab as loaded
+  unsigned char* d_imm = nullptr;      // immutable slab
+  size_t mut_bytes = 0, imm_bytes = 0;
+  DevSession dev{};                    // device pointers
+  uint32_t* d_task_class = nullptr;    // [T] (immutable slab)
+  int32_t* d_job_ready0 = nullptr;     // [J] (immutable slab)
+  Ctl* h_ctl = nullptr;                // pinned
+  kb_decision* h_dec = nullptr;        // pinned [T]
+  size_t off_tiles = 0, off_used = 0, off_job_ready = 0, off_job_share = 0, off_q_share = 0, off_q_alloc = 0;
+  size_t off_q_deserved_imm = 0;
+  std::vector<uint32_t> job_placed_host;
+  std::vector<int32_t> job_min_avail_host;
+  uint32_t gang_ready = 0;
+  uint32_t scan_grid = 1;
+  size_t visit_smem = 0, tile_smem = 0;
+  float load_ms = 0;
+  int sm_count = 148;
+};
+
+namespace {
+
+int fail(kb_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  if (e) e->err = buf;
+  return code;
+}
+#define CUDA_TRY(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return fail((e), KB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_c)); } while (0)
+
+thread_local std::string g_create_err;
+
+void free_session(kb_engine* e) {
+  if (e->d_mut) cudaFree(e->d_mut);
+  if (e->d_pristine) cudaFree(e->d_pristine);
+  if (e->d_imm) cudaFree(e->d_imm);
+  if (e->h_dec) cudaFreeHost(e->h_dec);
+  e->d_mut = e->d_pristine = e->d_imm = nullptr; e->h_dec = nullptr;
+  e->loaded = false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* kb_version(void) { return KB_VERSION_STRING; }
+
+const char* kb_status_str(int s) {
+  switch (s) {
+    case KB_OK: return "KB_OK";
+    case KB_E_BADARG: return "KB_E_BADARG";
+    case KB_E_UNSUPPORTED_PLUGIN: return "KB_E_UNSUPPORTED_PLUGIN";
+    case KB_E_CUDA: return "KB_E_CUDA";
+    case KB_E_NCCL: return "KB_E_NCCL";
+    case KB_E_STATE: return "KB_E_STATE";
+    case KB_E_UNSUPPORTED_FEATURE: return "KB_E_UNSUPPORTED_FEATURE";
+  }
+  return "KB_E_UNKNOWN";
+}
+
+const char* kb_last_error(kb_engine* e) { return e ? e->err.c_str() : g_create_err.c_str(); }
+
+int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
+  if (!opts || !out) { g_create_err = "opts/out is NULL"; return KB_E_BADARG; }
+  if (opts->abi_version != KB_ABI_VERSION) { g_create_err = "abi_version mismatch"; return KB_E_BADARG; }
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t c = cudaGetDeviceCount(&ndev);
+  if (c != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(c);
+    return KB_E_CUDA;
+  }
+  if (opts->device < 0 || opts->device >= ndev) { g_create_err = "device ordinal out of range"; return KB_E_BADARG; }
+  if (opts->world_size != 1 && opts->world_size != 0) {
+    g_create_err = "world_size > 1 needs the NCCL build of libkbgpu (node-axis sharding)"; return KB_E_NCCL; }
+  kb_engine* e = new kb_engine();
+  e->device = opts->device;
+  e->rank = 0; e->world = 1;
+  if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
+      (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
+      (c = cudaMallocHost(&e->h_ctl, sizeof(Ctl))) != cudaSuccess) {
+    g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(c);
+    delete e; return KB_E_CUDA;
+  }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+  *out = e;
+  return KB_OK;
+}
+
+void kb_engine_destroy(kb_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->device);
+  free_session(e);
+  if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  if (e->ev0) cudaEventDestroy(e->ev0);
+  if (e->ev1) cudaEventDestroy(e->ev1);
+  if (e->stream) cudaStreamDestroy(e->stream);
+  delete e;
+}
+
+int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* conf) {
+  if (!e) return KB_E_BADARG;
+  auto t_start = std::chrono::steady_clock::now();
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  free_session(e);
+  BuiltSession B;
+  BuildErr be;
+  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be)) return fail(e, rc, "%s", be.msg.c_str());
+  const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q, C = B.C, NT = B.NT, ncols = B.ncols, To = B.To, grid = B.grid;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  Slab& mut = B.mut; Slab& imm = B.imm;
+  const OffMut& om = B.om; const OffImm& oi = B.oi;
+  const HostConf& hc = B.hc;
+
+  // ---------------- upload ----------------
+  e->mut_bytes = mut.host.size(); e->imm_bytes = imm.host.size();
+  CUDA_TRY(e, cudaMalloc(&e->d_mut, e->mut_bytes));
+  CUDA_TRY(e, cudaMalloc(&e->d_pristine, e->mut_bytes));
+  CUDA_TRY(e, cudaMalloc(&e->d_imm, e->imm_bytes));
+  CUDA_TRY(e, cudaMallocHost(&e->h_dec, std::max<size_t>(1, T) * sizeof(kb_decision)));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_pristine, mut.host.data(), e->mut_bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_imm, imm.host.data(), e->imm_bytes, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  B.bind(e->dev, e->d_mut, e->d_imm);
+  e->d_task_class = (uint32_t*)(e->d_imm + oi.task_class);
+  e->d_job_ready0 = (int32_t*)(e->d_imm + oi.job_ready0);
+  e->R = R; e->W = W; e->N = N; e->T = T; e->J = J; e->Q = Q; e->C = C; e->NT = NT; e->ncols = ncols; e->To = To;
+  e->off_tiles = om.tiles; e->off_used = om.used; e->off_job_ready = om.job_ready; e->off_job_share = om.job_share;
+  e->off_q_share = om.q_share; e->off_q_alloc = om.q_alloc; e->off_q_deserved_imm = oi.q_des;
+  e->gang_ready = hc.gang_ready;
+  e->job_min_avail_host = B.job_min_avail;
+  e->scan_grid = grid;
+  e->tile_smem = tile_u64 * 8;
+  e->visit_smem = ((sizeof(VisitSmem) + 127) / 128) * 128 + 2 * e->tile_smem;
+  CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
+  e->loaded = true;
+  e->load_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+  return KB_OK;
+}
+
+int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_allocate before kb_session_load");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
+  uint32_t launches = 0;
+  const uint32_t BATCH = 64;
+  // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
+  const uint64_t cap = 4ull * ((uint64_t)e->J + e->To) + 1024;
+  for (;;) {
+    for (uint32_t i = 0; i < BATCH; ++i)
+      visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+    launches += BATCH;
+    CUDA_TRY(e, cudaGetLastError());
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, e->dev.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+    if (e->h_ctl->done) break;
+    if (launches > cap) return fail(e, KB_E_STATE, "allocate cycle did not terminate within %llu launches", (unsigned long long)cap);
+  }
+  if (e->J) {
+    const uint32_t warps_per_block = 4;
+    gang_commit_kernel<<<(e->J + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, e->stream>>>(e->dev, e->d_job_ready0);
+    launches += 1;
+  }
+  CUDA_TRY(e, cudaGetLastError());
+  if (e->T) CUDA_TRY(e, cudaMemcpyAsync(e->h_dec, e->dev.dec, (size_t)e->T * sizeof(kb_decision), cudaMemcpyDeviceToHost, e->stream));
+  std::vector<uint32_t> placed(e->J);
+  std::vector<int32_t> ready(e->J);
+  if (e->J) {
+    CUDA_TRY(e, cudaMemcpyAsync(placed.data(), e->dev.job_placed, (size_t)e->J * 4, cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(ready.data(), e->dev.job_ready, (size_t)e->J * 4, cudaMemcpyDeviceToHost, e->stream));
+  }
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (e->h_ctl->error) return fail(e, KB_E_STATE, "device reported invariant violation %u", e->h_ctl->error);
+  if (out && e->T) memcpy(out, e->h_dec, (size_t)e->T * sizeof(kb_decision));
+  if (stats) {
+    const Ctl& c = *e->h_ctl;
+    memset(stats, 0, sizeof *stats);
+    stats->pairs_logical = c.pairs_logical; stats->pairs_scanned = c.pairs_scanned; stats->pairs_replayed = c.pairs_replayed;
+    stats->tasks_processed = c.tasks_processed; stats->tasks_allocated = c.tasks_allocated; stats->tasks_pipelined = c.tasks_pipelined;
+    stats->visits = c.visits; stats->kernel_launches = launches; stats->n_classes = e->C;
+    uint32_t jr = 0;
+    for (uint32_t j = 0; j < e->J; ++j)
+      if (placed[j] && (!e->gang_ready || ready[j] >= e->job_min_avail_host[j])) ++jr;
+    stats->jobs_ready = jr;
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    stats->gpu_ms = ms; stats->load_ms = e->load_ms;
+  }
+  return KB_OK;
+}
+
+int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_predicate_score before kb_session_load");
+  if (task_lo > task_hi || task_hi > e->T) return fail(e, KB_E_BADARG, "task range [%u,%u) outside [0,%u)", task_lo, task_hi, e->T);
+  const size_t n = (size_t)(task_hi - task_lo) * e->N;
+  if (n == 0 || e->NT == 0) return KB_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  uint8_t* d_fit = nullptr; double* d_score = nullptr;
+  if (fit) CUDA_TRY(e, cudaMalloc(&d_fit, n));
+  if (score) CUDA_TRY(e, cudaMalloc(&d_score, n * 8));
+  dim3 grid(e->NT, (task_hi - task_lo + MATRIX_TASKS_PER_CTA - 1) / MATRIX_TASKS_PER_CTA);
+  matrix_kernel<<<grid, SCAN_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_fit, d_score);
+  cudaError_t c = cudaGetLastError();
+  if (c == cudaSuccess && fit) c = cudaMemcpyAsync(fit, d_fit, n, cudaMemcpyDeviceToHost, e->stream);
+  if (c == cudaSuccess && score) c = cudaMemcpyAsync(score, d_score, n * 8, cudaMemcpyDeviceToHost, e->stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+  if (d_fit) cudaFree(d_fit);
+  if (d_score) cudaFree(d_score);
+  if (c != cudaSuccess) return fail(e, KB_E_CUDA, "matrix_kernel: %s", cudaGetErrorString(c));
+  return KB_OK;
+}
+
+int kb_best_nodes(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint64_t* best_key) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_best_nodes before kb_session_load");
+  if (task_lo > task_hi || task_hi > e->T || !best_key) return fail(e, KB_E_BADARG, "bad task range or NULL output");
+  const uint32_t n = task_hi - task_lo;
+  if (n == 0) return KB_OK;
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  unsigned long long* d_best = nullptr;
+  CUDA_TRY(e, cudaMalloc(&d_best, (size_t)n * 8));
+  cudaError_t c = cudaMemsetAsync(d_best, 0, (size_t)n * 8, e->stream);
+  if (c == cudaSuccess && e->NT) {
+    // enough task chunks to fill the machine a few times over, each CTA keeps its node tile in shared memory
+    uint32_t chunks = std::max(1u, std::min(n, (uint32_t)(8 * e->sm_count + e->NT - 1) / std::max(1u, e->NT)));
+    dim3 grid(e->NT, chunks);
+    best_nodes_kernel<<<grid, SCAN_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_best);
+    c = cudaGetLastError();
+  }
+  if (c == cudaSuccess) c = cudaMemcpyAsync(best_key, d_best, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream);
+  if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
+  cudaFree(d_best);
+  if (c != cudaSuccess) return fail(e, KB_E_CUDA, "best_nodes_kernel: %s", cudaGetErrorString(c));
+  return KB_OK;
+}
+
+int kb_node_state(kb_engine* e, double* idle, double* releasing, double* used, int32_t* pods, int64_t* nz_cpu, int64_t* nz_mem, uint64_t* ports) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_node_state before kb_session_load");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const uint32_t R = e->R, W = e->W, N = e->N;
+  const size_t tile_u64 = (size_t)e->ncols * TILE_NODES;
+  std::vector<uint64_t> tiles((size_t)std::max(1u, e->NT) * tile_u64);
+  std::vector<double> usedv((size_t)R * std::max(1u, N));
+  CUDA_TRY(e, cudaMemcpyAsync(tiles.data(), e->dev.tiles, (size_t)e->NT * tile_u64 * 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(usedv.data(), e->dev.node_used, (size_t)R * N * 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  for (uint32_t n = 0; n < N; ++n) {
+    TileAcc a{tiles.data() + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+    for (uint32_t r = 0; r < R; ++r) {
+      if (idle) idle[(size_t)r * N + n] = a.idle(r);
+      if (releasing) releasing[(size_t)r * N + n] = a.rel(r);
+      if (used) used[(size_t)r * N + n] = usedv[(size_t)r * N + n];
+    }
+    if (pods) pods[n] = a.pods();
+    if (nz_cpu) nz_cpu[n] = a.nz_cpu();
+    if (nz_mem) nz_mem[n] = a.nz_mem();
+    if (ports) for (uint32_t w = 0; w < W; ++w) ports[(size_t)w * N + n] = a.ports(w);
+  }
+  return KB_OK;
+}
+
+int kb_order_state(kb_engine* e, double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_order_state before kb_session_load");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  if (job_share && e->J) CUDA_TRY(e, cudaMemcpyAsync(job_share, e->dev.job_share, (size_t)e->J * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (job_ready && e->J) CUDA_TRY(e, cudaMemcpyAsync(job_ready, e->dev.job_ready, (size_t)e->J * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (queue_share && e->Q) CUDA_TRY(e, cudaMemcpyAsync(queue_share, e->dev.q_share, (size_t)e->Q * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (queue_deserved && e->Q) CUDA_TRY(e, cudaMemcpyAsync(queue_deserved, e->dev.q_deserved, (size_t)e->R * e->Q * 8, cudaMemcpyDeviceToHost, e->stream));
+  if (queue_allocated && e->Q) CUDA_TRY(e, cudaMemcpyAsync(queue_allocated, e->dev.q_allocated, (size_t)e->R * e->Q * 8, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  return KB_OK;
+}
+
+}  // extern "C"

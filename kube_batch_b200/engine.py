@@ -1,0 +1,151 @@
+"""ctypes binding of libkbgpu.so — the product path.  There is no fallback: if the shared object
+or a CUDA device is missing, construction raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import abi
+from .snapshot import PluginConf, Snapshot
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
+
+EXPORTS = [
+    "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_predicate_score",
+    "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
+]
+
+
+class KbError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{msg} (status {code})")
+        self.code = code
+
+
+_lib = None
+
+
+def load_library():
+    """dlopen libkbgpu.so (built in-tree by __graft_entry__.build()).  Raises if it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FileNotFoundError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                    "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.kb_last_error.restype = C.c_char_p
+        L.kb_last_error.argtypes = [C.c_void_p]
+        L.kb_status_str.restype = C.c_char_p
+        L.kb_version.restype = C.c_char_p
+        L.kb_engine_destroy.restype = None
+        L.kb_engine_destroy.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+@dataclass
+class CycleResult:
+    decisions: np.ndarray          # structured, abi.DECISION_DTYPE, one per snapshot task
+    stats: abi.kb_stats
+
+    def bind_map(self):
+        d = self.decisions
+        return {int(t): int(d["node"][t]) for t in np.nonzero(d["dispatched"])[0]}
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Engine:
+    """One kb_engine.  Not thread-safe (like the single runOnce goroutine of the reference)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: Optional[bytes] = None):
+        self.L = load_library()
+        self._h = C.c_void_p()
+        opts = abi.kb_engine_opts()
+        opts.abi_version = abi.KB_ABI_VERSION
+        opts.device = device
+        opts.rank = rank
+        opts.world_size = world_size
+        self._uid = (C.c_char * 128).from_buffer_copy(nccl_unique_id) if nccl_unique_id else None
+        opts.nccl_unique_id = C.cast(self._uid, C.c_void_p) if self._uid is not None else None
+        opts.flags = 0
+        rc = self.L.kb_engine_create(C.byref(opts), C.byref(self._h))
+        if rc != 0:
+            raise KbError(rc, "kb_engine_create: " + self.L.kb_last_error(None).decode())
+        self.snap: Optional[Snapshot] = None
+
+    def close(self):
+        if self._h:
+            self.L.kb_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise KbError(rc, f"{what}: {self.L.kb_last_error(self._h).decode()}")
+
+    def load(self, snap: Snapshot, conf: PluginConf):
+        cs, keep1 = snap.to_c()
+        cc, keep2 = conf.to_c()
+        self._check(self.L.kb_session_load(self._h, C.byref(cs), C.byref(cc)), "kb_session_load")
+        self.snap = snap
+        return self
+
+    def allocate(self) -> CycleResult:
+        T = self.snap.T
+        dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+        st = abi.kb_stats()
+        self._check(self.L.kb_allocate(self._h, dec.ctypes.data_as(C.c_void_p), C.byref(st)), "kb_allocate")
+        return CycleResult(dec[:T], st)
+
+    def predicate_score(self, lo: int, hi: int):
+        N = self.snap.N
+        fit = np.zeros((hi - lo, N), dtype=np.uint8)
+        score = np.zeros((hi - lo, N), dtype=np.float64)
+        self._check(self.L.kb_predicate_score(self._h, C.c_uint32(lo), C.c_uint32(hi), _p(fit, C.c_uint8), _p(score, C.c_double)),
+                    "kb_predicate_score")
+        return fit, score
+
+    def best_nodes(self, lo: int, hi: int) -> np.ndarray:
+        out = np.zeros(max(hi - lo, 1), dtype=np.uint64)
+        self._check(self.L.kb_best_nodes(self._h, C.c_uint32(lo), C.c_uint32(hi), _p(out, C.c_uint64)), "kb_best_nodes")
+        return out[: hi - lo]
+
+    def node_state(self):
+        s = self.snap
+        out = dict(idle=np.zeros((s.R, s.N)), releasing=np.zeros((s.R, s.N)), used=np.zeros((s.R, s.N)),
+                   pods=np.zeros(s.N, dtype=np.int32), nz_cpu=np.zeros(s.N, dtype=np.int64),
+                   nz_mem=np.zeros(s.N, dtype=np.int64), ports=np.zeros((s.W, s.N), dtype=np.uint64))
+        self._check(self.L.kb_node_state(self._h, _p(out["idle"], C.c_double), _p(out["releasing"], C.c_double),
+                                         _p(out["used"], C.c_double), _p(out["pods"], C.c_int32),
+                                         _p(out["nz_cpu"], C.c_int64), _p(out["nz_mem"], C.c_int64),
+                                         _p(out["ports"], C.c_uint64)), "kb_node_state")
+        return out
+
+    def order_state(self):
+        s = self.snap
+        out = dict(job_share=np.zeros(s.J), job_ready=np.zeros(s.J, dtype=np.int32), queue_share=np.zeros(s.Q),
+                   queue_deserved=np.zeros((s.R, s.Q)), queue_allocated=np.zeros((s.R, s.Q)))
+        self._check(self.L.kb_order_state(self._h, _p(out["job_share"], C.c_double), _p(out["job_ready"], C.c_int32),
+                                          _p(out["queue_share"], C.c_double), _p(out["queue_deserved"], C.c_double),
+                                          _p(out["queue_allocated"], C.c_double)), "kb_order_state")
+        return out
+
+
+def key_node(key: np.ndarray) -> np.ndarray:
+    """Decode the packed best key of kb_best_nodes: node index, -1 where no node fits."""
+    k = np.asarray(key, dtype=np.uint64)
+    node = (np.uint64(0xFFFFFFFF) - (k & np.uint64(0xFFFFFFFF))).astype(np.int64)
+    return np.where(k == 0, -1, node)

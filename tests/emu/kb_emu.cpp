@@ -1,0 +1,222 @@
+// kb_emu.cpp — CPU emulation of the DEVICE ALGORITHM (test infrastructure, never shipped).
+//
+// Compiles the product's host/device-shared headers (kb_core.h, kb_ctl.h, kb_build.h) with g++ and
+// re-enacts visit_kernel step by step in one thread: scan of the node tiles for the current class ->
+// exact top-KTOP list -> replay with the dirty-slot / certification rules -> control plane ->
+// gang-commit prefix rule.  It shares NO code with oracle/ and lets `-m "not gpu"` tests check the
+// engine's logic (everything except the CUDA thread mechanics) against the oracle without a GPU.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../kube_batch_b200/csrc/kb_build.h"
+
+using namespace kb;
+
+namespace {
+thread_local std::string g_err;
+
+struct Slot {                     // one dirty node: a private copy of its tile columns
+  uint32_t node;
+  uint64_t col[2 * KB_MAX_R + 6 + 3 * KB_MAX_W];
+  double used_add[KB_MAX_R];
+};
+struct SlotAcc {
+  const Slot* s; uint32_t R, W;
+  uint64_t col(uint32_t c) const { return s->col[c]; }
+  double idle(uint32_t r) const { return u64_as_double(col(col_idle(R, r))); }
+  double rel(uint32_t r) const { return u64_as_double(col(col_rel(R, r))); }
+  int64_t alloc_cpu() const { return (int64_t)col(col_alloc_cpu(R)); }
+  int64_t alloc_mem() const { return (int64_t)col(col_alloc_mem(R)); }
+  int64_t nz_cpu() const { return (int64_t)col(col_nz_cpu(R)); }
+  int64_t nz_mem() const { return (int64_t)col(col_nz_mem(R)); }
+  int32_t pods() const { return (int32_t)(uint32_t)(col(col_pods(R)) & 0xFFFFFFFFull); }
+  int32_t max_pods() const { return (int32_t)(uint32_t)(col(col_pods(R)) >> 32); }
+  uint32_t flags() const { return (uint32_t)col(col_flags(R)); }
+  uint64_t labels(uint32_t w) const { return col(col_labels(R, W, w)); }
+  uint64_t taints(uint32_t w) const { return col(col_taints(R, W, w)); }
+  uint64_t ports(uint32_t w) const { return col(col_ports(R, W, w)); }
+};
+
+// one visit_kernel launch
+void emulate_launch(const DevSession& S) {
+  Ctl& c = *S.ctl;
+  if (c.done) return;
+  const uint32_t cls_id = c.cur_class;
+  const ClassRec& cls = S.classes[cls_id];
+  const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  // scan + K3
+  std::vector<uint64_t> keys;
+  for (uint32_t n = 0; n < S.N; ++n) {
+    TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+    uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr);
+    if (k) keys.push_back(k);
+  }
+  std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+  uint64_t L[KTOP];
+  for (int i = 0; i < KTOP; ++i) L[i] = i < (int)keys.size() ? keys[i] : 0;
+  c.scans += 1; c.pairs_scanned += S.N;
+
+  std::vector<Slot> dirty;
+  uint32_t p = 0;
+  for (;;) {
+    if (c.done || c.cur_class != cls_id) break;
+    const uint32_t j = (uint32_t)c.cur_job;
+    const uint32_t jend = S.job_ord_off[j + 1];
+    uint32_t run_left = c.cur_run, placed = 0, reason = STOP_RUN_DONE;
+    while (run_left > 0) {
+      if (dirty.size() == (size_t)DMAX) { reason = STOP_RESCAN; break; }
+      uint64_t clean_key = 0;
+      while (p < (uint32_t)KTOP) {
+        clean_key = L[p];
+        if (clean_key == 0) break;
+        const uint32_t pn = key_node(clean_key);
+        bool m = false;
+        for (auto& d : dirty) m = m || d.node == pn;
+        if (!m) break;
+        ++p;
+      }
+      if (p == (uint32_t)KTOP) { reason = STOP_RESCAN; break; }
+      const uint32_t pos = S.job_pos[j];
+      uint64_t best = clean_key;
+      std::vector<uint8_t> fi(dirty.size(), 0);
+      for (size_t s = 0; s < dirty.size(); ++s) {
+        bool f = false;
+        SlotAcc acc{&dirty[s], R, W};
+        uint64_t k = eval_pair(S.cf, cls, acc, dirty[s].node, &f);
+        fi[s] = f;
+        if (k > best) best = k;
+      }
+      S.job_pos[j] = pos + 1;
+      c.tasks_processed += 1; c.pairs_logical += S.N; c.pairs_replayed += dirty.size();
+      run_left -= 1;
+      if (best == 0) { reason = STOP_NOFIT; break; }
+      const uint32_t bn = key_node(best);
+      int slot = -1;
+      for (size_t s = 0; s < dirty.size(); ++s) if (dirty[s].node == bn) slot = (int)s;
+      bool fits_idle;
+      if (slot >= 0) fits_idle = fi[slot];
+      else {
+        Slot sl; sl.node = bn;
+        const uint64_t* gt = S.tiles + (size_t)(bn / TILE_NODES) * tile_u64 + (bn % TILE_NODES);
+        for (uint32_t cc = 0; cc < ncols; ++cc) sl.col[cc] = gt[(size_t)cc * TILE_NODES];
+        for (auto& x : sl.used_add) x = 0;
+        dirty.push_back(sl);
+        slot = (int)dirty.size() - 1;
+        SlotAcc acc{&dirty[slot], R, W};
+        fits_idle = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+      }
+      Slot& d = dirty[slot];
+      const uint32_t base_col = fits_idle ? col_idle(R, 0) : col_rel(R, 0);
+      for (uint32_t k = 0; k < R; ++k) {
+        d.col[base_col + k] = double_as_u64(u64_as_double(d.col[base_col + k]) - cls.resreq[k]);
+        d.used_add[k] += cls.resreq[k];
+      }
+      d.col[col_nz_cpu(R)] = (uint64_t)((int64_t)d.col[col_nz_cpu(R)] + cls.nz_cpu);
+      d.col[col_nz_mem(R)] = (uint64_t)((int64_t)d.col[col_nz_mem(R)] + cls.nz_mem);
+      d.col[col_pods(R)] += 1ull;
+      for (uint32_t w = 0; w < W; ++w) d.col[col_ports(R, W, w)] |= cls.port_own[w];
+      kb_decision dd;
+      dd.node = (int32_t)bn; dd.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED; dd.dispatched = 0; dd.reserved = 0;
+      dd.step = c.step; dd.dispatch_step = 0xFFFFFFFFu;
+      S.dec[S.ord_task[pos]] = dd;
+      c.step += 1;
+      if (fits_idle) { c.tasks_allocated += 1; S.job_ready[j] += 1; } else c.tasks_pipelined += 1;
+      S.job_placed[j] += 1;
+      on_allocate_event(S, j, cls);
+      placed += 1;
+      if (ssn_job_ready(S, j) && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
+    }
+    if (reason == STOP_RESCAN) c.rescans += 1;
+    after_run(S, c, reason, placed);
+    if (reason == STOP_RESCAN) break;
+  }
+  for (auto& d : dirty) {
+    uint64_t* gt = S.tiles + (size_t)(d.node / TILE_NODES) * tile_u64 + (d.node % TILE_NODES);
+    for (uint32_t cc = 0; cc < ncols; ++cc) gt[(size_t)cc * TILE_NODES] = d.col[cc];
+    for (uint32_t r = 0; r < R; ++r) S.node_used[(size_t)r * S.N + d.node] += d.used_add[r];
+  }
+}
+
+// gang_commit_kernel, serially
+void emulate_gang_commit(const DevSession& S, const int32_t* ready0) {
+  for (uint32_t j = 0; j < S.J; ++j) {
+    const uint32_t lo = S.job_ord_off[j], hi = S.job_pos[j];
+    const int32_t need = S.gang_ready ? S.job_min_avail[j] - ready0[j] : 0;
+    int32_t incl = 0;
+    uint32_t estar = 0xFFFFFFFFu, estep = 0;
+    for (uint32_t i = lo; i < hi; ++i) {
+      const kb_decision& d = S.dec[S.ord_task[i]];
+      if (d.kind == KB_KIND_ALLOCATED) { incl += 1; if (incl >= need) { estar = i; estep = d.step; break; } }
+    }
+    if (estar == 0xFFFFFFFFu) continue;
+    for (uint32_t i = lo; i < hi; ++i) {
+      kb_decision& d = S.dec[S.ord_task[i]];
+      if (d.kind != KB_KIND_ALLOCATED) continue;
+      d.dispatched = 1;
+      d.dispatch_step = i <= estar ? estep : d.step;
+    }
+  }
+}
+}  // namespace
+
+extern "C" {
+
+const char* kbemu_last_error(void) { return g_err.c_str(); }
+
+int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, kb_decision* out, kb_stats* stats,
+                   double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                   int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                   double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
+  BuiltSession B;
+  BuildErr be;
+  if (int rc = build_session(snap, conf, 148, B, &be)) { g_err = be.msg; return rc; }
+  DevSession S{};
+  B.bind(S, B.mut.host.data(), B.imm.host.data());
+  const int32_t* ready0 = (const int32_t*)(B.imm.host.data() + B.oi.job_ready0);
+  uint64_t guard = 4ull * ((uint64_t)B.J + B.To) + 1024;
+  uint32_t launches = 0;
+  while (!S.ctl->done) {
+    emulate_launch(S);
+    if (++launches > guard) { g_err = "emulated cycle did not terminate"; return KB_E_STATE; }
+  }
+  emulate_gang_commit(S, ready0);
+  const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q;
+  if (out) memcpy(out, S.dec, (size_t)T * sizeof(kb_decision));
+  const size_t tile_u64 = (size_t)B.ncols * TILE_NODES;
+  for (uint32_t n = 0; n < N; ++n) {
+    TileAcc a{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+    for (uint32_t r = 0; r < R; ++r) {
+      if (node_idle) node_idle[(size_t)r * N + n] = a.idle(r);
+      if (node_releasing) node_releasing[(size_t)r * N + n] = a.rel(r);
+      if (node_used) node_used[(size_t)r * N + n] = S.node_used[(size_t)r * N + n];
+    }
+    if (node_pods) node_pods[n] = a.pods();
+    if (node_nz_cpu) node_nz_cpu[n] = a.nz_cpu();
+    if (node_nz_mem) node_nz_mem[n] = a.nz_mem();
+    if (node_ports) for (uint32_t w = 0; w < W; ++w) node_ports[(size_t)w * N + n] = a.ports(w);
+  }
+  for (uint32_t j = 0; j < J; ++j) { if (job_share) job_share[j] = S.job_share[j]; if (job_ready) job_ready[j] = S.job_ready[j]; }
+  for (uint32_t q = 0; q < Q; ++q) {
+    if (queue_share) queue_share[q] = S.q_share[q];
+    for (uint32_t r = 0; r < R; ++r) {
+      if (queue_deserved) queue_deserved[(size_t)r * Q + q] = S.q_deserved[(size_t)r * Q + q];
+      if (queue_allocated) queue_allocated[(size_t)r * Q + q] = S.q_allocated[(size_t)r * Q + q];
+    }
+  }
+  if (stats) {
+    const Ctl& c = *S.ctl;
+    memset(stats, 0, sizeof *stats);
+    stats->pairs_logical = c.pairs_logical; stats->pairs_scanned = c.pairs_scanned; stats->pairs_replayed = c.pairs_replayed;
+    stats->tasks_processed = c.tasks_processed; stats->tasks_allocated = c.tasks_allocated; stats->tasks_pipelined = c.tasks_pipelined;
+    stats->visits = c.visits; stats->kernel_launches = launches; stats->n_classes = B.C;
+    uint32_t jr = 0;
+    for (uint32_t j = 0; j < J; ++j) if (S.job_placed[j] && ssn_job_ready(S, j)) ++jr;
+    stats->jobs_ready = jr;
+  }
+  return KB_OK;
+}
+
+}  // extern "C"

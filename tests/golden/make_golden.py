@@ -1,0 +1,33 @@
+"""Regenerates the committed golden fixtures.
+
+The reference (Go) cannot be executed in this image, so the fixtures are (a) the expected bind maps
+transcribed from the reference's own action test
+(/root/reference/pkg/scheduler/actions/allocate/allocate_test.go:51-144) and (b) oracle outputs for the
+seeded BASELINE configs c1 / c2 — the oracle itself being pinned on the reference's known answers by
+tests/test_oracle_golden.py.  Run from the repo root:  python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from kube_batch_b200 import synth  # noqa: E402
+from oracle import kbo  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+if __name__ == "__main__":
+    json.dump({
+        "source": "pkg/scheduler/actions/allocate/allocate_test.go:51-144",
+        "case1": {"c1/p1": "n1", "c1/p2": "n1"},
+        "case2": {"c2/p1": "n1", "c1/p1": "n1"},
+    }, open(os.path.join(HERE, "allocate_test_expected.json"), "w"), indent=1)
+    for name in ("c1", "c2"):
+        snap, conf = synth.make(name)
+        o = kbo.allocate(snap, conf)
+        np.savez_compressed(os.path.join(HERE, f"{name}_oracle.npz"), decisions=o.decisions,
+                            node_idle=o.node_idle, job_share=o.job_share, job_ready=o.job_ready)
+        print(name, "tasks", snap.T, "allocated", o.result.tasks_allocated)

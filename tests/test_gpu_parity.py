@@ -1,0 +1,154 @@
+"""`-m gpu`: the CUDA path, called through the C ABI (libkbgpu.so via ctypes), against the CPU oracle,
+the committed golden fixtures and size-independent properties.  Bit-exact: every field of every decision."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from kube_batch_b200 import abi, engine, synth
+from kube_batch_b200.snapshot import PluginConf
+from oracle import kbo
+import cases
+import util
+from test_emu_parity import CONFS
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.Engine(device=0)
+    yield e
+    e.close()
+
+
+def run_and_check(eng, snap, conf, what, states=True):
+    o = kbo.allocate(snap, conf)
+    eng.load(snap, conf)
+    r = eng.allocate()
+    util.assert_same_decisions(o.decisions, r.decisions, what)
+    if states:
+        util.assert_same_state(o, eng.node_state(), eng.order_state(), what)
+    st = r.stats
+    assert st.tasks_processed == o.result.tasks_processed
+    assert st.tasks_allocated == o.result.tasks_allocated
+    assert st.tasks_pipelined == o.result.tasks_pipelined
+    assert st.visits == o.result.visits
+    assert st.jobs_ready == o.result.jobs_ready
+    assert st.pairs_logical == o.result.pairs_logical
+    return o, r
+
+
+def test_reference_allocate_test_cases(eng):
+    exp = json.load(open(os.path.join(GOLD, "allocate_test_expected.json")))
+    for name, mk in (("case1", cases.allocate_test_case1), ("case2", cases.allocate_test_case2)):
+        s = mk()
+        eng.load(s, cases.tiers_allocate_test())
+        r = eng.allocate()
+        binds = {s.meta["tasks"][t]: s.meta["nodes"][n] for t, n in r.bind_map().items()}
+        assert binds == exp[name], name
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_baseline_configs_vs_oracle_and_golden(eng, name):
+    s, conf = synth.make(name)
+    o, r = run_and_check(eng, s, conf, name)
+    g = np.load(os.path.join(GOLD, f"{name}_oracle.npz"))
+    util.assert_same_decisions(g["decisions"], r.decisions, name + " (committed golden)")
+    np.testing.assert_array_equal(g["node_idle"], eng.node_state()["idle"])
+
+
+def test_allocate_is_repeatable(eng):
+    s, conf = synth.make("c2")
+    eng.load(s, conf)
+    a = eng.allocate()
+    b = eng.allocate()
+    util.assert_same_decisions(a.decisions, b.decisions, "second kb_allocate on the same session")
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_sessions_all_confs(eng, seed):
+    rng = np.random.default_rng(seed)
+    tasks = int(rng.integers(5, 300))
+    jobs = int(rng.integers(1, min(tasks, 40) + 1))
+    s = synth.random_session(seed, tasks=tasks, jobs=jobs, nodes=int(rng.integers(1, 200)), queues=int(rng.integers(1, 5)),
+                             min_member_frac=float(rng.choice([0.0, 0.5, 1.0])), hetero=float(rng.choice([0, 0.3, 1.0])),
+                             prio_levels=int(rng.integers(1, 4)), oversub=float(rng.choice([0.7, 1.3, 3.0])))
+    for cname, conf in CONFS.items():
+        run_and_check(eng, s, conf, f"seed{seed}/{cname}")
+
+
+def test_long_run_forces_rescans(eng):
+    s = synth.random_session(7, tasks=400, jobs=1, nodes=300, hetero=0.0, oversub=0.5)
+    run_and_check(eng, s, synth.conf_c2(), "long-run")
+
+
+def test_multi_tile_grid(eng):
+    # > 148 tiles: every scan CTA walks several TMA tiles (double buffer) and the merge sees 148 lists
+    s = synth.generate(synth.SynthSpec("wide", tasks=600, jobs=60, nodes=148 * 128 * 2 + 77, seed=99))
+    run_and_check(eng, s, PluginConf.default(), "wide", states=True)
+
+
+def test_predicate_score_matrix_vs_oracle(eng):
+    s, conf = synth.make("c2")
+    eng.load(s, conf)
+    fit, score = eng.predicate_score(0, s.T)
+    for t in list(range(0, s.T, 97)) + [s.T - 1]:
+        of, osc = kbo.predicate_score(s, conf, t)
+        np.testing.assert_array_equal(of, fit[t], err_msg=f"fit row {t}")
+        np.testing.assert_array_equal(osc, score[t], err_msg=f"score row {t}")
+    # K3: the fused argmax equals first-max of the matrix row (SelectBestNode with the deterministic rule)
+    best = engine.key_node(eng.best_nodes(0, s.T))
+    masked = np.where(fit > 0, score, -1.0)
+    exp = np.where(fit.any(axis=1), masked.argmax(axis=1), -1)
+    np.testing.assert_array_equal(exp, best)
+
+
+def test_degenerate_sessions(eng):
+    from kube_batch_b200.snapshot import Snapshot
+    for (T, J, N) in [(0, 0, 0), (0, 0, 5), (3, 1, 0)]:
+        s = Snapshot(3, 1, N, T, J, 1)
+        s.job_task_off[:] = [0] + [T] * J
+        s.task_uid_rank[:] = np.arange(T)
+        s.task_resreq[0, :] = 1000
+        s.task_initreq[0, :] = 1000
+        s.queue_weight[:] = 1
+        if N:
+            s.node_idle[0, :] = 4000
+            s.node_allocatable[0, :] = 4000
+            s.node_max_pods[:] = 10
+        run_and_check(eng, s, PluginConf.default(), f"degenerate T{T} J{J} N{N}")
+
+
+def test_unknown_plugin_and_unsupported_feature_fail_loudly(eng):
+    s, _ = synth.make("c1")
+    with pytest.raises(engine.KbError) as ei:
+        eng.load(s, PluginConf.from_names([["gang", "my-custom-plugin"]]))
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_PLUGIN
+    s.task_flags[0] |= abi.KB_TASK_HAS_POD_AFFINITY
+    with pytest.raises(engine.KbError) as ei:
+        eng.load(s, PluginConf.default())
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+
+
+def test_c3_full_size_parity_and_properties(eng):
+    """BASELINE config 3 (50k tasks x 5k nodes, default tiers) — full-size parity and invariants."""
+    s, conf = synth.make("c3")
+    o, r = run_and_check(eng, s, conf, "c3", states=True)
+    d = r.decisions
+    ns = eng.node_state()
+    # no node over-committed: Idle never below -epsilon, Used + Idle == Allocatable for untouched releasing
+    assert (ns["idle"][0] > -10).all() and (ns["idle"][1] > -10 * 1024 * 1024).all()
+    # gang: a job's tasks are dispatched iff the job reached MinAvailable
+    tj = s.job_of_task()
+    osr = eng.order_state()
+    ready = osr["job_ready"] >= s.job_min_avail
+    alloc = d["kind"] == abi.KB_KIND_ALLOCATED
+    assert (d["dispatched"][alloc] == ready[tj[alloc]]).all()
+    assert not d["dispatched"][~alloc].any()
+    # steps are a permutation of 0..placed-1
+    placed = d["step"] != 0xFFFFFFFF
+    assert sorted(d["step"][placed].tolist()) == list(range(int(placed.sum())))
+    assert r.stats.pairs_logical == int(r.stats.tasks_processed) * s.N

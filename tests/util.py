@@ -1,0 +1,89 @@
+"""Shared test helpers: CPU emulation binding + result comparison against the oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from kube_batch_b200 import abi
+from kube_batch_b200.snapshot import PluginConf, Snapshot
+from oracle import kbo
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_EMU = os.path.join(_HERE, "emu", "libkbemu.so")
+_emu = None
+
+
+def emu_lib():
+    global _emu
+    if _emu is None:
+        subprocess.check_call(["make", "-C", os.path.join(_HERE, "emu"), "-s"])
+        _emu = C.CDLL(_EMU)
+        _emu.kbemu_last_error.restype = C.c_char_p
+    return _emu
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def emu_allocate(snap: Snapshot, conf: PluginConf) -> kbo.OracleOut:
+    """Run the CPU emulation of the device algorithm; same result container as the oracle."""
+    L = emu_lib()
+    cs, k1 = snap.to_c()
+    cc, k2 = conf.to_c()
+    R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
+    dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+    st = abi.kb_stats()
+    out = kbo.OracleOut(
+        decisions=dec, result=st,
+        node_idle=np.zeros((R, N)), node_releasing=np.zeros((R, N)), node_used=np.zeros((R, N)),
+        node_pods=np.zeros(N, dtype=np.int32), node_nz_cpu=np.zeros(N, dtype=np.int64),
+        node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
+        job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
+        queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
+    rc = L.kbemu_allocate(C.byref(cs), C.byref(cc), dec.ctypes.data_as(C.c_void_p), C.byref(st),
+                          _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
+                          _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
+                          _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
+                          _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double), _p(out.queue_allocated, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"kbemu_allocate rc={rc}: {L.kbemu_last_error().decode()}")
+    out.decisions = dec[:T]
+    return out
+
+
+def assert_same_decisions(ref: np.ndarray, got: np.ndarray, what: str = ""):
+    """Bit-exact placement parity: node, kind, dispatched, step and dispatch_step of every task."""
+    assert ref.shape == got.shape, (what, ref.shape, got.shape)
+    for f in ("kind", "node", "step", "dispatched", "dispatch_step"):
+        bad = np.nonzero(ref[f] != got[f])[0]
+        if len(bad):
+            t = int(bad[0])
+            raise AssertionError(f"{what}: field '{f}' differs for {len(bad)} task(s); first task {t}: "
+                                 f"oracle={ref[t]} got={got[t]}")
+
+
+def assert_same_state(o: kbo.OracleOut, node_state: dict, order_state: dict, what: str = ""):
+    np.testing.assert_array_equal(o.node_idle, node_state["idle"], err_msg=f"{what}: node idle")
+    np.testing.assert_array_equal(o.node_releasing, node_state["releasing"], err_msg=f"{what}: node releasing")
+    np.testing.assert_array_equal(o.node_used, node_state["used"], err_msg=f"{what}: node used")
+    np.testing.assert_array_equal(o.node_pods, node_state["pods"], err_msg=f"{what}: pods")
+    np.testing.assert_array_equal(o.node_nz_cpu, node_state["nz_cpu"], err_msg=f"{what}: nz_cpu")
+    np.testing.assert_array_equal(o.node_nz_mem, node_state["nz_mem"], err_msg=f"{what}: nz_mem")
+    np.testing.assert_array_equal(o.node_ports, node_state["ports"], err_msg=f"{what}: ports")
+    np.testing.assert_array_equal(o.job_share, order_state["job_share"], err_msg=f"{what}: job share")
+    np.testing.assert_array_equal(o.job_ready, order_state["job_ready"], err_msg=f"{what}: job ready")
+    np.testing.assert_array_equal(o.queue_share, order_state["queue_share"], err_msg=f"{what}: queue share")
+    np.testing.assert_array_equal(o.queue_deserved, order_state["queue_deserved"], err_msg=f"{what}: deserved")
+    np.testing.assert_array_equal(o.queue_allocated, order_state["queue_allocated"], err_msg=f"{what}: allocated")
+
+
+def emu_states(e: kbo.OracleOut):
+    ns = dict(idle=e.node_idle, releasing=e.node_releasing, used=e.node_used, pods=e.node_pods, nz_cpu=e.node_nz_cpu,
+              nz_mem=e.node_nz_mem, ports=e.node_ports)
+    os_ = dict(job_share=e.job_share, job_ready=e.job_ready, queue_share=e.queue_share, queue_deserved=e.queue_deserved,
+               queue_allocated=e.queue_allocated)
+    return ns, os_
