@@ -196,6 +196,14 @@ typedef struct kb_stats {
   uint32_t n_classes;       /* task equivalence classes in the session                          */
   float    gpu_ms;          /* device time of the cycle (CUDA events on the engine stream)      */
   float    load_ms;         /* host time of kb_session_load (flatten->device)                   */
+  uint64_t h2d_bytes;       /* bytes kb_session_load copied host->device                        */
+  uint64_t d2h_bytes;       /* bytes kb_allocate copied device->host (decisions + control block) */
+  uint32_t scans;           /* visit_kernel launches that scanned the node table                */
+  uint32_t rescans;         /* runs cut short because the candidate list could not certify a pick */
+  uint64_t cyc_scan;        /* SM cycles (clock64) of the last CTA per launch, summed: scan phase */
+  uint64_t cyc_merge;       /*   ... candidate-list merge                                        */
+  uint64_t cyc_replay;      /*   ... replay + control                                            */
+  uint64_t cyc_total;
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

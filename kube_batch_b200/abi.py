@@ -163,6 +163,14 @@ class kb_stats(C.Structure):
         ("n_classes", C.c_uint32),
         ("gpu_ms", C.c_float),
         ("load_ms", C.c_float),
+        ("h2d_bytes", C.c_uint64),
+        ("d2h_bytes", C.c_uint64),
+        ("scans", C.c_uint32),
+        ("rescans", C.c_uint32),
+        ("cyc_scan", C.c_uint64),
+        ("cyc_merge", C.c_uint64),
+        ("cyc_replay", C.c_uint64),
+        ("cyc_total", C.c_uint64),
     ]
 
 

@@ -189,7 +189,7 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl; };
-struct OffImm { size_t classes, ord_task, ord_class, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
+struct OffImm { size_t classes, ord_task, ord_class, ord_run, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
 
 struct BuiltSession {
   Slab mut, imm;
@@ -217,6 +217,7 @@ struct BuiltSession {
     D.qheap = (uint32_t*)(mb + om.qheap); D.dec = (kb_decision*)(mb + om.dec); D.cand = (uint64_t*)(mb + om.cand);
     D.ctl = (Ctl*)(mb + om.ctl);
     D.classes = (ClassRec*)(ib + oi.classes); D.ord_task = (uint32_t*)(ib + oi.ord_task); D.ord_class = (uint32_t*)(ib + oi.ord_class);
+    D.ord_run = (uint32_t*)(ib + oi.ord_run);
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -324,6 +325,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.classes = imm.alloc((size_t)C * sizeof(ClassRec));
   oi.ord_task = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.ord_class = imm.alloc((size_t)std::max(1u, To) * 4);
+  oi.ord_run = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.job_ord_off = imm.alloc((size_t)(J + 1) * 4);
   oi.job_min = imm.alloc((size_t)std::max(1u, J) * 4);
   oi.job_queue = imm.alloc((size_t)std::max(1u, J) * 4);
@@ -373,6 +375,9 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   // ---------------- immutable job / queue / class tables ----------------
   memcpy(H.classes, classes.data(), (size_t)C * sizeof(ClassRec));
   if (To) { memcpy(H.ord_task, ord_task.data(), (size_t)To * 4); memcpy(H.ord_class, ord_class.data(), (size_t)To * 4); }
+  for (uint32_t j = 0; j < J; ++j)                     // run lengths, right to left inside each job
+    for (uint32_t i = job_ord_off[j + 1]; i-- > job_ord_off[j];)
+      H.ord_run[i] = (i + 1 < job_ord_off[j + 1] && ord_class[i + 1] == ord_class[i]) ? H.ord_run[i + 1] + 1 : 1;
   memcpy(H.job_ord_off, job_ord_off.data(), (size_t)(J + 1) * 4);
   if (T) memcpy(imm.host.data() + oi.task_class, task_class.data(), (size_t)T * 4);
   std::vector<uint32_t> tb_order(J);

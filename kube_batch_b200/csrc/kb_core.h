@@ -117,17 +117,30 @@ KB_HD double share_of(double l, double r) {
   return KB_DDIV(l, r);
 }
 
+// a / b for b > 0 when the quotient is known to lie in [0, 10]: ten independent multiply-compares instead
+// of a 64-bit integer division (which costs hundreds of cycles on the GPU).  Exact: q = #{k in 1..10 : k*b <= a}.
+KB_HD int64_t div_0_to_10(int64_t a, int64_t b) {
+  if (a < 0 || a > 10 * b) return a / b;          // outside the fast range (never on sane inputs)
+  int64_t q = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int64_t k = 1; k <= 10; ++k) q += (k * b <= a) ? 1 : 0;
+  return q;
+}
 // least_requested.go:49-58
 KB_HD int64_t least_requested_score(int64_t requested, int64_t capacity) {
   if (capacity == 0) return 0;
   if (requested > capacity) return 0;
-  return ((capacity - requested) * 10) / capacity;
+  if (capacity < 0 || capacity > ((int64_t)1 << 58)) return ((capacity - requested) * 10) / capacity;
+  return div_0_to_10((capacity - requested) * 10, capacity);
 }
 // most_requested.go:52-61
 KB_HD int64_t most_requested_score(int64_t requested, int64_t capacity) {
   if (capacity == 0) return 0;
   if (requested > capacity) return 0;
-  return (requested * 10) / capacity;
+  if (capacity < 0 || capacity > ((int64_t)1 << 58)) return (requested * 10) / capacity;
+  return div_0_to_10(requested * 10, capacity);
 }
 // balanced_resource_allocation.go:42-79 (BalanceAttachedNodeVolumes gate off)
 KB_HD int64_t balanced_score(int64_t req_cpu, int64_t cap_cpu, int64_t req_mem, int64_t cap_mem) {

@@ -32,6 +32,8 @@ struct Ctl {
   uint32_t tasks_processed, tasks_allocated, tasks_pipelined, visits, scans, rescans;
   uint32_t error;         // sticky: an invariant the reference would panic on
   unsigned long long pairs_logical, pairs_scanned, pairs_replayed;
+  // phase timers of the LAST CTA of every launch, SM cycles (clock64), summed over the cycle
+  unsigned long long cyc_scan, cyc_merge, cyc_replay, cyc_total;
 };
 
 struct DevSession {
@@ -53,6 +55,7 @@ struct DevSession {
   // tasks in TaskOrderFn order, grouped by job
   uint32_t* ord_task;     // [To] snapshot task index
   uint32_t* ord_class;    // [To]
+  uint32_t* ord_run;      // [To] number of consecutive slots of the same class starting here (within the job)
   uint32_t* job_ord_off;  // [J+1]
   uint32_t* job_pos;      // [J] cursor into ord_* (pendingTasks[job.UID], allocate.go:110-126)
   // jobs
@@ -190,12 +193,15 @@ KB_HD void qheap_down(const DevSession& S, int i0, int n) {
     i = j;
   }
 }
+// With a single queue every heap entry is the same element: Push/Pop only move the length.
 KB_HD void qheap_push(const DevSession& S, Ctl& c, uint32_t q) {
+  if (S.Q == 1) { c.qheap_len += 1; return; }
   S.qheap[c.qheap_len] = q;
   c.qheap_len += 1;
   qheap_up(S, (int)c.qheap_len - 1);
 }
 KB_HD uint32_t qheap_pop(const DevSession& S, Ctl& c) {
+  if (S.Q == 1) { c.qheap_len -= 1; return 0; }
   int n = (int)c.qheap_len - 1;
   uint32_t t = S.qheap[0]; S.qheap[0] = S.qheap[n]; S.qheap[n] = t;
   qheap_down(S, 0, n);
@@ -248,13 +254,9 @@ KB_HD void on_allocate_event(const DevSession& S, uint32_t j, const ClassRec& c)
 // visit state machine
 // ---------------------------------------------------------------------------------------------
 KB_HD void setup_run(const DevSession& S, Ctl& c) {
-  const uint32_t j = (uint32_t)c.cur_job;
-  const uint32_t pos = S.job_pos[j], end = S.job_ord_off[j + 1];
-  const uint32_t cls = S.ord_class[pos];
-  uint32_t run = 1;
-  while (pos + run < end && S.ord_class[pos + run] == cls) ++run;
-  c.cur_class = cls;
-  c.cur_run = run;
+  const uint32_t pos = S.job_pos[(uint32_t)c.cur_job];
+  c.cur_class = S.ord_class[pos];
+  c.cur_run = S.ord_run[pos];
 }
 
 // jobs.Pop() for queue q: minimum of {head of the static sorted list} U {re-pushed jobs of q}

@@ -236,6 +236,10 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
     stats->jobs_ready = jr;
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     stats->gpu_ms = ms; stats->load_ms = e->load_ms;
+    stats->scans = c.scans; stats->rescans = c.rescans;
+    stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total;
+    stats->h2d_bytes = (uint64_t)e->mut_bytes + e->imm_bytes;
+    stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / BATCH) * sizeof(Ctl);
   }
   return KB_OK;
 }

@@ -78,49 +78,53 @@ struct ColAcc {
 };
 
 // ---------------------------------------------------------------------------------------------
-// CTA-wide exact top-KTOP merge by rank counting.
-//   keys[0..KTOP)            current list, descending, 0-padded
-//   keys[KTOP..KTOP+128)     128 fresh keys (one per thread, 0 = none)
-// Non-zero keys are unique (distinct node indices), so ranks are unique.  All SCAN_THREADS call it.
+// Warp-level exact top-32 selection: bitonic networks over one key per lane (shuffles only).
+// Lists are descending (lane 0 = best), 0-padded.  KTOP == 32 == warp size.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void cta_topk_merge(uint64_t* keys, uint64_t* newl, uint64_t fresh, int tid) {
-  keys[KTOP + tid] = fresh;
-  if (tid < KTOP) newl[tid] = 0;
-  __syncthreads();
-  const bool beats = fresh > keys[KTOP - 1];
-  if (!__syncthreads_or(beats ? 1 : 0)) return;        // nothing can enter the list
-  if (fresh != 0) {
-    int r = 0;
-#pragma unroll 8
-    for (int i = 0; i < KTOP + SCAN_THREADS; ++i) r += keys[i] > fresh ? 1 : 0;
-    if (r < KTOP) newl[r] = fresh;
-  }
-  if (tid < KTOP) {
-    const uint64_t old = keys[tid];
-    if (old != 0) {
-      int r = 0;
-#pragma unroll 8
-      for (int i = 0; i < KTOP + SCAN_THREADS; ++i) r += keys[i] > old ? 1 : 0;
-      if (r < KTOP) newl[r] = old;
+__device__ __forceinline__ uint64_t warp_sort_desc(uint64_t v, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(FULL, v, j);
+      const bool take_max = (((lane & k) == 0) == ((lane & j) == 0));
+      v = take_max ? (o > v ? o : v) : (o < v ? o : v);
     }
   }
-  __syncthreads();
-  if (tid < KTOP) keys[tid] = newl[tid];
-  __syncthreads();
+  return v;
+}
+// top-32 of the union of two descending lists, descending
+__device__ __forceinline__ uint64_t warp_merge_top32(uint64_t a, uint64_t b, int lane) {
+  const uint64_t br = __shfl_sync(FULL, b, 31 - lane);
+  uint64_t v = a > br ? a : br;                  // bitonic sequence holding the 32 largest
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t o = __shfl_xor_sync(FULL, v, j);
+    const bool take_max = (lane & j) == 0;
+    v = take_max ? (o > v ? o : v) : (o < v ? o : v);
+  }
+  return v;
 }
 
-struct DirtySlots {
-  uint64_t col[MAXCOLS][DMAX];      // same column scheme as a tile, stride DMAX
-  double   used_add[KB_MAX_R][DMAX];
-  uint32_t node[DMAX];
+
+// job-level state of the run being replayed, kept in shared memory so that a step touches no global
+// memory except the decision store and (for a newly dirtied node) one column gather
+struct RunState {
+  double   jalloc[KB_MAX_R];   // drfAttr.allocated of the job
+  double   qalloc[KB_MAX_R];   // queueAttr.allocated of its queue
+  uint32_t tasks[32];          // ord_task[] window
+  int32_t  ready, min_avail;
+  uint32_t placed_total;
 };
 
 struct VisitSmem {
   ClassRec cls;
   Ctl ctl;
-  uint64_t keys[KTOP + SCAN_THREADS];
-  uint64_t newl[KTOP];
-  DirtySlots dirty;
+  RunState rs;
+  uint64_t keys[KTOP];                       // merged candidate list of the scan (K3 result)
+  uint64_t wlist[SCAN_THREADS / 32][KTOP];   // per-warp lists exchanged through shared memory
+  uint64_t slot[2][MAXCOLS][32];             // candidate l: column c of state s at slot[s][c][l] (tile column scheme)
+  double   used_add[KB_MAX_R][32];           // NodeInfo.Used delta per candidate
   uint64_t mbar[2];
   uint32_t is_last;
 };
@@ -149,8 +153,8 @@ visit_kernel(const __grid_constant__ DevSession S) {
     for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
   }
   if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); }
-  if (tid < KTOP) sm.keys[tid] = 0;
   __syncthreads();
+  const long long t_start = clock64();
 
   // ---------------- scan: tiles blockIdx.x, +gridDim.x, ... double-buffered TMA ----------------
   const uint32_t first = blockIdx.x, stride = gridDim.x;
@@ -159,12 +163,16 @@ visit_kernel(const __grid_constant__ DevSession S) {
     mbar_expect_tx(&sm.mbar[0], tile_bytes);
     tma_load_1d(tilebuf, S.tiles + (size_t)first * tile_u64, tile_bytes, &sm.mbar[0]);
   }
+  uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
   for (uint32_t it = 0; it < n_local; ++it) {
     const uint32_t b = it & 1u;
-    if (tid == 0 && it + 1 < n_local) {      // prefetch next tile into the other buffer (freed by the
-      const uint32_t nb = b ^ 1u;            // __syncthreads at the end of the previous iteration)
-      mbar_expect_tx(&sm.mbar[nb], tile_bytes);
-      tma_load_1d(tilebuf + (size_t)nb * tile_u64, S.tiles + (size_t)(first + (it + 1) * stride) * tile_u64, tile_bytes, &sm.mbar[nb]);
+    if (it + 1 < n_local) {
+      __syncthreads();                       // every thread is done reading the other buffer (iteration it-1)
+      if (tid == 0) {
+        const uint32_t nb = b ^ 1u;
+        mbar_expect_tx(&sm.mbar[nb], tile_bytes);
+        tma_load_1d(tilebuf + (size_t)nb * tile_u64, S.tiles + (size_t)(first + (it + 1) * stride) * tile_u64, tile_bytes, &sm.mbar[nb]);
+      }
     }
     mbar_wait(&sm.mbar[b], (it >> 1) & 1u);
     const uint32_t t = first + it * stride;
@@ -174,29 +182,57 @@ visit_kernel(const __grid_constant__ DevSession S) {
       ColAcc acc{tilebuf + (size_t)b * tile_u64, (uint32_t)tid, TILE_NODES, S.cf.R, S.cf.W};
       key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
     }
-    cta_topk_merge(sm.keys, sm.newl, key, tid);       // ends with __syncthreads: buffer b is free again
+    // K3, warp level: skip the networks when nothing in this warp can enter its list
+    const uint64_t thr = __shfl_sync(FULL, mylist, 31);
+    if (__any_sync(FULL, key > thr)) {
+      key = warp_sort_desc(key, lane);
+      mylist = it == 0 ? key : warp_merge_top32(mylist, key, lane);
+    }
   }
-  // publish this CTA's list
-  if (tid < KTOP) S.cand[(size_t)blockIdx.x * KTOP + tid] = sm.keys[tid];
-  __threadfence();
+  // CTA level: warp 0 folds the other warps' lists in, then publishes the CTA's list
+  sm.wlist[warp][lane] = mylist;
   __syncthreads();
-  if (tid == 0) {
-    const uint32_t ticket = atomicAdd(&gctl->arrive, 1u);
-    sm.is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < SCAN_THREADS / 32; ++w) mylist = warp_merge_top32(mylist, sm.wlist[w][lane], lane);
+    S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
+    sm.keys[lane] = mylist;
+    __threadfence();
+    __syncwarp();                            // every lane's list entry is fenced before the ticket is taken
+    if (lane == 0) {
+      const uint32_t ticket = atomicAdd(&gctl->arrive, 1u);
+      sm.is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
   }
   __syncthreads();
   if (!sm.is_last) return;
   __threadfence();
+  const long long t_scan = clock64();
 
-  // ---------------- K3: merge the per-CTA lists (all 128 threads) ----------------
+  // ---------------- K3: merge the per-CTA lists: 4 warps, each folds every 4th list ----------------
   if (gridDim.x > 1) {
-    if (tid < KTOP) sm.keys[tid] = 0;
+    const uint32_t G = gridDim.x;
+    uint64_t acc = 0;
+    uint32_t g = warp;
+    uint64_t nxt = g < G ? __ldcg(&S.cand[(size_t)g * KTOP + lane]) : 0ull;
+    bool firstl = true;
+    while (g < G) {
+      const uint64_t cur = nxt;
+      const uint32_t g2 = g + SCAN_THREADS / 32;
+      nxt = g2 < G ? __ldcg(&S.cand[(size_t)g2 * KTOP + lane]) : 0ull;     // prefetch the next list
+      const uint64_t thr = __shfl_sync(FULL, acc, 31);
+      const uint64_t head = __shfl_sync(FULL, cur, 0);
+      if (firstl) { acc = cur; firstl = false; }
+      else if (head > thr) acc = warp_merge_top32(acc, cur, lane);
+      g = g2;
+    }
+    __syncthreads();                         // wlist is being reused
+    sm.wlist[warp][lane] = acc;
     __syncthreads();
-    const uint32_t total = gridDim.x * KTOP;
-    for (uint32_t base = 0; base < total; base += SCAN_THREADS) {
-      const uint32_t i = base + tid;
-      const uint64_t k = i < total ? __ldcg(&S.cand[i]) : 0ull;
-      cta_topk_merge(sm.keys, sm.newl, k, tid);
+    if (warp == 0) {
+#pragma unroll
+      for (int w = 1; w < SCAN_THREADS / 32; ++w) acc = warp_merge_top32(acc, sm.wlist[w][lane], lane);
+      sm.keys[lane] = acc;
     }
   }
   if (tid == 0) sm.ctl = *gctl;
@@ -204,100 +240,130 @@ visit_kernel(const __grid_constant__ DevSession S) {
   if (warp != 0) return;
 
   // ---------------- exact replay + control: warp 0 only ----------------
+  // Lane l OWNS candidate l of the merged list: its node record lives in two shared-memory slots
+  // (current state / state after one more placement of this class) and the lane keeps the packed key
+  // of both.  A step is then a warp arg-max over the current keys; the chosen lane swaps to its
+  // pre-evaluated next state.  eval_pair only runs in `refresh` rounds, for every lane whose look-ahead
+  // is stale, all at once.  Exactness: nodes outside the list have keys < floor_key (the 32nd key of a
+  // full list), so a pick is certified iff its key >= floor_key; otherwise the run stops for a rescan.
   Ctl& c = sm.ctl;
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
-  uint32_t nd = 0;        // dirty nodes
-  uint32_t p = 0;         // first list entry not known to be dirty
   if (lane == 0) { c.scans += 1; c.pairs_scanned += (unsigned long long)S.N; }
+  uint64_t cur_key = sm.keys[lane];
+  const uint64_t floor_key = sm.keys[KTOP - 1];
+  const bool have = cur_key != 0;
+  const uint32_t my_node = key_node(cur_key);
+  uint64_t* gt_mine = S.tiles + (size_t)(my_node / TILE_NODES) * (ncols * TILE_NODES) + (my_node % TILE_NODES);
+  uint32_t which = 0;                 // slot holding my CURRENT state
+  bool cur_fi = false, next_fi = false, next_valid = false, modified = false;
+  uint64_t next_key = 0;
+  if (have) {
+    for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(gt_mine + (size_t)cc * TILE_NODES);
+    ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
+    cur_fi = res_less_equal(R, [&](uint32_t k) { return sm.cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+  }
+#pragma unroll
+  for (int k = 0; k < KB_MAX_R; ++k) sm.used_add[k][lane] = 0.0;
+  // look-ahead refresh: next state = current state + one placement (Allocate if InitResreq <= Idle else Pipeline)
+  auto refresh = [&]() {
+    const bool need = have && cur_key != 0 && !next_valid;
+    const unsigned todo = __ballot_sync(FULL, need);
+    if (need) {
+      const uint64_t (*src)[32] = sm.slot[which];
+      uint64_t (*dst)[32] = sm.slot[which ^ 1u];
+      for (uint32_t cc = 0; cc < ncols; ++cc) dst[cc][lane] = src[cc][lane];
+      const uint32_t base_col = cur_fi ? col_idle(R, 0) : col_rel(R, 0);
+      for (uint32_t k = 0; k < R; ++k)
+        dst[base_col + k][lane] = double_as_u64(KB_DSUB(u64_as_double(src[base_col + k][lane]), sm.cls.resreq[k]));
+      dst[col_nz_cpu(R)][lane] = (uint64_t)((int64_t)src[col_nz_cpu(R)][lane] + sm.cls.nz_cpu);
+      dst[col_nz_mem(R)][lane] = (uint64_t)((int64_t)src[col_nz_mem(R)][lane] + sm.cls.nz_mem);
+      dst[col_pods(R)][lane] = src[col_pods(R)][lane] + 1ull;          // pods live in the low 32 bits
+      for (uint32_t w = 0; w < W; ++w) dst[col_ports(R, W, w)][lane] = src[col_ports(R, W, w)][lane] | sm.cls.port_own[w];
+      ColAcc acc{&dst[0][0], (uint32_t)lane, 32u, R, W};
+      next_key = eval_pair(S.cf, sm.cls, acc, my_node, &next_fi);
+      next_valid = true;
+    }
+    if (lane == 0) c.pairs_replayed += (unsigned long long)__popc(todo);
+  };
+  refresh();
   __syncwarp();
+  const long long t_merge = clock64();
 
   for (;;) {              // runs
     if (c.done || c.cur_class != cls_id) break;
     const uint32_t j = (uint32_t)c.cur_job;
+    const uint32_t q = c.cur_queue;
     const uint32_t jend = S.job_ord_off[j + 1];
+    const uint32_t pos0 = __shfl_sync(FULL, lane == 0 ? S.job_pos[j] : 0u, 0);
     uint32_t run_left = c.cur_run;
-    uint32_t placed = 0;
+    uint32_t placed = 0, popped = 0;
     uint32_t reason = STOP_RUN_DONE;
+    // load the job-level state once per run
+    if (lane == 0) { sm.rs.ready = S.job_ready[j]; sm.rs.min_avail = S.job_min_avail[j]; sm.rs.placed_total = S.job_placed[j]; }
+    if (lane < R) {
+      sm.rs.jalloc[lane] = S.drf_present ? S.job_alloc[(size_t)lane * S.J + j] : 0.0;
+      sm.rs.qalloc[lane] = S.proportion_present ? S.q_allocated[(size_t)lane * S.Q + q] : 0.0;
+    }
+    __syncwarp();
     while (run_left > 0) {      // steps: one pending task each
-      if (nd == DMAX) { reason = STOP_RESCAN; break; }
-      // advance p over entries that became dirty
-      uint64_t clean_key = 0;
-      while (p < (uint32_t)KTOP) {
-        clean_key = sm.keys[p];
-        if (clean_key == 0) break;
-        const uint32_t pn = key_node(clean_key);
-        const bool m = lane < nd && sm.dirty.node[lane] == pn;
-        if (!__any_sync(FULL, m)) break;
-        ++p;
+      const uint64_t best = warp_max_u64(cur_key);
+      if (best < floor_key) { reason = STOP_RESCAN; break; }      // a node outside the list might win: cannot certify
+      // pop the task (allocate.go:130); the ord_task window is refilled every 32 steps
+      const uint32_t pos = pos0 + popped;
+      if ((popped & 31u) == 0) {
+        __syncwarp();
+        if (pos + lane < jend) sm.rs.tasks[lane] = S.ord_task[pos + lane];
+        __syncwarp();
       }
-      if (p == (uint32_t)KTOP) { reason = STOP_RESCAN; break; }   // list exhausted while full: cannot certify
-      // pop the task (allocate.go:130); lane 0 owns the job arrays
-      const uint32_t pos = __shfl_sync(FULL, lane == 0 ? S.job_pos[j] : 0u, 0);
-      // exact re-evaluation of every dirty node against its current state
-      uint64_t my = 0;
-      bool fi = false;
-      if (lane < nd) {
-        ColAcc acc{&sm.dirty.col[0][0], (uint32_t)lane, DMAX, R, W};
-        my = eval_pair(S.cf, sm.cls, acc, sm.dirty.node[lane], &fi);
-      }
-      uint64_t best = warp_max_u64(my);
-      best = clean_key > best ? clean_key : best;
-      if (lane == 0) {
-        S.job_pos[j] = pos + 1;
-        c.tasks_processed += 1;
-        c.pairs_logical += (unsigned long long)S.N;
-        c.pairs_replayed += (unsigned long long)nd;
-      }
+      if (lane == 0) { c.tasks_processed += 1; c.pairs_logical += (unsigned long long)S.N; }
+      popped += 1;
       run_left -= 1;
       if (best == 0) { reason = STOP_NOFIT; break; }              // allocate.go:144-148
+      const uint32_t owner = (uint32_t)__ffs(__ballot_sync(FULL, cur_key == best)) - 1u;
+      if (!__shfl_sync(FULL, next_valid ? 1 : 0, owner)) refresh();
       const uint32_t bn = key_node(best);
-      const unsigned hit = __ballot_sync(FULL, lane < nd && sm.dirty.node[lane] == bn);
-      uint32_t slot;
-      bool fits_idle;
-      if (hit) {
-        slot = (uint32_t)__ffs(hit) - 1u;
-        fits_idle = __shfl_sync(FULL, fi ? 1 : 0, slot) != 0;
-      } else {
-        slot = nd;
-        const uint64_t* gt = S.tiles + (size_t)(bn / TILE_NODES) * (ncols * TILE_NODES) + (bn % TILE_NODES);
-        for (uint32_t cc = lane; cc < ncols; cc += 32) sm.dirty.col[cc][slot] = __ldcg(gt + (size_t)cc * TILE_NODES);
-        if (lane < KB_MAX_R) sm.dirty.used_add[lane][slot] = 0.0;
-        if (lane == 0) sm.dirty.node[slot] = bn;
-        nd += 1;
-        __syncwarp();
-        ColAcc acc{&sm.dirty.col[0][0], slot, DMAX, R, W};
-        fits_idle = res_less_equal(R, [&](uint32_t k) { return sm.cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+      const bool fits_idle = __shfl_sync(FULL, cur_fi ? 1 : 0, owner) != 0;
+      // commit: ssn.Allocate (session.go:235) or ssn.Pipeline (session.go:194) -> NodeInfo.AddTask (node_info.go:172-212):
+      // the owner lane switches to its pre-evaluated next state
+      if ((uint32_t)lane == owner) {
+        for (uint32_t k = 0; k < R; ++k) sm.used_add[k][lane] = KB_DADD(sm.used_add[k][lane], sm.cls.resreq[k]);
+        which ^= 1u;
+        cur_key = next_key; cur_fi = next_fi; next_valid = false; modified = true;
       }
-      // commit: ssn.Allocate (session.go:235) or ssn.Pipeline (session.go:194) -> NodeInfo.AddTask (node_info.go:172-212)
+      // AllocateFunc handlers of drf (drf.go:136-144) and proportion (proportion.go:213-222)
+      if (lane < R) {
+        sm.rs.jalloc[lane] = KB_DADD(sm.rs.jalloc[lane], sm.cls.resreq[lane]);
+        sm.rs.qalloc[lane] = KB_DADD(sm.rs.qalloc[lane], sm.cls.resreq[lane]);
+      }
       if (lane == 0) {
-        const uint32_t base_col = fits_idle ? col_idle(R, 0) : col_rel(R, 0);
-        for (uint32_t k = 0; k < R; ++k) {
-          const double cur = u64_as_double(sm.dirty.col[base_col + k][slot]);
-          sm.dirty.col[base_col + k][slot] = double_as_u64(KB_DSUB(cur, sm.cls.resreq[k]));
-          sm.dirty.used_add[k][slot] = KB_DADD(sm.dirty.used_add[k][slot], sm.cls.resreq[k]);
-        }
-        sm.dirty.col[col_nz_cpu(R)][slot] = (uint64_t)((int64_t)sm.dirty.col[col_nz_cpu(R)][slot] + sm.cls.nz_cpu);
-        sm.dirty.col[col_nz_mem(R)][slot] = (uint64_t)((int64_t)sm.dirty.col[col_nz_mem(R)][slot] + sm.cls.nz_mem);
-        sm.dirty.col[col_pods(R)][slot] += 1ull;                   // pods live in the low 32 bits
-        for (uint32_t w = 0; w < W; ++w) sm.dirty.col[col_ports(R, W, w)][slot] |= sm.cls.port_own[w];
         kb_decision d;
         d.node = (int32_t)bn;
         d.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED;
         d.dispatched = 0; d.reserved = 0;
         d.step = c.step;
         d.dispatch_step = 0xFFFFFFFFu;
-        S.dec[S.ord_task[pos]] = d;
+        S.dec[sm.rs.tasks[(popped - 1) & 31u]] = d;
         c.step += 1;
-        if (fits_idle) { c.tasks_allocated += 1; S.job_ready[j] += 1; } else c.tasks_pipelined += 1;
-        S.job_placed[j] += 1;
-        on_allocate_event(S, j, sm.cls);
+        if (fits_idle) { c.tasks_allocated += 1; sm.rs.ready += 1; } else c.tasks_pipelined += 1;
+        sm.rs.placed_total += 1;
       }
       placed += 1;
       __syncwarp();
       // allocate.go:185-188: a ready job yields after every task while tasks remain
-      const bool yield = __shfl_sync(FULL, (lane == 0 && ssn_job_ready(S, j) && (pos + 1 < jend)) ? 1 : 0, 0) != 0;
-      if (yield) { reason = STOP_YIELD; break; }
+      const bool jr = !S.gang_ready || sm.rs.ready >= sm.rs.min_avail;     // ssn.JobReady
+      if (jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
     }
+    // write the job-level state back, then run the control plane
+    if (lane == 0) {
+      S.job_pos[j] = pos0 + popped;
+      S.job_ready[j] = sm.rs.ready;
+      S.job_placed[j] = sm.rs.placed_total;
+    }
+    if (lane < R && placed) {
+      if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = sm.rs.jalloc[lane];
+      if (S.proportion_present) S.q_allocated[(size_t)lane * S.Q + q] = sm.rs.qalloc[lane];
+    }
+    __syncwarp();
     if (lane == 0) {
       if (reason == STOP_RESCAN) c.rescans += 1;
       after_run(S, c, reason, placed);
@@ -306,15 +372,22 @@ visit_kernel(const __grid_constant__ DevSession S) {
     if (reason == STOP_RESCAN) break;
   }
 
-  // write the dirty nodes back to the global table
-  for (uint32_t s = 0; s < nd; ++s) {
-    const uint32_t n = sm.dirty.node[s];
-    uint64_t* gt = S.tiles + (size_t)(n / TILE_NODES) * (ncols * TILE_NODES) + (n % TILE_NODES);
-    for (uint32_t cc = lane; cc < ncols; cc += 32) gt[(size_t)cc * TILE_NODES] = sm.dirty.col[cc][s];
-    if (lane < R) S.node_used[(size_t)lane * S.N + n] = KB_DADD(S.node_used[(size_t)lane * S.N + n], sm.dirty.used_add[lane][s]);
+  // write the modified candidates back to the global table
+  if (modified) {
+    const uint64_t (*src)[32] = sm.slot[which];
+    for (uint32_t cc = 0; cc < ncols; ++cc) gt_mine[(size_t)cc * TILE_NODES] = src[cc][lane];
+    for (uint32_t k = 0; k < R; ++k)
+      S.node_used[(size_t)k * S.N + my_node] = KB_DADD(S.node_used[(size_t)k * S.N + my_node], sm.used_add[k][lane]);
   }
   __syncwarp();
-  if (lane == 0) { c.arrive = 0; *gctl = c; }
+  if (lane == 0) {
+    const long long t_end = clock64();
+    c.cyc_scan += (unsigned long long)(t_scan - t_start);
+    c.cyc_merge += (unsigned long long)(t_merge - t_scan);
+    c.cyc_replay += (unsigned long long)(t_end - t_merge);
+    c.cyc_total += (unsigned long long)(t_end - t_start);
+    c.arrive = 0; *gctl = c;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

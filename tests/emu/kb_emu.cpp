@@ -2,7 +2,7 @@
 //
 // Compiles the product's host/device-shared headers (kb_core.h, kb_ctl.h, kb_build.h) with g++ and
 // re-enacts visit_kernel step by step in one thread: scan of the node tiles for the current class ->
-// exact top-KTOP list -> replay with the dirty-slot / certification rules -> control plane ->
+// exact top-KTOP list -> replay with the lane-owned-candidate / look-ahead / certification rules -> control plane ->
 // gang-commit prefix rule.  It shares NO code with oracle/ and lets `-m "not gpu"` tests check the
 // engine's logic (everything except the CUDA thread mechanics) against the oracle without a GPU.
 #include <algorithm>
@@ -59,65 +59,63 @@ void emulate_launch(const DevSession& S) {
   for (int i = 0; i < KTOP; ++i) L[i] = i < (int)keys.size() ? keys[i] : 0;
   c.scans += 1; c.pairs_scanned += S.N;
 
-  std::vector<Slot> dirty;
-  uint32_t p = 0;
+  // lane-owned candidates with a pre-evaluated look-ahead state (mirrors visit_kernel's epilogue)
+  struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = false, modified = false;
+                uint64_t cur_key = 0, next_key = 0; uint32_t node = 0; Slot st[2]; int which = 0; };
+  std::vector<Cand> cand(KTOP);
+  const uint64_t floor_key = L[KTOP - 1];
+  for (int l = 0; l < KTOP; ++l) {
+    Cand& cd = cand[l];
+    cd.cur_key = L[l]; cd.have = L[l] != 0;
+    if (!cd.have) continue;
+    cd.node = key_node(L[l]);
+    const uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
+    for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = gt[(size_t)cc * TILE_NODES];
+    for (auto& x : cd.st[0].used_add) x = 0;
+    cd.st[0].node = cd.st[1].node = cd.node;
+    SlotAcc acc{&cd.st[0], R, W};
+    cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+  }
+  auto refresh = [&]() {
+    for (auto& cd : cand) {
+      if (!(cd.have && cd.cur_key != 0 && !cd.next_valid)) continue;
+      const Slot& src = cd.st[cd.which];
+      Slot& dst = cd.st[cd.which ^ 1];
+      for (uint32_t cc = 0; cc < ncols; ++cc) dst.col[cc] = src.col[cc];
+      const uint32_t base_col = cd.cur_fi ? col_idle(R, 0) : col_rel(R, 0);
+      for (uint32_t k = 0; k < R; ++k) dst.col[base_col + k] = double_as_u64(u64_as_double(src.col[base_col + k]) - cls.resreq[k]);
+      dst.col[col_nz_cpu(R)] = (uint64_t)((int64_t)src.col[col_nz_cpu(R)] + cls.nz_cpu);
+      dst.col[col_nz_mem(R)] = (uint64_t)((int64_t)src.col[col_nz_mem(R)] + cls.nz_mem);
+      dst.col[col_pods(R)] = src.col[col_pods(R)] + 1ull;
+      for (uint32_t w = 0; w < W; ++w) dst.col[col_ports(R, W, w)] = src.col[col_ports(R, W, w)] | cls.port_own[w];
+      SlotAcc acc{&dst, R, W};
+      bool f = false;
+      cd.next_key = eval_pair(S.cf, cls, acc, cd.node, &f);
+      cd.next_fi = f; cd.next_valid = true;
+      c.pairs_replayed += 1;
+    }
+  };
+  refresh();
   for (;;) {
     if (c.done || c.cur_class != cls_id) break;
     const uint32_t j = (uint32_t)c.cur_job;
     const uint32_t jend = S.job_ord_off[j + 1];
     uint32_t run_left = c.cur_run, placed = 0, reason = STOP_RUN_DONE;
     while (run_left > 0) {
-      if (dirty.size() == (size_t)DMAX) { reason = STOP_RESCAN; break; }
-      uint64_t clean_key = 0;
-      while (p < (uint32_t)KTOP) {
-        clean_key = L[p];
-        if (clean_key == 0) break;
-        const uint32_t pn = key_node(clean_key);
-        bool m = false;
-        for (auto& d : dirty) m = m || d.node == pn;
-        if (!m) break;
-        ++p;
-      }
-      if (p == (uint32_t)KTOP) { reason = STOP_RESCAN; break; }
+      uint64_t best = 0; int owner = -1;
+      for (int l = 0; l < KTOP; ++l) if (cand[l].cur_key > best) { best = cand[l].cur_key; owner = l; }
+      if (best < floor_key) { reason = STOP_RESCAN; break; }
       const uint32_t pos = S.job_pos[j];
-      uint64_t best = clean_key;
-      std::vector<uint8_t> fi(dirty.size(), 0);
-      for (size_t s = 0; s < dirty.size(); ++s) {
-        bool f = false;
-        SlotAcc acc{&dirty[s], R, W};
-        uint64_t k = eval_pair(S.cf, cls, acc, dirty[s].node, &f);
-        fi[s] = f;
-        if (k > best) best = k;
-      }
       S.job_pos[j] = pos + 1;
-      c.tasks_processed += 1; c.pairs_logical += S.N; c.pairs_replayed += dirty.size();
+      c.tasks_processed += 1; c.pairs_logical += S.N;
       run_left -= 1;
       if (best == 0) { reason = STOP_NOFIT; break; }
+      Cand& cd = cand[owner];
+      if (!cd.next_valid) refresh();
+      const bool fits_idle = cd.cur_fi;
       const uint32_t bn = key_node(best);
-      int slot = -1;
-      for (size_t s = 0; s < dirty.size(); ++s) if (dirty[s].node == bn) slot = (int)s;
-      bool fits_idle;
-      if (slot >= 0) fits_idle = fi[slot];
-      else {
-        Slot sl; sl.node = bn;
-        const uint64_t* gt = S.tiles + (size_t)(bn / TILE_NODES) * tile_u64 + (bn % TILE_NODES);
-        for (uint32_t cc = 0; cc < ncols; ++cc) sl.col[cc] = gt[(size_t)cc * TILE_NODES];
-        for (auto& x : sl.used_add) x = 0;
-        dirty.push_back(sl);
-        slot = (int)dirty.size() - 1;
-        SlotAcc acc{&dirty[slot], R, W};
-        fits_idle = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
-      }
-      Slot& d = dirty[slot];
-      const uint32_t base_col = fits_idle ? col_idle(R, 0) : col_rel(R, 0);
-      for (uint32_t k = 0; k < R; ++k) {
-        d.col[base_col + k] = double_as_u64(u64_as_double(d.col[base_col + k]) - cls.resreq[k]);
-        d.used_add[k] += cls.resreq[k];
-      }
-      d.col[col_nz_cpu(R)] = (uint64_t)((int64_t)d.col[col_nz_cpu(R)] + cls.nz_cpu);
-      d.col[col_nz_mem(R)] = (uint64_t)((int64_t)d.col[col_nz_mem(R)] + cls.nz_mem);
-      d.col[col_pods(R)] += 1ull;
-      for (uint32_t w = 0; w < W; ++w) d.col[col_ports(R, W, w)] |= cls.port_own[w];
+      for (uint32_t k = 0; k < R; ++k) cd.st[0].used_add[k] += cls.resreq[k];
+      cd.which ^= 1; cd.cur_key = cd.next_key; cd.cur_fi = cd.next_fi; cd.next_valid = false; cd.modified = true;
       kb_decision dd;
       dd.node = (int32_t)bn; dd.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED; dd.dispatched = 0; dd.reserved = 0;
       dd.step = c.step; dd.dispatch_step = 0xFFFFFFFFu;
@@ -133,10 +131,12 @@ void emulate_launch(const DevSession& S) {
     after_run(S, c, reason, placed);
     if (reason == STOP_RESCAN) break;
   }
-  for (auto& d : dirty) {
-    uint64_t* gt = S.tiles + (size_t)(d.node / TILE_NODES) * tile_u64 + (d.node % TILE_NODES);
-    for (uint32_t cc = 0; cc < ncols; ++cc) gt[(size_t)cc * TILE_NODES] = d.col[cc];
-    for (uint32_t r = 0; r < R; ++r) S.node_used[(size_t)r * S.N + d.node] += d.used_add[r];
+  for (auto& cd : cand) {
+    if (!cd.modified) continue;
+    const Slot& src = cd.st[cd.which];
+    uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
+    for (uint32_t cc = 0; cc < ncols; ++cc) gt[(size_t)cc * TILE_NODES] = src.col[cc];
+    for (uint32_t r = 0; r < R; ++r) S.node_used[(size_t)r * S.N + cd.node] += cd.st[0].used_add[r];
   }
 }
 
