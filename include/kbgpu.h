@@ -204,6 +204,8 @@ typedef struct kb_stats {
   uint64_t cyc_merge;       /*   ... candidate-list merge                                        */
   uint64_t cyc_replay;      /*   ... replay + control                                            */
   uint64_t cyc_total;
+  uint64_t cyc_steps;       /*   ... of cyc_replay: the per-task step loops                      */
+  uint64_t cyc_ctl;         /*   ... of cyc_replay: the control plane (after_run)                 */
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

@@ -171,6 +171,8 @@ class kb_stats(C.Structure):
         ("cyc_merge", C.c_uint64),
         ("cyc_replay", C.c_uint64),
         ("cyc_total", C.c_uint64),
+        ("cyc_steps", C.c_uint64),
+        ("cyc_ctl", C.c_uint64),
     ]
 
 

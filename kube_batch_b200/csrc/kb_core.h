@@ -167,49 +167,61 @@ KB_HD int64_t key_score(uint64_t key) { return (int64_t)(key >> 32); }
 // InitResreq <= Idle, which decides Allocate vs Pipeline at commit (allocate.go:160).
 template <class NodeAcc>
 KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n, uint32_t node_idx, bool* fits_idle) {
+  // Written branch-free on purpose: a lone warp (the replay) or one warp per SM sub-partition (the scan)
+  // hides latency only through instruction-level parallelism, so every check is computed and AND-ed.
   const uint32_t R = cf.R, W = cf.W;
-  auto init = [&](uint32_t k) { return c.initreq[k]; };
   // allocate.go:82: !InitResreq.LessEqual(Idle) && !InitResreq.LessEqual(Releasing) -> ResourceFit failed
-  bool fi = res_less_equal(R, init, [&](uint32_t k) { return n.idle(k); });
+  bool fi = le_func(c.initreq[0], n.idle(0), KB_MIN_MILLI_CPU) & le_func(c.initreq[1], n.idle(1), KB_MIN_MEMORY);
+  bool fr = le_func(c.initreq[0], n.rel(0), KB_MIN_MILLI_CPU) & le_func(c.initreq[1], n.rel(1), KB_MIN_MEMORY);
+  for (uint32_t k = 2; k < R; ++k) {            // resource_info.go:286-299: scalars <= 10 are skipped
+    const double lq = c.initreq[k];
+    const bool skip = lq <= KB_MIN_MILLI_SCALAR;
+    fi = fi & (skip | le_func(lq, n.idle(k), KB_MIN_MILLI_SCALAR));
+    fr = fr & (skip | le_func(lq, n.rel(k), KB_MIN_MILLI_SCALAR));
+  }
   if (fits_idle) *fits_idle = fi;
-  if (!fi && !res_less_equal(R, init, [&](uint32_t k) { return n.rel(k); })) return 0;
+  bool ok = fi | fr;
 
   if (cf.predicates) {
-    if (n.max_pods() <= n.pods()) return 0;                                                     // predicates.go:127
-    uint32_t fl = n.flags();
-    if (fl & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) return 0;   // vendored :1675-1698
+    const uint32_t fl = n.flags();
+    ok = ok & (n.max_pods() > n.pods());                                                             // predicates.go:127
+    ok = ok & ((fl & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) == 0);   // vendored :1675-1698
     uint64_t bad = 0;
+    uint64_t miss[KB_MAX_AFF_TERMS] = {0, 0, 0, 0};
     for (uint32_t w = 0; w < W; ++w) {
-      uint64_t lab = n.labels(w);
+      const uint64_t lab = n.labels(w);
       bad |= (lab & c.sel_req[w]) ^ c.sel_req[w];          // nodeSelector atoms missing        (:927-935)
       bad |= n.ports(w) & c.port_conflict[w];              // host port conflict                 (:1153-1173)
       bad |= n.taints(w) & ~c.tol[w];                      // untolerated NoSchedule/NoExecute   (:1596-1624)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (uint32_t t = 0; t < KB_MAX_AFF_TERMS; ++t) miss[t] |= (lab & c.aff[t][w]) ^ c.aff[t][w];
     }
-    if (bad) return 0;
-    if (c.n_aff) {                                         // required node affinity: OR of AND-terms (:944-968)
-      bool any = false;
-      for (uint32_t t = 0; t < c.n_aff; ++t) {
-        uint64_t miss = 0;
-        for (uint32_t w = 0; w < W; ++w) miss |= (n.labels(w) & c.aff[t][w]) ^ c.aff[t][w];
-        any = any || (miss == 0);
-      }
-      if (!any) return 0;
-    }
-    if (cf.mem_pressure && (c.flags & KB_TASK_BEST_EFFORT_QOS) && (fl & KB_NODE_MEM_PRESSURE)) return 0;   // :1633-1650
-    if (cf.disk_pressure && (fl & KB_NODE_DISK_PRESSURE)) return 0;                                         // :1654-1660
-    if (cf.pid_pressure && (fl & KB_NODE_PID_PRESSURE)) return 0;                                           // :1664-1671
+    ok = ok & (bad == 0);
+    // required node affinity: OR of AND-terms (:944-968); unused term slots hold all-zero masks, so gate on n_aff
+    bool any = c.n_aff == 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (uint32_t t = 0; t < KB_MAX_AFF_TERMS; ++t) any = any | ((t < c.n_aff) & (miss[t] == 0));
+    ok = ok & any;
+    const bool memp = cf.mem_pressure && (c.flags & KB_TASK_BEST_EFFORT_QOS) && (fl & KB_NODE_MEM_PRESSURE);   // :1633-1650
+    const bool diskp = cf.disk_pressure && (fl & KB_NODE_DISK_PRESSURE);                                       // :1654-1660
+    const bool pidp = cf.pid_pressure && (fl & KB_NODE_PID_PRESSURE);                                          // :1664-1671
+    ok = ok & !(memp | diskp | pidp);
   }
 
   int64_t score = cf.score_bias;
   if (cf.nodeorder) {
     // resource_allocation.go:100-123: req = nodeInfo.NonZeroRequest() + pod non-zero request
-    int64_t rc = n.nz_cpu() + c.nz_cpu, rm = n.nz_mem() + c.nz_mem;
-    int64_t ac = n.alloc_cpu(), am = n.alloc_mem();
+    const int64_t rc = n.nz_cpu() + c.nz_cpu, rm = n.nz_mem() + c.nz_mem;
+    const int64_t ac = n.alloc_cpu(), am = n.alloc_mem();
     if (cf.w_least)    score += ((least_requested_score(rc, ac) + least_requested_score(rm, am)) / 2) * (int64_t)cf.w_least;
     if (cf.w_most)     score += ((most_requested_score(rc, ac) + most_requested_score(rm, am)) / 2) * (int64_t)cf.w_most;
     if (cf.w_balanced) score += balanced_score(rc, ac, rm, am) * (int64_t)cf.w_balanced;
   }
-  return pack_key(score, node_idx);
+  return ok ? pack_key(score, node_idx) : 0ull;
 }
 
 }  // namespace kb

@@ -33,7 +33,7 @@ struct Ctl {
   uint32_t error;         // sticky: an invariant the reference would panic on
   unsigned long long pairs_logical, pairs_scanned, pairs_replayed;
   // phase timers of the LAST CTA of every launch, SM cycles (clock64), summed over the cycle
-  unsigned long long cyc_scan, cyc_merge, cyc_replay, cyc_total;
+  unsigned long long cyc_scan, cyc_merge, cyc_replay, cyc_total, cyc_steps, cyc_ctl;
 };
 
 struct DevSession {

@@ -61,7 +61,10 @@ struct kb_engine {
   size_t visit_smem = 0, tile_smem = 0;
   float load_ms = 0;
   int sm_count = 148;
+  cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per session
+  cudaGraphExec_t graph_exec = nullptr;
 };
+constexpr uint32_t BATCH = 64;
 
 namespace {
 
@@ -76,6 +79,9 @@ int fail(kb_engine* e, int code, const char* fmt, ...) {
 thread_local std::string g_create_err;
 
 void free_session(kb_engine* e) {
+  if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
+  if (e->graph) cudaGraphDestroy(e->graph);
+  e->graph_exec = nullptr; e->graph = nullptr;
   if (e->d_mut) cudaFree(e->d_mut);
   if (e->d_pristine) cudaFree(e->d_pristine);
   if (e->d_imm) cudaFree(e->d_imm);
@@ -182,6 +188,12 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
+  // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch)
+  CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+  for (uint32_t i = 0; i < BATCH; ++i)
+    visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+  CUDA_TRY(e, cudaStreamEndCapture(e->stream, &e->graph));
+  CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
   e->loaded = true;
   e->load_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_start).count();
   return KB_OK;
@@ -194,14 +206,11 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
   uint32_t launches = 0;
-  const uint32_t BATCH = 64;
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
   const uint64_t cap = 4ull * ((uint64_t)e->J + e->To) + 1024;
   for (;;) {
-    for (uint32_t i = 0; i < BATCH; ++i)
-      visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+    CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
     launches += BATCH;
-    CUDA_TRY(e, cudaGetLastError());
     CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, e->dev.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (e->h_ctl->done) break;
@@ -237,7 +246,7 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
     float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
     stats->gpu_ms = ms; stats->load_ms = e->load_ms;
     stats->scans = c.scans; stats->rescans = c.rescans;
-    stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total;
+    stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total; stats->cyc_steps = c.cyc_steps; stats->cyc_ctl = c.cyc_ctl;
     stats->h2d_bytes = (uint64_t)e->mut_bytes + e->imm_bytes;
     stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / BATCH) * sizeof(Ctl);
   }

@@ -107,24 +107,12 @@ __device__ __forceinline__ uint64_t warp_merge_top32(uint64_t a, uint64_t b, int
 }
 
 
-// job-level state of the run being replayed, kept in shared memory so that a step touches no global
-// memory except the decision store and (for a newly dirtied node) one column gather
-struct RunState {
-  double   jalloc[KB_MAX_R];   // drfAttr.allocated of the job
-  double   qalloc[KB_MAX_R];   // queueAttr.allocated of its queue
-  uint32_t tasks[32];          // ord_task[] window
-  int32_t  ready, min_avail;
-  uint32_t placed_total;
-};
-
 struct VisitSmem {
   ClassRec cls;
   Ctl ctl;
-  RunState rs;
   uint64_t keys[KTOP];                       // merged candidate list of the scan (K3 result)
   uint64_t wlist[SCAN_THREADS / 32][KTOP];   // per-warp lists exchanged through shared memory
   uint64_t slot[2][MAXCOLS][32];             // candidate l: column c of state s at slot[s][c][l] (tile column scheme)
-  double   used_add[KB_MAX_R][32];           // NodeInfo.Used delta per candidate
   uint64_t mbar[2];
   uint32_t is_last;
 };
@@ -262,8 +250,6 @@ visit_kernel(const __grid_constant__ DevSession S) {
     ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
     cur_fi = res_less_equal(R, [&](uint32_t k) { return sm.cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
   }
-#pragma unroll
-  for (int k = 0; k < KB_MAX_R; ++k) sm.used_add[k][lane] = 0.0;
   // look-ahead refresh: next state = current state + one placement (Allocate if InitResreq <= Idle else Pipeline)
   auto refresh = [&]() {
     const bool need = have && cur_key != 0 && !next_valid;
@@ -289,84 +275,92 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __syncwarp();
   const long long t_merge = clock64();
 
+  uint32_t my_cnt = 0;        // placements on MY candidate (NodeInfo.Used delta = my_cnt x Resreq, applied at write-back)
   for (;;) {              // runs
     if (c.done || c.cur_class != cls_id) break;
     const uint32_t j = (uint32_t)c.cur_job;
     const uint32_t q = c.cur_queue;
     const uint32_t jend = S.job_ord_off[j + 1];
-    const uint32_t pos0 = __shfl_sync(FULL, lane == 0 ? S.job_pos[j] : 0u, 0);
     uint32_t run_left = c.cur_run;
-    uint32_t placed = 0, popped = 0;
+    uint32_t placed = 0, popped = 0, n_alloc = 0;
     uint32_t reason = STOP_RUN_DONE;
-    // load the job-level state once per run
-    if (lane == 0) { sm.rs.ready = S.job_ready[j]; sm.rs.min_avail = S.job_min_avail[j]; sm.rs.placed_total = S.job_placed[j]; }
+    // job-level state of the run lives in registers: lane 0 keeps the counters, lane k < R keeps dimension k
+    // of drfAttr.allocated / queueAttr.allocated; nothing but the decision store touches memory in a step
+    const uint32_t pos0 = __shfl_sync(FULL, lane == 0 ? S.job_pos[j] : 0u, 0);
+    int32_t ready = 0, min_avail = 0;
+    if (lane == 0) { ready = S.job_ready[j]; min_avail = S.job_min_avail[j]; }
+    ready = __shfl_sync(FULL, ready, 0); min_avail = __shfl_sync(FULL, min_avail, 0);
+    double jalloc = 0.0, qalloc = 0.0, my_rq = 0.0;
     if (lane < R) {
-      sm.rs.jalloc[lane] = S.drf_present ? S.job_alloc[(size_t)lane * S.J + j] : 0.0;
-      sm.rs.qalloc[lane] = S.proportion_present ? S.q_allocated[(size_t)lane * S.Q + q] : 0.0;
+      my_rq = sm.cls.resreq[lane];
+      if (S.drf_present) jalloc = S.job_alloc[(size_t)lane * S.J + j];
+      if (S.proportion_present) qalloc = S.q_allocated[(size_t)lane * S.Q + q];
     }
-    __syncwarp();
+    const uint32_t step0 = c.step;
+    uint32_t my_task = 0;       // lane l holds ord_task[window base + l]
+    const long long t_run0 = clock64();
     while (run_left > 0) {      // steps: one pending task each
       const uint64_t best = warp_max_u64(cur_key);
       if (best < floor_key) { reason = STOP_RESCAN; break; }      // a node outside the list might win: cannot certify
       // pop the task (allocate.go:130); the ord_task window is refilled every 32 steps
       const uint32_t pos = pos0 + popped;
-      if ((popped & 31u) == 0) {
-        __syncwarp();
-        if (pos + lane < jend) sm.rs.tasks[lane] = S.ord_task[pos + lane];
-        __syncwarp();
-      }
-      if (lane == 0) { c.tasks_processed += 1; c.pairs_logical += (unsigned long long)S.N; }
+      if ((popped & 31u) == 0) my_task = (pos + lane < jend) ? S.ord_task[pos + lane] : 0u;
+      const uint32_t task = __shfl_sync(FULL, my_task, popped & 31u);
       popped += 1;
       run_left -= 1;
       if (best == 0) { reason = STOP_NOFIT; break; }              // allocate.go:144-148
       const uint32_t owner = (uint32_t)__ffs(__ballot_sync(FULL, cur_key == best)) - 1u;
-      if (!__shfl_sync(FULL, next_valid ? 1 : 0, owner)) refresh();
-      const uint32_t bn = key_node(best);
-      const bool fits_idle = __shfl_sync(FULL, cur_fi ? 1 : 0, owner) != 0;
+      const unsigned ownbits = __shfl_sync(FULL, (next_valid ? 1u : 0u) | (cur_fi ? 2u : 0u), owner);
+      if (!(ownbits & 1u)) refresh();
+      const bool fits_idle = (ownbits & 2u) != 0;
       // commit: ssn.Allocate (session.go:235) or ssn.Pipeline (session.go:194) -> NodeInfo.AddTask (node_info.go:172-212):
       // the owner lane switches to its pre-evaluated next state
       if ((uint32_t)lane == owner) {
-        for (uint32_t k = 0; k < R; ++k) sm.used_add[k][lane] = KB_DADD(sm.used_add[k][lane], sm.cls.resreq[k]);
+        my_cnt += 1;
         which ^= 1u;
         cur_key = next_key; cur_fi = next_fi; next_valid = false; modified = true;
       }
       // AllocateFunc handlers of drf (drf.go:136-144) and proportion (proportion.go:213-222)
-      if (lane < R) {
-        sm.rs.jalloc[lane] = KB_DADD(sm.rs.jalloc[lane], sm.cls.resreq[lane]);
-        sm.rs.qalloc[lane] = KB_DADD(sm.rs.qalloc[lane], sm.cls.resreq[lane]);
-      }
+      jalloc = KB_DADD(jalloc, my_rq);
+      qalloc = KB_DADD(qalloc, my_rq);
       if (lane == 0) {
         kb_decision d;
-        d.node = (int32_t)bn;
+        d.node = (int32_t)key_node(best);
         d.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED;
         d.dispatched = 0; d.reserved = 0;
-        d.step = c.step;
+        d.step = step0 + placed;
         d.dispatch_step = 0xFFFFFFFFu;
-        S.dec[sm.rs.tasks[(popped - 1) & 31u]] = d;
-        c.step += 1;
-        if (fits_idle) { c.tasks_allocated += 1; sm.rs.ready += 1; } else c.tasks_pipelined += 1;
-        sm.rs.placed_total += 1;
+        S.dec[task] = d;
       }
       placed += 1;
-      __syncwarp();
+      n_alloc += fits_idle ? 1u : 0u;
       // allocate.go:185-188: a ready job yields after every task while tasks remain
-      const bool jr = !S.gang_ready || sm.rs.ready >= sm.rs.min_avail;     // ssn.JobReady
+      const bool jr = !S.gang_ready || (ready + (int32_t)n_alloc) >= min_avail;     // ssn.JobReady
       if (jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
     }
     // write the job-level state back, then run the control plane
     if (lane == 0) {
       S.job_pos[j] = pos0 + popped;
-      S.job_ready[j] = sm.rs.ready;
-      S.job_placed[j] = sm.rs.placed_total;
+      S.job_ready[j] = ready + (int32_t)n_alloc;
+      S.job_placed[j] += placed;
+      c.step = step0 + placed;
+      c.tasks_processed += popped;
+      c.pairs_logical += (unsigned long long)popped * S.N;
+      c.tasks_allocated += n_alloc;
+      c.tasks_pipelined += placed - n_alloc;
     }
     if (lane < R && placed) {
-      if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = sm.rs.jalloc[lane];
-      if (S.proportion_present) S.q_allocated[(size_t)lane * S.Q + q] = sm.rs.qalloc[lane];
+      if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = jalloc;
+      if (S.proportion_present) S.q_allocated[(size_t)lane * S.Q + q] = qalloc;
     }
     __syncwarp();
+    const long long t_run1 = clock64();
     if (lane == 0) {
       if (reason == STOP_RESCAN) c.rescans += 1;
       after_run(S, c, reason, placed);
+      const long long t_run2 = clock64();
+      c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
+      c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
     }
     __syncwarp();
     if (reason == STOP_RESCAN) break;
@@ -376,8 +370,11 @@ visit_kernel(const __grid_constant__ DevSession S) {
   if (modified) {
     const uint64_t (*src)[32] = sm.slot[which];
     for (uint32_t cc = 0; cc < ncols; ++cc) gt_mine[(size_t)cc * TILE_NODES] = src[cc][lane];
-    for (uint32_t k = 0; k < R; ++k)
-      S.node_used[(size_t)k * S.N + my_node] = KB_DADD(S.node_used[(size_t)k * S.N + my_node], sm.used_add[k][lane]);
+    for (uint32_t k = 0; k < R; ++k) {             // Used.Add(Resreq) once per placement (node_info.go:203)
+      double u = S.node_used[(size_t)k * S.N + my_node];
+      for (uint32_t i = 0; i < my_cnt; ++i) u = KB_DADD(u, sm.cls.resreq[k]);
+      S.node_used[(size_t)k * S.N + my_node] = u;
+    }
   }
   __syncwarp();
   if (lane == 0) {
