@@ -211,6 +211,9 @@ typedef struct kb_stats {
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,
  * and (world_size > 1) the NCCL communicator used for the per-run best-candidate exchange. */
 int kb_engine_create(const kb_engine_opts* opts, struct kb_engine** out);
+/* Fills `out128` (128 bytes) with a fresh ncclUniqueId (rank 0 calls it, the caller distributes it to the
+ * other ranks' kb_engine_opts.nccl_unique_id).  NCCL is dlopen'ed on first use: single-GPU use never needs it. */
+int kb_nccl_unique_id(void* out128);
 void kb_engine_destroy(struct kb_engine* e);
 
 /* Replaces framework.OpenSession's in-memory wiring (framework/framework.go:30-52): the snapshot

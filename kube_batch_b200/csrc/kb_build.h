@@ -188,7 +188,7 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 
-struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl; };
+struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf; };
 struct OffImm { size_t classes, ord_task, ord_class, ord_run, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
 
 struct BuiltSession {
@@ -200,6 +200,7 @@ struct BuiltSession {
   uint32_t total_dims_mask = 3;
   double total[KB_MAX_R] = {0};
   std::vector<int32_t> job_min_avail;
+  uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0;
 
   void bind(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     D.cf = hc.cf;
@@ -216,6 +217,8 @@ struct BuiltSession {
     D.dyn_jobs = (uint32_t*)(mb + om.dyn); D.q_allocated = (double*)(mb + om.q_alloc); D.q_share = (double*)(mb + om.q_share);
     D.qheap = (uint32_t*)(mb + om.qheap); D.dec = (kb_decision*)(mb + om.dec); D.cand = (uint64_t*)(mb + om.cand);
     D.ctl = (Ctl*)(mb + om.ctl);
+    D.rank = rank; D.world = world; D.tile_lo = tile_lo; D.tile_hi = tile_hi; D.nodes_per_rank = nodes_per_rank;
+    D.sendbuf = (uint64_t*)(mb + om.sendbuf); D.recvbuf = (uint64_t*)(mb + om.recvbuf);
     D.classes = (ClassRec*)(ib + oi.classes); D.ord_task = (uint32_t*)(ib + oi.ord_task); D.ord_class = (uint32_t*)(ib + oi.ord_class);
     D.ord_run = (uint32_t*)(ib + oi.ord_run);
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
@@ -226,7 +229,8 @@ struct BuiltSession {
 };
 
 // Everything kb_session_load does before touching the device.  `max_grid` = scan CTAs (SM count).
-inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e) {
+inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e,
+                         uint32_t rank = 0, uint32_t world = 1) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
@@ -306,7 +310,13 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   DevSession H{};            // host view: pointers into the slabs' host buffers
   OffMut& om = B.om; OffImm& oi = B.oi;
   const uint32_t GMAX = std::max(1u, max_grid);
-  const uint32_t grid = std::max(1u, std::min(NT, GMAX));
+  // shard = a contiguous block of tiles per rank (nodes are in canonical name order)
+  const uint32_t tiles_per_rank = (NT + world - 1) / std::max(1u, world);
+  B.rank = rank; B.world = std::max(1u, world);
+  B.tile_lo = std::min(NT, rank * tiles_per_rank);
+  B.tile_hi = std::min(NT, (rank + 1) * tiles_per_rank);
+  B.nodes_per_rank = std::max(1u, tiles_per_rank * (uint32_t)TILE_NODES);
+  const uint32_t grid = std::max(1u, std::min(B.tile_hi - B.tile_lo, GMAX));
   om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
   om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
   om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
@@ -322,6 +332,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   om.dec = mut.alloc((size_t)std::max(1u, T) * sizeof(kb_decision));
   om.cand = mut.alloc((size_t)grid * KTOP * 8);
   om.ctl = mut.alloc(sizeof(Ctl));
+  om.sendbuf = mut.alloc((size_t)(1 + ncols) * 32 * 8);
+  om.recvbuf = mut.alloc((size_t)std::max(1u, world) * (1 + ncols) * 32 * 8);
   oi.classes = imm.alloc((size_t)C * sizeof(ClassRec));
   oi.ord_task = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.ord_class = imm.alloc((size_t)std::max(1u, To) * 4);

@@ -81,6 +81,12 @@ struct DevSession {
   kb_decision* dec;       // [T]
   uint64_t* cand;         // [grid][KTOP] per-CTA candidate lists of the current scan
   Ctl* ctl;
+  // node-axis sharding.  Every rank holds the full (replicated) tables; a rank SCANS tiles
+  // [tile_lo, tile_hi) only, then the ranks all-gather their top-KTOP keys together with the candidates'
+  // node records and every rank replays identically, so the replicas never diverge.
+  uint32_t rank, world, tile_lo, tile_hi, nodes_per_rank;
+  uint64_t* sendbuf;      // [(1 + ncols) * 32]: keys[32], then columns [ncols][32]
+  uint64_t* recvbuf;      // [world] x the same
 };
 
 // ---- tile columns (u64 each, TILE_NODES entries per column) ----

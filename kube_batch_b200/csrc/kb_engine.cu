@@ -11,6 +11,7 @@
 //                   Ctl.done, runs the gang-commit prefix scan and copies the decisions back.
 // No CPU fallback exists: every decision is produced by the kernels.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <chrono>
@@ -31,9 +32,37 @@ using namespace kb;
 
 namespace {
 
+// ---- NCCL through dlopen (libnccl.so.2; prototypes per nccl.h 2.27) ----
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+struct NcclApi {
+  void* h = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int /*ncclDataType_t*/, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  std::string err;
+  bool load() {
+    if (h) return true;
+    h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { err = std::string("dlopen libnccl.so.2: ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    AllGather = (decltype(AllGather))dlsym(h, "ncclAllGather");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !CommDestroy || !AllGather || !GetErrorString) { err = "libnccl.so.2 lacks a required symbol"; h = nullptr; return false; }
+    return true;
+  }
+};
+NcclApi g_nccl;
+constexpr int kNcclUint64 = 5;   // ncclUint64 (nccl.h)
+
 }  // namespace
 
 struct kb_engine {
+  ncclComm_t comm = nullptr;
   int device = 0;
   int rank = 0, world = 1;
   cudaStream_t stream = nullptr;
@@ -58,11 +87,13 @@ struct kb_engine {
   std::vector<int32_t> job_min_avail_host;
   uint32_t gang_ready = 0;
   uint32_t scan_grid = 1;
-  size_t visit_smem = 0, tile_smem = 0;
+  size_t visit_smem = 0, tile_smem = 0, replay_smem = 0;
   float load_ms = 0;
   int sm_count = 148;
-  cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per session
+  cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
+  DevSession graph_dev{};              // kernel parameter the graph was captured with
+  size_t cap_mut = 0, cap_imm = 0, cap_dec = 0;   // capacities of the device / pinned buffers (reused across loads)
 };
 constexpr uint32_t BATCH = 64;
 
@@ -78,10 +109,14 @@ int fail(kb_engine* e, int code, const char* fmt, ...) {
 
 thread_local std::string g_create_err;
 
-void free_session(kb_engine* e) {
+void free_graph(kb_engine* e) {
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
   if (e->graph) cudaGraphDestroy(e->graph);
   e->graph_exec = nullptr; e->graph = nullptr;
+}
+void free_session(kb_engine* e) {
+  free_graph(e);
+  e->cap_mut = e->cap_imm = e->cap_dec = 0;
   if (e->d_mut) cudaFree(e->d_mut);
   if (e->d_pristine) cudaFree(e->d_pristine);
   if (e->d_imm) cudaFree(e->d_imm);
@@ -95,6 +130,16 @@ void free_session(kb_engine* e) {
 extern "C" {
 
 const char* kb_version(void) { return KB_VERSION_STRING; }
+
+int kb_nccl_unique_id(void* out128) {
+  if (!out128) return KB_E_BADARG;
+  if (!g_nccl.load()) { g_create_err = g_nccl.err; return KB_E_NCCL; }
+  ncclUniqueId id;
+  int rc = g_nccl.GetUniqueId(&id);
+  if (rc != 0) { g_create_err = std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(rc); return KB_E_NCCL; }
+  memcpy(out128, id.internal, sizeof id.internal);
+  return KB_OK;
+}
 
 const char* kb_status_str(int s) {
   switch (s) {
@@ -122,11 +167,13 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
     return KB_E_CUDA;
   }
   if (opts->device < 0 || opts->device >= ndev) { g_create_err = "device ordinal out of range"; return KB_E_BADARG; }
-  if (opts->world_size != 1 && opts->world_size != 0) {
-    g_create_err = "world_size > 1 needs the NCCL build of libkbgpu (node-axis sharding)"; return KB_E_NCCL; }
+  const int world = opts->world_size <= 0 ? 1 : opts->world_size;
+  if (world > 1 && (opts->rank < 0 || opts->rank >= world || !opts->nccl_unique_id)) {
+    g_create_err = "world_size > 1 needs 0 <= rank < world_size and a 128-byte nccl_unique_id"; return KB_E_BADARG; }
+  if (world > 1 && !g_nccl.load()) { g_create_err = g_nccl.err; return KB_E_NCCL; }
   kb_engine* e = new kb_engine();
   e->device = opts->device;
-  e->rank = 0; e->world = 1;
+  e->rank = world > 1 ? opts->rank : 0; e->world = world;
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
       (c = cudaMallocHost(&e->h_ctl, sizeof(Ctl))) != cudaSuccess) {
@@ -135,6 +182,12 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+  if (world > 1) {
+    ncclUniqueId id;
+    memcpy(id.internal, opts->nccl_unique_id, sizeof id.internal);
+    int rc = g_nccl.CommInitRank(&e->comm, world, id, e->rank);
+    if (rc != 0) { g_create_err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc); kb_engine_destroy(e); return KB_E_NCCL; }
+  }
   *out = e;
   return KB_OK;
 }
@@ -143,6 +196,7 @@ void kb_engine_destroy(kb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   free_session(e);
+  if (e->comm) g_nccl.CommDestroy(e->comm);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
@@ -154,10 +208,11 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   if (!e) return KB_E_BADARG;
   auto t_start = std::chrono::steady_clock::now();
   CUDA_TRY(e, cudaSetDevice(e->device));
-  free_session(e);
+  e->loaded = false;
   BuiltSession B;
   BuildErr be;
-  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be)) return fail(e, rc, "%s", be.msg.c_str());
+  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world))
+    return fail(e, rc, "%s", be.msg.c_str());
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q, C = B.C, NT = B.NT, ncols = B.ncols, To = B.To, grid = B.grid;
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;
   Slab& mut = B.mut; Slab& imm = B.imm;
@@ -166,10 +221,30 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
 
   // ---------------- upload ----------------
   e->mut_bytes = mut.host.size(); e->imm_bytes = imm.host.size();
-  CUDA_TRY(e, cudaMalloc(&e->d_mut, e->mut_bytes));
-  CUDA_TRY(e, cudaMalloc(&e->d_pristine, e->mut_bytes));
-  CUDA_TRY(e, cudaMalloc(&e->d_imm, e->imm_bytes));
-  CUDA_TRY(e, cudaMallocHost(&e->h_dec, std::max<size_t>(1, T) * sizeof(kb_decision)));
+  // buffers are reused across sessions (a scheduler loads one snapshot per cycle): grow-only
+  if (e->mut_bytes > e->cap_mut) {
+    if (e->d_mut) cudaFree(e->d_mut);
+    if (e->d_pristine) cudaFree(e->d_pristine);
+    e->d_mut = e->d_pristine = nullptr; e->cap_mut = 0;
+    const size_t cap = e->mut_bytes + e->mut_bytes / 4;
+    CUDA_TRY(e, cudaMalloc(&e->d_mut, cap));
+    CUDA_TRY(e, cudaMalloc(&e->d_pristine, cap));
+    e->cap_mut = cap;
+  }
+  if (e->imm_bytes > e->cap_imm) {
+    if (e->d_imm) cudaFree(e->d_imm);
+    e->d_imm = nullptr; e->cap_imm = 0;
+    const size_t cap = e->imm_bytes + e->imm_bytes / 4;
+    CUDA_TRY(e, cudaMalloc(&e->d_imm, cap));
+    e->cap_imm = cap;
+  }
+  const size_t dec_bytes = std::max<size_t>(1, T) * sizeof(kb_decision);
+  if (dec_bytes > e->cap_dec) {
+    if (e->h_dec) cudaFreeHost(e->h_dec);
+    e->h_dec = nullptr; e->cap_dec = 0;
+    CUDA_TRY(e, cudaMallocHost(&e->h_dec, dec_bytes + dec_bytes / 4));
+    e->cap_dec = dec_bytes + dec_bytes / 4;
+  }
   CUDA_TRY(e, cudaMemcpyAsync(e->d_pristine, mut.host.data(), e->mut_bytes, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(e->d_imm, imm.host.data(), e->imm_bytes, cudaMemcpyHostToDevice, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
@@ -189,11 +264,17 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch)
-  CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-  for (uint32_t i = 0; i < BATCH; ++i)
-    visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
-  CUDA_TRY(e, cudaStreamEndCapture(e->stream, &e->graph));
-  CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+  e->replay_smem = ((sizeof(VisitSmem) + 127) / 128) * 128;
+  CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
+  if (e->world == 1 && (!e->graph_exec || memcmp(&e->graph_dev, &e->dev, sizeof(DevSession)) != 0)) {
+    free_graph(e);
+    CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+    for (uint32_t i = 0; i < BATCH; ++i)
+      visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+    CUDA_TRY(e, cudaStreamEndCapture(e->stream, &e->graph));
+    CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
+    memcpy(&e->graph_dev, &e->dev, sizeof(DevSession));
+  }
   e->loaded = true;
   e->load_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_start).count();
   return KB_OK;
@@ -209,8 +290,21 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
   const uint64_t cap = 4ull * ((uint64_t)e->J + e->To) + 1024;
   for (;;) {
-    CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
-    launches += BATCH;
+    if (e->world == 1) {
+      CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
+      launches += BATCH;
+    } else {
+      // sharded node axis: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
+      const size_t cnt = (size_t)(1 + e->ncols) * 32;
+      for (uint32_t i = 0; i < BATCH; ++i) {
+        visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+        int rc = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream);
+        if (rc != 0) return fail(e, KB_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
+        replay_kernel<<<1, 32, e->replay_smem, e->stream>>>(e->dev);
+      }
+      CUDA_TRY(e, cudaGetLastError());
+      launches += 2 * BATCH;
+    }
     CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, e->dev.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (e->h_ctl->done) break;

@@ -118,116 +118,14 @@ struct VisitSmem {
 };
 
 // ---------------------------------------------------------------------------------------------
-// visit_kernel
+// Exact replay + control plane, executed by ONE warp.  sm.keys holds the merged candidate list of the
+// scan for class `cls_id` (sm.cls), sm.ctl a copy of the control block.  `rec_base`/`rec_stride` say
+// where THIS lane's candidate record can be read (column c at rec_base[c * rec_stride]): the local node
+// tiles on one GPU, the all-gathered records of the owning rank when the node axis is sharded.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS)
-visit_kernel(const __grid_constant__ DevSession S) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [VisitSmem][pad to 128][tile buffer 0][tile buffer 1]
-  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
-  const uint32_t tile_u64 = S.ncols * TILE_NODES;
-  const uint32_t tile_bytes = tile_u64 * 8u;
-  uint64_t* tilebuf = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(VisitSmem) + 127) / 128) * 128);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Ctl* gctl = S.ctl;
-  if (*((volatile uint32_t*)&gctl->done)) return;
-  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
-
-  // class record -> shared memory (broadcast reads afterwards)
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
-    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
-  }
-  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); }
-  __syncthreads();
-  const long long t_start = clock64();
-
-  // ---------------- scan: tiles blockIdx.x, +gridDim.x, ... double-buffered TMA ----------------
-  const uint32_t first = blockIdx.x, stride = gridDim.x;
-  uint32_t n_local = first < S.NT ? (S.NT - first + stride - 1) / stride : 0;
-  if (tid == 0 && n_local > 0) {
-    mbar_expect_tx(&sm.mbar[0], tile_bytes);
-    tma_load_1d(tilebuf, S.tiles + (size_t)first * tile_u64, tile_bytes, &sm.mbar[0]);
-  }
-  uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
-  for (uint32_t it = 0; it < n_local; ++it) {
-    const uint32_t b = it & 1u;
-    if (it + 1 < n_local) {
-      __syncthreads();                       // every thread is done reading the other buffer (iteration it-1)
-      if (tid == 0) {
-        const uint32_t nb = b ^ 1u;
-        mbar_expect_tx(&sm.mbar[nb], tile_bytes);
-        tma_load_1d(tilebuf + (size_t)nb * tile_u64, S.tiles + (size_t)(first + (it + 1) * stride) * tile_u64, tile_bytes, &sm.mbar[nb]);
-      }
-    }
-    mbar_wait(&sm.mbar[b], (it >> 1) & 1u);
-    const uint32_t t = first + it * stride;
-    const uint32_t node = t * TILE_NODES + tid;
-    uint64_t key = 0;
-    if (node < S.N) {
-      ColAcc acc{tilebuf + (size_t)b * tile_u64, (uint32_t)tid, TILE_NODES, S.cf.R, S.cf.W};
-      key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
-    }
-    // K3, warp level: skip the networks when nothing in this warp can enter its list
-    const uint64_t thr = __shfl_sync(FULL, mylist, 31);
-    if (__any_sync(FULL, key > thr)) {
-      key = warp_sort_desc(key, lane);
-      mylist = it == 0 ? key : warp_merge_top32(mylist, key, lane);
-    }
-  }
-  // CTA level: warp 0 folds the other warps' lists in, then publishes the CTA's list
-  sm.wlist[warp][lane] = mylist;
-  __syncthreads();
-  if (warp == 0) {
-#pragma unroll
-    for (int w = 1; w < SCAN_THREADS / 32; ++w) mylist = warp_merge_top32(mylist, sm.wlist[w][lane], lane);
-    S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
-    sm.keys[lane] = mylist;
-    __threadfence();
-    __syncwarp();                            // every lane's list entry is fenced before the ticket is taken
-    if (lane == 0) {
-      const uint32_t ticket = atomicAdd(&gctl->arrive, 1u);
-      sm.is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
-    }
-  }
-  __syncthreads();
-  if (!sm.is_last) return;
-  __threadfence();
-  const long long t_scan = clock64();
-
-  // ---------------- K3: merge the per-CTA lists: 4 warps, each folds every 4th list ----------------
-  if (gridDim.x > 1) {
-    const uint32_t G = gridDim.x;
-    uint64_t acc = 0;
-    uint32_t g = warp;
-    uint64_t nxt = g < G ? __ldcg(&S.cand[(size_t)g * KTOP + lane]) : 0ull;
-    bool firstl = true;
-    while (g < G) {
-      const uint64_t cur = nxt;
-      const uint32_t g2 = g + SCAN_THREADS / 32;
-      nxt = g2 < G ? __ldcg(&S.cand[(size_t)g2 * KTOP + lane]) : 0ull;     // prefetch the next list
-      const uint64_t thr = __shfl_sync(FULL, acc, 31);
-      const uint64_t head = __shfl_sync(FULL, cur, 0);
-      if (firstl) { acc = cur; firstl = false; }
-      else if (head > thr) acc = warp_merge_top32(acc, cur, lane);
-      g = g2;
-    }
-    __syncthreads();                         // wlist is being reused
-    sm.wlist[warp][lane] = acc;
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-      for (int w = 1; w < SCAN_THREADS / 32; ++w) acc = warp_merge_top32(acc, sm.wlist[w][lane], lane);
-      sm.keys[lane] = acc;
-    }
-  }
-  if (tid == 0) sm.ctl = *gctl;
-  __syncthreads();
-  if (warp != 0) return;
-
-  // ---------------- exact replay + control: warp 0 only ----------------
+__device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& sm, Ctl* gctl, const int lane, const uint32_t cls_id,
+                                                const uint64_t* rec_base, const uint32_t rec_stride,
+                                                const long long t_start, const long long t_scan) {
   // Lane l OWNS candidate l of the merged list: its node record lives in two shared-memory slots
   // (current state / state after one more placement of this class) and the lane keeps the packed key
   // of both.  A step is then a warp arg-max over the current keys; the chosen lane swaps to its
@@ -246,7 +144,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
   bool cur_fi = false, next_fi = false, next_valid = false, modified = false;
   uint64_t next_key = 0;
   if (have) {
-    for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(gt_mine + (size_t)cc * TILE_NODES);
+    for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(rec_base + (size_t)cc * rec_stride);
     ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
     cur_fi = res_less_equal(R, [&](uint32_t k) { return sm.cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
   }
@@ -385,6 +283,174 @@ visit_kernel(const __grid_constant__ DevSession S) {
     c.cyc_total += (unsigned long long)(t_end - t_start);
     c.arrive = 0; *gctl = c;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// visit_kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+visit_kernel(const __grid_constant__ DevSession S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [VisitSmem][pad to 128][tile buffer 0][tile buffer 1]
+  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
+  const uint32_t tile_u64 = S.ncols * TILE_NODES;
+  const uint32_t tile_bytes = tile_u64 * 8u;
+  uint64_t* tilebuf = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(VisitSmem) + 127) / 128) * 128);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctl* gctl = S.ctl;
+  if (*((volatile uint32_t*)&gctl->done)) return;
+  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
+
+  // class record -> shared memory (broadcast reads afterwards)
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); }
+  __syncthreads();
+  const long long t_start = clock64();
+
+  // ---------------- scan: tiles blockIdx.x, +gridDim.x, ... double-buffered TMA ----------------
+  const uint32_t first = S.tile_lo + blockIdx.x, stride = gridDim.x;
+  uint32_t n_local = first < S.tile_hi ? (S.tile_hi - first + stride - 1) / stride : 0;
+  if (tid == 0 && n_local > 0) {
+    mbar_expect_tx(&sm.mbar[0], tile_bytes);
+    tma_load_1d(tilebuf, S.tiles + (size_t)first * tile_u64, tile_bytes, &sm.mbar[0]);
+  }
+  uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
+  for (uint32_t it = 0; it < n_local; ++it) {
+    const uint32_t b = it & 1u;
+    if (it + 1 < n_local) {
+      __syncthreads();                       // every thread is done reading the other buffer (iteration it-1)
+      if (tid == 0) {
+        const uint32_t nb = b ^ 1u;
+        mbar_expect_tx(&sm.mbar[nb], tile_bytes);
+        tma_load_1d(tilebuf + (size_t)nb * tile_u64, S.tiles + (size_t)(first + (it + 1) * stride) * tile_u64, tile_bytes, &sm.mbar[nb]);
+      }
+    }
+    mbar_wait(&sm.mbar[b], (it >> 1) & 1u);
+    const uint32_t t = first + it * stride;
+    const uint32_t node = t * TILE_NODES + tid;
+    uint64_t key = 0;
+    if (node < S.N) {
+      ColAcc acc{tilebuf + (size_t)b * tile_u64, (uint32_t)tid, TILE_NODES, S.cf.R, S.cf.W};
+      key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
+    }
+    // K3, warp level: skip the networks when nothing in this warp can enter its list
+    const uint64_t thr = __shfl_sync(FULL, mylist, 31);
+    if (__any_sync(FULL, key > thr)) {
+      key = warp_sort_desc(key, lane);
+      mylist = it == 0 ? key : warp_merge_top32(mylist, key, lane);
+    }
+  }
+  // CTA level: warp 0 folds the other warps' lists in, then publishes the CTA's list
+  sm.wlist[warp][lane] = mylist;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < SCAN_THREADS / 32; ++w) mylist = warp_merge_top32(mylist, sm.wlist[w][lane], lane);
+    S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
+    sm.keys[lane] = mylist;
+    __threadfence();
+    __syncwarp();                            // every lane's list entry is fenced before the ticket is taken
+    if (lane == 0) {
+      const uint32_t ticket = atomicAdd(&gctl->arrive, 1u);
+      sm.is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+  }
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  const long long t_scan = clock64();
+
+  // ---------------- K3: merge the per-CTA lists: 4 warps, each folds every 4th list ----------------
+  if (gridDim.x > 1) {
+    const uint32_t G = gridDim.x;
+    uint64_t acc = 0;
+    uint32_t g = warp;
+    uint64_t nxt = g < G ? __ldcg(&S.cand[(size_t)g * KTOP + lane]) : 0ull;
+    bool firstl = true;
+    while (g < G) {
+      const uint64_t cur = nxt;
+      const uint32_t g2 = g + SCAN_THREADS / 32;
+      nxt = g2 < G ? __ldcg(&S.cand[(size_t)g2 * KTOP + lane]) : 0ull;     // prefetch the next list
+      const uint64_t thr = __shfl_sync(FULL, acc, 31);
+      const uint64_t head = __shfl_sync(FULL, cur, 0);
+      if (firstl) { acc = cur; firstl = false; }
+      else if (head > thr) acc = warp_merge_top32(acc, cur, lane);
+      g = g2;
+    }
+    __syncthreads();                         // wlist is being reused
+    sm.wlist[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+      for (int w = 1; w < SCAN_THREADS / 32; ++w) acc = warp_merge_top32(acc, sm.wlist[w][lane], lane);
+      sm.keys[lane] = acc;
+    }
+  }
+  if (S.world > 1) {
+    // sharded node axis: publish this rank's candidates WITH their node records; the replay happens in
+    // replay_kernel after the all-gather
+    __syncthreads();
+    if (warp == 0) {
+      const uint64_t k = sm.keys[lane];
+      S.sendbuf[lane] = k;
+      if (k) {
+        const uint32_t n = key_node(k);
+        const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
+        for (uint32_t cc = 0; cc < S.ncols; ++cc) S.sendbuf[(size_t)(1 + cc) * 32 + lane] = __ldcg(rec + (size_t)cc * TILE_NODES);
+      }
+    }
+    return;
+  }
+  if (tid == 0) sm.ctl = *gctl;
+  __syncthreads();
+  if (warp != 0) return;
+
+  // ---------------- exact replay + control: warp 0 only ----------------
+  {
+    const uint32_t n = key_node(sm.keys[lane]);
+    const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
+    replay_epilogue(S, sm, gctl, lane, cls_id, rec, TILE_NODES, t_start, t_scan);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// replay_kernel (sharded node axis only): one warp merges the ranks' all-gathered candidate lists, each
+// lane finds the record of its candidate in the owning rank's block and the shared epilogue replays.
+// Every rank runs this identically on identical inputs, so every replica applies the same updates.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+replay_kernel(const __grid_constant__ DevSession S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
+  const int lane = threadIdx.x;
+  Ctl* gctl = S.ctl;
+  if (*((volatile uint32_t*)&gctl->done)) return;
+  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+    for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
+  }
+  const long long t_start = clock64();
+  const size_t rank_u64 = (size_t)(1 + S.ncols) * 32;
+  uint64_t acc = __ldcg(S.recvbuf + lane);
+  for (uint32_t r = 1; r < S.world; ++r) acc = warp_merge_top32(acc, __ldcg(S.recvbuf + r * rank_u64 + lane), lane);
+  sm.keys[lane] = acc;
+  const uint32_t node = key_node(acc);
+  uint32_t owner = node / S.nodes_per_rank;
+  owner = owner < S.world ? owner : S.world - 1;
+  uint32_t idx = 0;
+  if (acc)
+    for (uint32_t i = 0; i < 32; ++i)
+      if (__ldcg(S.recvbuf + owner * rank_u64 + i) == acc) idx = i;
+  if (lane == 0) sm.ctl = *gctl;
+  __syncwarp();
+  replay_epilogue(S, sm, gctl, lane, cls_id, S.recvbuf + owner * rank_u64 + 32 + idx, 32u, t_start, clock64());
 }
 
 // ---------------------------------------------------------------------------------------------

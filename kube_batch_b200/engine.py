@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
 EXPORTS = [
     "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_predicate_score",
     "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
+    "kb_nccl_unique_id",
 ]
 
 
@@ -142,6 +143,16 @@ class Engine:
                                           _p(out["queue_share"], C.c_double), _p(out["queue_deserved"], C.c_double),
                                           _p(out["queue_allocated"], C.c_double)), "kb_order_state")
         return out
+
+
+def nccl_unique_id() -> bytes:
+    """A fresh ncclUniqueId (rank 0); broadcast it and pass it to every rank's Engine(...)."""
+    L = load_library()
+    buf = (C.c_char * 128)()
+    rc = L.kb_nccl_unique_id(C.cast(buf, C.c_void_p))
+    if rc != 0:
+        raise KbError(rc, "kb_nccl_unique_id: " + L.kb_last_error(None).decode())
+    return bytes(buf.raw)
 
 
 def key_node(key: np.ndarray) -> np.ndarray:

@@ -59,8 +59,11 @@ class Snapshot:
             assert len(np.unique(self.task_uid_rank)) == self.T
 
     def to_c(self):
-        """Return (kb_snapshot, keepalive). The struct points into this object's arrays."""
-        self.validate()
+        """Return (kb_snapshot, keepalive). The struct points into this object's arrays.
+        Validation runs once per object (call `invalidate()` after editing arrays in place)."""
+        if not getattr(self, "_validated", False):
+            self.validate()
+            self._validated = True
         s = abi.kb_snapshot()
         s.abi_version = abi.KB_ABI_VERSION
         s.R, s.W, s.N, s.T, s.J, s.Q = self.R, self.W, self.N, self.T, self.J, self.Q
@@ -73,6 +76,9 @@ class Snapshot:
             keep.append(a)
             setattr(s, name, a.ctypes.data_as(ptr))
         return s, keep
+
+    def invalidate(self) -> None:
+        self._validated = False
 
     def job_of_task(self) -> np.ndarray:
         j = np.zeros(self.T, dtype=np.int64)

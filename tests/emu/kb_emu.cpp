@@ -1,10 +1,15 @@
 // kb_emu.cpp — CPU emulation of the DEVICE ALGORITHM (test infrastructure, never shipped).
 //
 // Compiles the product's host/device-shared headers (kb_core.h, kb_ctl.h, kb_build.h) with g++ and
-// re-enacts visit_kernel step by step in one thread: scan of the node tiles for the current class ->
-// exact top-KTOP list -> replay with the lane-owned-candidate / look-ahead / certification rules -> control plane ->
-// gang-commit prefix rule.  It shares NO code with oracle/ and lets `-m "not gpu"` tests check the
-// engine's logic (everything except the CUDA thread mechanics) against the oracle without a GPU.
+// re-enacts the kernels step by step in one thread:
+//   scan    (visit_kernel's scan + merge)  this rank's tiles -> exact top-KTOP keys + their node records
+//   replay  (replay_epilogue)              merge the ranks' lists, lane-owned candidates with look-ahead,
+//                                          certification rule, AddTask bookkeeping, control plane
+//   finish  (gang_commit_kernel)           per-PodGroup prefix rule
+// With world == 1 scan feeds replay directly; with world > 1 the caller all-gathers the send buffers
+// (tests use torch.distributed/gloo) exactly like ncclAllGather does between the two kernels.
+// It shares NO code with oracle/ and lets `-m "not gpu"` tests check the engine's logic (everything except
+// the CUDA thread mechanics) against the oracle without a GPU.
 #include <algorithm>
 #include <cstring>
 #include <string>
@@ -17,11 +22,8 @@ using namespace kb;
 namespace {
 thread_local std::string g_err;
 
-struct Slot {                     // one dirty node: a private copy of its tile columns
-  uint32_t node;
-  uint64_t col[2 * KB_MAX_R + 6 + 3 * KB_MAX_W];
-  double used_add[KB_MAX_R];
-};
+constexpr uint32_t MAXC = 2 * KB_MAX_R + 6 + 3 * KB_MAX_W;
+struct Slot { uint64_t col[MAXC]; };
 struct SlotAcc {
   const Slot* s; uint32_t R, W;
   uint64_t col(uint32_t c) const { return s->col[c]; }
@@ -39,40 +41,72 @@ struct SlotAcc {
   uint64_t ports(uint32_t w) const { return col(col_ports(R, W, w)); }
 };
 
-// one visit_kernel launch
-void emulate_launch(const DevSession& S) {
+struct Emu {
+  BuiltSession B;
+  DevSession S{};
+  uint32_t launches = 0;
+};
+
+// visit_kernel, scan + merge + (sharded) pack: keys[32] then columns [ncols][32]
+void emu_scan(Emu& E, uint64_t* sendbuf) {
+  const DevSession& S = E.S;
+  const Ctl& c = *S.ctl;
+  const size_t cnt = (size_t)(1 + S.ncols) * 32;
+  std::fill(sendbuf, sendbuf + cnt, 0ull);
+  if (c.done) return;
+  const ClassRec& cls = S.classes[c.cur_class];
+  const uint32_t R = S.cf.R, W = S.cf.W;
+  const size_t tile_u64 = (size_t)S.ncols * TILE_NODES;
+  std::vector<uint64_t> keys;
+  for (uint32_t t = S.tile_lo; t < S.tile_hi; ++t)
+    for (uint32_t i = 0; i < TILE_NODES; ++i) {
+      const uint32_t n = t * TILE_NODES + i;
+      if (n >= S.N) break;
+      TileAcc acc{S.tiles + (size_t)t * tile_u64, i, R, W};
+      uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr);
+      if (k) keys.push_back(k);
+    }
+  std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+  for (uint32_t l = 0; l < 32 && l < keys.size(); ++l) {
+    sendbuf[l] = keys[l];
+    const uint32_t n = key_node(keys[l]);
+    const uint64_t* gt = S.tiles + (size_t)(n / TILE_NODES) * tile_u64 + (n % TILE_NODES);
+    for (uint32_t cc = 0; cc < S.ncols; ++cc) sendbuf[(size_t)(1 + cc) * 32 + l] = gt[(size_t)cc * TILE_NODES];
+  }
+}
+
+// replay_kernel / replay_epilogue
+void emu_replay(Emu& E, const uint64_t* recvbuf) {
+  const DevSession& S = E.S;
   Ctl& c = *S.ctl;
+  E.launches += 1;
   if (c.done) return;
   const uint32_t cls_id = c.cur_class;
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;
-  // scan + K3
-  std::vector<uint64_t> keys;
-  for (uint32_t n = 0; n < S.N; ++n) {
-    TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
-    uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr);
-    if (k) keys.push_back(k);
-  }
-  std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
-  uint64_t L[KTOP];
-  for (int i = 0; i < KTOP; ++i) L[i] = i < (int)keys.size() ? keys[i] : 0;
+  const size_t rank_u64 = (size_t)(1 + ncols) * 32;
+  // merge the ranks' lists
+  struct Src { uint64_t key; uint32_t rank, idx; };
+  std::vector<Src> all;
+  for (uint32_t r = 0; r < S.world; ++r)
+    for (uint32_t i = 0; i < 32; ++i) {
+      uint64_t k = recvbuf[r * rank_u64 + i];
+      if (k) all.push_back({k, r, i});
+    }
+  std::sort(all.begin(), all.end(), [](const Src& a, const Src& b) { return a.key > b.key; });
   c.scans += 1; c.pairs_scanned += S.N;
 
-  // lane-owned candidates with a pre-evaluated look-ahead state (mirrors visit_kernel's epilogue)
   struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = false, modified = false;
-                uint64_t cur_key = 0, next_key = 0; uint32_t node = 0; Slot st[2]; int which = 0; };
+                uint64_t cur_key = 0, next_key = 0; uint32_t node = 0, cnt = 0; Slot st[2]; int which = 0; };
   std::vector<Cand> cand(KTOP);
-  const uint64_t floor_key = L[KTOP - 1];
-  for (int l = 0; l < KTOP; ++l) {
+  const uint64_t floor_key = all.size() >= (size_t)KTOP ? all[KTOP - 1].key : 0ull;
+  for (int l = 0; l < KTOP && l < (int)all.size(); ++l) {
     Cand& cd = cand[l];
-    cd.cur_key = L[l]; cd.have = L[l] != 0;
-    if (!cd.have) continue;
-    cd.node = key_node(L[l]);
-    const uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
-    for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = gt[(size_t)cc * TILE_NODES];
-    for (auto& x : cd.st[0].used_add) x = 0;
-    cd.st[0].node = cd.st[1].node = cd.node;
+    cd.cur_key = all[l].key; cd.have = true;
+    cd.node = key_node(cd.cur_key);
+    const uint64_t* rec = recvbuf + all[l].rank * rank_u64 + 32 + all[l].idx;
+    for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = rec[(size_t)cc * 32];
     SlotAcc acc{&cd.st[0], R, W};
     cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
   }
@@ -113,11 +147,10 @@ void emulate_launch(const DevSession& S) {
       Cand& cd = cand[owner];
       if (!cd.next_valid) refresh();
       const bool fits_idle = cd.cur_fi;
-      const uint32_t bn = key_node(best);
-      for (uint32_t k = 0; k < R; ++k) cd.st[0].used_add[k] += cls.resreq[k];
+      cd.cnt += 1;
       cd.which ^= 1; cd.cur_key = cd.next_key; cd.cur_fi = cd.next_fi; cd.next_valid = false; cd.modified = true;
       kb_decision dd;
-      dd.node = (int32_t)bn; dd.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED; dd.dispatched = 0; dd.reserved = 0;
+      dd.node = (int32_t)key_node(best); dd.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED; dd.dispatched = 0; dd.reserved = 0;
       dd.step = c.step; dd.dispatch_step = 0xFFFFFFFFu;
       S.dec[S.ord_task[pos]] = dd;
       c.step += 1;
@@ -131,17 +164,18 @@ void emulate_launch(const DevSession& S) {
     after_run(S, c, reason, placed);
     if (reason == STOP_RESCAN) break;
   }
-  for (auto& cd : cand) {
+  for (auto& cd : cand) {          // every replica writes every modified candidate back
     if (!cd.modified) continue;
     const Slot& src = cd.st[cd.which];
     uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
     for (uint32_t cc = 0; cc < ncols; ++cc) gt[(size_t)cc * TILE_NODES] = src.col[cc];
-    for (uint32_t r = 0; r < R; ++r) S.node_used[(size_t)r * S.N + cd.node] += cd.st[0].used_add[r];
+    for (uint32_t r = 0; r < R; ++r)
+      for (uint32_t i = 0; i < cd.cnt; ++i) S.node_used[(size_t)r * S.N + cd.node] += cls.resreq[r];
   }
 }
 
 // gang_commit_kernel, serially
-void emulate_gang_commit(const DevSession& S, const int32_t* ready0) {
+void emu_gang_commit(const DevSession& S, const int32_t* ready0) {
   for (uint32_t j = 0; j < S.J; ++j) {
     const uint32_t lo = S.job_ord_off[j], hi = S.job_pos[j];
     const int32_t need = S.gang_ready ? S.job_min_avail[j] - ready0[j] : 0;
@@ -166,23 +200,27 @@ extern "C" {
 
 const char* kbemu_last_error(void) { return g_err.c_str(); }
 
-int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, kb_decision* out, kb_stats* stats,
-                   double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
-                   int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
-                   double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
-  BuiltSession B;
+void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world) {
+  Emu* E = new Emu();
   BuildErr be;
-  if (int rc = build_session(snap, conf, 148, B, &be)) { g_err = be.msg; return rc; }
-  DevSession S{};
-  B.bind(S, B.mut.host.data(), B.imm.host.data());
-  const int32_t* ready0 = (const int32_t*)(B.imm.host.data() + B.oi.job_ready0);
-  uint64_t guard = 4ull * ((uint64_t)B.J + B.To) + 1024;
-  uint32_t launches = 0;
-  while (!S.ctl->done) {
-    emulate_launch(S);
-    if (++launches > guard) { g_err = "emulated cycle did not terminate"; return KB_E_STATE; }
-  }
-  emulate_gang_commit(S, ready0);
+  if (build_session(snap, conf, 148, E->B, &be, rank, world)) { g_err = be.msg; delete E; return nullptr; }
+  E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
+  return E;
+}
+void kbemu_destroy(void* h) { delete (Emu*)h; }
+int kbemu_done(void* h) { return ((Emu*)h)->S.ctl->done ? 1 : 0; }
+uint32_t kbemu_buf_u64(void* h) { return (1 + ((Emu*)h)->S.ncols) * 32; }
+void kbemu_scan(void* h, uint64_t* sendbuf) { emu_scan(*(Emu*)h, sendbuf); }
+void kbemu_replay(void* h, const uint64_t* recvbuf) { emu_replay(*(Emu*)h, recvbuf); }
+
+int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
+                 double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                 int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                 double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
+  Emu& E = *(Emu*)h;
+  const DevSession& S = E.S;
+  const BuiltSession& B = E.B;
+  emu_gang_commit(S, (const int32_t*)(B.imm.host.data() + B.oi.job_ready0));
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q;
   if (out) memcpy(out, S.dec, (size_t)T * sizeof(kb_decision));
   const size_t tile_u64 = (size_t)B.ncols * TILE_NODES;
@@ -211,12 +249,33 @@ int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, kb_decis
     memset(stats, 0, sizeof *stats);
     stats->pairs_logical = c.pairs_logical; stats->pairs_scanned = c.pairs_scanned; stats->pairs_replayed = c.pairs_replayed;
     stats->tasks_processed = c.tasks_processed; stats->tasks_allocated = c.tasks_allocated; stats->tasks_pipelined = c.tasks_pipelined;
-    stats->visits = c.visits; stats->kernel_launches = launches; stats->n_classes = B.C;
+    stats->visits = c.visits; stats->kernel_launches = E.launches; stats->n_classes = B.C;
+    stats->scans = c.scans; stats->rescans = c.rescans;
     uint32_t jr = 0;
     for (uint32_t j = 0; j < J; ++j) if (S.job_placed[j] && ssn_job_ready(S, j)) ++jr;
     stats->jobs_ready = jr;
   }
   return KB_OK;
+}
+
+// single-rank convenience: the whole cycle
+int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, kb_decision* out, kb_stats* stats,
+                   double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                   int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                   double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
+  Emu* E = (Emu*)kbemu_create(snap, conf, 0, 1);
+  if (!E) return KB_E_BADARG;
+  std::vector<uint64_t> buf(kbemu_buf_u64(E));
+  const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To) + 1024;
+  while (!E->S.ctl->done) {
+    emu_scan(*E, buf.data());
+    emu_replay(*E, buf.data());
+    if (E->launches > guard) { g_err = "emulated cycle did not terminate"; delete E; return KB_E_STATE; }
+  }
+  int rc = kbemu_finish(E, out, stats, node_idle, node_releasing, node_used, node_pods, node_nz_cpu, node_nz_mem, node_ports,
+                        job_share, job_ready, queue_share, queue_deserved, queue_allocated);
+  delete E;
+  return rc;
 }
 
 }  // extern "C"

@@ -87,3 +87,63 @@ def emu_states(e: kbo.OracleOut):
     os_ = dict(job_share=e.job_share, job_ready=e.job_ready, queue_share=e.queue_share, queue_deserved=e.queue_deserved,
                queue_allocated=e.queue_allocated)
     return ns, os_
+
+
+# ------------------------------------------------------------------------------------------------
+# sharded node axis on CPU: one process per rank, torch.distributed / gloo instead of NCCL
+# ------------------------------------------------------------------------------------------------
+def emu_sharded_rank(rank: int, world: int, port: int, snap: Snapshot, conf: PluginConf):
+    """Run the scan -> all-gather -> replay chain of the multi-GPU path with the CPU emulation and gloo.
+    Returns the same container as emu_allocate (every rank holds the full, identical result)."""
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        L = emu_lib()
+        L.kbemu_create.restype = C.c_void_p
+        L.kbemu_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+        L.kbemu_buf_u64.argtypes = [C.c_void_p]
+        L.kbemu_buf_u64.restype = C.c_uint32
+        for f in ("kbemu_scan", "kbemu_replay"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+            getattr(L, f).restype = None
+        L.kbemu_done.argtypes = [C.c_void_p]
+        L.kbemu_destroy.argtypes = [C.c_void_p]
+        cs, k1 = snap.to_c()
+        cc, k2 = conf.to_c()
+        h = L.kbemu_create(C.addressof(cs), C.addressof(cc), rank, world)
+        if not h:
+            raise RuntimeError(L.kbemu_last_error().decode())
+        n = L.kbemu_buf_u64(h)
+        send = torch.zeros(n, dtype=torch.int64)
+        recv = torch.zeros(world * n, dtype=torch.int64)
+        guard = 0
+        while not L.kbemu_done(h):
+            L.kbemu_scan(h, C.c_void_p(send.data_ptr()))
+            dist.all_gather_into_tensor(recv, send)          # == ncclAllGather(sendbuf, recvbuf, ...)
+            L.kbemu_replay(h, C.c_void_p(recv.data_ptr()))
+            guard += 1
+            assert guard < 10_000_000
+        R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
+        dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+        st = abi.kb_stats()
+        out = kbo.OracleOut(
+            decisions=dec, result=st,
+            node_idle=np.zeros((R, N)), node_releasing=np.zeros((R, N)), node_used=np.zeros((R, N)),
+            node_pods=np.zeros(N, dtype=np.int32), node_nz_cpu=np.zeros(N, dtype=np.int64),
+            node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
+            job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
+            queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
+        L.kbemu_finish.argtypes = [C.c_void_p] + [C.c_void_p] * 14
+        L.kbemu_finish(h, dec.ctypes.data, C.addressof(st), out.node_idle.ctypes.data, out.node_releasing.ctypes.data,
+                       out.node_used.ctypes.data, out.node_pods.ctypes.data, out.node_nz_cpu.ctypes.data,
+                       out.node_nz_mem.ctypes.data, out.node_ports.ctypes.data, out.job_share.ctypes.data,
+                       out.job_ready.ctypes.data, out.queue_share.ctypes.data, out.queue_deserved.ctypes.data,
+                       out.queue_allocated.ctypes.data)
+        out.decisions = dec[:T]
+        L.kbemu_destroy(h)
+        return out
+    finally:
+        dist.destroy_process_group()
