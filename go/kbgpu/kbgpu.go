@@ -1,0 +1,75 @@
+// Package kbgpu binds libkbgpu.so (include/kbgpu.h) into kube-batch through cgo.
+//
+// NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Go toolchain.  The file is the binding a
+// kube-batch maintainer adds under pkg/scheduler/kbgpu; everything below the C ABI is exercised through
+// the same ABI from Python/ctypes (tests/) and C (tests/test_abi.py).
+package kbgpu
+
+/*
+#cgo CFLAGS: -I${SRCDIR}/../../include
+#cgo LDFLAGS: -L${SRCDIR}/../../kube_batch_b200 -lkbgpu
+#include <stdlib.h>
+#include "kbgpu.h"
+*/
+import "C"
+
+import (
+	"fmt"
+	"unsafe"
+)
+
+// Engine wraps one kb_engine (one CUDA device, one session in flight — like the single runOnce goroutine).
+type Engine struct{ h *C.struct_kb_engine }
+
+func NewEngine(device int) (*Engine, error) {
+	opts := C.kb_engine_opts{abi_version: C.KB_ABI_VERSION, device: C.int32_t(device), rank: 0, world_size: 1}
+	var h *C.struct_kb_engine
+	if rc := C.kb_engine_create(&opts, &h); rc != 0 {
+		return nil, fmt.Errorf("kb_engine_create: %s (%s)", C.GoString(C.kb_last_error(nil)), C.GoString(C.kb_status_str(rc)))
+	}
+	return &Engine{h: h}, nil
+}
+
+func (e *Engine) Close() { C.kb_engine_destroy(e.h) }
+
+func (e *Engine) err(what string, rc C.int) error {
+	return fmt.Errorf("%s: %s (%s)", what, C.GoString(C.kb_last_error(e.h)), C.GoString(C.kb_status_str(rc)))
+}
+
+// Load hands the flattened snapshot + tiers to the device.  kb_session_load copies everything before it
+// returns, so passing pointers into Go slices for the duration of the call is within the cgo rules.
+func (e *Engine) Load(f *Flat, tiers []C.kb_tier) error {
+	snap := f.cSnapshot() // fills a C.kb_snapshot whose pointers alias f's slices (pinned for the call by cgo)
+	conf := C.kb_plugin_conf{n_tiers: C.uint32_t(len(tiers))}
+	if len(tiers) > 0 {
+		conf.tiers = &tiers[0]
+	}
+	if rc := C.kb_session_load(e.h, &snap, &conf); rc != 0 {
+		return e.err("kb_session_load", rc)
+	}
+	return nil
+}
+
+// Decision mirrors kb_decision.
+type Decision struct {
+	Node         int32
+	Kind         uint8 // 0 none, 1 allocated, 2 pipelined, 3 skipped (BestEffort)
+	Dispatched   bool
+	Step         uint32
+	DispatchStep uint32
+}
+
+// Allocate runs the whole allocate cycle on the GPU and returns one decision per flattened task.
+func (e *Engine) Allocate(nTasks int) ([]Decision, error) {
+	raw := make([]C.kb_decision, nTasks+1)
+	var st C.kb_stats
+	if rc := C.kb_allocate(e.h, (*C.kb_decision)(unsafe.Pointer(&raw[0])), &st); rc != 0 {
+		return nil, e.err("kb_allocate", rc)
+	}
+	out := make([]Decision, nTasks)
+	for i := range out {
+		out[i] = Decision{Node: int32(raw[i].node), Kind: uint8(raw[i].kind), Dispatched: raw[i].dispatched != 0,
+			Step: uint32(raw[i].step), DispatchStep: uint32(raw[i].dispatch_step)}
+	}
+	return out, nil
+}

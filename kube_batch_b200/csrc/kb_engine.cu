@@ -266,14 +266,31 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch)
   e->replay_smem = ((sizeof(VisitSmem) + 127) / 128) * 128;
   CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
-  if (e->world == 1 && (!e->graph_exec || memcmp(&e->graph_dev, &e->dev, sizeof(DevSession)) != 0)) {
+  if (!e->graph_exec || memcmp(&e->graph_dev, &e->dev, sizeof(DevSession)) != 0) {
     free_graph(e);
-    CUDA_TRY(e, cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-    for (uint32_t i = 0; i < BATCH; ++i)
+    // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch).
+    // Sharded: scan shard -> ncclAllGather (top-32 keys + node records per rank) -> identical replay on every rank.
+    const size_t cnt = (size_t)(1 + e->ncols) * 32;
+    cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
+    bool ok = ce == cudaSuccess;
+    for (uint32_t i = 0; ok && i < BATCH; ++i) {
       visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
-    CUDA_TRY(e, cudaStreamEndCapture(e->stream, &e->graph));
-    CUDA_TRY(e, cudaGraphInstantiate(&e->graph_exec, e->graph, 0));
-    memcpy(&e->graph_dev, &e->dev, sizeof(DevSession));
+      if (e->world > 1) {
+        ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
+        replay_kernel<<<1, 32, e->replay_smem, e->stream>>>(e->dev);
+      }
+    }
+    cudaGraph_t g = nullptr;
+    ce = cudaStreamEndCapture(e->stream, &g);
+    ok = ok && ce == cudaSuccess && g != nullptr;
+    if (ok) ok = cudaGraphInstantiate(&e->graph_exec, g, 0) == cudaSuccess;
+    if (ok) { e->graph = g; memcpy(&e->graph_dev, &e->dev, sizeof(DevSession)); }
+    else {
+      if (g) cudaGraphDestroy(g);
+      e->graph_exec = nullptr;
+      cudaGetLastError();                      // clear; kb_allocate falls back to plain stream launches
+      if (e->world == 1) return fail(e, KB_E_CUDA, "CUDA graph capture of the visit chain failed");
+    }
   }
   e->loaded = true;
   e->load_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_start).count();
@@ -290,9 +307,9 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
   const uint64_t cap = 4ull * ((uint64_t)e->J + e->To) + 1024;
   for (;;) {
-    if (e->world == 1) {
+    if (e->graph_exec) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
-      launches += BATCH;
+      launches += (e->world == 1 ? 1 : 2) * BATCH;
     } else {
       // sharded node axis: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
       const size_t cnt = (size_t)(1 + e->ncols) * 32;
