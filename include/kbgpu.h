@@ -239,6 +239,9 @@ int kb_predicate_score(struct kb_engine* e, uint32_t task_lo, uint32_t task_hi, 
  * (util.SelectBestNode with the deterministic first-max rule, scheduler_helper.go:188-208). */
 int kb_best_nodes(struct kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint64_t* best_key);
 
+/* Device time (CUDA events on the engine stream) of the most recent kb_predicate_score / kb_best_nodes kernel. */
+int kb_last_kernel_ms(struct kb_engine* e, float* ms);
+
 /* Current node bookkeeping after kb_allocate (NodeInfo.Idle/Releasing/Used, pod count, nonzero
  * request, used host ports) — what node_info.go:172-212 AddTask left behind.  Any pointer may be NULL. */
 int kb_node_state(struct kb_engine* e, double* idle /*[R][N]*/, double* releasing /*[R][N]*/, double* used /*[R][N]*/,

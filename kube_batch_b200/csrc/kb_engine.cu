@@ -89,6 +89,7 @@ struct kb_engine {
   uint32_t scan_grid = 1;
   size_t visit_smem = 0, tile_smem = 0, replay_smem = 0;
   float load_ms = 0;
+  float last_kernel_ms = 0;
   int sm_count = 148;
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
@@ -375,7 +376,9 @@ int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t
   if (fit) CUDA_TRY(e, cudaMalloc(&d_fit, n));
   if (score) CUDA_TRY(e, cudaMalloc(&d_score, n * 8));
   dim3 grid(e->NT, (task_hi - task_lo + MATRIX_TASKS_PER_CTA - 1) / MATRIX_TASKS_PER_CTA);
+  cudaEventRecord(e->ev0, e->stream);
   matrix_kernel<<<grid, SCAN_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_fit, d_score);
+  cudaEventRecord(e->ev1, e->stream);
   cudaError_t c = cudaGetLastError();
   if (c == cudaSuccess && fit) c = cudaMemcpyAsync(fit, d_fit, n, cudaMemcpyDeviceToHost, e->stream);
   if (c == cudaSuccess && score) c = cudaMemcpyAsync(score, d_score, n * 8, cudaMemcpyDeviceToHost, e->stream);
@@ -383,6 +386,7 @@ int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t
   if (d_fit) cudaFree(d_fit);
   if (d_score) cudaFree(d_score);
   if (c != cudaSuccess) return fail(e, KB_E_CUDA, "matrix_kernel: %s", cudaGetErrorString(c));
+  cudaEventElapsedTime(&e->last_kernel_ms, e->ev0, e->ev1);
   return KB_OK;
 }
 
@@ -400,13 +404,22 @@ int kb_best_nodes(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint64_t* be
     // enough task chunks to fill the machine a few times over, each CTA keeps its node tile in shared memory
     uint32_t chunks = std::max(1u, std::min(n, (uint32_t)(8 * e->sm_count + e->NT - 1) / std::max(1u, e->NT)));
     dim3 grid(e->NT, chunks);
+    cudaEventRecord(e->ev0, e->stream);
     best_nodes_kernel<<<grid, SCAN_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_best);
+    cudaEventRecord(e->ev1, e->stream);
     c = cudaGetLastError();
   }
   if (c == cudaSuccess) c = cudaMemcpyAsync(best_key, d_best, (size_t)n * 8, cudaMemcpyDeviceToHost, e->stream);
   if (c == cudaSuccess) c = cudaStreamSynchronize(e->stream);
   cudaFree(d_best);
   if (c != cudaSuccess) return fail(e, KB_E_CUDA, "best_nodes_kernel: %s", cudaGetErrorString(c));
+  cudaEventElapsedTime(&e->last_kernel_ms, e->ev0, e->ev1);
+  return KB_OK;
+}
+
+int kb_last_kernel_ms(kb_engine* e, float* ms) {
+  if (!e || !ms) return KB_E_BADARG;
+  *ms = e->last_kernel_ms;
   return KB_OK;
 }
 

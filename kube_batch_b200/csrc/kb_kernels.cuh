@@ -50,13 +50,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   } while (!ok);
 }
 
+// max of a 64-bit key across the warp as two hardware 32-bit warp reductions (REDUX): high word first,
+// then the low word among the lanes that hold the winning high word
 __device__ __forceinline__ uint64_t warp_max_u64(uint64_t v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    uint64_t t = __shfl_xor_sync(FULL, v, o);
-    v = t > v ? t : v;
-  }
-  return v;
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_max_sync(FULL, hi);
+  const unsigned mlo = __reduce_max_sync(FULL, hi == mhi ? lo : 0u);
+  return ((uint64_t)mhi << 32) | (uint64_t)mlo;
 }
 
 // Strided column accessor (shared-memory tile: stride TILE_NODES; dirty slots: stride DMAX)

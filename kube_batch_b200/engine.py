@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
 EXPORTS = [
     "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_predicate_score",
     "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
-    "kb_nccl_unique_id",
+    "kb_nccl_unique_id", "kb_last_kernel_ms",
 ]
 
 
@@ -123,6 +123,11 @@ class Engine:
         out = np.zeros(max(hi - lo, 1), dtype=np.uint64)
         self._check(self.L.kb_best_nodes(self._h, C.c_uint32(lo), C.c_uint32(hi), _p(out, C.c_uint64)), "kb_best_nodes")
         return out[: hi - lo]
+
+    def last_kernel_ms(self) -> float:
+        ms = C.c_float()
+        self._check(self.L.kb_last_kernel_ms(self._h, C.byref(ms)), "kb_last_kernel_ms")
+        return float(ms.value)
 
     def node_state(self):
         s = self.snap
