@@ -152,3 +152,15 @@ def test_c3_full_size_parity_and_properties(eng):
     placed = d["step"] != 0xFFFFFFFF
     assert sorted(d["step"][placed].tolist()) == list(range(int(placed.sum())))
     assert r.stats.pairs_logical == int(r.stats.tasks_processed) * s.N
+
+
+@pytest.mark.skipif(os.environ.get("KB_SLOW") != "1", reason="set KB_SLOW=1: the CPU oracle needs minutes at this size")
+def test_c4_multiqueue_full_size_parity(eng):
+    """BASELINE config 4 (200k tasks x 20k nodes, 8 queues with proportion): exact Go-heap replay with stale keys at scale."""
+    s, conf = synth.make("c4")
+    o = kbo.allocate(s, conf, threads=16)
+    eng.load(s, conf)
+    r = eng.allocate()
+    util.assert_same_decisions(o.decisions, r.decisions, "c4")
+    util.assert_same_state(o, eng.node_state(), eng.order_state(), "c4")
+    print(f"c4: gpu {r.stats.gpu_ms:.1f} ms, oracle {o.result.seconds:.1f} s, scans {r.stats.scans}, visits {r.stats.visits}")
