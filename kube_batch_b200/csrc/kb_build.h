@@ -200,7 +200,7 @@ struct BuiltSession {
   uint32_t total_dims_mask = 3;
   double total[KB_MAX_R] = {0};
   std::vector<int32_t> job_min_avail;
-  uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0;
+  uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1;
 
   void bind(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     D.cf = hc.cf;
@@ -217,6 +217,7 @@ struct BuiltSession {
     D.dyn_jobs = (uint32_t*)(mb + om.dyn); D.q_allocated = (double*)(mb + om.q_alloc); D.q_share = (double*)(mb + om.q_share);
     D.qheap = (uint32_t*)(mb + om.qheap); D.dec = (kb_decision*)(mb + om.dec); D.cand = (uint64_t*)(mb + om.cand);
     D.ctl = (Ctl*)(mb + om.ctl);
+    D.tpi = tpi;
     D.rank = rank; D.world = world; D.tile_lo = tile_lo; D.tile_hi = tile_hi; D.nodes_per_rank = nodes_per_rank;
     D.sendbuf = (uint64_t*)(mb + om.sendbuf); D.recvbuf = (uint64_t*)(mb + om.recvbuf);
     D.classes = (ClassRec*)(ib + oi.classes); D.ord_task = (uint32_t*)(ib + oi.ord_task); D.ord_class = (uint32_t*)(ib + oi.ord_class);
@@ -316,7 +317,15 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   B.tile_lo = std::min(NT, rank * tiles_per_rank);
   B.tile_hi = std::min(NT, (rank + 1) * tiles_per_rank);
   B.nodes_per_rank = std::max(1u, tiles_per_rank * (uint32_t)TILE_NODES);
-  const uint32_t grid = std::max(1u, std::min(B.tile_hi - B.tile_lo, GMAX));
+  // tiles per scan iteration: up to 4 (16 warps), bounded by ~190 KB of shared memory for the two staging buffers
+  {
+    const size_t tile_bytes = (size_t)ncols * TILE_NODES * 8;
+    uint32_t tpi = 4;
+    while (tpi > 1 && 2 * tpi * tile_bytes > 190 * 1024) --tpi;
+    B.tpi = tpi;
+  }
+  const uint32_t n_groups = (B.tile_hi - B.tile_lo + B.tpi - 1) / B.tpi;
+  const uint32_t grid = std::max(1u, std::min(n_groups, GMAX));
   om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
   om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
   om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);

@@ -85,6 +85,7 @@ struct DevSession {
   // [tile_lo, tile_hi) only, then the ranks all-gather their top-KTOP keys together with the candidates'
   // node records and every rank replays identically, so the replicas never diverge.
   uint32_t rank, world, tile_lo, tile_hi, nodes_per_rank;
+  uint32_t tpi;           // node tiles a scan CTA stages per iteration (sized to shared memory)
   uint64_t* sendbuf;      // [(1 + ncols) * 32]: keys[32], then columns [ncols][32]
   uint64_t* recvbuf;      // [world] x the same
 };

@@ -260,7 +260,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->job_min_avail_host = B.job_min_avail;
   e->scan_grid = grid;
   e->tile_smem = tile_u64 * 8;
-  e->visit_smem = ((sizeof(VisitSmem) + 127) / 128) * 128 + 2 * e->tile_smem;
+  e->visit_smem = ((sizeof(VisitSmem) + 127) / 128) * 128 + 2 * (size_t)B.tpi * e->tile_smem;
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
@@ -377,7 +377,7 @@ int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t
   if (score) CUDA_TRY(e, cudaMalloc(&d_score, n * 8));
   dim3 grid(e->NT, (task_hi - task_lo + MATRIX_TASKS_PER_CTA - 1) / MATRIX_TASKS_PER_CTA);
   cudaEventRecord(e->ev0, e->stream);
-  matrix_kernel<<<grid, SCAN_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_fit, d_score);
+  matrix_kernel<<<grid, MATRIX_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_fit, d_score);
   cudaEventRecord(e->ev1, e->stream);
   cudaError_t c = cudaGetLastError();
   if (c == cudaSuccess && fit) c = cudaMemcpyAsync(fit, d_fit, n, cudaMemcpyDeviceToHost, e->stream);
@@ -405,7 +405,7 @@ int kb_best_nodes(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint64_t* be
     uint32_t chunks = std::max(1u, std::min(n, (uint32_t)(8 * e->sm_count + e->NT - 1) / std::max(1u, e->NT)));
     dim3 grid(e->NT, chunks);
     cudaEventRecord(e->ev0, e->stream);
-    best_nodes_kernel<<<grid, SCAN_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_best);
+    best_nodes_kernel<<<grid, MATRIX_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_best);
     cudaEventRecord(e->ev1, e->stream);
     c = cudaGetLastError();
   }

@@ -22,7 +22,10 @@
 
 namespace kb {
 
-constexpr int SCAN_THREADS = TILE_NODES;           // 128: one node per thread per tile
+constexpr int MATRIX_THREADS = TILE_NODES;         // matrix / best_nodes kernels: one node per thread, one tile per CTA
+constexpr int SCAN_WARPS = 16;                     // visit_kernel: 16 warps = up to 4 node tiles in flight per iteration
+constexpr int SCAN_THREADS = SCAN_WARPS * 32;
+constexpr int MAX_TPI = SCAN_WARPS / 4;            // tiles per iteration (4 warps x 32 lanes cover one 128-node tile)
 constexpr int MAXCOLS = 2 * KB_MAX_R + 6 + 3 * KB_MAX_W;   // 34
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -107,11 +110,24 @@ __device__ __forceinline__ uint64_t warp_merge_top32(uint64_t a, uint64_t b, int
 }
 
 
+// CTA-level fold of the SCAN_WARPS per-warp lists into warp 0 (binary tree through shared memory).
+// Every thread of the CTA must call it; returns the folded list in warp 0.
+__device__ __forceinline__ uint64_t cta_fold_lists(uint64_t mine, uint64_t (*wlist)[KTOP], int warp, int lane) {
+#pragma unroll
+  for (int s = SCAN_WARPS / 2; s > 0; s >>= 1) {
+    if (warp >= s && warp < 2 * s) wlist[warp][lane] = mine;
+    __syncthreads();
+    if (warp < s) mine = warp_merge_top32(mine, wlist[warp + s][lane], lane);
+    __syncthreads();
+  }
+  return mine;
+}
+
 struct VisitSmem {
   ClassRec cls;
   Ctl ctl;
   uint64_t keys[KTOP];                       // merged candidate list of the scan (K3 result)
-  uint64_t wlist[SCAN_THREADS / 32][KTOP];   // per-warp lists exchanged through shared memory
+  uint64_t wlist[SCAN_WARPS][KTOP];          // per-warp lists exchanged through shared memory
   uint64_t slot[2][MAXCOLS][32];             // candidate l: column c of state s at slot[s][c][l] (tile column scheme)
   uint64_t mbar[2];
   uint32_t is_last;
@@ -312,45 +328,45 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   const long long t_start = clock64();
 
-  // ---------------- scan: tiles blockIdx.x, +gridDim.x, ... double-buffered TMA ----------------
-  const uint32_t first = S.tile_lo + blockIdx.x, stride = gridDim.x;
-  uint32_t n_local = first < S.tile_hi ? (S.tile_hi - first + stride - 1) / stride : 0;
-  if (tid == 0 && n_local > 0) {
-    mbar_expect_tx(&sm.mbar[0], tile_bytes);
-    tma_load_1d(tilebuf, S.tiles + (size_t)first * tile_u64, tile_bytes, &sm.mbar[0]);
-  }
+  // ---------------- scan: tile GROUPS blockIdx.x, +gridDim.x, ...: S.tpi tiles per iteration, double-buffered TMA ----------------
+  const uint32_t tpi = S.tpi;                                        // tiles per iteration (<= MAX_TPI, sized to shared memory)
+  const uint32_t n_groups = (S.tile_hi - S.tile_lo + tpi - 1) / tpi;
+  const uint32_t firstg = blockIdx.x, stride = gridDim.x;
+  const uint32_t n_local = firstg < n_groups ? (n_groups - firstg + stride - 1) / stride : 0;
+  auto issue_group = [&](uint32_t grp, uint32_t buf) {                 // thread 0: one bulk copy per tile of the group
+    const uint32_t t0 = S.tile_lo + grp * tpi;
+    const uint32_t cnt = min(tpi, S.tile_hi - t0);
+    mbar_expect_tx(&sm.mbar[buf], cnt * tile_bytes);
+    for (uint32_t k = 0; k < cnt; ++k)
+      tma_load_1d(tilebuf + ((size_t)buf * tpi + k) * tile_u64, S.tiles + (size_t)(t0 + k) * tile_u64, tile_bytes, &sm.mbar[buf]);
+  };
+  if (tid == 0 && n_local > 0) issue_group(firstg, 0);
+  const uint32_t sub = (uint32_t)warp >> 2, part = (uint32_t)warp & 3u;    // which tile of the group / which 32 nodes of it
   uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
   for (uint32_t it = 0; it < n_local; ++it) {
     const uint32_t b = it & 1u;
     if (it + 1 < n_local) {
       __syncthreads();                       // every thread is done reading the other buffer (iteration it-1)
-      if (tid == 0) {
-        const uint32_t nb = b ^ 1u;
-        mbar_expect_tx(&sm.mbar[nb], tile_bytes);
-        tma_load_1d(tilebuf + (size_t)nb * tile_u64, S.tiles + (size_t)(first + (it + 1) * stride) * tile_u64, tile_bytes, &sm.mbar[nb]);
-      }
+      if (tid == 0) issue_group(firstg + (it + 1) * stride, b ^ 1u);
     }
     mbar_wait(&sm.mbar[b], (it >> 1) & 1u);
-    const uint32_t t = first + it * stride;
-    const uint32_t node = t * TILE_NODES + tid;
+    const uint32_t t = S.tile_lo + (firstg + it * stride) * tpi + sub;
+    const uint32_t node = t * TILE_NODES + part * 32u + lane;
     uint64_t key = 0;
-    if (node < S.N) {
-      ColAcc acc{tilebuf + (size_t)b * tile_u64, (uint32_t)tid, TILE_NODES, S.cf.R, S.cf.W};
+    if (sub < tpi && t < S.tile_hi && node < S.N) {
+      ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
       key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
     }
     // K3, warp level: skip the networks when nothing in this warp can enter its list
     const uint64_t thr = __shfl_sync(FULL, mylist, 31);
     if (__any_sync(FULL, key > thr)) {
       key = warp_sort_desc(key, lane);
-      mylist = it == 0 ? key : warp_merge_top32(mylist, key, lane);
+      mylist = warp_merge_top32(mylist, key, lane);
     }
   }
-  // CTA level: warp 0 folds the other warps' lists in, then publishes the CTA's list
-  sm.wlist[warp][lane] = mylist;
-  __syncthreads();
+  // CTA level: tree-fold the warps' lists into warp 0, which publishes the CTA's list
+  mylist = cta_fold_lists(mylist, sm.wlist, warp, lane);
   if (warp == 0) {
-#pragma unroll
-    for (int w = 1; w < SCAN_THREADS / 32; ++w) mylist = warp_merge_top32(mylist, sm.wlist[w][lane], lane);
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
     sm.keys[lane] = mylist;
     __threadfence();
@@ -365,31 +381,23 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __threadfence();
   const long long t_scan = clock64();
 
-  // ---------------- K3: merge the per-CTA lists: 4 warps, each folds every 4th list ----------------
+  // ---------------- K3: merge the per-CTA lists: every warp folds every 16th list, then the tree ----------------
   if (gridDim.x > 1) {
     const uint32_t G = gridDim.x;
     uint64_t acc = 0;
     uint32_t g = warp;
     uint64_t nxt = g < G ? __ldcg(&S.cand[(size_t)g * KTOP + lane]) : 0ull;
-    bool firstl = true;
     while (g < G) {
       const uint64_t cur = nxt;
-      const uint32_t g2 = g + SCAN_THREADS / 32;
+      const uint32_t g2 = g + SCAN_WARPS;
       nxt = g2 < G ? __ldcg(&S.cand[(size_t)g2 * KTOP + lane]) : 0ull;     // prefetch the next list
       const uint64_t thr = __shfl_sync(FULL, acc, 31);
       const uint64_t head = __shfl_sync(FULL, cur, 0);
-      if (firstl) { acc = cur; firstl = false; }
-      else if (head > thr) acc = warp_merge_top32(acc, cur, lane);
+      if (head > thr) acc = warp_merge_top32(acc, cur, lane);
       g = g2;
     }
-    __syncthreads();                         // wlist is being reused
-    sm.wlist[warp][lane] = acc;
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-      for (int w = 1; w < SCAN_THREADS / 32; ++w) acc = warp_merge_top32(acc, sm.wlist[w][lane], lane);
-      sm.keys[lane] = acc;
-    }
+    acc = cta_fold_lists(acc, sm.wlist, warp, lane);
+    if (warp == 0) sm.keys[lane] = acc;
   }
   if (S.world > 1) {
     // sharded node axis: publish this rank's candidates WITH their node records; the replay happens in
@@ -503,7 +511,7 @@ gang_commit_kernel(const __grid_constant__ DevSession S, const int32_t* __restri
 // ---------------------------------------------------------------------------------------------
 constexpr int MATRIX_TASKS_PER_CTA = 32;
 
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(MATRIX_THREADS)
 matrix_kernel(const __grid_constant__ DevSession S, const uint32_t* __restrict__ task_class, uint32_t task_lo, uint32_t task_hi,
               uint8_t* __restrict__ fit, double* __restrict__ score) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -528,7 +536,7 @@ matrix_kernel(const __grid_constant__ DevSession S, const uint32_t* __restrict__
     {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[task_class[t]]);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&cls);
-      for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+      for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += MATRIX_THREADS) dst[i] = src[i];
     }
     __syncthreads();
     if (node < S.N) {
@@ -541,7 +549,7 @@ matrix_kernel(const __grid_constant__ DevSession S, const uint32_t* __restrict__
 }
 
 // K1+K2+K3 fused: per-task best packed key over ALL nodes in one launch.
-__global__ void __launch_bounds__(SCAN_THREADS)
+__global__ void __launch_bounds__(MATRIX_THREADS)
 best_nodes_kernel(const __grid_constant__ DevSession S, const uint32_t* __restrict__ task_class, uint32_t task_lo, uint32_t task_hi,
                   unsigned long long* __restrict__ best_key) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -569,7 +577,7 @@ best_nodes_kernel(const __grid_constant__ DevSession S, const uint32_t* __restri
       __syncthreads();
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cid]);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&cls);
-      for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+      for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += MATRIX_THREADS) dst[i] = src[i];
       __syncthreads();
       cur_cls = cid;
     }
