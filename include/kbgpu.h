@@ -206,6 +206,8 @@ typedef struct kb_stats {
   uint64_t cyc_total;
   uint64_t cyc_steps;       /*   ... of cyc_replay: the per-task step loops                      */
   uint64_t cyc_ctl;         /*   ... of cyc_replay: the control plane (after_run)                 */
+  uint32_t predictions;     /* overlap mode: launches whose scan ran ahead on a predicted class   */
+  uint32_t mispredictions;  /*   ... of which the prediction was wrong (that launch's scan is redone) */
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

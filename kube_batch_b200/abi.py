@@ -173,6 +173,8 @@ class kb_stats(C.Structure):
         ("cyc_total", C.c_uint64),
         ("cyc_steps", C.c_uint64),
         ("cyc_ctl", C.c_uint64),
+        ("predictions", C.c_uint32),
+        ("mispredictions", C.c_uint32),
     ]
 
 

@@ -189,7 +189,7 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf; };
-struct OffImm { size_t classes, ord_task, ord_class, ord_run, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
+struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
 
 struct BuiltSession {
   Slab mut, imm;
@@ -200,7 +200,7 @@ struct BuiltSession {
   uint32_t total_dims_mask = 3;
   double total[KB_MAX_R] = {0};
   std::vector<int32_t> job_min_avail;
-  uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1;
+  uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1, overlap = 0;
 
   void bind(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     D.cf = hc.cf;
@@ -221,7 +221,8 @@ struct BuiltSession {
     D.rank = rank; D.world = world; D.tile_lo = tile_lo; D.tile_hi = tile_hi; D.nodes_per_rank = nodes_per_rank;
     D.sendbuf = (uint64_t*)(mb + om.sendbuf); D.recvbuf = (uint64_t*)(mb + om.recvbuf);
     D.classes = (ClassRec*)(ib + oi.classes); D.ord_task = (uint32_t*)(ib + oi.ord_task); D.ord_class = (uint32_t*)(ib + oi.ord_class);
-    D.ord_run = (uint32_t*)(ib + oi.ord_run);
+    D.ord_run = (uint32_t*)(ib + oi.ord_run); D.ord_peek = (uint32_t*)(ib + oi.ord_peek);
+    D.overlap = overlap;
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -325,7 +326,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     B.tpi = tpi;
   }
   const uint32_t n_groups = (B.tile_hi - B.tile_lo + B.tpi - 1) / B.tpi;
-  const uint32_t grid = std::max(1u, std::min(n_groups, GMAX));
+  // overlap mode (one GPU) keeps one SM for the replayer CTA
+  const uint32_t grid = std::max(1u, std::min(n_groups, (world <= 1 && GMAX > 1) ? GMAX - 1 : GMAX));
   om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
   om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
   om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
@@ -347,6 +349,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.ord_task = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.ord_class = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.ord_run = imm.alloc((size_t)std::max(1u, To) * 4);
+  oi.ord_peek = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.job_ord_off = imm.alloc((size_t)(J + 1) * 4);
   oi.job_min = imm.alloc((size_t)std::max(1u, J) * 4);
   oi.job_queue = imm.alloc((size_t)std::max(1u, J) * 4);
@@ -497,8 +500,19 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     for (uint32_t q = 0; q < Q; ++q) {
       std::sort(H.q_static + cnt[q], H.q_static + cnt[q + 1], [&](uint32_t l, uint32_t r) { return job_before(H, l, r); });
       H.q_static_head[q] = cnt[q];
+      // prediction table: walking the queue's static job order backwards, the first class that differs from a slot's own
+      uint32_t next_slot = 0xFFFFFFFFu;
+      for (uint32_t k = cnt[q + 1]; k-- > cnt[q];) {
+        const uint32_t j = H.q_static[k];
+        for (uint32_t i = job_ord_off[j + 1]; i-- > job_ord_off[j];) {
+          if (next_slot == 0xFFFFFFFFu) H.ord_peek[i] = 0xFFFFFFFFu;
+          else H.ord_peek[i] = (ord_class[next_slot] != ord_class[i]) ? ord_class[next_slot] : H.ord_peek[next_slot];
+          next_slot = i;
+        }
+      }
     }
   }
+  B.overlap = (world <= 1) ? 1u : 0u;
   Ctl& c0 = *H.ctl;
   memset(&c0, 0, sizeof c0);
   c0.cur_job = -1;
@@ -509,7 +523,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     H.dec[t] = d;
   }
   select_next_visit(H, c0);
-
+  c0.scan_class = c0.cur_class;      // the first launch has no list yet: scan for the first visit, nothing excluded
+  c0.n_excl = 0; c0.list_valid = 0; c0.patch_valid = 0;
 
   B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.grid = grid;
   B.job_min_avail.assign(s->job_min_avail, s->job_min_avail + J);

@@ -34,6 +34,18 @@ struct Ctl {
   unsigned long long pairs_logical, pairs_scanned, pairs_replayed;
   // phase timers of the LAST CTA of every launch, SM cycles (clock64), summed over the cycle
   unsigned long long cyc_scan, cyc_merge, cyc_replay, cyc_total, cyc_steps, cyc_ctl;
+  // ---- scan / replay overlap (single GPU): launch k scans `scan_class` (the predicted class of the visit after the
+  //      one being replayed) while the replayer CTA consumes `list` (produced by launch k-1).  The scanners skip the
+  //      `excl` nodes — exactly the nodes the replayer may modify — and the replayer contributes their fresh keys
+  //      for `scan_class` as `patch`, so the merged list is exact for the table state at the end of the launch.
+  uint32_t scan_class;
+  uint32_t n_excl;
+  uint32_t list_class, list_valid;
+  uint32_t patch_valid;
+  uint32_t predictions, mispredictions;
+  uint32_t excl[32];
+  unsigned long long list[32];
+  unsigned long long patch[32];
 };
 
 struct DevSession {
@@ -56,6 +68,8 @@ struct DevSession {
   uint32_t* ord_task;     // [To] snapshot task index
   uint32_t* ord_class;    // [To]
   uint32_t* ord_run;      // [To] number of consecutive slots of the same class starting here (within the job)
+  uint32_t* ord_peek;     // [To] first class != ord_class[i] later in the queue's static job order (prediction only), ~0u = none
+  uint32_t overlap;       // 1: visit_kernel runs scanners + one replayer CTA concurrently (world == 1)
   uint32_t* job_ord_off;  // [J+1]
   uint32_t* job_pos;      // [J] cursor into ord_* (pendingTasks[job.UID], allocate.go:110-126)
   // jobs

@@ -262,6 +262,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->tile_smem = tile_u64 * 8;
   e->visit_smem = ((sizeof(VisitSmem) + 127) / 128) * 128 + 2 * (size_t)B.tpi * e->tile_smem;
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(visit_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch)
@@ -275,7 +276,8 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     bool ok = ce == cudaSuccess;
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
-      visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+      if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+      else visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
       if (e->world > 1) {
         ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
         replay_kernel<<<1, 32, e->replay_smem, e->stream>>>(e->dev);
@@ -359,6 +361,7 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
     stats->gpu_ms = ms; stats->load_ms = e->load_ms;
     stats->scans = c.scans; stats->rescans = c.rescans;
     stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total; stats->cyc_steps = c.cyc_steps; stats->cyc_ctl = c.cyc_ctl;
+    stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
     stats->h2d_bytes = (uint64_t)e->mut_bytes + e->imm_bytes;
     stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / BATCH) * sizeof(Ctl);
   }

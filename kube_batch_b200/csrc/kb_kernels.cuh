@@ -131,6 +131,8 @@ struct VisitSmem {
   uint64_t slot[2][MAXCOLS][32];             // candidate l: column c of state s at slot[s][c][l] (tile column scheme)
   uint64_t mbar[2];
   uint32_t is_last;
+  uint32_t n_excl;
+  uint32_t excl[32];                         // nodes the scanners skip (overlap mode)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -139,8 +141,18 @@ struct VisitSmem {
 // where THIS lane's candidate record can be read (column c at rec_base[c * rec_stride]): the local node
 // tiles on one GPU, the all-gathered records of the owning rank when the node axis is sharded.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& sm, Ctl* gctl, const int lane, const uint32_t cls_id,
-                                                const uint64_t* rec_base, const uint32_t rec_stride,
+// Copies the control block back to global memory WITHOUT its first word (`arrive`, the ticket counter other CTAs may
+// be incrementing right now).  One warp.
+__device__ __forceinline__ void store_ctl(Ctl* g, const Ctl& c, int lane) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&c);
+  uint32_t* dst = reinterpret_cast<uint32_t*>(g);
+  for (uint32_t i = 1 + lane; i < sizeof(Ctl) / 4; i += 32) dst[i] = src[i];
+}
+
+// `patch_class` != ~0u (overlap mode): after the replay, if the control plane's next visit has that class, every lane
+// evaluates ITS candidate's current state for it and the sorted keys go to c.patch (see Ctl).  The caller stores c.
+__device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& sm, const int lane, const uint32_t cls_id,
+                                                const uint64_t* rec_base, const uint32_t rec_stride, const uint32_t patch_class,
                                                 const long long t_start, const long long t_scan) {
   // Lane l OWNS candidate l of the merged list: its node record lives in two shared-memory slots
   // (current state / state after one more placement of this class) and the lane keeps the packed key
@@ -150,7 +162,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   // full list), so a pick is certified iff its key >= floor_key; otherwise the run stops for a rescan.
   Ctl& c = sm.ctl;
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
-  if (lane == 0) { c.scans += 1; c.pairs_scanned += (unsigned long long)S.N; }
+  if (lane == 0 && patch_class == 0xFFFFFFFFu) { c.scans += 1; c.pairs_scanned += (unsigned long long)S.N; }
   uint64_t cur_key = sm.keys[lane];
   const uint64_t floor_key = sm.keys[KTOP - 1];
   const bool have = cur_key != 0;
@@ -291,47 +303,51 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     }
   }
   __syncwarp();
+  if (patch_class != 0xFFFFFFFFu) {
+    // overlap mode: fresh keys of MY candidate (the scanners skipped it) for the class they scanned meanwhile
+    const bool hit = !c.done && c.cur_class == patch_class;
+    if (hit) {
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[patch_class]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+        for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
+      }
+      __syncwarp();
+      uint64_t pk = 0;
+      if (have) {
+        ColAcc acc{&sm.slot[which][0][0], (uint32_t)lane, 32u, R, W};
+        pk = eval_pair(S.cf, sm.cls, acc, my_node, nullptr);
+      }
+      const unsigned n = __popc(__ballot_sync(FULL, have));
+      pk = warp_sort_desc(pk, lane);
+      c.patch[lane] = pk;
+      if (lane == 0) { c.patch_valid = 1; c.pairs_replayed += (unsigned long long)n; }
+    } else if (lane == 0) c.patch_valid = 0;
+  }
+  __syncwarp();
   if (lane == 0) {
     const long long t_end = clock64();
     c.cyc_scan += (unsigned long long)(t_scan - t_start);
     c.cyc_merge += (unsigned long long)(t_merge - t_scan);
     c.cyc_replay += (unsigned long long)(t_end - t_merge);
-    c.cyc_total += (unsigned long long)(t_end - t_start);
-    c.arrive = 0; *gctl = c;
+    if (patch_class == 0xFFFFFFFFu) c.cyc_total += (unsigned long long)(t_end - t_start);
   }
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------
-// visit_kernel
+// Scan phase of one scanner CTA: tile GROUPS scanner_idx, +n_scanners, ... (S.tpi tiles per iteration, double-buffered
+// TMA), K1+K2 per node against sm.cls, warp-level top-32, CTA tree fold.  Nodes listed in sm.excl (overlap mode) are
+// skipped.  Every thread of the CTA calls it; the CTA's list is returned in warp 0.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SCAN_THREADS)
-visit_kernel(const __grid_constant__ DevSession S) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  // layout: [VisitSmem][pad to 128][tile buffer 0][tile buffer 1]
-  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
+__device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx,
+                                               const uint32_t n_scanners, const int tid, const int lane, const int warp) {
   const uint32_t tile_u64 = S.ncols * TILE_NODES;
   const uint32_t tile_bytes = tile_u64 * 8u;
-  uint64_t* tilebuf = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(VisitSmem) + 127) / 128) * 128);
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  Ctl* gctl = S.ctl;
-  if (*((volatile uint32_t*)&gctl->done)) return;
-  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
-
-  // class record -> shared memory (broadcast reads afterwards)
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
-    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
-  }
-  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); }
-  __syncthreads();
-  const long long t_start = clock64();
-
   // ---------------- scan: tile GROUPS blockIdx.x, +gridDim.x, ...: S.tpi tiles per iteration, double-buffered TMA ----------------
   const uint32_t tpi = S.tpi;                                        // tiles per iteration (<= MAX_TPI, sized to shared memory)
   const uint32_t n_groups = (S.tile_hi - S.tile_lo + tpi - 1) / tpi;
-  const uint32_t firstg = blockIdx.x, stride = gridDim.x;
+  const uint32_t firstg = scanner_idx, stride = n_scanners;
   const uint32_t n_local = firstg < n_groups ? (n_groups - firstg + stride - 1) / stride : 0;
   auto issue_group = [&](uint32_t grp, uint32_t buf) {                 // thread 0: one bulk copy per tile of the group
     const uint32_t t0 = S.tile_lo + grp * tpi;
@@ -353,7 +369,11 @@ visit_kernel(const __grid_constant__ DevSession S) {
     const uint32_t t = S.tile_lo + (firstg + it * stride) * tpi + sub;
     const uint32_t node = t * TILE_NODES + part * 32u + lane;
     uint64_t key = 0;
-    if (sub < tpi && t < S.tile_hi && node < S.N) {
+    // overlap mode: the replayer CTA may be modifying these nodes right now; it contributes their keys itself
+    const uint32_t wbase = t * TILE_NODES + part * 32u;
+    const uint32_t d = sm.excl[lane] - wbase;
+    const unsigned exmask = __reduce_or_sync(FULL, ((uint32_t)lane < sm.n_excl && d < 32u) ? (1u << d) : 0u);
+    if (sub < tpi && t < S.tile_hi && node < S.N && !((exmask >> lane) & 1u)) {
       ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
       key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
     }
@@ -366,6 +386,36 @@ visit_kernel(const __grid_constant__ DevSession S) {
   }
   // CTA level: tree-fold the warps' lists into warp 0, which publishes the CTA's list
   mylist = cta_fold_lists(mylist, sm.wlist, warp, lane);
+  return mylist;
+}
+
+// ---------------------------------------------------------------------------------------------
+// visit_kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SCAN_THREADS)
+visit_kernel(const __grid_constant__ DevSession S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  // layout: [VisitSmem][pad to 128][tile buffer 0][tile buffer 1]
+  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
+  uint64_t* tilebuf = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(VisitSmem) + 127) / 128) * 128);
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctl* gctl = S.ctl;
+  if (*((volatile uint32_t*)&gctl->done)) return;
+  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
+
+  // class record -> shared memory (broadcast reads afterwards)
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+  }
+  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; }
+  if (tid < 32) sm.excl[tid] = 0;
+  __syncthreads();
+  const long long t_start = clock64();
+
+  uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, gridDim.x, tid, lane, warp);
   if (warp == 0) {
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
     sm.keys[lane] = mylist;
@@ -422,8 +472,149 @@ visit_kernel(const __grid_constant__ DevSession S) {
   {
     const uint32_t n = key_node(sm.keys[lane]);
     const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
-    replay_epilogue(S, sm, gctl, lane, cls_id, rec, TILE_NODES, t_start, t_scan);
+    replay_epilogue(S, sm, lane, cls_id, rec, TILE_NODES, 0xFFFFFFFFu, t_start, t_scan);
+    store_ctl(gctl, sm.ctl, lane);
+    if (lane == 0) gctl->arrive = 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// visit_overlap_kernel (single GPU): scan and replay of consecutive visits run CONCURRENTLY.
+//   CTAs 0..G-1  scanners: evaluate Ctl.scan_class — the predicted class of the visit after the one being replayed —
+//                over the whole table, skipping Ctl.excl (the nodes the replayer may be modifying);
+//   CTA  G       replayer: consumes Ctl.list (built by the previous launch) for the current visit(s), runs the control
+//                plane, writes its candidates back and contributes their fresh keys for scan_class (Ctl.patch);
+//   last CTA     (ticket over G+1) merges the scan lists with the patch into Ctl.list for the next launch, and
+//                publishes the next scan_class (prediction table ord_peek) and exclusion set (the new list's nodes).
+// The merged list is exact for the table state at the end of the launch: every node is either scanned unmodified or
+// patched from the replayer's own up-to-date copy.  A wrong prediction only costs the overlap of one launch.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void load_ctl(Ctl& dst, const Ctl* g, int lane) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+  for (uint32_t i = lane; i < sizeof(Ctl) / 4; i += 32) d[i] = __ldcg(src + i);
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS)
+visit_overlap_kernel(const __grid_constant__ DevSession S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
+  uint64_t* tilebuf = reinterpret_cast<uint64_t*>(smem_raw + ((sizeof(VisitSmem) + 127) / 128) * 128);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctl* gctl = S.ctl;
+  if (*((volatile uint32_t*)&gctl->done)) return;
+  const uint32_t n_scanners = gridDim.x - 1;
+  const bool is_replayer = blockIdx.x == n_scanners;
+  const long long t_start = clock64();
+
+  if (!is_replayer) {
+    // ---------------- scanner ----------------
+    const uint32_t cls_id = *((volatile uint32_t*)&gctl->scan_class);
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+      for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = *((volatile uint32_t*)&gctl->n_excl); }
+    if (tid < 32) sm.excl[tid] = *((volatile uint32_t*)&gctl->excl[tid]);
+    __syncthreads();
+    const uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, n_scanners, tid, lane, warp);
+    if (warp == 0) S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
+  } else if (warp == 0) {
+    // ---------------- replayer ----------------
+    load_ctl(sm.ctl, gctl, lane);
+    __syncwarp();
+    Ctl& c = sm.ctl;
+    const bool go = c.list_valid != 0 && c.list_class == c.cur_class;
+    if (go) {
+      const uint32_t cls_id = c.list_class;
+      const uint32_t patch_class = c.n_excl > 0 ? c.scan_class : 0xFFFFFFFEu;   // 0xFFFFFFFE never matches a class
+      {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+        for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
+      }
+      sm.keys[lane] = c.list[lane];
+      __syncwarp();
+      if (lane == 0) c.list_valid = 0;                  // consumed
+      const uint32_t n = key_node(sm.keys[lane]);
+      const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
+      const long long t0 = clock64();
+      replay_epilogue(S, sm, lane, cls_id, rec, TILE_NODES, patch_class, t0, t0);
+    } else if (lane == 0) c.patch_valid = 0;
+    __syncwarp();
+    store_ctl(gctl, c, lane);
+  }
+
+  // ---------------- ticket over scanners + replayer ----------------
+  __syncthreads();
+  if (warp == 0) {
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) {
+      const uint32_t ticket = atomicAdd(&gctl->arrive, 1u);
+      sm.is_last = (ticket == gridDim.x - 1) ? 1u : 0u;
+    }
+  }
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  const long long t_scan = clock64();
+
+  // ---------------- merger: all 16 warps fold the scan lists; warp 0 adds the patch and publishes ----------------
+  uint64_t acc = 0;
+  {
+    uint32_t g = warp;
+    uint64_t nxt = g < n_scanners ? __ldcg(&S.cand[(size_t)g * KTOP + lane]) : 0ull;
+    while (g < n_scanners) {
+      const uint64_t cur = nxt;
+      const uint32_t g2 = g + SCAN_WARPS;
+      nxt = g2 < n_scanners ? __ldcg(&S.cand[(size_t)g2 * KTOP + lane]) : 0ull;
+      const uint64_t thr = __shfl_sync(FULL, acc, 31);
+      const uint64_t head = __shfl_sync(FULL, cur, 0);
+      if (head > thr) acc = warp_merge_top32(acc, cur, lane);
+      g = g2;
+    }
+    acc = cta_fold_lists(acc, sm.wlist, warp, lane);
+  }
+  if (warp != 0) return;
+  load_ctl(sm.ctl, gctl, lane);
+  __syncwarp();
+  Ctl& c = sm.ctl;
+  const uint32_t n_excl0 = c.n_excl, scan_class0 = c.scan_class;
+  if (c.patch_valid) acc = warp_merge_top32(acc, c.patch[lane], lane);
+  __syncwarp();
+  c.list[lane] = acc;
+  const unsigned nz = __ballot_sync(FULL, acc != 0);
+  if (lane == 0) {
+    c.list_class = scan_class0;
+    c.list_valid = (n_excl0 == 0 || c.patch_valid) ? 1u : 0u;
+    c.scans += 1; c.pairs_scanned += (unsigned long long)S.N;
+    if (n_excl0 > 0) { c.predictions += 1; if (!c.patch_valid) c.mispredictions += 1; }
+  }
+  __syncwarp();
+  if (!c.done) {
+    const bool useful = c.list_valid != 0 && c.list_class == c.cur_class;
+    if (useful) {
+      c.excl[lane] = acc ? key_node(acc) : 0u;
+      if (lane == 0) {
+        const uint32_t pk = S.ord_peek[S.job_pos[(uint32_t)c.cur_job]];
+        c.scan_class = pk != 0xFFFFFFFFu ? pk : c.cur_class;
+        c.n_excl = (uint32_t)__popc(nz);
+      }
+    } else if (lane == 0) { c.scan_class = c.cur_class; c.n_excl = 0; }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    const long long t_end = clock64();
+    c.cyc_scan += (unsigned long long)(t_scan - t_start);
+    c.cyc_merge += (unsigned long long)(t_end - t_scan);
+    c.cyc_total += (unsigned long long)(t_end - t_start);
+  }
+  __syncwarp();
+  store_ctl(gctl, c, lane);
+  __syncwarp();
+  if (lane == 0) gctl->arrive = 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -458,7 +649,9 @@ replay_kernel(const __grid_constant__ DevSession S) {
       if (__ldcg(S.recvbuf + owner * rank_u64 + i) == acc) idx = i;
   if (lane == 0) sm.ctl = *gctl;
   __syncwarp();
-  replay_epilogue(S, sm, gctl, lane, cls_id, S.recvbuf + owner * rank_u64 + 32 + idx, 32u, t_start, clock64());
+  replay_epilogue(S, sm, lane, cls_id, S.recvbuf + owner * rank_u64 + 32 + idx, 32u, 0xFFFFFFFFu, t_start, clock64());
+  store_ctl(gctl, sm.ctl, lane);
+  if (lane == 0) gctl->arrive = 0;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -75,41 +75,13 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
   }
 }
 
-// replay_kernel / replay_epilogue
-void emu_replay(Emu& E, const uint64_t* recvbuf) {
-  const DevSession& S = E.S;
-  Ctl& c = *S.ctl;
-  E.launches += 1;
-  if (c.done) return;
-  const uint32_t cls_id = c.cur_class;
+struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = false, modified = false;
+              uint64_t cur_key = 0, next_key = 0; uint32_t node = 0, cnt = 0; Slot st[2]; int which = 0; };
+
+// replay_epilogue's core: look-ahead refresh + certified steps + control plane, for candidates already loaded
+void replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
-  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
-  const size_t rank_u64 = (size_t)(1 + ncols) * 32;
-  // merge the ranks' lists
-  struct Src { uint64_t key; uint32_t rank, idx; };
-  std::vector<Src> all;
-  for (uint32_t r = 0; r < S.world; ++r)
-    for (uint32_t i = 0; i < 32; ++i) {
-      uint64_t k = recvbuf[r * rank_u64 + i];
-      if (k) all.push_back({k, r, i});
-    }
-  std::sort(all.begin(), all.end(), [](const Src& a, const Src& b) { return a.key > b.key; });
-  c.scans += 1; c.pairs_scanned += S.N;
-
-  struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = false, modified = false;
-                uint64_t cur_key = 0, next_key = 0; uint32_t node = 0, cnt = 0; Slot st[2]; int which = 0; };
-  std::vector<Cand> cand(KTOP);
-  const uint64_t floor_key = all.size() >= (size_t)KTOP ? all[KTOP - 1].key : 0ull;
-  for (int l = 0; l < KTOP && l < (int)all.size(); ++l) {
-    Cand& cd = cand[l];
-    cd.cur_key = all[l].key; cd.have = true;
-    cd.node = key_node(cd.cur_key);
-    const uint64_t* rec = recvbuf + all[l].rank * rank_u64 + 32 + all[l].idx;
-    for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = rec[(size_t)cc * 32];
-    SlotAcc acc{&cd.st[0], R, W};
-    cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
-  }
   auto refresh = [&]() {
     for (auto& cd : cand) {
       if (!(cd.have && cd.cur_key != 0 && !cd.next_valid)) continue;
@@ -164,13 +136,142 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
     after_run(S, c, reason, placed);
     if (reason == STOP_RESCAN) break;
   }
-  for (auto& cd : cand) {          // every replica writes every modified candidate back
+}
+
+void write_back(const DevSession& S, const ClassRec& cls, std::vector<Cand>& cand) {
+  const uint32_t R = S.cf.R, ncols = S.ncols;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  for (auto& cd : cand) {
     if (!cd.modified) continue;
     const Slot& src = cd.st[cd.which];
     uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
     for (uint32_t cc = 0; cc < ncols; ++cc) gt[(size_t)cc * TILE_NODES] = src.col[cc];
     for (uint32_t r = 0; r < R; ++r)
       for (uint32_t i = 0; i < cd.cnt; ++i) S.node_used[(size_t)r * S.N + cd.node] += cls.resreq[r];
+  }
+}
+
+// replay_kernel / replay_epilogue
+void emu_replay(Emu& E, const uint64_t* recvbuf) {
+  const DevSession& S = E.S;
+  Ctl& c = *S.ctl;
+  E.launches += 1;
+  if (c.done) return;
+  const uint32_t cls_id = c.cur_class;
+  const ClassRec& cls = S.classes[cls_id];
+  const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  const size_t rank_u64 = (size_t)(1 + ncols) * 32;
+  // merge the ranks' lists
+  struct Src { uint64_t key; uint32_t rank, idx; };
+  std::vector<Src> all;
+  for (uint32_t r = 0; r < S.world; ++r)
+    for (uint32_t i = 0; i < 32; ++i) {
+      uint64_t k = recvbuf[r * rank_u64 + i];
+      if (k) all.push_back({k, r, i});
+    }
+  std::sort(all.begin(), all.end(), [](const Src& a, const Src& b) { return a.key > b.key; });
+  c.scans += 1; c.pairs_scanned += S.N;
+
+  std::vector<Cand> cand(KTOP);
+  const uint64_t floor_key = all.size() >= (size_t)KTOP ? all[KTOP - 1].key : 0ull;
+  for (int l = 0; l < KTOP && l < (int)all.size(); ++l) {
+    Cand& cd = cand[l];
+    cd.cur_key = all[l].key; cd.have = true;
+    cd.node = key_node(cd.cur_key);
+    const uint64_t* rec = recvbuf + all[l].rank * rank_u64 + 32 + all[l].idx;
+    for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = rec[(size_t)cc * 32];
+    SlotAcc acc{&cd.st[0], R, W};
+    cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+  }
+  replay_core(S, c, cls_id, cand, floor_key);
+  write_back(S, cls, cand);          // every replica writes every modified candidate back
+}
+
+// One launch of visit_kernel in OVERLAP mode (single GPU): the scanner CTAs evaluate Ctl.scan_class (the predicted class of
+// the visit after the current one) skipping Ctl.excl, while the replayer CTA consumes Ctl.list; the last CTA merges the scan
+// lists with the replayer's patch keys and publishes list / scan_class / excl for the next launch.
+void emu_launch_overlap(Emu& E) {
+  const DevSession& S = E.S;
+  Ctl& c = *S.ctl;
+  E.launches += 1;
+  if (c.done) return;
+  const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  const uint32_t scan_class = c.scan_class, n_excl = c.n_excl;
+  uint32_t excl[32];
+  for (uint32_t i = 0; i < 32; ++i) excl[i] = c.excl[i];
+
+  // ---- replayer CTA ----
+  std::vector<Cand> cand(KTOP);
+  bool replayed = false;
+  if (c.list_valid && c.list_class == c.cur_class) {
+    replayed = true;
+    const uint32_t cls_id = c.list_class;
+    const ClassRec& cls = S.classes[cls_id];
+    c.list_valid = 0;                                  // consumed
+    const uint64_t floor_key = c.list[KTOP - 1];
+    for (int l = 0; l < KTOP; ++l) {
+      Cand& cd = cand[l];
+      cd.cur_key = c.list[l]; cd.have = cd.cur_key != 0;
+      if (!cd.have) continue;
+      cd.node = key_node(cd.cur_key);
+      const uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
+      for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = gt[(size_t)cc * TILE_NODES];
+      SlotAcc acc{&cd.st[0], R, W};
+      cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+    }
+    replay_core(S, c, cls_id, cand, floor_key);
+    write_back(S, cls, cand);
+  }
+  c.patch_valid = 0;
+  if (replayed && !c.done && n_excl > 0 && c.cur_class == scan_class) {      // prediction hit: fresh keys of the excluded nodes
+    const ClassRec& pc = S.classes[scan_class];
+    std::vector<uint64_t> pk;
+    for (auto& cd : cand) {
+      if (!cd.have) continue;
+      SlotAcc acc{&cd.st[cd.which], R, W};
+      uint64_t k = eval_pair(S.cf, pc, acc, cd.node, nullptr);
+      c.pairs_replayed += 1;
+      if (k) pk.push_back(k);
+    }
+    std::sort(pk.begin(), pk.end(), [](uint64_t a, uint64_t b) { return a > b; });
+    for (int l = 0; l < KTOP; ++l) c.patch[l] = l < (int)pk.size() ? pk[l] : 0ull;
+    c.patch_valid = 1;
+  }
+
+  // ---- scanner CTAs (concurrent on the device; equivalent in any order because they skip the excluded nodes) ----
+  std::vector<uint64_t> keys;
+  {
+    const ClassRec& sc = S.classes[scan_class];
+    for (uint32_t n = 0; n < S.N; ++n) {
+      bool skip = false;
+      for (uint32_t i = 0; i < n_excl; ++i) skip = skip || excl[i] == n;
+      if (skip) continue;
+      TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+      uint64_t k = eval_pair(S.cf, sc, acc, n, nullptr);
+      if (k) keys.push_back(k);
+    }
+  }
+  // ---- merger (last CTA) ----
+  if (c.patch_valid) for (int l = 0; l < KTOP; ++l) if (c.patch[l]) keys.push_back(c.patch[l]);
+  std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+  for (int l = 0; l < KTOP; ++l) c.list[l] = l < (int)keys.size() ? keys[l] : 0ull;
+  c.list_class = scan_class;
+  c.list_valid = (n_excl == 0 || c.patch_valid) ? 1u : 0u;
+  c.scans += 1; c.pairs_scanned += S.N;
+  if (n_excl > 0) { c.predictions += 1; if (!c.patch_valid) c.mispredictions += 1; }
+  if (!c.done) {
+    if (c.list_valid && c.list_class == c.cur_class) {
+      const uint32_t pk = S.ord_peek[S.job_pos[(uint32_t)c.cur_job]];
+      c.scan_class = pk != 0xFFFFFFFFu ? pk : c.cur_class;
+      uint32_t n = 0;
+      for (int l = 0; l < KTOP; ++l) if (c.list[l]) c.excl[n++] = key_node(c.list[l]);
+      c.n_excl = n;
+    } else {
+      c.scan_class = c.cur_class;
+      c.n_excl = 0;
+    }
   }
 }
 
@@ -250,7 +351,7 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
     stats->pairs_logical = c.pairs_logical; stats->pairs_scanned = c.pairs_scanned; stats->pairs_replayed = c.pairs_replayed;
     stats->tasks_processed = c.tasks_processed; stats->tasks_allocated = c.tasks_allocated; stats->tasks_pipelined = c.tasks_pipelined;
     stats->visits = c.visits; stats->kernel_launches = E.launches; stats->n_classes = B.C;
-    stats->scans = c.scans; stats->rescans = c.rescans;
+    stats->scans = c.scans; stats->rescans = c.rescans; stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
     uint32_t jr = 0;
     for (uint32_t j = 0; j < J; ++j) if (S.job_placed[j] && ssn_job_ready(S, j)) ++jr;
     stats->jobs_ready = jr;
@@ -268,8 +369,8 @@ int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, kb_decis
   std::vector<uint64_t> buf(kbemu_buf_u64(E));
   const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To) + 1024;
   while (!E->S.ctl->done) {
-    emu_scan(*E, buf.data());
-    emu_replay(*E, buf.data());
+    if (E->S.overlap) emu_launch_overlap(*E);
+    else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
     if (E->launches > guard) { g_err = "emulated cycle did not terminate"; delete E; return KB_E_STATE; }
   }
   int rc = kbemu_finish(E, out, stats, node_idle, node_releasing, node_used, node_pods, node_nz_cpu, node_nz_mem, node_ports,
