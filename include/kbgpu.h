@@ -162,6 +162,9 @@ typedef struct kb_plugin_conf {
   const kb_tier* tiers;
 } kb_plugin_conf;
 
+#define KB_ENGINE_NO_OVERLAP    (1u << 0) /* never run the scan of the next visit concurrently with the replay */
+#define KB_ENGINE_FORCE_OVERLAP (1u << 1) /* always (single GPU); default: only when the scan dominates (large N) */
+
 typedef struct kb_engine_opts {
   uint32_t abi_version;     /* KB_ABI_VERSION */
   int32_t  device;          /* CUDA device ordinal */
@@ -171,7 +174,7 @@ typedef struct kb_engine_opts {
   int32_t  rank;
   int32_t  world_size;
   const void* nccl_unique_id;
-  uint32_t flags;           /* reserved, 0 */
+  uint32_t flags;           /* KB_ENGINE_* bits */
 } kb_engine_opts;
 
 typedef struct kb_decision {

@@ -232,7 +232,7 @@ struct BuiltSession {
 
 // Everything kb_session_load does before touching the device.  `max_grid` = scan CTAs (SM count).
 inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e,
-                         uint32_t rank = 0, uint32_t world = 1) {
+                         uint32_t rank = 0, uint32_t world = 1, int overlap_mode = -1 /* -1 auto, 0 off, 1 on */) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
@@ -327,7 +327,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   const uint32_t n_groups = (B.tile_hi - B.tile_lo + B.tpi - 1) / B.tpi;
   // overlap mode (one GPU) keeps one SM for the replayer CTA
-  const uint32_t grid = std::max(1u, std::min(n_groups, (world <= 1 && GMAX > 1) ? GMAX - 1 : GMAX));
+  const uint32_t grid = std::max(1u, std::min(n_groups, GMAX > 1 ? GMAX - 1 : GMAX));   // one SM stays free for the replayer CTA
   om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
   om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
   om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
@@ -512,7 +512,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
       }
     }
   }
-  B.overlap = (world <= 1) ? 1u : 0u;
+  // overlap pays when the scan side (several tile groups per CTA + a wide merge) rivals the replay side
+  B.overlap = (world <= 1) ? (overlap_mode < 0 ? ((N >= 65536 && Q == 1) ? 1u : 0u) : (uint32_t)overlap_mode) : 0u;
   Ctl& c0 = *H.ctl;
   memset(&c0, 0, sizeof c0);
   c0.cur_job = -1;

@@ -91,6 +91,7 @@ struct kb_engine {
   float load_ms = 0;
   float last_kernel_ms = 0;
   int sm_count = 148;
+  int overlap_mode = -1;
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
   DevSession graph_dev{};              // kernel parameter the graph was captured with
@@ -175,6 +176,7 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   kb_engine* e = new kb_engine();
   e->device = opts->device;
   e->rank = world > 1 ? opts->rank : 0; e->world = world;
+  e->overlap_mode = (opts->flags & KB_ENGINE_NO_OVERLAP) ? 0 : (opts->flags & KB_ENGINE_FORCE_OVERLAP) ? 1 : -1;
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
       (c = cudaMallocHost(&e->h_ctl, sizeof(Ctl))) != cudaSuccess) {
@@ -212,7 +214,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->loaded = false;
   BuiltSession B;
   BuildErr be;
-  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world))
+  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode))
     return fail(e, rc, "%s", be.msg.c_str());
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q, C = B.C, NT = B.NT, ncols = B.ncols, To = B.To, grid = B.grid;
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;

@@ -66,7 +66,7 @@ def _p(a, t):
 class Engine:
     """One kb_engine.  Not thread-safe (like the single runOnce goroutine of the reference)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: Optional[bytes] = None):
+    def __init__(self, device: int = 0, rank: int = 0, world_size: int = 1, nccl_unique_id: Optional[bytes] = None, flags: int = 0):
         self.L = load_library()
         self._h = C.c_void_p()
         opts = abi.kb_engine_opts()
@@ -76,7 +76,7 @@ class Engine:
         opts.world_size = world_size
         self._uid = (C.c_char * 128).from_buffer_copy(nccl_unique_id) if nccl_unique_id else None
         opts.nccl_unique_id = C.cast(self._uid, C.c_void_p) if self._uid is not None else None
-        opts.flags = 0
+        opts.flags = flags
         rc = self.L.kb_engine_create(C.byref(opts), C.byref(self._h))
         if rc != 0:
             raise KbError(rc, "kb_engine_create: " + self.L.kb_last_error(None).decode())

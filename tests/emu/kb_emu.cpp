@@ -304,7 +304,8 @@ const char* kbemu_last_error(void) { return g_err.c_str(); }
 void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world) {
   Emu* E = new Emu();
   BuildErr be;
-  if (build_session(snap, conf, 148, E->B, &be, rank, world)) { g_err = be.msg; delete E; return nullptr; }
+  // the emulation always exercises the overlap protocol on one rank (the device enables it by size)
+  if (build_session(snap, conf, 148, E->B, &be, rank, world, 1)) { g_err = be.msg; delete E; return nullptr; }
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   return E;
 }

@@ -80,6 +80,24 @@ def test_random_sessions_all_confs(eng, seed):
         run_and_check(eng, s, conf, f"seed{seed}/{cname}")
 
 
+def test_overlap_mode_is_bit_exact():
+    """KB_ENGINE_FORCE_OVERLAP: scanners run ahead on the predicted class while one CTA replays (exclusion + patch)."""
+    e = engine.Engine(device=0, flags=2)
+    try:
+        for name in ("c2",):
+            s, conf = synth.make(name)
+            run_and_check(e, s, conf, name + "/overlap")
+        for seed in range(6):
+            s = synth.random_session(100 + seed, tasks=200 + 40 * seed, jobs=12 + seed, nodes=150 + 60 * seed, queues=1 + seed % 3,
+                                     min_member_frac=[0.0, 0.5, 1.0][seed % 3], hetero=[0, 0.3, 1.0][seed % 3], prio_levels=2)
+            for cname in ("default", "c2", "nogang", "weights"):
+                run_and_check(e, s, CONFS[cname], f"overlap seed{seed}/{cname}")
+        s = synth.generate(synth.SynthSpec("wide", tasks=600, jobs=60, nodes=148 * 128 * 2 + 77, seed=99))
+        run_and_check(e, s, PluginConf.default(), "wide/overlap")
+    finally:
+        e.close()
+
+
 def test_long_run_forces_rescans(eng):
     s = synth.random_session(7, tasks=400, jobs=1, nodes=300, hetero=0.0, oversub=0.5)
     run_and_check(eng, s, synth.conf_c2(), "long-run")

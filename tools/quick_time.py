@@ -6,7 +6,8 @@ from kube_batch_b200 import engine, synth
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
 reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 snap, conf = synth.make(name)
-eng = engine.Engine(0)
+flags = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+eng = engine.Engine(0, flags=flags)
 t0 = time.time(); eng.load(snap, conf); t1 = time.time()
 print(f"{name}: T={snap.T} N={snap.N} J={snap.J} load {1e3*(t1-t0):.1f} ms")
 for i in range(reps):
