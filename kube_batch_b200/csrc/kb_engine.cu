@@ -81,9 +81,6 @@ struct kb_engine {
   int32_t* d_job_ready0 = nullptr;     // [J] (immutable slab)
   Ctl* h_ctl = nullptr;                // pinned
   kb_decision* h_dec = nullptr;        // pinned [T]
-  size_t off_tiles = 0, off_used = 0, off_job_ready = 0, off_job_share = 0, off_q_share = 0, off_q_alloc = 0;
-  size_t off_q_deserved_imm = 0;
-  std::vector<uint32_t> job_placed_host;
   std::vector<int32_t> job_min_avail_host;
   uint32_t gang_ready = 0;
   uint32_t scan_grid = 1;
@@ -256,8 +253,6 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->d_task_class = (uint32_t*)(e->d_imm + oi.task_class);
   e->d_job_ready0 = (int32_t*)(e->d_imm + oi.job_ready0);
   e->R = R; e->W = W; e->N = N; e->T = T; e->J = J; e->Q = Q; e->C = C; e->NT = NT; e->ncols = ncols; e->To = To;
-  e->off_tiles = om.tiles; e->off_used = om.used; e->off_job_ready = om.job_ready; e->off_job_share = om.job_share;
-  e->off_q_share = om.q_share; e->off_q_alloc = om.q_alloc; e->off_q_deserved_imm = oi.q_des;
   e->gang_ready = hc.gang_ready;
   e->job_min_avail_host = B.job_min_avail;
   e->scan_grid = grid;
