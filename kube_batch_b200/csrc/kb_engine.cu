@@ -216,7 +216,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q, C = B.C, NT = B.NT, ncols = B.ncols, To = B.To, grid = B.grid;
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;
   Slab& mut = B.mut; Slab& imm = B.imm;
-  const OffMut& om = B.om; const OffImm& oi = B.oi;
+  const OffImm& oi = B.oi;
   const HostConf& hc = B.hc;
 
   // ---------------- upload ----------------
