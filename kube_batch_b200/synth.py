@@ -38,6 +38,8 @@ class SynthSpec:
     oversub: float = 1.3             # demand / free capacity on the scarcest of cpu, mem
     hetero_job_frac: float = 0.0     # fraction of jobs whose tasks are NOT identical
     prio_levels: int = 1
+    R: int = 3                       # resource dims: cpu, memory, nvidia.com/gpu, then extra scalars
+    W: int = 2                       # 64-bit words per label / taint / port mask
     seed: Optional[int] = None
     conf: Optional[PluginConf] = None
 
@@ -78,7 +80,8 @@ def config_conf(name: str) -> PluginConf:
 
 def generate(spec: SynthSpec) -> Snapshot:
     rng = np.random.Generator(np.random.PCG64(spec.seed if spec.seed is not None else 0xB200))
-    R, W = 3, 2
+    R, W = spec.R, spec.W
+    assert 3 <= R <= abi.KB_MAX_R and 2 <= W <= abi.KB_MAX_W
     N, Jp, Q = spec.nodes, spec.jobs, spec.queues
     # pending tasks per job
     base = spec.tasks // Jp
@@ -95,16 +98,24 @@ def generate(spec: SynthSpec) -> Snapshot:
     else:
         shape_id = rng.choice(3, size=N, p=NODE_PROBS)
     shapes = np.array(NODE_SHAPES, dtype=np.float64)
-    alloc = shapes[shape_id].T.copy()                     # [R][N]
+    alloc = np.zeros((R, N))
+    alloc[:3] = shapes[shape_id].T                        # [R][N]
+    present = np.where(alloc[2] > 0, 1 << 2, 0).astype(np.uint32)
+    for r in range(3, R):                                 # extra scalar resources on a third of the nodes
+        has = rng.random(N) < 0.33
+        alloc[r] = np.where(has, 4000.0, 0.0)
+        present |= np.where(has, 1 << r, 0).astype(np.uint32)
     s.node_allocatable[:] = alloc
-    s.node_alloc_present[:] = np.where(alloc[2] > 0, 1 << 2, 0).astype(np.uint32)
+    s.node_alloc_present[:] = present
     s.node_alloc_cpu[:] = alloc[0].astype(np.int64)
     s.node_alloc_mem[:] = alloc[1].astype(np.int64)
     s.node_max_pods[:] = 110
     zone = rng.integers(0, 3, size=N)
     s.node_labels[0] = (np.uint64(1) << zone.astype(np.uint64))
-    s.node_labels[1] = np.where(rng.random(N) < 0.5, np.uint64(1) << np.uint64(5), np.uint64(0))
+    s.node_labels[W - 1] = np.where(rng.random(N) < 0.5, np.uint64(1) << np.uint64(5), np.uint64(0))
     s.node_taints[0] = np.where(rng.random(N) < 0.05, np.uint64(1), np.uint64(0))
+    if W > 2:                                             # a second taint atom in the last word
+        s.node_taints[W - 1] = np.where(rng.random(N) < 0.03, np.uint64(1) << np.uint64(9), np.uint64(0))
     s.node_ports[0] = np.where(rng.random(N) < 0.01, np.uint64(1), np.uint64(0))
     flags = np.zeros(N, dtype=np.uint32)
     u = rng.random(N)
@@ -137,11 +148,16 @@ def generate(spec: SynthSpec) -> Snapshot:
         cpu = np.where(ht, rng.choice(TASK_CPU, size=T), cpu)
         mem = np.where(ht, rng.choice(TASK_MEM, size=T), mem)
     s.task_resreq[0], s.task_resreq[1], s.task_resreq[2] = cpu, mem, gpu
+    extra_present = np.zeros(T, dtype=np.uint32)
+    for r in range(3, R):                                 # ~6 % of the jobs ask for one unit of an extra scalar
+        wants = (rng.random(Jp) < 0.06)[tj]
+        s.task_resreq[r] = np.where(wants, 1000.0, 0.0)
+        extra_present |= np.where(wants, 1 << r, 0).astype(np.uint32)
     s.task_initreq[:] = s.task_resreq
     # a few pods carry an init container larger than the sum of containers (api/pod_info.go:53-73)
     big_init = rng.random(T) < 0.01
     s.task_initreq[0] = np.where(big_init, s.task_initreq[0] + 500, s.task_initreq[0])
-    s.task_res_present[:] = 1 << 2                       # BuildResourceList always lists nvidia.com/gpu
+    s.task_res_present[:] = (1 << 2) | extra_present      # BuildResourceList always lists nvidia.com/gpu
     s.task_nz_cpu[:] = cpu.astype(np.int64)
     s.task_nz_mem[:] = mem.astype(np.int64)
     zt = job_zone[tj]
@@ -149,9 +165,11 @@ def generate(spec: SynthSpec) -> Snapshot:
     at = job_aff[tj]
     s.task_n_aff_terms[:] = np.where(at, 2, 0)
     s.task_aff_terms[0, 0] = np.where(at, np.uint64(1), np.uint64(0))             # term 0: zone a ...
-    s.task_aff_terms[0, 1] = np.where(at, np.uint64(1) << np.uint64(5), np.uint64(0))  # ... AND disk=ssd
+    s.task_aff_terms[0, W - 1] = np.where(at, np.uint64(1) << np.uint64(5), np.uint64(0))  # ... AND disk=ssd
     s.task_aff_terms[1, 0] = np.where(at, np.uint64(2), np.uint64(0))             # term 1: zone b
     s.task_tol[0] = np.where(job_tol[tj], np.uint64(1), np.uint64(0))
+    if W > 2:
+        s.task_tol[W - 1] = np.where((rng.random(Jp) < 0.5)[tj], np.uint64(1) << np.uint64(9), np.uint64(0))
     pt = job_port[tj]
     s.task_port_own[0] = np.where(pt, np.uint64(1), np.uint64(0))
     s.task_port_conflict[0] = s.task_port_own[0]
@@ -180,7 +198,8 @@ def generate(spec: SynthSpec) -> Snapshot:
     # filler pods are 1/64-of-the-node bricks (nz == request: requests are always set)
     brick = np.stack([alloc[0] / 64.0, alloc[1] / 64.0, np.zeros(N)])     # [R][N], integral for every shape
     k = np.floor(node_util * 64.0).astype(np.int64)
-    used = brick * k[None, :]
+    used = np.zeros((R, N))
+    used[:3] = brick * k[None, :]
     gpu_used = np.where(alloc[2] > 0, 1000.0 * rng.integers(0, 5, size=N), 0.0)
     used[2] = gpu_used
     s.node_used[:] = used
@@ -190,7 +209,8 @@ def generate(spec: SynthSpec) -> Snapshot:
     s.node_nz_mem[:] = used[1].astype(np.int64)
     # ~2% of nodes carry one Releasing pod (deleted, still terminating): Idle shrinks, Releasing grows
     rel = (rng.random(N) < 0.02) & (s.node_idle[0] >= 4000) & (s.node_idle[1] >= 8 * GiB)
-    relreq = np.array([4000.0, 8.0 * GiB, 0.0])
+    relreq = np.zeros(R)
+    relreq[0], relreq[1] = 4000.0, 8.0 * GiB
     s.node_releasing[:] = np.where(rel[None, :], relreq[:, None], 0.0)
     s.node_idle[:] -= s.node_releasing
     s.node_used[:] += s.node_releasing
@@ -221,10 +241,10 @@ def make(name: str) -> Tuple[Snapshot, PluginConf]:
 # ------------------------------------------------------------------------------------------------
 def random_session(seed: int, tasks: int = 60, jobs: int = 8, nodes: int = 12, queues: int = 1,
                    min_member_frac: float = 1.0, hetero: float = 0.3, prio_levels: int = 3,
-                   oversub: float = 1.3) -> Snapshot:
+                   oversub: float = 1.3, R: int = 3, W: int = 2) -> Snapshot:
     spec = SynthSpec(f"rand{seed}", tasks=tasks, jobs=jobs, nodes=nodes, queues=queues,
                      min_member_frac=min_member_frac, hetero_job_frac=hetero, prio_levels=prio_levels,
-                     oversub=oversub, seed=seed)
+                     oversub=oversub, seed=seed, R=R, W=W)
     s = generate(spec)
     rng = np.random.Generator(np.random.PCG64(seed ^ 0x5EED))
     # sprinkle BestEffort (empty Resreq) tasks — allocate must skip them (allocate.go:113-118)

@@ -61,6 +61,15 @@ def test_random_sessions_all_confs(seed):
         check(s, conf, f"seed{seed}/{cname}")
 
 
+@pytest.mark.parametrize("R,W", [(4, 3), (6, 4), (8, 4), (5, 2)])
+def test_wide_records_more_dims_and_mask_words(R, W):
+    # wider node records: extra scalar resources (R) and more label / taint / port mask words (W)
+    for seed in range(3):
+        s = synth.random_session(seed + 50, tasks=150, jobs=15, nodes=300, queues=2, hetero=0.3, R=R, W=W)
+        for cname in ("default", "c2"):
+            check(s, CONFS[cname], f"R{R}W{W}/seed{seed}/{cname}")
+
+
 def test_long_run_forces_rescans():
     # one job, 400 identical tasks, spreading score: > DMAX distinct nodes get dirtied inside one run
     s = synth.random_session(7, tasks=400, jobs=1, nodes=300, hetero=0.0, oversub=0.5)

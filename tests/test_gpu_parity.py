@@ -98,6 +98,20 @@ def test_overlap_mode_is_bit_exact():
         e.close()
 
 
+@pytest.mark.parametrize("R,W", [(4, 3), (6, 4), (8, 4), (5, 2)])
+def test_wide_records_more_dims_and_mask_words(eng, R, W):
+    """Generic tile geometry: ncols = 2R + 6 + 3W up to 34 columns -> wider TMA tiles, fewer tiles per scan iteration."""
+    for seed in range(3):
+        s = synth.random_session(seed + 50, tasks=150, jobs=15, nodes=300 + 700 * seed, queues=2, hetero=0.3, R=R, W=W)
+        for cname in ("default", "c2"):
+            run_and_check(eng, s, CONFS[cname], f"R{R}W{W}/seed{seed}/{cname}")
+    fit, score = eng.predicate_score(0, min(s.T, 40))
+    for t in range(0, min(s.T, 40), 7):
+        of, osc = kbo.predicate_score(s, CONFS["c2"], t)
+        np.testing.assert_array_equal(of, fit[t])
+        np.testing.assert_array_equal(osc, score[t])
+
+
 def test_long_run_forces_rescans(eng):
     s = synth.random_session(7, tasks=400, jobs=1, nodes=300, hetero=0.0, oversub=0.5)
     run_and_check(eng, s, synth.conf_c2(), "long-run")
