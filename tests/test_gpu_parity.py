@@ -105,6 +105,7 @@ def test_wide_records_more_dims_and_mask_words(eng, R, W):
         s = synth.random_session(seed + 50, tasks=150, jobs=15, nodes=300 + 700 * seed, queues=2, hetero=0.3, R=R, W=W)
         for cname in ("default", "c2"):
             run_and_check(eng, s, CONFS[cname], f"R{R}W{W}/seed{seed}/{cname}")
+    eng.load(s, CONFS["c2"])              # back to the snapshot's initial node state
     fit, score = eng.predicate_score(0, min(s.T, 40))
     for t in range(0, min(s.T, 40), 7):
         of, osc = kbo.predicate_score(s, CONFS["c2"], t)
