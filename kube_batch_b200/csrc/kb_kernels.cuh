@@ -113,13 +113,17 @@ __device__ __forceinline__ uint64_t warp_merge_top32(uint64_t a, uint64_t b, int
 // CTA-level fold of the SCAN_WARPS per-warp lists into warp 0 (binary tree through shared memory).
 // Every thread of the CTA must call it; returns the folded list in warp 0.
 __device__ __forceinline__ uint64_t cta_fold_lists(uint64_t mine, uint64_t (*wlist)[KTOP], int warp, int lane) {
+  // ping-pong between the two halves of wlist (rows [0,8) and [8,16)): the writers of round r+1 are readers of round r,
+  // and they write the OTHER half, so one barrier per round is enough
+  int flip = 0;
 #pragma unroll
   for (int s = SCAN_WARPS / 2; s > 0; s >>= 1) {
-    if (warp >= s && warp < 2 * s) wlist[warp][lane] = mine;
+    if (warp >= s && warp < 2 * s) wlist[flip * (SCAN_WARPS / 2) + (warp - s)][lane] = mine;
     __syncthreads();
-    if (warp < s) mine = warp_merge_top32(mine, wlist[warp + s][lane], lane);
-    __syncthreads();
+    if (warp < s) mine = warp_merge_top32(mine, wlist[flip * (SCAN_WARPS / 2) + warp][lane], lane);
+    flip ^= 1;
   }
+  __syncthreads();      // callers reuse wlist right away
   return mine;
 }
 
@@ -370,9 +374,11 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
     const uint32_t node = t * TILE_NODES + part * 32u + lane;
     uint64_t key = 0;
     // overlap mode: the replayer CTA may be modifying these nodes right now; it contributes their keys itself
-    const uint32_t wbase = t * TILE_NODES + part * 32u;
-    const uint32_t d = sm.excl[lane] - wbase;
-    const unsigned exmask = __reduce_or_sync(FULL, ((uint32_t)lane < sm.n_excl && d < 32u) ? (1u << d) : 0u);
+    unsigned exmask = 0;
+    if (sm.n_excl) {
+      const uint32_t d = sm.excl[lane] - (t * TILE_NODES + part * 32u);
+      exmask = __reduce_or_sync(FULL, ((uint32_t)lane < sm.n_excl && d < 32u) ? (1u << d) : 0u);
+    }
     if (sub < tpi && t < S.tile_hi && node < S.N && !((exmask >> lane) & 1u)) {
       ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
       key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
