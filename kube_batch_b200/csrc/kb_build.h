@@ -253,7 +253,18 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   std::vector<uint32_t> task_class(T, 0);
   std::vector<uint8_t> task_empty(T, 0);
   {
-    std::unordered_map<std::string, uint32_t> dedup;
+    // open-addressing table keyed by a 64-bit hash of the record, verified with memcmp; a task usually equals its
+    // predecessor (PodGroups are homogeneous), so that case is checked first
+    std::vector<uint32_t> table(1024, 0xFFFFFFFFu);
+    std::vector<uint64_t> class_hash;
+    auto hash_rec = [](const ClassRec& c) {
+      const uint64_t* w = reinterpret_cast<const uint64_t*>(&c);
+      uint64_t h = 0x9E3779B97F4A7C15ull;
+      for (size_t i = 0; i < sizeof(ClassRec) / 8; ++i) { h ^= w[i] + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2); h *= 0xFF51AFD7ED558CCDull; h ^= h >> 32; }
+      return h;
+    };
+    static_assert(sizeof(ClassRec) % 8 == 0, "ClassRec is hashed as 64-bit words");
+    uint32_t prev_class = 0xFFFFFFFFu;
     for (uint32_t t = 0; t < T; ++t) {
       if (s->task_flags[t] & (KB_TASK_HAS_POD_AFFINITY | KB_TASK_HAS_PREFERRED_NODE_AFFINITY))
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod / preferred node affinity terms: outside this build (no CPU fallback)", t);
@@ -276,10 +287,28 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         for (uint32_t a = 0; a < c.n_aff; ++a) c.aff[a][w] = s->task_aff_terms[((size_t)a * W + w) * T + t];
       }
       task_empty[t] = res_is_empty(R, [&](uint32_t k) { return c.resreq[k]; }) ? 1 : 0;   // allocate.go:113-118
-      std::string key(reinterpret_cast<const char*>(&c), sizeof c);
-      auto it = dedup.find(key);
-      if (it == dedup.end()) { it = dedup.emplace(std::move(key), (uint32_t)classes.size()).first; classes.push_back(c); }
-      task_class[t] = it->second;
+      if (prev_class != 0xFFFFFFFFu && memcmp(&classes[prev_class], &c, sizeof c) == 0) { task_class[t] = prev_class; continue; }
+      const uint64_t h = hash_rec(c);
+      size_t mask = table.size() - 1, slot = (size_t)h & mask;
+      uint32_t found = 0xFFFFFFFFu;
+      while (table[slot] != 0xFFFFFFFFu) {
+        const uint32_t id = table[slot];
+        if (class_hash[id] == h && memcmp(&classes[id], &c, sizeof c) == 0) { found = id; break; }
+        slot = (slot + 1) & mask;
+      }
+      if (found == 0xFFFFFFFFu) {
+        found = (uint32_t)classes.size();
+        classes.push_back(c); class_hash.push_back(h);
+        table[slot] = found;
+        if (classes.size() * 2 > table.size()) {            // grow + rehash
+          std::vector<uint32_t> nt(table.size() * 4, 0xFFFFFFFFu);
+          const size_t nm = nt.size() - 1;
+          for (uint32_t id = 0; id < classes.size(); ++id) { size_t sl = (size_t)class_hash[id] & nm; while (nt[sl] != 0xFFFFFFFFu) sl = (sl + 1) & nm; nt[sl] = id; }
+          table.swap(nt);
+        }
+      }
+      task_class[t] = found;
+      prev_class = found;
     }
   }
   if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); }
