@@ -150,6 +150,10 @@ def run_ours(args, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dist = None
     uid = None
+    # NCCL prints its version banner on the C-level stdout: keep stdout clean for the ONE JSON line
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -286,7 +290,10 @@ def run_ours(args, rank, world, local_rank):
         "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
         "lib": eng.L.kb_version().decode(),
     }
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
     print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
