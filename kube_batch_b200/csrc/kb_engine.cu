@@ -277,7 +277,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
       else visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
       if (e->world > 1) {
         ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
-        replay_kernel<<<1, 32, e->replay_smem, e->stream>>>(e->dev);
+        replay_kernel<<<1, 64, e->replay_smem, e->stream>>>(e->dev);
       }
     }
     cudaGraph_t g = nullptr;
@@ -317,7 +317,7 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
         visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
         int rc = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream);
         if (rc != 0) return fail(e, KB_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
-        replay_kernel<<<1, 32, e->replay_smem, e->stream>>>(e->dev);
+        replay_kernel<<<1, 64, e->replay_smem, e->stream>>>(e->dev);
       }
       CUDA_TRY(e, cudaGetLastError());
       launches += 2 * BATCH;

@@ -137,6 +137,8 @@ struct VisitSmem {
   uint32_t is_last;
   uint32_t n_excl;
   uint32_t excl[32];                         // nodes the scanners skip (overlap mode)
+  uint32_t sink;                             // keeps the shadow prefetch loads alive
+  Ctl ctl2;                                  // replay_kernel's shadow warp reads its own copy
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -395,6 +397,59 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
   return mylist;
 }
 
+__device__ __forceinline__ void load_ctl(Ctl& dst, const Ctl* g, int lane) {
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+  for (uint32_t i = lane; i < sizeof(Ctl) / 4; i += 32) d[i] = __ldcg(src + i);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Shadow prefetch (warp 1 of the last CTA, concurrent with warp 0's gather / look-ahead / steps): touch the
+// job-level state of the current visit and what select_next_visit / setup_run will most likely read next (the head of
+// the queue's static job list), so that warp 0 finds it in L1 instead of paying a chain of L2 round trips.
+// Read-only; the sum goes to `sink` only to keep the loads alive.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& c, const int lane, uint32_t* sink) {
+  if (c.done || c.cur_job < 0) return;
+  const uint32_t j = (uint32_t)c.cur_job, q = c.cur_queue, R = S.cf.R;
+  uint32_t acc = 0;
+  const uint32_t pos = S.job_pos[j], end = S.job_ord_off[j + 1];
+  acc += (uint32_t)S.job_ready[j] + (uint32_t)S.job_min_avail[j] + S.job_placed[j];
+  if (pos + lane < end) acc += S.ord_task[pos + lane];
+  if ((uint32_t)lane < R) {
+    acc += (uint32_t)double_as_u64(S.job_alloc[(size_t)lane * S.J + j]);
+    acc += (uint32_t)double_as_u64(S.q_allocated[(size_t)lane * S.Q + q]) + (uint32_t)double_as_u64(S.q_deserved[(size_t)lane * S.Q + q]);
+  }
+  acc += S.q_deserved_present[q] + (uint32_t)double_as_u64(S.q_share[q]) + (uint32_t)double_as_u64(S.job_share[j]);
+  const uint32_t h = S.q_static_head[q];
+  if (h < S.q_static_off[q + 1]) {
+    const uint32_t jn = S.q_static[h];
+    const uint32_t pn = S.job_pos[jn], en = S.job_ord_off[jn + 1];
+    acc += (uint32_t)S.job_ready[jn] + (uint32_t)S.job_min_avail[jn] + S.job_placed[jn] + S.job_queue[jn];
+    if (pn < en) acc += S.ord_class[pn] + S.ord_run[pn];
+    if (pn + lane < en) acc += S.ord_task[pn + lane];
+    if ((uint32_t)lane < R) acc += (uint32_t)double_as_u64(S.job_alloc[(size_t)lane * S.J + jn]);
+  }
+  if (S.Q > 1) {
+    // several queues: the Go-heap emulation walks qheap from the root (pop) and from the tail (push) and compares
+    // proportion shares; pull the first two levels-of-64, the tail's parent chain and every queue's share / deserved /
+    // allocated rows
+    const uint32_t len = c.qheap_len;
+    if ((uint32_t)lane < len) acc += S.qheap[lane];
+    if (32u + lane < len) acc += S.qheap[32 + lane];
+    const uint32_t up = ((len + 1) >> lane);                 // ancestors of the push position `len`
+    if (up >= 1 && up - 1 < len) acc += S.qheap[up - 1];
+    for (uint32_t qq = lane; qq < S.Q; qq += 32) {
+      acc += (uint32_t)double_as_u64(S.q_share[qq]) + (uint32_t)S.q_ctime[qq] + S.q_static_head[qq] + S.q_static_off[qq + 1];
+      for (uint32_t k = 0; k < R; ++k)
+        acc += (uint32_t)double_as_u64(S.q_deserved[(size_t)k * S.Q + qq]) + (uint32_t)double_as_u64(S.q_allocated[(size_t)k * S.Q + qq]);
+    }
+    if ((uint32_t)lane < c.dyn_len) acc += S.dyn_jobs[lane];
+  }
+  acc = __reduce_add_sync(FULL, acc);
+  if (lane == 0) *sink = acc;
+}
+
 // ---------------------------------------------------------------------------------------------
 // visit_kernel
 // ---------------------------------------------------------------------------------------------
@@ -472,6 +527,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
   }
   if (tid == 0) sm.ctl = *gctl;
   __syncthreads();
+  if (warp == 1) shadow_prefetch(S, sm.ctl, lane, &sm.sink);
   if (warp != 0) return;
 
   // ---------------- exact replay + control: warp 0 only ----------------
@@ -495,11 +551,6 @@ visit_kernel(const __grid_constant__ DevSession S) {
 // The merged list is exact for the table state at the end of the launch: every node is either scanned unmodified or
 // patched from the replayer's own up-to-date copy.  A wrong prediction only costs the overlap of one launch.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void load_ctl(Ctl& dst, const Ctl* g, int lane) {
-  const uint32_t* src = reinterpret_cast<const uint32_t*>(g);
-  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
-  for (uint32_t i = lane; i < sizeof(Ctl) / 4; i += 32) d[i] = __ldcg(src + i);
-}
 
 __global__ void __launch_bounds__(SCAN_THREADS)
 visit_overlap_kernel(const __grid_constant__ DevSession S) {
@@ -526,6 +577,10 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
     __syncthreads();
     const uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, n_scanners, tid, lane, warp);
     if (warp == 0) S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
+  } else if (warp == 1) {
+    load_ctl(sm.ctl2, gctl, lane);
+    __syncwarp();
+    shadow_prefetch(S, sm.ctl2, lane, &sm.sink);
   } else if (warp == 0) {
     // ---------------- replayer ----------------
     load_ctl(sm.ctl, gctl, lane);
@@ -628,13 +683,19 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
 // lane finds the record of its candidate in the owning rank's block and the shared epilogue replays.
 // Every rank runs this identically on identical inputs, so every replica applies the same updates.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(64)
 replay_kernel(const __grid_constant__ DevSession S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   Ctl* gctl = S.ctl;
   if (*((volatile uint32_t*)&gctl->done)) return;
+  if (threadIdx.x >= 32) {                       // warp 1: shadow prefetch from its own copy of the control block
+    load_ctl(sm.ctl2, gctl, lane);
+    __syncwarp();
+    shadow_prefetch(S, sm.ctl2, lane, &sm.sink);
+    return;
+  }
   const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
