@@ -347,7 +347,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
 // skipped.  Every thread of the CTA calls it; the CTA's list is returned in warp 0.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx,
-                                               const uint32_t n_scanners, const int tid, const int lane, const int warp) {
+                                               const uint32_t n_scanners, const uint32_t cls_id, const int tid, const int lane, const int warp) {
   const uint32_t tile_u64 = S.ncols * TILE_NODES;
   const uint32_t tile_bytes = tile_u64 * 8u;
   // ---------------- scan: tile GROUPS blockIdx.x, +gridDim.x, ...: S.tpi tiles per iteration, double-buffered TMA ----------------
@@ -363,6 +363,13 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
       tma_load_1d(tilebuf + ((size_t)buf * tpi + k) * tile_u64, S.tiles + (size_t)(t0 + k) * tile_u64, tile_bytes, &sm.mbar[buf]);
   };
   if (tid == 0 && n_local > 0) issue_group(firstg, 0);
+  {
+    // class record -> shared memory (broadcast reads afterwards) while the first tiles are in flight
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
   const uint32_t sub = (uint32_t)warp >> 2, part = (uint32_t)warp & 3u;    // which tile of the group / which 32 nodes of it
   uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
   for (uint32_t it = 0; it < n_local; ++it) {
@@ -435,8 +442,7 @@ __device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& 
     // proportion shares; pull the first two levels-of-64, the tail's parent chain and every queue's share / deserved /
     // allocated rows
     const uint32_t len = c.qheap_len;
-    if ((uint32_t)lane < len) acc += S.qheap[lane];
-    if (32u + lane < len) acc += S.qheap[32 + lane];
+    for (uint32_t i = (uint32_t)lane * 32u; i < len && i < 4096u; i += 1024u) acc += S.qheap[i];   // top 12 levels, one load per line
     const uint32_t up = ((len + 1) >> lane);                 // ancestors of the push position `len`
     if (up >= 1 && up - 1 < len) acc += S.qheap[up - 1];
     for (uint32_t qq = lane; qq < S.Q; qq += 32) {
@@ -465,18 +471,12 @@ visit_kernel(const __grid_constant__ DevSession S) {
   if (*((volatile uint32_t*)&gctl->done)) return;
   const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
 
-  // class record -> shared memory (broadcast reads afterwards)
-  {
-    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
-    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
-    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
-  }
   if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; }
   if (tid < 32) sm.excl[tid] = 0;
   __syncthreads();
   const long long t_start = clock64();
 
-  uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, gridDim.x, tid, lane, warp);
+  uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp);
   if (warp == 0) {
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
     sm.keys[lane] = mylist;
@@ -567,15 +567,10 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
   if (!is_replayer) {
     // ---------------- scanner ----------------
     const uint32_t cls_id = *((volatile uint32_t*)&gctl->scan_class);
-    {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
-      for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
-    }
     if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = *((volatile uint32_t*)&gctl->n_excl); }
     if (tid < 32) sm.excl[tid] = *((volatile uint32_t*)&gctl->excl[tid]);
     __syncthreads();
-    const uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, n_scanners, tid, lane, warp);
+    const uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, n_scanners, cls_id, tid, lane, warp);
     if (warp == 0) S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
   } else if (warp == 1) {
     load_ctl(sm.ctl2, gctl, lane);
