@@ -137,6 +137,7 @@ struct VisitSmem {
   uint32_t is_last;
   uint32_t n_excl;
   uint32_t excl[32];                         // nodes the scanners skip (overlap mode)
+  double   used0[KB_MAX_R][32];              // NodeInfo.Used rows of the candidates, fetched at gather time
   uint32_t sink;                             // keeps the shadow prefetch loads alive
   Ctl ctl2;                                  // replay_kernel's shadow warp reads its own copy
 };
@@ -177,6 +178,8 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   uint32_t which = 0;                 // slot holding my CURRENT state
   bool cur_fi = false, next_fi = false, next_valid = false, modified = false;
   uint64_t next_key = 0;
+  // NodeInfo.Used of my candidate, fetched now so the write-back at the end does not wait for it
+  if (have) for (uint32_t k = 0; k < R; ++k) sm.used0[k][lane] = S.node_used[(size_t)k * S.N + my_node];
   if (have) {
     for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(rec_base + (size_t)cc * rec_stride);
     ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
@@ -303,7 +306,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     const uint64_t (*src)[32] = sm.slot[which];
     for (uint32_t cc = 0; cc < ncols; ++cc) gt_mine[(size_t)cc * TILE_NODES] = src[cc][lane];
     for (uint32_t k = 0; k < R; ++k) {             // Used.Add(Resreq) once per placement (node_info.go:203)
-      double u = S.node_used[(size_t)k * S.N + my_node];
+      double u = sm.used0[k][lane];
       for (uint32_t i = 0; i < my_cnt; ++i) u = KB_DADD(u, sm.cls.resreq[k]);
       S.node_used[(size_t)k * S.N + my_node] = u;
     }
@@ -491,6 +494,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
   if (!sm.is_last) return;
   __threadfence();
   const long long t_scan = clock64();
+  if (warp == SCAN_WARPS - 1) load_ctl(sm.ctl, gctl, lane);     // off the critical path: the folds below end with barriers
 
   // ---------------- K3: merge the per-CTA lists: every warp folds every 16th list, then the tree ----------------
   if (gridDim.x > 1) {
@@ -525,7 +529,6 @@ visit_kernel(const __grid_constant__ DevSession S) {
     }
     return;
   }
-  if (tid == 0) sm.ctl = *gctl;
   __syncthreads();
   if (warp == 1) shadow_prefetch(S, sm.ctl, lane, &sm.sink);
   if (warp != 0) return;
