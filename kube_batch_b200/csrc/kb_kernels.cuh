@@ -137,7 +137,6 @@ struct VisitSmem {
   uint32_t is_last;
   uint32_t n_excl;
   uint32_t excl[32];                         // nodes the scanners skip (overlap mode)
-  double   used0[KB_MAX_R][32];              // NodeInfo.Used rows of the candidates, fetched at gather time
   uint32_t sink;                             // keeps the shadow prefetch loads alive
   Ctl ctl2;                                  // replay_kernel's shadow warp reads its own copy
 };
@@ -178,8 +177,6 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   uint32_t which = 0;                 // slot holding my CURRENT state
   bool cur_fi = false, next_fi = false, next_valid = false, modified = false;
   uint64_t next_key = 0;
-  // NodeInfo.Used of my candidate, fetched now so the write-back at the end does not wait for it
-  if (have) for (uint32_t k = 0; k < R; ++k) sm.used0[k][lane] = S.node_used[(size_t)k * S.N + my_node];
   if (have) {
     for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(rec_base + (size_t)cc * rec_stride);
     ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
@@ -306,7 +303,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     const uint64_t (*src)[32] = sm.slot[which];
     for (uint32_t cc = 0; cc < ncols; ++cc) gt_mine[(size_t)cc * TILE_NODES] = src[cc][lane];
     for (uint32_t k = 0; k < R; ++k) {             // Used.Add(Resreq) once per placement (node_info.go:203)
-      double u = sm.used0[k][lane];
+      double u = S.node_used[(size_t)k * S.N + my_node];     // L1 hit: prefetched by the shadow warp
       for (uint32_t i = 0; i < my_cnt; ++i) u = KB_DADD(u, sm.cls.resreq[k]);
       S.node_used[(size_t)k * S.N + my_node] = u;
     }
@@ -419,10 +416,12 @@ __device__ __forceinline__ void load_ctl(Ctl& dst, const Ctl* g, int lane) {
 // the queue's static job list), so that warp 0 finds it in L1 instead of paying a chain of L2 round trips.
 // Read-only; the sum goes to `sink` only to keep the loads alive.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& c, const int lane, uint32_t* sink) {
+__device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& c, const int lane, uint32_t* sink, const uint64_t cand_key) {
   if (c.done || c.cur_job < 0) return;
   const uint32_t j = (uint32_t)c.cur_job, q = c.cur_queue, R = S.cf.R;
   uint32_t acc = 0;
+  if (cand_key)                                   // NodeInfo.Used rows of this lane's candidate (read at write-back time)
+    for (uint32_t k = 0; k < R; ++k) acc += (uint32_t)double_as_u64(S.node_used[(size_t)k * S.N + key_node(cand_key)]);
   const uint32_t pos = S.job_pos[j], end = S.job_ord_off[j + 1];
   acc += (uint32_t)S.job_ready[j] + (uint32_t)S.job_min_avail[j] + S.job_placed[j];
   if (pos + lane < end) acc += S.ord_task[pos + lane];
@@ -494,7 +493,16 @@ visit_kernel(const __grid_constant__ DevSession S) {
   if (!sm.is_last) return;
   __threadfence();
   const long long t_scan = clock64();
-  if (warp == SCAN_WARPS - 1) load_ctl(sm.ctl, gctl, lane);     // off the critical path: the folds below end with barriers
+  // control block: the loads are issued now by the last warp and land in registers while everybody merges
+  constexpr int CTLW = (int)((sizeof(Ctl) / 4 + 31) / 32);
+  uint32_t cw[CTLW];
+  if (warp == SCAN_WARPS - 1) {
+#pragma unroll
+    for (int i = 0; i < CTLW; ++i) {
+      const uint32_t idx = (uint32_t)i * 32u + lane;
+      cw[i] = idx < sizeof(Ctl) / 4 ? __ldcg(reinterpret_cast<const uint32_t*>(gctl) + idx) : 0u;
+    }
+  }
 
   // ---------------- K3: merge the per-CTA lists: every warp folds every 16th list, then the tree ----------------
   if (gridDim.x > 1) {
@@ -529,8 +537,15 @@ visit_kernel(const __grid_constant__ DevSession S) {
     }
     return;
   }
+  if (warp == SCAN_WARPS - 1) {
+#pragma unroll
+    for (int i = 0; i < CTLW; ++i) {
+      const uint32_t idx = (uint32_t)i * 32u + lane;
+      if (idx < sizeof(Ctl) / 4) reinterpret_cast<uint32_t*>(&sm.ctl)[idx] = cw[i];
+    }
+  }
   __syncthreads();
-  if (warp == 1) shadow_prefetch(S, sm.ctl, lane, &sm.sink);
+  if (warp == 1) shadow_prefetch(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
   if (warp != 0) return;
 
   // ---------------- exact replay + control: warp 0 only ----------------
@@ -578,7 +593,7 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
   } else if (warp == 1) {
     load_ctl(sm.ctl2, gctl, lane);
     __syncwarp();
-    shadow_prefetch(S, sm.ctl2, lane, &sm.sink);
+    shadow_prefetch(S, sm.ctl2, lane, &sm.sink, sm.ctl2.list[lane]);
   } else if (warp == 0) {
     // ---------------- replayer ----------------
     load_ctl(sm.ctl, gctl, lane);
@@ -691,7 +706,7 @@ replay_kernel(const __grid_constant__ DevSession S) {
   if (threadIdx.x >= 32) {                       // warp 1: shadow prefetch from its own copy of the control block
     load_ctl(sm.ctl2, gctl, lane);
     __syncwarp();
-    shadow_prefetch(S, sm.ctl2, lane, &sm.sink);
+    shadow_prefetch(S, sm.ctl2, lane, &sm.sink, 0ull);
     return;
   }
   const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
