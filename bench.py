@@ -286,6 +286,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
                 "what": "kb_session_load (host flatten + H2D) + kb_allocate (cycle + decisions D2H), wall clock"},
         "gpu_launches": launches,
+        "exchange": {0: "none (single GPU)", 1: "ncclAllGather per scan", 2: "fused peer-memory exchange (NVLink stores + flags) inside visit_kernel"}[int(st.exchange_mode)],
         "roofline": roofline, "roofline_matrix_kernel": matrix, "cpu_baseline": cpu_baseline, "clocks": clocks,
         "wall_ms_per_step_incl_flush": 1e3 * (t_wall1 - t_wall0) / args.steps,
         "lib": eng.L.kb_version().decode(),

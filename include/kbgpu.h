@@ -211,6 +211,8 @@ typedef struct kb_stats {
   uint64_t cyc_ctl;         /*   ... of cyc_replay: the control plane (after_run)                 */
   uint32_t predictions;     /* overlap mode: launches whose scan ran ahead on a predicted class   */
   uint32_t mispredictions;  /*   ... of which the prediction was wrong (that launch's scan is redone) */
+  uint32_t exchange_mode;   /* 0 single GPU, 1 NCCL all-gather per scan, 2 fused peer-memory exchange  */
+  uint32_t reserved1;
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

@@ -175,6 +175,8 @@ class kb_stats(C.Structure):
         ("cyc_ctl", C.c_uint64),
         ("predictions", C.c_uint32),
         ("mispredictions", C.c_uint32),
+        ("exchange_mode", C.c_uint32),
+        ("reserved1", C.c_uint32),
     ]
 
 

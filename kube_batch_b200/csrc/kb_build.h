@@ -555,6 +555,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   select_next_visit(H, c0);
   c0.scan_class = c0.cur_class;      // the first launch has no list yet: scan for the first visit, nothing excluded
   c0.n_excl = 0; c0.list_valid = 0; c0.patch_valid = 0;
+  c0.xchg_epoch = 1;
 
   B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.grid = grid;
   B.job_min_avail.assign(s->job_min_avail, s->job_min_avail + J);

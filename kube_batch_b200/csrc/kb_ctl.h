@@ -43,6 +43,7 @@ struct Ctl {
   uint32_t list_class, list_valid;
   uint32_t patch_valid;
   uint32_t predictions, mispredictions;
+  uint32_t xchg_epoch;     // peer-memory exchange: sequence number of the next scan (starts at 1; flags are zeroed per cycle)
   uint32_t excl[32];
   unsigned long long list[32];
   unsigned long long patch[32];
@@ -102,7 +103,16 @@ struct DevSession {
   uint32_t tpi;           // node tiles a scan CTA stages per iteration (sized to shared memory)
   uint64_t* sendbuf;      // [(1 + ncols) * 32]: keys[32], then columns [ncols][32]
   uint64_t* recvbuf;      // [world] x the same
+  // Peer-memory exchange (fused scan + exchange + replay, no NCCL inside the cycle): every rank exposes one region
+  //   recv[2 parities][KB_MAX_WORLD][P2P_RANK_U64] u64, then flags[2][KB_MAX_WORLD] u64
+  // through CUDA IPC; peer_base[r] is rank r's region as mapped into THIS process (peer_base[rank] is local).
+  uint32_t p2p;
+  uint64_t* peer_base[8];
 };
+constexpr uint32_t KB_MAX_WORLD = 8;
+constexpr uint32_t P2P_RANK_U64 = (1 + 2 * KB_MAX_R + 6 + 3 * KB_MAX_W) * 32;         // keys + widest record block
+constexpr uint32_t P2P_FLAG_OFF = 2 * KB_MAX_WORLD * P2P_RANK_U64;
+constexpr size_t   P2P_REGION_BYTES = ((size_t)P2P_FLAG_OFF + 2 * KB_MAX_WORLD) * 8;
 
 // ---- tile columns (u64 each, TILE_NODES entries per column) ----
 KB_HD uint32_t tile_ncols(uint32_t R, uint32_t W) { return 2 * R + 6 + 3 * W; }

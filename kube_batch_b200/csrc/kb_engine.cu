@@ -63,6 +63,11 @@ constexpr int kNcclUint64 = 5;   // ncclUint64 (nccl.h)
 
 struct kb_engine {
   ncclComm_t comm = nullptr;
+  // peer-memory exchange (world > 1): this rank's region and every rank's region as mapped here
+  uint64_t* p2p_local = nullptr;
+  uint64_t* p2p_peer[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool p2p = false;
+  unsigned char* d_xchg = nullptr;     // small device scratch for handle exchange / barriers
   int device = 0;
   int rank = 0, world = 1;
   cudaStream_t stream = nullptr;
@@ -122,6 +127,46 @@ void free_session(kb_engine* e) {
   if (e->h_dec) cudaFreeHost(e->h_dec);
   e->d_mut = e->d_pristine = e->d_imm = nullptr; e->h_dec = nullptr;
   e->loaded = false;
+}
+
+// Collective over e->comm.  Every rank allocates its exchange region, the IPC handles are all-gathered through NCCL,
+// peers are opened, and the outcome is all-gathered again so that all ranks agree on p2p vs NCCL.
+void setup_p2p(kb_engine* e) {
+  e->p2p = false;
+  const int W = e->world;
+  if (W > (int)KB_MAX_WORLD) return;
+  const char* off = getenv("KB_NO_P2P");
+  bool ok = !(off && off[0] == '1');
+  if (cudaMalloc(&e->d_xchg, 64 * 8 + 64) != cudaSuccess) return;
+  if (cudaMalloc(&e->p2p_local, P2P_REGION_BYTES) != cudaSuccess) { e->p2p_local = nullptr; ok = false; }
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof mine);
+  if (ok) {
+    cudaMemset(e->p2p_local, 0, P2P_REGION_BYTES);
+    if (cudaIpcGetMemHandle(&mine, e->p2p_local) != cudaSuccess) { ok = false; cudaGetLastError(); }
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  cudaMemcpy(e->d_xchg + (size_t)e->rank * 64, &mine, 64, cudaMemcpyHostToDevice);
+  if (g_nccl.AllGather(e->d_xchg + (size_t)e->rank * 64, e->d_xchg, 64, 0 /*ncclChar*/, e->comm, e->stream) != 0) return;
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return;
+  cudaIpcMemHandle_t all[8];
+  cudaMemcpy(all, e->d_xchg, (size_t)W * 64, cudaMemcpyDeviceToHost);
+  for (int r = 0; r < W && ok; ++r) {
+    if (r == e->rank) { e->p2p_peer[r] = e->p2p_local; continue; }
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; cudaGetLastError(); break; }
+    e->p2p_peer[r] = (uint64_t*)ptr;
+  }
+  // agree
+  unsigned char st = ok ? 1 : 0;
+  cudaMemcpy(e->d_xchg + 512 + e->rank, &st, 1, cudaMemcpyHostToDevice);
+  if (g_nccl.AllGather(e->d_xchg + 512 + e->rank, e->d_xchg + 512, 1, 0, e->comm, e->stream) != 0) return;
+  if (cudaStreamSynchronize(e->stream) != cudaSuccess) return;
+  unsigned char sts[8];
+  cudaMemcpy(sts, e->d_xchg + 512, (size_t)W, cudaMemcpyDeviceToHost);
+  bool all_ok = true;
+  for (int r = 0; r < W; ++r) all_ok = all_ok && sts[r] == 1;
+  e->p2p = all_ok;
 }
 
 }  // namespace
@@ -187,6 +232,7 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
     memcpy(id.internal, opts->nccl_unique_id, sizeof id.internal);
     int rc = g_nccl.CommInitRank(&e->comm, world, id, e->rank);
     if (rc != 0) { g_create_err = std::string("ncclCommInitRank: ") + g_nccl.GetErrorString(rc); kb_engine_destroy(e); return KB_E_NCCL; }
+    setup_p2p(e);      // collective; falls back to the NCCL exchange when peer memory is unavailable on any rank
   }
   *out = e;
   return KB_OK;
@@ -196,6 +242,9 @@ void kb_engine_destroy(kb_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   free_session(e);
+  for (int r = 0; r < 8; ++r) if (e->p2p_peer[r] && r != e->rank) cudaIpcCloseMemHandle(e->p2p_peer[r]);
+  if (e->p2p_local) cudaFree(e->p2p_local);
+  if (e->d_xchg) cudaFree(e->d_xchg);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
   if (e->ev0) cudaEventDestroy(e->ev0);
@@ -250,6 +299,8 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   B.bind(e->dev, e->d_mut, e->d_imm);
+  e->dev.p2p = (e->world > 1 && e->p2p) ? 1u : 0u;
+  for (int r = 0; r < 8; ++r) e->dev.peer_base[r] = e->p2p_peer[r];
   e->d_task_class = (uint32_t*)(e->d_imm + oi.task_class);
   e->d_job_ready0 = (int32_t*)(e->d_imm + oi.job_ready0);
   e->R = R; e->W = W; e->N = N; e->T = T; e->J = J; e->Q = Q; e->C = C; e->NT = NT; e->ncols = ncols; e->To = To;
@@ -275,7 +326,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
       if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
       else visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
-      if (e->world > 1) {
+      if (e->world > 1 && !e->dev.p2p) {
         ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
         replay_kernel<<<1, 64, e->replay_smem, e->stream>>>(e->dev);
       }
@@ -303,13 +354,20 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
   CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
+  if (e->world > 1 && e->dev.p2p) {
+    // a new cycle restarts the exchange sequence at 1: clear my flags, then make sure every rank has done so before
+    // anybody can raise one (the all-gather is only used as a stream-ordered barrier)
+    CUDA_TRY(e, cudaMemsetAsync(e->p2p_local + P2P_FLAG_OFF, 0, 2 * KB_MAX_WORLD * 8, e->stream));
+    if (g_nccl.AllGather(e->d_xchg + 520 + e->rank, e->d_xchg + 520, 1, 0, e->comm, e->stream) != 0)
+      return fail(e, KB_E_NCCL, "barrier all-gather failed");
+  }
   uint32_t launches = 0;
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
   const uint64_t cap = 4ull * ((uint64_t)e->J + e->To) + 1024;
   for (;;) {
     if (e->graph_exec) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
-      launches += (e->world == 1 ? 1 : 2) * BATCH;
+      launches += ((e->world == 1 || e->dev.p2p) ? 1 : 2) * BATCH;
     } else {
       // sharded node axis: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
       const size_t cnt = (size_t)(1 + e->ncols) * 32;
@@ -342,6 +400,7 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
   }
   CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (e->h_ctl->error == 2) return fail(e, KB_E_NCCL, "peer-memory exchange timed out waiting for another rank");
   if (e->h_ctl->error) return fail(e, KB_E_STATE, "device reported invariant violation %u", e->h_ctl->error);
   if (out && e->T) memcpy(out, e->h_dec, (size_t)e->T * sizeof(kb_decision));
   if (stats) {
@@ -359,6 +418,7 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
     stats->scans = c.scans; stats->rescans = c.rescans;
     stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total; stats->cyc_steps = c.cyc_steps; stats->cyc_ctl = c.cyc_ctl;
     stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
+    stats->exchange_mode = e->world == 1 ? 0u : (e->dev.p2p ? 2u : 1u);
     stats->h2d_bytes = (uint64_t)e->mut_bytes + e->imm_bytes;
     stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / BATCH) * sizeof(Ctl);
   }

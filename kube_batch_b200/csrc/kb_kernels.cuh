@@ -522,6 +522,67 @@ visit_kernel(const __grid_constant__ DevSession S) {
     acc = cta_fold_lists(acc, sm.wlist, warp, lane);
     if (warp == 0) sm.keys[lane] = acc;
   }
+  if (S.world > 1 && S.p2p) {
+    // ---------------- fused exchange over peer memory (NVLink): no NCCL, no second kernel ----------------
+    // Every rank pushes its top-32 keys + the candidates' node records into each peer's recv slot [parity][rank],
+    // fences system-wide, raises its flag there, then waits for all peers' flags in its own region.  A rank can run at
+    // most one scan ahead of a peer (it needs the peer's block to finish), so two parities are enough.
+    __syncthreads();
+    const uint32_t epoch = *((volatile uint32_t*)&gctl->xchg_epoch);
+    const uint32_t par = epoch & 1u;
+    if (warp == 0) {
+      const uint64_t k = sm.keys[lane];
+      if (k) {
+        const uint32_t n = key_node(k);
+        const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
+        for (uint32_t cc = 0; cc < S.ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(rec + (size_t)cc * TILE_NODES);
+      }
+    }
+    __syncthreads();
+    if ((uint32_t)warp < S.world) {
+      uint64_t* dst = S.peer_base[warp] + (size_t)(par * KB_MAX_WORLD + S.rank) * P2P_RANK_U64;
+      dst[lane] = sm.keys[lane];
+      for (uint32_t cc = 0; cc < S.ncols; ++cc) dst[(size_t)(1 + cc) * 32 + lane] = sm.slot[0][cc][lane];
+      __threadfence_system();
+      __syncwarp();
+      if (lane == 0) *((volatile uint64_t*)(S.peer_base[warp] + P2P_FLAG_OFF + par * KB_MAX_WORLD + S.rank)) = (uint64_t)epoch;
+    }
+    if (warp == 1) { load_ctl(sm.ctl2, gctl, lane); __syncwarp(); shadow_prefetch(S, sm.ctl2, lane, &sm.sink, 0ull); }
+    if (warp != 0) return;
+    // wait for every rank's block (bounded: ~2 s at 2 GHz, then the cycle is aborted with an error)
+    {
+      const volatile uint64_t* fl = S.peer_base[S.rank] + P2P_FLAG_OFF + par * KB_MAX_WORLD + lane;
+      const long long deadline = clock64() + 4000000000ll;
+      bool ok = true;
+      while ((uint32_t)lane < S.world && *fl != (uint64_t)epoch) {
+        if (clock64() > deadline) { ok = false; break; }
+      }
+      if (!__all_sync(FULL, ok)) {
+        if (lane == 0) { gctl->error = 2; gctl->done = 1; gctl->arrive = 0; }
+        return;
+      }
+    }
+    __threadfence();
+    const uint64_t* recv = S.peer_base[S.rank] + (size_t)par * KB_MAX_WORLD * P2P_RANK_U64;
+    uint64_t acc = __ldcg(recv + lane);
+    for (uint32_t r = 1; r < S.world; ++r) acc = warp_merge_top32(acc, __ldcg(recv + (size_t)r * P2P_RANK_U64 + lane), lane);
+    sm.keys[lane] = acc;
+    const uint32_t node = key_node(acc);
+    uint32_t owner = node / S.nodes_per_rank;
+    owner = owner < S.world ? owner : S.world - 1;
+    uint32_t idx = 0;
+    if (acc)
+      for (uint32_t i = 0; i < 32; ++i)
+        if (__ldcg(recv + (size_t)owner * P2P_RANK_U64 + i) == acc) idx = i;
+    load_ctl(sm.ctl, gctl, lane);
+    __syncwarp();
+    replay_epilogue(S, sm, lane, cls_id, recv + (size_t)owner * P2P_RANK_U64 + 32 + idx, 32u, 0xFFFFFFFFu, t_start, t_scan);
+    if (lane == 0) sm.ctl.xchg_epoch = epoch + 1;
+    __syncwarp();
+    store_ctl(gctl, sm.ctl, lane);
+    if (lane == 0) gctl->arrive = 0;
+    return;
+  }
   if (S.world > 1) {
     // sharded node axis: publish this rank's candidates WITH their node records; the replay happens in
     // replay_kernel after the all-gather

@@ -39,7 +39,7 @@ for name, mk in cases.items():
     except AssertionError as e:
         msg = "FAIL " + str(e)[:300]; ok = False
     t = [eng.allocate().stats.gpu_ms for _ in range(3)]
-    print(f"[rank {rank}/{world}] {name}: {msg}; gpu_ms {min(t):.2f}; launches {r.stats.kernel_launches} scans {r.stats.scans}", flush=True)
+    print(f"[rank {rank}/{world}] {name}: {msg}; gpu_ms {min(t):.2f}; launches {r.stats.kernel_launches} scans {r.stats.scans} exchange_mode {r.stats.exchange_mode}", flush=True)
 dist.barrier()
 eng.close()
 dist.destroy_process_group()
