@@ -35,12 +35,22 @@ class kbo_result(C.Structure):
     ]
 
 
-def build(force: bool = False) -> str:
+def _stale() -> bool:
     src = os.path.join(_HERE, "kb_oracle.cpp")
-    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
-            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "kb_oracle.h")),
-            os.path.getmtime(os.path.join(_HERE, "..", "include", "kbgpu.h"))):
-        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+        os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "kb_oracle.h")),
+        os.path.getmtime(os.path.join(_HERE, "..", "include", "kbgpu.h")))
+
+
+def build(force: bool = False) -> str:
+    """(Re)build the oracle library if needed.  Several ranks / test workers may call this at once: serialise on a lock
+    file and re-check, so that nobody dlopens a half-written .so."""
+    if force or _stale():
+        import fcntl
+        with open(os.path.join(_HERE, ".build.lock"), "w") as lk:
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            if force or _stale():
+                subprocess.check_call(["make", "-C", _HERE, "-s"])
     return _LIB_PATH
 
 

@@ -19,7 +19,10 @@ _emu = None
 def emu_lib():
     global _emu
     if _emu is None:
-        subprocess.check_call(["make", "-C", os.path.join(_HERE, "emu"), "-s"])
+        import fcntl
+        with open(os.path.join(_HERE, "emu", ".build.lock"), "w") as lk:     # ranks / workers build one at a time
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            subprocess.check_call(["make", "-C", os.path.join(_HERE, "emu"), "-s"])
         _emu = C.CDLL(_EMU)
         _emu.kbemu_last_error.restype = C.c_char_p
     return _emu
