@@ -1,17 +1,21 @@
 // kb_kernels.cuh — sm_100a kernels of the allocate cycle.
 //
-//   visit_kernel        one launch = one SCAN of the node table for the class of the next run
-//                       (K1 predicate bitmask + K2 fused score, node tiles staged into shared memory
-//                       by TMA bulk copies) -> per-CTA top-KTOP candidate keys; the LAST CTA to finish
-//                       (ticket) merges them (K3), then replays as many runs of that class as it can
-//                       certify exactly (dirty-node re-evaluation, AddTask bookkeeping, gang stop rule)
-//                       and runs the control plane (kb_ctl.h) to pick the next visit.  The host only
-//                       pumps launches until Ctl.done — no host round trip inside the cycle.
-//   gang_commit_kernel  K4: per-PodGroup inclusive prefix scan over the Allocated flags in processing
-//                       order -> dispatched bit + dispatch step (framework/session.go:277-285).
-//   matrix_kernel       full fit / score matrix for a task range (debug / parity, kb_predicate_score).
-//   best_nodes_kernel   K1+K2+K3 over a task range x all nodes in ONE launch: per-task argmax via
-//                       warp-shuffle max + one 64-bit atomicMax per warp (kb_best_nodes).
+//   visit_kernel          one launch = one SCAN of the node table for the class of the next run (K1 predicate bitmask +
+//                         K2 fused score; node tiles staged into shared memory by TMA bulk copies, 16 warps = 4 tiles per
+//                         iteration) -> per-warp / per-CTA top-32 candidate keys by bitonic networks (K3); the LAST CTA to
+//                         finish (ticket) merges the lists, then warp 0 replays as many runs of that class as it can certify
+//                         exactly (lane-owned candidates with a pre-evaluated next state, AddTask bookkeeping, gang stop
+//                         rule) and runs the control plane (kb_ctl.h) to pick the next visit, while warp 1 prefetches the
+//                         control plane's rows into L1.  The host only pumps a CUDA graph of launches until Ctl.done.
+//                         Sharded node axis: the same kernel also performs the exchange over peer memory (NVLink stores +
+//                         flags into CUDA-IPC mapped buffers) before the replay — scan, exchange and replay are ONE kernel.
+//   replay_kernel         NCCL fallback of the sharded path: merge the all-gathered lists, same epilogue.
+//   visit_overlap_kernel  opt-in: scanners run ahead on the predicted next class while one CTA replays (exclusion + patch).
+//   gang_commit_kernel    K4: per-PodGroup inclusive prefix scan over the Allocated flags in processing order -> dispatched
+//                         bit + dispatch step (framework/session.go:277-285).
+//   matrix_kernel         full fit / score matrix for a task range (debug / parity, kb_predicate_score).
+//   best_nodes_kernel     K1+K2+K3 over a task range x all nodes in ONE launch: per-task argmax via hardware warp reduce
+//                         + one 64-bit atomicMax per warp (kb_best_nodes).
 //
 // No tensor cores anywhere: this is integer / FP64-compare work on an L2-resident table.
 #pragma once
