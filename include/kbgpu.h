@@ -195,7 +195,7 @@ typedef struct kb_stats {
   uint32_t tasks_pipelined;
   uint32_t jobs_ready;      /* jobs with JobReady at cycle end that placed >= 1 task this cycle */
   uint32_t visits;          /* job visits (allocate.go:109 pops)                                */
-  uint32_t kernel_launches; /* CUDA kernels launched by kb_allocate                             */
+  uint32_t kernel_launches; /* CUDA kernels launched by this kb_allocate / kb_backfill call       */
   uint32_t n_classes;       /* task equivalence classes in the session                          */
   float    gpu_ms;          /* device time of the cycle (CUDA events on the engine stream)      */
   float    load_ms;         /* host time of kb_session_load (flatten->device)                   */
@@ -234,6 +234,16 @@ int kb_session_load(struct kb_engine* e, const kb_snapshot* snap, const kb_plugi
  * JobReady gang commit).  `out` has T entries indexed like the snapshot's tasks.  The Go shim then
  * replays `out` in `step` order through the unchanged ssn.Allocate / ssn.Pipeline. */
 int kb_allocate(struct kb_engine* e, kb_decision* out, kb_stats* stats);
+
+/* Replaces backfillAction.Execute (actions/backfill/backfill.go:40-71), the action that follows allocate in the
+ * default action list ("allocate, backfill", pkg/scheduler/util.go:31-42): every Pending task whose InitResreq is
+ * empty (best effort) goes to the FIRST node — canonical node order, SURVEY.md §8c — on which ssn.PredicateFn passes
+ * and ssn.Allocate succeeds (NodeInfo.AddTask: Resreq <= Idle, node_info.go:161-167); jobs in JobID order, tasks in UID
+ * order.  Runs on the CURRENT device state: after kb_allocate it continues that cycle (step numbers, counters and the
+ * gang commit carry on; a job that backfill makes ready gets its earlier Allocated tasks dispatched at that step);
+ * straight after kb_session_load it is the action list "backfill" alone.  kb_allocate restarts from the loaded state.
+ * `out` (T entries) is the full decision table; best-effort tasks that found no node change from SKIPPED to NONE. */
+int kb_backfill(struct kb_engine* e, kb_decision* out, kb_stats* stats);
 
 /* Debug / parity: predicate + score of tasks [task_lo, task_hi) against every node in the CURRENT
  * device state (util.PredicateNodes + util.PrioritizeNodes for a task range, scheduler_helper.go:63-171).

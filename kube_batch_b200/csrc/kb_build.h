@@ -188,8 +188,10 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 
-struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf; };
-struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0; };
+struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf,
+                bf_job_pos, bf_ctl; };
+struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0,
+                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes; };
 
 struct BuiltSession {
   Slab mut, imm;
@@ -201,6 +203,24 @@ struct BuiltSession {
   double total[KB_MAX_R] = {0};
   std::vector<int32_t> job_min_avail;
   uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1, overlap = 0;
+  uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
+
+  // The BACKFILL VIEW of the same session (backfillAction.Execute, actions/backfill/backfill.go:40-71): same node table,
+  // job / queue accounting, decisions and exchange buffers; its own task order (best-effort tasks only), cursors and
+  // control block; no resource predicate, no nodeorder (the first node that passes wins = lowest node index).
+  void bind_backfill(DevSession& D, unsigned char* mb, unsigned char* ib) const {
+    bind(D, mb, ib);
+    D.backfill = 1; D.overlap = 0;
+    D.cf.fit_mode = 1; D.cf.nodeorder = 0; D.cf.score_bias = 0;
+    D.To = Tb;
+    D.classes = (ClassRec*)(ib + oi.bf_classes);        // same ids; `initreq` holds Resreq (EvalConf.fit_mode)
+    D.ord_task = (uint32_t*)(ib + oi.bf_ord_task); D.ord_class = (uint32_t*)(ib + oi.bf_ord_class);
+    D.ord_run = (uint32_t*)(ib + oi.bf_ord_run); D.ord_peek = (uint32_t*)(ib + oi.bf_ord_peek);
+    D.job_ord_off = (uint32_t*)(ib + oi.bf_job_ord_off);
+    D.job_pos = (uint32_t*)(mb + om.bf_job_pos);
+    D.q_static = (uint32_t*)(ib + oi.bf_jobs); D.q_static_off = (uint32_t*)(ib + oi.bf_jobs_off);
+    D.ctl = (Ctl*)(mb + om.bf_ctl);
+  }
 
   void bind(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     D.cf = hc.cf;
@@ -332,6 +352,21 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   ord_class.resize(To);
   for (uint32_t i = 0; i < To; ++i) ord_class[i] = task_class[ord_task[i]];
 
+  // ---------------- backfill order (backfill.go:45-47): per job, Pending tasks with an empty InitResreq, UID order ----------------
+  std::vector<uint32_t> bf_task, bf_job_off(J + 1, 0), bf_jobs;
+  for (uint32_t j = 0; j < J; ++j) {
+    bf_job_off[j] = (uint32_t)bf_task.size();
+    const size_t b = bf_task.size();
+    for (uint32_t t = s->job_task_off[j]; t < s->job_task_off[j + 1]; ++t) {
+      const ClassRec& c = classes[task_class[t]];
+      if (res_is_empty(R, [&](uint32_t k) { return c.initreq[k]; })) bf_task.push_back(t);
+    }
+    std::sort(bf_task.begin() + b, bf_task.end(), [&](uint32_t l, uint32_t r) { return s->task_uid_rank[l] < s->task_uid_rank[r]; });
+    if (bf_task.size() > b) bf_jobs.push_back(j);
+  }
+  bf_job_off[J] = (uint32_t)bf_task.size();
+  const uint32_t Tb = (uint32_t)bf_task.size();
+
   // ---------------- slabs ----------------
   const uint32_t NT = (N + TILE_NODES - 1) / TILE_NODES;
   const uint32_t ncols = tile_ncols(R, W);
@@ -374,6 +409,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   om.ctl = mut.alloc(sizeof(Ctl));
   om.sendbuf = mut.alloc((size_t)(1 + ncols) * 32 * 8);
   om.recvbuf = mut.alloc((size_t)std::max(1u, world) * (1 + ncols) * 32 * 8);
+  om.bf_job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
+  om.bf_ctl = mut.alloc(sizeof(Ctl));
   oi.classes = imm.alloc((size_t)C * sizeof(ClassRec));
   oi.ord_task = imm.alloc((size_t)std::max(1u, To) * 4);
   oi.ord_class = imm.alloc((size_t)std::max(1u, To) * 4);
@@ -391,10 +428,18 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.q_ctime = imm.alloc((size_t)std::max(1u, Q) * 8);
   oi.task_class = imm.alloc((size_t)std::max(1u, T) * 4);
   oi.job_ready0 = imm.alloc((size_t)std::max(1u, J) * 4);
+  oi.bf_ord_task = imm.alloc((size_t)std::max(1u, Tb) * 4);
+  oi.bf_ord_class = imm.alloc((size_t)std::max(1u, Tb) * 4);
+  oi.bf_ord_run = imm.alloc((size_t)std::max(1u, Tb) * 4);
+  oi.bf_ord_peek = imm.alloc((size_t)std::max(1u, Tb) * 4);
+  oi.bf_job_ord_off = imm.alloc((size_t)(J + 1) * 4);
+  oi.bf_jobs = imm.alloc((size_t)std::max<size_t>(1, bf_jobs.size()) * 4);
+  oi.bf_jobs_off = imm.alloc(2 * 4);
+  oi.bf_classes = imm.alloc((size_t)(Tb ? C : 1) * sizeof(ClassRec));
   mut.host.resize((mut.host.size() + 255) & ~(size_t)255);
   imm.host.resize((imm.host.size() + 255) & ~(size_t)255);
 
-  B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To;
+  B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.Tb = Tb;
   B.bind(H, mut.host.data(), imm.host.data());
 
   // ---------------- node tiles ----------------
@@ -556,6 +601,31 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   c0.scan_class = c0.cur_class;      // the first launch has no list yet: scan for the first visit, nothing excluded
   c0.n_excl = 0; c0.list_valid = 0; c0.patch_valid = 0;
   c0.xchg_epoch = 1;
+
+  // ---------------- backfill view: order tables, cursors, first visit ----------------
+  {
+    DevSession HB{};
+    B.bind_backfill(HB, mut.host.data(), imm.host.data());
+    if (Tb) {
+      memcpy(HB.classes, classes.data(), (size_t)C * sizeof(ClassRec));
+      for (uint32_t k = 0; k < C; ++k) for (uint32_t r = 0; r < KB_MAX_R; ++r) HB.classes[k].initreq[r] = HB.classes[k].resreq[r];
+    }
+    for (uint32_t i = 0; i < Tb; ++i) { HB.ord_task[i] = bf_task[i]; HB.ord_class[i] = task_class[bf_task[i]]; HB.ord_peek[i] = 0xFFFFFFFFu; }
+    for (uint32_t j = 0; j < J; ++j) {
+      for (uint32_t i = bf_job_off[j + 1]; i-- > bf_job_off[j];)
+        HB.ord_run[i] = (i + 1 < bf_job_off[j + 1] && HB.ord_class[i + 1] == HB.ord_class[i]) ? HB.ord_run[i + 1] + 1 : 1;
+      HB.job_pos[j] = bf_job_off[j];
+    }
+    memcpy(HB.job_ord_off, bf_job_off.data(), (size_t)(J + 1) * 4);
+    for (size_t i = 0; i < bf_jobs.size(); ++i) HB.q_static[i] = bf_jobs[i];
+    HB.q_static_off[0] = 0; HB.q_static_off[1] = (uint32_t)bf_jobs.size();
+    Ctl& cb = *HB.ctl;
+    memset(&cb, 0, sizeof cb);
+    cb.cur_job = -1;
+    select_next_visit(HB, cb);
+    cb.scan_class = cb.cur_class;
+    cb.xchg_epoch = 1;
+  }
 
   B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.grid = grid;
   B.job_min_avail.assign(s->job_min_avail, s->job_min_avail + J);

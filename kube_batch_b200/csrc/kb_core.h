@@ -67,6 +67,11 @@ struct EvalConf {
   uint32_t nodeorder;         // nodeorder plugin registered && EnabledNodeOrder
   int32_t  w_least, w_most, w_balanced;                 // nodeorder.go:107-131 (node/pod-affinity terms are 0 here)
   int64_t  score_bias;        // makes the weighted sum non-negative so it packs into the key
+  uint32_t fit_mode;          // 0: allocate — InitResreq <= Idle || InitResreq <= Releasing (allocate.go:82)
+                              // 1: backfill — no resource predicate, but NodeInfo.AddTask needs Resreq <= Idle
+                              //    (node_info.go:161-167): the backfill view's class table carries Resreq in `initreq`
+                              //    and the Releasing alternative is masked off
+  uint32_t pad0;
 };
 
 // One task equivalence class: every field of a pending task that predicateFn / the prioritizers /
@@ -179,6 +184,7 @@ KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n
     fi = fi & (skip | le_func(lq, n.idle(k), KB_MIN_MILLI_SCALAR));
     fr = fr & (skip | le_func(lq, n.rel(k), KB_MIN_MILLI_SCALAR));
   }
+  fr = fr & (cf.fit_mode == 0);                 // backfill only ever allocates from Idle
   if (fits_idle) *fits_idle = fi;
   bool ok = fi | fr;
 

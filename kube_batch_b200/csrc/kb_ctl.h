@@ -44,6 +44,8 @@ struct Ctl {
   uint32_t patch_valid;
   uint32_t predictions, mispredictions;
   uint32_t xchg_epoch;     // peer-memory exchange: sequence number of the next scan (starts at 1; flags are zeroed per cycle)
+  uint32_t bf_cursor;      // backfill view: next entry of the best-effort job list (DevSession.q_static)
+  uint32_t bf_seeded;      // backfill view: step / counters were carried over from the allocate view
   uint32_t excl[32];
   unsigned long long list[32];
   unsigned long long patch[32];
@@ -71,6 +73,8 @@ struct DevSession {
   uint32_t* ord_run;      // [To] number of consecutive slots of the same class starting here (within the job)
   uint32_t* ord_peek;     // [To] first class != ord_class[i] later in the queue's static job order (prediction only), ~0u = none
   uint32_t overlap;       // 1: visit_kernel runs scanners + one replayer CTA concurrently (world == 1)
+  uint32_t backfill;      // 1: this view drives backfillAction.Execute (backfill.go:40-71): jobs in JobID order, a task without
+                          //    a node does not end the job, no yield rule, no resource predicate (EvalConf.fit_mode 1)
   uint32_t* job_ord_off;  // [J+1]
   uint32_t* job_pos;      // [J] cursor into ord_* (pendingTasks[job.UID], allocate.go:110-126)
   // jobs
@@ -314,18 +318,33 @@ KB_HD bool queue_has_jobs(const DevSession& S, const Ctl& c, uint32_t q) {
 }
 
 // The outer `for {}` of allocate.go:89-193 from "queues.Pop()" until a job with tasks is found.
+// BF: compile-time copy of DevSession.backfill (-1 = read it at run time); the allocate kernels are instantiated with 0
+// so that the backfill branches cost them nothing.
+template <int BF = -1>
 KB_HD void select_next_visit(const DevSession& S, Ctl& c) {
+  const bool bf = BF < 0 ? S.backfill != 0 : BF != 0;
   c.cur_job = -1;
   for (;;) {
-    if (c.qheap_len == 0) { c.done = 1; return; }                      // :90-92
-    uint32_t q = qheap_pop(S, c);                                       // :94
-    if (queue_overused(S, q)) continue;                                 // :95-98
-    if (!queue_has_jobs(S, c, q)) continue;                             // :104-107
-    int32_t j = pick_job(S, c, q);                                      // :109
-    c.visits += 1;
-    if (S.job_pos[j] >= S.job_ord_off[j + 1]) {                         // tasks.Empty(): the for at :129 is skipped
-      qheap_push(S, c, q);                                              // :192
-      continue;
+    uint32_t q;
+    int32_t j;
+    if (bf) {
+      // backfill.go:45-46: every job (JobID order), its Pending tasks with an empty InitResreq in UID
+      // order.  q_static holds the jobs that have such tasks; no queue heap, no overused check, no JobOrderFn.
+      if (c.bf_cursor >= S.q_static_off[1]) { c.done = 1; return; }
+      j = (int32_t)S.q_static[c.bf_cursor];
+      c.bf_cursor += 1;
+      q = S.job_queue[j];
+    } else {
+      if (c.qheap_len == 0) { c.done = 1; return; }                      // :90-92
+      q = qheap_pop(S, c);                                                // :94
+      if (queue_overused(S, q)) continue;                                 // :95-98
+      if (!queue_has_jobs(S, c, q)) continue;                             // :104-107
+      j = pick_job(S, c, q);                                              // :109
+      c.visits += 1;
+      if (S.job_pos[j] >= S.job_ord_off[j + 1]) {                         // tasks.Empty(): the for at :129 is skipped
+        qheap_push(S, c, q);                                              // :192
+        continue;
+      }
     }
     c.cur_job = j;
     c.cur_queue = q;
@@ -335,7 +354,9 @@ KB_HD void select_next_visit(const DevSession& S, Ctl& c) {
 }
 
 // Called once a run stopped.  `placed` = tasks of the run that went through Allocate/Pipeline.
+template <int BF = -1>
 KB_HD void after_run(const DevSession& S, Ctl& c, uint32_t reason, uint32_t placed) {
+  const bool bf = BF < 0 ? S.backfill != 0 : BF != 0;
   const uint32_t j = (uint32_t)c.cur_job;
   if (placed) {
     if (S.drf_present) update_job_share(S, j);
@@ -343,14 +364,15 @@ KB_HD void after_run(const DevSession& S, Ctl& c, uint32_t reason, uint32_t plac
   }
   if (reason == STOP_RESCAN) { setup_run(S, c); return; }
   bool end_visit;
-  if (reason == STOP_NOFIT) end_visit = true;                           // :144-148 break, job not re-pushed
+  if (reason == STOP_NOFIT) end_visit = bf ? (S.job_pos[j] >= S.job_ord_off[j + 1])   // backfill.go:50-65: next task
+                                                   : true;                                    // :144-148 break, job not re-pushed
   else if (reason == STOP_YIELD) {                                      // :185-188
     S.dyn_jobs[c.dyn_len] = j; c.dyn_len += 1;
     end_visit = true;
   } else end_visit = S.job_pos[j] >= S.job_ord_off[j + 1];
   if (!end_visit) { setup_run(S, c); return; }
-  qheap_push(S, c, c.cur_queue);                                        // :192
-  select_next_visit(S, c);
+  if (!bf) qheap_push(S, c, c.cur_queue);                               // :192
+  select_next_visit<BF>(S, c);
 }
 
 }  // namespace kb

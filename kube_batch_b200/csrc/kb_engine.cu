@@ -81,7 +81,10 @@ struct kb_engine {
   unsigned char* d_pristine = nullptr; // copy of the mutable slab as loaded
   unsigned char* d_imm = nullptr;      // immutable slab
   size_t mut_bytes = 0, imm_bytes = 0;
-  DevSession dev{};                    // device pointers
+  DevSession dev{};                    // device pointers (allocate view)
+  DevSession dev_bf{};                 // backfill view of the same slabs (kb_backfill)
+  uint32_t Tb = 0;                     // backfill order slots
+  bool allocate_ran = false;           // kb_allocate ran since kb_session_load (kb_backfill continues its counters)
   uint32_t* d_task_class = nullptr;    // [T] (immutable slab)
   int32_t* d_job_ready0 = nullptr;     // [J] (immutable slab)
   Ctl* h_ctl = nullptr;                // pinned
@@ -301,6 +304,11 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   B.bind(e->dev, e->d_mut, e->d_imm);
   e->dev.p2p = (e->world > 1 && e->p2p) ? 1u : 0u;
   for (int r = 0; r < 8; ++r) e->dev.peer_base[r] = e->p2p_peer[r];
+  B.bind_backfill(e->dev_bf, e->d_mut, e->d_imm);
+  e->dev_bf.p2p = e->dev.p2p;
+  for (int r = 0; r < 8; ++r) e->dev_bf.peer_base[r] = e->p2p_peer[r];
+  e->Tb = B.Tb;
+  e->allocate_ran = false;
   e->d_task_class = (uint32_t*)(e->d_imm + oi.task_class);
   e->d_job_ready0 = (int32_t*)(e->d_imm + oi.job_ready0);
   e->R = R; e->W = W; e->N = N; e->T = T; e->J = J; e->Q = Q; e->C = C; e->NT = NT; e->ncols = ncols; e->To = To;
@@ -309,13 +317,15 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->scan_grid = grid;
   e->tile_smem = tile_u64 * 8;
   e->visit_smem = ((sizeof(VisitSmem) + 127) / 128) * 128 + 2 * (size_t)B.tpi * e->tile_smem;
-  CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(visit_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch)
   e->replay_smem = ((sizeof(VisitSmem) + 127) / 128) * 128;
-  CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
   if (!e->graph_exec || memcmp(&e->graph_dev, &e->dev, sizeof(DevSession)) != 0) {
     free_graph(e);
     // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch).
@@ -325,10 +335,10 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     bool ok = ce == cudaSuccess;
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
       if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
-      else visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+      else visit_kernel<0><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
       if (e->world > 1 && !e->dev.p2p) {
         ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
-        replay_kernel<<<1, 64, e->replay_smem, e->stream>>>(e->dev);
+        replay_kernel<0><<<1, 64, e->replay_smem, e->stream>>>(e->dev);
       }
     }
     cudaGraph_t g = nullptr;
@@ -348,14 +358,20 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   return KB_OK;
 }
 
-int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
-  if (!e) return KB_E_BADARG;
-  if (!e->loaded) return fail(e, KB_E_STATE, "kb_allocate before kb_session_load");
+namespace {
+
+// One action of the cycle on view `D`: launches until the view's control block reports done, then the gang commit and
+// the read-back.  allocate (D = e->dev) starts from the pristine tables and pumps the captured graph; backfill
+// (D = e->dev_bf) continues on the current tables with plain launches (there are few best-effort tasks).
+int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* stats) {
+  const DevSession& D = backfill ? e->dev_bf : e->dev;
   CUDA_TRY(e, cudaSetDevice(e->device));
   CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
-  if (e->world > 1 && e->dev.p2p) {
-    // a new cycle restarts the exchange sequence at 1: clear my flags, then make sure every rank has done so before
+  if (!backfill) CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
+  else seed_backfill_kernel<<<1, 32, 0, e->stream>>>(e->dev.ctl, e->dev_bf.ctl, e->allocate_ran ? 1 : 0);
+  if (!backfill) e->allocate_ran = true;
+  if (e->world > 1 && D.p2p) {
+    // a new action restarts the exchange sequence at 1: clear my flags, then make sure every rank has done so before
     // anybody can raise one (the all-gather is only used as a stream-ordered barrier)
     CUDA_TRY(e, cudaMemsetAsync(e->p2p_local + P2P_FLAG_OFF, 0, 2 * KB_MAX_WORLD * 8, e->stream));
     if (g_nccl.AllGather(e->d_xchg + 520 + e->rank, e->d_xchg + 520, 1, 0, e->comm, e->stream) != 0)
@@ -363,31 +379,39 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
   }
   uint32_t launches = 0;
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
-  const uint64_t cap = 4ull * ((uint64_t)e->J + e->To) + 1024;
+  const uint64_t cap = 4ull * ((uint64_t)e->J + e->To + e->Tb) + 1024;
+  const bool use_graph = !backfill && e->graph_exec;
+  const uint32_t batch = backfill ? 16u : BATCH;
   for (;;) {
-    if (e->graph_exec) {
+    if (use_graph) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
-      launches += ((e->world == 1 || e->dev.p2p) ? 1 : 2) * BATCH;
+      launches += ((e->world == 1 || D.p2p) ? 1 : 2) * BATCH;
     } else {
-      // sharded node axis: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
+      // sharded node axis without peer memory: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
       const size_t cnt = (size_t)(1 + e->ncols) * 32;
-      for (uint32_t i = 0; i < BATCH; ++i) {
-        visit_kernel<<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
-        int rc = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream);
-        if (rc != 0) return fail(e, KB_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
-        replay_kernel<<<1, 64, e->replay_smem, e->stream>>>(e->dev);
+      for (uint32_t i = 0; i < batch; ++i) {
+        if (backfill) visit_kernel<1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
+        else if (D.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
+        else visit_kernel<0><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
+        if (e->world > 1 && !D.p2p) {
+          int rc = g_nccl.AllGather(D.sendbuf, D.recvbuf, cnt, kNcclUint64, e->comm, e->stream);
+          if (rc != 0) return fail(e, KB_E_NCCL, "ncclAllGather: %s", g_nccl.GetErrorString(rc));
+          if (backfill) replay_kernel<1><<<1, 64, e->replay_smem, e->stream>>>(D);
+          else replay_kernel<0><<<1, 64, e->replay_smem, e->stream>>>(D);
+        }
       }
       CUDA_TRY(e, cudaGetLastError());
-      launches += 2 * BATCH;
+      launches += ((e->world == 1 || D.p2p) ? 1 : 2) * batch;
     }
-    CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, e->dev.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, D.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (e->h_ctl->done) break;
-    if (launches > cap) return fail(e, KB_E_STATE, "allocate cycle did not terminate within %llu launches", (unsigned long long)cap);
+    if (launches > cap) return fail(e, KB_E_STATE, "%s cycle did not terminate within %llu launches", backfill ? "backfill" : "allocate", (unsigned long long)cap);
   }
   if (e->J) {
     const uint32_t warps_per_block = 4;
-    gang_commit_kernel<<<(e->J + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, e->stream>>>(e->dev, e->d_job_ready0);
+    gang_commit_kernel<<<(e->J + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, e->stream>>>(
+        e->dev, e->d_job_ready0, e->dev_bf.ord_task, e->dev_bf.job_ord_off, e->dev_bf.job_pos);
     launches += 1;
   }
   CUDA_TRY(e, cudaGetLastError());
@@ -418,11 +442,25 @@ int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
     stats->scans = c.scans; stats->rescans = c.rescans;
     stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total; stats->cyc_steps = c.cyc_steps; stats->cyc_ctl = c.cyc_ctl;
     stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
-    stats->exchange_mode = e->world == 1 ? 0u : (e->dev.p2p ? 2u : 1u);
-    stats->h2d_bytes = (uint64_t)e->mut_bytes + e->imm_bytes;
-    stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / BATCH) * sizeof(Ctl);
+    stats->exchange_mode = e->world == 1 ? 0u : (D.p2p ? 2u : 1u);
+    stats->h2d_bytes = backfill ? 0 : (uint64_t)e->mut_bytes + e->imm_bytes;
+    stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / batch) * sizeof(Ctl);
   }
   return KB_OK;
+}
+
+}  // namespace
+
+int kb_allocate(kb_engine* e, kb_decision* out, kb_stats* stats) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_allocate before kb_session_load");
+  return run_action(e, false, out, stats);
+}
+
+int kb_backfill(kb_engine* e, kb_decision* out, kb_stats* stats) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_backfill before kb_session_load");
+  return run_action(e, true, out, stats);
 }
 
 int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {

@@ -161,6 +161,7 @@ __device__ __forceinline__ void store_ctl(Ctl* g, const Ctl& c, int lane) {
 
 // `patch_class` != ~0u (overlap mode): after the replay, if the control plane's next visit has that class, every lane
 // evaluates ITS candidate's current state for it and the sorted keys go to c.patch (see Ctl).  The caller stores c.
+template <int BF>
 __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& sm, const int lane, const uint32_t cls_id,
                                                 const uint64_t* rec_base, const uint32_t rec_stride, const uint32_t patch_class,
                                                 const long long t_start, const long long t_scan) {
@@ -272,7 +273,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       n_alloc += fits_idle ? 1u : 0u;
       // allocate.go:185-188: a ready job yields after every task while tasks remain
       const bool jr = !S.gang_ready || (ready + (int32_t)n_alloc) >= min_avail;     // ssn.JobReady
-      if (jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
+      if (!BF && jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
     }
     // write the job-level state back, then run the control plane
     if (lane == 0) {
@@ -293,7 +294,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     const long long t_run1 = clock64();
     if (lane == 0) {
       if (reason == STOP_RESCAN) c.rescans += 1;
-      after_run(S, c, reason, placed);
+      after_run<BF>(S, c, reason, placed);
       const long long t_run2 = clock64();
       c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
       c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
@@ -420,8 +421,9 @@ __device__ __forceinline__ void load_ctl(Ctl& dst, const Ctl* g, int lane) {
 // the queue's static job list), so that warp 0 finds it in L1 instead of paying a chain of L2 round trips.
 // Read-only; the sum goes to `sink` only to keep the loads alive.
 // ---------------------------------------------------------------------------------------------
+template <int BF>
 __device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& c, const int lane, uint32_t* sink, const uint64_t cand_key) {
-  if (c.done || c.cur_job < 0) return;
+  if (BF || c.done || c.cur_job < 0) return;
   const uint32_t j = (uint32_t)c.cur_job, q = c.cur_queue, R = S.cf.R;
   uint32_t acc = 0;
   if (cand_key)                                   // NodeInfo.Used rows of this lane's candidate (read at write-back time)
@@ -465,6 +467,7 @@ __device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& 
 // ---------------------------------------------------------------------------------------------
 // visit_kernel
 // ---------------------------------------------------------------------------------------------
+template <int BF>
 __global__ void __launch_bounds__(SCAN_THREADS)
 visit_kernel(const __grid_constant__ DevSession S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -551,7 +554,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
       __syncwarp();
       if (lane == 0) *((volatile uint64_t*)(S.peer_base[warp] + P2P_FLAG_OFF + par * KB_MAX_WORLD + S.rank)) = (uint64_t)epoch;
     }
-    if (warp == 1) { load_ctl(sm.ctl2, gctl, lane); __syncwarp(); shadow_prefetch(S, sm.ctl2, lane, &sm.sink, 0ull); }
+    if (warp == 1) { load_ctl(sm.ctl2, gctl, lane); __syncwarp(); shadow_prefetch<BF>(S, sm.ctl2, lane, &sm.sink, 0ull); }
     if (warp != 0) return;
     // wait for every rank's block (bounded: ~2 s at 2 GHz, then the cycle is aborted with an error)
     {
@@ -580,7 +583,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
         if (__ldcg(recv + (size_t)owner * P2P_RANK_U64 + i) == acc) idx = i;
     load_ctl(sm.ctl, gctl, lane);
     __syncwarp();
-    replay_epilogue(S, sm, lane, cls_id, recv + (size_t)owner * P2P_RANK_U64 + 32 + idx, 32u, 0xFFFFFFFFu, t_start, t_scan);
+    replay_epilogue<BF>(S, sm, lane, cls_id, recv + (size_t)owner * P2P_RANK_U64 + 32 + idx, 32u, 0xFFFFFFFFu, t_start, t_scan);
     if (lane == 0) sm.ctl.xchg_epoch = epoch + 1;
     __syncwarp();
     store_ctl(gctl, sm.ctl, lane);
@@ -610,14 +613,14 @@ visit_kernel(const __grid_constant__ DevSession S) {
     }
   }
   __syncthreads();
-  if (warp == 1) shadow_prefetch(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
+  if (warp == 1) shadow_prefetch<BF>(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
   if (warp != 0) return;
 
   // ---------------- exact replay + control: warp 0 only ----------------
   {
     const uint32_t n = key_node(sm.keys[lane]);
     const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
-    replay_epilogue(S, sm, lane, cls_id, rec, TILE_NODES, 0xFFFFFFFFu, t_start, t_scan);
+    replay_epilogue<BF>(S, sm, lane, cls_id, rec, TILE_NODES, 0xFFFFFFFFu, t_start, t_scan);
     store_ctl(gctl, sm.ctl, lane);
     if (lane == 0) gctl->arrive = 0;
   }
@@ -658,7 +661,7 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
   } else if (warp == 1) {
     load_ctl(sm.ctl2, gctl, lane);
     __syncwarp();
-    shadow_prefetch(S, sm.ctl2, lane, &sm.sink, sm.ctl2.list[lane]);
+    shadow_prefetch<0>(S, sm.ctl2, lane, &sm.sink, sm.ctl2.list[lane]);
   } else if (warp == 0) {
     // ---------------- replayer ----------------
     load_ctl(sm.ctl, gctl, lane);
@@ -679,7 +682,7 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
       const uint32_t n = key_node(sm.keys[lane]);
       const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
       const long long t0 = clock64();
-      replay_epilogue(S, sm, lane, cls_id, rec, TILE_NODES, patch_class, t0, t0);
+      replay_epilogue<0>(S, sm, lane, cls_id, rec, TILE_NODES, patch_class, t0, t0);
     } else if (lane == 0) c.patch_valid = 0;
     __syncwarp();
     store_ctl(gctl, c, lane);
@@ -761,6 +764,7 @@ visit_overlap_kernel(const __grid_constant__ DevSession S) {
 // lane finds the record of its candidate in the owning rank's block and the shared epilogue replays.
 // Every rank runs this identically on identical inputs, so every replica applies the same updates.
 // ---------------------------------------------------------------------------------------------
+template <int BF>
 __global__ void __launch_bounds__(64)
 replay_kernel(const __grid_constant__ DevSession S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -771,7 +775,7 @@ replay_kernel(const __grid_constant__ DevSession S) {
   if (threadIdx.x >= 32) {                       // warp 1: shadow prefetch from its own copy of the control block
     load_ctl(sm.ctl2, gctl, lane);
     __syncwarp();
-    shadow_prefetch(S, sm.ctl2, lane, &sm.sink, 0ull);
+    shadow_prefetch<BF>(S, sm.ctl2, lane, &sm.sink, 0ull);
     return;
   }
   const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
@@ -794,7 +798,7 @@ replay_kernel(const __grid_constant__ DevSession S) {
       if (__ldcg(S.recvbuf + owner * rank_u64 + i) == acc) idx = i;
   if (lane == 0) sm.ctl = *gctl;
   __syncwarp();
-  replay_epilogue(S, sm, lane, cls_id, S.recvbuf + owner * rank_u64 + 32 + idx, 32u, 0xFFFFFFFFu, t_start, clock64());
+  replay_epilogue<BF>(S, sm, lane, cls_id, S.recvbuf + owner * rank_u64 + 32 + idx, 32u, 0xFFFFFFFFu, t_start, clock64());
   store_ctl(gctl, sm.ctl, lane);
   if (lane == 0) gctl->arrive = 0;
 }
@@ -805,21 +809,33 @@ replay_kernel(const __grid_constant__ DevSession S) {
 // gang's JobReadyFn is not enabled); a task allocated at position i is dispatched at step[max(i, e*)].
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-gang_commit_kernel(const __grid_constant__ DevSession S, const int32_t* __restrict__ job_ready0) {
+gang_commit_kernel(const __grid_constant__ DevSession S, const int32_t* __restrict__ job_ready0,
+                   const uint32_t* __restrict__ bf_ord_task, const uint32_t* __restrict__ bf_job_ord_off,
+                   const uint32_t* __restrict__ bf_job_pos) {
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp_global >= S.J) return;
   const uint32_t j = warp_global;
-  const uint32_t lo = S.job_ord_off[j], hi = S.job_pos[j];    // processed slots
-  if (lo >= hi) return;
+  // processed slots in step order: the allocate view's, then the backfill view's (backfill runs after allocate)
+  const uint32_t lo = S.job_ord_off[j], na = S.job_pos[j] - lo;
+  const uint32_t blo = bf_job_ord_off[j], nb = bf_job_pos[j] - blo;
+  const uint32_t n = na + nb;
+  if (n == 0) return;
+  auto task_at = [&](uint32_t v) { return v < na ? S.ord_task[lo + v] : bf_ord_task[blo + (v - na)]; };
+  // a best-effort task the backfill pass went through without finding a node is no longer "skipped"
+  for (uint32_t v = na + lane; v < n; v += 32) {
+    const uint32_t t = task_at(v);
+    if (S.dec[t].kind == KB_KIND_SKIPPED) S.dec[t].kind = KB_KIND_NONE;
+  }
+  __syncwarp();
   const int32_t need = S.gang_ready ? S.job_min_avail[j] - job_ready0[j] : 0;   // allocations required before JobReady
   // pass 1: find e* (slot index) and its step
   uint32_t estar = 0xFFFFFFFFu, estep = 0;
   int32_t carried = 0;
-  for (uint32_t base = lo; base < hi && estar == 0xFFFFFFFFu; base += 32) {
+  for (uint32_t base = 0; base < n && estar == 0xFFFFFFFFu; base += 32) {
     const uint32_t i = base + lane;
     uint32_t alloc = 0, step = 0;
-    if (i < hi) { const kb_decision d = S.dec[S.ord_task[i]]; alloc = d.kind == KB_KIND_ALLOCATED; step = d.step; }
+    if (i < n) { const kb_decision d = S.dec[task_at(i)]; alloc = d.kind == KB_KIND_ALLOCATED; step = d.step; }
     int32_t x = (int32_t)alloc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
@@ -833,14 +849,30 @@ gang_commit_kernel(const __grid_constant__ DevSession S, const int32_t* __restri
     carried = __shfl_sync(FULL, incl, 31);
   }
   if (estar == 0xFFFFFFFFu) return;                   // never became ready: nothing is dispatched
-  for (uint32_t i = lo + lane; i < hi; i += 32) {
-    const uint32_t t = S.ord_task[i];
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t t = task_at(i);
     kb_decision d = S.dec[t];
     if (d.kind != KB_KIND_ALLOCATED) continue;
     d.dispatched = 1;
     d.dispatch_step = i <= estar ? estep : d.step;
     S.dec[t] = d;
   }
+}
+
+// kb_backfill: the backfill view continues the allocate view's Allocate sequence numbers and cycle counters
+// (`carry` = kb_allocate ran on this session state; otherwise backfill is the first action and starts from zero)
+__global__ void seed_backfill_kernel(const Ctl* __restrict__ main_ctl, Ctl* __restrict__ bf, const int carry) {
+  if (threadIdx.x != 0 || bf->bf_seeded) return;
+  bf->bf_seeded = 1;
+  if (!carry) return;
+  bf->step = main_ctl->step;
+  bf->tasks_processed = main_ctl->tasks_processed; bf->tasks_allocated = main_ctl->tasks_allocated;
+  bf->tasks_pipelined = main_ctl->tasks_pipelined; bf->visits = main_ctl->visits;
+  bf->scans = main_ctl->scans; bf->rescans = main_ctl->rescans;
+  bf->pairs_logical = main_ctl->pairs_logical; bf->pairs_scanned = main_ctl->pairs_scanned; bf->pairs_replayed = main_ctl->pairs_replayed;
+  bf->cyc_scan = main_ctl->cyc_scan; bf->cyc_merge = main_ctl->cyc_merge; bf->cyc_replay = main_ctl->cyc_replay;
+  bf->cyc_total = main_ctl->cyc_total; bf->cyc_steps = main_ctl->cyc_steps; bf->cyc_ctl = main_ctl->cyc_ctl;
+  bf->predictions = main_ctl->predictions; bf->mispredictions = main_ctl->mispredictions;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
 
 EXPORTS = [
-    "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_predicate_score",
+    "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_backfill", "kb_predicate_score",
     "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
     "kb_nccl_unique_id", "kb_last_kernel_ms",
 ]
@@ -109,6 +109,15 @@ class Engine:
         dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
         st = abi.kb_stats()
         self._check(self.L.kb_allocate(self._h, dec.ctypes.data_as(C.c_void_p), C.byref(st)), "kb_allocate")
+        return CycleResult(dec[:T], st)
+
+    def backfill(self) -> CycleResult:
+        """backfillAction.Execute (actions/backfill/backfill.go:40-71) on the current device state: call it after
+        allocate() for the default action list "allocate, backfill".  Returns the full, updated decision table."""
+        T = self.snap.T
+        dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+        st = abi.kb_stats()
+        self._check(self.L.kb_backfill(self._h, dec.ctypes.data_as(C.c_void_p), C.byref(st)), "kb_backfill")
         return CycleResult(dec[:T], st)
 
     def predicate_score(self, lo: int, hi: int):

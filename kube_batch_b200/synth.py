@@ -241,7 +241,7 @@ def make(name: str) -> Tuple[Snapshot, PluginConf]:
 # ------------------------------------------------------------------------------------------------
 def random_session(seed: int, tasks: int = 60, jobs: int = 8, nodes: int = 12, queues: int = 1,
                    min_member_frac: float = 1.0, hetero: float = 0.3, prio_levels: int = 3,
-                   oversub: float = 1.3, R: int = 3, W: int = 2) -> Snapshot:
+                   oversub: float = 1.3, R: int = 3, W: int = 2, be_frac: float = 0.05, be_variants: bool = False) -> Snapshot:
     spec = SynthSpec(f"rand{seed}", tasks=tasks, jobs=jobs, nodes=nodes, queues=queues,
                      min_member_frac=min_member_frac, hetero_job_frac=hetero, prio_levels=prio_levels,
                      oversub=oversub, seed=seed, R=R, W=W)
@@ -249,10 +249,22 @@ def random_session(seed: int, tasks: int = 60, jobs: int = 8, nodes: int = 12, q
     rng = np.random.Generator(np.random.PCG64(seed ^ 0x5EED))
     # sprinkle BestEffort (empty Resreq) tasks — allocate must skip them (allocate.go:113-118)
     if s.T:
-        be = rng.random(s.T) < 0.05
+        be = rng.random(s.T) < be_frac
         s.task_resreq[:, be] = 0
         s.task_initreq[:, be] = 0
         s.task_flags[be] |= abi.KB_TASK_BEST_EFFORT_QOS
         s.task_nz_cpu[be] = 100           # DefaultMilliCPURequest / DefaultMemoryRequest (non_zero.go:32-40)
         s.task_nz_mem[be] = 200 * 1024 * 1024
+        if be_variants:
+            # backfill's corner cases: requests below the IsEmpty epsilons (still "empty", but AddTask subtracts them),
+            # and an init container that makes InitResreq non-empty while Resreq is empty (allocate skips the task AND
+            # backfill leaves it alone, backfill.go:47 / :66-68)
+            u = rng.random(s.T)
+            tiny = be & (u < 0.3)
+            s.task_resreq[0, tiny] = 5.0
+            s.task_initreq[0, tiny] = 5.0
+            s.task_flags[tiny] &= ~np.uint32(abi.KB_TASK_BEST_EFFORT_QOS)
+            s.task_nz_cpu[tiny] = 5
+            init = be & (u > 0.8)
+            s.task_initreq[0, init] = 500.0
     return s

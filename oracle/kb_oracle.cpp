@@ -1154,7 +1154,6 @@ void Execute(Session& ssn, const kbo_opts& opts, kbo_result& res) {
   std::map<uint32_t, PriorityQueue<uint32_t>> pendingTasks;   // :69
   std::vector<PriorityConfig> cfgs;
   std::vector<double> priorityList;
-  std::set<uint32_t> placed_jobs;
   bool stop = false;
 
   for (;;) {                                           // :89
@@ -1196,12 +1195,10 @@ void Execute(Session& ssn, const kbo_opts& opts, kbo_result& res) {
       NodeInfo& node = ssn.Nodes[predicateNodes[Executor::SelectBestNode(priorityList)]];   // :156-157
       if (ssn.A.LessEqual(task.InitResreq, node.Idle)) {                        // :160
         ssn.Allocate(task, node);
-        placed_jobs.insert(j);
       } else {
         // :168-170 NodesFitDelta bookkeeping feeds only the unschedulable message (job_info.go FitError)
         if (ssn.A.LessEqual(task.InitResreq, node.Releasing)) {                 // :175
           ssn.Pipeline(task, node);
-          placed_jobs.insert(j);
         }
       }
       if (ssn.JobReady(job) && !tasks.Empty()) {                                // :185-188
@@ -1213,8 +1210,31 @@ void Execute(Session& ssn, const kbo_opts& opts, kbo_result& res) {
   }
   res.tasks_allocated = ssn.n_allocated;
   res.tasks_pipelined = ssn.n_pipelined;
-  for (uint32_t j : placed_jobs) if (ssn.JobReady(ssn.Jobs[j])) ++res.jobs_ready;
   res.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// actions/backfill/backfill.go:40-71.  Deterministic rules: jobs in ascending JobID, a job's Pending tasks in ascending
+// TaskInfo.UID, nodes in ascending Name (all three are Go map iterations in the reference).
+void ExecuteBackfill(Session& ssn, kbo_result& res) {
+  for (auto& job : ssn.Jobs) {                                              // :45
+    std::vector<uint32_t> pend;
+    auto pit = job.TaskStatusIndex.find(Pending);
+    if (pit != job.TaskStatusIndex.end()) pend.assign(pit->second.begin(), pit->second.end());
+    std::sort(pend.begin(), pend.end(), [&](uint32_t a, uint32_t b) { return ssn.Tasks[a].uid_rank < ssn.Tasks[b].uid_rank; });
+    for (uint32_t tid : pend) {                                             // :46
+      TaskInfo& task = ssn.Tasks[tid];
+      if (!ssn.A.IsEmpty(task.InitResreq)) continue;                        // :47 (else branch :66-68 is a TODO)
+      ++res.tasks_processed;
+      res.pairs_logical += ssn.Nodes.size();
+      for (auto& node : ssn.Nodes) {                                        // :50
+        if (!ssn.PredicateFn(task, node, node.pods, node.ports)) continue;  // :53-57 — ssn.PredicateFn only, no resource fit
+        if (!ssn.Allocate(task, node)) continue;                            // :60-63 (AddTask: Resreq <= Idle, node_info.go:161-167)
+        break;                                                              // :64
+      }
+    }
+  }
+  res.tasks_allocated = ssn.n_allocated;
+  res.tasks_pipelined = ssn.n_pipelined;
 }
 
 Resource mkres(uint32_t R, const double* v, uint32_t present) {
@@ -1259,7 +1279,17 @@ int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_
       for (int32_t i = 0; i < j.ready0 && Nn > 0; ++i) ssn->placeholder_alloc[j.idx].push_back((uint32_t)(((uint64_t)(k++) * 2654435761ull) % Nn));
   }
   kbo_result res{};
-  Execute(*ssn, opts, res);
+  const int actions = opts.actions ? opts.actions : KBO_ACTION_ALLOCATE;
+  if (actions & KBO_ACTION_ALLOCATE) Execute(*ssn, opts, res);
+  if (actions & KBO_ACTION_BACKFILL) ExecuteBackfill(*ssn, res);
+  // bench metric (BASELINE.json): PodGroups that received a placement in this cycle and are JobReady at its end
+  res.jobs_ready = 0;
+  for (auto& job : ssn->Jobs) {
+    bool placed = false;
+    for (uint32_t t = snap->job_task_off[job.idx]; t < snap->job_task_off[job.idx + 1] && !placed; ++t)
+      placed = ssn->Tasks[t].step != 0xFFFFFFFFu;
+    if (placed && ssn->JobReady(job)) ++res.jobs_ready;
+  }
   const uint32_t R = snap->R, W = snap->W, N = snap->N, T = snap->T, J = snap->J, Q = snap->Q;
   if (out)
     for (uint32_t t = 0; t < T; ++t) {
@@ -1269,7 +1299,8 @@ int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_
       d.step = ti.step;
       d.dispatch_step = ti.dispatch_step;
       d.dispatched = ti.dispatched ? 1 : 0;
-      if (ti.Status == Pending) d.kind = ssn->A.IsEmpty(ti.Resreq) ? KB_KIND_SKIPPED : KB_KIND_NONE;
+      const bool bf = (actions & KBO_ACTION_BACKFILL) != 0;
+      if (ti.Status == Pending) d.kind = ssn->A.IsEmpty(ti.Resreq) ? ((bf && ssn->A.IsEmpty(ti.InitResreq)) ? KB_KIND_NONE : KB_KIND_SKIPPED) : KB_KIND_NONE;
       else if (ti.Status == Pipelined) d.kind = KB_KIND_PIPELINED;
       else d.kind = KB_KIND_ALLOCATED;
       out[t] = d;

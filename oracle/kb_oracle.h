@@ -36,7 +36,12 @@ typedef struct kbo_opts {
                             uses 16 (util/scheduler_helper.go:84,137); <=1 = serial                */
   int64_t max_tasks;     /* >0: stop after this many tasks were popped (bounded timing sample)    */
   double  max_seconds;   /* >0: stop once this much wall time has elapsed (bounded timing sample)  */
+  int32_t actions;       /* bit 0 allocate (default when 0), bit 1 backfill afterwards on the same session
+                            ("allocate, backfill" = the default action list, pkg/scheduler/util.go:31-42)  */
+  int32_t reserved;
 } kbo_opts;
+#define KBO_ACTION_ALLOCATE 1
+#define KBO_ACTION_BACKFILL 2
 
 typedef struct kbo_result {
   uint64_t pairs_logical;    /* sum over processed tasks of N                                      */

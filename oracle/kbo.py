@@ -24,7 +24,8 @@ KBO_MODE_FAITHFUL = 1
 
 
 class kbo_opts(C.Structure):
-    _fields_ = [("mode", C.c_int32), ("threads", C.c_int32), ("max_tasks", C.c_int64), ("max_seconds", C.c_double)]
+    _fields_ = [("mode", C.c_int32), ("threads", C.c_int32), ("max_tasks", C.c_int64), ("max_seconds", C.c_double),
+                ("actions", C.c_int32), ("reserved", C.c_int32)]
 
 
 class kbo_result(C.Structure):
@@ -99,12 +100,16 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+KBO_ACTION_ALLOCATE = 1
+KBO_ACTION_BACKFILL = 2
+
+
 def allocate(snap: Snapshot, conf: PluginConf, mode: int = KBO_MODE_OPTIMISED, threads: int = 1,
-             max_tasks: int = 0, max_seconds: float = 0.0) -> OracleOut:
+             max_tasks: int = 0, max_seconds: float = 0.0, actions: int = KBO_ACTION_ALLOCATE) -> OracleOut:
     L = lib()
     cs, keep1 = snap.to_c()
     cc, keep2 = conf.to_c()
-    o = kbo_opts(mode, threads, max_tasks, max_seconds)
+    o = kbo_opts(mode, threads, max_tasks, max_seconds, actions, 0)
     R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
     dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
     res = kbo_result()

@@ -43,13 +43,15 @@ struct SlotAcc {
 
 struct Emu {
   BuiltSession B;
-  DevSession S{};
+  DevSession S{};            // allocate view
+  DevSession Sbf{};          // backfill view (kb_backfill)
+  DevSession* cur = nullptr; // view the launches run on
   uint32_t launches = 0;
 };
 
 // visit_kernel, scan + merge + (sharded) pack: keys[32] then columns [ncols][32]
 void emu_scan(Emu& E, uint64_t* sendbuf) {
-  const DevSession& S = E.S;
+  const DevSession& S = *E.cur;
   const Ctl& c = *S.ctl;
   const size_t cnt = (size_t)(1 + S.ncols) * 32;
   std::fill(sendbuf, sendbuf + cnt, 0ull);
@@ -130,7 +132,7 @@ void replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       S.job_placed[j] += 1;
       on_allocate_event(S, j, cls);
       placed += 1;
-      if (ssn_job_ready(S, j) && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
+      if (ssn_job_ready(S, j) && (pos + 1 < jend) && !S.backfill) { reason = STOP_YIELD; break; }
     }
     if (reason == STOP_RESCAN) c.rescans += 1;
     after_run(S, c, reason, placed);
@@ -153,7 +155,7 @@ void write_back(const DevSession& S, const ClassRec& cls, std::vector<Cand>& can
 
 // replay_kernel / replay_epilogue
 void emu_replay(Emu& E, const uint64_t* recvbuf) {
-  const DevSession& S = E.S;
+  const DevSession& S = *E.cur;
   Ctl& c = *S.ctl;
   E.launches += 1;
   if (c.done) return;
@@ -192,7 +194,7 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
 // the visit after the current one) skipping Ctl.excl, while the replayer CTA consumes Ctl.list; the last CTA merges the scan
 // lists with the replayer's patch keys and publishes list / scan_class / excl for the next launch.
 void emu_launch_overlap(Emu& E) {
-  const DevSession& S = E.S;
+  const DevSession& S = *E.cur;
   Ctl& c = *S.ctl;
   E.launches += 1;
   if (c.done) return;
@@ -275,25 +277,47 @@ void emu_launch_overlap(Emu& E) {
   }
 }
 
-// gang_commit_kernel, serially
-void emu_gang_commit(const DevSession& S, const int32_t* ready0) {
+// gang_commit_kernel, serially: a job's processed slots of the allocate view, then of the backfill view
+void emu_gang_commit(const DevSession& S, const DevSession& Sbf, const int32_t* ready0) {
   for (uint32_t j = 0; j < S.J; ++j) {
-    const uint32_t lo = S.job_ord_off[j], hi = S.job_pos[j];
+    std::vector<uint32_t> tasks;
+    for (uint32_t i = S.job_ord_off[j]; i < S.job_pos[j]; ++i) tasks.push_back(S.ord_task[i]);
+    for (uint32_t i = Sbf.job_ord_off[j]; i < Sbf.job_pos[j]; ++i) {
+      const uint32_t t = Sbf.ord_task[i];
+      if (S.dec[t].kind == KB_KIND_SKIPPED) S.dec[t].kind = KB_KIND_NONE;
+      tasks.push_back(t);
+    }
     const int32_t need = S.gang_ready ? S.job_min_avail[j] - ready0[j] : 0;
     int32_t incl = 0;
-    uint32_t estar = 0xFFFFFFFFu, estep = 0;
-    for (uint32_t i = lo; i < hi; ++i) {
-      const kb_decision& d = S.dec[S.ord_task[i]];
+    size_t estar = (size_t)-1; uint32_t estep = 0;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+      const kb_decision& d = S.dec[tasks[i]];
       if (d.kind == KB_KIND_ALLOCATED) { incl += 1; if (incl >= need) { estar = i; estep = d.step; break; } }
     }
-    if (estar == 0xFFFFFFFFu) continue;
-    for (uint32_t i = lo; i < hi; ++i) {
-      kb_decision& d = S.dec[S.ord_task[i]];
+    if (estar == (size_t)-1) continue;
+    for (size_t i = 0; i < tasks.size(); ++i) {
+      kb_decision& d = S.dec[tasks[i]];
       if (d.kind != KB_KIND_ALLOCATED) continue;
       d.dispatched = 1;
       d.dispatch_step = i <= estar ? estep : d.step;
     }
   }
+}
+
+// seed_backfill_kernel + the switch kb_backfill makes
+void emu_begin_backfill(Emu& E, bool carry) {
+  const Ctl& m = *E.S.ctl;
+  Ctl& b = *E.Sbf.ctl;
+  if (!b.bf_seeded && !carry) b.bf_seeded = 1;
+  if (!b.bf_seeded) {
+    b.bf_seeded = 1;
+    b.step = m.step;
+    b.tasks_processed = m.tasks_processed; b.tasks_allocated = m.tasks_allocated; b.tasks_pipelined = m.tasks_pipelined;
+    b.visits = m.visits; b.scans = m.scans; b.rescans = m.rescans;
+    b.pairs_logical = m.pairs_logical; b.pairs_scanned = m.pairs_scanned; b.pairs_replayed = m.pairs_replayed;
+    b.predictions = m.predictions; b.mispredictions = m.mispredictions;
+  }
+  E.cur = &E.Sbf;
 }
 }  // namespace
 
@@ -307,10 +331,13 @@ void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t
   // the emulation always exercises the overlap protocol on one rank (the device enables it by size)
   if (build_session(snap, conf, 148, E->B, &be, rank, world, 1)) { g_err = be.msg; delete E; return nullptr; }
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
+  E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
+  E->cur = &E->S;
   return E;
 }
 void kbemu_destroy(void* h) { delete (Emu*)h; }
-int kbemu_done(void* h) { return ((Emu*)h)->S.ctl->done ? 1 : 0; }
+int kbemu_done(void* h) { return ((Emu*)h)->cur->ctl->done ? 1 : 0; }
+void kbemu_begin_backfill(void* h, int allocate_ran) { emu_begin_backfill(*(Emu*)h, allocate_ran != 0); }
 uint32_t kbemu_buf_u64(void* h) { return (1 + ((Emu*)h)->S.ncols) * 32; }
 void kbemu_scan(void* h, uint64_t* sendbuf) { emu_scan(*(Emu*)h, sendbuf); }
 void kbemu_replay(void* h, const uint64_t* recvbuf) { emu_replay(*(Emu*)h, recvbuf); }
@@ -322,7 +349,7 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
   Emu& E = *(Emu*)h;
   const DevSession& S = E.S;
   const BuiltSession& B = E.B;
-  emu_gang_commit(S, (const int32_t*)(B.imm.host.data() + B.oi.job_ready0));
+  emu_gang_commit(S, E.Sbf, (const int32_t*)(B.imm.host.data() + B.oi.job_ready0));
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q;
   if (out) memcpy(out, S.dec, (size_t)T * sizeof(kb_decision));
   const size_t tile_u64 = (size_t)B.ncols * TILE_NODES;
@@ -347,7 +374,7 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
     }
   }
   if (stats) {
-    const Ctl& c = *S.ctl;
+    const Ctl& c = *E.cur->ctl;
     memset(stats, 0, sizeof *stats);
     stats->pairs_logical = c.pairs_logical; stats->pairs_scanned = c.pairs_scanned; stats->pairs_replayed = c.pairs_replayed;
     stats->tasks_processed = c.tasks_processed; stats->tasks_allocated = c.tasks_allocated; stats->tasks_pipelined = c.tasks_pipelined;
@@ -361,18 +388,23 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
 }
 
 // single-rank convenience: the whole cycle
-int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, kb_decision* out, kb_stats* stats,
+int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t actions /* bit0 allocate, bit1 backfill */,
+                   kb_decision* out, kb_stats* stats,
                    double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
                    int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
                    double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
   Emu* E = (Emu*)kbemu_create(snap, conf, 0, 1);
   if (!E) return KB_E_BADARG;
   std::vector<uint64_t> buf(kbemu_buf_u64(E));
-  const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To) + 1024;
-  while (!E->S.ctl->done) {
-    if (E->S.overlap) emu_launch_overlap(*E);
-    else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
-    if (E->launches > guard) { g_err = "emulated cycle did not terminate"; delete E; return KB_E_STATE; }
+  const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To + E->B.Tb) + 1024;
+  for (uint32_t pass = 0; pass < 2; ++pass) {
+    if (!((actions ? actions : 1u) & (1u << pass))) continue;
+    if (pass == 1) emu_begin_backfill(*E, ((actions ? actions : 1u) & 1u) != 0);
+    while (!E->cur->ctl->done) {
+      if (E->cur->overlap) emu_launch_overlap(*E);
+      else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
+      if (E->launches > guard) { g_err = "emulated cycle did not terminate"; delete E; return KB_E_STATE; }
+    }
   }
   int rc = kbemu_finish(E, out, stats, node_idle, node_releasing, node_used, node_pods, node_nz_cpu, node_nz_mem, node_ports,
                         job_share, job_ready, queue_share, queue_deserved, queue_allocated);

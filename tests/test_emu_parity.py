@@ -4,6 +4,7 @@ the oracle bit-exactly.  The CUDA thread mechanics themselves are covered by the
 import numpy as np
 import pytest
 
+from kube_batch_b200 import abi
 from kube_batch_b200 import builder as B
 from kube_batch_b200 import synth
 from kube_batch_b200.snapshot import PluginConf, PluginOption, Snapshot
@@ -28,9 +29,9 @@ CONFS = {
 }
 
 
-def check(snap, conf, what):
-    o = kbo.allocate(snap, conf)
-    e = util.emu_allocate(snap, conf)
+def check(snap, conf, what, actions=1):
+    o = kbo.allocate(snap, conf, actions=actions)
+    e = util.emu_allocate(snap, conf, actions=actions)
     util.assert_same_decisions(o.decisions, e.decisions, what)
     ns, os_ = util.emu_states(e)
     util.assert_same_state(o, ns, os_, what)
@@ -133,6 +134,59 @@ def test_host_ports_taints_selectors_affinity():
     assert got["ns/port-1"] != got["ns/port-2"] and got["ns/port-1"] is not None   # wildcard IP conflicts with 10.0.0.1
     assert got["ns/aff"] == "n3"
     assert got["ns/nowhere"] is None
+
+
+# ---------------- backfill (actions/backfill/backfill.go:40-71), the action after allocate in the default list ----------------
+@pytest.mark.parametrize("seed", range(16))
+def test_backfill_random_sessions(seed):
+    rng = np.random.default_rng(1000 + seed)
+    tasks = int(rng.integers(5, 300))
+    s = synth.random_session(seed + 300, tasks=tasks, jobs=int(rng.integers(1, min(tasks, 40) + 1)), nodes=int(rng.integers(1, 200)),
+                             queues=int(rng.integers(1, 5)), min_member_frac=float(rng.choice([0.0, 0.5, 1.0])),
+                             hetero=float(rng.choice([0, 0.3, 1.0])), oversub=float(rng.choice([0.7, 1.3, 3.0])),
+                             be_frac=float(rng.choice([0.1, 0.3, 0.9])), be_variants=True)
+    for cname in ("default", "c2", "none", "allocate_test", "weights"):
+        for actions in (2, 3):           # "backfill" alone and "allocate, backfill"
+            check(s, CONFS[cname], f"backfill seed{seed}/{cname}/actions{actions}", actions=actions)
+
+
+def test_backfill_first_feasible_node_pod_cap_and_gang():
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "a-gang3", "q", min_member=3))      # JobID order: ns/a-gang3 before ns/be
+    b.add_pod_group(B.PodGroup("ns", "be", "q", min_member=1))
+    b.add_node(B.Node("n0", {"cpu": 8, "memory": 32e9, "pods": 3}, labels={"zone": "a"}))
+    b.add_node(B.Node("n1", {"cpu": 8, "memory": 32e9, "pods": 4}, labels={"zone": "b"}))
+    req = {"cpu": 1, "memory": 1e9}
+    # gang of 3: two regular pods (allocate places them, the job is NOT ready) + one best-effort pod (backfill completes it)
+    b.add_pod(B.Pod("ns", "g-a", "", "Pending", req, group="a-gang3", creation=1))
+    b.add_pod(B.Pod("ns", "g-b", "", "Pending", req, group="a-gang3", creation=2))
+    b.add_pod(B.Pod("ns", "g-be", "", "Pending", {}, group="a-gang3", creation=3))
+    # best-effort pods: first feasible node in name order, the pod cap moves them on, a selector nobody matches leaves one out
+    for i in range(3):
+        b.add_pod(B.Pod("ns", f"be-{i}", "", "Pending", {}, group="be", creation=10 + i))
+    b.add_pod(B.Pod("ns", "be-zone-b", "", "Pending", {}, group="be", node_selector={"zone": "b"}, creation=20))
+    b.add_pod(B.Pod("ns", "be-nowhere", "", "Pending", {}, group="be", node_selector={"zone": "z"}, creation=21))
+    b.add_pod(B.Pod("ns", "be-late", "", "Pending", {}, group="be", creation=22))
+    s = b.flatten()
+    conf = PluginConf.default()
+    o1, _ = check(s, conf, "backfill-hand/allocate", actions=1)
+    o, e = check(s, conf, "backfill-hand/allocate+backfill", actions=3)
+    name = {s.meta["tasks"][t]: t for t in range(s.T)}
+    d1, d = o1.decisions, o.decisions
+    node = lambda n: s.meta["nodes"][int(d["node"][name[n]])] if d["node"][name[n]] >= 0 else None
+    # after allocate alone the gang is short of one member: nothing dispatched, the best-effort pod was skipped
+    assert not d1["dispatched"][name["ns/g-a"]] and d1["kind"][name["ns/g-be"]] == abi.KB_KIND_SKIPPED
+    assert {node("ns/g-a"), node("ns/g-b")} == {"n0", "n1"}              # least-requested spreads the two
+    # backfill completes the gang: all three dispatched AT the backfill step of g-be
+    for n in ("ns/g-a", "ns/g-b", "ns/g-be"):
+        assert d["dispatched"][name[n]] and d["dispatch_step"][name[n]] == d["step"][name["ns/g-be"]]
+    assert d["step"][name["ns/g-be"]] > max(d["step"][name["ns/g-a"]], d["step"][name["ns/g-b"]])
+    got = [node(n) for n in ("ns/g-be", "ns/be-0", "ns/be-1", "ns/be-2", "ns/be-zone-b", "ns/be-nowhere", "ns/be-late")]
+    # tasks go in UID order (be-0, be-1, be-2, be-late, be-nowhere, be-zone-b): be-late takes n1's last slot (cap 4)
+    assert got == ["n0", "n0", "n1", "n1", None, None, "n1"]
+    assert d["kind"][name["ns/be-nowhere"]] == abi.KB_KIND_NONE and d["kind"][name["ns/be-zone-b"]] == abi.KB_KIND_NONE
+    assert o.node_pods.tolist() == [3, 4]
 
 
 def test_unknown_plugin_is_refused():

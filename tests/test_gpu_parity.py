@@ -166,6 +166,46 @@ def test_unknown_plugin_and_unsupported_feature_fail_loudly(eng):
     assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
 
 
+# ---------------- kb_backfill (actions/backfill/backfill.go:40-71) ----------------
+def run_backfill_and_check(eng, snap, conf, what, actions):
+    o = kbo.allocate(snap, conf, actions=actions)
+    eng.load(snap, conf)
+    r = eng.allocate() if actions & 1 else None
+    r = eng.backfill()
+    util.assert_same_decisions(o.decisions, r.decisions, what)
+    util.assert_same_state(o, eng.node_state(), eng.order_state(), what)
+    st = r.stats
+    assert (st.tasks_processed, st.tasks_allocated, st.tasks_pipelined, st.visits, st.jobs_ready, st.pairs_logical) == \
+        (o.result.tasks_processed, o.result.tasks_allocated, o.result.tasks_pipelined, o.result.visits, o.result.jobs_ready,
+         o.result.pairs_logical), what
+    return o, r
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_backfill_random_sessions(eng, seed):
+    rng = np.random.default_rng(1000 + seed)
+    tasks = int(rng.integers(5, 300))
+    s = synth.random_session(seed + 300, tasks=tasks, jobs=int(rng.integers(1, min(tasks, 40) + 1)), nodes=int(rng.integers(1, 200)),
+                             queues=int(rng.integers(1, 5)), min_member_frac=float(rng.choice([0.0, 0.5, 1.0])),
+                             hetero=float(rng.choice([0, 0.3, 1.0])), oversub=float(rng.choice([0.7, 1.3, 3.0])),
+                             be_frac=float(rng.choice([0.1, 0.3, 0.9])), be_variants=True)
+    for cname in ("default", "c2", "allocate_test"):
+        for actions in (2, 3):
+            run_backfill_and_check(eng, s, CONFS[cname], f"backfill seed{seed}/{cname}/actions{actions}", actions)
+
+
+def test_backfill_multi_tile_then_allocate_restarts(eng):
+    # many nodes (several tiles), many best-effort pods; afterwards kb_allocate must restart from the loaded state
+    s = synth.random_session(77, tasks=1500, jobs=60, nodes=3000, queues=2, min_member_frac=0.5, hetero=0.3, oversub=1.3,
+                             be_frac=0.3, be_variants=True)
+    conf = PluginConf.default()
+    o, r = run_backfill_and_check(eng, s, conf, "backfill multi-tile", 3)
+    again = eng.backfill()                       # nothing left to do: same table
+    util.assert_same_decisions(r.decisions, again.decisions, "second kb_backfill")
+    a = eng.allocate()
+    util.assert_same_decisions(kbo.allocate(s, conf).decisions, a.decisions, "kb_allocate after kb_backfill")
+
+
 def test_c3_full_size_parity_and_properties(eng):
     """BASELINE config 3 (50k tasks x 5k nodes, default tiers) — full-size parity and invariants."""
     s, conf = synth.make("c3")

@@ -26,8 +26,9 @@ def _worker(rank, world, port, case, q):
     import util
     from oracle import kbo
     snap, conf = case()
-    out = util.emu_sharded_rank(rank, world, port, snap, conf)
-    ref = kbo.allocate(snap, conf)
+    actions = getattr(case, "actions", 1)
+    out = util.emu_sharded_rank(rank, world, port, snap, conf, actions=actions)
+    ref = kbo.allocate(snap, conf, actions=actions)
     try:
         util.assert_same_decisions(ref.decisions, out.decisions, f"rank{rank}/{world}")
         ns, os_ = util.emu_states(out)
@@ -51,7 +52,15 @@ def case_fewer_tiles_than_ranks():
     return synth.random_session(5, tasks=80, jobs=9, nodes=40, queues=2), PluginConf.default()
 
 
-@pytest.mark.parametrize("world,case", [(2, case_c2), (2, case_multi_tile_multi_queue), (3, case_multi_tile_multi_queue),
+def case_allocate_then_backfill():
+    s = synth.random_session(11, tasks=400, jobs=30, nodes=700, queues=2, min_member_frac=0.5, be_frac=0.3, be_variants=True)
+    return s, PluginConf.default()
+
+
+case_allocate_then_backfill.actions = 3      # "allocate, backfill": kb_allocate then kb_backfill on every rank
+
+
+@pytest.mark.parametrize("world,case", [(2, case_c2), (2, case_allocate_then_backfill), (2, case_multi_tile_multi_queue), (3, case_multi_tile_multi_queue),
                                         (2, case_fewer_tiles_than_ranks)])
 def test_sharded_node_axis_matches_oracle(world, case):
     ctx = mp.get_context("spawn")

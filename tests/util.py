@@ -32,8 +32,9 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def emu_allocate(snap: Snapshot, conf: PluginConf) -> kbo.OracleOut:
-    """Run the CPU emulation of the device algorithm; same result container as the oracle."""
+def emu_allocate(snap: Snapshot, conf: PluginConf, actions: int = 1) -> kbo.OracleOut:
+    """Run the CPU emulation of the device algorithm; same result container as the oracle.
+    actions: bit 0 = allocate (kb_allocate), bit 1 = backfill afterwards (kb_backfill)."""
     L = emu_lib()
     cs, k1 = snap.to_c()
     cc, k2 = conf.to_c()
@@ -47,7 +48,7 @@ def emu_allocate(snap: Snapshot, conf: PluginConf) -> kbo.OracleOut:
         node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
         job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
         queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
-    rc = L.kbemu_allocate(C.byref(cs), C.byref(cc), dec.ctypes.data_as(C.c_void_p), C.byref(st),
+    rc = L.kbemu_allocate(C.byref(cs), C.byref(cc), C.c_uint32(actions), dec.ctypes.data_as(C.c_void_p), C.byref(st),
                           _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
                           _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
                           _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
@@ -95,7 +96,7 @@ def emu_states(e: kbo.OracleOut):
 # ------------------------------------------------------------------------------------------------
 # sharded node axis on CPU: one process per rank, torch.distributed / gloo instead of NCCL
 # ------------------------------------------------------------------------------------------------
-def emu_sharded_rank(rank: int, world: int, port: int, snap: Snapshot, conf: PluginConf):
+def emu_sharded_rank(rank: int, world: int, port: int, snap: Snapshot, conf: PluginConf, actions: int = 1):
     """Run the scan -> all-gather -> replay chain of the multi-GPU path with the CPU emulation and gloo.
     Returns the same container as emu_allocate (every rank holds the full, identical result)."""
     import torch
@@ -122,13 +123,20 @@ def emu_sharded_rank(rank: int, world: int, port: int, snap: Snapshot, conf: Plu
         n = L.kbemu_buf_u64(h)
         send = torch.zeros(n, dtype=torch.int64)
         recv = torch.zeros(world * n, dtype=torch.int64)
+        L.kbemu_begin_backfill.argtypes = [C.c_void_p, C.c_int]
+        L.kbemu_begin_backfill.restype = None
         guard = 0
-        while not L.kbemu_done(h):
-            L.kbemu_scan(h, C.c_void_p(send.data_ptr()))
-            dist.all_gather_into_tensor(recv, send)          # == ncclAllGather(sendbuf, recvbuf, ...)
-            L.kbemu_replay(h, C.c_void_p(recv.data_ptr()))
-            guard += 1
-            assert guard < 10_000_000
+        for bit in (1, 2):
+            if not (actions & bit):
+                continue
+            if bit == 2:
+                L.kbemu_begin_backfill(h, 1 if (actions & 1) else 0)                        # kb_backfill: switch to the backfill view
+            while not L.kbemu_done(h):
+                L.kbemu_scan(h, C.c_void_p(send.data_ptr()))
+                dist.all_gather_into_tensor(recv, send)          # == ncclAllGather(sendbuf, recvbuf, ...)
+                L.kbemu_replay(h, C.c_void_p(recv.data_ptr()))
+                guard += 1
+                assert guard < 10_000_000
         R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
         dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
         st = abi.kb_stats()
