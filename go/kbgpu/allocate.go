@@ -19,18 +19,27 @@ func (alloc *allocateAction) Initialize()        {}
 func (alloc *allocateAction) UnInitialize()      {}
 
 // Execute replaces the queue->job->task loop of allocate.go:43-194: flatten, one kb_allocate, replay.
-func (alloc *allocateAction) Execute(ssn *framework.Session) {
+func (alloc *allocateAction) Execute(ssn *framework.Session) { run(alloc.engine, ssn, false) }
+
+// run is one action on the GPU; every action flattens the session as it is NOW, like the reference runs its
+// actions one after the other on the same *framework.Session (scheduler.go:88-92).
+func run(engine *Engine, ssn *framework.Session, backfill bool) {
 	flat, tiers, err := Flatten(ssn) // canonical orders + label/taint/port atom interning; see flatten.go
 	if err != nil {
 		// e.g. a non built-in plugin registered a PredicateFn: no CPU fallback — skip the cycle loudly.
 		glog.Errorf("kbgpu: session cannot be flattened: %v", err)
 		return
 	}
-	if err := alloc.engine.Load(flat, tiers); err != nil {
+	if err := engine.Load(flat, tiers); err != nil {
 		glog.Errorf("kbgpu: %v", err)
 		return
 	}
-	dec, err := alloc.engine.Allocate(len(flat.Tasks))
+	var dec []Decision
+	if backfill {
+		dec, err = engine.Backfill(len(flat.Tasks))
+	} else {
+		dec, err = engine.Allocate(len(flat.Tasks))
+	}
 	if err != nil {
 		glog.Errorf("kbgpu: %v", err)
 		return

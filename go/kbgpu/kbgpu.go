@@ -60,10 +60,19 @@ type Decision struct {
 }
 
 // Allocate runs the whole allocate cycle on the GPU and returns one decision per flattened task.
-func (e *Engine) Allocate(nTasks int) ([]Decision, error) {
+func (e *Engine) Allocate(nTasks int) ([]Decision, error) { return e.action(nTasks, false) }
+
+// Backfill runs backfillAction.Execute (backfill.go:40-71) on the loaded session's current device state.
+func (e *Engine) Backfill(nTasks int) ([]Decision, error) { return e.action(nTasks, true) }
+
+func (e *Engine) action(nTasks int, backfill bool) ([]Decision, error) {
 	raw := make([]C.kb_decision, nTasks+1)
 	var st C.kb_stats
-	if rc := C.kb_allocate(e.h, (*C.kb_decision)(unsafe.Pointer(&raw[0])), &st); rc != 0 {
+	if backfill {
+		if rc := C.kb_backfill(e.h, (*C.kb_decision)(unsafe.Pointer(&raw[0])), &st); rc != 0 {
+			return nil, e.err("kb_backfill", rc)
+		}
+	} else if rc := C.kb_allocate(e.h, (*C.kb_decision)(unsafe.Pointer(&raw[0])), &st); rc != 0 {
 		return nil, e.err("kb_allocate", rc)
 	}
 	out := make([]Decision, nTasks)

@@ -488,11 +488,13 @@ inline Flat Flatten(const framework::Session& ssn) {
   return f;
 }
 
-class allocateAction : public framework::Action {
- public:
-  std::string Name() const override { return "allocate"; }               // allocate.go:38
-  // actions/allocate/allocate.go:43-194, on the GPU: flatten -> kb_session_load -> kb_allocate -> replay
-  void Execute(framework::Session* ssn) override {
+// One action on the GPU: flatten the session as it is NOW -> kb_session_load -> kb_allocate | kb_backfill -> replay the
+// decisions through the session's own Allocate / Pipeline.  Every action flattens afresh, so "allocate, backfill" (the
+// default list, pkg/scheduler/util.go:31-42) is two such calls, exactly like the reference runs two Execute()s on one
+// session.  (A shim that wants to save the second flatten + upload can call kb_allocate and kb_backfill back to back on
+// one loaded session instead: see INTEGRATION.md.)
+inline void ExecuteOnGpu(framework::Session* ssn, const bool backfill) {
+  {
     // tiers: only built-in registrations can be honoured
     std::vector<kb_plugin_option> opts; std::vector<kb_tier> tiers; std::vector<std::vector<const char*>> keys, vals;
     size_t total = 0; for (auto& t : ssn->Tiers) total += t.Plugins.size();
@@ -539,8 +541,8 @@ class allocateAction : public framework::Action {
     if (rc != KB_OK) throw std::runtime_error(std::string("kb_session_load: ") + kb_last_error(eng) + " [" + kb_status_str(rc) + "]");
     std::vector<kb_decision> dec(std::max(1u, f.T));
     kb_stats st{};
-    rc = kb_allocate(eng, dec.data(), &st);
-    if (rc != KB_OK) throw std::runtime_error(std::string("kb_allocate: ") + kb_last_error(eng) + " [" + kb_status_str(rc) + "]");
+    rc = backfill ? kb_backfill(eng, dec.data(), &st) : kb_allocate(eng, dec.data(), &st);
+    if (rc != KB_OK) throw std::runtime_error(std::string(backfill ? "kb_backfill: " : "kb_allocate: ") + kb_last_error(eng) + " [" + kb_status_str(rc) + "]");
     // replay in call order through the session's own Allocate / Pipeline (gang dispatch, Binder.Bind happen there)
     std::vector<uint32_t> order;
     for (uint32_t t = 0; t < f.T; ++t) if (dec[t].kind == KB_KIND_ALLOCATED || dec[t].kind == KB_KIND_PIPELINED) order.push_back(t);
@@ -550,9 +552,26 @@ class allocateAction : public framework::Action {
       else ssn->Pipeline(f.tasks[t], f.nodeNames[dec[t].node]);
     }
   }
+}
+
+class allocateAction : public framework::Action {
+ public:
+  std::string Name() const override { return "allocate"; }               // allocate.go:38
+  // actions/allocate/allocate.go:43-194, on the GPU
+  void Execute(framework::Session* ssn) override { ExecuteOnGpu(ssn, false); }
 };
 inline std::unique_ptr<framework::Action> New() { return std::make_unique<allocateAction>(); }
 
 }}  // namespace actions::allocate
+
+namespace actions { namespace backfill {
+class backfillAction : public framework::Action {
+ public:
+  std::string Name() const override { return "backfill"; }               // backfill.go:35
+  // actions/backfill/backfill.go:40-71, on the GPU
+  void Execute(framework::Session* ssn) override { allocate::ExecuteOnGpu(ssn, true); }
+};
+inline std::unique_ptr<framework::Action> New() { return std::make_unique<backfillAction>(); }
+}}  // namespace actions::backfill
 
 }  // namespace kb

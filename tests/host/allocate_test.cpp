@@ -26,6 +26,7 @@ struct Case {
   std::vector<std::pair<std::string, int>> queues;
   std::vector<conf::Tier> tiers;
   std::map<std::string, std::string> expected;
+  std::vector<std::string> actions = {"allocate"};
 };
 
 int main() {
@@ -62,6 +63,26 @@ int main() {
                      {{"ns/a0", "n1"}, {"ns/a1", "n1"}}});
   }
 
+  {
+    // "allocate, backfill" (the default action list, pkg/scheduler/util.go:31-42): the gang of 3 has two regular pods and
+    // one best-effort pod; allocate leaves the job one short, backfill (backfill.go:40-71) places the best-effort pod and the
+    // session then dispatches all three.  The selector-less best-effort pod of pgBE goes to the first node by name.
+    conf::PluginOption gang = Opt("gang"); gang.EnabledJobOrder = 1; gang.EnabledJobReady = 1;
+    conf::PluginOption pred = Opt("predicates"); pred.EnabledPredicate = 1;
+    conf::PluginOption nodeorder = Opt("nodeorder"); nodeorder.EnabledNodeOrder = 1;
+    api::ResourceList node = BuildResourceList(4, 16 * G); node["pods"] = 110;
+    std::vector<api::Pod> pods;
+    pods.push_back(BuildPod("ns", "g0", "", "Pending", BuildResourceList(1, 1 * G), "pgG"));
+    pods.push_back(BuildPod("ns", "g1", "", "Pending", BuildResourceList(1, 1 * G), "pgG"));
+    pods.push_back(BuildPod("ns", "g2-be", "", "Pending", {}, "pgG"));
+    pods.push_back(BuildPod("ns", "solo-be", "", "Pending", {}, "pgBE"));
+    Case c{"allocate, backfill: a best-effort pod completes the gang", {{"ns", "pgG", "q", 3}, {"ns", "pgBE", "q", 1}}, pods,
+           {BuildNode("n1", node), BuildNode("n2", node)}, {{"q", 1}}, {conf::Tier{{gang}}, conf::Tier{{pred, nodeorder}}},
+           {{"ns/g0", "n1"}, {"ns/g1", "n2"}, {"ns/g2-be", "n1"}, {"ns/solo-be", "n1"}}};
+    c.actions = {"allocate", "backfill"};
+    tests.push_back(c);
+  }
+
   int failed = 0;
   for (size_t i = 0; i < tests.size(); ++i) {
     auto& test = tests[i];
@@ -73,9 +94,11 @@ int main() {
     for (auto& ss : test.podGroups) schedulerCache.AddPodGroup(ss);
     for (auto& q : test.queues) schedulerCache.AddQueue(q.first, q.second);
     auto ssn = framework::OpenSession(&schedulerCache, test.tiers);
-    auto allocate = actions::allocate::New();
     try {
-      allocate->Execute(ssn.get());
+      for (auto& name : test.actions) {                                   // scheduler.go:88-92: every action on the same session
+        auto action = name == "backfill" ? actions::backfill::New() : actions::allocate::New();
+        action->Execute(ssn.get());
+      }
     } catch (const std::exception& e) {
       std::cerr << "case " << i << " (" << test.name << "): Execute failed loudly: " << e.what() << "\n";
       framework::CloseSession(ssn.get());

@@ -32,4 +32,4 @@ def test_reference_allocate_test_in_cpp():
     _build()
     p = subprocess.run([EXE], capture_output=True, text=True)
     assert p.returncode == 0, p.stdout + p.stderr
-    assert p.stdout.count("ok   case") == 3
+    assert p.stdout.count("ok   case") == 4
