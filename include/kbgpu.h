@@ -164,6 +164,9 @@ typedef struct kb_plugin_conf {
 
 #define KB_ENGINE_NO_OVERLAP    (1u << 0) /* never run the scan of the next visit concurrently with the replay */
 #define KB_ENGINE_FORCE_OVERLAP (1u << 1) /* always (single GPU); default: only when the scan dominates (large N) */
+#define KB_ENGINE_CHAIN_OFF     (1u << 2) /* one class per launch (visit_kernel); default: chained visits (single GPU, no overlap) */
+#define KB_ENGINE_CHAIN2        (1u << 3) /* scan 2 classes per launch and replay the following visit from the look-ahead list  */
+#define KB_ENGINE_CHAIN4        (1u << 4) /* ... 4 classes per launch                                                          */
 
 typedef struct kb_engine_opts {
   uint32_t abi_version;     /* KB_ABI_VERSION */
@@ -212,7 +215,7 @@ typedef struct kb_stats {
   uint32_t predictions;     /* overlap mode: launches whose scan ran ahead on a predicted class   */
   uint32_t mispredictions;  /*   ... of which the prediction was wrong (that launch's scan is redone) */
   uint32_t exchange_mode;   /* 0 single GPU, 1 NCCL all-gather per scan, 2 fused peer-memory exchange  */
-  uint32_t reserved1;
+  uint32_t chain_hits;      /* chained visits: visits replayed from a look-ahead list of an earlier launch's scan */
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

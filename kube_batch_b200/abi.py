@@ -7,6 +7,11 @@ from __future__ import annotations
 
 import ctypes as C
 
+KB_ENGINE_NO_OVERLAP = 1 << 0
+KB_ENGINE_FORCE_OVERLAP = 1 << 1
+KB_ENGINE_CHAIN_OFF = 1 << 2
+KB_ENGINE_CHAIN2 = 1 << 3
+KB_ENGINE_CHAIN4 = 1 << 4
 KB_ABI_VERSION = 1
 KB_MAX_R = 8
 KB_MAX_W = 4
@@ -176,7 +181,7 @@ class kb_stats(C.Structure):
         ("predictions", C.c_uint32),
         ("mispredictions", C.c_uint32),
         ("exchange_mode", C.c_uint32),
-        ("reserved1", C.c_uint32),
+        ("chain_hits", C.c_uint32),
     ]
 
 

@@ -191,7 +191,7 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf,
                 bf_job_pos, bf_ctl; };
 struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0,
-                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes; };
+                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes, ord_chain; };
 
 struct BuiltSession {
   Slab mut, imm;
@@ -203,6 +203,7 @@ struct BuiltSession {
   double total[KB_MAX_R] = {0};
   std::vector<int32_t> job_min_avail;
   uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1, overlap = 0;
+  uint32_t kchain = 1;               // classes per launch (visit_chain_kernel), 1 = off
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
 
   // The BACKFILL VIEW of the same session (backfillAction.Execute, actions/backfill/backfill.go:40-71): same node table,
@@ -210,7 +211,7 @@ struct BuiltSession {
   // control block; no resource predicate, no nodeorder (the first node that passes wins = lowest node index).
   void bind_backfill(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     bind(D, mb, ib);
-    D.backfill = 1; D.overlap = 0;
+    D.backfill = 1; D.overlap = 0; D.kchain = 1;
     D.cf.fit_mode = 1; D.cf.nodeorder = 0; D.cf.score_bias = 0;
     D.To = Tb;
     D.classes = (ClassRec*)(ib + oi.bf_classes);        // same ids; `initreq` holds Resreq (EvalConf.fit_mode)
@@ -243,6 +244,7 @@ struct BuiltSession {
     D.classes = (ClassRec*)(ib + oi.classes); D.ord_task = (uint32_t*)(ib + oi.ord_task); D.ord_class = (uint32_t*)(ib + oi.ord_class);
     D.ord_run = (uint32_t*)(ib + oi.ord_run); D.ord_peek = (uint32_t*)(ib + oi.ord_peek);
     D.overlap = overlap;
+    D.kchain = kchain; D.ord_chain = (uint32_t*)(ib + oi.ord_chain);
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -252,7 +254,8 @@ struct BuiltSession {
 
 // Everything kb_session_load does before touching the device.  `max_grid` = scan CTAs (SM count).
 inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e,
-                         uint32_t rank = 0, uint32_t world = 1, int overlap_mode = -1 /* -1 auto, 0 off, 1 on */) {
+                         uint32_t rank = 0, uint32_t world = 1, int overlap_mode = -1 /* -1 auto, 0 off, 1 on */,
+                         uint32_t kchain = 1 /* classes per launch: 1, 2 or 4 (single GPU, no overlap) */) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
@@ -405,7 +408,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   om.q_share = mut.alloc((size_t)std::max(1u, Q) * 8);
   om.qheap = mut.alloc((size_t)std::max(1u, J) * 4);
   om.dec = mut.alloc((size_t)std::max(1u, T) * sizeof(kb_decision));
-  om.cand = mut.alloc((size_t)grid * KTOP * 8);
+  om.cand = mut.alloc((size_t)grid * KTOP * 8 * KB_CHAIN_MAX);
   om.ctl = mut.alloc(sizeof(Ctl));
   om.sendbuf = mut.alloc((size_t)(1 + ncols) * 32 * 8);
   om.recvbuf = mut.alloc((size_t)std::max(1u, world) * (1 + ncols) * 32 * 8);
@@ -436,6 +439,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.bf_jobs = imm.alloc((size_t)std::max<size_t>(1, bf_jobs.size()) * 4);
   oi.bf_jobs_off = imm.alloc(2 * 4);
   oi.bf_classes = imm.alloc((size_t)(Tb ? C : 1) * sizeof(ClassRec));
+  oi.ord_chain = imm.alloc((size_t)std::max(1u, To) * (KB_CHAIN_MAX - 1) * 4);
   mut.host.resize((mut.host.size() + 255) & ~(size_t)255);
   imm.host.resize((imm.host.size() + 255) & ~(size_t)255);
 
@@ -570,6 +574,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     for (uint32_t q = 0; q < Q; ++q) cnt[q + 1] += cnt[q];
     memcpy(H.q_static_off, cnt.data(), (size_t)(Q + 1) * 4);
     std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
+    std::vector<uint32_t> next_diff(std::max(1u, To), 0xFFFFFFFFu);     // first later slot (static walk) with another class
     for (uint32_t j = 0; j < J; ++j) H.q_static[fill[s->job_queue[j]]++] = j;
     for (uint32_t q = 0; q < Q; ++q) {
       std::sort(H.q_static + cnt[q], H.q_static + cnt[q + 1], [&](uint32_t l, uint32_t r) { return job_before(H, l, r); });
@@ -579,8 +584,23 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
       for (uint32_t k = cnt[q + 1]; k-- > cnt[q];) {
         const uint32_t j = H.q_static[k];
         for (uint32_t i = job_ord_off[j + 1]; i-- > job_ord_off[j];) {
-          if (next_slot == 0xFFFFFFFFu) H.ord_peek[i] = 0xFFFFFFFFu;
-          else H.ord_peek[i] = (ord_class[next_slot] != ord_class[i]) ? ord_class[next_slot] : H.ord_peek[next_slot];
+          if (next_slot == 0xFFFFFFFFu) { H.ord_peek[i] = 0xFFFFFFFFu; next_diff[i] = 0xFFFFFFFFu; }
+          else {
+            H.ord_peek[i] = (ord_class[next_slot] != ord_class[i]) ? ord_class[next_slot] : H.ord_peek[next_slot];
+            next_diff[i] = (ord_class[next_slot] != ord_class[i]) ? next_slot : next_diff[next_slot];
+          }
+          // chain: classes of the following runs, each different from every class before it in the chain
+          uint32_t seen[KB_CHAIN_MAX] = {ord_class[i]};
+          uint32_t ns = 1, sl = next_diff[i];
+          for (uint32_t c = 0; c + 1 < KB_CHAIN_MAX; ++c) {
+            uint32_t cls = 0xFFFFFFFFu;
+            if (sl != 0xFFFFFFFFu && ns == c + 1) {
+              cls = ord_class[sl];
+              for (uint32_t z = 0; z < ns; ++z) if (seen[z] == cls) cls = 0xFFFFFFFFu;     // a repeat ends the chain
+              if (cls != 0xFFFFFFFFu) { seen[ns++] = cls; sl = next_diff[sl]; }
+            }
+            H.ord_chain[(size_t)i * (KB_CHAIN_MAX - 1) + c] = cls;
+          }
           next_slot = i;
         }
       }
@@ -588,6 +608,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   // overlap pays when the scan side (several tile groups per CTA + a wide merge) rivals the replay side
   B.overlap = (world <= 1) ? (overlap_mode < 0 ? ((N >= 65536 && Q == 1) ? 1u : 0u) : (uint32_t)overlap_mode) : 0u;
+  B.kchain = (world <= 1 && !B.overlap && (kchain == 2 || kchain == 4)) ? kchain : 1u;
+  H.kchain = B.kchain;
   Ctl& c0 = *H.ctl;
   memset(&c0, 0, sizeof c0);
   c0.cur_job = -1;
@@ -601,6 +623,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   c0.scan_class = c0.cur_class;      // the first launch has no list yet: scan for the first visit, nothing excluded
   c0.n_excl = 0; c0.list_valid = 0; c0.patch_valid = 0;
   c0.xchg_epoch = 1;
+  publish_chain(H, c0);
 
   // ---------------- backfill view: order tables, cursors, first visit ----------------
   {

@@ -17,6 +17,7 @@
 
 namespace kb {
 
+constexpr uint32_t KB_CHAIN_MAX = 4;        // classes one visit_chain_kernel launch can scan (cur_class + 3 predicted)
 enum StopReason : uint32_t { STOP_RUN_DONE = 0, STOP_NOFIT = 1, STOP_YIELD = 2, STOP_RESCAN = 3 };
 
 struct Ctl {
@@ -46,6 +47,10 @@ struct Ctl {
   uint32_t xchg_epoch;     // peer-memory exchange: sequence number of the next scan (starts at 1; flags are zeroed per cycle)
   uint32_t bf_cursor;      // backfill view: next entry of the best-effort job list (DevSession.q_static)
   uint32_t bf_seeded;      // backfill view: step / counters were carried over from the allocate view
+  // ---- chained visits (visit_chain_kernel): the next launch scans cur_class AND these predicted classes of the
+  //      following visits in one pass over the table (~0u = none); see DevSession.kchain
+  uint32_t chain[KB_CHAIN_MAX - 1];
+  uint32_t chain_hits;     // visits replayed from a look-ahead list (no launch of their own)
   uint32_t excl[32];
   unsigned long long list[32];
   unsigned long long patch[32];
@@ -73,6 +78,9 @@ struct DevSession {
   uint32_t* ord_run;      // [To] number of consecutive slots of the same class starting here (within the job)
   uint32_t* ord_peek;     // [To] first class != ord_class[i] later in the queue's static job order (prediction only), ~0u = none
   uint32_t overlap;       // 1: visit_kernel runs scanners + one replayer CTA concurrently (world == 1)
+  uint32_t kchain;        // 1: one class per launch; 2 / 4: visit_chain_kernel scans that many classes per launch and replays
+                          //    the following visits from the look-ahead lists (patched with the nodes modified meanwhile)
+  uint32_t* ord_chain;    // [To][KB_CHAIN_MAX-1] classes of the next runs with a different class in the queue's static job order
   uint32_t backfill;      // 1: this view drives backfillAction.Execute (backfill.go:40-71): jobs in JobID order, a task without
                           //    a node does not end the job, no yield rule, no resource predicate (EvalConf.fit_mode 1)
   uint32_t* job_ord_off;  // [J+1]
@@ -351,6 +359,15 @@ KB_HD void select_next_visit(const DevSession& S, Ctl& c) {
     setup_run(S, c);
     return;
   }
+}
+
+// End of a launch: the classes the NEXT launch scans besides cur_class (prediction only — a miss costs nothing but the
+// wasted look-ahead).
+KB_HD void publish_chain(const DevSession& S, Ctl& c) {
+  for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX; ++k) c.chain[k] = 0xFFFFFFFFu;
+  if (c.done || c.cur_job < 0 || S.kchain <= 1) return;
+  const uint32_t s0 = S.job_pos[(uint32_t)c.cur_job];
+  for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX && k + 1 < S.kchain; ++k) c.chain[k] = S.ord_chain[(size_t)s0 * (KB_CHAIN_MAX - 1) + k];
 }
 
 // Called once a run stopped.  `placed` = tasks of the run that went through Allocate/Pipeline.

@@ -61,6 +61,8 @@ constexpr int kNcclUint64 = 5;   // ncclUint64 (nccl.h)
 
 }  // namespace
 
+constexpr uint32_t KB_DEFAULT_CHAIN = 1;      // default classes per launch on one GPU (flags / env KB_CHAIN override)
+
 struct kb_engine {
   ncclComm_t comm = nullptr;
   // peer-memory exchange (world > 1): this rank's region and every rank's region as mapped here
@@ -92,11 +94,12 @@ struct kb_engine {
   std::vector<int32_t> job_min_avail_host;
   uint32_t gang_ready = 0;
   uint32_t scan_grid = 1;
-  size_t visit_smem = 0, tile_smem = 0, replay_smem = 0;
+  size_t visit_smem = 0, tile_smem = 0, replay_smem = 0, chain_smem = 0;
   float load_ms = 0;
   float last_kernel_ms = 0;
   int sm_count = 148;
   int overlap_mode = -1;
+  uint32_t kchain_req = KB_DEFAULT_CHAIN;   // classes per launch requested (flags / KB_CHAIN), 1 = visit_kernel
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
   DevSession graph_dev{};              // kernel parameter the graph was captured with
@@ -222,6 +225,8 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   e->device = opts->device;
   e->rank = world > 1 ? opts->rank : 0; e->world = world;
   e->overlap_mode = (opts->flags & KB_ENGINE_NO_OVERLAP) ? 0 : (opts->flags & KB_ENGINE_FORCE_OVERLAP) ? 1 : -1;
+  e->kchain_req = (opts->flags & KB_ENGINE_CHAIN_OFF) ? 1u : (opts->flags & KB_ENGINE_CHAIN4) ? 4u : (opts->flags & KB_ENGINE_CHAIN2) ? 2u : KB_DEFAULT_CHAIN;
+  if (const char* kc = getenv("KB_CHAIN")) { const int v = atoi(kc); if (v == 1 || v == 2 || v == 4) e->kchain_req = (uint32_t)v; }
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
       (c = cudaMallocHost(&e->h_ctl, sizeof(Ctl))) != cudaSuccess) {
@@ -263,7 +268,18 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->loaded = false;
   BuiltSession B;
   BuildErr be;
-  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode))
+  uint32_t kchain = e->world == 1 ? e->kchain_req : 1u;
+  {
+    // the chain kernel keeps K class records, K lists and the fold buffers next to the tile staging buffers: when that
+    // does not fit into shared memory for this record width, fall back to fewer classes per launch
+    const size_t tile_b = (size_t)tile_ncols(s ? s->R : 2, s ? s->W : 1) * TILE_NODES * 8;
+    uint32_t tpi = 4;
+    while (tpi > 1 && 2 * tpi * tile_b > 190 * 1024) --tpi;
+    const size_t lim = 227 * 1024;
+    if (kchain == 4 && chain_smem_header<4>() + 2 * tpi * tile_b > lim) kchain = 2;
+    if (kchain == 2 && chain_smem_header<2>() + 2 * tpi * tile_b > lim) kchain = 1;
+  }
+  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode, kchain))
     return fail(e, rc, "%s", be.msg.c_str());
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q, C = B.C, NT = B.NT, ncols = B.ncols, To = B.To, grid = B.grid;
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;
@@ -320,6 +336,9 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(visit_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  e->chain_smem = 0;
+  if (B.kchain == 2) { e->chain_smem = chain_smem_header<2>() + 2 * (size_t)B.tpi * e->tile_smem; CUDA_TRY(e, cudaFuncSetAttribute(visit_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->chain_smem)); }
+  if (B.kchain == 4) { e->chain_smem = chain_smem_header<4>() + 2 * (size_t)B.tpi * e->tile_smem; CUDA_TRY(e, cudaFuncSetAttribute(visit_chain_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->chain_smem)); }
   CUDA_TRY(e, cudaFuncSetAttribute(matrix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(best_nodes_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->tile_smem));
   // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch)
@@ -335,6 +354,8 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     bool ok = ce == cudaSuccess;
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
       if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+      else if (e->dev.kchain == 2) visit_chain_kernel<2><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(e->dev);
+      else if (e->dev.kchain == 4) visit_chain_kernel<4><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(e->dev);
       else visit_kernel<0><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
       if (e->world > 1 && !e->dev.p2p) {
         ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
@@ -392,6 +413,8 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       for (uint32_t i = 0; i < batch; ++i) {
         if (backfill) visit_kernel<1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
         else if (D.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
+        else if (D.kchain == 2) visit_chain_kernel<2><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(D);
+        else if (D.kchain == 4) visit_chain_kernel<4><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(D);
         else visit_kernel<0><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
         if (e->world > 1 && !D.p2p) {
           int rc = g_nccl.AllGather(D.sendbuf, D.recvbuf, cnt, kNcclUint64, e->comm, e->stream);
@@ -442,6 +465,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
     stats->scans = c.scans; stats->rescans = c.rescans;
     stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total; stats->cyc_steps = c.cyc_steps; stats->cyc_ctl = c.cyc_ctl;
     stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
+    stats->chain_hits = c.chain_hits;
     stats->exchange_mode = e->world == 1 ? 0u : (D.p2p ? 2u : 1u);
     stats->h2d_bytes = backfill ? 0 : (uint64_t)e->mut_bytes + e->imm_bytes;
     stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / batch) * sizeof(Ctl);

@@ -143,6 +143,12 @@ struct VisitSmem {
   uint32_t excl[32];                         // nodes the scanners skip (overlap mode)
   uint32_t sink;                             // keeps the shadow prefetch loads alive
   Ctl ctl2;                                  // replay_kernel's shadow warp reads its own copy
+  // chained visits (visit_chain_kernel): nodes modified by the replays of this launch (no duplicates), the certification
+  // floor of the list being replayed, and whether the last replay stopped for a rescan
+  uint64_t chain_floor;
+  uint32_t mod[KTOP * KB_CHAIN_MAX];
+  uint32_t nmod;
+  uint32_t last_rescan;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -161,7 +167,9 @@ __device__ __forceinline__ void store_ctl(Ctl* g, const Ctl& c, int lane) {
 
 // `patch_class` != ~0u (overlap mode): after the replay, if the control plane's next visit has that class, every lane
 // evaluates ITS candidate's current state for it and the sorted keys go to c.patch (see Ctl).  The caller stores c.
-template <int BF>
+// CH = 1 (visit_chain_kernel): the floor comes from sm.chain_floor (a patched list's floor is not its 32nd key), the nodes
+// this replay modified are appended to sm.mod and a rescan stop is reported in sm.last_rescan.
+template <int BF, int CH = 0>
 __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& sm, const int lane, const uint32_t cls_id,
                                                 const uint64_t* rec_base, const uint32_t rec_stride, const uint32_t patch_class,
                                                 const long long t_start, const long long t_scan) {
@@ -175,8 +183,9 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   if (lane == 0 && patch_class == 0xFFFFFFFFu) { c.scans += 1; c.pairs_scanned += (unsigned long long)S.N; }
   uint64_t cur_key = sm.keys[lane];
-  const uint64_t floor_key = sm.keys[KTOP - 1];
+  const uint64_t floor_key = CH ? sm.chain_floor : sm.keys[KTOP - 1];
   const bool have = cur_key != 0;
+  bool rescanned = false;
   const uint32_t my_node = key_node(cur_key);
   uint64_t* gt_mine = S.tiles + (size_t)(my_node / TILE_NODES) * (ncols * TILE_NODES) + (my_node % TILE_NODES);
   uint32_t which = 0;                 // slot holding my CURRENT state
@@ -300,7 +309,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
     }
     __syncwarp();
-    if (reason == STOP_RESCAN) break;
+    if (reason == STOP_RESCAN) { rescanned = true; break; }
   }
 
   // write the modified candidates back to the global table
@@ -314,6 +323,16 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     }
   }
   __syncwarp();
+  if (CH) {
+    bool add = modified;
+    const uint32_t nm = sm.nmod;
+    if (add) for (uint32_t i = 0; i < nm; ++i) if (sm.mod[i] == my_node) { add = false; break; }
+    const unsigned mm = __ballot_sync(FULL, add);
+    if (add) sm.mod[nm + __popc(mm & ((1u << lane) - 1u))] = my_node;
+    if (lane == 0) { sm.nmod = nm + __popc(mm); sm.last_rescan = rescanned ? 1u : 0u; }
+    __threadfence();                          // the write-backs are visible before a later patch re-reads the records
+    __syncwarp();
+  }
   if (patch_class != 0xFFFFFFFFu) {
     // overlap mode: fresh keys of MY candidate (the scanners skipped it) for the class they scanned meanwhile
     const bool hit = !c.done && c.cur_class == patch_class;
@@ -624,6 +643,252 @@ visit_kernel(const __grid_constant__ DevSession S) {
     store_ctl(gctl, sm.ctl, lane);
     if (lane == 0) gctl->arrive = 0;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// visit_chain_kernel<K> (single GPU): ONE pass over the node table serves up to K consecutive visits.
+//   scan     every CTA evaluates cur_class AND the K-1 predicted classes of the following visits (Ctl.chain, from the
+//            static job order) for each of its nodes: K exact top-32 lists per CTA, folded in log2(16) rounds that
+//            spread the K x 16 warp lists over all warps;
+//   merge    the last CTA folds the per-CTA lists of all classes at once (16/K warps per class);
+//   replay   warp 0 replays the first visit as visit_kernel does.  While the control plane's next visit has the class
+//            of an unused look-ahead list, that list is PATCHED — entries of nodes modified since the scan are dropped,
+//            those nodes are re-evaluated from their current records, the 32 best stay and the certification floor rises
+//            to the best key that did not fit — and replayed in the same launch.
+// Exactness: an unmodified node outside a look-ahead list still has a key below that list's floor; every modified node
+// is re-evaluated; keys are unique (node index), so "best >= floor" certifies a pick exactly as in visit_kernel.
+// A wrong prediction only wastes the look-ahead evaluation.  tests/emu mirrors this protocol (emu_launch_chain).
+// ---------------------------------------------------------------------------------------------
+template <int K>
+struct ChainSmem {
+  ClassRec cls[K];
+  uint32_t cls_id[K];
+  uint64_t keys[K][KTOP];                    // merged list per class (launch-start state)
+  uint64_t fold[2][K][SCAN_WARPS][KTOP];     // ping-pong buffers of the fold rounds
+};
+template <int K>
+__host__ __device__ constexpr size_t chain_smem_header() {
+  return ((sizeof(VisitSmem) + 127) / 128) * 128 + ((sizeof(ChainSmem<K>) + 127) / 128) * 128;
+}
+
+// one fold round over lists of `nK` classes: n lists per class in buf[cur] -> n/2 in buf[cur^1]; jobs spread over the warps
+template <int K>
+__device__ __forceinline__ void chain_fold_round(ChainSmem<K>& cs, const int cur, const int n, const int nK, const int warp, const int lane) {
+  const int half = n >> 1, jobs = nK * half;
+  for (int t = warp; t < jobs; t += SCAN_WARPS) {
+    const int k = t / half, i = t - k * half;
+    cs.fold[cur ^ 1][k][i][lane] = warp_merge_top32(cs.fold[cur][k][2 * i][lane], cs.fold[cur][k][2 * i + 1][lane], lane);
+  }
+  __syncthreads();
+}
+
+template <int K>
+__global__ void __launch_bounds__(SCAN_THREADS)
+visit_chain_kernel(const __grid_constant__ DevSession S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  VisitSmem& sm = *reinterpret_cast<VisitSmem*>(smem_raw);
+  ChainSmem<K>& cs = *reinterpret_cast<ChainSmem<K>*>(smem_raw + ((sizeof(VisitSmem) + 127) / 128) * 128);
+  uint64_t* tilebuf = reinterpret_cast<uint64_t*>(smem_raw + chain_smem_header<K>());
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Ctl* gctl = S.ctl;
+  if (*((volatile uint32_t*)&gctl->done)) return;
+  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; sm.nmod = 0; sm.last_rescan = 0; }
+  if (tid < K) cs.cls_id[tid] = tid == 0 ? *((volatile uint32_t*)&gctl->cur_class) : *((volatile uint32_t*)&gctl->chain[tid - 1]);
+  __syncthreads();
+  int nK = 1;
+  while (nK < K && cs.cls_id[nK] != 0xFFFFFFFFu) ++nK;
+  const long long t_start = clock64();
+
+  // ---------------- scan: as scan_phase, K classes per node ----------------
+  const uint32_t tile_u64 = S.ncols * TILE_NODES;
+  const uint32_t tile_bytes = tile_u64 * 8u;
+  const uint32_t tpi = S.tpi;
+  const uint32_t n_groups = (S.tile_hi - S.tile_lo + tpi - 1) / tpi;
+  const uint32_t firstg = blockIdx.x, stride = gridDim.x;
+  const uint32_t n_local = firstg < n_groups ? (n_groups - firstg + stride - 1) / stride : 0;
+  auto issue_group = [&](uint32_t grp, uint32_t buf) {
+    const uint32_t t0 = S.tile_lo + grp * tpi;
+    const uint32_t cnt = min(tpi, S.tile_hi - t0);
+    mbar_expect_tx(&sm.mbar[buf], cnt * tile_bytes);
+    for (uint32_t k = 0; k < cnt; ++k)
+      tma_load_1d(tilebuf + ((size_t)buf * tpi + k) * tile_u64, S.tiles + (size_t)(t0 + k) * tile_u64, tile_bytes, &sm.mbar[buf]);
+  };
+  if (tid == 0 && n_local > 0) issue_group(firstg, 0);
+  for (int k = 0; k < nK; ++k) {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cs.cls_id[k]]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&cs.cls[k]);
+    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+  }
+  __syncthreads();
+  const uint32_t sub = (uint32_t)warp >> 2, part = (uint32_t)warp & 3u;
+  uint64_t mylist[K];
+#pragma unroll
+  for (int k = 0; k < K; ++k) mylist[k] = 0;
+  for (uint32_t it = 0; it < n_local; ++it) {
+    const uint32_t b = it & 1u;
+    if (it + 1 < n_local) {
+      __syncthreads();
+      if (tid == 0) issue_group(firstg + (it + 1) * stride, b ^ 1u);
+    }
+    mbar_wait(&sm.mbar[b], (it >> 1) & 1u);
+    const uint32_t t = S.tile_lo + (firstg + it * stride) * tpi + sub;
+    const uint32_t node = t * TILE_NODES + part * 32u + lane;
+    const bool valid = sub < tpi && t < S.tile_hi && node < S.N;
+    ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      if (k < nK) {
+        uint64_t key = valid ? eval_pair(S.cf, cs.cls[k], acc, node, nullptr) : 0ull;
+        const uint64_t thr = __shfl_sync(FULL, mylist[k], 31);
+        if (__any_sync(FULL, key > thr)) {
+          key = warp_sort_desc(key, lane);
+          mylist[k] = warp_merge_top32(mylist[k], key, lane);
+        }
+      }
+    }
+  }
+  // CTA fold: K x 16 warp lists -> K lists, 4 rounds
+#pragma unroll
+  for (int k = 0; k < K; ++k) if (k < nK) cs.fold[0][k][warp][lane] = mylist[k];
+  __syncthreads();
+  int cur = 0;
+  for (int n = SCAN_WARPS; n > 1; n >>= 1) { chain_fold_round<K>(cs, cur, n, nK, warp, lane); cur ^= 1; }
+  const uint32_t G = gridDim.x;
+  if (warp < nK) {
+    const uint64_t v = cs.fold[cur][warp][0][lane];
+    S.cand[((size_t)warp * G + blockIdx.x) * KTOP + lane] = v;
+    cs.keys[warp][lane] = v;
+    __threadfence();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const uint32_t ticket = atomicAdd(&gctl->arrive, 1u);
+    sm.is_last = (ticket == G - 1) ? 1u : 0u;
+  }
+  __syncthreads();
+  if (!sm.is_last) return;
+  __threadfence();
+  const long long t_scan = clock64();
+  constexpr int CTLW = (int)((sizeof(Ctl) / 4 + 31) / 32);
+  uint32_t cw[CTLW];
+  if (warp == SCAN_WARPS - 1) {
+#pragma unroll
+    for (int i = 0; i < CTLW; ++i) {
+      const uint32_t idx = (uint32_t)i * 32u + lane;
+      cw[i] = idx < sizeof(Ctl) / 4 ? __ldcg(reinterpret_cast<const uint32_t*>(gctl) + idx) : 0u;
+    }
+  }
+  // ---------------- merge the per-CTA lists: 16/K warps per class, then log2(16/K) rounds ----------------
+  if (G > 1) {
+    constexpr int P = SCAN_WARPS / K;
+    const int k = warp % K, p = warp / K;
+    uint64_t acc = 0;
+    if (k < nK) {
+      uint32_t g = (uint32_t)p;
+      uint64_t nxt = g < G ? __ldcg(&S.cand[((size_t)k * G + g) * KTOP + lane]) : 0ull;
+      while (g < G) {
+        const uint64_t c0 = nxt;
+        const uint32_t g2 = g + P;
+        nxt = g2 < G ? __ldcg(&S.cand[((size_t)k * G + g2) * KTOP + lane]) : 0ull;
+        const uint64_t thr = __shfl_sync(FULL, acc, 31);
+        const uint64_t head = __shfl_sync(FULL, c0, 0);
+        if (head > thr) acc = warp_merge_top32(acc, c0, lane);
+        g = g2;
+      }
+      cs.fold[0][k][p][lane] = acc;
+    }
+    __syncthreads();
+    cur = 0;
+    for (int n = P; n > 1; n >>= 1) { chain_fold_round<K>(cs, cur, n, nK, warp, lane); cur ^= 1; }
+    if (warp < nK) cs.keys[warp][lane] = cs.fold[cur][warp][0][lane];
+  }
+  if (warp == 0) { __syncwarp(); sm.keys[lane] = cs.keys[0][lane]; if (lane == 0) sm.chain_floor = cs.keys[0][KTOP - 1]; }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&cs.cls[0]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+    for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+  }
+  if (warp == SCAN_WARPS - 1) {
+#pragma unroll
+    for (int i = 0; i < CTLW; ++i) {
+      const uint32_t idx = (uint32_t)i * 32u + lane;
+      if (idx < sizeof(Ctl) / 4) reinterpret_cast<uint32_t*>(&sm.ctl)[idx] = cw[i];
+    }
+  }
+  __syncthreads();
+  if (warp == 1) shadow_prefetch<0>(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
+  if (warp != 0) return;
+
+  // ---------------- replay chain: warp 0 ----------------
+  const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  uint32_t used = 1u, kcur = 0;
+  long long ts = t_start, tsc = t_scan;
+  for (;;) {
+    {
+      const uint32_t n = key_node(sm.keys[lane]);
+      const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)ncols * TILE_NODES) + (n % TILE_NODES);
+      replay_epilogue<0, 1>(S, sm, lane, cs.cls_id[kcur], rec, TILE_NODES, 0xFFFFFFFFu, ts, tsc);
+    }
+    __syncwarp();
+    if (sm.ctl.done || sm.last_rescan) break;
+    uint32_t nk = 0xFFFFFFFFu;
+#pragma unroll
+    for (int z = K - 1; z >= 0; --z) if (z < nK && !((used >> z) & 1u) && cs.cls_id[z] == sm.ctl.cur_class) nk = (uint32_t)z;
+    if (nk == 0xFFFFFFFFu) break;
+    const uint32_t nm = sm.nmod;
+    if (nm + KTOP > KTOP * KB_CHAIN_MAX) break;
+    ts = tsc = clock64();
+    // patch list nk: drop the entries of modified nodes, re-evaluate those nodes from their current records
+    uint64_t key = cs.keys[nk][lane];
+    uint64_t fl = cs.keys[nk][KTOP - 1];
+    if (key) {
+      const uint32_t nd = key_node(key);
+      for (uint32_t i = 0; i < nm; ++i) if (sm.mod[i] == nd) { key = 0; break; }
+    }
+    key = warp_sort_desc(key, lane);
+    for (uint32_t base = 0; base < nm; base += 32) {
+      uint64_t pk = 0;
+      const bool mine = base + lane < nm;
+      if (mine) {
+        const uint32_t nd = sm.mod[base + lane];
+        const uint64_t* g = S.tiles + (size_t)(nd / TILE_NODES) * ((size_t)ncols * TILE_NODES) + (nd % TILE_NODES);
+        for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(g + (size_t)cc * TILE_NODES);
+        ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
+        pk = eval_pair(S.cf, cs.cls[nk], acc, nd, nullptr);
+      }
+      const unsigned cnt = __popc(__ballot_sync(FULL, mine));
+      if (lane == 0) sm.ctl.pairs_replayed += (unsigned long long)cnt;
+      pk = warp_sort_desc(pk, lane);
+      const uint64_t br = __shfl_sync(FULL, pk, 31 - lane);
+      const uint64_t lo = key < br ? key : br;
+      uint64_t v = key > br ? key : br;
+      const uint64_t dropped = warp_max_u64(lo);           // best key that no longer fits into the 32 lanes
+      fl = dropped > fl ? dropped : fl;
+#pragma unroll
+      for (int j = 16; j > 0; j >>= 1) {
+        const uint64_t o = __shfl_xor_sync(FULL, v, j);
+        const bool take_max = (lane & j) == 0;
+        v = take_max ? (o > v ? o : v) : (o < v ? o : v);
+      }
+      key = v;
+      __syncwarp();
+    }
+    sm.keys[lane] = key;
+    if (lane == 0) { sm.chain_floor = fl; sm.ctl.chain_hits += 1; }
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&cs.cls[nk]);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+      for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
+    }
+    used |= 1u << nk;
+    kcur = nk;
+    __syncwarp();
+  }
+  if (lane == 0) publish_chain(S, sm.ctl);
+  __syncwarp();
+  store_ctl(gctl, sm.ctl, lane);
+  if (lane == 0) gctl->arrive = 0;
 }
 
 // ---------------------------------------------------------------------------------------------

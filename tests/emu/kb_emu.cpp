@@ -81,7 +81,7 @@ struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = f
               uint64_t cur_key = 0, next_key = 0; uint32_t node = 0, cnt = 0; Slot st[2]; int which = 0; };
 
 // replay_epilogue's core: look-ahead refresh + certified steps + control plane, for candidates already loaded
-void replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key) {
+bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   auto refresh = [&]() {
@@ -136,8 +136,9 @@ void replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
     }
     if (reason == STOP_RESCAN) c.rescans += 1;
     after_run(S, c, reason, placed);
-    if (reason == STOP_RESCAN) break;
+    if (reason == STOP_RESCAN) return true;
   }
+  return false;
 }
 
 void write_back(const DevSession& S, const ClassRec& cls, std::vector<Cand>& cand) {
@@ -277,6 +278,87 @@ void emu_launch_overlap(Emu& E) {
   }
 }
 
+// One launch of visit_chain_kernel<K> (single GPU): ONE pass over the table evaluates cur_class and the predicted classes
+// of the following visits (Ctl.chain); the first visit is replayed as usual, every following visit whose class has a
+// look-ahead list is replayed in the same launch after the list was PATCHED: entries of nodes modified since the scan are
+// dropped, those nodes are re-evaluated against their current records, and the certification floor rises to the largest
+// key that no longer fits into the 32 lanes.
+void emu_launch_chain(Emu& E) {
+  const DevSession& S = *E.cur;
+  Ctl& c = *S.ctl;
+  E.launches += 1;
+  if (c.done) return;
+  const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  uint32_t cls[KB_CHAIN_MAX]; uint32_t nK = 1;
+  cls[0] = c.cur_class;
+  for (uint32_t k = 0; k + 1 < S.kchain && k + 1 < KB_CHAIN_MAX; ++k) { if (c.chain[k] == 0xFFFFFFFFu) break; cls[nK++] = c.chain[k]; }
+  // ---- scan: every class against the table as it is at launch start ----
+  std::vector<std::vector<uint64_t>> lists(nK);
+  std::vector<uint64_t> floor(nK, 0);
+  for (uint32_t k = 0; k < nK; ++k) {
+    std::vector<uint64_t> keys;
+    for (uint32_t n = 0; n < S.N; ++n) {
+      TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+      uint64_t key = eval_pair(S.cf, S.classes[cls[k]], acc, n, nullptr);
+      if (key) keys.push_back(key);
+    }
+    std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+    keys.resize(KTOP, 0ull);
+    lists[k] = keys; floor[k] = keys[KTOP - 1];
+  }
+  std::vector<uint32_t> mod;          // nodes modified in this launch, no duplicates
+  uint32_t used = 0;
+  uint32_t k = 0;
+  for (;;) {
+    used |= 1u << k;
+    const ClassRec& cr = S.classes[cls[k]];
+    c.scans += 1; c.pairs_scanned += S.N;
+    std::vector<Cand> cand(KTOP);
+    for (int l = 0; l < KTOP; ++l) {
+      Cand& cd = cand[l];
+      cd.cur_key = lists[k][l]; cd.have = cd.cur_key != 0;
+      if (!cd.have) continue;
+      cd.node = key_node(cd.cur_key);
+      const uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
+      for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = gt[(size_t)cc * TILE_NODES];
+      SlotAcc acc{&cd.st[0], R, W};
+      cd.cur_fi = res_less_equal(R, [&](uint32_t q) { return cr.initreq[q]; }, [&](uint32_t q) { return acc.idle(q); });
+    }
+    const bool rescan = replay_core(S, c, cls[k], cand, floor[k]);
+    write_back(S, cr, cand);
+    for (auto& cd : cand) if (cd.modified && std::find(mod.begin(), mod.end(), cd.node) == mod.end()) mod.push_back(cd.node);
+    if (c.done || rescan) break;
+    // next visit: is there an unused look-ahead list of its class?
+    uint32_t nk = 0xFFFFFFFFu;
+    for (uint32_t z = 0; z < nK; ++z) if (!((used >> z) & 1u) && cls[z] == c.cur_class) { nk = z; break; }
+    if (nk == 0xFFFFFFFFu) break;
+    if (mod.size() + KTOP > (size_t)KTOP * KB_CHAIN_MAX) break;            // capacity of the device's modified-node list
+    // ---- patch list nk ----
+    std::vector<uint64_t> keep, fresh;
+    for (uint64_t key : lists[nk]) if (key && std::find(mod.begin(), mod.end(), key_node(key)) == mod.end()) keep.push_back(key);
+    uint64_t fl = floor[nk];
+    for (size_t base = 0; base < mod.size(); base += 32) {                  // the device merges 32 fresh keys at a time
+      std::vector<uint64_t> all = keep;
+      for (size_t i = base; i < mod.size() && i < base + 32; ++i) {
+        const uint32_t n = mod[i];
+        TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+        const uint64_t key = eval_pair(S.cf, S.classes[cls[nk]], acc, n, nullptr);
+        c.pairs_replayed += 1;
+        if (key) all.push_back(key);
+      }
+      std::sort(all.begin(), all.end(), [](uint64_t a, uint64_t b) { return a > b; });
+      if (all.size() > (size_t)KTOP) { fl = std::max(fl, all[KTOP]); all.resize(KTOP); }
+      keep = all;
+    }
+    keep.resize(KTOP, 0ull);
+    lists[nk] = keep; floor[nk] = fl;
+    c.chain_hits += 1;
+    k = nk;
+  }
+  publish_chain(S, c);
+}
+
 // gang_commit_kernel, serially: a job's processed slots of the allocate view, then of the backfill view
 void emu_gang_commit(const DevSession& S, const DevSession& Sbf, const int32_t* ready0) {
   for (uint32_t j = 0; j < S.J; ++j) {
@@ -325,16 +407,18 @@ extern "C" {
 
 const char* kbemu_last_error(void) { return g_err.c_str(); }
 
-void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world) {
+// mode (single rank): 0 = scan/replay overlap protocol, 1 = plain one-class launches, 2 / 4 = chained visits (visit_chain_kernel<K>)
+void* kbemu_create2(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world, uint32_t mode) {
   Emu* E = new Emu();
   BuildErr be;
-  // the emulation always exercises the overlap protocol on one rank (the device enables it by size)
-  if (build_session(snap, conf, 148, E->B, &be, rank, world, 1)) { g_err = be.msg; delete E; return nullptr; }
+  if (build_session(snap, conf, 148, E->B, &be, rank, world, mode == 0 ? 1 : 0, mode >= 2 ? mode : 1)) { g_err = be.msg; delete E; return nullptr; }
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
   E->cur = &E->S;
   return E;
 }
+// the default emulation exercises the overlap protocol on one rank (the device enables it by size)
+void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world) { return kbemu_create2(snap, conf, rank, world, 0); }
 void kbemu_destroy(void* h) { delete (Emu*)h; }
 int kbemu_done(void* h) { return ((Emu*)h)->cur->ctl->done ? 1 : 0; }
 void kbemu_begin_backfill(void* h, int allocate_ran) { emu_begin_backfill(*(Emu*)h, allocate_ran != 0); }
@@ -380,6 +464,7 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
     stats->tasks_processed = c.tasks_processed; stats->tasks_allocated = c.tasks_allocated; stats->tasks_pipelined = c.tasks_pipelined;
     stats->visits = c.visits; stats->kernel_launches = E.launches; stats->n_classes = B.C;
     stats->scans = c.scans; stats->rescans = c.rescans; stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
+    stats->chain_hits = c.chain_hits;
     uint32_t jr = 0;
     for (uint32_t j = 0; j < J; ++j) if (S.job_placed[j] && ssn_job_ready(S, j)) ++jr;
     stats->jobs_ready = jr;
@@ -389,11 +474,11 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
 
 // single-rank convenience: the whole cycle
 int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t actions /* bit0 allocate, bit1 backfill */,
-                   kb_decision* out, kb_stats* stats,
+                   uint32_t mode /* kbemu_create2 */, kb_decision* out, kb_stats* stats,
                    double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
                    int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
                    double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
-  Emu* E = (Emu*)kbemu_create(snap, conf, 0, 1);
+  Emu* E = (Emu*)kbemu_create2(snap, conf, 0, 1, mode);
   if (!E) return KB_E_BADARG;
   std::vector<uint64_t> buf(kbemu_buf_u64(E));
   const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To + E->B.Tb) + 1024;
@@ -402,6 +487,7 @@ int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t
     if (pass == 1) emu_begin_backfill(*E, ((actions ? actions : 1u) & 1u) != 0);
     while (!E->cur->ctl->done) {
       if (E->cur->overlap) emu_launch_overlap(*E);
+      else if (E->cur->kchain > 1) emu_launch_chain(*E);
       else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
       if (E->launches > guard) { g_err = "emulated cycle did not terminate"; delete E; return KB_E_STATE; }
     }

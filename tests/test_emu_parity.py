@@ -29,9 +29,9 @@ CONFS = {
 }
 
 
-def check(snap, conf, what, actions=1):
+def check(snap, conf, what, actions=1, mode=0):
     o = kbo.allocate(snap, conf, actions=actions)
-    e = util.emu_allocate(snap, conf, actions=actions)
+    e = util.emu_allocate(snap, conf, actions=actions, mode=mode)
     util.assert_same_decisions(o.decisions, e.decisions, what)
     ns, os_ = util.emu_states(e)
     util.assert_same_state(o, ns, os_, what)
@@ -134,6 +134,36 @@ def test_host_ports_taints_selectors_affinity():
     assert got["ns/port-1"] != got["ns/port-2"] and got["ns/port-1"] is not None   # wildcard IP conflicts with 10.0.0.1
     assert got["ns/aff"] == "n3"
     assert got["ns/nowhere"] is None
+
+
+# ---------------- chained visits (visit_chain_kernel<K>): K classes per scan, look-ahead lists patched before their replay ----------------
+@pytest.mark.parametrize("seed", range(12))
+def test_chained_visits_random_sessions(seed):
+    rng = np.random.default_rng(2000 + seed)
+    tasks = int(rng.integers(5, 400))
+    s = synth.random_session(seed + 700, tasks=tasks, jobs=int(rng.integers(1, min(tasks, 60) + 1)), nodes=int(rng.integers(1, 300)),
+                             queues=int(rng.integers(1, 5)), min_member_frac=float(rng.choice([0.0, 0.5, 1.0])),
+                             hetero=float(rng.choice([0, 0.3, 1.0])), prio_levels=int(rng.integers(1, 4)),
+                             oversub=float(rng.choice([0.7, 1.3, 3.0])))
+    for cname, conf in CONFS.items():
+        for mode in (1, 2, 4):            # 1 = plain one-class launches (no overlap protocol)
+            check(s, conf, f"chain seed{seed}/{cname}/K{mode}", mode=mode)
+
+
+def test_chained_visits_save_launches_and_patch_small_clusters():
+    # few nodes: every visit modifies nodes that sit in the look-ahead lists, so the patch path (drop + re-evaluate + floor) is hot
+    s = synth.random_session(31, tasks=600, jobs=120, nodes=24, queues=1, min_member_frac=0.0, hetero=1.0, oversub=0.9)
+    base = None
+    for mode in (1, 2, 4):
+        o, e = check(s, CONFS["default"], f"chain small/K{mode}", mode=mode)
+        if mode == 1:
+            base = e.result.kernel_launches
+        else:
+            assert e.result.chain_hits > 0 and e.result.kernel_launches < base
+    s, conf = synth.make("c2")
+    o, e1 = check(s, conf, "chain c2/K1", mode=1)
+    o, e4 = check(s, conf, "chain c2/K4", mode=4)
+    assert e4.result.kernel_launches * 3 < e1.result.kernel_launches       # single queue, static job order: predictions hit
 
 
 # ---------------- backfill (actions/backfill/backfill.go:40-71), the action after allocate in the default list ----------------

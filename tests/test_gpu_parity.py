@@ -98,6 +98,32 @@ def test_overlap_mode_is_bit_exact():
         e.close()
 
 
+@pytest.mark.parametrize("flag", [abi.KB_ENGINE_CHAIN2, abi.KB_ENGINE_CHAIN4])
+def test_chained_visits_are_bit_exact(flag):
+    """visit_chain_kernel<2|4>: K classes per scan; following visits replayed from patched look-ahead lists."""
+    e = engine.Engine(device=0, flags=flag)
+    try:
+        s, conf = synth.make("c2")
+        o, r = run_and_check(e, s, conf, "c2/chain")
+        assert r.stats.chain_hits > 0
+        for seed in range(6):
+            s = synth.random_session(100 + seed, tasks=200 + 40 * seed, jobs=12 + seed, nodes=150 + 60 * seed, queues=1 + seed % 3,
+                                     min_member_frac=[0.0, 0.5, 1.0][seed % 3], hetero=[0, 0.3, 1.0][seed % 3], prio_levels=2)
+            for cname in ("default", "c2", "nogang", "weights"):
+                run_and_check(e, s, CONFS[cname], f"chain seed{seed}/{cname}")
+        s = synth.random_session(31, tasks=600, jobs=120, nodes=24, queues=1, min_member_frac=0.0, hetero=1.0, oversub=0.9)
+        run_and_check(e, s, CONFS["default"], "chain small cluster (patch path)")
+        s = synth.generate(synth.SynthSpec("wide", tasks=600, jobs=60, nodes=148 * 128 * 2 + 77, seed=99))
+        run_and_check(e, s, PluginConf.default(), "wide/chain")
+        for (R, W) in [(8, 4), (5, 2)]:
+            s = synth.random_session(60, tasks=150, jobs=15, nodes=300, queues=2, hetero=0.3, R=R, W=W)
+            run_and_check(e, s, CONFS["default"], f"chain R{R}W{W}")
+        s, conf = synth.make("c3")
+        run_and_check(e, s, conf, "c3/chain")
+    finally:
+        e.close()
+
+
 @pytest.mark.parametrize("R,W", [(4, 3), (6, 4), (8, 4), (5, 2)])
 def test_wide_records_more_dims_and_mask_words(eng, R, W):
     """Generic tile geometry: ncols = 2R + 6 + 3W up to 34 columns -> wider TMA tiles, fewer tiles per scan iteration."""

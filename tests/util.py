@@ -32,9 +32,10 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def emu_allocate(snap: Snapshot, conf: PluginConf, actions: int = 1) -> kbo.OracleOut:
+def emu_allocate(snap: Snapshot, conf: PluginConf, actions: int = 1, mode: int = 0) -> kbo.OracleOut:
     """Run the CPU emulation of the device algorithm; same result container as the oracle.
-    actions: bit 0 = allocate (kb_allocate), bit 1 = backfill afterwards (kb_backfill)."""
+    actions: bit 0 = allocate (kb_allocate), bit 1 = backfill afterwards (kb_backfill).
+    mode: 0 = scan/replay overlap protocol, 1 = plain one-class launches, 2 / 4 = chained visits (visit_chain_kernel<K>)."""
     L = emu_lib()
     cs, k1 = snap.to_c()
     cc, k2 = conf.to_c()
@@ -48,7 +49,7 @@ def emu_allocate(snap: Snapshot, conf: PluginConf, actions: int = 1) -> kbo.Orac
         node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
         job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
         queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
-    rc = L.kbemu_allocate(C.byref(cs), C.byref(cc), C.c_uint32(actions), dec.ctypes.data_as(C.c_void_p), C.byref(st),
+    rc = L.kbemu_allocate(C.byref(cs), C.byref(cc), C.c_uint32(actions), C.c_uint32(mode), dec.ctypes.data_as(C.c_void_p), C.byref(st),
                           _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
                           _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
                           _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
