@@ -371,11 +371,13 @@ KB_HD void publish_chain(const DevSession& S, Ctl& c) {
 }
 
 // Called once a run stopped.  `placed` = tasks of the run that went through Allocate/Pipeline.
+// shares_done: the caller already refreshed the job's drf share and the queue's proportion share (the replay warp does
+// the divisions of all dimensions in parallel lanes)
 template <int BF = -1>
-KB_HD void after_run(const DevSession& S, Ctl& c, uint32_t reason, uint32_t placed) {
+KB_HD void after_run(const DevSession& S, Ctl& c, uint32_t reason, uint32_t placed, const bool shares_done = false) {
   const bool bf = BF < 0 ? S.backfill != 0 : BF != 0;
   const uint32_t j = (uint32_t)c.cur_job;
-  if (placed) {
+  if (placed && !shares_done) {
     if (S.drf_present) update_job_share(S, j);
     if (S.proportion_present) update_queue_share(S, S.job_queue[j]);
   }

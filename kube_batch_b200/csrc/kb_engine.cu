@@ -99,6 +99,7 @@ struct kb_engine {
   float last_kernel_ms = 0;
   int sm_count = 148;
   int overlap_mode = -1;
+  bool pdl = true;                          // programmatic dependent launch of the visit chain (KB_PDL=0 disables)
   uint32_t kchain_req = KB_DEFAULT_CHAIN;   // classes per launch requested (flags / KB_CHAIN), 1 = visit_kernel
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
@@ -118,6 +119,21 @@ int fail(kb_engine* e, int code, const char* fmt, ...) {
 #define CUDA_TRY(e, call) do { cudaError_t _c = (call); if (_c != cudaSuccess) return fail((e), KB_E_CUDA, "%s failed: %s", #call, cudaGetErrorString(_c)); } while (0)
 
 thread_local std::string g_create_err;
+
+// Launch with the programmatic-stream-serialization attribute (PDL): the grid may be scheduled while its predecessor in the
+// stream / captured graph is still running and blocks in griddepcontrol.wait until that one has completed and flushed.
+// visit_kernel / visit_chain_kernel release their successor when only the replaying CTA is left, which hides the launch
+// latency of every link of the chain behind the replay.
+template <typename Kernel>
+cudaError_t launch_visit(Kernel k, uint32_t grid, size_t smem, cudaStream_t st, const DevSession& D, bool pdl) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(SCAN_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, D);
+}
 
 void free_graph(kb_engine* e) {
   if (e->graph_exec) cudaGraphExecDestroy(e->graph_exec);
@@ -226,6 +242,7 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   e->rank = world > 1 ? opts->rank : 0; e->world = world;
   e->overlap_mode = (opts->flags & KB_ENGINE_NO_OVERLAP) ? 0 : (opts->flags & KB_ENGINE_FORCE_OVERLAP) ? 1 : -1;
   e->kchain_req = (opts->flags & KB_ENGINE_CHAIN_OFF) ? 1u : (opts->flags & KB_ENGINE_CHAIN4) ? 4u : (opts->flags & KB_ENGINE_CHAIN2) ? 2u : KB_DEFAULT_CHAIN;
+  if (const char* pd = getenv("KB_PDL")) e->pdl = atoi(pd) != 0;
   if (const char* kc = getenv("KB_CHAIN")) { const int v = atoi(kc); if (v == 1 || v == 2 || v == 4) e->kchain_req = (uint32_t)v; }
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
@@ -353,10 +370,11 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     bool ok = ce == cudaSuccess;
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
+      const bool pdl = e->pdl && e->world == 1;
       if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
-      else if (e->dev.kchain == 2) visit_chain_kernel<2><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(e->dev);
-      else if (e->dev.kchain == 4) visit_chain_kernel<4><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(e->dev);
-      else visit_kernel<0><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+      else if (e->dev.kchain == 2) ok = launch_visit(visit_chain_kernel<2>, e->scan_grid, e->chain_smem, e->stream, e->dev, pdl) == cudaSuccess;
+      else if (e->dev.kchain == 4) ok = launch_visit(visit_chain_kernel<4>, e->scan_grid, e->chain_smem, e->stream, e->dev, pdl) == cudaSuccess;
+      else ok = launch_visit(visit_kernel<0>, e->scan_grid, e->visit_smem, e->stream, e->dev, pdl) == cudaSuccess;
       if (e->world > 1 && !e->dev.p2p) {
         ok = g_nccl.AllGather(e->dev.sendbuf, e->dev.recvbuf, cnt, kNcclUint64, e->comm, e->stream) == 0;
         replay_kernel<0><<<1, 64, e->replay_smem, e->stream>>>(e->dev);

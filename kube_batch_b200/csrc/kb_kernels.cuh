@@ -49,6 +49,9 @@ __device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// programmatic dependent launch (PTX griddepcontrol): see visit_kernel
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   do {
@@ -192,7 +195,15 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   bool cur_fi = false, next_fi = false, next_valid = false, modified = false;
   uint64_t next_key = 0;
   if (have) {
-    for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(rec_base + (size_t)cc * rec_stride);
+    // the candidate's record: the first 18 columns (the whole record at R=3, W=2) as ONE batch of independent loads
+    // = one L2 round trip; wider records finish in a loop
+    constexpr uint32_t GATHER_UNROLL = 18;
+    uint64_t tmp[GATHER_UNROLL];
+#pragma unroll
+    for (uint32_t cc = 0; cc < GATHER_UNROLL; ++cc) tmp[cc] = cc < ncols ? __ldcg(rec_base + (size_t)cc * rec_stride) : 0ull;
+#pragma unroll
+    for (uint32_t cc = 0; cc < GATHER_UNROLL; ++cc) if (cc < ncols) sm.slot[0][cc][lane] = tmp[cc];
+    for (uint32_t cc = GATHER_UNROLL; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(rec_base + (size_t)cc * rec_stride);
     ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
     cur_fi = res_less_equal(R, [&](uint32_t k) { return sm.cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
   }
@@ -299,11 +310,29 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = jalloc;
       if (S.proportion_present) S.q_allocated[(size_t)lane * S.Q + q] = qalloc;
     }
+    // drf.calculateShare (drf.go:161-171) / proportion.updateShare (proportion.go:241-253): one FP64 division per
+    // dimension, all dimensions at once in lanes 0..R-1, then a max over the lanes (shares are >= 0, so the IEEE bit
+    // patterns order like the values)
+    if (placed) {
+      if (S.drf_present) {
+        double v = 0.0;
+        if ((uint32_t)lane < R && ((S.total_dims_mask >> lane) & 1u)) v = share_of(jalloc, S.total[lane]);
+        const uint64_t m = warp_max_u64(double_as_u64(v));
+        if (lane == 0) S.job_share[j] = u64_as_double(m);
+      }
+      if (S.proportion_present) {
+        double v = 0.0;
+        const uint32_t present = S.q_deserved_present[q] | 3u;
+        if ((uint32_t)lane < R && ((present >> lane) & 1u)) v = share_of(qalloc, S.q_deserved[(size_t)lane * S.Q + q]);
+        const uint64_t m = warp_max_u64(double_as_u64(v));
+        if (lane == 0) S.q_share[q] = u64_as_double(m);
+      }
+    }
     __syncwarp();
     const long long t_run1 = clock64();
     if (lane == 0) {
       if (reason == STOP_RESCAN) c.rescans += 1;
-      after_run<BF>(S, c, reason, placed);
+      after_run<BF>(S, c, reason, placed, true);
       const long long t_run2 = clock64();
       c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
       c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
@@ -370,8 +399,26 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
 // TMA), K1+K2 per node against sm.cls, warp-level top-32, CTA tree fold.  Nodes listed in sm.excl (overlap mode) are
 // skipped.  Every thread of the CTA calls it; the CTA's list is returned in warp 0.
 // ---------------------------------------------------------------------------------------------
+// thread 0 of a scanner CTA: start the bulk copies of its first tile group into staging buffer 0 (returns whether the
+// CTA has any group).  The tiles do not depend on the class, so visit_kernel issues this BEFORE it reads the control
+// block; scan_phase is then told that buffer 0 is already in flight.
+__device__ __forceinline__ bool issue_first_group(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx) {
+  const uint32_t tile_u64 = S.ncols * TILE_NODES;
+  const uint32_t tile_bytes = tile_u64 * 8u;
+  const uint32_t tpi = S.tpi;
+  const uint32_t n_groups = (S.tile_hi - S.tile_lo + tpi - 1) / tpi;
+  if (scanner_idx >= n_groups) return false;
+  const uint32_t t0 = S.tile_lo + scanner_idx * tpi;
+  const uint32_t cnt = min(tpi, S.tile_hi - t0);
+  mbar_expect_tx(&sm.mbar[0], cnt * tile_bytes);
+  for (uint32_t k = 0; k < cnt; ++k)
+    tma_load_1d(tilebuf + (size_t)k * tile_u64, S.tiles + (size_t)(t0 + k) * tile_u64, tile_bytes, &sm.mbar[0]);
+  return true;
+}
+
 __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx,
-                                               const uint32_t n_scanners, const uint32_t cls_id, const int tid, const int lane, const int warp) {
+                                               const uint32_t n_scanners, const uint32_t cls_id, const int tid, const int lane, const int warp,
+                                               const bool first_issued = false) {
   const uint32_t tile_u64 = S.ncols * TILE_NODES;
   const uint32_t tile_bytes = tile_u64 * 8u;
   // ---------------- scan: tile GROUPS blockIdx.x, +gridDim.x, ...: S.tpi tiles per iteration, double-buffered TMA ----------------
@@ -386,7 +433,7 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
     for (uint32_t k = 0; k < cnt; ++k)
       tma_load_1d(tilebuf + ((size_t)buf * tpi + k) * tile_u64, S.tiles + (size_t)(t0 + k) * tile_u64, tile_bytes, &sm.mbar[buf]);
   };
-  if (tid == 0 && n_local > 0) issue_group(firstg, 0);
+  if (tid == 0 && n_local > 0 && !first_issued) issue_group(firstg, 0);
   {
     // class record -> shared memory (broadcast reads afterwards) while the first tiles are in flight
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
@@ -496,15 +543,23 @@ visit_kernel(const __grid_constant__ DevSession S) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ctl* gctl = S.ctl;
-  if (*((volatile uint32_t*)&gctl->done)) return;
-  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
-
   if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; }
   if (tid < 32) sm.excl[tid] = 0;
+  // programmatic dependent launch: this grid may have been scheduled while the previous launch was still replaying;
+  // nothing the previous launch writes is read before this point (no-op when launched without the attribute)
+  pdl_wait();
+  // the node tiles do not depend on the class: start staging them before the control block is even read
+  bool in_flight = false;
+  if (tid == 0) in_flight = issue_first_group(S, sm, tilebuf, blockIdx.x);
+  if (*((volatile uint32_t*)&gctl->done)) {
+    if (in_flight) mbar_wait(&sm.mbar[0], 0);        // a CTA must not exit with bulk copies into its shared memory in flight
+    return;
+  }
+  const uint32_t cls_id = *((volatile uint32_t*)&gctl->cur_class);
   __syncthreads();
   const long long t_start = clock64();
 
-  uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp);
+  uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true);
   if (warp == 0) {
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
     sm.keys[lane] = mylist;
@@ -518,6 +573,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   if (!sm.is_last) return;
   __threadfence();
+  pdl_launch_dependents();                   // every other CTA has exited: the next launch can be scheduled while this CTA replays
   const long long t_scan = clock64();
   // control block: the loads are issued now by the last warp and land in registers while everybody merges
   constexpr int CTLW = (int)((sizeof(Ctl) / 4 + 31) / 32);
@@ -692,8 +748,9 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ctl* gctl = S.ctl;
-  if (*((volatile uint32_t*)&gctl->done)) return;
   if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; sm.nmod = 0; sm.last_rescan = 0; }
+  pdl_wait();
+  if (*((volatile uint32_t*)&gctl->done)) return;
   if (tid < K) cs.cls_id[tid] = tid == 0 ? *((volatile uint32_t*)&gctl->cur_class) : *((volatile uint32_t*)&gctl->chain[tid - 1]);
   __syncthreads();
   int nK = 1;
@@ -769,6 +826,7 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   if (!sm.is_last) return;
   __threadfence();
+  pdl_launch_dependents();
   const long long t_scan = clock64();
   constexpr int CTLW = (int)((sizeof(Ctl) / 4 + 31) / 32);
   uint32_t cw[CTLW];
