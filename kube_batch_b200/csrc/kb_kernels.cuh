@@ -151,7 +151,10 @@ struct VisitSmem {
   uint64_t chain_floor;
   uint32_t mod[KTOP * KB_CHAIN_MAX];
   uint32_t nmod;
+  uint32_t nmod_prev;                        // sm.nmod before the last replay's appends
   uint32_t last_rescan;
+  uint32_t chain_seq;                        // warp 0 -> shadow warp: a new chained visit is ready to be prefetched (~0u = stop)
+  uint32_t lane_node[32], lane_which[32], lane_mod[32];   // the last replay's candidates: node, slot holding the current record, modified?
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -353,13 +356,15 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   }
   __syncwarp();
   if (CH) {
+    // what a following patch needs: this replay's modified candidates keep their CURRENT record in sm.slot[which]
+    sm.lane_node[lane] = my_node; sm.lane_which[lane] = which; sm.lane_mod[lane] = modified ? 1u : 0u;
     bool add = modified;
     const uint32_t nm = sm.nmod;
     if (add) for (uint32_t i = 0; i < nm; ++i) if (sm.mod[i] == my_node) { add = false; break; }
     const unsigned mm = __ballot_sync(FULL, add);
     if (add) sm.mod[nm + __popc(mm & ((1u << lane) - 1u))] = my_node;
-    if (lane == 0) { sm.nmod = nm + __popc(mm); sm.last_rescan = rescanned ? 1u : 0u; }
-    __threadfence();                          // the write-backs are visible before a later patch re-reads the records
+    if (lane == 0) { sm.nmod_prev = nm; sm.nmod = nm + __popc(mm); sm.last_rescan = rescanned ? 1u : 0u; }
+    __threadfence();                          // the write-backs are visible before the next gather / patch re-reads records
     __syncwarp();
   }
   if (patch_class != 0xFFFFFFFFu) {
@@ -748,7 +753,7 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ctl* gctl = S.ctl;
-  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; sm.nmod = 0; sm.last_rescan = 0; }
+  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; sm.nmod = 0; sm.nmod_prev = 0; sm.last_rescan = 0; sm.chain_seq = 0; }
   pdl_wait();
   if (*((volatile uint32_t*)&gctl->done)) return;
   if (tid < K) cs.cls_id[tid] = tid == 0 ? *((volatile uint32_t*)&gctl->cur_class) : *((volatile uint32_t*)&gctl->chain[tid - 1]);
@@ -875,18 +880,32 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
     }
   }
   __syncthreads();
-  if (warp == 1) shadow_prefetch<0>(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
+  if (warp == 1) {
+    // shadow warp: prefetch for the first visit now, then for every chained visit as soon as warp 0 announces it
+    shadow_prefetch<0>(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
+    uint32_t seen = 0;
+    for (;;) {
+      uint32_t v;
+      while ((v = *((volatile uint32_t*)&sm.chain_seq)) == seen) __nanosleep(64);
+      if (v == 0xFFFFFFFFu) break;
+      seen = v;
+      __threadfence_block();
+      shadow_prefetch<0>(S, sm.ctl, lane, &sm.sink, sm.keys[lane]);
+    }
+    return;
+  }
   if (warp != 0) return;
 
   // ---------------- replay chain: warp 0 ----------------
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
-  uint32_t used = 1u, kcur = 0;
+  constexpr int CHM = 1;
+  uint32_t used = 1u, kcur = 0, seq = 0;
   long long ts = t_start, tsc = t_scan;
   for (;;) {
     {
       const uint32_t n = key_node(sm.keys[lane]);
       const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)ncols * TILE_NODES) + (n % TILE_NODES);
-      replay_epilogue<0, 1>(S, sm, lane, cs.cls_id[kcur], rec, TILE_NODES, 0xFFFFFFFFu, ts, tsc);
+      replay_epilogue<0, CHM>(S, sm, lane, cs.cls_id[kcur], rec, TILE_NODES, 0xFFFFFFFFu, ts, tsc);
     }
     __syncwarp();
     if (sm.ctl.done || sm.last_rescan) break;
@@ -894,34 +913,31 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
 #pragma unroll
     for (int z = K - 1; z >= 0; --z) if (z < nK && !((used >> z) & 1u) && cs.cls_id[z] == sm.ctl.cur_class) nk = (uint32_t)z;
     if (nk == 0xFFFFFFFFu) break;
-    const uint32_t nm = sm.nmod;
+    const uint32_t nm = sm.nmod, nprev = sm.nmod_prev;
     if (nm + KTOP > KTOP * KB_CHAIN_MAX) break;
     ts = tsc = clock64();
-    // patch list nk: drop the entries of modified nodes, re-evaluate those nodes from their current records
+    // ---- patch list nk ----
+    // (1) drop the entries of modified nodes; the survivors stay sorted, so compacting them needs no sort
     uint64_t key = cs.keys[nk][lane];
     uint64_t fl = cs.keys[nk][KTOP - 1];
-    if (key) {
+    bool alive = key != 0;
+    if (alive) {
       const uint32_t nd = key_node(key);
-      for (uint32_t i = 0; i < nm; ++i) if (sm.mod[i] == nd) { key = 0; break; }
+      for (uint32_t i = 0; i < nm; ++i) if (sm.mod[i] == nd) { alive = false; break; }
     }
-    key = warp_sort_desc(key, lane);
-    for (uint32_t base = 0; base < nm; base += 32) {
-      uint64_t pk = 0;
-      const bool mine = base + lane < nm;
-      if (mine) {
-        const uint32_t nd = sm.mod[base + lane];
-        const uint64_t* g = S.tiles + (size_t)(nd / TILE_NODES) * ((size_t)ncols * TILE_NODES) + (nd % TILE_NODES);
-        for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(g + (size_t)cc * TILE_NODES);
-        ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
-        pk = eval_pair(S.cf, cs.cls[nk], acc, nd, nullptr);
-      }
-      const unsigned cnt = __popc(__ballot_sync(FULL, mine));
-      if (lane == 0) sm.ctl.pairs_replayed += (unsigned long long)cnt;
+    {
+      const unsigned am = __ballot_sync(FULL, alive);
+      const unsigned src = __fns(am, 0, lane + 1);              // lane holding the (lane+1)-th survivor
+      const uint64_t ck = __shfl_sync(FULL, key, (int)(src & 31u));
+      key = src < 32u ? ck : 0ull;
+    }
+    // merges 32 fresh keys into the list, keeps the 32 best sorted, raises the floor to the best key dropped
+    auto merge_fresh = [&](uint64_t pk) {
       pk = warp_sort_desc(pk, lane);
       const uint64_t br = __shfl_sync(FULL, pk, 31 - lane);
       const uint64_t lo = key < br ? key : br;
       uint64_t v = key > br ? key : br;
-      const uint64_t dropped = warp_max_u64(lo);           // best key that no longer fits into the 32 lanes
+      const uint64_t dropped = warp_max_u64(lo);
       fl = dropped > fl ? dropped : fl;
 #pragma unroll
       for (int j = 16; j > 0; j >>= 1) {
@@ -930,7 +946,42 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
         v = take_max ? (o > v ? o : v) : (o < v ? o : v);
       }
       key = v;
-      __syncwarp();
+    };
+    // (2) the nodes the replay just finished modified: their current records are still in this warp's slots
+    {
+      uint64_t pk = 0;
+      const bool mine = sm.lane_mod[lane] != 0;
+      if (mine) {
+        ColAcc acc{&sm.slot[sm.lane_which[lane]][0][0], (uint32_t)lane, 32u, R, W};
+        pk = eval_pair(S.cf, cs.cls[nk], acc, sm.lane_node[lane], nullptr);
+      }
+      const unsigned cnt = __popc(__ballot_sync(FULL, mine));
+      if (lane == 0) sm.ctl.pairs_replayed += (unsigned long long)cnt;
+      merge_fresh(pk);
+    }
+    __syncwarp();
+    // (3) K > 2: nodes modified by EARLIER replays of this launch (not touched again by the last one): re-read from the table
+    if (K > 2) {
+      for (uint32_t base = 0; base < nprev; base += 32) {
+        uint64_t pk = 0;
+        bool mine = base + lane < nprev;
+        uint32_t nd = 0;
+        if (mine) {
+          nd = sm.mod[base + lane];
+          for (uint32_t z = 0; z < 32; ++z) if (sm.lane_mod[z] && sm.lane_node[z] == nd) { mine = false; break; }
+        }
+        __syncwarp();
+        if (mine) {
+          const uint64_t* g = S.tiles + (size_t)(nd / TILE_NODES) * ((size_t)ncols * TILE_NODES) + (nd % TILE_NODES);
+          for (uint32_t cc = 0; cc < ncols; ++cc) sm.slot[0][cc][lane] = __ldcg(g + (size_t)cc * TILE_NODES);
+          ColAcc acc{&sm.slot[0][0][0], (uint32_t)lane, 32u, R, W};
+          pk = eval_pair(S.cf, cs.cls[nk], acc, nd, nullptr);
+        }
+        const unsigned cnt = __popc(__ballot_sync(FULL, mine));
+        if (lane == 0) sm.ctl.pairs_replayed += (unsigned long long)cnt;
+        merge_fresh(pk);
+        __syncwarp();
+      }
     }
     sm.keys[lane] = key;
     if (lane == 0) { sm.chain_floor = fl; sm.ctl.chain_hits += 1; }
@@ -942,7 +993,9 @@ visit_chain_kernel(const __grid_constant__ DevSession S) {
     used |= 1u << nk;
     kcur = nk;
     __syncwarp();
+    if (lane == 0) { __threadfence_block(); *((volatile uint32_t*)&sm.chain_seq) = ++seq; }   // shadow warp: prefetch this visit
   }
+  if (lane == 0) *((volatile uint32_t*)&sm.chain_seq) = 0xFFFFFFFFu;
   if (lane == 0) publish_chain(S, sm.ctl);
   __syncwarp();
   store_ctl(gctl, sm.ctl, lane);
