@@ -20,12 +20,15 @@
 namespace kb {
 
 struct Slab {                       // bump allocator over one byte buffer; offsets are 256-byte aligned
-  std::vector<unsigned char> host;
+  std::vector<unsigned char> host;  // sized (and zeroed) ONCE by commit(): the capacity is reused when the Slab is
+  size_t top = 0;
+  void reset() { top = 0; }
   size_t alloc(size_t bytes) {
-    size_t off = (host.size() + 255) & ~(size_t)255;
-    host.resize(off + bytes, 0);
+    const size_t off = (top + 255) & ~(size_t)255;
+    top = off + bytes;
     return off;
   }
+  void commit() { host.assign((top + 255) & ~(size_t)255, 0); }
 };
 
 struct HostRes { double v[KB_MAX_R]; uint32_t present; HostRes() : present(0) { for (double& x : v) x = 0; } };
@@ -262,6 +265,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   if (s->Q > KB_MAX_Q) return bfail(e, KB_E_BADARG, "Q=%u > KB_MAX_Q", s->Q);
   if (s->N >= 0xFFFFFFF0u) return bfail(e, KB_E_BADARG, "N too large for the packed key");
   const uint32_t R = s->R, W = s->W, N = s->N, T = s->T, J = s->J, Q = s->Q;
+  B.hc = HostConf();                 // a BuiltSession may be reused across loads (the engine keeps one to recycle its buffers)
   HostConf& hc = B.hc;
   int rc = resolve_conf(e, conf, R, W, hc);
   if (rc) return rc;
@@ -288,7 +292,33 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     };
     static_assert(sizeof(ClassRec) % 8 == 0, "ClassRec is hashed as 64-bit words");
     uint32_t prev_class = 0xFFFFFFFFu;
+    // PodGroups are homogeneous: most tasks carry exactly the fields of their predecessor.  Comparing the flattened columns of
+    // t and t-1 (bit patterns, like the memcmp of the records below) is far cheaper than building and hashing a record.
+    auto bits = [](const double* a, size_t i) { uint64_t u; memcpy(&u, a + i, 8); return u; };
+    auto same_as_prev = [&](uint32_t t) {
+      if (s->task_flags[t] != s->task_flags[t - 1] || s->task_n_aff_terms[t] != s->task_n_aff_terms[t - 1] ||
+          s->task_nz_cpu[t] != s->task_nz_cpu[t - 1] || s->task_nz_mem[t] != s->task_nz_mem[t - 1]) return false;
+      for (uint32_t r = 0; r < R; ++r) {
+        const size_t i = (size_t)r * T + t;
+        if (bits(s->task_initreq, i) != bits(s->task_initreq, i - 1) || bits(s->task_resreq, i) != bits(s->task_resreq, i - 1)) return false;
+      }
+      const uint32_t na = s->task_n_aff_terms[t];
+      for (uint32_t w = 0; w < W; ++w) {
+        const size_t i = (size_t)w * T + t;
+        if (s->task_sel_req[i] != s->task_sel_req[i - 1] || s->task_tol[i] != s->task_tol[i - 1] ||
+            s->task_port_own[i] != s->task_port_own[i - 1] || s->task_port_conflict[i] != s->task_port_conflict[i - 1]) return false;
+        for (uint32_t a = 0; a < na && a < KB_MAX_AFF_TERMS; ++a) {
+          const size_t k = ((size_t)a * W + w) * T + t;
+          if (s->task_aff_terms[k] != s->task_aff_terms[k - 1]) return false;
+        }
+      }
+      return true;
+    };
     for (uint32_t t = 0; t < T; ++t) {
+      if (t > 0 && prev_class != 0xFFFFFFFFu && same_as_prev(t)) {     // t-1 passed every check below with the same values
+        task_class[t] = prev_class; task_empty[t] = task_empty[t - 1];
+        continue;
+      }
       if (s->task_flags[t] & (KB_TASK_HAS_POD_AFFINITY | KB_TASK_HAS_PREFERRED_NODE_AFFINITY))
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod / preferred node affinity terms: outside this build (no CPU fallback)", t);
       if (s->task_n_aff_terms[t] > KB_MAX_AFF_TERMS) return bfail(e, KB_E_BADARG, "task %u: n_aff_terms > KB_MAX_AFF_TERMS", t);
@@ -344,11 +374,12 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     job_ord_off[j] = (uint32_t)ord_task.size();
     size_t b = ord_task.size();
     for (uint32_t t = s->job_task_off[j]; t < s->job_task_off[j + 1]; ++t) if (!task_empty[t]) ord_task.push_back(t);
-    std::sort(ord_task.begin() + b, ord_task.end(), [&](uint32_t l, uint32_t r) {
+    auto before = [&](uint32_t l, uint32_t r) {
       if (hc.task_order_priority && s->task_prio[l] != s->task_prio[r]) return s->task_prio[l] > s->task_prio[r];
       if (s->task_ctime[l] != s->task_ctime[r]) return s->task_ctime[l] < s->task_ctime[r];
       return s->task_uid_rank[l] < s->task_uid_rank[r];
-    });
+    };
+    if (!std::is_sorted(ord_task.begin() + b, ord_task.end(), before)) std::sort(ord_task.begin() + b, ord_task.end(), before);
   }
   job_ord_off[J] = (uint32_t)ord_task.size();
   const uint32_t To = (uint32_t)ord_task.size();
@@ -375,7 +406,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   const uint32_t ncols = tile_ncols(R, W);
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;
   Slab& mut = B.mut; Slab& imm = B.imm;
-  mut.host.clear(); imm.host.clear();
+  mut.reset(); imm.reset();
   DevSession H{};            // host view: pointers into the slabs' host buffers
   OffMut& om = B.om; OffImm& oi = B.oi;
   const uint32_t GMAX = std::max(1u, max_grid);
@@ -440,8 +471,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.bf_jobs_off = imm.alloc(2 * 4);
   oi.bf_classes = imm.alloc((size_t)(Tb ? C : 1) * sizeof(ClassRec));
   oi.ord_chain = imm.alloc((size_t)std::max(1u, To) * (KB_CHAIN_MAX - 1) * 4);
-  mut.host.resize((mut.host.size() + 255) & ~(size_t)255);
-  imm.host.resize((imm.host.size() + 255) & ~(size_t)255);
+  mut.commit(); imm.commit();
 
   B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.Tb = Tb;
   B.bind(H, mut.host.data(), imm.host.data());
@@ -484,10 +514,13 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   if (T) memcpy(imm.host.data() + oi.task_class, task_class.data(), (size_t)T * 4);
   std::vector<uint32_t> tb_order(J);
   for (uint32_t j = 0; j < J; ++j) tb_order[j] = j;
-  std::sort(tb_order.begin(), tb_order.end(), [&](uint32_t l, uint32_t r) {
-    if (s->job_ctime[l] != s->job_ctime[r]) return s->job_ctime[l] < s->job_ctime[r];
-    return l < r;
-  });
+  {
+    auto before = [&](uint32_t l, uint32_t r) {
+      if (s->job_ctime[l] != s->job_ctime[r]) return s->job_ctime[l] < s->job_ctime[r];
+      return l < r;
+    };
+    if (!std::is_sorted(tb_order.begin(), tb_order.end(), before)) std::sort(tb_order.begin(), tb_order.end(), before);
+  }
   for (uint32_t i = 0; i < J; ++i) H.job_tb_rank[tb_order[i]] = i;
   int32_t* h_ready0 = (int32_t*)(imm.host.data() + oi.job_ready0);
   for (uint32_t j = 0; j < J; ++j) {
@@ -575,10 +608,16 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     memcpy(H.q_static_off, cnt.data(), (size_t)(Q + 1) * 4);
     std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
     std::vector<uint32_t> next_diff(std::max(1u, To), 0xFFFFFFFFu);     // first later slot (static walk) with another class
+    const bool want_chain = world <= 1 && (kchain == 2 || kchain == 4);
+    const bool want_peek = world <= 1 && (overlap_mode > 0 || (overlap_mode < 0 && N >= 65536 && Q == 1));
     for (uint32_t j = 0; j < J; ++j) H.q_static[fill[s->job_queue[j]]++] = j;
     for (uint32_t q = 0; q < Q; ++q) {
-      std::sort(H.q_static + cnt[q], H.q_static + cnt[q + 1], [&](uint32_t l, uint32_t r) { return job_before(H, l, r); });
+      {
+        auto before = [&](uint32_t l, uint32_t r) { return job_before(H, l, r); };
+        if (!std::is_sorted(H.q_static + cnt[q], H.q_static + cnt[q + 1], before)) std::sort(H.q_static + cnt[q], H.q_static + cnt[q + 1], before);
+      }
       H.q_static_head[q] = cnt[q];
+      if (!want_peek && !want_chain) continue;      // the prediction tables are only read by the overlap / chained-visit kernels
       // prediction table: walking the queue's static job order backwards, the first class that differs from a slot's own
       uint32_t next_slot = 0xFFFFFFFFu;
       for (uint32_t k = cnt[q + 1]; k-- > cnt[q];) {

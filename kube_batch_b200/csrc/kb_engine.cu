@@ -85,6 +85,7 @@ struct kb_engine {
   size_t mut_bytes = 0, imm_bytes = 0;
   DevSession dev{};                    // device pointers (allocate view)
   DevSession dev_bf{};                 // backfill view of the same slabs (kb_backfill)
+  BuiltSession built;                  // host-side build of the current session
   uint32_t Tb = 0;                     // backfill order slots
   bool allocate_ran = false;           // kb_allocate ran since kb_session_load (kb_backfill continues its counters)
   uint32_t* d_task_class = nullptr;    // [T] (immutable slab)
@@ -283,7 +284,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   auto t_start = std::chrono::steady_clock::now();
   CUDA_TRY(e, cudaSetDevice(e->device));
   e->loaded = false;
-  BuiltSession B;
+  BuiltSession& B = e->built;        // kept across loads: the host slabs' capacity is recycled
   BuildErr be;
   uint32_t kchain = e->world == 1 ? e->kchain_req : 1u;
   {
