@@ -405,6 +405,7 @@ void emu_begin_backfill(Emu& E, bool carry) {
 
 extern "C" {
 
+uint32_t kbemu_buf_u64(void* h);
 const char* kbemu_last_error(void) { return g_err.c_str(); }
 
 // mode (single rank): 0 = scan/replay overlap protocol, 1 = plain one-class launches, 2 / 4 = chained visits (visit_chain_kernel<K>)
@@ -419,6 +420,33 @@ void* kbemu_create2(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_
 }
 // the default emulation exercises the overlap protocol on one rank (the device enables it by size)
 void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world) { return kbemu_create2(snap, conf, rank, world, 0); }
+// kb_session_load on an engine that already holds a session: the BuiltSession (and its slabs' capacity) is reused
+int kbemu_reload(void* h, const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t mode) {
+  Emu* E = (Emu*)h;
+  BuildErr be;
+  if (int rc = build_session(snap, conf, 148, E->B, &be, 0, 1, mode == 0 ? 1 : 0, mode >= 2 ? mode : 1)) { g_err = be.msg; return rc; }
+  E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
+  E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
+  E->cur = &E->S;
+  E->launches = 0;
+  return KB_OK;
+}
+int kbemu_run(void* h, uint32_t actions) {
+  Emu* E = (Emu*)h;
+  std::vector<uint64_t> buf(kbemu_buf_u64(E));
+  const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To + E->B.Tb) + 1024;
+  for (uint32_t pass = 0; pass < 2; ++pass) {
+    if (!((actions ? actions : 1u) & (1u << pass))) continue;
+    if (pass == 1) emu_begin_backfill(*E, ((actions ? actions : 1u) & 1u) != 0);
+    while (!E->cur->ctl->done) {
+      if (E->cur->overlap) emu_launch_overlap(*E);
+      else if (E->cur->kchain > 1) emu_launch_chain(*E);
+      else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
+      if (E->launches > guard) { g_err = "emulated cycle did not terminate"; return KB_E_STATE; }
+    }
+  }
+  return KB_OK;
+}
 void kbemu_destroy(void* h) { delete (Emu*)h; }
 int kbemu_done(void* h) { return ((Emu*)h)->cur->ctl->done ? 1 : 0; }
 void kbemu_begin_backfill(void* h, int allocate_ran) { emu_begin_backfill(*(Emu*)h, allocate_ran != 0); }

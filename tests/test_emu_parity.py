@@ -136,6 +136,44 @@ def test_host_ports_taints_selectors_affinity():
     assert got["ns/nowhere"] is None
 
 
+def test_session_reload_reuses_the_built_session():
+    """kb_session_load again and again on one engine: the host-side BuiltSession (slabs, conf, tables) is recycled, nothing
+    of the previous session may leak into the next — bigger, smaller, other plugins, other modes."""
+    import ctypes as C
+    L = util.emu_lib()
+    L.kbemu_create2.restype = C.c_void_p
+    L.kbemu_create2.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
+    L.kbemu_reload.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
+    L.kbemu_run.argtypes = [C.c_void_p, C.c_uint32]
+    L.kbemu_finish.argtypes = [C.c_void_p] + [C.c_void_p] * 14
+    L.kbemu_destroy.argtypes = [C.c_void_p]
+    seq = [(synth.random_session(1, tasks=300, jobs=30, nodes=200, queues=3), "default", 1, 1),
+           (synth.random_session(2, tasks=20, jobs=3, nodes=7, queues=1), "none", 4, 1),
+           (synth.random_session(3, tasks=500, jobs=60, nodes=400, queues=2, be_frac=0.3, be_variants=True), "c2", 2, 3),
+           (synth.random_session(4, tasks=60, jobs=8, nodes=12, queues=4, R=5, W=3), "weights", 0, 1),
+           (synth.random_session(5, tasks=250, jobs=25, nodes=90, queues=2), "allocate_test", 1, 3)]
+    h = None
+    try:
+        for snap, cname, mode, actions in seq:
+            conf = CONFS[cname]
+            cs, k1 = snap.to_c()
+            cc, k2 = conf.to_c()
+            if h is None:
+                h = L.kbemu_create2(C.addressof(cs), C.addressof(cc), 0, 1, mode)
+                assert h
+            else:
+                assert L.kbemu_reload(h, C.addressof(cs), C.addressof(cc), mode) == 0
+            assert L.kbemu_run(h, actions) == 0
+            dec = np.zeros(max(snap.T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+            st = abi.kb_stats()
+            L.kbemu_finish(h, dec.ctypes.data, C.addressof(st), *([None] * 12))
+            o = kbo.allocate(snap, conf, actions=actions)
+            util.assert_same_decisions(o.decisions, dec[:snap.T], f"reload {cname} mode{mode} actions{actions}")
+    finally:
+        if h:
+            L.kbemu_destroy(h)
+
+
 # ---------------- chained visits (visit_chain_kernel<K>): K classes per scan, look-ahead lists patched before their replay ----------------
 @pytest.mark.parametrize("seed", range(12))
 def test_chained_visits_random_sessions(seed):
