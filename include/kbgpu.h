@@ -31,6 +31,7 @@ extern "C" {
 /* Compile-time capacity of the dense encodings. */
 #define KB_MAX_R 8          /* resource dims: 0 = cpu (milli), 1 = memory (bytes), 2.. = scalar resources (milli) */
 #define KB_MAX_W 4          /* 64-bit words per label / taint / host-port bitmask */
+#define KB_MAX_PREF_TERMS 4   /* preferred node-affinity terms per task */
 #define KB_MAX_AFF_TERMS 4  /* OR-ed required node-affinity terms carried per task */
 #define KB_MAX_Q 256        /* queues */
 
@@ -131,6 +132,14 @@ typedef struct kb_snapshot {
   /* ---- queues (api.QueueInfo, api/queue_info.go:74-81) ---- */
   const int32_t*  queue_weight;       /* [Q]                                                         */
   const int64_t*  queue_ctime;        /* [Q]                                                         */
+
+  /* ---- preferred node affinity (NodeAffinityPriority, vendor/.../priorities/node_affinity.go:34-77) ----
+   * Only read for tasks that carry KB_TASK_HAS_PREFERRED_NODE_AFFINITY; all three may be NULL otherwise.  The CPU oracle
+   * evaluates them (count = sum of the weights of the matching terms, NormalizeReduce(10) over the feasible nodes);
+   * this build of the engine still refuses such tasks (KB_E_UNSUPPORTED_FEATURE). */
+  const uint32_t* task_n_pref_terms;  /* [T] 0..KB_MAX_PREF_TERMS                                    */
+  const uint64_t* task_pref_terms;    /* [KB_MAX_PREF_TERMS][W][T] requirement atoms of term p: ALL must hold on the node */
+  const int32_t*  task_pref_weights;  /* [KB_MAX_PREF_TERMS][T] PreferredSchedulingTerm.Weight (0 = term skipped) */
 } kb_snapshot;
 
 /* Mirrors conf.PluginOption (pkg/scheduler/conf/scheduler_conf.go:33-56).  The Enabled* tri-states

@@ -16,6 +16,7 @@ KB_ABI_VERSION = 1
 KB_MAX_R = 8
 KB_MAX_W = 4
 KB_MAX_AFF_TERMS = 4
+KB_MAX_PREF_TERMS = 4
 KB_MAX_Q = 256
 
 KB_OK = 0
@@ -90,6 +91,9 @@ SNAPSHOT_ARRAYS = [
     ("job_ctime", _pi64, "i8", "J"),
     ("queue_weight", _pi32, "i4", "Q"),
     ("queue_ctime", _pi64, "i8", "Q"),
+    ("task_n_pref_terms", _pu32, "u4", "T"),
+    ("task_pref_terms", _pu64, "u8", "PWT"),
+    ("task_pref_weights", _pi32, "i4", "PT"),
 ]
 
 

@@ -78,6 +78,8 @@ class Pod:
     node_selector: Dict[str, str] = field(default_factory=dict)
     # required node affinity: OR over terms, each an AND of (key, op, values), op in In NotIn Exists DoesNotExist Gt Lt
     affinity_terms: Optional[List[List[Tuple[str, str, Sequence[str]]]]] = None
+    # nodeAffinity.preferredDuringSchedulingIgnoredDuringExecution: [(weight, [(key, op, values), ...]), ...]
+    preferred_terms: List[Tuple[int, List[Tuple[str, str, Sequence[str]]]]] = field(default_factory=list)
     tolerations: List[Tuple[str, str, str, str]] = field(default_factory=list)   # (key, operator, value, effect)
     host_ports: List[Tuple[str, str, int]] = field(default_factory=list)          # (hostIP, protocol, hostPort)
     priority: Optional[int] = None
@@ -256,6 +258,9 @@ class SessionBuilder:
             for term in (p.affinity_terms or []):
                 for (k, op, vals) in term:
                     atom_of(k, op, vals)
+            for (_, exprs) in p.preferred_terms:
+                for (k, op, vals) in exprs:
+                    atom_of(k, op, vals)
         taint_atoms: Dict[Tuple, int] = {}
         for n in nodes:
             for t in n.taints:
@@ -397,6 +402,15 @@ class SessionBuilder:
             fl = 0
             if not p.requests and not p.limits:
                 fl |= abi.KB_TASK_BEST_EFFORT_QOS
+            if p.preferred_terms:                # NodeAffinityPriority (node_affinity.go:34-77); an empty expression list matches every node
+                assert len(p.preferred_terms) <= abi.KB_MAX_PREF_TERMS
+                fl |= abi.KB_TASK_HAS_PREFERRED_NODE_AFFINITY
+                s.task_n_pref_terms[t] = len(p.preferred_terms)
+                for pi, (weight, exprs) in enumerate(p.preferred_terms):
+                    s.task_pref_weights[pi, t] = weight
+                    for (k, op, vals) in exprs:
+                        a = atom_of(k, op, vals)
+                        s.task_pref_terms[pi, a // 64, t] |= np.uint64(1) << np.uint64(a % 64)
             s.task_flags[t] = fl
             s.task_prio[t] = 1 if p.priority is None else p.priority    # api.NewTaskInfo (job_info.go:82-90)
             s.task_ctime[t] = p.creation

@@ -43,7 +43,8 @@ class Snapshot:
         self.meta: Dict[str, object] = {}
 
     def dims(self) -> Dict[str, int]:
-        return {"R": self.R, "W": self.W, "N": self.N, "T": self.T, "J": self.J, "Q": self.Q, "A": abi.KB_MAX_AFF_TERMS}
+        return {"R": self.R, "W": self.W, "N": self.N, "T": self.T, "J": self.J, "Q": self.Q, "A": abi.KB_MAX_AFF_TERMS,
+                "P": abi.KB_MAX_PREF_TERMS}
 
     def validate(self) -> None:
         dims = self.dims()

@@ -203,6 +203,10 @@ struct TaskInfo {                       // api/job_info.go:36-54
   uint64_t sel_req[KB_MAX_W], tol[KB_MAX_W], port_own[KB_MAX_W], port_conflict[KB_MAX_W];
   uint64_t aff[KB_MAX_AFF_TERMS][KB_MAX_W];
   uint32_t n_aff = 0, flags = 0;
+  // nodeAffinity.preferredDuringSchedulingIgnoredDuringExecution: requirement atoms + weight per term
+  uint64_t pref[KB_MAX_PREF_TERMS][KB_MAX_W];
+  int32_t pref_w[KB_MAX_PREF_TERMS];
+  uint32_t n_pref = 0;
   // bookkeeping for the decision output
   uint32_t step = 0xFFFFFFFFu, dispatch_step = 0xFFFFFFFFu;
   bool dispatched = false;
@@ -413,11 +417,29 @@ int64_t balancedResourceScorer(int64_t req_cpu, int64_t alloc_cpu, int64_t req_m
 // ---------------------------------------------------------------------------------------------
 // framework.Session (framework/session.go:37-61) + dispatchers (framework/session_plugins.go)
 // ---------------------------------------------------------------------------------------------
-struct PriorityConfig {                 // vendor/.../priorities/types.go:46-54 (Map-only configs on this path)
+struct PriorityConfig {                 // vendor/.../priorities/types.go:46-54 (Map [+ Reduce] configs on this path)
   std::string Name;
   std::function<int64_t(const TaskInfo&, const NodeInfo&, int64_t nz_cpu, int64_t nz_mem)> Map;
   int Weight = 0;
+  std::function<void(std::vector<int64_t>&)> Reduce;   // over the FEASIBLE nodes' Map results (scheduler_helper.go:139-156)
 };
+
+// priorities.NormalizeReduce(maxPriority, reverse) (vendor/.../priorities/reduce.go:28-63)
+inline std::function<void(std::vector<int64_t>&)> NormalizeReduce(int64_t maxPriority, bool reverse) {
+  return [=](std::vector<int64_t>& result) {
+    int64_t maxCount = 0;
+    for (int64_t v : result) if (v > maxCount) maxCount = v;
+    if (maxCount == 0) {
+      if (reverse) for (int64_t& v : result) v = maxPriority;
+      return;
+    }
+    for (int64_t& v : result) {
+      int64_t score = maxPriority * v / maxCount;
+      if (reverse) score = maxPriority - score;
+      v = score;
+    }
+  };
+}
 
 struct Session;
 struct Plugin {
@@ -855,19 +877,32 @@ struct nodeOrderPlugin : Plugin {
     cfgs.push_back({"LeastRequestedPriority",
                     [](const TaskInfo& t, const NodeInfo& n, int64_t nzc, int64_t nzm) {
                       return leastResourceScorer(nzc + t.nz_cpu, n.alloc_cpu, nzm + t.nz_mem, n.alloc_mem); },
-                    leastReqWeight});
+                    leastReqWeight, nullptr});
     cfgs.push_back({"MostRequestedPriority",
                     [](const TaskInfo& t, const NodeInfo& n, int64_t nzc, int64_t nzm) {
                       return mostResourceScorer(nzc + t.nz_cpu, n.alloc_cpu, nzm + t.nz_mem, n.alloc_mem); },
-                    mostReqWeight});
-    // NodeAffinityPriority (node_affinity.go:34-77 + NormalizeReduce) and InterPodAffinityPriority
-    // (interpod_affinity.go:99-235): no preferred terms in the snapshot -> every count is 0 -> score 0.
-    cfgs.push_back({"NodeAffinityPriority", [](const TaskInfo&, const NodeInfo&, int64_t, int64_t) { return (int64_t)0; }, nodeAffinityWeight});
-    cfgs.push_back({"InterPodAffinityPriority", [](const TaskInfo&, const NodeInfo&, int64_t, int64_t) { return (int64_t)0; }, podAffinityWeight});
+                    mostReqWeight, nullptr});
+    // NodeAffinityPriority: CalculateNodeAffinityPriorityMap (node_affinity.go:34-77): count = sum of the weights of the
+    // preferred terms whose selector matches the node's labels (weight 0 terms are skipped, an empty term matches every
+    // node); CalculateNodeAffinityPriorityReduce = NormalizeReduce(10, false) over the feasible nodes.
+    cfgs.push_back({"NodeAffinityPriority",
+                    [](const TaskInfo& t, const NodeInfo& n, int64_t, int64_t) {
+                      int64_t count = 0;
+                      for (uint32_t p = 0; p < t.n_pref; ++p) {
+                        if (t.pref_w[p] == 0) continue;
+                        bool match = true;
+                        for (uint32_t w = 0; w < KB_MAX_W; ++w) if ((n.labels[w] & t.pref[p][w]) != t.pref[p][w]) { match = false; break; }
+                        if (match) count += t.pref_w[p];
+                      }
+                      return count; },
+                    nodeAffinityWeight, NormalizeReduce(10, false)});
+    // InterPodAffinityPriority (interpod_affinity.go:99-235): no pod (anti)affinity terms in the snapshot (tasks carrying
+    // them are refused) -> every count is 0 -> score 0.
+    cfgs.push_back({"InterPodAffinityPriority", [](const TaskInfo&, const NodeInfo&, int64_t, int64_t) { return (int64_t)0; }, podAffinityWeight, nullptr});
     cfgs.push_back({"BalancedResourceAllocation",
                     [](const TaskInfo& t, const NodeInfo& n, int64_t nzc, int64_t nzm) {
                       return balancedResourceScorer(nzc + t.nz_cpu, n.alloc_cpu, nzm + t.nz_mem, n.alloc_mem); },
-                    balancedResourceWeight});
+                    balancedResourceWeight, nullptr});
     ssn->nodePrioritizers[Name()] = cfgs;
   }
 };
@@ -984,8 +1019,19 @@ int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, st
       ti.Priority = s->task_prio[t]; ti.ctime = s->task_ctime[t]; ti.uid_rank = s->task_uid_rank[t];
       ti.nz_cpu = s->task_nz_cpu[t]; ti.nz_mem = s->task_nz_mem[t];
       ti.flags = s->task_flags[t];
-      if (ti.flags & (KB_TASK_HAS_POD_AFFINITY | KB_TASK_HAS_PREFERRED_NODE_AFFINITY)) {
-        g_err = "inter-pod / preferred node affinity is outside this build"; return KB_E_UNSUPPORTED_FEATURE; }
+      if (ti.flags & KB_TASK_HAS_POD_AFFINITY) { g_err = "inter-pod affinity is outside this build"; return KB_E_UNSUPPORTED_FEATURE; }
+      ti.n_pref = 0;
+      for (auto& pw : ti.pref_w) pw = 0;
+      for (auto& pr : ti.pref) for (uint32_t w = 0; w < KB_MAX_W; ++w) pr[w] = 0;
+      if (ti.flags & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) {
+        if (!s->task_n_pref_terms || !s->task_pref_terms || !s->task_pref_weights) { g_err = "KB_TASK_HAS_PREFERRED_NODE_AFFINITY without task_pref_* arrays"; return KB_E_BADARG; }
+        ti.n_pref = s->task_n_pref_terms[t];
+        if (ti.n_pref > KB_MAX_PREF_TERMS) { g_err = "task_n_pref_terms > KB_MAX_PREF_TERMS"; return KB_E_BADARG; }
+        for (uint32_t p = 0; p < ti.n_pref; ++p) {
+          ti.pref_w[p] = s->task_pref_weights[(size_t)p * T + t];
+          for (uint32_t w = 0; w < W; ++w) ti.pref[p][w] = s->task_pref_terms[((size_t)p * W + w) * T + t];
+        }
+      }
       ti.n_aff = s->task_n_aff_terms[t];
       if (ti.n_aff > KB_MAX_AFF_TERMS) { g_err = "task_n_aff_terms > KB_MAX_AFF_TERMS"; return KB_E_BADARG; }
       for (uint32_t w = 0; w < KB_MAX_W; ++w) { ti.sel_req[w] = ti.tol[w] = ti.port_own[w] = ti.port_conflict[w] = 0; for (auto& a : ti.aff) a[w] = 0; }
@@ -1122,9 +1168,18 @@ struct Executor {
         nzc = a.nz_cpu; nzm = a.nz_mem;
       }
       double score = 0;
-      for (auto& c : cfgs) score += (double)(c.Map(task, node, nzc, nzm) * (int64_t)c.Weight);   // :162-168
+      for (auto& c : cfgs) if (!c.Reduce) score += (double)(c.Map(task, node, nzc, nzm) * (int64_t)c.Weight);   // :162-168
       result[i] = score;
     });
+    // configs with a Reduce step: Map over the feasible nodes, Reduce the whole list, then the weighted sum (:139-168).
+    // Without preferred terms every count is 0 and NormalizeReduce leaves zeros: skip the pass.
+    for (auto& c : cfgs) {
+      if (!c.Reduce || task.n_pref == 0) continue;
+      std::vector<int64_t> col(nodes.size());
+      for (size_t i = 0; i < nodes.size(); ++i) col[i] = c.Map(task, ssn.Nodes[nodes[i]], 0, 0);
+      c.Reduce(col);
+      for (size_t i = 0; i < nodes.size(); ++i) result[i] += (double)(col[i] * (int64_t)c.Weight);
+    }
   }
 
   // util.SelectBestNode (util/scheduler_helper.go:188-208) with rule (3): first max

@@ -207,3 +207,68 @@ def test_gang_dispatch_only_when_min_member_reached():
     assert got["ns/a0"] == (1, 1) and got["ns/a1"] == (1, 1)
     assert sorted(v for k, v in got.items() if k.startswith("ns/b")) == [(0, 0), (1, 0), (1, 0)]
     assert o.node_idle[0, 0] == 0.0
+
+
+# ---------------- NodeAffinityPriority: vendor/.../priorities/node_affinity.go:34-77 + reduce.go:28-63 ----------------
+# The reference carries no test for it ("parity unpinned by the reference"); the vectors below are hand-computed from the
+# vendored code.  The ENGINE refuses such tasks in this build (KB_E_UNSUPPORTED_FEATURE) — this pins the oracle for the next round.
+def _pref_session(pods):
+    from kube_batch_b200 import builder as B
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "g", "q", min_member=1))
+    for name, labels, taints in (("n0", {"zone": "a"}, []), ("n1", {"zone": "b", "disk": "ssd"}, [("dedicated", "x", "NoSchedule")]),
+                                 ("n2", {"zone": "b"}, []), ("n3", {"zone": "c"}, [])):
+        b.add_node(B.Node(name, {"cpu": 8, "memory": 32e9, "pods": 10}, labels=labels, taints=taints))
+    for p in pods:
+        b.add_pod(p)
+    return b.flatten()
+
+
+def test_node_affinity_priority_counts_and_normalisation():
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf
+    req = {"cpu": 1, "memory": 1e9}
+    pref = [(80, [("zone", "In", ["b"])]), (20, [("disk", "In", ["ssd"])]), (0, [("zone", "In", ["c"])])]
+    tol = [("dedicated", "Equal", "x", "NoSchedule")]
+    s = _pref_session([B.Pod("ns", f"p{i}", "", "Pending", req, group="g", creation=i, preferred_terms=pref, tolerations=tol) for i in range(3)])
+    conf = PluginConf.from_names([["gang"], ["predicates", "nodeorder"]])
+    # counts: n0 0, n1 100, n2 80, n3 0 (the weight-0 term is skipped) -> NormalizeReduce(10): 0, 10, 8, 0
+    fit, score = kbo.predicate_score(s, conf, 0)
+    # base = least (8+9)/2 = 8 + balanced int((1 - |0.125 - 0.03125|) * 10) = 9 -> 17 on every (empty, identical) node
+    assert fit.tolist() == [1, 1, 1, 1] and score.tolist() == [17.0, 27.0, 25.0, 17.0]
+    o = kbo.allocate(s, conf)
+    names = [s.meta["nodes"][n] for n in o.decisions["node"]]
+    # p0 -> n1 (27).  p1: n1 now scores least 8 + balanced 8 + 10 = 26 > n2 25.  p2: n1 7 + 7 + 10 = 24 < n2 25.
+    assert names == ["n1", "n1", "n2"]
+
+
+def test_node_affinity_priority_normalises_over_feasible_nodes_only():
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf
+    req = {"cpu": 1, "memory": 1e9}
+    pref = [(80, [("zone", "In", ["b"])]), (20, [("disk", "In", ["ssd"])])]
+    # no toleration: n1 (the only 100-count node) is infeasible, so maxCount = 80 and n2 gets the full 10
+    s = _pref_session([B.Pod("ns", "p", "", "Pending", req, group="g", preferred_terms=pref)])
+    conf = PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "3"}})
+    fit, score = kbo.predicate_score(s, conf, 0)
+    assert fit.tolist() == [1, 0, 1, 1] and score[[0, 2, 3]].tolist() == [17.0, 17.0 + 3 * 10, 17.0]
+    o = kbo.allocate(s, conf)
+    assert s.meta["nodes"][int(o.decisions["node"][0])] == "n2"
+    # an empty preferred term matches every node: all counts equal -> every node gets 10 -> no effect on the order
+    s = _pref_session([B.Pod("ns", "p", "", "Pending", req, group="g", preferred_terms=[(5, [])])])
+    fit, score = kbo.predicate_score(s, PluginConf.from_names([["gang"], ["predicates", "nodeorder"]]), 0)
+    assert score[[0, 2, 3]].tolist() == [27.0, 27.0, 27.0]
+    # nodeaffinity.weight 0 switches the term off
+    s = _pref_session([B.Pod("ns", "p", "", "Pending", req, group="g", preferred_terms=pref)])
+    fit, score = kbo.predicate_score(s, PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "0"}}), 0)
+    assert score[[0, 2, 3]].tolist() == [17.0, 17.0, 17.0]
+
+
+def test_engine_side_still_refuses_preferred_node_affinity():
+    import util
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf
+    s = _pref_session([B.Pod("ns", "p", "", "Pending", {"cpu": 1}, group="g", preferred_terms=[(1, [("zone", "In", ["a"])])])])
+    with pytest.raises(RuntimeError, match="preferred node affinity"):
+        util.emu_allocate(s, PluginConf.default())       # the engine's host build (kb_build.h) is what the emulation runs
