@@ -416,7 +416,24 @@ class SessionBuilder:
             s.task_ctime[t] = p.creation
             s.task_uid_rank[t] = uid_rank[p.uid or f"{p.namespace}-{p.name}"]
         s.job_task_off[:] = np.cumsum(counts).astype(np.uint32)
-        s.meta = {"nodes": [n.name for n in nodes], "tasks": [f"{p.namespace}/{p.name}" for p in pending],
+        # ---- Running tasks one by one (only the oracle's reclaim / preempt read them: oracle/kb_oracle.h kbo_running) ----
+        running = [p for p in self.pods if self._task_status(p) == "Running" and f"{p.namespace}/{p.group}" in jidx and p.node_name in nidx]
+        ruids = sorted((p.uid or f"{p.namespace}-{p.name}") for p in running)
+        rrank = {u: i for i, u in enumerate(ruids)}
+        rt = {"node": np.array([nidx[p.node_name] for p in running], dtype=np.uint32),
+              "job": np.array([jidx[f"{p.namespace}/{p.group}"] for p in running], dtype=np.uint32),
+              "resreq": np.zeros((R, len(running))), "res_present": np.zeros(len(running), dtype=np.uint32),
+              "prio": np.array([1 if p.priority is None else p.priority for p in running], dtype=np.int32),
+              "ctime": np.array([p.creation for p in running], dtype=np.int64),
+              "uid_rank": np.array([rrank[p.uid or f"{p.namespace}-{p.name}"] for p in running], dtype=np.uint32),
+              "flags": np.array([1 if (p.namespace == "kube-system" or p.labels.get("priorityClassName") in
+                                       ("system-cluster-critical", "system-node-critical")) else 0 for p in running], dtype=np.uint32),
+              "names": [f"{p.namespace}/{p.name}" for p in running]}
+        for i, p in enumerate(running):
+            v, present = pod_resreq(p)
+            rt["resreq"][:, i] = v
+            rt["res_present"][i] = present
+        s.meta = {"running": rt, "nodes": [n.name for n in nodes], "tasks": [f"{p.namespace}/{p.name}" for p in pending],
                   "jobs": list(jidx.keys()), "queues": [q.name for q in queues], "dims": dims}
         s.validate()
         return s

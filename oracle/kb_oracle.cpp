@@ -210,6 +210,10 @@ struct TaskInfo {                       // api/job_info.go:36-54
   // bookkeeping for the decision output
   uint32_t step = 0xFFFFFFFFu, dispatch_step = 0xFFFFFFFFu;
   bool dispatched = false;
+  // running tasks (kbo_running): conformance-critical pod, eviction record (cache.Evict == FakeEvictor here)
+  bool critical = false;
+  bool evicted = false;
+  uint32_t evict_order = 0xFFFFFFFFu;
 };
 
 struct PodStub {                        // what NewNodeInfo(node.Pods()...) re-aggregates per pod in mode A
@@ -466,6 +470,12 @@ struct Session {
   std::map<std::string, std::function<bool(const JobInfo&)>> jobReadyFns;
   std::map<std::string, std::vector<PriorityConfig>> nodePrioritizers;
   std::vector<std::function<void(const TaskInfo&)>> allocateHandlers;   // EventHandler.AllocateFunc
+  std::vector<std::function<void(const TaskInfo&)>> deallocateHandlers; // EventHandler.DeallocateFunc
+  // victims functions: (preemptor / reclaimer, candidate task ids) -> victim task ids, in candidate order
+  using VictimFn = std::function<std::vector<uint32_t>(const TaskInfo&, const std::vector<uint32_t>&)>;
+  std::map<std::string, VictimFn> preemptableFns, reclaimableFns;
+  std::map<std::string, std::function<bool(const JobInfo&)>> jobPipelinedFns;
+  uint32_t n_evicted = 0;               // cache.Evict calls (util.FakeEvictor.Evicts)
 
   // resolved once after OnSessionOpen: the (tier, plugin) walk of PredicateFn with its map lookups hoisted
   std::vector<const std::function<bool(const TaskInfo&, const NodeInfo&, int32_t, const uint64_t*)>*> resolvedPredicates;
@@ -595,6 +605,7 @@ struct Session {
 
   // api/node_info.go:172-212
   bool AddTask(NodeInfo& ni, TaskInfo& task) {
+    if (task.NodeName >= 0 && task.NodeName != (int)ni.idx) return false;   // :173-176 "task already on different node"
     if (ni.Tasks.count(task.idx)) return false;
     TaskInfo ti = task;  // clone
     switch (ti.Status) {
@@ -657,6 +668,138 @@ struct Session {
     for (auto& eh : allocateHandlers) eh(task);
     return true;
   }
+
+  // api/job_info.go:396-405, :430-434
+  int32_t WaitingTaskNum(const JobInfo& ji) const {
+    auto it = ji.TaskStatusIndex.find(Pipelined);
+    return it == ji.TaskStatusIndex.end() ? 0 : (int32_t)it->second.size();
+  }
+  bool JobInfoPipelined(const JobInfo& ji) const { return WaitingTaskNum(ji) + ReadyTaskNum(ji) >= ji.MinAvailable; }
+  // session_plugins.go:203-221
+  bool JobPipelined(const JobInfo& job) const {
+    for (auto& tier : Tiers)
+      for (auto& plugin : tier.Plugins) {
+        if (!plugin.EnabledJobPipelined) continue;
+        auto it = jobPipelinedFns.find(plugin.Name);
+        if (it == jobPipelinedFns.end()) continue;
+        if (!it->second(job)) return false;
+      }
+    return true;
+  }
+  // session_plugins.go:80-162 (Reclaimable and Preemptable are the same walk over different registries).  Go's nil slice
+  // and "empty" coincide here (every victims slice is built by append from nil), and `init` survives across tiers.
+  std::vector<uint32_t> victims_of(bool reclaim, const TaskInfo& evictor, const std::vector<uint32_t>& evictees) const {
+    std::vector<uint32_t> victims;
+    bool init = false;
+    const auto& fns = reclaim ? reclaimableFns : preemptableFns;
+    for (auto& tier : Tiers) {
+      for (auto& plugin : tier.Plugins) {
+        if (!(reclaim ? plugin.EnabledReclaimable : plugin.EnabledPreemptable)) continue;
+        auto it = fns.find(plugin.Name);
+        if (it == fns.end()) continue;
+        std::vector<uint32_t> candidates = it->second(evictor, evictees);
+        if (!init) { victims = candidates; init = true; }
+        else {
+          std::vector<uint32_t> intersection;
+          for (uint32_t v : victims) for (uint32_t c : candidates) if (v == c) intersection.push_back(v);
+          victims = intersection;
+        }
+      }
+      if (!victims.empty()) return victims;      // "Plugins in this tier made decision if victims is not nil"
+    }
+    return victims;
+  }
+  std::vector<uint32_t> Reclaimable(const TaskInfo& r, const std::vector<uint32_t>& c) const { return victims_of(true, r, c); }
+  std::vector<uint32_t> Preemptable(const TaskInfo& r, const std::vector<uint32_t>& c) const { return victims_of(false, r, c); }
+
+  // api/node_info.go:214-243; the node holds its own clone, whose status decides what is given back
+  bool RemoveTask(NodeInfo& ni, const TaskInfo& ti) {
+    auto it = ni.Tasks.find(ti.idx);
+    if (it == ni.Tasks.end()) return false;
+    const TaskInfo& task = it->second;
+    switch (task.Status) {
+      case Releasing:
+        if (!A.Sub(ni.Releasing, task.Resreq)) { g_err = "panic: Resource is not sufficient to do operation (Releasing.Sub in RemoveTask)"; return false; }
+        A.Add(ni.Idle, task.Resreq);
+        break;
+      case Pipelined:
+        A.Add(ni.Releasing, task.Resreq);
+        break;
+      default:
+        A.Add(ni.Idle, task.Resreq);
+        break;
+    }
+    if (!A.Sub(ni.Used, task.Resreq)) { g_err = "panic: Resource is not sufficient to do operation (Used.Sub in RemoveTask)"; return false; }
+    ni.pods -= 1; ni.nz_cpu -= task.nz_cpu; ni.nz_mem -= task.nz_mem;
+    // host ports of the removed pod: recomputed from the remaining tasks would need the pre-existing pods' ports, which the
+    // snapshot only carries as an aggregate; tasks that move through RemoveTask here (evicted Running pods keep their node,
+    // un-pipelined preemptors) give their ports back only in the unpipeline case:
+    if (task.Status == Pipelined) for (uint32_t w = 0; w < W; ++w) ni.ports[w] &= ~task.port_own[w];
+    ni.Tasks.erase(it);
+    return true;
+  }
+  // api/node_info.go:245-259
+  bool UpdateTask(NodeInfo& ni, TaskInfo& ti) {
+    if (!RemoveTask(ni, ti)) return false;
+    const int keep = ti.NodeName;
+    if (!AddTask(ni, ti)) { g_err = "glog.Fatalf: Failed to add Task to Node during task update"; ti.NodeName = keep; return false; }
+    return true;
+  }
+  // framework/session.go:317-353 (Session.Evict: cache.Evict first) and framework/statement.go:36-64 (Statement.Evict: cache.Evict
+  // only at Commit).  `commit_now` selects between the two.
+  bool EvictTask(TaskInfo& reclaimee, bool commit_now) {
+    if (commit_now) record_evict(reclaimee);
+    JobInfo& job = Jobs[reclaimee.Job];
+    UpdateTaskStatus(job, reclaimee, Releasing);
+    if (reclaimee.NodeName >= 0) UpdateTask(Nodes[reclaimee.NodeName], reclaimee);
+    for (auto& eh : deallocateHandlers) eh(reclaimee);
+    return true;
+  }
+  void record_evict(TaskInfo& t) { t.evicted = true; t.evict_order = n_evicted++; }
+};
+
+// framework/statement.go
+struct Statement {
+  Session& ssn;
+  struct Op { bool evict; uint32_t task; };
+  std::vector<Op> operations;
+  explicit Statement(Session& s) : ssn(s) {}
+  void Evict(TaskInfo& reclaimee) {                                       // :36-64
+    ssn.EvictTask(reclaimee, false);
+    operations.push_back({true, reclaimee.idx});
+  }
+  void Pipeline(TaskInfo& task, NodeInfo& node) {                         // :110-148 (no volume / NodeName handling here)
+    JobInfo& job = ssn.Jobs[task.Job];
+    ssn.UpdateTaskStatus(job, task, Pipelined);
+    if (ssn.AddTask(node, task)) { task.step = ssn.step_counter++; ++ssn.n_pipelined; }
+    for (auto& eh : ssn.allocateHandlers) eh(task);
+    operations.push_back({false, task.idx});
+  }
+  void unevict(TaskInfo& reclaimee) {                                     // :78-107
+    JobInfo& job = ssn.Jobs[reclaimee.Job];
+    ssn.UpdateTaskStatus(job, reclaimee, Running);
+    if (reclaimee.NodeName >= 0) ssn.UpdateTask(ssn.Nodes[reclaimee.NodeName], reclaimee);
+    for (auto& eh : ssn.allocateHandlers) eh(reclaimee);
+  }
+  void unpipeline(TaskInfo& task) {                                       // :153-188
+    JobInfo& job = ssn.Jobs[task.Job];
+    ssn.UpdateTaskStatus(job, task, Pending);
+    if (task.NodeName >= 0) {
+      if (ssn.RemoveTask(ssn.Nodes[task.NodeName], task)) { --ssn.n_pipelined; task.step = 0xFFFFFFFFu; }
+    }
+    for (auto& eh : ssn.deallocateHandlers) eh(task);
+  }
+  void Discard() {                                                        // :191-203
+    for (size_t i = operations.size(); i-- > 0;) {
+      TaskInfo& t = ssn.Tasks[operations[i].task];
+      if (operations[i].evict) unevict(t); else unpipeline(t);
+    }
+    operations.clear();
+  }
+  void Commit() {                                                         // :206-217 (cache.Evict never fails here)
+    for (auto& op : operations) if (op.evict) ssn.record_evict(ssn.Tasks[op.task]);
+    operations.clear();
+  }
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -674,6 +817,13 @@ struct priorityPlugin : Plugin {
       if (lv.Priority > rv.Priority) return -1;
       if (lv.Priority < rv.Priority) return 1;
       return 0;
+    };
+    ssn->preemptableFns[Name()] = [ssn](const TaskInfo& preemptor, const std::vector<uint32_t>& preemptees) {   // :81-100
+      const JobInfo& preemptorJob = ssn->Jobs[preemptor.Job];
+      std::vector<uint32_t> victims;
+      for (uint32_t id : preemptees)
+        if (!(ssn->Jobs[ssn->Tasks[id].Job].Priority >= preemptorJob.Priority)) victims.push_back(id);
+      return victims;
     };
   }
 };
@@ -693,6 +843,19 @@ struct gangPlugin : Plugin {
       return 0;
     };
     ssn->jobReadyFns[Name()] = [ssn](const JobInfo& ji) { return ssn->Ready(ji); };  // :122-125
+    auto preemptableFn = [ssn](const TaskInfo&, const std::vector<uint32_t>& preemptees) {                // :70-90
+      std::vector<uint32_t> victims;
+      for (uint32_t id : preemptees) {
+        const JobInfo& job = ssn->Jobs[ssn->Tasks[id].Job];
+        const int32_t occupid = ssn->ReadyTaskNum(job);
+        const bool preemptable = job.MinAvailable <= occupid - 1 || job.MinAvailable == 1;
+        if (preemptable) victims.push_back(id);
+      }
+      return victims;
+    };
+    ssn->reclaimableFns[Name()] = preemptableFn;                                                           // :93
+    ssn->preemptableFns[Name()] = preemptableFn;                                                           // :94
+    ssn->jobPipelinedFns[Name()] = [ssn](const JobInfo& ji) { return ssn->JobInfoPipelined(ji); };        // :126-129
   }
 };
 
@@ -732,6 +895,27 @@ struct drfPlugin : Plugin {
       ssn->A.Add(attr.allocated, task.Resreq);
       attr.share = calculateShare(ssn, attr.allocated, totalResource);
     });
+    ssn->deallocateHandlers.push_back([this, ssn](const TaskInfo& task) {        // :145-153
+      drfAttr& attr = jobOpts[task.Job];
+      if (!ssn->A.Sub(attr.allocated, task.Resreq)) g_err = "panic: Resource is not sufficient to do operation (drf DeallocateFunc)";
+      attr.share = calculateShare(ssn, attr.allocated, totalResource);
+    });
+    ssn->preemptableFns[Name()] = [this, ssn](const TaskInfo& preemptor, const std::vector<uint32_t>& preemptees) {   // :84-110
+      std::vector<uint32_t> victims;
+      Resource lalloc = jobOpts[preemptor.Job].allocated;
+      ssn->A.Add(lalloc, preemptor.Resreq);
+      const double ls = calculateShare(ssn, lalloc, totalResource);
+      std::map<uint32_t, Resource> allocations;
+      for (uint32_t id : preemptees) {
+        const TaskInfo& preemptee = ssn->Tasks[id];
+        if (!allocations.count(preemptee.Job)) allocations[preemptee.Job] = jobOpts[preemptee.Job].allocated;
+        Resource& ralloc = allocations[preemptee.Job];
+        if (!ssn->A.Sub(ralloc, preemptee.Resreq)) { g_err = "panic: Resource is not sufficient to do operation (drf preemptableFn)"; break; }
+        const double rs = calculateShare(ssn, ralloc, totalResource);
+        if (ls < rs || std::fabs(ls - rs) <= 0.000001) victims.push_back(id);     // shareDelta, drf.go:31
+      }
+      return victims;
+    };
   }
 };
 
@@ -808,6 +992,26 @@ struct proportionPlugin : Plugin {
       ssn->A.Add(attr.allocated, task.Resreq);
       updateShare(ssn, attr);
     });
+    ssn->deallocateHandlers.push_back([this, ssn](const TaskInfo& task) {         // :223-232
+      queueAttr& attr = queueOpts[ssn->Jobs[task.Job].Queue];
+      if (!ssn->A.Sub(attr.allocated, task.Resreq)) g_err = "panic: Resource is not sufficient to do operation (proportion DeallocateFunc)";
+      updateShare(ssn, attr);
+    });
+    ssn->reclaimableFns[Name()] = [this, ssn](const TaskInfo&, const std::vector<uint32_t>& reclaimees) {   // :171-196
+      std::vector<uint32_t> victims;
+      std::map<uint32_t, Resource> allocations;
+      for (uint32_t id : reclaimees) {
+        const TaskInfo& reclaimee = ssn->Tasks[id];
+        const uint32_t q = ssn->Jobs[reclaimee.Job].Queue;
+        queueAttr& attr = queueOpts[q];
+        if (!allocations.count(q)) allocations[q] = attr.allocated;
+        Resource& allocated = allocations[q];
+        if (ssn->A.Less(allocated, reclaimee.Resreq)) continue;                     // "not enough resource"
+        if (!ssn->A.Sub(allocated, reclaimee.Resreq)) { g_err = "panic: Resource is not sufficient to do operation (proportion reclaimableFn)"; break; }
+        if (ssn->A.LessEqual(attr.deserved, allocated)) victims.push_back(id);
+      }
+      return victims;
+    };
   }
 };
 
@@ -909,7 +1113,15 @@ struct nodeOrderPlugin : Plugin {
 
 struct conformancePlugin : Plugin {   // plugins/conformance/conformance.go:41-63 — evictable filter only
   std::string Name() const override { return "conformance"; }
-  void OnSessionOpen(Session*) override {}
+  void OnSessionOpen(Session* ssn) override {
+    auto evictableFn = [ssn](const TaskInfo&, const std::vector<uint32_t>& evictees) {
+      std::vector<uint32_t> victims;
+      for (uint32_t id : evictees) if (!ssn->Tasks[id].critical) victims.push_back(id);   // system-critical class / kube-system
+      return victims;
+    };
+    ssn->preemptableFns[Name()] = evictableFn;
+    ssn->reclaimableFns[Name()] = evictableFn;
+  }
 };
 
 // plugins/factory.go:31-42
@@ -935,7 +1147,7 @@ int check_snapshot(const kb_snapshot* s) {
   return KB_OK;
 }
 
-int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, std::unique_ptr<Session>& out) {
+int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, std::unique_ptr<Session>& out, const kbo_running* run = nullptr) {
   int rc = check_snapshot(s);
   if (rc) return rc;
   auto ssn = std::make_unique<Session>(s->R, s->W);
@@ -1044,6 +1256,31 @@ int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, st
       }
       ti.Status = Pending;
       ji.TaskStatusIndex[Pending].insert(t);
+    }
+  }
+
+  // Running tasks, one by one (reclaim / preempt walk node.Tasks): the node and job aggregates of the snapshot already count
+  // them, so they only join job.TaskStatusIndex[Running] (moving out of the ready0 aggregate) and node.Tasks.
+  if (run && run->n) {
+    ssn->Tasks.resize((size_t)T + run->n);
+    for (uint32_t i = 0; i < run->n; ++i) {
+      TaskInfo& ti = ssn->Tasks[(size_t)T + i];
+      ti.idx = T + i;
+      if (run->job[i] >= J || run->node[i] >= N) { g_err = "kbo_running: job / node index out of range"; return KB_E_BADARG; }
+      ti.Job = run->job[i];
+      for (uint32_t r = 0; r < R; ++r) ti.Resreq.v[r] = ti.InitResreq.v[r] = run->resreq[(size_t)r * run->n + i];
+      ti.Resreq.present = ti.InitResreq.present = run->res_present[i] & ~3u;
+      ti.Priority = run->prio[i]; ti.ctime = run->ctime[i]; ti.uid_rank = run->uid_rank[i];
+      ti.critical = (run->flags[i] & 1u) != 0;
+      ti.n_aff = ti.n_pref = 0;
+      for (uint32_t w = 0; w < KB_MAX_W; ++w) { ti.sel_req[w] = ti.tol[w] = ti.port_own[w] = ti.port_conflict[w] = 0; for (auto& a : ti.aff) a[w] = 0; for (auto& a : ti.pref) a[w] = 0; }
+      ti.Status = Running;
+      ti.NodeName = (int)run->node[i];
+      JobInfo& ji = ssn->Jobs[ti.Job];
+      if (ji.ready0 <= 0) { g_err = "kbo_running: job_ready0 does not cover the job's running tasks"; return KB_E_BADARG; }
+      ji.ready0 -= 1;
+      ji.TaskStatusIndex[Running].insert(ti.idx);
+      ssn->Nodes[run->node[i]].Tasks[ti.idx] = ti;
     }
   }
 
@@ -1292,6 +1529,177 @@ void ExecuteBackfill(Session& ssn, kbo_result& res) {
   res.tasks_pipelined = ssn.n_pipelined;
 }
 
+// Running tasks of a node that `filter` accepts, in ascending TaskInfo.UID (node.Tasks is a Go map in the reference)
+template <class F>
+std::vector<uint32_t> node_running_tasks(Session& ssn, const NodeInfo& node, F filter) {
+  std::vector<uint32_t> ids;
+  for (auto& kv : node.Tasks) if (kv.second.Status == Running && filter(kv.second)) ids.push_back(kv.first);   // the NODE's clone decides
+  std::sort(ids.begin(), ids.end(), [&](uint32_t a, uint32_t b) { return ssn.Tasks[a].uid_rank < ssn.Tasks[b].uid_rank; });
+  return ids;
+}
+
+// actions/reclaim/reclaim.go:40-193.  Deterministic rules: ssn.Jobs in ascending JobID, ssn.Nodes in ascending Name,
+// node.Tasks in ascending UID.
+void ExecuteReclaim(Session& ssn, kbo_result& res) {
+  PriorityQueue<uint32_t> queues([&](const uint32_t& l, const uint32_t& r) { return ssn.QueueOrderFn(ssn.Queues[l], ssn.Queues[r]); });
+  std::set<uint32_t> queueMap;
+  std::map<uint32_t, PriorityQueue<uint32_t>> preemptorsMap, preemptorTasks;
+  auto jobLess = [&](const uint32_t& l, const uint32_t& r) { return ssn.JobOrderFn(ssn.Jobs[l], ssn.Jobs[r]); };
+  auto taskLess = [&](const uint32_t& l, const uint32_t& r) { return ssn.TaskOrderFn(ssn.Tasks[l], ssn.Tasks[r]); };
+  for (auto& job : ssn.Jobs) {                                            // :53-81
+    if (!queueMap.count(job.Queue)) { queueMap.insert(job.Queue); queues.Push(job.Queue); }
+    auto pit = job.TaskStatusIndex.find(Pending);
+    if (pit != job.TaskStatusIndex.end() && !pit->second.empty()) {
+      if (!preemptorsMap.count(job.Queue)) preemptorsMap.emplace(job.Queue, PriorityQueue<uint32_t>(jobLess));
+      preemptorsMap.at(job.Queue).Push(job.idx);
+      PriorityQueue<uint32_t> tasks(taskLess);
+      for (uint32_t id : pit->second) tasks.Push(id);
+      preemptorTasks.emplace(job.idx, std::move(tasks));
+    }
+  }
+  for (;;) {                                                              // :83
+    if (queues.Empty()) break;
+    const uint32_t q = queues.Pop();
+    if (ssn.Overused(ssn.Queues[q])) continue;                            // :93-96
+    auto jit = preemptorsMap.find(q);
+    if (jit == preemptorsMap.end() || jit->second.Empty()) continue;      // :99-103
+    const uint32_t j = jit->second.Pop();
+    auto tit = preemptorTasks.find(j);
+    if (tit == preemptorTasks.end() || tit->second.Empty()) continue;     // :106-110
+    TaskInfo& task = ssn.Tasks[tit->second.Pop()];
+    const JobInfo& job = ssn.Jobs[j];
+    ++res.tasks_processed;
+    res.pairs_logical += ssn.Nodes.size();
+    bool assigned = false;
+    for (auto& n : ssn.Nodes) {                                           // :113
+      if (!ssn.PredicateFn(task, n, n.pods, n.ports)) continue;           // :115-117
+      const Resource resreq = task.InitResreq;
+      Resource reclaimed;
+      std::vector<uint32_t> reclaimees = node_running_tasks(ssn, n, [&](const TaskInfo& t) { return ssn.Jobs[t.Job].Queue != job.Queue; });   // :125-138
+      std::vector<uint32_t> victims = ssn.Reclaimable(task, reclaimees);
+      if (victims.empty()) continue;                                      // :141-144
+      Resource allRes;
+      for (uint32_t v : victims) ssn.A.Add(allRes, ssn.Tasks[v].Resreq);
+      if (!ssn.A.LessEqual(resreq, allRes)) continue;                     // :147-154
+      for (uint32_t v : victims) {                                        // :157-170
+        TaskInfo& reclaimee = ssn.Tasks[v];
+        ssn.EvictTask(reclaimee, true);
+        ssn.A.Add(reclaimed, reclaimee.Resreq);
+        if (ssn.A.LessEqual(resreq, reclaimed)) break;
+      }
+      if (ssn.A.LessEqual(task.InitResreq, reclaimed)) {                  // :175-185
+        ssn.Pipeline(task, n);
+        assigned = true;
+        break;
+      }
+    }
+    if (assigned) queues.Push(q);                                         // :188-190
+  }
+  res.tasks_pipelined = ssn.n_pipelined;
+}
+
+// actions/preempt/preempt.go:171-252
+bool preempt_one(Session& ssn, Executor& ex, Statement& stmt, TaskInfo& preemptor, const std::function<bool(const TaskInfo&)>& filter,
+                 kbo_result& res) {
+  bool assigned = false;
+  ++res.tasks_processed;
+  res.pairs_logical += ssn.Nodes.size();
+  std::vector<uint32_t> predicateNodes;                                   // util.PredicateNodes(preemptor, allNodes, ssn.PredicateFn)
+  for (auto& n : ssn.Nodes) if (ssn.PredicateFn(preemptor, n, n.pods, n.ports)) predicateNodes.push_back(n.idx);
+  std::vector<double> priorityList;
+  ex.PrioritizeNodes(preemptor, predicateNodes, ssn.NodePrioritizers(), priorityList);
+  // util.SortNodes: sort.Sort(sort.Reverse(priorityList)) — not stable in Go; deterministic rule: score descending, then node order
+  std::vector<size_t> order(predicateNodes.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) { return priorityList[a] > priorityList[b]; });
+  for (size_t oi : order) {
+    NodeInfo& node = ssn.Nodes[predicateNodes[oi]];
+    Resource preempted;
+    const Resource resreq = preemptor.InitResreq;
+    std::vector<uint32_t> preemptees = node_running_tasks(ssn, node, filter);      // :195-201 (filter sees the node's clone)
+    std::vector<uint32_t> victims = ssn.Preemptable(preemptor, preemptees);
+    {                                                                                // validateVictims :254-270
+      if (victims.empty()) continue;
+      Resource allRes;
+      for (uint32_t v : victims) ssn.A.Add(allRes, ssn.Tasks[v].Resreq);
+      if (!ssn.A.LessEqual(resreq, allRes)) continue;
+    }
+    PriorityQueue<uint32_t> victimsQueue([&](const uint32_t& l, const uint32_t& r) { return !ssn.TaskOrderFn(ssn.Tasks[l], ssn.Tasks[r]); });   // :210-215
+    for (uint32_t v : victims) victimsQueue.Push(v);
+    while (!victimsQueue.Empty()) {                                       // :217-231: lowest priority first
+      TaskInfo& preemptee = ssn.Tasks[victimsQueue.Pop()];
+      stmt.Evict(preemptee);
+      ssn.A.Add(preempted, preemptee.Resreq);
+      if (ssn.A.LessEqual(resreq, preempted)) break;
+    }
+    if (ssn.A.LessEqual(preemptor.InitResreq, preempted)) {               // :237-247
+      stmt.Pipeline(preemptor, node);
+      assigned = true;
+      break;
+    }
+  }
+  return assigned;
+}
+
+// actions/preempt/preempt.go:43-167.  Deterministic rules as above; `queues` (a Go map) in ascending QueueID.
+void ExecutePreempt(Session& ssn, const kbo_opts& opts, kbo_result& res) {
+  Executor ex(ssn, opts.threads);
+  auto jobLess = [&](const uint32_t& l, const uint32_t& r) { return ssn.JobOrderFn(ssn.Jobs[l], ssn.Jobs[r]); };
+  auto taskLess = [&](const uint32_t& l, const uint32_t& r) { return ssn.TaskOrderFn(ssn.Tasks[l], ssn.Tasks[r]); };
+  std::map<uint32_t, PriorityQueue<uint32_t>> preemptorsMap, preemptorTasks;
+  std::vector<uint32_t> underRequest;
+  std::set<uint32_t> queues;
+  for (auto& job : ssn.Jobs) {                                            // :54-75
+    queues.insert(job.Queue);
+    auto pit = job.TaskStatusIndex.find(Pending);
+    if (pit != job.TaskStatusIndex.end() && !pit->second.empty()) {
+      if (!preemptorsMap.count(job.Queue)) preemptorsMap.emplace(job.Queue, PriorityQueue<uint32_t>(jobLess));
+      preemptorsMap.at(job.Queue).Push(job.idx);
+      underRequest.push_back(job.idx);
+      PriorityQueue<uint32_t> tasks(taskLess);
+      for (uint32_t id : pit->second) tasks.Push(id);
+      preemptorTasks.emplace(job.idx, std::move(tasks));
+    }
+  }
+  for (uint32_t q : queues) {                                             // :78 Preemption between Jobs within Queue
+    for (;;) {
+      auto pit = preemptorsMap.find(q);
+      if (pit == preemptorsMap.end() || pit->second.Empty()) break;       // :83-86
+      const uint32_t pj = pit->second.Pop();
+      JobInfo& preemptorJob = ssn.Jobs[pj];
+      Statement stmt(ssn);
+      bool assigned = false;
+      for (;;) {
+        PriorityQueue<uint32_t>& tasks = preemptorTasks.at(pj);
+        if (tasks.Empty()) break;                                         // :95-99
+        TaskInfo& preemptor = ssn.Tasks[tasks.Pop()];
+        if (preempt_one(ssn, ex, stmt, preemptor, [&](const TaskInfo& task) {   // :103-116
+              if (task.Status != Running) return false;
+              return ssn.Jobs[task.Job].Queue == preemptorJob.Queue && preemptor.Job != task.Job;
+            }, res)) assigned = true;
+        if (ssn.JobPipelined(preemptorJob)) { stmt.Commit(); break; }     // :121-124
+      }
+      if (!ssn.JobPipelined(preemptorJob)) { stmt.Discard(); continue; }  // :128-131
+      if (assigned) pit->second.Push(pj);                                 // :133-135
+    }
+    for (uint32_t uj : underRequest) {                                    // :139 Preemption between Task within Job
+      for (;;) {
+        auto tit = preemptorTasks.find(uj);
+        if (tit == preemptorTasks.end() || tit->second.Empty()) break;
+        TaskInfo& preemptor = ssn.Tasks[tit->second.Pop()];
+        Statement stmt(ssn);
+        const bool assigned = preempt_one(ssn, ex, stmt, preemptor, [&](const TaskInfo& task) {   // :152-159
+          if (task.Status != Running) return false;
+          return preemptor.Job == task.Job;
+        }, res);
+        stmt.Commit();
+        if (!assigned) break;                                             // :163-165
+      }
+    }
+  }
+  res.tasks_pipelined = ssn.n_pipelined;
+}
+
 Resource mkres(uint32_t R, const double* v, uint32_t present) {
   Resource r;
   for (uint32_t k = 0; k < R && k < KB_MAX_R; ++k) r.v[k] = v[k];
@@ -1309,17 +1717,18 @@ extern "C" {
 
 const char* kbo_last_error(void) { return g_err.c_str(); }
 
-int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_opts* opts_in,
-                 kb_decision* out, kbo_result* res_out,
-                 double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
-                 int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
-                 double* job_share, int32_t* job_ready, double* queue_share,
-                 double* queue_deserved, double* queue_allocated) {
+int kbo_cycle(const kb_snapshot* snap, const kbo_running* running, const kb_plugin_conf* conf, const kbo_opts* opts_in,
+              const uint8_t* action_list, uint32_t n_actions,
+              kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kbo_result* res_out,
+              double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+              int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+              double* job_share, int32_t* job_ready, double* queue_share,
+              double* queue_deserved, double* queue_allocated) {
   g_err.clear();
   kbo_opts opts{};
   if (opts_in) opts = *opts_in;
   std::unique_ptr<Session> ssn;
-  int rc = build_session(snap, conf, opts.mode, ssn);
+  int rc = build_session(snap, conf, opts.mode, ssn, running);
   if (rc) return rc;
   if (opts.mode == KBO_MODE_FAITHFUL) {
     const uint32_t Nn = (uint32_t)ssn->Nodes.size();
@@ -1334,9 +1743,24 @@ int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_
       for (int32_t i = 0; i < j.ready0 && Nn > 0; ++i) ssn->placeholder_alloc[j.idx].push_back((uint32_t)(((uint64_t)(k++) * 2654435761ull) % Nn));
   }
   kbo_result res{};
-  const int actions = opts.actions ? opts.actions : KBO_ACTION_ALLOCATE;
-  if (actions & KBO_ACTION_ALLOCATE) Execute(*ssn, opts, res);
-  if (actions & KBO_ACTION_BACKFILL) ExecuteBackfill(*ssn, res);
+  bool backfill_ran = false;
+  for (uint32_t i = 0; i < n_actions; ++i) {
+    switch (action_list[i]) {
+      case KBO_ACT_RECLAIM: ExecuteReclaim(*ssn, res); break;
+      case KBO_ACT_ALLOCATE: Execute(*ssn, opts, res); break;
+      case KBO_ACT_BACKFILL: ExecuteBackfill(*ssn, res); backfill_ran = true; break;
+      case KBO_ACT_PREEMPT: ExecutePreempt(*ssn, opts, res); break;
+      default: g_err = "unknown action"; return KB_E_BADARG;
+    }
+  }
+  res.tasks_allocated = ssn->n_allocated;
+  res.tasks_pipelined = ssn->n_pipelined;
+  res.evictions = ssn->n_evicted;
+  if (running) for (uint32_t i = 0; i < running->n; ++i) {
+    const TaskInfo& ti = ssn->Tasks[(size_t)snap->T + i];
+    if (evicted) evicted[i] = ti.evicted ? 1 : 0;
+    if (evict_order) evict_order[i] = ti.evict_order;
+  }
   // bench metric (BASELINE.json): PodGroups that received a placement in this cycle and are JobReady at its end
   res.jobs_ready = 0;
   for (auto& job : ssn->Jobs) {
@@ -1350,11 +1774,11 @@ int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_
     for (uint32_t t = 0; t < T; ++t) {
       const TaskInfo& ti = ssn->Tasks[t];
       kb_decision d{};
-      d.node = ti.NodeName;
+      d.node = (ti.Status == Pending) ? -1 : ti.NodeName;     // an un-pipelined preemptor keeps a stale NodeName (statement.go:153-188)
       d.step = ti.step;
       d.dispatch_step = ti.dispatch_step;
       d.dispatched = ti.dispatched ? 1 : 0;
-      const bool bf = (actions & KBO_ACTION_BACKFILL) != 0;
+      const bool bf = backfill_ran;
       if (ti.Status == Pending) d.kind = ssn->A.IsEmpty(ti.Resreq) ? ((bf && ssn->A.IsEmpty(ti.InitResreq)) ? KB_KIND_NONE : KB_KIND_SKIPPED) : KB_KIND_NONE;
       else if (ti.Status == Pipelined) d.kind = KB_KIND_PIPELINED;
       else d.kind = KB_KIND_ALLOCATED;
@@ -1389,6 +1813,20 @@ int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_
   if (res_out) *res_out = res;
   if (!g_err.empty()) return KB_E_STATE;
   return KB_OK;
+}
+
+int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_opts* opts_in,
+                 kb_decision* out, kbo_result* res_out,
+                 double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                 int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                 double* job_share, int32_t* job_ready, double* queue_share,
+                 double* queue_deserved, double* queue_allocated) {
+  const int actions = (opts_in && opts_in->actions) ? opts_in->actions : KBO_ACTION_ALLOCATE;
+  uint8_t list[2]; uint32_t n = 0;
+  if (actions & KBO_ACTION_ALLOCATE) list[n++] = KBO_ACT_ALLOCATE;
+  if (actions & KBO_ACTION_BACKFILL) list[n++] = KBO_ACT_BACKFILL;
+  return kbo_cycle(snap, nullptr, conf, opts_in, list, n, out, nullptr, nullptr, res_out, node_idle, node_releasing, node_used, node_pods,
+                   node_nz_cpu, node_nz_mem, node_ports, job_share, job_ready, queue_share, queue_deserved, queue_allocated);
 }
 
 int kbo_predicate_score(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t task,

@@ -10,6 +10,9 @@
  * stale keys, the rand tie-break, plugin arithmetic) is "parity unpinned" by the reference
  * and defined by the deterministic rules of SURVEY.md §8c.
  *
+ * Beyond the allocate path it also restates backfill (kb_backfill's oracle) and, ORACLE ONLY so far, NodeAffinityPriority
+ * with preferred terms, reclaim and preempt (kbo_cycle) — pinned on preempt_test.go / reclaim_test.go.
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
  * may load this library.  libkbgpu.so never links or calls it.
  */
@@ -43,6 +46,25 @@ typedef struct kbo_opts {
 #define KBO_ACTION_ALLOCATE 1
 #define KBO_ACTION_BACKFILL 2
 
+/* ---- the other two actions of the reference, ORACLE ONLY so far: the engine has no kb_reclaim /
+ * kb_preempt yet.  They need what the flattened snapshot only carries as aggregates: the Running tasks, one by one. ---- */
+typedef struct kbo_running {
+  uint32_t n;                  /* Running tasks (api.Running) that sit on a node of the snapshot                         */
+  const uint32_t* node;        /* [n] node index                                                                          */
+  const uint32_t* job;         /* [n] job index (the job's job_ready0 / job_alloc0 already count the task)                */
+  const double*   resreq;      /* [R][n] TaskInfo.Resreq                                                                  */
+  const uint32_t* res_present; /* [n] scalar presence                                                                     */
+  const int32_t*  prio;        /* [n] TaskInfo.Priority                                                                   */
+  const int64_t*  ctime;       /* [n] Pod.CreationTimestamp                                                               */
+  const uint32_t* uid_rank;    /* [n] rank of TaskInfo.UID among the running tasks                                        */
+  const uint32_t* flags;       /* [n] bit 0: system-critical priority class or kube-system namespace (conformance.go:45-53) */
+} kbo_running;
+
+#define KBO_ACT_RECLAIM  0 /* actions/reclaim/reclaim.go   */
+#define KBO_ACT_ALLOCATE 1 /* actions/allocate/allocate.go */
+#define KBO_ACT_BACKFILL 2 /* actions/backfill/backfill.go */
+#define KBO_ACT_PREEMPT  3 /* actions/preempt/preempt.go   */
+
 typedef struct kbo_result {
   uint64_t pairs_logical;    /* sum over processed tasks of N                                      */
   uint32_t tasks_processed;
@@ -51,6 +73,8 @@ typedef struct kbo_result {
   uint32_t jobs_ready;
   uint32_t visits;
   uint32_t truncated;        /* 1 if max_tasks / max_seconds stopped the cycle early               */
+  uint32_t evictions;        /* cache.Evict calls (util.FakeEvictor.Evicts)                        */
+  uint32_t reserved;
   double   seconds;          /* wall time of Execute                                               */
 } kbo_result;
 
@@ -63,6 +87,18 @@ int kbo_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, const kbo_
                  int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
                  double* job_share, int32_t* job_ready, double* queue_share,
                  double* queue_deserved, double* queue_allocated);
+
+/* One scheduling cycle: the actions of `actions[0..n_actions)` in that order on ONE session (scheduler.go:88-101; the
+ * shipped configuration is "reclaim, allocate, backfill, preempt", config/kube-batch-conf.yaml:1).  `running` may be NULL
+ * (then reclaim / preempt find no victims).  evicted / evict_order [running->n]: cache.Evict calls in call order.
+ * The other outputs are those of kbo_allocate. */
+int kbo_cycle(const kb_snapshot* snap, const kbo_running* running, const kb_plugin_conf* conf, const kbo_opts* opts,
+              const uint8_t* actions, uint32_t n_actions,
+              kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kbo_result* res,
+              double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+              int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+              double* job_share, int32_t* job_ready, double* queue_share,
+              double* queue_deserved, double* queue_allocated);
 
 /* predicateFn + PrioritizeNodes of one task against the snapshot's initial node state. */
 int kbo_predicate_score(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t task,

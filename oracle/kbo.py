@@ -32,7 +32,7 @@ class kbo_result(C.Structure):
     _fields_ = [
         ("pairs_logical", C.c_uint64), ("tasks_processed", C.c_uint32), ("tasks_allocated", C.c_uint32),
         ("tasks_pipelined", C.c_uint32), ("jobs_ready", C.c_uint32), ("visits", C.c_uint32),
-        ("truncated", C.c_uint32), ("seconds", C.c_double),
+        ("truncated", C.c_uint32), ("evictions", C.c_uint32), ("reserved", C.c_uint32), ("seconds", C.c_double),
     ]
 
 
@@ -130,6 +130,62 @@ def allocate(snap: Snapshot, conf: PluginConf, mode: int = KBO_MODE_OPTIMISED, t
         raise RuntimeError(f"kbo_allocate rc={rc}: {L.kbo_last_error().decode()}")
     out.decisions = dec[:T]
     return out
+
+
+class kbo_running(C.Structure):
+    _fields_ = [("n", C.c_uint32), ("node", C.POINTER(C.c_uint32)), ("job", C.POINTER(C.c_uint32)), ("resreq", C.POINTER(C.c_double)),
+                ("res_present", C.POINTER(C.c_uint32)), ("prio", C.POINTER(C.c_int32)), ("ctime", C.POINTER(C.c_int64)),
+                ("uid_rank", C.POINTER(C.c_uint32)), ("flags", C.POINTER(C.c_uint32))]
+
+
+ACTIONS = {"reclaim": 0, "allocate": 1, "backfill": 2, "preempt": 3}      # KBO_ACT_*
+
+
+def cycle(snap: Snapshot, conf: PluginConf, actions=("allocate",), running: Optional[dict] = None, threads: int = 1):
+    """One scheduling cycle on ONE session: `actions` in order (scheduler.go:88-101).  `running` = the table of Running tasks
+    (builder.flatten() puts it into snap.meta["running"]); needed by reclaim / preempt.  Returns (OracleOut, evicted, evict_order)."""
+    L = lib()
+    cs, keep1 = snap.to_c()
+    cc, keep2 = conf.to_c()
+    o = kbo_opts(KBO_MODE_OPTIMISED, threads, 0, 0.0, 0, 0)
+    R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
+    dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+    res = kbo_result()
+    out = OracleOut(
+        decisions=dec, result=res,
+        node_idle=np.zeros((R, N)), node_releasing=np.zeros((R, N)), node_used=np.zeros((R, N)),
+        node_pods=np.zeros(N, dtype=np.int32), node_nz_cpu=np.zeros(N, dtype=np.int64),
+        node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
+        job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
+        queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
+    run = None
+    nrun = 0
+    keep3 = []
+    if running is not None and len(running["node"]):
+        nrun = len(running["node"])
+        arrs = {k: np.ascontiguousarray(running[k], dtype=dt) for k, dt in
+                (("node", np.uint32), ("job", np.uint32), ("resreq", np.float64), ("res_present", np.uint32), ("prio", np.int32),
+                 ("ctime", np.int64), ("uid_rank", np.uint32), ("flags", np.uint32))}
+        assert arrs["resreq"].shape == (R, nrun)
+        keep3 = list(arrs.values())
+        run = kbo_running(nrun, _p(arrs["node"], C.c_uint32), _p(arrs["job"], C.c_uint32), _p(arrs["resreq"], C.c_double),
+                          _p(arrs["res_present"], C.c_uint32), _p(arrs["prio"], C.c_int32), _p(arrs["ctime"], C.c_int64),
+                          _p(arrs["uid_rank"], C.c_uint32), _p(arrs["flags"], C.c_uint32))
+    evicted = np.zeros(max(nrun, 1), dtype=np.uint8)
+    order = np.zeros(max(nrun, 1), dtype=np.uint32)
+    acts = np.array([ACTIONS[a] for a in actions], dtype=np.uint8)
+    rc = L.kbo_cycle(C.byref(cs), C.byref(run) if run is not None else None, C.byref(cc), C.byref(o),
+                     _p(acts, C.c_uint8), C.c_uint32(len(acts)), dec.ctypes.data_as(C.c_void_p), _p(evicted, C.c_uint8), _p(order, C.c_uint32),
+                     C.byref(res),
+                     _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
+                     _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
+                     _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
+                     _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double), _p(out.queue_allocated, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"kbo_cycle rc={rc}: {L.kbo_last_error().decode()}")
+    out.decisions = dec[:T]
+    del keep3
+    return out, evicted[:nrun].astype(bool), order[:nrun]
 
 
 def predicate_score(snap: Snapshot, conf: PluginConf, task: int):

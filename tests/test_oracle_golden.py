@@ -8,6 +8,7 @@ import pytest
 
 from kube_batch_b200 import builder as B
 from kube_batch_b200.snapshot import PluginConf, PluginOption
+from kube_batch_b200 import abi
 from oracle import kbo
 
 S1, S2 = 2, 3          # dims: 0 cpu, 1 memory, 2 "scalar.test/scalar1", 3 "hugepages-test"
@@ -272,3 +273,137 @@ def test_engine_side_still_refuses_preferred_node_affinity():
     s = _pref_session([B.Pod("ns", "p", "", "Pending", {"cpu": 1}, group="g", preferred_terms=[(1, [("zone", "In", ["a"])])])])
     with pytest.raises(RuntimeError, match="preferred node affinity"):
         util.emu_allocate(s, PluginConf.default())       # the engine's host build (kb_build.h) is what the emulation runs
+
+
+# ---------------- preempt / reclaim: ORACLE ONLY so far; pinned on the reference's own action tests ----------------
+def _evict_session(pods, node_res, queues, groups):
+    from kube_batch_b200 import builder as B
+    b = B.SessionBuilder()
+    for g, q in groups:
+        b.add_pod_group(B.PodGroup("c1", g, q))
+    for name, node, phase, group in pods:
+        b.add_pod(B.build_pod("c1", name, node, phase, B.build_resource_list("1", "1G"), group))
+    b.add_node(B.build_node("n1", B.build_resource_list(*node_res)))
+    for q in queues:
+        b.add_queue(B.Queue(q, 1))
+    return b.flatten()
+
+
+def test_preempt_golden():
+    """preempt_test.go:51-144 — tiers conformance + gang with EnabledPreemptable; expected = number of cache.Evict calls."""
+    from kube_batch_b200.snapshot import PluginConf, PluginOption
+    tiers = PluginConf([[PluginOption("conformance", enabled_preemptable=True), PluginOption("gang", enabled_preemptable=True)]])
+    # "one Job with two Pods on one node" (:51-85): expected 1
+    s = _evict_session([("preemptee1", "n1", "Running", "pg1"), ("preemptee2", "n1", "Running", "pg1"),
+                        ("preemptor1", "", "Pending", "pg1"), ("preemptor2", "", "Pending", "pg1")], ("3", "3Gi"), ["q1"], [("pg1", "q1")])
+    o, ev, order = kbo.cycle(s, tiers, actions=("preempt",), running=s.meta["running"])
+    assert o.result.evictions == 1 and int(ev.sum()) == 1
+    assert (o.decisions["kind"] == 2).sum() == 1          # one preemptor pipelined onto the freed resources
+    # "two Jobs on one node" (:86-144): expected 2
+    s = _evict_session([("preemptee1", "n1", "Running", "pg1"), ("preemptee2", "n1", "Running", "pg1"),
+                        ("preemptor1", "", "Pending", "pg2"), ("preemptor2", "", "Pending", "pg2")], ("2", "2G"), ["q1"],
+                       [("pg1", "q1"), ("pg2", "q1")])
+    o, ev, order = kbo.cycle(s, tiers, actions=("preempt",), running=s.meta["running"])
+    assert o.result.evictions == 2 and ev.all() and sorted(order.tolist()) == [0, 1]
+    assert (o.decisions["kind"] == 2).all() and not o.decisions["dispatched"].any()
+
+
+def test_reclaim_golden():
+    """reclaim_test.go:51-105 — two queues, q1 holds the whole node, a pending task of q2 reclaims one pod: expected 1."""
+    from kube_batch_b200.snapshot import PluginConf, PluginOption
+    tiers = PluginConf([[PluginOption("conformance", enabled_reclaimable=True), PluginOption("gang", enabled_reclaimable=True)]])
+    s = _evict_session([("preemptee1", "n1", "Running", "pg1"), ("preemptee2", "n1", "Running", "pg1"), ("preemptee3", "n1", "Running", "pg1"),
+                        ("preemptor1", "", "Pending", "pg2")], ("3", "3Gi"), ["q1", "q2"], [("pg1", "q1"), ("pg2", "q2")])
+    o, ev, order = kbo.cycle(s, tiers, actions=("reclaim",), running=s.meta["running"])
+    assert o.result.evictions == 1 and ev.tolist() == [True, False, False]      # node.Tasks in UID order, first victim suffices
+    assert int(o.decisions["kind"][0]) == 2 and int(o.decisions["node"][0]) == 0
+    assert o.node_releasing[0, 0] == 0.0 and o.node_used[0, 0] == 4000.0          # evicted pod still counted in Used + the pipelined one
+
+
+def test_gang_protects_min_available_and_priority_orders_victims():
+    """Hand-computed: gang refuses victims whose job would drop below MinAvailable (gang.go:70-90); among the victims the
+    lowest-priority task goes first (preempt.go:210-231); a discarded statement leaves no trace (statement.go:191-203)."""
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf, PluginOption
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "held", "q", min_member=2))      # 2 running, MinAvailable 2 -> not preemptable (2 <= 2-1 is false)
+    b.add_pod_group(B.PodGroup("ns", "loose", "q", min_member=1))     # MinAvailable == 1 -> preemptable
+    b.add_pod_group(B.PodGroup("ns", "want", "q", min_member=1))
+    b.add_node(B.Node("n0", {"cpu": 4, "memory": 16e9, "pods": 10}))
+    req = {"cpu": 1, "memory": 1e9}
+    b.add_pod(B.Pod("ns", "h0", "n0", "Running", req, group="held"))
+    b.add_pod(B.Pod("ns", "h1", "n0", "Running", req, group="held"))
+    b.add_pod(B.Pod("ns", "l-hi", "n0", "Running", req, group="loose", priority=9))
+    b.add_pod(B.Pod("ns", "l-lo", "n0", "Running", req, group="loose", priority=1))
+    b.add_pod(B.Pod("ns", "w0", "", "Pending", req, group="want"))
+    b.add_pod(B.Pod("ns", "w-big", "", "Pending", {"cpu": 3, "memory": 1e9}, group="want", creation=5))
+    s = b.flatten()
+    tiers = PluginConf([[PluginOption("priority", enabled_task_order=True), PluginOption("gang", enabled_preemptable=True, enabled_job_pipelined=True),
+                         PluginOption("conformance", enabled_preemptable=True)]])
+    o, ev, order = kbo.cycle(s, tiers, actions=("preempt",), running=s.meta["running"])
+    names = s.meta["running"]["names"]
+    evicted = {names[i] for i in range(len(names)) if ev[i]}
+    # w0 (created first) preempts the lowest-priority loose pod; w-big needs 3 cpu but only l-hi (1 cpu) is left as a victim -> nothing
+    assert evicted == {"ns/l-lo"}
+    t = {s.meta["tasks"][i]: i for i in range(s.T)}
+    assert int(o.decisions["kind"][t["ns/w0"]]) == 2 and int(o.decisions["kind"][t["ns/w-big"]]) == 0
+    assert int(o.decisions["node"][t["ns/w-big"]]) == -1
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_full_action_list_keeps_the_books_balanced(seed):
+    """"reclaim, allocate, backfill, preempt" (config/kube-batch-conf.yaml:1) on random clusters with Running, terminating and
+    Pending pods in several queues: whatever the actions decide, the node / eviction bookkeeping must stay consistent."""
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf
+    rng = np.random.default_rng(4000 + seed)
+    b = B.SessionBuilder()
+    nq = int(rng.integers(1, 4))
+    for q in range(nq):
+        b.add_queue(B.Queue(f"q{q}", int(rng.integers(1, 4))))
+    nn = int(rng.integers(2, 9))
+    for n in range(nn):
+        b.add_node(B.Node(f"n{n}", {"cpu": 8, "memory": 32e9, "pods": 12}))
+    cap = {f"n{n}": 8.0 for n in range(nn)}
+    pods = []
+    for g in range(int(rng.integers(2, 9))):
+        b.add_pod_group(B.PodGroup("ns", f"g{g}", f"q{int(rng.integers(0, nq))}", min_member=int(rng.integers(0, 4)), priority=int(rng.integers(0, 3))))
+        cpu = float(rng.choice([0.5, 1, 2]))
+        for k in range(int(rng.integers(1, 7))):
+            state = rng.choice(["Running", "Running", "Pending", "Pending", "Deleting"])
+            node = ""
+            if state != "Pending":
+                free = [n for n, c in cap.items() if c >= cpu]
+                if not free:
+                    state = "Pending"
+                else:
+                    node = str(rng.choice(free))
+                    cap[node] -= cpu
+            p = B.Pod("ns", f"g{g}-p{k}", node, "Pending" if state == "Pending" else "Running", {"cpu": cpu, "memory": cpu * 1e9},
+                      group=f"g{g}", priority=int(rng.integers(0, 3)), creation=len(pods), deleting=(state == "Deleting"))
+            pods.append(p)
+            b.add_pod(p)
+    s = b.flatten()
+    o, ev, order = kbo.cycle(s, PluginConf.default(), actions=("reclaim", "allocate", "backfill", "preempt"), running=s.meta["running"])
+    k = int(ev.sum())
+    assert o.result.evictions == k and sorted(order[ev].tolist()) == list(range(k))
+    # per node: Allocatable = Idle + Used - (pipelined tasks); Releasing = terminating + evicted - pipelined >= 0
+    rt = s.meta["running"]
+    pip = np.zeros((s.R, s.N)); rel = np.zeros((s.R, s.N))
+    d = o.decisions
+    for t in np.nonzero(d["kind"] == abi.KB_KIND_PIPELINED)[0]:
+        pip[:, d["node"][t]] += s.task_resreq[:, t]
+    for i in np.nonzero(ev)[0]:
+        rel[:, rt["node"][i]] += rt["resreq"][:, i]
+    for p in pods:
+        if p.deleting:
+            n = s.meta["nodes"].index(p.node_name)
+            rel[0, n] += p.requests["cpu"] * 1000
+            rel[1, n] += p.requests["memory"]
+    np.testing.assert_allclose(o.node_idle + o.node_used - pip, s.node_allocatable, rtol=0, atol=1e-3)
+    np.testing.assert_allclose(o.node_releasing, rel - pip, rtol=0, atol=1e-3)
+    assert (o.node_idle >= -1e-6).all() and (o.node_releasing >= -1e-6).all()
+    placed = d["kind"] != abi.KB_KIND_NONE
+    assert (d["node"][(d["kind"] == abi.KB_KIND_ALLOCATED) | (d["kind"] == abi.KB_KIND_PIPELINED)] >= 0).all()
+    assert (d["node"][d["kind"] == abi.KB_KIND_NONE] == -1).all() and placed.sum() >= 0
