@@ -416,7 +416,7 @@ class SessionBuilder:
             s.task_ctime[t] = p.creation
             s.task_uid_rank[t] = uid_rank[p.uid or f"{p.namespace}-{p.name}"]
         s.job_task_off[:] = np.cumsum(counts).astype(np.uint32)
-        # ---- Running tasks one by one (only the oracle's reclaim / preempt read them: oracle/kb_oracle.h kbo_running) ----
+        # ---- Running tasks one by one: what reclaim / preempt walk (node.Tasks); not part of kb_snapshot yet ----
         running = [p for p in self.pods if self._task_status(p) == "Running" and f"{p.namespace}/{p.group}" in jidx and p.node_name in nidx]
         ruids = sorted((p.uid or f"{p.namespace}-{p.name}") for p in running)
         rrank = {u: i for i, u in enumerate(ruids)}
