@@ -407,3 +407,72 @@ def test_full_action_list_keeps_the_books_balanced(seed):
     placed = d["kind"] != abi.KB_KIND_NONE
     assert (d["node"][(d["kind"] == abi.KB_KIND_ALLOCATED) | (d["kind"] == abi.KB_KIND_PIPELINED)] >= 0).all()
     assert (d["node"][d["kind"] == abi.KB_KIND_NONE] == -1).all() and placed.sum() >= 0
+
+
+def test_proportion_reclaims_only_what_exceeds_the_deserved_share():
+    """Hand-computed (proportion.go:171-196): a reclaimee is a victim only while its queue's allocation, minus everything already
+    counted, stays >= deserved IN EVERY DIMENSION.  Two queues of weight 1 on one node of 8 cpu / 8 GB: deserved = 4 cpu / 4 GB each
+    (both request more).  q-rich runs 6 x (1 cpu, 1 GB): only the first two reclaimees (allocated 6 -> 5 -> 4) are victims."""
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf, PluginOption
+
+    def session(cpu):
+        b = B.SessionBuilder()
+        b.add_queue(B.Queue("q-poor", 1))
+        b.add_queue(B.Queue("q-rich", 1))
+        b.add_pod_group(B.PodGroup("ns", "rich", "q-rich", min_member=1))
+        b.add_pod_group(B.PodGroup("ns", "poor", "q-poor", min_member=1))
+        b.add_node(B.Node("n0", {"cpu": 8, "memory": 8e9, "pods": 20}))
+        for i in range(6):
+            b.add_pod(B.Pod("ns", f"r{i}", "n0", "Running", {"cpu": 1, "memory": 1e9}, group="rich"))
+        for i in range(4):
+            b.add_pod(B.Pod("ns", f"p{i}", "", "Pending", {"cpu": cpu, "memory": cpu * 1e9}, group="poor", creation=i))
+        return b.flatten()
+
+    tiers = PluginConf([[PluginOption("gang", enabled_reclaimable=True), PluginOption("proportion", enabled_reclaimable=True, enabled_queue_order=True)]])
+    s = session(3)
+    o, ev, order = kbo.cycle(s, tiers, actions=("reclaim",), running=s.meta["running"])
+    # water-filling: total 8 cpu; requests rich 6, poor 12 -> 4 / 4, nothing left
+    np.testing.assert_array_equal(o.queue_deserved[0], [4000.0, 4000.0])
+    # p0 needs 3 cpu: the victims on n0 are r0, r1 only (2 cpu) -> "not enough resource from victims": nothing evicted
+    assert o.result.evictions == 0 and (o.decisions["kind"] == 0).all()
+    # a 2-cpu task: the two victims suffice; both are evicted, the task is pipelined; reclaim pops ONE task per job visit and does
+    # not push the job back, so p1..p3 are never tried
+    s = session(2)
+    o, ev, order = kbo.cycle(s, tiers, actions=("reclaim",), running=s.meta["running"])
+    names = s.meta["running"]["names"]
+    assert {names[i] for i in np.nonzero(ev)[0]} == {"ns/r0", "ns/r1"} and o.result.evictions == 2
+    assert (o.decisions["kind"] == 2).sum() == 1 and int(o.decisions["kind"][0]) == 2
+    np.testing.assert_array_equal(o.queue_allocated[0], [2000.0, 4000.0])      # q-poor got 2 cpu pipelined, q-rich gave 2 back
+
+
+def test_drf_preempts_only_towards_a_fairer_split():
+    """Hand-computed (drf.go:84-110): preemptee is a victim iff the preemptor job's share AFTER gaining its task is <= the preemptee
+    job's share AFTER losing that task (cumulatively per job).  10-cpu node: job big runs 6 x 1 cpu (share 0.6), job small runs 1
+    (0.1) and wants one more: ls = 0.2; big: 0.5 (victim), 0.4 (victim), ... 0.2 -> victim while rs >= 0.2 - 1e-6: four tasks."""
+    from kube_batch_b200 import builder as B
+    from kube_batch_b200.snapshot import PluginConf, PluginOption
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "big", "q", min_member=1))
+    b.add_pod_group(B.PodGroup("ns", "small", "q", min_member=1))
+    b.add_node(B.Node("n0", {"cpu": 10, "memory": 100e9, "pods": 20}))
+    for i in range(6):
+        b.add_pod(B.Pod("ns", f"b{i}", "n0", "Running", {"cpu": 1, "memory": 1e9}, group="big"))
+    b.add_pod(B.Pod("ns", "s-run", "n0", "Running", {"cpu": 1, "memory": 1e9}, group="small"))
+    b.add_pod(B.Pod("ns", "s-new", "", "Pending", {"cpu": 4, "memory": 1e9}, group="small"))
+    s = b.flatten()
+    tiers = PluginConf([[PluginOption("drf", enabled_preemptable=True, enabled_job_order=True)]])
+    o, ev, order = kbo.cycle(s, tiers, actions=("preempt",), running=s.meta["running"])
+    # s-new needs 4 cpu: ls = (1+4)/10 = 0.5; big after losing k tasks: 0.5, 0.4, ... -> only the FIRST preemptee (rs 0.5 >= ls 0.5) is a
+    # victim: 1 cpu < 4 cpu -> validateVictims fails -> nothing happens
+    assert o.result.evictions == 0 and int(o.decisions["kind"][0]) == 0
+    # a 1-cpu preemptor: ls = 0.2; victims b0..b3 (rs 0.5, 0.4, 0.3, 0.2); one eviction is enough
+    b.pods[-1] = B.Pod("ns", "s-new", "", "Pending", {"cpu": 1, "memory": 1e9}, group="small")
+    s = b.flatten()
+    o, ev, order = kbo.cycle(s, tiers, actions=("preempt",), running=s.meta["running"])
+    assert o.result.evictions == 1 and int(o.decisions["kind"][0]) == 2
+    # the victims queue pops the LOWEST TaskOrderFn task first: equal priority / creation -> highest UID among b0..b3
+    names = s.meta["running"]["names"]
+    assert {names[i] for i in np.nonzero(ev)[0]} == {"ns/b3"}
+    np.testing.assert_allclose(o.job_share, [0.5, 0.2])
