@@ -86,7 +86,7 @@ typedef struct kb_snapshot {
   uint32_t reserved0;       /* 0 */
 
   /* ---- nodes (api.NodeInfo, api/node_info.go:28-47) ---- */
-  const double*   node_idle;          /* [R][N] NodeInfo.Idle                                        */
+  const double*   node_idle;          /* [R][N] NodeInfo.Idle; >= -epsilon (the cache never over-commits a node), else KB_E_BADARG */
   const double*   node_releasing;     /* [R][N] NodeInfo.Releasing                                   */
   const double*   node_used;          /* [R][N] NodeInfo.Used (bookkeeping; returned by kb_node_state) */
   const double*   node_allocatable;   /* [R][N] NodeInfo.Allocatable as float64 (drf.go:62-64, proportion.go:60-62) */

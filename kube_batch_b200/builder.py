@@ -211,6 +211,22 @@ class SessionBuilder:
         return v, present
 
     @staticmethod
+    def _less_equal(l, lpresent: int, r, rpresent: int) -> bool:
+        """Resource.LessEqual (resource_info.go:268-302) on dense vectors + scalar-presence masks."""
+        def le(a, b, diff):
+            return a < b or abs(a - b) < diff
+        if not le(l[0], r[0], 10.0) or not le(l[1], r[1], 10.0 * 1024 * 1024):
+            return False
+        for k in range(2, len(l)):
+            if not (lpresent >> k) & 1 or l[k] <= 10.0:
+                continue
+            if (rpresent >> 2) == 0:
+                return False
+            if not le(l[k], r[k] if (rpresent >> k) & 1 else 0.0, 10.0):
+                return False
+        return True
+
+    @staticmethod
     def _task_status(p: Pod) -> str:
         """api.getTaskStatus (api/helpers.go:38-62)."""
         if p.phase == "Running":
@@ -322,6 +338,7 @@ class SessionBuilder:
             mem = int(p.requests["memory"]) if "memory" in p.requests else DEFAULT_MEMORY_REQUEST
             return int(cpu), int(mem)
 
+        on_node = set()                     # pods node.AddTask accepted
         for p in self.pods:
             st = self._task_status(p)
             key = f"{p.namespace}/{p.group}"
@@ -336,6 +353,11 @@ class SessionBuilder:
                     s.job_ready0[j] += 1
             if p.node_name and p.node_name in nidx and st != "Pending":
                 i = nidx[p.node_name]
+                # cache.addTask: the job has the task (above); node.AddTask refuses what does not fit into Idle
+                # (allocateIdleResource, node_info.go:161-167), so a snapshot never carries an over-committed node
+                if st != "Pipelined" and not self._less_equal(v, present, s.node_idle[:, i], int(s.node_alloc_present[i])):
+                    continue
+                on_node.add(id(p))
                 # api.NodeInfo.AddTask (node_info.go:172-212)
                 if st == "Releasing":
                     s.node_idle[:, i] -= v
@@ -417,7 +439,7 @@ class SessionBuilder:
             s.task_uid_rank[t] = uid_rank[p.uid or f"{p.namespace}-{p.name}"]
         s.job_task_off[:] = np.cumsum(counts).astype(np.uint32)
         # ---- Running tasks one by one: what reclaim / preempt walk (node.Tasks); not part of kb_snapshot yet ----
-        running = [p for p in self.pods if self._task_status(p) == "Running" and f"{p.namespace}/{p.group}" in jidx and p.node_name in nidx]
+        running = [p for p in self.pods if self._task_status(p) == "Running" and f"{p.namespace}/{p.group}" in jidx and id(p) in on_node]
         ruids = sorted((p.uid or f"{p.namespace}-{p.name}") for p in running)
         rrank = {u: i for i, u in enumerate(ruids)}
         rt = {"node": np.array([nidx[p.node_name] for p in running], dtype=np.uint32),

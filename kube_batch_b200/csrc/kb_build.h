@@ -276,6 +276,15 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     if (s->job_queue[j] >= Q) return bfail(e, KB_E_BADARG, "job %u: queue %u does not exist (cache.Snapshot drops such jobs, cache.go:652-656)", j, s->job_queue[j]);
   }
   if (J && (s->job_task_off[0] != 0 || s->job_task_off[J] != T)) return bfail(e, KB_E_BADARG, "job_task_off must cover [0,T)");
+  // The reference's cache never hands out an over-committed node: node.AddTask refuses a task that does not fit into Idle
+  // (api/node_info.go:161-167), so Idle >= -epsilon.  Outside that domain ssn.Allocate's "status first, node second" order
+  // (framework/session.go:235-262) becomes observable, which this engine does not model.
+  for (uint32_t n = 0; n < N; ++n)
+    for (uint32_t r = 0; r < R; ++r) {
+      const double eps = r == 0 ? KB_MIN_MILLI_CPU : r == 1 ? KB_MIN_MEMORY : KB_MIN_MILLI_SCALAR;
+      if (s->node_idle[(size_t)r * N + n] <= -eps)
+        return bfail(e, KB_E_BADARG, "node %u: Idle is negative in dim %u (over-committed node: the reference cache would not produce it)", n, r);
+    }
   std::vector<ClassRec> classes;
   std::vector<uint32_t> task_class(T, 0);
   std::vector<uint8_t> task_empty(T, 0);

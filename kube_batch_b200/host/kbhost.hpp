@@ -52,6 +52,20 @@ struct Resource {                                     // api/resource_info.go:28
   }
   Resource& Add(const Resource& rr) { MilliCPU += rr.MilliCPU; Memory += rr.Memory; for (auto& kv : rr.ScalarResources) ScalarResources[kv.first] += kv.second; return *this; }
   Resource& SubUnchecked(const Resource& rr) { MilliCPU -= rr.MilliCPU; Memory -= rr.Memory; for (auto& kv : rr.ScalarResources) ScalarResources[kv.first] -= kv.second; return *this; }
+  // Resource.LessEqual (resource_info.go:268-302): epsilons 10 m / 10 Mi / 10; scalars <= 10 are skipped; a nil map on the
+  // right makes any larger scalar fail
+  bool LessEqual(const Resource& rr) const {
+    auto le = [](double l, double r, double diff) { return l < r || std::fabs(l - r) < diff; };
+    if (!le(MilliCPU, rr.MilliCPU, 10.0)) return false;
+    if (!le(Memory, rr.Memory, 10.0 * 1024 * 1024)) return false;
+    for (auto& kv : ScalarResources) {
+      if (kv.second <= 10.0) continue;
+      if (rr.ScalarResources.empty()) return false;
+      auto it = rr.ScalarResources.find(kv.first);
+      if (!le(kv.second, it == rr.ScalarResources.end() ? 0.0 : it->second, 10.0)) return false;
+    }
+    return true;
+  }
   void SetMaxResource(const Resource& rr) { MilliCPU = std::max(MilliCPU, rr.MilliCPU); Memory = std::max(Memory, rr.Memory);
     for (auto& kv : rr.ScalarResources) { auto& x = ScalarResources[kv.first]; x = std::max(x, kv.second); } }
 };
@@ -208,7 +222,13 @@ struct SchedulerCache {                               // the literal cache of al
     auto j = getOrCreateJob(pod.Namespace, pod.GroupName);
     t->Job = j->UID;
     j->AddTaskInfo(t);
-    if (!pod.NodeName.empty() && Nodes.count(pod.NodeName) && t->Status != api::Pending) Nodes[pod.NodeName]->AddTask(t);
+    // cache.addTask (cache/event_handlers.go): the job gets the task, then node.AddTask — which refuses a task that does not
+    // fit into Idle (allocateIdleResource, node_info.go:161-167; a Pipelined task takes Releasing instead), so a node is never
+    // over-committed in the snapshot
+    if (!pod.NodeName.empty() && Nodes.count(pod.NodeName) && t->Status != api::Pending) {
+      auto& n = *Nodes[pod.NodeName];
+      if (t->Status == api::Pipelined || t->Resreq.LessEqual(n.Idle)) n.AddTask(t);
+    }
   }
   ClusterInfo Snapshot() const {                      // cache/cache.go:627-683 (objects are shared, not deep-copied)
     ClusterInfo ci;

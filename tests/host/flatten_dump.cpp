@@ -37,6 +37,7 @@ int main() {
   {
     api::Pod p = pod("r0", "n0", "Running", {{"cpu", 2}, {"memory", 4 * G}}, "old", 1); p.HostPorts = {{"", "TCP", 8080}}; sc.AddPod(p);
     p = pod("r1", "n1", "Running", {{"cpu", 3}, {"memory", 6 * G}}, "old", 2); p.Deleting = true; sc.AddPod(p);
+    p = pod("r2", "n2", "Running", {{"cpu", 6}, {"memory", 1 * G}}, "old", 3); sc.AddPod(p);      // 6 cpu on a 4-cpu node: node.AddTask refuses it
     p = pod("a0", "", "Pending", {{"cpu", 1}, {"memory", 1 * G}}, "pgA", 10); p.NodeSelector = {{"zone", "b"}};
     p.Tolerations = {{"dedicated", "Equal", "batch", "NoSchedule"}}; sc.AddPod(p);
     p = pod("a1", "", "Pending", {{"cpu", 1}, {"memory", 1 * G}}, "pgA", 11); p.NodeSelector = {{"zone", "b"}}; p.HostPorts = {{"", "TCP", 8080}}; sc.AddPod(p);

@@ -257,6 +257,15 @@ def test_backfill_first_feasible_node_pod_cap_and_gang():
     assert o.node_pods.tolist() == [3, 4]
 
 
+def test_over_committed_node_is_refused():
+    # Idle < -epsilon cannot come out of the reference's cache (node.AddTask refuses what does not fit); the load says so
+    s = synth.random_session(3, tasks=20, jobs=3, nodes=5)
+    s.node_idle[0, 2] = -500.0
+    s.invalidate()
+    with pytest.raises(RuntimeError, match="over-committed"):
+        util.emu_allocate(s, PluginConf.default())
+
+
 def test_unknown_plugin_is_refused():
     s, _ = synth.make("c1")
     bad = PluginConf.from_names([["gang", "my-custom-plugin"]])

@@ -63,6 +63,7 @@ def test_cpp_flatten_matches_the_python_specification():
     b.add_pod_group(B.PodGroup("ns", "pgB", "q2", 1, priority=7, creation=5))
     b.add_pod(B.Pod("ns", "r0", "n0", "Running", {"cpu": 2, "memory": 4 * G}, group="old", creation=1, host_ports=[("", "TCP", 8080)]))
     b.add_pod(B.Pod("ns", "r1", "n1", "Running", {"cpu": 3, "memory": 6 * G}, group="old", creation=2, deleting=True))
+    b.add_pod(B.Pod("ns", "r2", "n2", "Running", {"cpu": 6, "memory": 1 * G}, group="old", creation=3))   # does not fit: stays off the node
     b.add_pod(B.Pod("ns", "a0", "", "Pending", {"cpu": 1, "memory": 1 * G}, group="pgA", creation=10, node_selector={"zone": "b"},
                     tolerations=[("dedicated", "Equal", "batch", "NoSchedule")]))
     b.add_pod(B.Pod("ns", "a1", "", "Pending", {"cpu": 1, "memory": 1 * G}, group="pgA", creation=11, node_selector={"zone": "b"},
@@ -91,5 +92,6 @@ def test_cpp_flatten_matches_the_python_specification():
     assert np.array_equal(np.asarray(got["rel_selector"], bool).reshape(T, N), sel)
     assert np.array_equal(np.asarray(got["rel_tolerated"], bool).reshape(T, N), tol)
     assert np.array_equal(np.asarray(got["rel_port_conflict"], bool).reshape(T, N), con)
+    assert s.node_pods.tolist() == [1, 1, 0] and s.job_ready0.tolist() == [2, 0, 0]      # r2 counts for its job, not for n2
     # sanity of the fixture itself: a1's wildcard 8080/TCP collides with r0's on n0; b1's 10.0.0.1:8080 collides with that wildcard too
     assert con[1, 0] and con[3, 0] and not con[0].any()
