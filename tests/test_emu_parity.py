@@ -273,3 +273,26 @@ def test_unknown_plugin_is_refused():
         util.emu_allocate(s, bad)
     with pytest.raises(RuntimeError):
         kbo.allocate(s, bad)
+
+
+def test_known_divergence_phantom_allocated_best_effort_task():
+    """DESIGN §8b "known divergence".  ssn.Allocate sets the task's status to Allocated BEFORE node.AddTask (framework/session.go:
+    241-262); when AddTask refuses the task on every node that passed the predicates, the reference leaves a task that is Allocated
+    but sits on no node.  Only a best-effort task with a NON-ZERO request below the IsEmpty epsilons can get there (a truly empty
+    Resreq always passes Resreq <= Idle because Idle > -epsilon).  The oracle reproduces the phantom, the engine reports the task as
+    unplaced (kind NONE): this test pins exactly that difference so that it cannot grow silently."""
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "g", "q", min_member=1))
+    b.add_node(B.Node("n0", {"cpu": 1, "memory": 4e9, "pods": 10}))
+    b.add_pod(B.Pod("ns", "full", "n0", "Running", {"cpu": 1, "memory": 1e9}, group="g"))        # Idle cpu = 0
+    b.add_pod(B.Pod("ns", "tiny-a", "", "Pending", {"cpu": 0.005}, group="g", creation=1))        # 5 m: IsEmpty, yet not zero
+    b.add_pod(B.Pod("ns", "tiny-b", "", "Pending", {"cpu": 0.005}, group="g", creation=2))
+    s = b.flatten()
+    conf = PluginConf.from_names([["gang"], ["predicates"]])
+    o = kbo.allocate(s, conf, actions=3)
+    e = util.emu_allocate(s, conf, actions=3, mode=1)
+    # tiny-a: 5 <= 0 within epsilon -> placed, Idle becomes -5.  tiny-b: |5 - (-5)| = 10 is not < 10 -> AddTask refuses it.
+    assert o.decisions["kind"].tolist() == [abi.KB_KIND_ALLOCATED, abi.KB_KIND_ALLOCATED] and o.decisions["node"].tolist() == [0, -1]
+    assert e.decisions["kind"].tolist() == [abi.KB_KIND_ALLOCATED, abi.KB_KIND_NONE] and e.decisions["node"].tolist() == [0, -1]
+    np.testing.assert_array_equal(o.node_idle, e.node_idle)          # the node bookkeeping itself is identical

@@ -74,3 +74,23 @@ def test_sharded_node_axis_matches_oracle(world, case):
         p.join(timeout=60)
     for rank, status, scans in sorted(res):
         assert status == "ok", (rank, status)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_node_axis_in_process(world):
+    """Same protocol with all ranks emulated in one process (the all-gather is a concatenation): cheap enough for many sessions,
+    including more ranks than tiles and the allocate + backfill pair."""
+    import util
+    from oracle import kbo
+    from test_emu_parity import CONFS
+    for seed in range(10):
+        rng = np.random.default_rng(9000 + seed)
+        s = synth.random_session(800 + seed, tasks=int(rng.integers(5, 300)), jobs=int(rng.integers(1, 30)), nodes=int(rng.integers(1, 700)),
+                                 queues=int(rng.integers(1, 4)), min_member_frac=float(rng.choice([0, .5, 1])), hetero=float(rng.choice([0, .3, 1])))
+        cname = list(CONFS)[seed % len(CONFS)]
+        for actions in (1, 3):
+            o = kbo.allocate(s, CONFS[cname], actions=actions)
+            for r, e in enumerate(util.emu_sharded_inprocess(s, CONFS[cname], world, actions=actions)):
+                util.assert_same_decisions(o.decisions, e.decisions, f"seed{seed}/{cname}/a{actions}/world{world}/rank{r}")
+                ns, os_ = util.emu_states(e)
+                util.assert_same_state(o, ns, os_, f"seed{seed}/{cname}/a{actions}/world{world}/rank{r}")

@@ -159,3 +159,71 @@ def emu_sharded_rank(rank: int, world: int, port: int, snap: Snapshot, conf: Plu
         return out
     finally:
         dist.destroy_process_group()
+
+
+def emu_sharded_inprocess(snap: Snapshot, conf: PluginConf, world: int, actions: int = 1):
+    """The sharded scan -> all-gather -> replay chain with all `world` ranks emulated in THIS process (the all-gather is a
+    concatenation).  Returns one result container per rank; every rank must hold the identical, complete result."""
+    L = emu_lib()
+    L.kbemu_create.restype = C.c_void_p
+    L.kbemu_create.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.kbemu_buf_u64.argtypes = [C.c_void_p]
+    L.kbemu_buf_u64.restype = C.c_uint32
+    for f in ("kbemu_scan", "kbemu_replay"):
+        getattr(L, f).argtypes = [C.c_void_p, C.c_void_p]
+        getattr(L, f).restype = None
+    L.kbemu_done.argtypes = [C.c_void_p]
+    L.kbemu_destroy.argtypes = [C.c_void_p]
+    L.kbemu_begin_backfill.argtypes = [C.c_void_p, C.c_int]
+    L.kbemu_begin_backfill.restype = None
+    L.kbemu_finish.argtypes = [C.c_void_p] + [C.c_void_p] * 14
+    cs, k1 = snap.to_c()
+    cc, k2 = conf.to_c()
+    hs = []
+    try:
+        for r in range(world):
+            h = L.kbemu_create(C.addressof(cs), C.addressof(cc), r, world)
+            if not h:
+                raise RuntimeError(L.kbemu_last_error().decode())
+            hs.append(h)
+        n = L.kbemu_buf_u64(hs[0])
+        send = [np.zeros(n, dtype=np.uint64) for _ in range(world)]
+        guard = 0
+        for bit in (1, 2):
+            if not (actions & bit):
+                continue
+            if bit == 2:
+                for h in hs:
+                    L.kbemu_begin_backfill(h, 1 if (actions & 1) else 0)
+            while not L.kbemu_done(hs[0]):
+                for r, h in enumerate(hs):
+                    L.kbemu_scan(h, send[r].ctypes.data)
+                recv = np.concatenate(send)                  # == ncclAllGather / the peer-memory exchange
+                for h in hs:
+                    L.kbemu_replay(h, recv.ctypes.data)
+                guard += 1
+                assert guard < 10_000_000
+            assert all(L.kbemu_done(h) for h in hs), "ranks disagree on the end of the cycle"
+        outs = []
+        R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
+        for h in hs:
+            dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+            st = abi.kb_stats()
+            out = kbo.OracleOut(
+                decisions=dec, result=st,
+                node_idle=np.zeros((R, N)), node_releasing=np.zeros((R, N)), node_used=np.zeros((R, N)),
+                node_pods=np.zeros(N, dtype=np.int32), node_nz_cpu=np.zeros(N, dtype=np.int64),
+                node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
+                job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
+                queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
+            L.kbemu_finish(h, dec.ctypes.data, C.addressof(st), out.node_idle.ctypes.data, out.node_releasing.ctypes.data,
+                           out.node_used.ctypes.data, out.node_pods.ctypes.data, out.node_nz_cpu.ctypes.data,
+                           out.node_nz_mem.ctypes.data, out.node_ports.ctypes.data, out.job_share.ctypes.data,
+                           out.job_ready.ctypes.data, out.queue_share.ctypes.data, out.queue_deserved.ctypes.data,
+                           out.queue_allocated.ctypes.data)
+            out.decisions = dec[:T]
+            outs.append(out)
+        return outs
+    finally:
+        for h in hs:
+            L.kbemu_destroy(h)
