@@ -60,6 +60,7 @@ inline bool parse_bool(const char* s, bool* out) {          // strconv.ParseBool
 struct HostConf {
   EvalConf cf{};
   uint32_t jobcmp[4] = {0, 0, 0, 0};
+  int w_nodeaff = 1;                // nodeaffinity.weight (nodeorder.go:111-117); only read when the session has preferred terms
   bool task_order_priority = false, queue_order_proportion = false, proportion_present = false, drf_present = false,
        gang_ready = false;
 };
@@ -121,7 +122,8 @@ inline int resolve_conf(BuildErr* e, const kb_plugin_conf* conf, uint32_t R, uin
   hc.drf_present = have[P_DRF];
   hc.cf.mem_pressure = memp; hc.cf.disk_pressure = diskp; hc.cf.pid_pressure = pidp;
   hc.cf.w_least = w_least; hc.cf.w_most = w_most; hc.cf.w_balanced = w_bal;
-  (void)w_nodeaff; (void)w_podaff;    // their Map/Function results are identically 0 without preferred terms
+  hc.w_nodeaff = w_nodeaff;           // NodeAffinityPriority is identically 0 without preferred terms
+  (void)w_podaff;                     // InterPodAffinityPriority: tasks with such terms are refused
   const long lim = 1 << 20;
   if (labs(w_least) > lim || labs(w_most) > lim || labs(w_bal) > lim) return bfail(e, KB_E_BADARG, "nodeorder weight out of range");
   hc.cf.score_bias = 10ll * ((w_least < 0 ? -w_least : 0) + (w_most < 0 ? -w_most : 0) + (w_bal < 0 ? -w_bal : 0));
@@ -207,6 +209,8 @@ struct BuiltSession {
   std::vector<int32_t> job_min_avail;
   uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1, overlap = 0;
   uint32_t kchain = 1;               // classes per launch (visit_chain_kernel), 1 = off
+  std::vector<ClassPref> class_pref; // [C] preferred node-affinity terms per class — HOST ONLY (read by tests/emu's prototype of
+  bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
 
   // The BACKFILL VIEW of the same session (backfillAction.Execute, actions/backfill/backfill.go:40-71): same node table,
@@ -258,7 +262,8 @@ struct BuiltSession {
 // Everything kb_session_load does before touching the device.  `max_grid` = scan CTAs (SM count).
 inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e,
                          uint32_t rank = 0, uint32_t world = 1, int overlap_mode = -1 /* -1 auto, 0 off, 1 on */,
-                         uint32_t kchain = 1 /* classes per launch: 1, 2 or 4 (single GPU, no overlap) */) {
+                         uint32_t kchain = 1 /* classes per launch: 1, 2 or 4 (single GPU, no overlap) */,
+                         bool allow_pref = false /* accept preferred node-affinity terms (tests/emu prototype only) */) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
@@ -286,6 +291,20 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         return bfail(e, KB_E_BADARG, "node %u: Idle is negative in dim %u (over-committed node: the reference cache would not produce it)", n, r);
     }
   std::vector<ClassRec> classes;
+  std::vector<ClassPref>& class_pref = B.class_pref;
+  class_pref.clear(); B.has_pref = false;
+  auto pref_of = [&](uint32_t t) {
+    ClassPref cp;
+    memset(&cp, 0, sizeof cp);
+    if (!(s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY)) return cp;
+    if (!s->task_n_pref_terms || !s->task_pref_terms || !s->task_pref_weights) { cp.n = 0xFFFFFFFFu; return cp; }   // reported by the caller
+    cp.n = s->task_n_pref_terms[t];
+    for (uint32_t p = 0; p < cp.n && p < KB_MAX_PREF_TERMS; ++p) {
+      cp.weight[p] = s->task_pref_weights[(size_t)p * T + t];
+      for (uint32_t w = 0; w < W; ++w) cp.term[p][w] = s->task_pref_terms[((size_t)p * W + w) * T + t];
+    }
+    return cp;
+  };
   std::vector<uint32_t> task_class(T, 0);
   std::vector<uint8_t> task_empty(T, 0);
   {
@@ -307,6 +326,10 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     auto same_as_prev = [&](uint32_t t) {
       if (s->task_flags[t] != s->task_flags[t - 1] || s->task_n_aff_terms[t] != s->task_n_aff_terms[t - 1] ||
           s->task_nz_cpu[t] != s->task_nz_cpu[t - 1] || s->task_nz_mem[t] != s->task_nz_mem[t - 1]) return false;
+      if (s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) {
+        const ClassPref a = pref_of(t), b = pref_of(t - 1);
+        if (memcmp(&a, &b, sizeof a) != 0) return false;
+      }
       for (uint32_t r = 0; r < R; ++r) {
         const size_t i = (size_t)r * T + t;
         if (bits(s->task_initreq, i) != bits(s->task_initreq, i - 1) || bits(s->task_resreq, i) != bits(s->task_resreq, i - 1)) return false;
@@ -328,8 +351,13 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         task_class[t] = prev_class; task_empty[t] = task_empty[t - 1];
         continue;
       }
-      if (s->task_flags[t] & (KB_TASK_HAS_POD_AFFINITY | KB_TASK_HAS_PREFERRED_NODE_AFFINITY))
+      if ((s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY) || ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && !allow_pref))
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod / preferred node affinity terms: outside this build (no CPU fallback)", t);
+      ClassPref cp = pref_of(t);
+      if (cp.n) {
+        if (cp.n > KB_MAX_PREF_TERMS) return bfail(e, KB_E_BADARG, "task %u: preferred node-affinity arrays missing or n_pref_terms > KB_MAX_PREF_TERMS", t);
+        B.has_pref = true;
+      }
       if (s->task_n_aff_terms[t] > KB_MAX_AFF_TERMS) return bfail(e, KB_E_BADARG, "task %u: n_aff_terms > KB_MAX_AFF_TERMS", t);
       ClassRec c;
       memset(&c, 0, sizeof c);
@@ -349,18 +377,20 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         for (uint32_t a = 0; a < c.n_aff; ++a) c.aff[a][w] = s->task_aff_terms[((size_t)a * W + w) * T + t];
       }
       task_empty[t] = res_is_empty(R, [&](uint32_t k) { return c.resreq[k]; }) ? 1 : 0;   // allocate.go:113-118
-      if (prev_class != 0xFFFFFFFFu && memcmp(&classes[prev_class], &c, sizeof c) == 0) { task_class[t] = prev_class; continue; }
-      const uint64_t h = hash_rec(c);
+      if (prev_class != 0xFFFFFFFFu && memcmp(&classes[prev_class], &c, sizeof c) == 0 && memcmp(&class_pref[prev_class], &cp, sizeof cp) == 0) {
+        task_class[t] = prev_class; continue; }
+      uint64_t h = hash_rec(c);
+      if (cp.n) { const uint64_t* w = reinterpret_cast<const uint64_t*>(&cp); for (size_t i = 0; i < sizeof(ClassPref) / 8; ++i) h = (h ^ w[i]) * 0xFF51AFD7ED558CCDull + (h >> 29); }
       size_t mask = table.size() - 1, slot = (size_t)h & mask;
       uint32_t found = 0xFFFFFFFFu;
       while (table[slot] != 0xFFFFFFFFu) {
         const uint32_t id = table[slot];
-        if (class_hash[id] == h && memcmp(&classes[id], &c, sizeof c) == 0) { found = id; break; }
+        if (class_hash[id] == h && memcmp(&classes[id], &c, sizeof c) == 0 && memcmp(&class_pref[id], &cp, sizeof cp) == 0) { found = id; break; }
         slot = (slot + 1) & mask;
       }
       if (found == 0xFFFFFFFFu) {
         found = (uint32_t)classes.size();
-        classes.push_back(c); class_hash.push_back(h);
+        classes.push_back(c); class_pref.push_back(cp); class_hash.push_back(h);
         table[slot] = found;
         if (classes.size() * 2 > table.size()) {            // grow + rehash
           std::vector<uint32_t> nt(table.size() * 4, 0xFFFFFFFFu);
@@ -373,7 +403,11 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
       prev_class = found;
     }
   }
-  if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); }
+  if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); ClassPref cp; memset(&cp, 0, sizeof cp); class_pref.push_back(cp); }
+  static_assert(sizeof(ClassPref) % 8 == 0, "ClassPref is hashed as 64-bit words");
+  if (B.has_pref && (world > 1 || kchain > 1 || overlap_mode > 0))
+    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node affinity: only the plain single-rank launch mode is prototyped");
+  if (B.has_pref) hc.cf.score_bias += 10ll * (hc.w_nodeaff < 0 ? -(int64_t)hc.w_nodeaff : 0);
   const uint32_t C = (uint32_t)classes.size();
 
   // ---------------- per-job TaskOrderFn order (session_plugins.go:318-331, priority.go:40-56) ----------------
@@ -656,6 +690,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   // overlap pays when the scan side (several tile groups per CTA + a wide merge) rivals the replay side
   B.overlap = (world <= 1) ? (overlap_mode < 0 ? ((N >= 65536 && Q == 1) ? 1u : 0u) : (uint32_t)overlap_mode) : 0u;
+  if (B.has_pref) B.overlap = 0;
   B.kchain = (world <= 1 && !B.overlap && (kchain == 2 || kchain == 4)) ? kchain : 1u;
   H.kchain = B.kchain;
   Ctl& c0 = *H.ctl;

@@ -89,6 +89,16 @@ struct ClassRec {
   uint32_t flags;             // KB_TASK_BEST_EFFORT_QOS only
 };
 
+// Preferred node-affinity terms of a class (NodeAffinityPriority, vendor/.../priorities/node_affinity.go:34-77): requirement
+// atoms that must ALL hold on the node + the term's weight.  Host-side only so far (the emulation prototypes the two-pass scan
+// that the kernels get next).
+struct ClassPref {
+  uint64_t term[KB_MAX_PREF_TERMS][KB_MAX_W];
+  int32_t  weight[KB_MAX_PREF_TERMS];
+  uint32_t n;
+  uint32_t pad[3];
+};
+
 // api/resource_info.go:268-274
 KB_HD bool le_func(double l, double r, double diff) { return l < r || KB_FABS(KB_DSUB(l, r)) < diff; }
 

@@ -47,7 +47,32 @@ struct Emu {
   DevSession Sbf{};          // backfill view (kb_backfill)
   DevSession* cur = nullptr; // view the launches run on
   uint32_t launches = 0;
+  // prototype of the two-pass scan for preferred node affinity (a12): pass 1 of a launch leaves the max count over the
+  // feasible nodes and how many feasible nodes reach it; the replay of that launch consumes them
+  int64_t pref_max = 0;
+  uint32_t pref_nmax = 0;
 };
+
+// NodeAffinityPriority of one (class, node): count = sum of the weights of the matching preferred terms (weight 0 skipped)
+template <class Acc>
+int64_t pref_count(const ClassPref& cp, const Acc& acc, uint32_t W) {
+  int64_t count = 0;
+  for (uint32_t p = 0; p < cp.n; ++p) {
+    if (cp.weight[p] == 0) continue;
+    bool match = true;
+    for (uint32_t w = 0; w < W; ++w) if ((acc.labels(w) & cp.term[p][w]) != cp.term[p][w]) { match = false; break; }
+    if (match) count += cp.weight[p];
+  }
+  return count;
+}
+struct PrefCtx { const ClassPref* cp; int64_t w_nodeaff; int64_t max; uint32_t* nmax; };
+// key of a feasible node with the NormalizeReduce(10) term added to the (biased) score half
+inline uint64_t add_pref_term(uint64_t key, const PrefCtx* pc, int64_t count) {
+  if (!key || !pc || pc->max <= 0) return key;
+  const int64_t term = pc->w_nodeaff * (10 * count / pc->max);
+  const int64_t hi = (int64_t)(key >> 32) + term;
+  return ((uint64_t)hi << 32) | (key & 0xFFFFFFFFull);
+}
 
 // visit_kernel, scan + merge + (sharded) pack: keys[32] then columns [ncols][32]
 void emu_scan(Emu& E, uint64_t* sendbuf) {
@@ -59,6 +84,19 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
   const ClassRec& cls = S.classes[c.cur_class];
   const uint32_t R = S.cf.R, W = S.cf.W;
   const size_t tile_u64 = (size_t)S.ncols * TILE_NODES;
+  // pass 1 (only for a class with preferred terms): max count over the FEASIBLE nodes + how many feasible nodes reach it
+  const ClassPref* cp = (E.B.has_pref && S.cf.nodeorder && !S.backfill && E.B.class_pref[c.cur_class].n) ? &E.B.class_pref[c.cur_class] : nullptr;
+  E.pref_max = 0; E.pref_nmax = 0;
+  if (cp)
+    for (uint32_t n = 0; n < S.N; ++n) {
+      TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+      if (!eval_pair(S.cf, cls, acc, n, nullptr)) continue;
+      const int64_t cnt = pref_count(*cp, acc, W);
+      if (cnt > E.pref_max) { E.pref_max = cnt; E.pref_nmax = 1; }
+      else if (cnt == E.pref_max) E.pref_nmax += 1;
+    }
+  uint32_t nmax_dummy = 0;
+  PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &nmax_dummy};
   std::vector<uint64_t> keys;
   for (uint32_t t = S.tile_lo; t < S.tile_hi; ++t)
     for (uint32_t i = 0; i < TILE_NODES; ++i) {
@@ -66,6 +104,7 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
       if (n >= S.N) break;
       TileAcc acc{S.tiles + (size_t)t * tile_u64, i, R, W};
       uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr);
+      if (k && cp) k = add_pref_term(k, &pc, pref_count(*cp, acc, W));
       if (k) keys.push_back(k);
     }
   std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
@@ -78,10 +117,11 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
 }
 
 struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = false, modified = false;
-              uint64_t cur_key = 0, next_key = 0; uint32_t node = 0, cnt = 0; Slot st[2]; int which = 0; };
+              uint64_t cur_key = 0, next_key = 0; uint32_t node = 0, cnt = 0; Slot st[2]; int which = 0; int64_t pref = 0; };
 
 // replay_epilogue's core: look-ahead refresh + certified steps + control plane, for candidates already loaded
-bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key) {
+bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key,
+                 const PrefCtx* pc = nullptr) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   auto refresh = [&]() {
@@ -98,14 +138,15 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       for (uint32_t w = 0; w < W; ++w) dst.col[col_ports(R, W, w)] = src.col[col_ports(R, W, w)] | cls.port_own[w];
       SlotAcc acc{&dst, R, W};
       bool f = false;
-      cd.next_key = eval_pair(S.cf, cls, acc, cd.node, &f);
+      cd.next_key = add_pref_term(eval_pair(S.cf, cls, acc, cd.node, &f), pc, cd.pref);
       cd.next_fi = f; cd.next_valid = true;
       c.pairs_replayed += 1;
     }
   };
   refresh();
+  bool pref_stale = false;      // the last feasible max-count node filled up: every key of this launch used a stale normalisation
   for (;;) {
-    if (c.done || c.cur_class != cls_id) break;
+    if (c.done || c.cur_class != cls_id || pref_stale) break;
     const uint32_t j = (uint32_t)c.cur_job;
     const uint32_t jend = S.job_ord_off[j + 1];
     uint32_t run_left = c.cur_run, placed = 0, reason = STOP_RUN_DONE;
@@ -132,7 +173,12 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       S.job_placed[j] += 1;
       on_allocate_event(S, j, cls);
       placed += 1;
+      if (pc && pc->max > 0 && cd.cur_key == 0 && cd.pref == pc->max) {            // a max-count node left the feasible set
+        *pc->nmax -= 1;
+        if (*pc->nmax == 0) pref_stale = true;
+      }
       if (ssn_job_ready(S, j) && (pos + 1 < jend) && !S.backfill) { reason = STOP_YIELD; break; }
+      if (pref_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
     }
     if (reason == STOP_RESCAN) c.rescans += 1;
     after_run(S, c, reason, placed);
@@ -187,7 +233,10 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
     SlotAcc acc{&cd.st[0], R, W};
     cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
   }
-  replay_core(S, c, cls_id, cand, floor_key);
+  const ClassPref* cp = (E.B.has_pref && S.cf.nodeorder && !S.backfill && E.B.class_pref[cls_id].n) ? &E.B.class_pref[cls_id] : nullptr;
+  PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &E.pref_nmax};
+  if (cp) for (auto& cd : cand) if (cd.have) { SlotAcc acc{&cd.st[0], R, W}; cd.pref = pref_count(*cp, acc, W); }
+  replay_core(S, c, cls_id, cand, floor_key, cp ? &pc : nullptr);
   write_back(S, cls, cand);          // every replica writes every modified candidate back
 }
 
@@ -412,7 +461,8 @@ const char* kbemu_last_error(void) { return g_err.c_str(); }
 void* kbemu_create2(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world, uint32_t mode) {
   Emu* E = new Emu();
   BuildErr be;
-  if (build_session(snap, conf, 148, E->B, &be, rank, world, mode == 0 ? 1 : 0, mode >= 2 ? mode : 1)) { g_err = be.msg; delete E; return nullptr; }
+  // mode 1 (plain launches) also accepts preferred node-affinity terms: the emulation prototypes the two-pass scan (a12)
+  if (build_session(snap, conf, 148, E->B, &be, rank, world, mode == 0 ? 1 : 0, mode >= 2 ? mode : 1, mode == 1)) { g_err = be.msg; delete E; return nullptr; }
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
   E->cur = &E->S;

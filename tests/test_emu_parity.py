@@ -296,3 +296,64 @@ def test_known_divergence_phantom_allocated_best_effort_task():
     assert o.decisions["kind"].tolist() == [abi.KB_KIND_ALLOCATED, abi.KB_KIND_ALLOCATED] and o.decisions["node"].tolist() == [0, -1]
     assert e.decisions["kind"].tolist() == [abi.KB_KIND_ALLOCATED, abi.KB_KIND_NONE] and e.decisions["node"].tolist() == [0, -1]
     np.testing.assert_array_equal(o.node_idle, e.node_idle)          # the node bookkeeping itself is identical
+
+
+# ---------------- a12 NodeAffinityPriority: prototype of the engine algorithm (emulation only; the kernels follow next round) ----------------
+def _pref_cluster(seed):
+    rng = np.random.default_rng(seed)
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    nn = int(rng.integers(2, 7))
+    zones = ["a", "b", "c"]
+    for n in range(nn):
+        b.add_node(B.Node(f"n{n}", {"cpu": float(rng.choice([2, 4, 8])), "memory": 64e9, "pods": int(rng.choice([3, 6, 110]))},
+                          labels={"zone": zones[n % 3], "rank": str(n)}))
+    for g in range(int(rng.integers(1, 4))):
+        b.add_pod_group(B.PodGroup("ns", f"g{g}", "q", min_member=int(rng.integers(0, 3))))
+        pref = [(int(rng.choice([0, 1, 20, 50, 100])), [("zone", "In", [str(rng.choice(zones))])]) for _ in range(int(rng.integers(1, 4)))]
+        cpu = float(rng.choice([0.5, 1, 2]))
+        for k in range(int(rng.integers(3, 14))):
+            b.add_pod(B.Pod("ns", f"g{g}-p{k:02d}", "", "Pending", {"cpu": cpu, "memory": 1e9}, group=f"g{g}", creation=k,
+                            preferred_terms=pref if rng.random() < 0.9 else []))
+    return b.flatten()
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_preferred_node_affinity_two_pass_scan_prototype(seed):
+    """The scan of a class with preferred terms runs in two passes (max count over the FEASIBLE nodes, then the keys with
+    10*count/max added); the replay stops for a rescan as soon as the last feasible max-count node fills up, because every
+    key of the launch used that normalisation.  Small clusters make that happen all the time."""
+    s = _pref_cluster(6000 + seed)
+    rescans = 0
+    for conf in (PluginConf.default(),
+                 PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "5"}}),
+                 PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "-3"}}),
+                 PluginConf.from_names([["gang", "priority"], ["predicates"]])):            # no nodeorder: the terms must not matter
+        o, e = check(s, conf, f"pref seed{seed}", mode=1)
+        rescans += e.result.rescans
+    assert rescans >= 0
+
+
+def test_preferred_node_affinity_normalisation_goes_stale_exactly_when_the_last_max_node_fills():
+    # n-a (count 100) takes two pods (pod cap 2).  n-b (count 20) is 40 % busy, n-c (count 0) is empty, so n-c's resource scores
+    # beat n-b's by 4..6 points: while n-a is feasible b's affinity term is 10*20/100 = 2 and n-c would win; once n-a is full the
+    # max count is 20, b's term jumps to 10 and n-b wins.  A replay that kept the stale normalisation would pick n-c.
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "g", "q", min_member=5))       # not ready before the 5th pod: the whole job is ONE run of one launch
+    b.add_pod_group(B.PodGroup("ns", "old", "q", min_member=1))
+    b.add_node(B.Node("n-a", {"cpu": 64, "memory": 256e9, "pods": 2}, labels={"zone": "a"}))
+    b.add_node(B.Node("n-b", {"cpu": 64, "memory": 256e9, "pods": 110}, labels={"zone": "b"}))
+    b.add_node(B.Node("n-c", {"cpu": 64, "memory": 256e9, "pods": 110}, labels={"zone": "c"}))
+    b.add_pod(B.Pod("ns", "busy", "n-b", "Running", {"cpu": 25, "memory": 1e9}, group="old"))
+    pref = [(100, [("zone", "In", ["a"])]), (20, [("zone", "In", ["b"])])]
+    for k in range(5):
+        b.add_pod(B.Pod("ns", f"p{k}", "", "Pending", {"cpu": 1, "memory": 1e9}, group="g", creation=k, preferred_terms=pref))
+    s = b.flatten()
+    conf = PluginConf.from_names([["gang"], ["predicates", "nodeorder"]])
+    fit, score = kbo.predicate_score(s, conf, 0)
+    assert score[2] - score[1] > 2 and score[2] - score[1] < 10 and score[0] > score[2]      # the fixture is in the sensitive band
+    o, e = check(s, conf, "pref stale", mode=1)
+    names = [s.meta["nodes"][n] for n in o.decisions["node"]]
+    assert names == ["n-a", "n-a", "n-b", "n-b", "n-b"]
+    assert e.result.rescans >= 1
