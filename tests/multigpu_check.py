@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N tools/multigpu_check.py  — sharded-node-axis parity on real GPUs (NCCL)."""
+"""torchrun --nproc-per-node N tests/multigpu_check.py  — sharded-node-axis parity on real GPUs (NCCL)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
