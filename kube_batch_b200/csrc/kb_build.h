@@ -405,8 +405,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); ClassPref cp; memset(&cp, 0, sizeof cp); class_pref.push_back(cp); }
   static_assert(sizeof(ClassPref) % 8 == 0, "ClassPref is hashed as 64-bit words");
-  if (B.has_pref && (world > 1 || kchain > 1 || overlap_mode > 0))
-    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node affinity: only the plain single-rank launch mode is prototyped");
+  if (B.has_pref && (kchain > 1 || overlap_mode > 0))
+    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node affinity: only the plain launch mode is prototyped");
   if (B.has_pref) hc.cf.score_bias += 10ll * (hc.w_nodeaff < 0 ? -(int64_t)hc.w_nodeaff : 0);
   const uint32_t C = (uint32_t)classes.size();
 

@@ -94,3 +94,18 @@ def test_sharded_node_axis_in_process(world):
                 util.assert_same_decisions(o.decisions, e.decisions, f"seed{seed}/{cname}/a{actions}/world{world}/rank{r}")
                 ns, os_ = util.emu_states(e)
                 util.assert_same_state(o, ns, os_, f"seed{seed}/{cname}/a{actions}/world{world}/rank{r}")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_preferred_node_affinity_prototype(world):
+    """a12 on a sharded node axis (prototype, emulation only): every rank runs pass 1 (max count over the feasible nodes) on its
+    replicated copy of the table, so no second exchange is needed; pass 2 (keys) stays sharded."""
+    import util
+    from oracle import kbo
+    from test_emu_parity import _pref_cluster
+    conf = PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "5"}})
+    for seed in range(12):
+        s = _pref_cluster(7000 + seed)
+        o = kbo.allocate(s, conf)
+        for r, e in enumerate(util.emu_sharded_inprocess(s, conf, world, mode=1)):
+            util.assert_same_decisions(o.decisions, e.decisions, f"pref seed{seed}/world{world}/rank{r}")

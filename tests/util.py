@@ -161,7 +161,7 @@ def emu_sharded_rank(rank: int, world: int, port: int, snap: Snapshot, conf: Plu
         dist.destroy_process_group()
 
 
-def emu_sharded_inprocess(snap: Snapshot, conf: PluginConf, world: int, actions: int = 1):
+def emu_sharded_inprocess(snap: Snapshot, conf: PluginConf, world: int, actions: int = 1, mode: int = 0):
     """The sharded scan -> all-gather -> replay chain with all `world` ranks emulated in THIS process (the all-gather is a
     concatenation).  Returns one result container per rank; every rank must hold the identical, complete result."""
     L = emu_lib()
@@ -181,8 +181,10 @@ def emu_sharded_inprocess(snap: Snapshot, conf: PluginConf, world: int, actions:
     cc, k2 = conf.to_c()
     hs = []
     try:
+        L.kbemu_create2.restype = C.c_void_p
+        L.kbemu_create2.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32]
         for r in range(world):
-            h = L.kbemu_create(C.addressof(cs), C.addressof(cc), r, world)
+            h = L.kbemu_create2(C.addressof(cs), C.addressof(cc), r, world, mode)
             if not h:
                 raise RuntimeError(L.kbemu_last_error().decode())
             hs.append(h)
