@@ -1882,6 +1882,17 @@ void kbo_heap_sort(const int64_t* keys, uint32_t n, int64_t* out) {
   for (uint32_t i = 0; i < n; ++i) pq.Push(keys[i]);
   for (uint32_t i = 0; i < n; ++i) out[i] = pq.Pop();
 }
+uint32_t kbo_select_best_node(const double* scores, uint32_t n) {
+  std::vector<double> v(scores, scores + n);
+  return (uint32_t)Executor::SelectBestNode(v);
+}
+int kbo_arguments_get_int(const char* value, int base) {
+  std::map<std::string, std::string> a;
+  if (value) a["intkey"] = value;
+  int v = base;
+  GetInt(a, &v, "intkey");
+  return v;
+}
 double kbo_share(double l, double r) { return Share(l, r); }
 
 }  // extern "C"

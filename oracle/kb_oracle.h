@@ -123,6 +123,10 @@ int64_t kbo_balanced(int64_t req_cpu, int64_t alloc_cpu, int64_t req_mem, int64_
 void kbo_heap_sort(const int64_t* keys, uint32_t n, int64_t* out);
 /* helpers.Share (api/helpers/helpers.go:47-60) */
 double kbo_share(double l, double r);
+/* util.SelectBestNode (util/scheduler_helper.go:188-208) under the deterministic rule "first max": index of the pick */
+uint32_t kbo_select_best_node(const double* scores, uint32_t n);
+/* framework.Arguments.GetInt (framework/arguments.go:29-46): `value` NULL = key absent; returns the resulting *ptr */
+int kbo_arguments_get_int(const char* value, int base);
 
 const char* kbo_last_error(void);
 

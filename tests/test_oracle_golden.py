@@ -476,3 +476,63 @@ def test_drf_preempts_only_towards_a_fairer_split():
     names = s.meta["running"]["names"]
     assert {names[i] for i in np.nonzero(ev)[0]} == {"ns/b3"}
     np.testing.assert_allclose(o.job_share, [0.5, 0.2])
+
+
+# ---- the remaining unit vectors of the reference that touch this path ----
+def test_select_best_node_golden():
+    """util/scheduler_helper_test.go:24-92: the pick must be ONE OF the max-score nodes (the reference picks randomly among them;
+    the deterministic rule takes the first)."""
+    import ctypes as C
+    L = kbo.lib()
+    L.kbo_select_best_node.restype = C.c_uint32
+    for scores, expected in (([1.0, 1.0, 2.0, 2.0], {2, 3}), ([1.0, 1.0, 3.0, 2.0, 2.0], {2})):
+        a = np.array(scores, dtype=np.float64)
+        got = L.kbo_select_best_node(a.ctypes.data_as(C.POINTER(C.c_double)), C.c_uint32(len(a)))
+        assert got in expected and got == min(expected)
+
+
+def test_arguments_get_int_golden():
+    """framework/arguments_test.go:30-78: absent key and unparsable values keep the base value."""
+    import ctypes as C
+    L = kbo.lib()
+    L.kbo_arguments_get_int.restype = C.c_int
+    L.kbo_arguments_get_int.argtypes = [C.c_char_p, C.c_int]
+    assert L.kbo_arguments_get_int(None, 10) == 10           # {"anotherkey": "12"}
+    assert L.kbo_arguments_get_int(b"15", 10) == 15
+    assert L.kbo_arguments_get_int(b"errorvalue", 11) == 11
+    assert L.kbo_arguments_get_int(b"", 0) == 0
+    # the engine's own parser (kb_build.h parse_int) must agree: an unparsable nodeorder weight keeps the default on both sides
+    import util
+    from kube_batch_b200 import synth
+    s = synth.random_session(12, tasks=80, jobs=8, nodes=30)
+    for bad in ("errorvalue", "", "3x", " 4"):
+        conf = PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"leastrequested.weight": bad, "mostrequested.weight": "2"}})
+        o = kbo.allocate(s, conf)
+        e = util.emu_allocate(s, conf, mode=1)
+        util.assert_same_decisions(o.decisions, e.decisions, f"weight {bad!r}")
+
+
+def test_job_info_add_task_golden():
+    """api/job_info_test.go:35-101: p1 Pending, p2 Running on n1 (2000m/2G), p3 and p4 Pending WITH a node name = Bound (1000m/1G
+    each) -> Allocated 4000m/4G, TaskStatusIndex {Pending: p1, Running: p2, Bound: p3, p4}."""
+    b = B.SessionBuilder()
+    b.add_node(B.build_node("n1", {"cpu": 8, "memory": 10e9}, pods=110))
+    b.add_queue(B.Queue("q"))
+    b.add_pod_group(B.PodGroup("c1", "uid", "q"))
+    b.add_pod(B.Pod("c1", "p1", "", "Pending", {"cpu": 1, "memory": 1e9}, group="uid"))
+    b.add_pod(B.Pod("c1", "p2", "n1", "Running", {"cpu": 2, "memory": 2e9}, group="uid"))
+    b.add_pod(B.Pod("c1", "p3", "n1", "Pending", {"cpu": 1, "memory": 1e9}, group="uid"))
+    b.add_pod(B.Pod("c1", "p4", "n1", "Pending", {"cpu": 1, "memory": 1e9}, group="uid"))
+    s = b.flatten()
+    assert s.T == 1 and s.meta["tasks"] == ["c1/p1"]
+    assert s.job_alloc0[:2, 0].tolist() == [4000.0, 4e9] and s.job_ready0[0] == 3
+    assert s.node_used[:2, 0].tolist() == [4000.0, 4e9] and s.node_pods[0] == 3
+
+
+def test_new_resource_golden():
+    """api/resource_info_test.go:27-57: cpu 4m -> MilliCPU 4, memory 2000 -> 2000, scalar quantities -> milli-units."""
+    v, present = B.SessionBuilder._resource({"cpu": 0.004, "memory": 2000, "scalar.test/scalar1": 1, "hugepages-test": 2},
+                                            ["cpu", "memory", "hugepages-test", "scalar.test/scalar1"])
+    assert v.tolist() == [4.0, 2000.0, 2000.0, 1000.0] and present == 0b1100
+    v, present = B.SessionBuilder._resource({}, ["cpu", "memory"])
+    assert v.tolist() == [0.0, 0.0] and present == 0
