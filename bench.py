@@ -89,6 +89,21 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def parity_verdict(workload, eng, res):
+    """'ok' iff this rank's decisions + node / job state equal the committed oracle digests (tests/golden/cycle_hashes.json)."""
+    from kube_batch_b200 import digest
+    hp = os.path.join(ROOT, "tests", "golden", "cycle_hashes.json")
+    g = json.load(open(hp)).get(workload) if os.path.exists(hp) else None
+    if g is None:
+        return "no committed digest for this workload"
+    ns, osr = eng.node_state(), eng.order_state()
+    if digest.decisions_digest(res.decisions) != g["decisions"]:
+        return "decisions differ from the oracle digest"
+    if digest.state_digest(ns["idle"], ns["releasing"], osr["job_ready"], osr["job_share"]) != g["state"]:
+        return "node/job state differs from the oracle digest"
+    return "ok"
+
+
 def cpu_sample(snap, conf, mode, threads, seconds):
     from oracle import kbo
     o = kbo.allocate(snap, conf, mode=mode, threads=threads, max_seconds=seconds)
@@ -199,6 +214,14 @@ def run_ours(args, rank, world, local_rank):
         dev_ms = float(t.item())
     st = last.stats
     pairs = int(st.pairs_logical)
+
+    # ---- parity of the timed cycle's outcome, on EVERY rank, against the committed oracle digests (outside the timed region) ----
+    parity = parity_verdict(args.workload, eng, last)
+    if dist is not None:
+        t = torch.tensor([1 if parity == "ok" else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        if int(t.item()) == 0 and parity == "ok":
+            parity = "mismatch on another rank"
     value = pairs * args.steps / (dev_ms * 1e-3)
     groups_per_s = int(st.jobs_ready) * args.steps / (dev_ms * 1e-3)
 
@@ -221,6 +244,8 @@ def run_ours(args, rank, world, local_rank):
         eng.close()
         if dist is not None:
             dist.destroy_process_group()
+        if parity != "ok" and args.workload in ("c2", "c3", "c4"):
+            raise SystemExit(f"bench.py rank {rank}: parity check failed: {parity}")
         return
 
     # ---- roofline of the dominant kernel (visit_kernel): algorithmic bytes of its scans / device time ----
@@ -281,6 +306,9 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f64 compares + i64 scores + u64 bitmasks", "data": "synthetic",
         "config": workload_desc(args.workload, snap, conf),
         "podgroups_placed_per_s": groups_per_s,
+        "parity": parity,
+        "pairs_scanned_per_s": int(st.pairs_scanned) / (st.gpu_ms * 1e-3),
+        "pairs_scanned_per_step": int(st.pairs_scanned),
         "tasks_processed": int(st.tasks_processed), "tasks_allocated": int(st.tasks_allocated), "podgroups_ready": int(st.jobs_ready),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(r.stats.h2d_bytes), "d2h_bytes_per_step": int(r.stats.d2h_bytes),
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
@@ -298,6 +326,8 @@ def run_ours(args, rank, world, local_rank):
     eng.close()
     if dist is not None:
         dist.destroy_process_group()
+    if parity != "ok" and args.workload in ("c2", "c3", "c4"):
+        raise SystemExit(f"bench.py: parity check failed: {parity}")
 
 
 def main():

@@ -251,15 +251,26 @@ def test_c3_full_size_parity_and_properties(eng):
     placed = d["step"] != 0xFFFFFFFF
     assert sorted(d["step"][placed].tolist()) == list(range(int(placed.sum())))
     assert r.stats.pairs_logical == int(r.stats.tasks_processed) * s.N
+    check_committed_digest(eng, "c3", r)
 
 
-@pytest.mark.skipif(os.environ.get("KB_SLOW") != "1", reason="set KB_SLOW=1: the CPU oracle needs minutes at this size")
+def check_committed_digest(eng, name, r):
+    """The committed oracle digests (tests/golden/cycle_hashes.json, made HERE by make_golden.py) — what bench.py checks at every N."""
+    from kube_batch_b200 import digest
+    g = json.load(open(os.path.join(GOLD, "cycle_hashes.json")))[name]
+    ns, osr = eng.node_state(), eng.order_state()
+    assert digest.decisions_digest(r.decisions) == g["decisions"], name + ": decisions differ from the committed oracle digest"
+    assert digest.state_digest(ns["idle"], ns["releasing"], osr["job_ready"], osr["job_share"]) == g["state"], name + ": state digest"
+
+
 def test_c4_multiqueue_full_size_parity(eng):
-    """BASELINE config 4 (200k tasks x 20k nodes, 8 queues with proportion): exact Go-heap replay with stale keys at scale."""
+    """BASELINE config 4 (200k tasks x 20k nodes, 8 queues with proportion): exact Go-heap replay with stale keys at scale.
+    The oracle runs here as well (about a minute on 16 host threads)."""
     s, conf = synth.make("c4")
-    o = kbo.allocate(s, conf, threads=16)
+    o = kbo.allocate(s, conf, threads=min(16, os.cpu_count() or 1))
     eng.load(s, conf)
     r = eng.allocate()
     util.assert_same_decisions(o.decisions, r.decisions, "c4")
     util.assert_same_state(o, eng.node_state(), eng.order_state(), "c4")
+    check_committed_digest(eng, "c4", r)
     print(f"c4: gpu {r.stats.gpu_ms:.1f} ms, oracle {o.result.seconds:.1f} s, scans {r.stats.scans}, visits {r.stats.visits}")

@@ -536,3 +536,17 @@ def test_new_resource_golden():
     assert v.tolist() == [4.0, 2000.0, 2000.0, 1000.0] and present == 0b1100
     v, present = B.SessionBuilder._resource({}, ["cpu", "memory"])
     assert v.tolist() == [0.0, 0.0] and present == 0
+
+
+def test_committed_cycle_digests_match_a_fresh_oracle_run():
+    """tests/golden/cycle_hashes.json (what bench.py and the full-size GPU tests compare against) is reproducible: c2 here,
+    c3 too (a few seconds); c4 is regenerated by make_golden.py only."""
+    import json, os
+    from kube_batch_b200 import digest, synth
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cycle_hashes.json")))
+    for name in ("c2", "c3"):
+        snap, conf = synth.make(name)
+        o = kbo.allocate(snap, conf, threads=os.cpu_count() or 1)
+        assert digest.decisions_digest(o.decisions) == g[name]["decisions"], name
+        assert digest.state_digest(o.node_idle, o.node_releasing, o.job_ready, o.job_share) == g[name]["state"], name
+        assert int(o.result.tasks_allocated) == g[name]["allocated"]
