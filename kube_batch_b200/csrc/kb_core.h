@@ -99,8 +99,13 @@ struct ClassPref {
   uint32_t pad[3];
 };
 
-// api/resource_info.go:268-274
-KB_HD bool le_func(double l, double r, double diff) { return l < r || KB_FABS(KB_DSUB(l, r)) < diff; }
+// api/resource_info.go:268-274: `l < r || math.Abs(l-r) < diff`.  Evaluated as ONE rounded subtraction and ONE compare:
+//   l <  r  ->  l - r < 0 < diff (a difference of distinct doubles never rounds to zero: gradual underflow), true either way;
+//   l >= r  ->  |l - r| == l - r, the same rounded value the reference compares.
+// (NaN never occurs: quantities are finite; +-inf from an overflowing subtraction compares like the reference's.)
+// Pinned against the two-term form over the reference's LessEqual vectors and random values in tests/test_emu_parity.py.
+KB_HD bool le_func(double l, double r, double diff) { return KB_DSUB(l, r) < diff; }
+KB_HD bool le_func_reference_form(double l, double r, double diff) { return l < r || KB_FABS(KB_DSUB(l, r)) < diff; }
 
 // Resource.LessEqual(l, r) on dense vectors (api/resource_info.go:268-302).  A nil scalar map and a
 // map of zeros are indistinguishable here: a scalar of l is only compared when l_k > 10, and then
@@ -132,15 +137,19 @@ KB_HD double share_of(double l, double r) {
   return KB_DDIV(l, r);
 }
 
-// a / b for b > 0 when the quotient is known to lie in [0, 10]: ten independent multiply-compares instead
-// of a 64-bit integer division (which costs hundreds of cycles on the GPU).  Exact: q = #{k in 1..10 : k*b <= a}.
+// a / b (Go int64 division) for b > 0 when the quotient is known to lie in [0, 10] — no 64-bit integer division (hundreds
+// of cycles on the GPU), no ten-step ladder: a single-precision estimate (relative error < 2^-21, so |est - a/b| < 1e-5)
+// and ONE exact multiply-compare fix-up in each direction.  Exact for every 0 <= a <= 10 b, b < 2^59.
 KB_HD int64_t div_0_to_10(int64_t a, int64_t b) {
   if (a < 0 || a > 10 * b) return a / b;          // outside the fast range (never on sane inputs)
-  int64_t q = 0;
 #if defined(__CUDA_ARCH__)
-#pragma unroll
+  int64_t q = (int64_t)__float2int_rz(__fdividef(__ll2float_rn(a), __ll2float_rn(b)));     // MUFU.RCP + FMUL
+#else
+  int64_t q = (int64_t)((float)a * (1.0f / (float)b));
 #endif
-  for (int64_t k = 1; k <= 10; ++k) q += (k * b <= a) ? 1 : 0;
+  q = q < 0 ? 0 : (q > 10 ? 10 : q);
+  q -= (q * b > a) ? 1 : 0;
+  q += ((q + 1) * b <= a) ? 1 : 0;
   return q;
 }
 // least_requested.go:49-58
@@ -180,14 +189,19 @@ KB_HD int64_t key_score(uint64_t key) { return (int64_t)(key >> 32); }
 // K1 (predicate bitmask) + K2 (fused score) for one (class, node) pair against the node's CURRENT state.
 // Returns the packed key, 0 if predicateFn would return an error.  `fits_idle` reports
 // InitResreq <= Idle, which decides Allocate vs Pipeline at commit (allocate.go:160).
-template <class NodeAcc>
+// RR / WW: compile-time copies of cf.R / cf.W (0 = read them at run time).  The kernels instantiate the common geometry
+// (R = 3, W = 2) so that every loop below unrolls into straight-line code; semantics are identical.
+template <int RR = 0, int WW = 0, class NodeAcc>
 KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n, uint32_t node_idx, bool* fits_idle) {
   // Written branch-free on purpose: a lone warp (the replay) or one warp per SM sub-partition (the scan)
   // hides latency only through instruction-level parallelism, so every check is computed and AND-ed.
-  const uint32_t R = cf.R, W = cf.W;
+  const uint32_t R = RR ? (uint32_t)RR : cf.R, W = WW ? (uint32_t)WW : cf.W;
   // allocate.go:82: !InitResreq.LessEqual(Idle) && !InitResreq.LessEqual(Releasing) -> ResourceFit failed
   bool fi = le_func(c.initreq[0], n.idle(0), KB_MIN_MILLI_CPU) & le_func(c.initreq[1], n.idle(1), KB_MIN_MEMORY);
   bool fr = le_func(c.initreq[0], n.rel(0), KB_MIN_MILLI_CPU) & le_func(c.initreq[1], n.rel(1), KB_MIN_MEMORY);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
   for (uint32_t k = 2; k < R; ++k) {            // resource_info.go:286-299: scalars <= 10 are skipped
     const double lq = c.initreq[k];
     const bool skip = lq <= KB_MIN_MILLI_SCALAR;
@@ -204,6 +218,9 @@ KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n
     ok = ok & ((fl & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) == 0);   // vendored :1675-1698
     uint64_t bad = 0;
     uint64_t miss[KB_MAX_AFF_TERMS] = {0, 0, 0, 0};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
     for (uint32_t w = 0; w < W; ++w) {
       const uint64_t lab = n.labels(w);
       bad |= (lab & c.sel_req[w]) ^ c.sel_req[w];          // nodeSelector atoms missing        (:927-935)

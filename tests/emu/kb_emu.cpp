@@ -209,7 +209,6 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
   const uint32_t cls_id = c.cur_class;
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
-  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
   const size_t rank_u64 = (size_t)(1 + ncols) * 32;
   // merge the ranks' lists
   struct Src { uint64_t key; uint32_t rank, idx; };
@@ -453,6 +452,11 @@ void emu_begin_backfill(Emu& E, bool carry) {
 }  // namespace
 
 extern "C" {
+
+// the engine's exact-arithmetic shortcuts next to the forms they replace (tests/test_emu_parity.py pins them on each other)
+int kbemu_le(double l, double r, double diff) { return le_func(l, r, diff) ? 1 : 0; }
+int kbemu_le_reference_form(double l, double r, double diff) { return le_func_reference_form(l, r, diff) ? 1 : 0; }
+long long kbemu_div_0_to_10(long long a, long long b) { return div_0_to_10(a, b); }
 
 uint32_t kbemu_buf_u64(void* h);
 const char* kbemu_last_error(void) { return g_err.c_str(); }

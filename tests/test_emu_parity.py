@@ -357,3 +357,45 @@ def test_preferred_node_affinity_normalisation_goes_stale_exactly_when_the_last_
     names = [s.meta["nodes"][n] for n in o.decisions["node"]]
     assert names == ["n-a", "n-a", "n-b", "n-b", "n-b"]
     assert e.result.rescans >= 1
+
+
+# ---------------- exact-arithmetic shortcuts of kb_core.h ----------------
+def test_le_func_single_subtraction_equals_the_reference_form():
+    """kb_core.h le_func evaluates `l < r || |l - r| < eps` (api/resource_info.go:268-274) as `(l - r) < eps`.  Same predicate on
+    the reference's LessEqual vectors (resource_info_test.go:246-304), around every epsilon boundary, and on random values."""
+    import ctypes as C
+    L = util.emu_lib()
+    for f in (L.kbemu_le, L.kbemu_le_reference_form):
+        f.argtypes = [C.c_double, C.c_double, C.c_double]
+        f.restype = C.c_int
+    eps = [10.0, 10.0 * 1024 * 1024]
+    vals = [0.0, -0.0, 1.0, 4.0, 10.0, 2000.0, 4000.0, 8000.0, 1e9, 4e9, 10.0 * 1024 * 1024, 1e300, -1e300, 5e-324, -5e-324, 9.999999999999998, 10.000000000000002]
+    rng = np.random.default_rng(3)
+    cases = [(l, r, e) for l in vals for r in vals for e in eps]
+    for e in eps:
+        for base in (0.0, 1000.0, 3e9, 1e15):
+            for d in (e, np.nextafter(e, 0), np.nextafter(e, 1e300), -e, e / 2, 0.0):
+                cases.append((base + d, base, e)); cases.append((base, base + d, e))
+    cases += [(float(a), float(b), float(e)) for a, b, e in zip(rng.integers(0, 1 << 40, 20000), rng.integers(0, 1 << 40, 20000), rng.choice(eps, 20000))]
+    cases += [(float(a), float(a + d), 10.0) for a, d in zip(rng.integers(0, 100000, 20000), rng.integers(-12, 13, 20000))]
+    for l, r, e in cases:
+        assert L.kbemu_le(l, r, e) == L.kbemu_le_reference_form(l, r, e), (l, r, e)
+
+
+def test_div_0_to_10_estimate_plus_fixup_is_exact():
+    """least / most requested use (x * 10) / capacity in Go int64 arithmetic (least_requested.go:49-58): the engine's
+    float-estimate + one fix-up each way must equal the integer quotient, including at every exact multiple and its neighbours."""
+    import ctypes as C
+    L = util.emu_lib()
+    L.kbemu_div_0_to_10.argtypes = [C.c_longlong, C.c_longlong]
+    L.kbemu_div_0_to_10.restype = C.c_longlong
+    rng = np.random.default_rng(5)
+    bs = [1, 2, 3, 7, 10, 999, 1000, 32000, 96000, 128 << 30, 384 << 30, (1 << 58) - 1, 1 << 58] + [int(x) for x in rng.integers(1, 1 << 58, 3000)]
+    for b in bs:
+        for k in range(0, 11):
+            for d in (-2, -1, 0, 1, 2):
+                a = k * b + d
+                if 0 <= a <= 10 * b:
+                    assert L.kbemu_div_0_to_10(a, b) == a // b, (a, b)
+        for a in rng.integers(0, 10 * b + 1, 20, dtype=np.uint64 if 10 * b >= 1 << 63 else np.int64):
+            assert L.kbemu_div_0_to_10(int(a), b) == int(a) // b, (int(a), b)
