@@ -176,6 +176,11 @@ typedef struct kb_plugin_conf {
 #define KB_ENGINE_CHAIN_OFF     (1u << 2) /* one class per launch (visit_kernel); default: chained visits (single GPU, no overlap) */
 #define KB_ENGINE_CHAIN2        (1u << 3) /* scan 2 classes per launch and replay the following visit from the look-ahead list  */
 #define KB_ENGINE_CHAIN4        (1u << 4) /* ... 4 classes per launch                                                          */
+#define KB_ENGINE_NO_PIPE       (1u << 5) /* never run the cycle as ONE persistent cooperative kernel (cycle_kernel); default: whenever
+                                             the record geometry (R = 3, W = 2) and the node count fit the scanners' shared memory */
+#define KB_ENGINE_SHARD         (1u << 6) /* world_size > 1: shard the node axis across the ranks (scan shard + exchange per visit).
+                                             Default: every rank runs the whole cycle on the full table (replicated, no exchange):
+                                             the cycle is bound by the serial replay, not by the scan */
 
 typedef struct kb_engine_opts {
   uint32_t abi_version;     /* KB_ABI_VERSION */
@@ -223,8 +228,14 @@ typedef struct kb_stats {
   uint64_t cyc_ctl;         /*   ... of cyc_replay: the control plane (after_run)                 */
   uint32_t predictions;     /* overlap mode: launches whose scan ran ahead on a predicted class   */
   uint32_t mispredictions;  /*   ... of which the prediction was wrong (that launch's scan is redone) */
-  uint32_t exchange_mode;   /* 0 single GPU, 1 NCCL all-gather per scan, 2 fused peer-memory exchange  */
+  uint32_t exchange_mode;   /* 0 single GPU, 1 NCCL all-gather per scan, 2 fused peer-memory exchange, 3 replicated (no exchange) */
   uint32_t chain_hits;      /* chained visits: visits replayed from a look-ahead list of an earlier launch's scan */
+  uint32_t pipeline;        /* 1: the cycle ran as one persistent cooperative kernel (cycle_kernel)         */
+  uint32_t pipe_requests;   /*   scan requests the replayer posted (look-ahead + urgent)                     */
+  uint32_t pipe_urgent;     /*   ... of which the replayer had to wait for (no usable look-ahead list)       */
+  uint32_t pipe_extends;    /*   candidate chains extended beyond the 8 pre-evaluated placement depths       */
+  uint32_t pipe_patched;    /*   lists consumed with a non-empty patch set (nodes modified since the scan)   */
+  uint32_t pipe_patch_entries; /* log entries re-evaluated by those patches                                  */
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

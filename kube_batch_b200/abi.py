@@ -12,6 +12,8 @@ KB_ENGINE_FORCE_OVERLAP = 1 << 1
 KB_ENGINE_CHAIN_OFF = 1 << 2
 KB_ENGINE_CHAIN2 = 1 << 3
 KB_ENGINE_CHAIN4 = 1 << 4
+KB_ENGINE_NO_PIPE = 1 << 5
+KB_ENGINE_SHARD = 1 << 6
 KB_ABI_VERSION = 1
 KB_MAX_R = 8
 KB_MAX_W = 4
@@ -186,6 +188,12 @@ class kb_stats(C.Structure):
         ("mispredictions", C.c_uint32),
         ("exchange_mode", C.c_uint32),
         ("chain_hits", C.c_uint32),
+        ("pipeline", C.c_uint32),
+        ("pipe_requests", C.c_uint32),
+        ("pipe_urgent", C.c_uint32),
+        ("pipe_extends", C.c_uint32),
+        ("pipe_patched", C.c_uint32),
+        ("pipe_patch_entries", C.c_uint32),
     ]
 
 

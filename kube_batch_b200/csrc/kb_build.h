@@ -194,7 +194,7 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf,
-                bf_job_pos, bf_ctl; };
+                bf_job_pos, bf_ctl, pipe_g, modlog, pcand; };
 struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0,
                 bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes, ord_chain; };
 
@@ -209,6 +209,7 @@ struct BuiltSession {
   std::vector<int32_t> job_min_avail;
   uint32_t rank = 0, world = 1, tile_lo = 0, tile_hi = 0, nodes_per_rank = 0, tpi = 1, overlap = 0;
   uint32_t kchain = 1;               // classes per launch (visit_chain_kernel), 1 = off
+  uint32_t pipe = 0, pipe_S = 0, pipe_tpc = 0;   // persistent pipeline (cycle_kernel): scanner CTAs, resident tiles per scanner CTA
   std::vector<ClassPref> class_pref; // [C] preferred node-affinity terms per class — HOST ONLY (read by tests/emu's prototype of
   bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
@@ -218,7 +219,7 @@ struct BuiltSession {
   // control block; no resource predicate, no nodeorder (the first node that passes wins = lowest node index).
   void bind_backfill(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     bind(D, mb, ib);
-    D.backfill = 1; D.overlap = 0; D.kchain = 1;
+    D.backfill = 1; D.overlap = 0; D.kchain = 1; D.pipe = 0;
     D.cf.fit_mode = 1; D.cf.nodeorder = 0; D.cf.score_bias = 0;
     D.To = Tb;
     D.classes = (ClassRec*)(ib + oi.bf_classes);        // same ids; `initreq` holds Resreq (EvalConf.fit_mode)
@@ -252,6 +253,8 @@ struct BuiltSession {
     D.ord_run = (uint32_t*)(ib + oi.ord_run); D.ord_peek = (uint32_t*)(ib + oi.ord_peek);
     D.overlap = overlap;
     D.kchain = kchain; D.ord_chain = (uint32_t*)(ib + oi.ord_chain);
+    D.pipe = pipe; D.pipe_S = pipe_S; D.pipe_tpc = pipe_tpc; D.pipe_pad = 0;
+    D.pg = (PipeG*)(mb + om.pipe_g); D.modlog = (uint32_t*)(mb + om.modlog); D.pcand = (uint64_t*)(mb + om.pcand);
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -263,7 +266,8 @@ struct BuiltSession {
 inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e,
                          uint32_t rank = 0, uint32_t world = 1, int overlap_mode = -1 /* -1 auto, 0 off, 1 on */,
                          uint32_t kchain = 1 /* classes per launch: 1, 2 or 4 (single GPU, no overlap) */,
-                         bool allow_pref = false /* accept preferred node-affinity terms (tests/emu prototype only) */) {
+                         bool allow_pref = false /* accept preferred node-affinity terms (tests/emu prototype only) */,
+                         int pipe_mode = 0 /* persistent pipeline (cycle_kernel): 0 off, 1 when the geometry allows it */) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
@@ -469,6 +473,19 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   const uint32_t n_groups = (B.tile_hi - B.tile_lo + B.tpi - 1) / B.tpi;
   // overlap mode (one GPU) keeps one SM for the replayer CTA
   const uint32_t grid = std::max(1u, std::min(n_groups, GMAX > 1 ? GMAX - 1 : GMAX));   // one SM stays free for the replayer CTA
+  // persistent pipeline: scanner CTAs keep their tiles resident in shared memory; built for the common record geometry
+  // (R = 3, W = 2: cpu, memory, one scalar; 128 label / taint / port atoms) on one GPU (or replicated on every rank)
+  B.pipe = 0; B.pipe_S = 0; B.pipe_tpc = 0;
+  if (pipe_mode > 0 && world <= 1 && !B.has_pref && NT > 0 && R == 3 && W == 2 && GMAX >= 2) {
+    const size_t tile_bytes = (size_t)ncols * TILE_NODES * 8;
+    const uint32_t max_tpc = (uint32_t)((227 * 1024 - 8 * 1024) / tile_bytes);
+    const uint32_t smax = GMAX - 1;
+    const uint32_t tpc = (NT + smax - 1) / smax;
+    if (tpc <= max_tpc) { B.pipe = 1; B.pipe_tpc = tpc; B.pipe_S = (NT + tpc - 1) / tpc; }
+  }
+  om.pipe_g = mut.alloc(sizeof(PipeG));
+  om.modlog = mut.alloc(((size_t)To + 64) * 4);
+  om.pcand = mut.alloc((size_t)PIPE_RING * std::max(1u, B.pipe_S) * KTOP * 8);
   om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
   om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
   om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
@@ -651,7 +668,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     memcpy(H.q_static_off, cnt.data(), (size_t)(Q + 1) * 4);
     std::vector<uint32_t> fill(cnt.begin(), cnt.end() - 1);
     std::vector<uint32_t> next_diff(std::max(1u, To), 0xFFFFFFFFu);     // first later slot (static walk) with another class
-    const bool want_chain = world <= 1 && (kchain == 2 || kchain == 4);
+    const bool want_chain = world <= 1 && (kchain == 2 || kchain == 4 || B.pipe);
     const bool want_peek = world <= 1 && (overlap_mode > 0 || (overlap_mode < 0 && N >= 65536 && Q == 1));
     for (uint32_t j = 0; j < J; ++j) H.q_static[fill[s->job_queue[j]]++] = j;
     for (uint32_t q = 0; q < Q; ++q) {

@@ -54,6 +54,23 @@ struct Ctl {
   uint32_t excl[32];
   unsigned long long list[32];
   unsigned long long patch[32];
+  // ---- persistent pipeline (cycle_kernel, kb_pipe.cuh): scan requests posted / of which the replayer had to wait for
+  //      (no usable look-ahead list), candidate-chain extensions, lists consumed with a non-empty patch set, log entries patched
+  uint32_t pipe_requests, pipe_urgent, pipe_extends, pipe_patched, pipe_patch_entries, pipe_pad;
+  unsigned long long cyc_wait;     // replayer cycles spent between posting the visit and the eval warps' results (list wait + eval)
+};
+
+// ---- persistent pipeline: global mailboxes between the replayer CTA and the scanner CTAs (kb_pipe.cuh) ----
+constexpr uint32_t PIPE_RING = 32;       // scan requests that can be in flight (request / list slots)
+constexpr uint32_t PIPE_PATCH = 32;      // modification-log entries a look-ahead list may lag behind at its use
+struct PipeG {
+  uint32_t log_head;                     // modification-log entries published (release) by the replayer's writer warp
+  uint32_t quit;                         // the cycle is over (or failed): scanners exit
+  uint32_t error;
+  uint32_t pad0[29];
+  unsigned long long req[PIPE_RING][2];  // NCCL-LL style words (tag << 32 | payload): class, stamp; tag = seq + 1
+  uint32_t ticket[PIPE_RING];            // scanner CTAs that delivered their list for the slot
+  unsigned long long list[PIPE_RING][2 * KTOP];   // merged top-32 of a request: two LL words (low / high half) per key
 };
 
 struct DevSession {
@@ -120,6 +137,12 @@ struct DevSession {
   // through CUDA IPC; peer_base[r] is rank r's region as mapped into THIS process (peer_base[rank] is local).
   uint32_t p2p;
   uint64_t* peer_base[8];
+  // persistent pipeline (one cooperative launch per cycle, kb_pipe.cuh): pipe_S scanner CTAs keep pipe_tpc node tiles each
+  // resident in shared memory, the last CTA replays
+  uint32_t pipe, pipe_S, pipe_tpc, pipe_pad;
+  PipeG* pg;
+  uint32_t* modlog;       // [To + 64] node ids in modification order (one entry per node a visit chain modified)
+  uint64_t* pcand;        // [PIPE_RING][pipe_S][KTOP] per-CTA candidate lists of the requests in flight
 };
 constexpr uint32_t KB_MAX_WORLD = 8;
 constexpr uint32_t P2P_RANK_U64 = (1 + 2 * KB_MAX_R + 6 + 3 * KB_MAX_W) * 32;         // keys + widest record block

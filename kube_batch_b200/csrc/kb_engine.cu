@@ -25,6 +25,7 @@
 
 #include "kb_build.h"
 #include "kb_kernels.cuh"
+#include "kb_pipe.cuh"
 
 using namespace kb;
 
@@ -102,6 +103,11 @@ struct kb_engine {
   int overlap_mode = -1;
   bool pdl = true;                          // programmatic dependent launch of the visit chain (KB_PDL=0 disables)
   uint32_t kchain_req = KB_DEFAULT_CHAIN;   // classes per launch requested (flags / KB_CHAIN), 1 = visit_kernel
+  bool pipe_req = true;                     // persistent pipeline (cycle_kernel) when the session's geometry allows it
+  bool shard_req = false;                   // world > 1: shard the node axis (per-launch kernels + exchange) instead of replicating
+  bool replicated = false;                  // world > 1 and every rank runs the whole cycle on the full node table
+  bool coop_ok = false;                     // device supports cooperative launches
+  size_t pipe_smem = 0;
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
   DevSession graph_dev{};              // kernel parameter the graph was captured with
@@ -243,6 +249,10 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   e->rank = world > 1 ? opts->rank : 0; e->world = world;
   e->overlap_mode = (opts->flags & KB_ENGINE_NO_OVERLAP) ? 0 : (opts->flags & KB_ENGINE_FORCE_OVERLAP) ? 1 : -1;
   e->kchain_req = (opts->flags & KB_ENGINE_CHAIN_OFF) ? 1u : (opts->flags & KB_ENGINE_CHAIN4) ? 4u : (opts->flags & KB_ENGINE_CHAIN2) ? 2u : KB_DEFAULT_CHAIN;
+  e->pipe_req = !(opts->flags & KB_ENGINE_NO_PIPE) && e->overlap_mode != 1 && e->kchain_req == 1;
+  e->shard_req = (opts->flags & KB_ENGINE_SHARD) != 0;
+  if (const char* pp = getenv("KB_PIPE")) e->pipe_req = atoi(pp) != 0;
+  if (const char* sh = getenv("KB_SHARD")) e->shard_req = atoi(sh) != 0;
   if (const char* pd = getenv("KB_PDL")) e->pdl = atoi(pd) != 0;
   if (const char* kc = getenv("KB_CHAIN")) { const int v = atoi(kc); if (v == 1 || v == 2 || v == 4) e->kchain_req = (uint32_t)v; }
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -252,7 +262,7 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
     delete e; return KB_E_CUDA;
   }
   cudaDeviceProp prop;
-  if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) e->sm_count = prop.multiProcessorCount;
+  if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) { e->sm_count = prop.multiProcessorCount; e->coop_ok = prop.cooperativeLaunch != 0; }
   if (world > 1) {
     ncclUniqueId id;
     memcpy(id.internal, opts->nccl_unique_id, sizeof id.internal);
@@ -297,8 +307,16 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     if (kchain == 4 && chain_smem_header<4>() + 2 * tpi * tile_b > lim) kchain = 2;
     if (kchain == 2 && chain_smem_header<2>() + 2 * tpi * tile_b > lim) kchain = 1;
   }
-  if (int rc = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode, kchain))
-    return fail(e, rc, "%s", be.msg.c_str());
+  // world > 1: by default every rank runs the whole cycle on the full (replicated) node table — the cycle is bound by the
+  // serial replay, not by the scan, so sharding the scan only adds an exchange per visit; KB_ENGINE_SHARD
+  // selects the node-sharded per-launch path instead.
+  const bool pipe_try = e->pipe_req && e->coop_ok && (e->world == 1 || !e->shard_req);
+  int rc_build = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, pipe_try ? 0u : (uint32_t)e->rank,
+                               pipe_try ? 1u : (uint32_t)e->world, e->overlap_mode, kchain, false, pipe_try ? 1 : 0);
+  if (rc_build == KB_OK && pipe_try && !B.pipe && e->world > 1)       // geometry outside the pipeline: fall back to the sharded path
+    rc_build = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode, kchain);
+  if (rc_build) return fail(e, rc_build, "%s", be.msg.c_str());
+  e->replicated = e->world > 1 && B.world == 1;
   const uint32_t R = B.R, W = B.W, N = B.N, T = B.T, J = B.J, Q = B.Q, C = B.C, NT = B.NT, ncols = B.ncols, To = B.To, grid = B.grid;
   const size_t tile_u64 = (size_t)ncols * TILE_NODES;
   Slab& mut = B.mut; Slab& imm = B.imm;
@@ -336,7 +354,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
   CUDA_TRY(e, cudaStreamSynchronize(e->stream));
   B.bind(e->dev, e->d_mut, e->d_imm);
-  e->dev.p2p = (e->world > 1 && e->p2p) ? 1u : 0u;
+  e->dev.p2p = (e->world > 1 && e->p2p && !e->replicated) ? 1u : 0u;
   for (int r = 0; r < 8; ++r) e->dev.peer_base[r] = e->p2p_peer[r];
   B.bind_backfill(e->dev_bf, e->d_mut, e->d_imm);
   e->dev_bf.p2p = e->dev.p2p;
@@ -363,7 +381,17 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->replay_smem = ((sizeof(VisitSmem) + 127) / 128) * 128;
   CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(replay_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->replay_smem));
-  if (!e->graph_exec || memcmp(&e->graph_dev, &e->dev, sizeof(DevSession)) != 0) {
+  e->pipe_smem = 0;
+  if (e->dev.pipe) {
+    const size_t scan_b = pipe_scan_header() + (size_t)e->dev.pipe_tpc * e->tile_smem;
+    e->pipe_smem = std::max(scan_b, sizeof(ReplaySmem<18>));
+    CUDA_TRY(e, cudaFuncSetAttribute(cycle_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pipe_smem));
+    int occ = 0;
+    CUDA_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cycle_kernel<3, 2>, PIPE_THREADS, e->pipe_smem));
+    if (occ < 1 || (int)e->dev.pipe_S + 1 > e->sm_count * occ)
+      return fail(e, KB_E_CUDA, "cycle_kernel: %u CTAs cannot be co-resident (occupancy %d x %d SMs)", e->dev.pipe_S + 1, occ, e->sm_count);
+  }
+  if (!e->dev.pipe && (!e->graph_exec || memcmp(&e->graph_dev, &e->dev, sizeof(DevSession)) != 0)) {
     free_graph(e);
     // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch).
     // Sharded: scan shard -> ncclAllGather (top-32 keys + node records per rank) -> identical replay on every rank.
@@ -410,7 +438,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
   if (!backfill) CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
   else seed_backfill_kernel<<<1, 32, 0, e->stream>>>(e->dev.ctl, e->dev_bf.ctl, e->allocate_ran ? 1 : 0);
   if (!backfill) e->allocate_ran = true;
-  if (e->world > 1 && D.p2p) {
+  if (e->world > 1 && D.p2p && !e->replicated) {
     // a new action restarts the exchange sequence at 1: clear my flags, then make sure every rank has done so before
     // anybody can raise one (the all-gather is only used as a stream-ordered barrier)
     CUDA_TRY(e, cudaMemsetAsync(e->p2p_local + P2P_FLAG_OFF, 0, 2 * KB_MAX_WORLD * 8, e->stream));
@@ -420,10 +448,17 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
   uint32_t launches = 0;
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
   const uint64_t cap = 4ull * ((uint64_t)e->J + e->To + e->Tb) + 1024;
-  const bool use_graph = !backfill && e->graph_exec;
+  const bool use_pipe = !backfill && D.pipe;
+  const bool use_graph = !backfill && !use_pipe && e->graph_exec;
   const uint32_t batch = backfill ? 16u : BATCH;
   for (;;) {
-    if (use_graph) {
+    if (use_pipe) {
+      // ONE cooperative launch runs the whole cycle: pipe_S scanner CTAs with resident tiles + the replayer CTA
+      DevSession dv = D;
+      void* args[] = {(void*)&dv};
+      CUDA_TRY(e, cudaLaunchCooperativeKernel((const void*)cycle_kernel<3, 2>, dim3(D.pipe_S + 1), dim3(PIPE_THREADS), args, e->pipe_smem, e->stream));
+      launches += 1;
+    } else if (use_graph) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
       launches += ((e->world == 1 || D.p2p) ? 1 : 2) * BATCH;
     } else {
@@ -448,6 +483,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
     CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, D.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (e->h_ctl->done) break;
+    if (use_pipe) return fail(e, e->h_ctl->error == 3 ? KB_E_CUDA : KB_E_STATE, "cycle_kernel ended without finishing the cycle (device error %u)", e->h_ctl->error);
     if (launches > cap) return fail(e, KB_E_STATE, "%s cycle did not terminate within %llu launches", backfill ? "backfill" : "allocate", (unsigned long long)cap);
   }
   if (e->J) {
@@ -485,7 +521,9 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
     stats->cyc_scan = c.cyc_scan; stats->cyc_merge = c.cyc_merge; stats->cyc_replay = c.cyc_replay; stats->cyc_total = c.cyc_total; stats->cyc_steps = c.cyc_steps; stats->cyc_ctl = c.cyc_ctl;
     stats->predictions = c.predictions; stats->mispredictions = c.mispredictions;
     stats->chain_hits = c.chain_hits;
-    stats->exchange_mode = e->world == 1 ? 0u : (D.p2p ? 2u : 1u);
+    stats->exchange_mode = e->world == 1 ? 0u : (e->replicated ? 3u : (D.p2p ? 2u : 1u));
+    stats->pipe_requests = c.pipe_requests; stats->pipe_urgent = c.pipe_urgent; stats->pipe_extends = c.pipe_extends;
+    stats->pipe_patched = c.pipe_patched; stats->pipe_patch_entries = c.pipe_patch_entries; stats->pipeline = use_pipe ? 1u : 0u;
     stats->h2d_bytes = backfill ? 0 : (uint64_t)e->mut_bytes + e->imm_bytes;
     stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)e->J * 8 + (uint64_t)(launches / batch) * sizeof(Ctl);
   }

@@ -1,0 +1,773 @@
+// kb_pipe.cuh — the allocate cycle as ONE persistent cooperative kernel (sm_100a).
+//
+// cycle_kernel<R, W>   grid = pipe_S scanner CTAs + 1 replayer CTA, all co-resident, one launch per kb_allocate.
+//
+//   scanner CTA   keeps pipe_tpc node tiles (TMA bulk copy at start) RESIDENT in shared memory for the whole cycle.
+//                 Four warp groups (4 warps = 128 threads = one node per thread per tile) serve scan requests
+//                 seq = g, g+4, ... concurrently: K1 predicate bitmask + K2 fused score (eval_pair) for the request's
+//                 class over the CTA's nodes, warp bitonic top-32 (K3), group fold, list -> global; the LAST group to
+//                 deliver (ticket) merges the pipe_S lists and publishes the request's top-32 (NCCL-LL style words:
+//                 the payload carries its own sequence tag, no separate flag, no fence on the reader).
+//                 A 17th warp (applier) follows the modification log and refreshes the resident tiles.
+//   replayer CTA  warp 0 walks the visits exactly like allocate.go:89-193: for the class of the next run it takes the
+//                 look-ahead list that was requested a few visits earlier (stamp = log position at the request),
+//                 PATCHES it — every node modified since the stamp is dropped from the list and re-evaluated from the
+//                 replayer's own copy (hot ring) — and replays.  16 eval warps evaluate, in ONE round, the candidate
+//                 pool (<= 32 list entries + <= 32 patch entries) at placement depths 0..7 (the state after k more
+//                 placements of this class is a pure function of the record), so a step of the run is a warp arg-max
+//                 plus a shared-memory read.  Warp 17 (writer) writes modified records back, appends the log, publishes
+//                 its head (st.release: no L1 invalidation on this SM) and posts scan requests for the predicted classes.
+//
+// Exactness (same argument as the per-launch kernels, generalised to a stale list): let L be the exact top-32 of class c
+// for the table state at log position s, floor = its 32nd key, M = nodes in log[s, now).  A node outside L and outside M
+// is unmodified since s, so its current key is below floor.  Every node of M is re-evaluated on its current record.  The
+// 32 best of (L \ M) U M are kept; the floor rises to the best key dropped.  A pick is certified iff best >= floor, else
+// the run stops and a fresh list is requested (STOP_RESCAN).  A scanner may read a record WHILE it is being rewritten
+// (torn read): that node is in log[s, now) for every list it can have influenced, so its entry is dropped and
+// re-evaluated; a garbage key can only displace true candidates, which raises nothing above the published floor.
+// tests/emu re-enacts the protocol (random staleness, garbage keys for in-flight nodes) against the oracle.
+#pragma once
+
+#include "kb_kernels.cuh"
+
+namespace kb {
+
+constexpr int PIPE_WARPS = 18;
+constexpr int PIPE_THREADS = PIPE_WARPS * 32;
+constexpr int PIPE_DEPTH = 8;              // placement depths evaluated up front per candidate
+constexpr uint32_t PIPE_HOT = 128;         // hot ring: records of the most recent log entries (replayer shared memory)
+constexpr uint32_t PIPE_RQ = 16;           // requested-table entries (most recent scan requests)
+constexpr uint32_t PIPE_CMDS = 64;
+constexpr long long PIPE_DEADLINE = 3000000000ll;     // cycles a wait may take before the cycle is aborted (error 3)
+
+enum PipeCmd : uint32_t { PCMD_WB = 1, PCMD_REQ = 2, PCMD_QUIT = 3 };
+
+// ---- memory-model helpers ----
+__device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {        // MEMBAR.ALL.GPU + store, no L1 invalidation
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_2u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+// record held in registers (column c at r[c]); NC = tile_ncols(R, W) is a compile-time constant here
+struct RegAcc {
+  const uint64_t* r; uint32_t R, W;
+  __device__ __forceinline__ uint64_t col(uint32_t c) const { return r[c]; }
+  __device__ __forceinline__ double idle(uint32_t k) const { return u64_as_double(col(col_idle(R, k))); }
+  __device__ __forceinline__ double rel(uint32_t k) const { return u64_as_double(col(col_rel(R, k))); }
+  __device__ __forceinline__ int64_t alloc_cpu() const { return (int64_t)col(col_alloc_cpu(R)); }
+  __device__ __forceinline__ int64_t alloc_mem() const { return (int64_t)col(col_alloc_mem(R)); }
+  __device__ __forceinline__ int64_t nz_cpu() const { return (int64_t)col(col_nz_cpu(R)); }
+  __device__ __forceinline__ int64_t nz_mem() const { return (int64_t)col(col_nz_mem(R)); }
+  __device__ __forceinline__ int32_t pods() const { return (int32_t)(uint32_t)(col(col_pods(R)) & 0xFFFFFFFFull); }
+  __device__ __forceinline__ int32_t max_pods() const { return (int32_t)(uint32_t)(col(col_pods(R)) >> 32); }
+  __device__ __forceinline__ uint32_t flags() const { return (uint32_t)col(col_flags(R)); }
+  __device__ __forceinline__ uint64_t labels(uint32_t w) const { return col(col_labels(R, W, w)); }
+  __device__ __forceinline__ uint64_t taints(uint32_t w) const { return col(col_taints(R, W, w)); }
+  __device__ __forceinline__ uint64_t ports(uint32_t w) const { return col(col_ports(R, W, w)); }
+};
+
+// NodeInfo.AddTask of one task of class c on a record (node_info.go:172-212 as allocate.go:160-183 drives it): Allocate
+// consumes Idle when InitResreq <= Idle, else Pipeline consumes Releasing.  Returns that fits-idle bit of the state BEFORE.
+// Branch-free selects: no dynamic register indexing.
+template <int RR, int WW>
+__device__ __forceinline__ bool advance_rec(uint64_t* rec, const ClassRec& c) {
+  constexpr uint32_t R = RR, W = WW;
+  RegAcc a{rec, R, W};
+  const bool fi = res_less_equal(R, [&](uint32_t k) { return c.initreq[k]; }, [&](uint32_t k) { return a.idle(k); });
+#pragma unroll
+  for (uint32_t k = 0; k < R; ++k) {
+    const double id = u64_as_double(rec[col_idle(R, k)]), rl = u64_as_double(rec[col_rel(R, k)]);
+    rec[col_idle(R, k)] = double_as_u64(fi ? KB_DSUB(id, c.resreq[k]) : id);
+    rec[col_rel(R, k)] = double_as_u64(fi ? rl : KB_DSUB(rl, c.resreq[k]));
+  }
+  rec[col_nz_cpu(R)] = (uint64_t)((int64_t)rec[col_nz_cpu(R)] + c.nz_cpu);
+  rec[col_nz_mem(R)] = (uint64_t)((int64_t)rec[col_nz_mem(R)] + c.nz_mem);
+  rec[col_pods(R)] = rec[col_pods(R)] + 1ull;
+#pragma unroll
+  for (uint32_t w = 0; w < W; ++w) rec[col_ports(R, W, w)] |= c.port_own[w];
+  return fi;
+}
+
+// bitonic sort / merge networks carrying a 32-bit payload with the key (descending, lane 0 = best)
+__device__ __forceinline__ void warp_sort_desc_kv(uint64_t& v, uint32_t& pl, int lane) {
+#pragma unroll
+  for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const uint64_t o = __shfl_xor_sync(FULL, v, j);
+      const uint32_t op = __shfl_xor_sync(FULL, pl, j);
+      const bool take_max = (((lane & k) == 0) == ((lane & j) == 0));
+      const bool take_o = take_max ? (o > v) : (o < v);
+      v = take_o ? o : v; pl = take_o ? op : pl;
+    }
+  }
+}
+// top-32 of two descending lists with payloads; `dropped` = the best key that did not make it (0 if none)
+__device__ __forceinline__ void warp_merge_top32_kv(uint64_t& a, uint32_t& ap, uint64_t b, uint32_t bp, uint64_t& dropped, int lane) {
+  const uint64_t br = __shfl_sync(FULL, b, 31 - lane);
+  const uint32_t bpr = __shfl_sync(FULL, bp, 31 - lane);
+  const bool tb = br > a;
+  const uint64_t lo = tb ? a : br;
+  uint64_t v = tb ? br : a;
+  uint32_t pl = tb ? bpr : ap;
+  dropped = warp_max_u64(lo);
+#pragma unroll
+  for (int j = 16; j > 0; j >>= 1) {
+    const uint64_t o = __shfl_xor_sync(FULL, v, j);
+    const uint32_t op = __shfl_xor_sync(FULL, pl, j);
+    const bool take_max = (lane & j) == 0;
+    const bool take_o = take_max ? (o > v) : (o < v);
+    v = take_o ? o : v; pl = take_o ? op : pl;
+  }
+  a = v; ap = pl;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scanner CTA
+// ---------------------------------------------------------------------------------------------
+struct ScanGroup {
+  ClassRec cls;
+  uint32_t cls_id, stamp, quit, is_last;
+  uint64_t wl[4][KTOP];
+};
+struct ScanSmem {
+  uint32_t applied;          // log entries applied to the resident tiles (volatile)
+  uint32_t pad[3];
+  uint64_t mbar;
+  uint64_t pad2;
+  ScanGroup grp[4];
+};
+__host__ __device__ constexpr size_t pipe_scan_header() { return ((sizeof(ScanSmem) + 127) / 128) * 128; }
+
+template <int RR, int WW>
+__device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char* smem_raw) {
+  constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
+  ScanSmem& sm = *reinterpret_cast<ScanSmem*>(smem_raw);
+  uint64_t* tiles = reinterpret_cast<uint64_t*>(smem_raw + pipe_scan_header());
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PipeG* pg = S.pg;
+  const uint32_t cta = blockIdx.x, nS = S.pipe_S, tpc = S.pipe_tpc;
+  const uint32_t t0 = cta * tpc, t1 = min(S.NT, t0 + tpc), ntl = t1 > t0 ? t1 - t0 : 0;
+  constexpr uint32_t tile_u64 = NC * TILE_NODES;
+  if (tid == 0) {
+    sm.applied = 0;
+    mbar_init(&sm.mbar, 1); fence_mbar_init();
+    mbar_expect_tx(&sm.mbar, ntl * tile_u64 * 8u);
+    for (uint32_t i = 0; i < ntl; ++i) tma_load_1d(tiles + (size_t)i * tile_u64, S.tiles + (size_t)(t0 + i) * tile_u64, tile_u64 * 8u, &sm.mbar);
+  }
+  __syncthreads();
+  mbar_wait(&sm.mbar, 0);
+
+  if (warp == 17) return;
+  if (warp == 16) {
+    // ---------------- applier: follow the modification log, refresh the resident copies of MY nodes ----------------
+    uint32_t cursor = 0;
+    for (;;) {
+      const uint32_t head = ld_acquire_u32(&pg->log_head);
+      if (head != cursor) {
+        for (uint32_t base = cursor; base < head; base += 32) {
+          const uint32_t i = base + lane;
+          if (i < head) {
+            const uint32_t node = __ldcg(&S.modlog[i]);
+            const uint32_t t = node / TILE_NODES;
+            if (t >= t0 && t < t1) {
+              const uint64_t* g = S.tiles + (size_t)t * tile_u64 + (node % TILE_NODES);
+              uint64_t* d = tiles + (size_t)(t - t0) * tile_u64 + (node % TILE_NODES);
+              uint64_t tmp[NC];
+#pragma unroll
+              for (uint32_t c = 0; c < NC; ++c) tmp[c] = __ldcg(g + (size_t)c * TILE_NODES);
+#pragma unroll
+              for (uint32_t c = 0; c < NC; ++c) d[(size_t)c * TILE_NODES] = tmp[c];
+            }
+          }
+        }
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) *((volatile uint32_t*)&sm.applied) = head;
+        cursor = head;
+      } else {
+        if (ld_relaxed_u32(&pg->quit)) return;
+        __nanosleep(64);
+      }
+    }
+  }
+
+  // ---------------- scan groups ----------------
+  const int g = warp >> 2, wg = warp & 3, gt = tid & 127;
+  ScanGroup& G = sm.grp[g];
+  const int bar_id = 1 + g;
+  for (uint32_t seq = (uint32_t)g;; seq += 4) {
+    const uint32_t slot = seq % PIPE_RING, tag = seq + 1;
+    if (wg == 0) {
+      unsigned long long w0 = 0, w1 = 0;
+      uint32_t quit = 0;
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      for (;;) {
+        ld_relaxed_2u64(&pg->req[slot][0], w0, w1);
+        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
+        if (ld_relaxed_u32(&pg->quit)) { quit = 1; break; }
+        if (clock64() > deadline) { quit = 1; if (lane == 0) { pg->error = 3; st_release_u32(&pg->quit, 1u); } break; }
+        __nanosleep(32);
+      }
+      if (lane == 0) { G.cls_id = (uint32_t)w0; G.stamp = (uint32_t)w1; G.quit = quit; }
+    }
+    bar_sync(bar_id, 128);
+    if (G.quit) return;
+    const uint32_t cls_id = G.cls_id, stamp = G.stamp;
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&G.cls);
+      for (uint32_t i = gt; i < sizeof(ClassRec) / 4; i += 128) dst[i] = src[i];
+    }
+    {
+      // the resident tiles must reflect every log entry below the request's stamp (entries at or above it are the replayer's patch)
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      while (*((volatile uint32_t*)&sm.applied) < stamp) {
+        if (clock64() > deadline) { pg->error = 3; st_release_u32(&pg->quit, 1u); break; }
+        __nanosleep(32);
+      }
+      __threadfence_block();
+    }
+    bar_sync(bar_id, 128);
+    uint64_t mylist = 0;
+    for (uint32_t i = 0; i < ntl; ++i) {
+      const uint32_t node = (t0 + i) * TILE_NODES + gt;
+      uint64_t key = 0;
+      if (node < S.N) {
+        ColAcc acc{tiles + (size_t)i * tile_u64, (uint32_t)gt, TILE_NODES, R, W};
+        key = eval_pair<RR, WW>(S.cf, G.cls, acc, node, nullptr);
+      }
+      const uint64_t thr = __shfl_sync(FULL, mylist, 31);
+      if (__any_sync(FULL, key > thr)) {
+        key = warp_sort_desc(key, lane);
+        mylist = warp_merge_top32(mylist, key, lane);
+      }
+    }
+    if (wg) G.wl[wg][lane] = mylist;
+    bar_sync(bar_id, 128);
+    if (wg == 0) {
+#pragma unroll
+      for (int w = 1; w < 4; ++w) mylist = warp_merge_top32(mylist, G.wl[w][lane], lane);
+      S.pcand[((size_t)slot * nS + cta) * KTOP + lane] = mylist;
+      __threadfence();
+      __syncwarp();
+      if (lane == 0) {
+        const uint32_t old = atomicAdd(&pg->ticket[slot], 1u);
+        G.is_last = (old == nS - 1) ? 1u : 0u;
+      }
+    }
+    bar_sync(bar_id, 128);
+    if (G.is_last) {
+      // ---------------- last group for this request: merge the CTAs' lists, publish ----------------
+      __threadfence();
+      uint64_t acc = 0;
+      for (uint32_t c = (uint32_t)wg; c < nS; c += 4) {
+        const uint64_t cur = __ldcg(&S.pcand[((size_t)slot * nS + c) * KTOP + lane]);
+        const uint64_t thr = __shfl_sync(FULL, acc, 31);
+        const uint64_t head = __shfl_sync(FULL, cur, 0);
+        if (head > thr) acc = warp_merge_top32(acc, cur, lane);
+      }
+      if (wg) G.wl[wg][lane] = acc;
+      bar_sync(bar_id, 128);
+      if (wg == 0) {
+#pragma unroll
+        for (int w = 1; w < 4; ++w) acc = warp_merge_top32(acc, G.wl[w][lane], lane);
+        if (lane == 0) pg->ticket[slot] = 0;
+        __threadfence();
+        st_relaxed_u64(&pg->list[slot][2 * lane], ((unsigned long long)tag << 32) | (acc & 0xFFFFFFFFull));
+        st_relaxed_u64(&pg->list[slot][2 * lane + 1], ((unsigned long long)tag << 32) | (acc >> 32));
+      }
+      bar_sync(bar_id, 128);      // G.wl / G.is_last are reused by the next request
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// replayer CTA
+// ---------------------------------------------------------------------------------------------
+template <int NC>
+struct ReplaySmem {
+  ClassRec cls;
+  Ctl ctl;
+  // visit descriptor (main warp -> eval warps)
+  uint32_t v_slot, v_tag, v_stamp, v_npatch, v_pvalid, v_quit, v_err, v_pad;
+  uint32_t pnode[32];                          // patch entry i: node of log entry v_stamp + i (valid bit in v_pvalid: latest entry of its node)
+  // eval results
+  uint64_t v_list[KTOP];                       // the request's list as published
+  uint64_t ckey[PIPE_DEPTH][64];               // key of pool slot s after d more placements of the class
+  uint32_t cfi[PIPE_DEPTH][2];                 // fits-idle ballots of the same states
+  uint64_t lsort_key[KTOP]; uint32_t lsort_slot[KTOP];   // surviving list entries, compacted (descending)
+  uint64_t psort_key[KTOP]; uint32_t psort_slot[KTOP];   // patch entries' fresh keys, sorted (descending)
+  // chain extension of ONE pool slot beyond PIPE_DEPTH
+  uint64_t ext_key[32]; uint32_t ext_fi, ext_slot, ext_base, ext_pad;
+  // hot ring: entry i of the modification log lives at i % PIPE_HOT until the writer has written it back and no list needs it
+  uint32_t hot_node[PIPE_HOT], hot_cnt[PIPE_HOT], hot_cls[PIPE_HOT];
+  uint64_t hot_rec[NC][PIPE_HOT];
+  // requested table
+  uint32_t rq_cls[PIPE_RQ], rq_seq[PIPE_RQ], rq_stamp[PIPE_RQ];
+  // main -> writer command ring
+  uint32_t cmd_kind[PIPE_CMDS], cmd_a[PIPE_CMDS], cmd_b[PIPE_CMDS];
+  uint32_t cmd_head, cmd_tail;                 // volatile: written by main / by the writer
+  uint32_t pub_head;                           // log entries the writer has published (volatile)
+  uint32_t sink;
+};
+
+// eval warps: pool slot (h * 32 + lane) at placement depth d
+template <int RR, int WW>
+__device__ __forceinline__ void pipe_eval_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int e, const int lane) {
+  constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
+  const int d = e >> 1, h = e & 1;
+  PipeG* pg = S.pg;
+  for (;;) {
+    bar_sync(1, 17 * 32);                       // go
+    if (*((volatile uint32_t*)&sm.v_quit)) return;
+    uint64_t rec[NC];
+    uint32_t node = 0;
+    bool have = false;
+    uint64_t listkey = 0;
+    if (h == 0) {
+      // the request's list: lane l polls its own two LL words (payload + tag in one 8-byte word each)
+      const uint32_t slot = sm.v_slot, tag = sm.v_tag;
+      unsigned long long w0 = 0, w1 = 0;
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      bool ok = true;
+      for (;;) {
+        ld_relaxed_2u64(&pg->list[slot][2 * lane], w0, w1);
+        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
+        if (clock64() > deadline) { ok = false; break; }
+      }
+      if (!__all_sync(FULL, ok)) { if (lane == 0) sm.v_err = 1; w0 = w1 = 0; }
+      listkey = (w0 & 0xFFFFFFFFull) | (w1 << 32);
+      node = key_node(listkey);
+      have = listkey != 0;
+      const uint32_t np = sm.v_npatch;
+      for (uint32_t i = 0; i < np; ++i) have = have && (sm.pnode[i] != node);     // modified since the stamp: the patch entry speaks for it
+      if (have) {
+        const uint64_t* g = S.tiles + (size_t)(node / TILE_NODES) * ((size_t)NC * TILE_NODES) + (node % TILE_NODES);
+#pragma unroll
+        for (uint32_t c = 0; c < NC; ++c) rec[c] = __ldcg(g + (size_t)c * TILE_NODES);
+      }
+    } else {
+      have = ((sm.v_pvalid >> lane) & 1u) != 0;
+      node = sm.pnode[lane];
+      if (have) {
+        const uint32_t hi = (sm.v_stamp + (uint32_t)lane) % PIPE_HOT;
+#pragma unroll
+        for (uint32_t c = 0; c < NC; ++c) rec[c] = sm.hot_rec[c][hi];
+      }
+    }
+    uint64_t key = 0;
+    bool fi = false;
+    if (have) {
+      for (int k = 0; k < d; ++k) advance_rec<RR, WW>(rec, sm.cls);
+      RegAcc acc{rec, R, W};
+      key = eval_pair<RR, WW>(S.cf, sm.cls, acc, node, &fi);
+    }
+    sm.ckey[d][h * 32 + lane] = key;
+    const unsigned fim = __ballot_sync(FULL, have && fi);
+    if (lane == 0) sm.cfi[d][h] = fim;
+    if (d == 0) {
+      if (h == 0) {
+        // surviving list entries keep their order: compact them with a ballot
+        sm.v_list[lane] = listkey;
+        const unsigned am = __ballot_sync(FULL, key != 0);
+        const unsigned src = __fns(am, 0, lane + 1);
+        const uint64_t ck = __shfl_sync(FULL, key, (int)(src & 31u));
+        sm.lsort_key[lane] = src < 32u ? ck : 0ull;
+        sm.lsort_slot[lane] = src < 32u ? src : 0u;
+      } else {
+        uint64_t k2 = key; uint32_t sl = 32u + (uint32_t)lane;
+        warp_sort_desc_kv(k2, sl, lane);
+        sm.psort_key[lane] = k2; sm.psort_slot[lane] = sl;
+      }
+    }
+    bar_sync(1, 17 * 32);                       // done
+  }
+}
+
+// writer / planner warp: write-backs, log, requests — everything that needs a membar, off the replay's critical path
+template <int RR, int WW>
+__device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int lane) {
+  constexpr uint32_t R = RR, NC = 2 * RR + 6 + 3 * WW;
+  PipeG* pg = S.pg;
+  uint32_t tail = 0;
+  for (;;) {
+    while (*((volatile uint32_t*)&sm.cmd_head) == tail) __nanosleep(40);
+    __threadfence_block();
+    const uint32_t kind = sm.cmd_kind[tail % PIPE_CMDS], a = sm.cmd_a[tail % PIPE_CMDS], b = sm.cmd_b[tail % PIPE_CMDS];
+    if (kind == PCMD_WB) {
+      // log entries [a, b): record -> global table, Used += cnt x Resreq (node_info.go:203), node id -> modlog
+      for (uint32_t base = a; base < b; base += 32) {
+        const uint32_t i = base + lane;
+        if (i < b) {
+          const uint32_t hi = i % PIPE_HOT, node = sm.hot_node[hi], cnt = sm.hot_cnt[hi];
+          uint64_t* gt = S.tiles + (size_t)(node / TILE_NODES) * ((size_t)NC * TILE_NODES) + (node % TILE_NODES);
+#pragma unroll
+          for (uint32_t c = 0; c < NC; ++c) gt[(size_t)c * TILE_NODES] = sm.hot_rec[c][hi];
+          const ClassRec& cr = S.classes[sm.hot_cls[hi]];
+#pragma unroll
+          for (uint32_t k = 0; k < R; ++k) {
+            double u = S.node_used[(size_t)k * S.N + node];
+            const double rq = cr.resreq[k];
+            for (uint32_t z = 0; z < cnt; ++z) u = KB_DADD(u, rq);
+            S.node_used[(size_t)k * S.N + node] = u;
+          }
+          st_release_u32(&S.modlog[i], node);       // this lane's stores above are performed before the entry
+        }
+      }
+      __syncwarp();
+      if (lane == 0) { st_release_u32(&pg->log_head, b); *((volatile uint32_t*)&sm.pub_head) = b; }
+    } else if (kind == PCMD_REQ) {
+      // a = class, b = seq.  The slot's previous request (seq - PIPE_RING) must have been answered before it is reused.
+      const uint32_t slot = b % PIPE_RING;
+      if (b >= PIPE_RING) {
+        const uint32_t otag = b - PIPE_RING + 1;
+        const long long deadline = clock64() + PIPE_DEADLINE;
+        for (;;) {
+          unsigned long long w0, w1;
+          ld_relaxed_2u64(&pg->list[slot][2 * lane], w0, w1);
+          const bool ok = (uint32_t)(w0 >> 32) == otag && (uint32_t)(w1 >> 32) == otag;
+          if (__all_sync(FULL, ok)) break;
+          if (clock64() > deadline) { if (lane == 0) { pg->error = 3; st_release_u32(&pg->quit, 1u); } break; }
+        }
+      }
+      if (lane == 0) {
+        const unsigned long long tag = (unsigned long long)(b + 1) << 32;
+        const uint32_t stamp = *((volatile uint32_t*)&sm.pub_head);
+        st_relaxed_u64(&pg->req[slot][1], tag | stamp);
+        st_relaxed_u64(&pg->req[slot][0], tag | a);
+      }
+    } else {   // PCMD_QUIT
+      if (lane == 0) st_release_u32(&pg->quit, 1u);
+      return;
+    }
+    tail += 1;
+    __syncwarp();
+    if (lane == 0) *((volatile uint32_t*)&sm.cmd_tail) = tail;
+  }
+}
+
+template <int RR, int WW>
+__device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char* smem_raw) {
+  constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
+  using RS = ReplaySmem<NC>;
+  RS& sm = *reinterpret_cast<RS*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  PipeG* pg = S.pg;
+  Ctl* gctl = S.ctl;
+  if (warp == 0) {
+    load_ctl(sm.ctl, gctl, lane);
+    if (lane < (int)PIPE_RQ) { sm.rq_cls[lane] = 0xFFFFFFFFu; sm.rq_seq[lane] = 0; sm.rq_stamp[lane] = 0; }
+    if (lane == 0) { sm.cmd_head = 0; sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.ext_slot = 0xFFFFFFFFu; }
+  }
+  __syncthreads();
+  if (warp >= 1 && warp <= 16) { pipe_eval_warp<RR, WW>(S, sm, warp - 1, lane); return; }
+  if (warp == 17) { pipe_writer_warp<RR, WW>(S, sm, lane); return; }
+
+  // ---------------- main warp ----------------
+  Ctl& c = sm.ctl;
+  uint32_t priv_head = 0;        // log entries appended (the writer publishes them a little later)
+  uint32_t next_seq = 0;         // scan requests posted
+  uint32_t cmd_head = 0;
+  uint32_t fresh_floor = 0;      // after a rescan stop: only a list requested at or after this log position will do
+  bool failed = false;
+  auto push_cmd = [&](uint32_t kind, uint32_t a, uint32_t b) {       // whole warp calls it
+    while (cmd_head - *((volatile uint32_t*)&sm.cmd_tail) >= PIPE_CMDS) __nanosleep(20);
+    if (lane == 0) {
+      sm.cmd_kind[cmd_head % PIPE_CMDS] = kind; sm.cmd_a[cmd_head % PIPE_CMDS] = a; sm.cmd_b[cmd_head % PIPE_CMDS] = b;
+      __threadfence_block();
+      *((volatile uint32_t*)&sm.cmd_head) = cmd_head + 1;
+    }
+    cmd_head += 1;
+    __syncwarp();
+  };
+  // newest request for class `cls` in the requested table: returns found; seq / stamp by reference
+  auto rq_lookup = [&](uint32_t cls, uint32_t& seq, uint32_t& stamp) -> bool {
+    const bool m = lane < (int)PIPE_RQ && sm.rq_cls[lane] == cls;
+    const uint32_t s1 = m ? sm.rq_seq[lane] + 1u : 0u;
+    const uint32_t best = __reduce_max_sync(FULL, s1);
+    if (best == 0) return false;
+    const int src = __ffs(__ballot_sync(FULL, m && s1 == best)) - 1;
+    seq = best - 1u;
+    stamp = __shfl_sync(FULL, m ? sm.rq_stamp[lane] : 0u, src);
+    return true;
+  };
+  auto post_request = [&](uint32_t cls) -> uint32_t {
+    const uint32_t seq = next_seq++;
+    if (lane == 0) { sm.rq_cls[seq % PIPE_RQ] = cls; sm.rq_seq[seq % PIPE_RQ] = seq; sm.rq_stamp[seq % PIPE_RQ] = priv_head; c.pipe_requests += 1; }
+    __syncwarp();
+    push_cmd(PCMD_REQ, cls, seq);
+    return seq;
+  };
+
+  const long long t_cycle0 = clock64();
+  while (!c.done && !failed) {
+    const uint32_t cls_id = c.cur_class;
+    const long long t_v0 = clock64();
+    // ---------------- visit start: which list ----------------
+    uint32_t seq = 0, stamp = 0;
+    bool usable = rq_lookup(cls_id, seq, stamp);
+    usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor;
+    if (!usable) { seq = post_request(cls_id); stamp = priv_head; if (lane == 0) c.pipe_urgent += 1; }
+    fresh_floor = 0;
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
+      for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
+    }
+    // patch set: log entries [stamp, priv_head); of several entries of one node only the latest holds its current record
+    const uint32_t npatch = priv_head - stamp;
+    {
+      const bool pv = (uint32_t)lane < npatch;
+      const uint32_t pn = pv ? sm.hot_node[(stamp + lane) % PIPE_HOT] : (0xFFFFFFF0u - (uint32_t)lane);
+      const unsigned same = __match_any_sync(FULL, pn);
+      const bool latest = pv && (same >> (lane + 1)) == 0u;
+      const unsigned pvalid = __ballot_sync(FULL, latest);
+      sm.pnode[lane] = pn;
+      if (lane == 0) {
+        sm.v_slot = seq % PIPE_RING; sm.v_tag = seq + 1; sm.v_stamp = stamp; sm.v_npatch = npatch; sm.v_pvalid = pvalid;
+        if (npatch) { c.pipe_patched += 1; c.pipe_patch_entries += npatch; }
+      }
+    }
+    __syncwarp();
+    bar_sync(1, 17 * 32);          // go: the 16 eval warps poll the list, gather, evaluate depths 0..7 of the pool
+    bar_sync(1, 17 * 32);          // done
+    if (*((volatile uint32_t*)&sm.v_err)) { if (lane == 0) { c.error = 3; } failed = true; break; }
+    const long long t_v1 = clock64();
+    // ---------------- pool -> 32 lane-owned candidates ----------------
+    uint64_t cur_key = sm.lsort_key[lane];
+    uint32_t slot = sm.lsort_slot[lane];
+    uint64_t dropped = 0;
+    warp_merge_top32_kv(cur_key, slot, sm.psort_key[lane], sm.psort_slot[lane], dropped, lane);
+    const uint64_t f0 = sm.v_list[KTOP - 1];
+    const uint64_t floor_key = f0 > dropped ? f0 : dropped;
+    const bool have = cur_key != 0;
+    const uint32_t my_node = key_node(cur_key);
+    const uint32_t my_h = slot >> 5, my_l = slot & 31u;
+    uint32_t depth = 0;                        // placements made on MY candidate
+    bool cur_fi = have && ((sm.cfi[0][my_h] >> my_l) & 1u);
+    if (lane == 0) { c.scans += 1; c.pairs_scanned += (unsigned long long)S.N; c.pairs_replayed += (unsigned long long)__popc(sm.v_pvalid) ; }
+    // my candidate's base record (state at depth 0), for the final state at write-back time
+    uint64_t rec0[NC];
+    if (have) {
+      if (my_h == 0) {
+        const uint64_t* g = S.tiles + (size_t)(my_node / TILE_NODES) * ((size_t)NC * TILE_NODES) + (my_node % TILE_NODES);
+#pragma unroll
+        for (uint32_t cc = 0; cc < NC; ++cc) rec0[cc] = __ldcg(g + (size_t)cc * TILE_NODES);
+      } else {
+        const uint32_t hi = (stamp + my_l) % PIPE_HOT;
+#pragma unroll
+        for (uint32_t cc = 0; cc < NC; ++cc) rec0[cc] = sm.hot_rec[cc][hi];
+      }
+    }
+    // key / fits-idle of MY candidate at depth dd (dd >= 1): precomputed chain, else the extension buffer
+    auto chain_has = [&](uint32_t dd) -> bool { return dd < (uint32_t)PIPE_DEPTH || (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u); };
+    auto chain_key = [&](uint32_t dd) -> uint64_t { return dd < (uint32_t)PIPE_DEPTH ? sm.ckey[dd][slot] : sm.ext_key[dd - sm.ext_base]; };
+    auto chain_fi = [&](uint32_t dd) -> bool {
+      return dd < (uint32_t)PIPE_DEPTH ? (((sm.cfi[dd][my_h] >> my_l) & 1u) != 0) : (((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0);
+    };
+    // extension: the whole warp evaluates depths base .. base+31 of the owner's candidate
+    auto extend = [&](const uint32_t owner) {
+      const uint32_t oslot = __shfl_sync(FULL, slot, owner), odepth = __shfl_sync(FULL, depth, owner), onode = __shfl_sync(FULL, my_node, owner);
+      uint64_t r2[NC];
+#pragma unroll
+      for (uint32_t cc = 0; cc < NC; ++cc) r2[cc] = __shfl_sync(FULL, rec0[cc], owner);
+      const uint32_t base = odepth + 1, target = base + (uint32_t)lane;
+      for (uint32_t k = 0; k < target; ++k) advance_rec<RR, WW>(r2, sm.cls);
+      RegAcc acc{r2, R, W};
+      bool f = false;
+      const uint64_t k2 = eval_pair<RR, WW>(S.cf, sm.cls, acc, onode, &f);
+      __syncwarp();
+      sm.ext_key[lane] = k2;
+      const unsigned fm = __ballot_sync(FULL, f);
+      if (lane == 0) { sm.ext_fi = fm; sm.ext_slot = oslot; sm.ext_base = base; c.pipe_extends += 1; c.pairs_replayed += 32ull; }
+      __syncwarp();
+    };
+    if (lane == 0) sm.ext_slot = 0xFFFFFFFFu;
+    __syncwarp();
+
+    bool rescanned = false;
+    for (;;) {              // runs of this class (consecutive visits of one class share the pool)
+      if (c.done || c.cur_class != cls_id) break;
+      const uint32_t j = (uint32_t)c.cur_job;
+      const uint32_t q = c.cur_queue;
+      const uint32_t jend = S.job_ord_off[j + 1];
+      uint32_t run_left = c.cur_run;
+      uint32_t placed = 0, popped = 0, n_alloc = 0;
+      uint32_t reason = STOP_RUN_DONE;
+      const uint32_t pos0 = __shfl_sync(FULL, lane == 0 ? S.job_pos[j] : 0u, 0);
+      int32_t ready = 0, min_avail = 0;
+      if (lane == 0) { ready = S.job_ready[j]; min_avail = S.job_min_avail[j]; }
+      ready = __shfl_sync(FULL, ready, 0); min_avail = __shfl_sync(FULL, min_avail, 0);
+      double jalloc = 0.0, qalloc = 0.0, my_rq = 0.0;
+      if ((uint32_t)lane < R) {
+        my_rq = sm.cls.resreq[lane];
+        if (S.drf_present) jalloc = S.job_alloc[(size_t)lane * S.J + j];
+        if (S.proportion_present) qalloc = S.q_allocated[(size_t)lane * S.Q + q];
+      }
+      const uint32_t step0 = c.step;
+      uint32_t my_task = 0;
+      const long long t_run0 = clock64();
+      while (run_left > 0) {      // steps: one pending task each (allocate.go:129-189)
+        const uint64_t best = warp_max_u64(cur_key);
+        if (best < floor_key) { reason = STOP_RESCAN; break; }
+        const uint32_t pos = pos0 + popped;
+        if ((popped & 31u) == 0) my_task = (pos + lane < jend) ? S.ord_task[pos + lane] : 0u;
+        const uint32_t task = __shfl_sync(FULL, my_task, popped & 31u);
+        popped += 1;
+        run_left -= 1;
+        if (best == 0) { reason = STOP_NOFIT; break; }              // allocate.go:144-148
+        const uint32_t owner = (uint32_t)__ffs(__ballot_sync(FULL, cur_key == best)) - 1u;
+        const unsigned ownbits = __shfl_sync(FULL, (chain_has(depth + 1) ? 1u : 0u) | (cur_fi ? 2u : 0u), owner);
+        if (!(ownbits & 1u)) extend(owner);
+        const bool fits_idle = (ownbits & 2u) != 0;
+        if ((uint32_t)lane == owner) {             // ssn.Allocate / ssn.Pipeline: my candidate moves to its next state
+          depth += 1;
+          cur_key = chain_key(depth);
+          cur_fi = chain_fi(depth);
+        }
+        jalloc = KB_DADD(jalloc, my_rq);
+        qalloc = KB_DADD(qalloc, my_rq);
+        if (lane == 0) {
+          kb_decision dd;
+          dd.node = (int32_t)key_node(best);
+          dd.kind = fits_idle ? KB_KIND_ALLOCATED : KB_KIND_PIPELINED;
+          dd.dispatched = 0; dd.reserved = 0;
+          dd.step = step0 + placed;
+          dd.dispatch_step = 0xFFFFFFFFu;
+          S.dec[task] = dd;
+        }
+        placed += 1;
+        n_alloc += fits_idle ? 1u : 0u;
+        const bool jr = !S.gang_ready || (ready + (int32_t)n_alloc) >= min_avail;     // ssn.JobReady
+        if (jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }                   // allocate.go:185-188
+      }
+      if (lane == 0) {
+        S.job_pos[j] = pos0 + popped;
+        S.job_ready[j] = ready + (int32_t)n_alloc;
+        S.job_placed[j] += placed;
+        c.step = step0 + placed;
+        c.tasks_processed += popped;
+        c.pairs_logical += (unsigned long long)popped * S.N;
+        c.tasks_allocated += n_alloc;
+        c.tasks_pipelined += placed - n_alloc;
+      }
+      if ((uint32_t)lane < R && placed) {
+        if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = jalloc;
+        if (S.proportion_present) S.q_allocated[(size_t)lane * S.Q + q] = qalloc;
+      }
+      if (placed) {        // drf.calculateShare / proportion.updateShare: one FP64 division per dimension, in parallel lanes
+        if (S.drf_present) {
+          double v = 0.0;
+          if ((uint32_t)lane < R && ((S.total_dims_mask >> lane) & 1u)) v = share_of(jalloc, S.total[lane]);
+          const uint64_t m = warp_max_u64(double_as_u64(v));
+          if (lane == 0) S.job_share[j] = u64_as_double(m);
+        }
+        if (S.proportion_present) {
+          double v = 0.0;
+          const uint32_t present = S.q_deserved_present[q] | 3u;
+          if ((uint32_t)lane < R && ((present >> lane) & 1u)) v = share_of(qalloc, S.q_deserved[(size_t)lane * S.Q + q]);
+          const uint64_t m = warp_max_u64(double_as_u64(v));
+          if (lane == 0) S.q_share[q] = u64_as_double(m);
+        }
+      }
+      __syncwarp();
+      const long long t_run1 = clock64();
+      if (lane == 0) {
+        if (reason == STOP_RESCAN) c.rescans += 1;
+        after_run<0>(S, c, reason, placed, true);
+        const long long t_run2 = clock64();
+        c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
+        c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
+      }
+      __syncwarp();
+      if (reason == STOP_RESCAN) { rescanned = true; break; }
+    }
+
+    // ---------------- end of the visit chain on this class: modified candidates -> hot ring + log ----------------
+    const bool modified = depth > 0;
+    const unsigned mm = __ballot_sync(FULL, modified);
+    const uint32_t nmod = (uint32_t)__popc(mm);
+    if (nmod) {
+      // the writer must have written back the ring entries this append overwrites
+      while (priv_head + nmod - *((volatile uint32_t*)&sm.pub_head) > PIPE_HOT - PIPE_PATCH) __nanosleep(20);
+      if (modified) {
+        for (uint32_t k = 0; k < depth; ++k) advance_rec<RR, WW>(rec0, sm.cls);
+        const uint32_t hi = (priv_head + (uint32_t)__popc(mm & ((1u << lane) - 1u))) % PIPE_HOT;
+#pragma unroll
+        for (uint32_t cc = 0; cc < NC; ++cc) sm.hot_rec[cc][hi] = rec0[cc];
+        sm.hot_node[hi] = my_node; sm.hot_cnt[hi] = depth; sm.hot_cls[hi] = cls_id;
+      }
+      __syncwarp();
+      push_cmd(PCMD_WB, priv_head, priv_head + nmod);
+      priv_head += nmod;
+    }
+    if (rescanned) fresh_floor = priv_head;
+    // ---------------- planner: scan requests for the classes of the next visits ----------------
+    if (!c.done) {
+      uint32_t pc[KB_CHAIN_MAX];
+      pc[0] = c.cur_class;
+      {
+        const uint32_t s0 = lane == 0 ? S.job_pos[(uint32_t)c.cur_job] : 0u;
+        const uint32_t s1 = __shfl_sync(FULL, s0, 0);
+#pragma unroll
+        for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX; ++k) pc[k + 1] = S.ord_chain[(size_t)s1 * (KB_CHAIN_MAX - 1) + k];
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < KB_CHAIN_MAX; ++k) {
+        const uint32_t pcls = pc[k];
+        if (pcls == 0xFFFFFFFFu) continue;
+        if (k == 0 && rescanned) continue;                      // the visit start posts the fresh request itself
+        uint32_t s2 = 0, st2 = 0;
+        const bool f = rq_lookup(pcls, s2, st2);
+        const uint32_t age = priv_head - st2;
+        const bool ok = f && (k == 0 ? age <= PIPE_PATCH : age + 8u * k <= 24u);
+        if (!ok) post_request(pcls);
+      }
+    }
+    if (lane == 0) {
+      const long long t_end = clock64();
+      c.cyc_wait += (unsigned long long)(t_v1 - t_v0);
+      c.cyc_scan += (unsigned long long)(t_v1 - t_v0);
+      c.cyc_replay += (unsigned long long)(t_end - t_v1);
+    }
+    __syncwarp();
+  }
+
+  // ---------------- wind down ----------------
+  if (lane == 0) { *((volatile uint32_t*)&sm.v_quit) = 1; }
+  __syncwarp();
+  bar_sync(1, 17 * 32);                         // releases the eval warps
+  push_cmd(PCMD_QUIT, 0, 0);
+  while (*((volatile uint32_t*)&sm.cmd_tail) != cmd_head - 1 + 0u && *((volatile uint32_t*)&sm.cmd_tail) != cmd_head) __nanosleep(40);
+  if (lane == 0) {
+    c.cyc_total += (unsigned long long)(clock64() - t_cycle0);
+    if (failed && !c.error) c.error = 3;
+    const uint32_t perr = ld_relaxed_u32(&pg->error);
+    if (perr && !c.error) c.error = perr;
+  }
+  __syncwarp();
+  store_ctl(gctl, c, lane);
+}
+
+template <int RR, int WW>
+__global__ void __launch_bounds__(PIPE_THREADS, 1)
+cycle_kernel(const __grid_constant__ DevSession S) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  if (blockIdx.x == gridDim.x - 1) pipe_replayer<RR, WW>(S, smem_raw);
+  else pipe_scanner<RR, WW>(S, smem_raw);
+}
+
+}  // namespace kb

@@ -51,6 +51,15 @@ struct Emu {
   // feasible nodes and how many feasible nodes reach it; the replay of that launch consumes them
   int64_t pref_max = 0;
   uint32_t pref_nmax = 0;
+  // persistent pipeline (cycle_kernel): modification log with the records, the scanners' lagging view of the table
+  bool pipe = false;
+  std::vector<uint32_t> log_node;
+  std::vector<std::vector<uint64_t>> log_rec;
+  std::vector<uint64_t> view;          // scanner-side copy of the node tiles
+  uint32_t view_pos = 0;               // log entries applied to it
+  uint64_t rng = 0x9E3779B97F4A7C15ull;
+  bool need_fresh = false;             // the last visit stopped for a rescan
+  uint32_t next() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); }
 };
 
 // NodeAffinityPriority of one (class, node): count = sum of the weights of the matching preferred terms (weight 0 skipped)
@@ -407,6 +416,85 @@ void emu_launch_chain(Emu& E) {
   publish_chain(S, c);
 }
 
+// One visit chain of cycle_kernel (kb_pipe.cuh).  The scanners answered the request for cur_class from THEIR copy of the
+// table as of an earlier log position (`stamp`, random lag of up to PIPE_PATCH entries; the copy only moves forward); nodes
+// with entries in log[stamp, head) may have been read torn, so their scanned keys are ARBITRARY (old state, current state,
+// zero, or an absurdly good score).  The replayer drops those nodes from the list, re-evaluates them on their current
+// records (hot ring), keeps the 32 best, raises the floor to the best key dropped, and replays.
+void emu_launch_pipe(Emu& E) {
+  const DevSession& S = *E.cur;
+  Ctl& c = *S.ctl;
+  E.launches += 1;
+  if (c.done) return;
+  const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  const size_t tile_u64 = (size_t)ncols * TILE_NODES;
+  const uint32_t cls_id = c.cur_class;
+  const ClassRec& cls = S.classes[cls_id];
+  const uint32_t head = (uint32_t)E.log_node.size();
+  if (E.view.empty()) { E.view.assign(S.tiles, S.tiles + (size_t)std::max(1u, S.NT) * tile_u64); E.view_pos = head; }
+  uint32_t lag = E.need_fresh ? 0u : E.next() % (PIPE_PATCH + 1);
+  if (E.next() % 4 == 0) lag = 0;
+  uint32_t stamp = head > lag ? head - lag : 0;
+  if (stamp < E.view_pos) stamp = E.view_pos;                  // the applier never goes back
+  E.need_fresh = false;
+  for (uint32_t i = E.view_pos; i < stamp; ++i) {              // applier: entries below the stamp are in the resident tiles
+    const uint32_t n = E.log_node[i];
+    uint64_t* vt = E.view.data() + (size_t)(n / TILE_NODES) * tile_u64 + (n % TILE_NODES);
+    for (uint32_t cc = 0; cc < ncols; ++cc) vt[(size_t)cc * TILE_NODES] = E.log_rec[i][cc];
+  }
+  E.view_pos = stamp;
+  std::vector<uint32_t> inflight;                              // distinct nodes of log[stamp, head)
+  for (uint32_t i = stamp; i < head; ++i) if (std::find(inflight.begin(), inflight.end(), E.log_node[i]) == inflight.end()) inflight.push_back(E.log_node[i]);
+  // ---- scanners ----
+  std::vector<uint64_t> keys;
+  for (uint32_t n = 0; n < S.N; ++n) {
+    uint64_t k;
+    if (std::find(inflight.begin(), inflight.end(), n) != inflight.end()) {
+      const uint32_t how = E.next() % 4;
+      if (how == 0) { TileAcc acc{E.view.data() + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W}; k = eval_pair(S.cf, cls, acc, n, nullptr); }
+      else if (how == 1) { TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W}; k = eval_pair(S.cf, cls, acc, n, nullptr); }
+      else if (how == 2) k = 0;
+      else k = pack_key(S.cf.score_bias + 1000 + (int64_t)(E.next() % 7), n);        // garbage from a torn read
+    } else {
+      TileAcc acc{E.view.data() + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+      k = eval_pair(S.cf, cls, acc, n, nullptr);
+    }
+    if (k) keys.push_back(k);
+  }
+  std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
+  keys.resize(KTOP, 0ull);
+  uint64_t fl = keys[KTOP - 1];
+  // ---- replayer: patch ----
+  std::vector<uint64_t> pool;
+  for (uint64_t k : keys) if (k && std::find(inflight.begin(), inflight.end(), key_node(k)) == inflight.end()) pool.push_back(k);
+  for (uint32_t n : inflight) {
+    TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+    const uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr);
+    c.pairs_replayed += 1;
+    if (k) pool.push_back(k);
+  }
+  std::sort(pool.begin(), pool.end(), [](uint64_t a, uint64_t b) { return a > b; });
+  if (pool.size() > (size_t)KTOP) { fl = std::max(fl, pool[KTOP]); pool.resize(KTOP); }
+  c.scans += 1; c.pairs_scanned += S.N;
+  std::vector<Cand> cand(KTOP);
+  for (int l = 0; l < KTOP && l < (int)pool.size(); ++l) {
+    Cand& cd = cand[l];
+    cd.cur_key = pool[l]; cd.have = true;
+    cd.node = key_node(cd.cur_key);
+    const uint64_t* gt = S.tiles + (size_t)(cd.node / TILE_NODES) * tile_u64 + (cd.node % TILE_NODES);
+    for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = gt[(size_t)cc * TILE_NODES];
+    SlotAcc acc{&cd.st[0], R, W};
+    cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+  }
+  E.need_fresh = replay_core(S, c, cls_id, cand, fl);
+  write_back(S, cls, cand);
+  for (auto& cd : cand) {
+    if (!cd.modified) continue;
+    E.log_node.push_back(cd.node);
+    E.log_rec.emplace_back(cd.st[cd.which].col, cd.st[cd.which].col + ncols);
+  }
+}
+
 // gang_commit_kernel, serially: a job's processed slots of the allocate view, then of the backfill view
 void emu_gang_commit(const DevSession& S, const DevSession& Sbf, const int32_t* ready0) {
   for (uint32_t j = 0; j < S.J; ++j) {
@@ -461,12 +549,14 @@ long long kbemu_div_0_to_10(long long a, long long b) { return div_0_to_10(a, b)
 uint32_t kbemu_buf_u64(void* h);
 const char* kbemu_last_error(void) { return g_err.c_str(); }
 
-// mode (single rank): 0 = scan/replay overlap protocol, 1 = plain one-class launches, 2 / 4 = chained visits (visit_chain_kernel<K>)
+// mode (single rank): 0 = scan/replay overlap protocol, 1 = plain one-class launches, 2 / 4 = chained visits (visit_chain_kernel<K>),
+// 5 = persistent pipeline (cycle_kernel: stale look-ahead lists + patch; only the R = 3 / W = 2 geometry runs it, other sessions fall back to mode 1)
 void* kbemu_create2(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t rank, uint32_t world, uint32_t mode) {
   Emu* E = new Emu();
   BuildErr be;
   // mode 1 (plain launches) also accepts preferred node-affinity terms: the emulation prototypes the two-pass scan (a12)
-  if (build_session(snap, conf, 148, E->B, &be, rank, world, mode == 0 ? 1 : 0, mode >= 2 ? mode : 1, mode == 1)) { g_err = be.msg; delete E; return nullptr; }
+  if (build_session(snap, conf, 148, E->B, &be, rank, world, mode == 0 ? 1 : 0, (mode == 2 || mode == 4) ? mode : 1, mode == 1, mode == 5 ? 1 : 0)) { g_err = be.msg; delete E; return nullptr; }
+  E->pipe = mode == 5;
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
   E->cur = &E->S;
@@ -478,7 +568,8 @@ void* kbemu_create(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t
 int kbemu_reload(void* h, const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t mode) {
   Emu* E = (Emu*)h;
   BuildErr be;
-  if (int rc = build_session(snap, conf, 148, E->B, &be, 0, 1, mode == 0 ? 1 : 0, mode >= 2 ? mode : 1)) { g_err = be.msg; return rc; }
+  if (int rc = build_session(snap, conf, 148, E->B, &be, 0, 1, mode == 0 ? 1 : 0, (mode == 2 || mode == 4) ? mode : 1, false, mode == 5 ? 1 : 0)) { g_err = be.msg; return rc; }
+  E->pipe = mode == 5; E->log_node.clear(); E->log_rec.clear(); E->view.clear(); E->view_pos = 0; E->need_fresh = false;
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
   E->cur = &E->S;
@@ -493,7 +584,8 @@ int kbemu_run(void* h, uint32_t actions) {
     if (!((actions ? actions : 1u) & (1u << pass))) continue;
     if (pass == 1) emu_begin_backfill(*E, ((actions ? actions : 1u) & 1u) != 0);
     while (!E->cur->ctl->done) {
-      if (E->cur->overlap) emu_launch_overlap(*E);
+      if (E->pipe && !E->cur->backfill) emu_launch_pipe(*E);
+      else if (E->cur->overlap) emu_launch_overlap(*E);
       else if (E->cur->kchain > 1) emu_launch_chain(*E);
       else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
       if (E->launches > guard) { g_err = "emulated cycle did not terminate"; return KB_E_STATE; }
@@ -568,7 +660,8 @@ int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t
     if (!((actions ? actions : 1u) & (1u << pass))) continue;
     if (pass == 1) emu_begin_backfill(*E, ((actions ? actions : 1u) & 1u) != 0);
     while (!E->cur->ctl->done) {
-      if (E->cur->overlap) emu_launch_overlap(*E);
+      if (E->pipe && !E->cur->backfill) emu_launch_pipe(*E);
+      else if (E->cur->overlap) emu_launch_overlap(*E);
       else if (E->cur->kchain > 1) emu_launch_chain(*E);
       else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
       if (E->launches > guard) { g_err = "emulated cycle did not terminate"; delete E; return KB_E_STATE; }

@@ -204,6 +204,36 @@ def test_chained_visits_save_launches_and_patch_small_clusters():
     assert e4.result.kernel_launches * 3 < e1.result.kernel_launches       # single queue, static job order: predictions hit
 
 
+# ---------------- persistent pipeline (cycle_kernel): stale look-ahead lists + patch, garbage keys for in-flight nodes ----------------
+@pytest.mark.parametrize("seed", range(16))
+def test_pipeline_protocol_random_sessions(seed):
+    """kb_pipe.cuh: the list of a visit was scanned at an EARLIER log position (random lag <= 32 entries) from the scanners' own
+    copy of the table; nodes modified since then carry arbitrary scanned keys (torn reads) and are dropped + re-evaluated."""
+    rng = np.random.default_rng(4000 + seed)
+    tasks = int(rng.integers(5, 400))
+    s = synth.random_session(seed + 900, tasks=tasks, jobs=int(rng.integers(1, min(tasks, 60) + 1)), nodes=int(rng.integers(1, 300)),
+                             queues=int(rng.integers(1, 5)), min_member_frac=float(rng.choice([0.0, 0.5, 1.0])),
+                             hetero=float(rng.choice([0, 0.3, 1.0])), prio_levels=int(rng.integers(1, 4)),
+                             oversub=float(rng.choice([0.7, 1.3, 3.0])))
+    for cname, conf in CONFS.items():
+        check(s, conf, f"pipe seed{seed}/{cname}", mode=5)
+        check(s, conf, f"pipe seed{seed}/{cname}/+backfill", actions=3, mode=5)
+
+
+def test_pipeline_protocol_small_clusters_and_baseline_configs():
+    # few nodes: most of the list is in flight at every visit
+    s = synth.random_session(31, tasks=600, jobs=120, nodes=24, queues=1, min_member_frac=0.0, hetero=1.0, oversub=0.9)
+    check(s, CONFS["default"], "pipe small", mode=5)
+    s = synth.random_session(33, tasks=900, jobs=90, nodes=40, queues=3, min_member_frac=0.5, hetero=0.3, oversub=1.1)
+    check(s, CONFS["default"], "pipe small multi-queue", mode=5)
+    for name in ("c1", "c2"):
+        s, conf = synth.make(name)
+        check(s, conf, "pipe " + name, mode=5)
+    for (R, W) in [(8, 4), (5, 2)]:
+        s = synth.random_session(60, tasks=150, jobs=15, nodes=300, queues=2, hetero=0.3, R=R, W=W)
+        check(s, CONFS["default"], f"pipe R{R}W{W}", mode=5)
+
+
 # ---------------- backfill (actions/backfill/backfill.go:40-71), the action after allocate in the default list ----------------
 @pytest.mark.parametrize("seed", range(16))
 def test_backfill_random_sessions(seed):
