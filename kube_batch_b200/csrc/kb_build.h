@@ -501,8 +501,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   om.dec = mut.alloc((size_t)std::max(1u, T) * sizeof(kb_decision));
   om.cand = mut.alloc((size_t)grid * KTOP * 8 * KB_CHAIN_MAX);
   om.ctl = mut.alloc(sizeof(Ctl));
-  om.sendbuf = mut.alloc((size_t)(1 + ncols) * 32 * 8);
-  om.recvbuf = mut.alloc((size_t)std::max(1u, world) * (1 + ncols) * 32 * 8);
+  om.sendbuf = mut.alloc((size_t)xchg_u64(ncols) * 8);
+  om.recvbuf = mut.alloc((size_t)std::max(1u, world) * xchg_u64(ncols) * 8);
   om.bf_job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
   om.bf_ctl = mut.alloc(sizeof(Ctl));
   oi.classes = imm.alloc((size_t)C * sizeof(ClassRec));

@@ -188,11 +188,12 @@ KB_HD int64_t key_score(uint64_t key) { return (int64_t)(key >> 32); }
 //
 // K1 (predicate bitmask) + K2 (fused score) for one (class, node) pair against the node's CURRENT state.
 // Returns the packed key, 0 if predicateFn would return an error.  `fits_idle` reports
-// InitResreq <= Idle, which decides Allocate vs Pipeline at commit (allocate.go:160).
+// InitResreq <= Idle, which decides Allocate vs Pipeline at commit (allocate.go:160); `pred_ok` (optional) reports
+// ssn.PredicateFn alone — backfill needs it to reproduce ssn.Allocate's status-before-AddTask order (session.go:241-262).
 // RR / WW: compile-time copies of cf.R / cf.W (0 = read them at run time).  The kernels instantiate the common geometry
 // (R = 3, W = 2) so that every loop below unrolls into straight-line code; semantics are identical.
 template <int RR = 0, int WW = 0, class NodeAcc>
-KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n, uint32_t node_idx, bool* fits_idle) {
+KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n, uint32_t node_idx, bool* fits_idle, bool* pred_ok = nullptr) {
   // Written branch-free on purpose: a lone warp (the replay) or one warp per SM sub-partition (the scan)
   // hides latency only through instruction-level parallelism, so every check is computed and AND-ed.
   const uint32_t R = RR ? (uint32_t)RR : cf.R, W = WW ? (uint32_t)WW : cf.W;
@@ -211,11 +212,12 @@ KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n
   fr = fr & (cf.fit_mode == 0);                 // backfill only ever allocates from Idle
   if (fits_idle) *fits_idle = fi;
   bool ok = fi | fr;
+  bool pok = true;            // ssn.PredicateFn alone (the predicates plugin), irrespective of the resource fit
 
   if (cf.predicates) {
     const uint32_t fl = n.flags();
-    ok = ok & (n.max_pods() > n.pods());                                                             // predicates.go:127
-    ok = ok & ((fl & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) == 0);   // vendored :1675-1698
+    pok = pok & (n.max_pods() > n.pods());                                                             // predicates.go:127
+    pok = pok & ((fl & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) == 0);   // vendored :1675-1698
     uint64_t bad = 0;
     uint64_t miss[KB_MAX_AFF_TERMS] = {0, 0, 0, 0};
 #if defined(__CUDA_ARCH__)
@@ -231,19 +233,21 @@ KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n
 #endif
       for (uint32_t t = 0; t < KB_MAX_AFF_TERMS; ++t) miss[t] |= (lab & c.aff[t][w]) ^ c.aff[t][w];
     }
-    ok = ok & (bad == 0);
+    pok = pok & (bad == 0);
     // required node affinity: OR of AND-terms (:944-968); unused term slots hold all-zero masks, so gate on n_aff
     bool any = c.n_aff == 0;
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (uint32_t t = 0; t < KB_MAX_AFF_TERMS; ++t) any = any | ((t < c.n_aff) & (miss[t] == 0));
-    ok = ok & any;
+    pok = pok & any;
     const bool memp = cf.mem_pressure && (c.flags & KB_TASK_BEST_EFFORT_QOS) && (fl & KB_NODE_MEM_PRESSURE);   // :1633-1650
     const bool diskp = cf.disk_pressure && (fl & KB_NODE_DISK_PRESSURE);                                       // :1654-1660
     const bool pidp = cf.pid_pressure && (fl & KB_NODE_PID_PRESSURE);                                          // :1664-1671
-    ok = ok & !(memp | diskp | pidp);
+    pok = pok & !(memp | diskp | pidp);
   }
+  if (pred_ok) *pred_ok = pok;
+  ok = ok & pok;
 
   int64_t score = cf.score_bias;
   if (cf.nodeorder) {

@@ -56,7 +56,8 @@ struct Ctl {
   unsigned long long patch[32];
   // ---- persistent pipeline (cycle_kernel, kb_pipe.cuh): scan requests posted / of which the replayer had to wait for
   //      (no usable look-ahead list), candidate-chain extensions, lists consumed with a non-empty patch set, log entries patched
-  uint32_t pipe_requests, pipe_urgent, pipe_extends, pipe_patched, pipe_patch_entries, pipe_pad;
+  uint32_t pipe_requests, pipe_urgent, pipe_extends, pipe_patched, pipe_patch_entries;
+  uint32_t phantoms;      // backfill: tasks left Allocated on no node (ssn.Allocate sets the status before node.AddTask refuses, session.go:241-262)
   unsigned long long cyc_wait;     // replayer cycles spent between posting the visit and the eval warps' results (list wait + eval)
 };
 
@@ -130,7 +131,8 @@ struct DevSession {
   // node records and every rank replays identically, so the replicas never diverge.
   uint32_t rank, world, tile_lo, tile_hi, nodes_per_rank;
   uint32_t tpi;           // node tiles a scan CTA stages per iteration (sized to shared memory)
-  uint64_t* sendbuf;      // [(1 + ncols) * 32]: keys[32], then columns [ncols][32]
+  uint64_t* sendbuf;      // [xchg_u64(ncols)]: keys[32], then columns [ncols][32], then a flag row (word 0: backfill's "some node
+                          // outside the list passes the plugin predicates" bit)
   uint64_t* recvbuf;      // [world] x the same
   // Peer-memory exchange (fused scan + exchange + replay, no NCCL inside the cycle): every rank exposes one region
   //   recv[2 parities][KB_MAX_WORLD][P2P_RANK_U64] u64, then flags[2][KB_MAX_WORLD] u64
@@ -145,9 +147,12 @@ struct DevSession {
   uint64_t* pcand;        // [PIPE_RING][pipe_S][KTOP] per-CTA candidate lists of the requests in flight
 };
 constexpr uint32_t KB_MAX_WORLD = 8;
-constexpr uint32_t P2P_RANK_U64 = (1 + 2 * KB_MAX_R + 6 + 3 * KB_MAX_W) * 32;         // keys + widest record block
+constexpr uint32_t P2P_RANK_U64 = (2 + 2 * KB_MAX_R + 6 + 3 * KB_MAX_W) * 32;         // keys + widest record block + flag row
 constexpr uint32_t P2P_FLAG_OFF = 2 * KB_MAX_WORLD * P2P_RANK_U64;
 constexpr size_t   P2P_REGION_BYTES = ((size_t)P2P_FLAG_OFF + 2 * KB_MAX_WORLD) * 8;
+
+// one rank's block of the sharded exchange: keys, the candidates' records, one flag row
+KB_HD uint32_t xchg_u64(uint32_t ncols) { return (2 + ncols) * 32; }
 
 // ---- tile columns (u64 each, TILE_NODES entries per column) ----
 KB_HD uint32_t tile_ncols(uint32_t R, uint32_t W) { return 2 * R + 6 + 3 * W; }

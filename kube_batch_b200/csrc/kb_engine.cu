@@ -395,7 +395,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     free_graph(e);
     // the cycle is a chain of identical launches: capture BATCH of them into one graph (one host call per batch).
     // Sharded: scan shard -> ncclAllGather (top-32 keys + node records per rank) -> identical replay on every rank.
-    const size_t cnt = (size_t)(1 + e->ncols) * 32;
+    const size_t cnt = (size_t)xchg_u64(e->ncols);
     cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     bool ok = ce == cudaSuccess;
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
@@ -463,7 +463,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       launches += ((e->world == 1 || D.p2p) ? 1 : 2) * BATCH;
     } else {
       // sharded node axis without peer memory: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
-      const size_t cnt = (size_t)(1 + e->ncols) * 32;
+      const size_t cnt = (size_t)xchg_u64(e->ncols);
       for (uint32_t i = 0; i < batch; ++i) {
         if (backfill) visit_kernel<1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
         else if (D.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(D);

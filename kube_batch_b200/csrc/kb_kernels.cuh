@@ -145,6 +145,8 @@ struct VisitSmem {
   uint32_t n_excl;
   uint32_t excl[32];                         // nodes the scanners skip (overlap mode)
   uint32_t sink;                             // keeps the shadow prefetch loads alive
+  uint32_t pred_any;                         // backfill: some node of THIS CTA's tiles with key 0 passes ssn.PredicateFn (no Idle for Resreq)
+  uint32_t pred_any_all;                     //   ... of any CTA / rank: what a task that finds no node needs to know (phantom Allocated)
   Ctl ctl2;                                  // replay_kernel's shadow warp reads its own copy
   // chained visits (visit_chain_kernel): nodes modified by the replays of this launch (no duplicates), the certification
   // floor of the list being replayed, and whether the last replay stopped for a rescan
@@ -242,7 +244,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     const uint32_t q = c.cur_queue;
     const uint32_t jend = S.job_ord_off[j + 1];
     uint32_t run_left = c.cur_run;
-    uint32_t placed = 0, popped = 0, n_alloc = 0;
+    uint32_t placed = 0, popped = 0, n_alloc = 0, n_phantom = 0;
     uint32_t reason = STOP_RUN_DONE;
     // job-level state of the run lives in registers: lane 0 keeps the counters, lane k < R keeps dimension k
     // of drfAttr.allocated / queueAttr.allocated; nothing but the decision store touches memory in a step
@@ -268,7 +270,29 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       const uint32_t task = __shfl_sync(FULL, my_task, popped & 31u);
       popped += 1;
       run_left -= 1;
-      if (best == 0) { reason = STOP_NOFIT; break; }              // allocate.go:144-148
+      if (best == 0) {                                             // allocate.go:144-148
+        if (BF) {
+          // backfill.go:53-63 calls ssn.Allocate on every node that passes ssn.PredicateFn; ssn.Allocate moves the task to
+          // Allocated BEFORE node.AddTask checks Resreq <= Idle (session.go:241-262).  No node took the task: if any node
+          // passes the predicates the reference leaves it Allocated on no node (it counts towards JobReady from now on).
+          // Nodes outside the list are unmodified since the scan (their bit is pred_any_all); candidates are re-checked.
+          bool pk = false;
+          if (have) {
+            ColAcc acc{&sm.slot[which][0][0], (uint32_t)lane, 32u, R, W};
+            eval_pair(S.cf, sm.cls, acc, my_node, nullptr, &pk);
+          }
+          if (sm.pred_any_all || __any_sync(FULL, pk)) {
+            if (lane == 0) {
+              kb_decision d;
+              d.node = -1; d.kind = KB_KIND_ALLOCATED; d.dispatched = 0; d.reserved = 0;
+              d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu;
+              S.dec[task] = d;
+            }
+            n_phantom += 1;
+          }
+        }
+        reason = STOP_NOFIT; break;
+      }
       const uint32_t owner = (uint32_t)__ffs(__ballot_sync(FULL, cur_key == best)) - 1u;
       const unsigned ownbits = __shfl_sync(FULL, (next_valid ? 1u : 0u) | (cur_fi ? 2u : 0u), owner);
       if (!(ownbits & 1u)) refresh();
@@ -301,13 +325,14 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
     // write the job-level state back, then run the control plane
     if (lane == 0) {
       S.job_pos[j] = pos0 + popped;
-      S.job_ready[j] = ready + (int32_t)n_alloc;
+      S.job_ready[j] = ready + (int32_t)n_alloc + (int32_t)n_phantom;
       S.job_placed[j] += placed;
       c.step = step0 + placed;
       c.tasks_processed += popped;
       c.pairs_logical += (unsigned long long)popped * S.N;
       c.tasks_allocated += n_alloc;
       c.tasks_pipelined += placed - n_alloc;
+      c.phantoms += n_phantom;
     }
     if (lane < R && placed) {
       if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = jalloc;
@@ -421,6 +446,7 @@ __device__ __forceinline__ bool issue_first_group(const DevSession& S, VisitSmem
   return true;
 }
 
+template <bool PH = false>
 __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx,
                                                const uint32_t n_scanners, const uint32_t cls_id, const int tid, const int lane, const int warp,
                                                const bool first_issued = false) {
@@ -448,6 +474,7 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
   __syncthreads();
   const uint32_t sub = (uint32_t)warp >> 2, part = (uint32_t)warp & 3u;    // which tile of the group / which 32 nodes of it
   uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
+  bool pany = false;                         // PH (backfill): a node that passes the plugin predicates but has no Idle for Resreq
   for (uint32_t it = 0; it < n_local; ++it) {
     const uint32_t b = it & 1u;
     if (it + 1 < n_local) {
@@ -466,7 +493,9 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
     }
     if (sub < tpi && t < S.tile_hi && node < S.N && !((exmask >> lane) & 1u)) {
       ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
-      key = eval_pair(S.cf, sm.cls, acc, node, nullptr);
+      bool pok = false;
+      key = eval_pair(S.cf, sm.cls, acc, node, nullptr, PH ? &pok : nullptr);
+      if (PH) pany = pany | (pok && key == 0);
     }
     // K3, warp level: skip the networks when nothing in this warp can enter its list
     const uint64_t thr = __shfl_sync(FULL, mylist, 31);
@@ -475,6 +504,7 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
       mylist = warp_merge_top32(mylist, key, lane);
     }
   }
+  if (PH) { if (__any_sync(FULL, pany) && lane == 0) atomicOr(&sm.pred_any, 1u); }
   // CTA level: tree-fold the warps' lists into warp 0, which publishes the CTA's list
   mylist = cta_fold_lists(mylist, sm.wlist, warp, lane);
   return mylist;
@@ -548,7 +578,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   Ctl* gctl = S.ctl;
-  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; }
+  if (tid == 0) { mbar_init(&sm.mbar[0], 1); mbar_init(&sm.mbar[1], 1); fence_mbar_init(); sm.n_excl = 0; sm.pred_any = 0; sm.pred_any_all = 0; }
   if (tid < 32) sm.excl[tid] = 0;
   // programmatic dependent launch: this grid may have been scheduled while the previous launch was still replaying;
   // nothing the previous launch writes is read before this point (no-op when launched without the attribute)
@@ -564,9 +594,10 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   const long long t_start = clock64();
 
-  uint64_t mylist = scan_phase(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true);
+  uint64_t mylist = scan_phase<BF != 0>(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true);
   if (warp == 0) {
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
+    if (BF && lane == 0) S.cand[((size_t)gridDim.x + blockIdx.x) * KTOP] = (uint64_t)sm.pred_any;      // second bank of the list area
     sm.keys[lane] = mylist;
     __threadfence();
     __syncwarp();                            // every lane's list entry is fenced before the ticket is taken
@@ -591,6 +622,12 @@ visit_kernel(const __grid_constant__ DevSession S) {
     }
   }
 
+  if (BF && warp == 1) {                     // backfill: OR of the CTAs' "a node outside the lists passes the predicates" bits
+    uint32_t f = 0;
+    for (uint32_t g2 = lane; g2 < gridDim.x; g2 += 32) f |= (uint32_t)__ldcg(&S.cand[((size_t)gridDim.x + g2) * KTOP]);
+    f = __reduce_or_sync(FULL, f);
+    if (lane == 0) sm.pred_any_all = f;
+  }
   // ---------------- K3: merge the per-CTA lists: every warp folds every 16th list, then the tree ----------------
   if (gridDim.x > 1) {
     const uint32_t G = gridDim.x;
@@ -630,6 +667,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
       uint64_t* dst = S.peer_base[warp] + (size_t)(par * KB_MAX_WORLD + S.rank) * P2P_RANK_U64;
       dst[lane] = sm.keys[lane];
       for (uint32_t cc = 0; cc < S.ncols; ++cc) dst[(size_t)(1 + cc) * 32 + lane] = sm.slot[0][cc][lane];
+      if (BF) dst[(size_t)(1 + S.ncols) * 32 + lane] = (uint64_t)sm.pred_any_all;
       __threadfence_system();
       __syncwarp();
       if (lane == 0) *((volatile uint64_t*)(S.peer_base[warp] + P2P_FLAG_OFF + par * KB_MAX_WORLD + S.rank)) = (uint64_t)epoch;
@@ -654,6 +692,12 @@ visit_kernel(const __grid_constant__ DevSession S) {
     uint64_t acc = __ldcg(recv + lane);
     for (uint32_t r = 1; r < S.world; ++r) acc = warp_merge_top32(acc, __ldcg(recv + (size_t)r * P2P_RANK_U64 + lane), lane);
     sm.keys[lane] = acc;
+    if (BF) {
+      uint32_t f = (uint32_t)lane < S.world ? (uint32_t)__ldcg(recv + (size_t)lane * P2P_RANK_U64 + (size_t)(1 + S.ncols) * 32) : 0u;
+      f = __reduce_or_sync(FULL, f);
+      if (lane == 0) sm.pred_any_all = f;
+      __syncwarp();
+    }
     const uint32_t node = key_node(acc);
     uint32_t owner = node / S.nodes_per_rank;
     owner = owner < S.world ? owner : S.world - 1;
@@ -677,6 +721,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
     if (warp == 0) {
       const uint64_t k = sm.keys[lane];
       S.sendbuf[lane] = k;
+      if (BF) S.sendbuf[(size_t)(1 + S.ncols) * 32 + lane] = (uint64_t)sm.pred_any_all;
       if (k) {
         const uint32_t n = key_node(k);
         const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
@@ -1161,7 +1206,13 @@ replay_kernel(const __grid_constant__ DevSession S) {
     for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
   }
   const long long t_start = clock64();
-  const size_t rank_u64 = (size_t)(1 + S.ncols) * 32;
+  const size_t rank_u64 = (size_t)xchg_u64(S.ncols);
+  if (BF) {
+    uint32_t f = (uint32_t)lane < S.world ? (uint32_t)__ldcg(S.recvbuf + (size_t)lane * rank_u64 + (size_t)(1 + S.ncols) * 32) : 0u;
+    f = __reduce_or_sync(FULL, f);
+    if (lane == 0) sm.pred_any_all = f;
+    __syncwarp();
+  }
   uint64_t acc = __ldcg(S.recvbuf + lane);
   for (uint32_t r = 1; r < S.world; ++r) acc = warp_merge_top32(acc, __ldcg(S.recvbuf + r * rank_u64 + lane), lane);
   sm.keys[lane] = acc;
@@ -1205,18 +1256,22 @@ gang_commit_kernel(const __grid_constant__ DevSession S, const int32_t* __restri
   }
   __syncwarp();
   const int32_t need = S.gang_ready ? S.job_min_avail[j] - job_ready0[j] : 0;   // allocations required before JobReady
-  // pass 1: find e* (slot index) and its step
+  // pass 1: find e* (slot index) and its step.  A phantom (backfill: Allocated on no node, step none) counts towards
+  // ReadyTaskNum but its ssn.Allocate returned before the JobReady check, so e* is always a REAL allocation.
   uint32_t estar = 0xFFFFFFFFu, estep = 0;
   int32_t carried = 0;
+  bool phantoms = false;
   for (uint32_t base = 0; base < n && estar == 0xFFFFFFFFu; base += 32) {
     const uint32_t i = base + lane;
-    uint32_t alloc = 0, step = 0;
+    uint32_t alloc = 0, step = 0xFFFFFFFFu;
     if (i < n) { const kb_decision d = S.dec[task_at(i)]; alloc = d.kind == KB_KIND_ALLOCATED; step = d.step; }
+    const bool real = alloc && step != 0xFFFFFFFFu;
+    phantoms = phantoms || __any_sync(FULL, alloc && !real);
     int32_t x = (int32_t)alloc;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { int32_t y = __shfl_up_sync(FULL, x, o); if (lane >= o) x += y; }
     const int32_t incl = carried + x;
-    const unsigned m = __ballot_sync(FULL, alloc && incl >= need);
+    const unsigned m = __ballot_sync(FULL, real && incl >= need);
     if (m) {
       const int src = __ffs(m) - 1;
       estar = base + src;
@@ -1229,8 +1284,17 @@ gang_commit_kernel(const __grid_constant__ DevSession S, const int32_t* __restri
     const uint32_t t = task_at(i);
     kb_decision d = S.dec[t];
     if (d.kind != KB_KIND_ALLOCATED) continue;
-    d.dispatched = 1;
-    d.dispatch_step = i <= estar ? estep : d.step;
+    if (i <= estar) { d.dispatched = 1; d.dispatch_step = estep; }
+    else if (d.step != 0xFFFFFFFFu) { d.dispatched = 1; d.dispatch_step = d.step; }
+    else {
+      // a phantom after e*: the next successful ssn.Allocate of the job finds it in TaskStatusIndex[Allocated] and
+      // dispatches it (session.go:277-285); if there is none it stays undispatched
+      for (uint32_t k = i + 1; k < n; ++k) {
+        const kb_decision dk = S.dec[task_at(k)];
+        if (dk.kind == KB_KIND_ALLOCATED && dk.step != 0xFFFFFFFFu) { d.dispatched = 1; d.dispatch_step = dk.step; break; }
+      }
+      if (!d.dispatched) continue;
+    }
     S.dec[t] = d;
   }
 }

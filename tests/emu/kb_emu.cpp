@@ -87,7 +87,7 @@ inline uint64_t add_pref_term(uint64_t key, const PrefCtx* pc, int64_t count) {
 void emu_scan(Emu& E, uint64_t* sendbuf) {
   const DevSession& S = *E.cur;
   const Ctl& c = *S.ctl;
-  const size_t cnt = (size_t)(1 + S.ncols) * 32;
+  const size_t cnt = (size_t)xchg_u64(S.ncols);
   std::fill(sendbuf, sendbuf + cnt, 0ull);
   if (c.done) return;
   const ClassRec& cls = S.classes[c.cur_class];
@@ -112,7 +112,9 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
       const uint32_t n = t * TILE_NODES + i;
       if (n >= S.N) break;
       TileAcc acc{S.tiles + (size_t)t * tile_u64, i, R, W};
-      uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr);
+      bool pok = false;
+      uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr, &pok);
+      if (S.backfill && pok && !k) sendbuf[(size_t)(1 + S.ncols) * 32] = 1;      // flag row: passes ssn.PredicateFn, no Idle for Resreq
       if (k && cp) k = add_pref_term(k, &pc, pref_count(*cp, acc, W));
       if (k) keys.push_back(k);
     }
@@ -130,7 +132,7 @@ struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = f
 
 // replay_epilogue's core: look-ahead refresh + certified steps + control plane, for candidates already loaded
 bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key,
-                 const PrefCtx* pc = nullptr) {
+                 const PrefCtx* pc = nullptr, const bool pred_any_outside = false) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   auto refresh = [&]() {
@@ -167,7 +169,27 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       S.job_pos[j] = pos + 1;
       c.tasks_processed += 1; c.pairs_logical += S.N;
       run_left -= 1;
-      if (best == 0) { reason = STOP_NOFIT; break; }
+      if (best == 0) {
+        if (S.backfill) {
+          // phantom Allocated (session.go:241-262): some node passes ssn.PredicateFn but none has Idle for Resreq
+          bool any = pred_any_outside;
+          for (auto& cd : cand) {
+            if (!cd.have) continue;
+            SlotAcc acc{&cd.st[cd.which], R, W};
+            bool pok = false;
+            eval_pair(S.cf, cls, acc, cd.node, nullptr, &pok);
+            any = any || pok;
+          }
+          if (any) {
+            kb_decision dd;
+            dd.node = -1; dd.kind = KB_KIND_ALLOCATED; dd.dispatched = 0; dd.reserved = 0; dd.step = 0xFFFFFFFFu; dd.dispatch_step = 0xFFFFFFFFu;
+            S.dec[S.ord_task[pos]] = dd;
+            S.job_ready[j] += 1;
+            c.phantoms += 1;
+          }
+        }
+        reason = STOP_NOFIT; break;
+      }
       Cand& cd = cand[owner];
       if (!cd.next_valid) refresh();
       const bool fits_idle = cd.cur_fi;
@@ -218,7 +240,9 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
   const uint32_t cls_id = c.cur_class;
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
-  const size_t rank_u64 = (size_t)(1 + ncols) * 32;
+  const size_t rank_u64 = (size_t)xchg_u64(ncols);
+  bool pred_any = false;
+  for (uint32_t r = 0; r < S.world; ++r) pred_any = pred_any || recvbuf[r * rank_u64 + (size_t)(1 + ncols) * 32] != 0;
   // merge the ranks' lists
   struct Src { uint64_t key; uint32_t rank, idx; };
   std::vector<Src> all;
@@ -244,7 +268,7 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
   const ClassPref* cp = (E.B.has_pref && S.cf.nodeorder && !S.backfill && E.B.class_pref[cls_id].n) ? &E.B.class_pref[cls_id] : nullptr;
   PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &E.pref_nmax};
   if (cp) for (auto& cd : cand) if (cd.have) { SlotAcc acc{&cd.st[0], R, W}; cd.pref = pref_count(*cp, acc, W); }
-  replay_core(S, c, cls_id, cand, floor_key, cp ? &pc : nullptr);
+  replay_core(S, c, cls_id, cand, floor_key, cp ? &pc : nullptr, pred_any);
   write_back(S, cls, cand);          // every replica writes every modified candidate back
 }
 
@@ -510,14 +534,21 @@ void emu_gang_commit(const DevSession& S, const DevSession& Sbf, const int32_t* 
     size_t estar = (size_t)-1; uint32_t estep = 0;
     for (size_t i = 0; i < tasks.size(); ++i) {
       const kb_decision& d = S.dec[tasks[i]];
-      if (d.kind == KB_KIND_ALLOCATED) { incl += 1; if (incl >= need) { estar = i; estep = d.step; break; } }
+      if (d.kind != KB_KIND_ALLOCATED) continue;
+      incl += 1;                                                 // phantoms (step none) count, but only a real Allocate dispatches
+      if (d.step != 0xFFFFFFFFu && incl >= need) { estar = i; estep = d.step; break; }
     }
     if (estar == (size_t)-1) continue;
     for (size_t i = 0; i < tasks.size(); ++i) {
       kb_decision& d = S.dec[tasks[i]];
       if (d.kind != KB_KIND_ALLOCATED) continue;
-      d.dispatched = 1;
-      d.dispatch_step = i <= estar ? estep : d.step;
+      if (i <= estar) { d.dispatched = 1; d.dispatch_step = estep; }
+      else if (d.step != 0xFFFFFFFFu) { d.dispatched = 1; d.dispatch_step = d.step; }
+      else
+        for (size_t k = i + 1; k < tasks.size(); ++k) {
+          const kb_decision& dk = S.dec[tasks[k]];
+          if (dk.kind == KB_KIND_ALLOCATED && dk.step != 0xFFFFFFFFu) { d.dispatched = 1; d.dispatch_step = dk.step; break; }
+        }
     }
   }
 }
@@ -596,7 +627,7 @@ int kbemu_run(void* h, uint32_t actions) {
 void kbemu_destroy(void* h) { delete (Emu*)h; }
 int kbemu_done(void* h) { return ((Emu*)h)->cur->ctl->done ? 1 : 0; }
 void kbemu_begin_backfill(void* h, int allocate_ran) { emu_begin_backfill(*(Emu*)h, allocate_ran != 0); }
-uint32_t kbemu_buf_u64(void* h) { return (1 + ((Emu*)h)->S.ncols) * 32; }
+uint32_t kbemu_buf_u64(void* h) { return xchg_u64(((Emu*)h)->S.ncols); }
 void kbemu_scan(void* h, uint64_t* sendbuf) { emu_scan(*(Emu*)h, sendbuf); }
 void kbemu_replay(void* h, const uint64_t* recvbuf) { emu_replay(*(Emu*)h, recvbuf); }
 

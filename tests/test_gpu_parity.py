@@ -220,6 +220,37 @@ def test_backfill_random_sessions(eng, seed):
             run_backfill_and_check(eng, s, CONFS[cname], f"backfill seed{seed}/{cname}/actions{actions}", actions)
 
 
+def test_backfill_phantom_allocated_tasks_on_the_gpu(eng):
+    """ssn.Allocate's status-before-AddTask order (session.go:241-262): sub-epsilon best-effort requests on exhausted nodes leave
+    tasks Allocated on no node; same random clusters as tests/test_emu_parity.py::test_phantom_corner_random_clusters."""
+    from kube_batch_b200 import builder as B
+    phantoms = 0
+    for seed in range(12):
+        rng = np.random.default_rng(7000 + seed)
+        b = B.SessionBuilder()
+        b.add_queue(B.Queue("q", 1))
+        nn = int(rng.integers(1, 5))
+        for n in range(nn):
+            b.add_node(B.Node(f"n{n}", {"cpu": 1, "memory": 4e9, "pods": int(rng.choice([2, 3, 10]))}, labels={"zone": "ab"[n % 2]}))
+        for g in range(int(rng.integers(1, 4))):
+            b.add_pod_group(B.PodGroup("ns", f"g{g}", "q", min_member=int(rng.integers(0, 5))))
+            if rng.random() < 0.8:
+                b.add_pod(B.Pod("ns", f"g{g}-full", f"n{int(rng.integers(0, nn))}", "Running",
+                                {"cpu": float(rng.choice([0.99, 0.995, 1.0])), "memory": 1e9}, group=f"g{g}"))
+            for k in range(int(rng.integers(1, 8))):
+                req = {"cpu": float(rng.choice([0.0, 0.001, 0.005, 0.009]))}
+                if req["cpu"] == 0.0:
+                    req = {}
+                b.add_pod(B.Pod("ns", f"g{g}-p{k}", "", "Pending", req, group=f"g{g}", creation=k,
+                                node_selector={"zone": str(rng.choice(["a", "b"]))} if rng.random() < 0.3 else {}))
+        s = b.flatten()
+        for conf in (PluginConf.from_names([["gang"], ["predicates"]]), PluginConf.default()):
+            for actions in (2, 3):
+                o, r = run_backfill_and_check(eng, s, conf, f"phantom seed{seed}/actions{actions}", actions)
+                phantoms += int(((r.decisions["kind"] == abi.KB_KIND_ALLOCATED) & (r.decisions["node"] == -1)).sum())
+    assert phantoms > 0
+
+
 def test_backfill_multi_tile_then_allocate_restarts(eng):
     # many nodes (several tiles), many best-effort pods; afterwards kb_allocate must restart from the loaded state
     s = synth.random_session(77, tasks=1500, jobs=60, nodes=3000, queues=2, min_member_frac=0.5, hetero=0.3, oversub=1.3,
