@@ -5,34 +5,52 @@ import (
 
 	"github.com/golang/glog"
 
-	"github.com/kubernetes-sigs/kube-batch/pkg/scheduler/api"
 	"github.com/kubernetes-sigs/kube-batch/pkg/scheduler/framework"
 )
 
 // allocateAction is a drop-in for pkg/scheduler/actions/allocate: same Name(), same framework.Action
 // interface (framework/interface.go:20-32), registered with framework.RegisterAction in actions/factory.go.
-type allocateAction struct{ engine *Engine }
+//
+// Fallback is the ORIGINAL action (actions/allocate.New()), still linked in.  libkbgpu itself has no CPU path and never
+// will; but one tenant pod with inter-pod affinity, a custom plugin or a CUDA error must not stop scheduling for the
+// whole cluster, so the shim hands exactly those cycles to the reference implementation and says so in the log.
+type allocateAction struct {
+	engine   *Engine
+	Fallback framework.Action
+}
 
-func New(e *Engine) *allocateAction              { return &allocateAction{engine: e} }
-func (alloc *allocateAction) Name() string       { return "allocate" }
-func (alloc *allocateAction) Initialize()        {}
-func (alloc *allocateAction) UnInitialize()      {}
+func New(e *Engine, fallback framework.Action) *allocateAction { return &allocateAction{engine: e, Fallback: fallback} }
+func (alloc *allocateAction) Name() string                      { return "allocate" }
+func (alloc *allocateAction) Initialize()                       {}
+func (alloc *allocateAction) UnInitialize()                     {}
 
 // Execute replaces the queue->job->task loop of allocate.go:43-194: flatten, one kb_allocate, replay.
-func (alloc *allocateAction) Execute(ssn *framework.Session) { run(alloc.engine, ssn, false) }
+func (alloc *allocateAction) Execute(ssn *framework.Session) {
+	if err := run(alloc.engine, ssn, false); err != nil {
+		fallBack(alloc.Fallback, ssn, err)
+	}
+}
 
-// run is one action on the GPU; every action flattens the session as it is NOW, like the reference runs its
-// actions one after the other on the same *framework.Session (scheduler.go:88-92).
-func run(engine *Engine, ssn *framework.Session, backfill bool) {
-	flat, tiers, err := Flatten(ssn) // canonical orders + label/taint/port atom interning; see flatten.go
-	if err != nil {
-		// e.g. a non built-in plugin registered a PredicateFn: no CPU fallback — skip the cycle loudly.
-		glog.Errorf("kbgpu: session cannot be flattened: %v", err)
+func fallBack(fb framework.Action, ssn *framework.Session, err error) {
+	if fb == nil {
+		glog.Errorf("kbgpu: %v; no fallback action configured: this cycle schedules nothing", err)
 		return
 	}
-	if err := engine.Load(flat, tiers); err != nil {
-		glog.Errorf("kbgpu: %v", err)
-		return
+	glog.Warningf("kbgpu: %v; running the Go %s action for this cycle", err, fb.Name())
+	fb.Execute(ssn)
+}
+
+// run is one action on the GPU; every action flattens the session as it is NOW, like the reference runs its
+// actions one after the other on the same *framework.Session (scheduler.go:88-92).  Nothing has been changed in
+// the session when an error is returned, so the caller can still run the reference action.
+func run(engine *Engine, ssn *framework.Session, backfill bool) error {
+	flat, err := Flatten(ssn) // canonical orders + label/taint/port atom interning; see flatten.go
+	if err != nil {
+		return err
+	}
+	defer flat.Free()
+	if err := engine.Load(flat); err != nil {
+		return err
 	}
 	var dec []Decision
 	if backfill {
@@ -41,8 +59,7 @@ func run(engine *Engine, ssn *framework.Session, backfill bool) {
 		dec, err = engine.Allocate(len(flat.Tasks))
 	}
 	if err != nil {
-		glog.Errorf("kbgpu: %v", err)
-		return
+		return err
 	}
 	// Replay in the order the reference would have made the calls, through the UNCHANGED session methods, so
 	// event handlers (drf / proportion), gang dispatch, cache.Bind, metrics and status updates behave as today
@@ -56,7 +73,7 @@ func run(engine *Engine, ssn *framework.Session, backfill bool) {
 	}
 	sort.Slice(order, func(a, b int) bool { return dec[order[a]].Step < dec[order[b]].Step })
 	for _, i := range order {
-		task := flat.Tasks[i] // *api.TaskInfo
+		task := flat.Tasks[i]
 		node := flat.NodeNames[dec[i].Node]
 		var err error
 		if dec[i].Kind == 1 {
@@ -68,5 +85,5 @@ func run(engine *Engine, ssn *framework.Session, backfill bool) {
 			glog.Errorf("kbgpu: replay of task %v on %v failed: %v", task.UID, node, err)
 		}
 	}
-	_ = api.Pending
+	return nil
 }

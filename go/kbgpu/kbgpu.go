@@ -36,15 +36,26 @@ func (e *Engine) err(what string, rc C.int) error {
 	return fmt.Errorf("%s: %s (%s)", what, C.GoString(C.kb_last_error(e.h)), C.GoString(C.kb_status_str(rc)))
 }
 
-// Load hands the flattened snapshot + tiers to the device.  kb_session_load copies everything before it
-// returns, so passing pointers into Go slices for the duration of the call is within the cgo rules.
-func (e *Engine) Load(f *Flat, tiers []C.kb_tier) error {
-	snap := f.cSnapshot() // fills a C.kb_snapshot whose pointers alias f's slices (pinned for the call by cgo)
-	conf := C.kb_plugin_conf{n_tiers: C.uint32_t(len(tiers))}
-	if len(tiers) > 0 {
-		conf.tiers = &tiers[0]
+// Load hands the flattened snapshot + tiers to the device.  kb_snapshot / kb_plugin_conf and every array they point to
+// live in C memory for the call (cgo pointer rules: C may not be handed Go memory that contains pointers);
+// kb_session_load copies everything it needs before it returns, so the arena is freed right after.
+func (e *Engine) Load(f *Flat) error {
+	if int(f.T) != len(f.Tasks) || int(f.N) != len(f.NodeNames) {
+		return fmt.Errorf("kbgpu: inconsistent Flat (T=%d, %d tasks; N=%d, %d nodes)", f.T, len(f.Tasks), f.N, len(f.NodeNames))
 	}
-	if rc := C.kb_session_load(e.h, &snap, &conf); rc != 0 {
+	var a arena
+	defer a.free()
+	snap := (*C.kb_snapshot)(C.calloc(1, C.size_t(unsafe.Sizeof(C.kb_snapshot{}))))
+	defer C.free(unsafe.Pointer(snap))
+	f.cSnapshot(snap, &a)
+	conf := (*C.kb_plugin_conf)(C.calloc(1, C.size_t(unsafe.Sizeof(C.kb_plugin_conf{}))))
+	defer C.free(unsafe.Pointer(conf))
+	conf.n_tiers = C.uint32_t(f.nTiers)
+	conf.tiers = f.cTiers
+	if rc := C.kb_session_load(e.h, snap, conf); rc != 0 {
+		if rc == C.KB_E_UNSUPPORTED_FEATURE || rc == C.KB_E_UNSUPPORTED_PLUGIN {
+			return &ErrUnsupported{C.GoString(C.kb_last_error(e.h))}
+		}
 		return e.err("kb_session_load", rc)
 	}
 	return nil

@@ -32,9 +32,17 @@
 
 namespace kb {
 
-constexpr int PIPE_WARPS = 18;
-constexpr int PIPE_THREADS = PIPE_WARPS * 32;
 constexpr int PIPE_DEPTH = 8;              // placement depths evaluated up front per candidate
+// replayer CTA warp roles: 0 main, 1..8 patch warps (one per depth), 9..16 prep teams, 17 writer, 18 shadow prefetch.
+// scanner CTAs: 0..15 scan groups, 16 applier, the rest exit.
+constexpr int PIPE_W_PATCH0 = 1;
+constexpr int PIPE_PREP_TEAMS = 2, PIPE_PREP_TW = 4;
+constexpr int PIPE_W_PREP0 = PIPE_W_PATCH0 + PIPE_DEPTH;
+constexpr int PIPE_W_WRITER = PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW;
+constexpr int PIPE_W_SHADOW = PIPE_W_WRITER + 1;
+constexpr int PIPE_WARPS = PIPE_W_SHADOW + 1;
+constexpr int PIPE_THREADS = PIPE_WARPS * 32;
+static_assert(PIPE_DEPTH % PIPE_PREP_TW == 0, "a prep warp owns depths w, w + TW, ...");
 constexpr uint32_t PIPE_HOT = 128;         // hot ring: records of the most recent log entries (replayer shared memory)
 constexpr uint32_t PIPE_RQ = 16;           // requested-table entries (most recent scan requests)
 constexpr uint32_t PIPE_CMDS = 64;
@@ -170,7 +178,7 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
   __syncthreads();
   mbar_wait(&sm.mbar, 0);
 
-  if (warp == 17) return;
+  if (warp > 16) return;
   if (warp == 16) {
     // ---------------- applier: follow the modification log, refresh the resident copies of MY nodes ----------------
     uint32_t cursor = 0;
@@ -297,103 +305,217 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
 // ---------------------------------------------------------------------------------------------
 // replayer CTA
 // ---------------------------------------------------------------------------------------------
+// One prepared look-ahead list: everything the replay needs about the request's 32 candidates, evaluated AHEAD of the visit
+// by a prep team (list wait, record gather and the depth chain are off the replay's critical path).  Valid for every entry
+// whose node is not in log[stamp, now): such a node is unmodified since the stamp, so its record — read at any time after
+// the stamp — and every key derived from it are current.  Entries of modified nodes are dropped at the visit (the patch
+// entry of the node speaks for it).
+template <int NC>
+struct PrepBuf {
+  ClassRec cls;
+  uint64_t list[KTOP];                         // the request's list as published (descending, 0-padded); [31] = floor
+  uint64_t key[PIPE_DEPTH][KTOP];              // key of entry l after d more placements of the class
+  uint32_t fi[PIPE_DEPTH];                     // fits-idle ballots of the same states
+  uint64_t rec[NC][KTOP];                      // entry l's record (state at depth 0)
+};
+
 template <int NC>
 struct ReplaySmem {
-  ClassRec cls;
   Ctl ctl;
-  // visit descriptor (main warp -> eval warps)
-  uint32_t v_slot, v_tag, v_stamp, v_npatch, v_pvalid, v_quit, v_err, v_pad;
+  // visit descriptor (main warp -> patch warps)
+  uint32_t v_pb, v_stamp, v_npatch, v_pvalid, v_quit, v_err, v_count, v_pad;
   uint32_t pnode[32];                          // patch entry i: node of log entry v_stamp + i (valid bit in v_pvalid: latest entry of its node)
-  // eval results
-  uint64_t v_list[KTOP];                       // the request's list as published
-  uint64_t ckey[PIPE_DEPTH][64];               // key of pool slot s after d more placements of the class
-  uint32_t cfi[PIPE_DEPTH][2];                 // fits-idle ballots of the same states
-  uint64_t lsort_key[KTOP]; uint32_t lsort_slot[KTOP];   // surviving list entries, compacted (descending)
-  uint64_t psort_key[KTOP]; uint32_t psort_slot[KTOP];   // patch entries' fresh keys, sorted (descending)
+  uint64_t pkey[PIPE_DEPTH][KTOP];             // patch entry i after d more placements
+  uint32_t pfi[PIPE_DEPTH];
+  uint64_t psort_key[KTOP]; uint32_t psort_slot[KTOP];   // patch entries' fresh keys, sorted (descending); slot = 32 + i
   // chain extension of ONE pool slot beyond PIPE_DEPTH
   uint64_t ext_key[32]; uint32_t ext_fi, ext_slot, ext_base, ext_pad;
   // hot ring: entry i of the modification log lives at i % PIPE_HOT until the writer has written it back and no list needs it
   uint32_t hot_node[PIPE_HOT], hot_cnt[PIPE_HOT], hot_cls[PIPE_HOT];
   uint64_t hot_rec[NC][PIPE_HOT];
-  // requested table
+  // requested table (request seq lives at seq % PIPE_RQ, and so does its prepared list)
   uint32_t rq_cls[PIPE_RQ], rq_seq[PIPE_RQ], rq_stamp[PIPE_RQ];
+  uint32_t rq_posted;                          // requests entered into the table (volatile: main -> prep teams)
+  uint32_t pb_ready[PIPE_RQ];                  // seq + 1 once pb[seq % PIPE_RQ] holds request seq (volatile: prep -> main)
+  uint32_t prep_done[PIPE_PREP_TEAMS];         // requests a team has finished (its next seq; volatile)
+  uint32_t prep_status[PIPE_PREP_TEAMS];       // warp 0 of a team -> its other warps
   // main -> writer command ring
   uint32_t cmd_kind[PIPE_CMDS], cmd_a[PIPE_CMDS], cmd_b[PIPE_CMDS];
   uint32_t cmd_head, cmd_tail;                 // volatile: written by main / by the writer
   uint32_t pub_head;                           // log entries the writer has published (volatile)
   uint32_t sink;
+  PrepBuf<NC> pb[PIPE_RQ];
 };
 
-// eval warps: pool slot (h * 32 + lane) at placement depth d
+// patch warps (one per placement depth): patch entry `lane` = the current record of a node modified since the list's stamp,
+// from the hot ring (shared memory) — the only evaluation left on the replay's critical path
 template <int RR, int WW>
-__device__ __forceinline__ void pipe_eval_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int e, const int lane) {
+__device__ __forceinline__ void pipe_patch_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int d, const int lane) {
   constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
-  const int d = e >> 1, h = e & 1;
-  PipeG* pg = S.pg;
   for (;;) {
-    bar_sync(1, 17 * 32);                       // go
+    bar_sync(1, (1 + PIPE_DEPTH) * 32);         // go
     if (*((volatile uint32_t*)&sm.v_quit)) return;
-    uint64_t rec[NC];
-    uint32_t node = 0;
-    bool have = false;
-    uint64_t listkey = 0;
-    if (h == 0) {
-      // the request's list: lane l polls its own two LL words (payload + tag in one 8-byte word each)
-      const uint32_t slot = sm.v_slot, tag = sm.v_tag;
-      unsigned long long w0 = 0, w1 = 0;
-      const long long deadline = clock64() + PIPE_DEADLINE;
-      bool ok = true;
-      for (;;) {
-        ld_relaxed_2u64(&pg->list[slot][2 * lane], w0, w1);
-        if ((uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag) break;
-        if (clock64() > deadline) { ok = false; break; }
-      }
-      if (!__all_sync(FULL, ok)) { if (lane == 0) sm.v_err = 1; w0 = w1 = 0; }
-      listkey = (w0 & 0xFFFFFFFFull) | (w1 << 32);
-      node = key_node(listkey);
-      have = listkey != 0;
-      const uint32_t np = sm.v_npatch;
-      for (uint32_t i = 0; i < np; ++i) have = have && (sm.pnode[i] != node);     // modified since the stamp: the patch entry speaks for it
-      if (have) {
-        const uint64_t* g = S.tiles + (size_t)(node / TILE_NODES) * ((size_t)NC * TILE_NODES) + (node % TILE_NODES);
-#pragma unroll
-        for (uint32_t c = 0; c < NC; ++c) rec[c] = __ldcg(g + (size_t)c * TILE_NODES);
-      }
-    } else {
-      have = ((sm.v_pvalid >> lane) & 1u) != 0;
-      node = sm.pnode[lane];
-      if (have) {
-        const uint32_t hi = (sm.v_stamp + (uint32_t)lane) % PIPE_HOT;
-#pragma unroll
-        for (uint32_t c = 0; c < NC; ++c) rec[c] = sm.hot_rec[c][hi];
-      }
-    }
+    const ClassRec& cls = sm.pb[sm.v_pb].cls;
+    const bool have = ((sm.v_pvalid >> lane) & 1u) != 0;
+    const uint32_t node = sm.pnode[lane];
     uint64_t key = 0;
     bool fi = false;
     if (have) {
-      for (int k = 0; k < d; ++k) advance_rec<RR, WW>(rec, sm.cls);
+      uint64_t rec[NC];
+      const uint32_t hi = (sm.v_stamp + (uint32_t)lane) % PIPE_HOT;
+#pragma unroll
+      for (uint32_t c = 0; c < NC; ++c) rec[c] = sm.hot_rec[c][hi];
+      for (int k = 0; k < d; ++k) advance_rec<RR, WW>(rec, cls);
       RegAcc acc{rec, R, W};
-      key = eval_pair<RR, WW>(S.cf, sm.cls, acc, node, &fi);
+      key = eval_pair<RR, WW>(S.cf, cls, acc, node, &fi);
     }
-    sm.ckey[d][h * 32 + lane] = key;
+    sm.pkey[d][lane] = key;
     const unsigned fim = __ballot_sync(FULL, have && fi);
-    if (lane == 0) sm.cfi[d][h] = fim;
+    if (lane == 0) sm.pfi[d] = fim;
     if (d == 0) {
-      if (h == 0) {
-        // surviving list entries keep their order: compact them with a ballot
-        sm.v_list[lane] = listkey;
-        const unsigned am = __ballot_sync(FULL, key != 0);
-        const unsigned src = __fns(am, 0, lane + 1);
-        const uint64_t ck = __shfl_sync(FULL, key, (int)(src & 31u));
-        sm.lsort_key[lane] = src < 32u ? ck : 0ull;
-        sm.lsort_slot[lane] = src < 32u ? src : 0u;
-      } else {
-        uint64_t k2 = key; uint32_t sl = 32u + (uint32_t)lane;
-        warp_sort_desc_kv(k2, sl, lane);
-        sm.psort_key[lane] = k2; sm.psort_slot[lane] = sl;
+      uint64_t k2 = key; uint32_t sl = 32u + (uint32_t)lane;
+      warp_sort_desc_kv(k2, sl, lane);
+      sm.psort_key[lane] = k2; sm.psort_slot[lane] = sl;
+    }
+    bar_sync(1, (1 + PIPE_DEPTH) * 32);         // done
+  }
+}
+
+// prep team (PIPE_PREP_TW warps): requests seq = team, team + PIPE_PREP_TEAMS, ...  Waits for the scanners' answer, gathers the
+// 32 records, evaluates the depth chain (warp w: depths w, w + TW, ...) and publishes pb[seq % PIPE_RQ].
+template <int RR, int WW>
+__device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int team, const int w, const int lane) {
+  constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
+  PipeG* pg = S.pg;
+  const int bar_id = 2 + team;
+  for (uint32_t seq = (uint32_t)team;; seq += PIPE_PREP_TEAMS) {
+    const uint32_t idx = seq % PIPE_RQ, slot = seq % PIPE_RING, tag = seq + 1;
+    PrepBuf<NC>& P = sm.pb[idx];
+    if (w == 0) {
+      // warp 0 of the team waits (for the request to exist, then for the scanners' answer) and decides for the team, so that
+      // all four warps leave together when the cycle ends
+      uint32_t status = 0;                      // 0 ok, 1 quit, 2 timeout (kept warp-uniform)
+      if (lane == 0) {
+        while ((int32_t)(*((volatile uint32_t*)&sm.rq_posted) - seq) <= 0) {
+          if (*((volatile uint32_t*)&sm.v_quit)) { status = 1; break; }
+          __nanosleep(40);
+        }
+      }
+      status = __shfl_sync(FULL, status, 0);
+      unsigned long long w0 = 0, w1 = 0;
+      if (status == 0) {
+        __threadfence_block();
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[sm.rq_cls[idx]]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&P.cls);
+        for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = __ldg(src + i);
+        // the request's list: lane l polls its own two LL words (payload + tag in one 8-byte word each)
+        const long long deadline = clock64() + PIPE_DEADLINE;
+        for (;;) {
+          ld_relaxed_2u64(&pg->list[slot][2 * lane], w0, w1);
+          const bool okl = (uint32_t)(w0 >> 32) == tag && (uint32_t)(w1 >> 32) == tag;
+          if (__all_sync(FULL, okl)) break;
+          const uint32_t st = *((volatile uint32_t*)&sm.v_quit) ? 1u : (clock64() > deadline ? 2u : 0u);
+          status = __shfl_sync(FULL, st, 0);     // nobody waits for this list any more / timeout: lane 0 decides
+          if (status) break;
+          __nanosleep(20);
+        }
+      }
+      P.list[lane] = status ? 0ull : ((w0 & 0xFFFFFFFFull) | (w1 << 32));
+      if (lane == 0) { sm.prep_status[team] = status; if (status == 2) sm.v_err = 1; }
+      __threadfence_block();
+    }
+    bar_sync(bar_id, PIPE_PREP_TW * 32);        // P.cls, P.list and the team's status are in place
+    if (*((volatile uint32_t*)&sm.prep_status[team]) == 1) return;
+    const uint64_t listkey = P.list[lane];
+    const uint32_t node = key_node(listkey);
+    const bool have = listkey != 0 && node < S.N;
+    uint64_t rec[NC];
+#pragma unroll
+    for (uint32_t c = 0; c < NC; ++c) rec[c] = 0;
+    if (have) {
+      const uint64_t* g = S.tiles + (size_t)(node / TILE_NODES) * ((size_t)NC * TILE_NODES) + (node % TILE_NODES);
+#pragma unroll
+      for (uint32_t c = 0; c < NC; ++c) rec[c] = __ldcg(g + (size_t)c * TILE_NODES);
+    }
+    if (w == 0) {
+#pragma unroll
+      for (uint32_t c = 0; c < NC; ++c) P.rec[c][lane] = rec[c];
+    }
+    for (int k = 0; k < w; ++k) advance_rec<RR, WW>(rec, P.cls);
+#pragma unroll 1
+    for (int d = w; d < PIPE_DEPTH; d += PIPE_PREP_TW) {
+      uint64_t key = 0;
+      bool fi = false;
+      if (have) {
+        RegAcc acc{rec, R, W};
+        key = eval_pair<RR, WW>(S.cf, P.cls, acc, node, &fi);
+      }
+      P.key[d][lane] = key;
+      const unsigned fim = __ballot_sync(FULL, have && fi);
+      if (lane == 0) P.fi[d] = fim;
+      if (d + PIPE_PREP_TW < PIPE_DEPTH)
+        for (int k = 0; k < PIPE_PREP_TW; ++k) advance_rec<RR, WW>(rec, P.cls);
+    }
+    __threadfence_block();
+    bar_sync(bar_id, PIPE_PREP_TW * 32);        // every depth is in place
+    if (w == 0 && lane == 0) {
+      *((volatile uint32_t*)&sm.pb_ready[idx]) = tag;
+      *((volatile uint32_t*)&sm.prep_done[team]) = seq + PIPE_PREP_TEAMS;
+    }
+  }
+}
+
+// shadow warp: pulls the job / queue rows the control plane will read at the next visits into this SM's L1 (the replayer CTA is
+// the only writer of those tables, so its L1 stays coherent): the jobs at the head of the current queue's static order, their
+// task order rows, the queue rows.  Read-only hints; nothing depends on what it reads.
+template <int NC>
+__device__ __forceinline__ void pipe_shadow_warp(const DevSession& S, ReplaySmem<NC>& sm, const int lane) {
+  uint32_t seen = 0;
+  uint32_t acc = 0;
+  for (;;) {
+    uint32_t v;
+    while ((v = *((volatile uint32_t*)&sm.v_count)) == seen) {
+      if (*((volatile uint32_t*)&sm.v_quit)) { if (lane == 0) sm.sink = acc; return; }
+      __nanosleep(100);
+    }
+    seen = v;
+    const uint32_t q = *((volatile uint32_t*)&sm.ctl.cur_queue);
+    if (q >= S.Q) continue;
+    const uint32_t R = S.cf.R;
+    const uint32_t h = S.q_static_head[q], hend = S.q_static_off[q + 1];
+    // lanes 0..7: one upcoming job each
+    if (lane < 8 && h + (uint32_t)lane < hend) {
+      const uint32_t jn = S.q_static[h + lane];
+      const uint32_t pn = S.job_pos[jn], en = S.job_ord_off[jn + 1];
+      acc += (uint32_t)S.job_ready[jn] + (uint32_t)S.job_min_avail[jn] + S.job_placed[jn] + S.job_queue[jn] + (uint32_t)S.job_prio[jn] + S.job_tb_rank[jn];
+      acc += (uint32_t)double_as_u64(S.job_share[jn]);
+      for (uint32_t k = 0; k < R; ++k) acc += (uint32_t)double_as_u64(S.job_alloc[(size_t)k * S.J + jn]);
+      if (pn < en) {
+        acc += S.ord_class[pn] + S.ord_run[pn] + S.ord_task[pn] + S.ord_task[min(en - 1, pn + 31)];
+        acc += S.ord_chain[(size_t)pn * (KB_CHAIN_MAX - 1)] + S.ord_chain[(size_t)pn * (KB_CHAIN_MAX - 1) + KB_CHAIN_MAX - 2];
       }
     }
-    bar_sync(1, 17 * 32);                       // done
+    if ((uint32_t)lane < R) acc += (uint32_t)double_as_u64(S.q_allocated[(size_t)lane * S.Q + q]) + (uint32_t)double_as_u64(S.q_deserved[(size_t)lane * S.Q + q]);
+    acc += S.q_deserved_present[q] + (uint32_t)double_as_u64(S.q_share[q]);
+    if (S.Q > 1) {
+      const uint32_t len = *((volatile uint32_t*)&sm.ctl.qheap_len);
+      for (uint32_t i = (uint32_t)lane * 32u; i < len && i < 4096u; i += 1024u) acc += S.qheap[i];
+      const uint32_t up = ((len + 1) >> lane);
+      if (up >= 1 && up - 1 < len) acc += S.qheap[up - 1];
+      for (uint32_t qq = lane; qq < S.Q; qq += 32) {
+        acc += (uint32_t)double_as_u64(S.q_share[qq]) + (uint32_t)S.q_ctime[qq] + S.q_static_head[qq] + S.q_static_off[qq + 1];
+        for (uint32_t k = 0; k < R; ++k)
+          acc += (uint32_t)double_as_u64(S.q_deserved[(size_t)k * S.Q + qq]) + (uint32_t)double_as_u64(S.q_allocated[(size_t)k * S.Q + qq]);
+        const uint32_t hq = S.q_static_head[qq];
+        if (hq < S.q_static_off[qq + 1]) {
+          const uint32_t jn = S.q_static[hq];
+          const uint32_t pn = S.job_pos[jn];
+          acc += (uint32_t)S.job_ready[jn] + (uint32_t)S.job_min_avail[jn] + S.job_ord_off[jn + 1] + S.ord_class[pn] + S.ord_run[pn] + S.ord_task[pn];
+        }
+      }
+      const uint32_t dl = *((volatile uint32_t*)&sm.ctl.dyn_len);
+      if ((uint32_t)lane < dl) acc += S.dyn_jobs[lane];
+    }
   }
 }
 
@@ -430,19 +552,9 @@ __device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem
       __syncwarp();
       if (lane == 0) { st_release_u32(&pg->log_head, b); *((volatile uint32_t*)&sm.pub_head) = b; }
     } else if (kind == PCMD_REQ) {
-      // a = class, b = seq.  The slot's previous request (seq - PIPE_RING) must have been answered before it is reused.
+      // a = class, b = seq.  The slot's previous request (seq - PIPE_RING) was consumed by its prep team long ago: main does
+      // not enter request seq into the table before the team has finished seq - PIPE_RQ (PIPE_RQ <= PIPE_RING).
       const uint32_t slot = b % PIPE_RING;
-      if (b >= PIPE_RING) {
-        const uint32_t otag = b - PIPE_RING + 1;
-        const long long deadline = clock64() + PIPE_DEADLINE;
-        for (;;) {
-          unsigned long long w0, w1;
-          ld_relaxed_2u64(&pg->list[slot][2 * lane], w0, w1);
-          const bool ok = (uint32_t)(w0 >> 32) == otag && (uint32_t)(w1 >> 32) == otag;
-          if (__all_sync(FULL, ok)) break;
-          if (clock64() > deadline) { if (lane == 0) { pg->error = 3; st_release_u32(&pg->quit, 1u); } break; }
-        }
-      }
       if (lane == 0) {
         const unsigned long long tag = (unsigned long long)(b + 1) << 32;
         const uint32_t stamp = *((volatile uint32_t*)&sm.pub_head);
@@ -469,12 +581,17 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   Ctl* gctl = S.ctl;
   if (warp == 0) {
     load_ctl(sm.ctl, gctl, lane);
-    if (lane < (int)PIPE_RQ) { sm.rq_cls[lane] = 0xFFFFFFFFu; sm.rq_seq[lane] = 0; sm.rq_stamp[lane] = 0; }
-    if (lane == 0) { sm.cmd_head = 0; sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.ext_slot = 0xFFFFFFFFu; }
+    if (lane < (int)PIPE_RQ) { sm.rq_cls[lane] = 0xFFFFFFFFu; sm.rq_seq[lane] = 0; sm.rq_stamp[lane] = 0; sm.pb_ready[lane] = 0; }
+    if (lane < PIPE_PREP_TEAMS) sm.prep_done[lane] = (uint32_t)lane;
+    if (lane == 0) { sm.cmd_head = 0; sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.v_count = 0; sm.rq_posted = 0; sm.ext_slot = 0xFFFFFFFFu; }
   }
   __syncthreads();
-  if (warp >= 1 && warp <= 16) { pipe_eval_warp<RR, WW>(S, sm, warp - 1, lane); return; }
-  if (warp == 17) { pipe_writer_warp<RR, WW>(S, sm, lane); return; }
+  if (warp >= PIPE_W_PATCH0 && warp < PIPE_W_PATCH0 + PIPE_DEPTH) { pipe_patch_warp<RR, WW>(S, sm, warp - PIPE_W_PATCH0, lane); return; }
+  if (warp >= PIPE_W_PREP0 && warp < PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW) {
+    pipe_prep_warp<RR, WW>(S, sm, (warp - PIPE_W_PREP0) / PIPE_PREP_TW, (warp - PIPE_W_PREP0) % PIPE_PREP_TW, lane); return; }
+  if (warp == PIPE_W_WRITER) { pipe_writer_warp<RR, WW>(S, sm, lane); return; }
+  if (warp == PIPE_W_SHADOW) { pipe_shadow_warp<NC>(S, sm, lane); return; }
+  if (warp != 0) return;
 
   // ---------------- main warp ----------------
   Ctl& c = sm.ctl;
@@ -506,7 +623,20 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   };
   auto post_request = [&](uint32_t cls) -> uint32_t {
     const uint32_t seq = next_seq++;
-    if (lane == 0) { sm.rq_cls[seq % PIPE_RQ] = cls; sm.rq_seq[seq % PIPE_RQ] = seq; sm.rq_stamp[seq % PIPE_RQ] = priv_head; c.pipe_requests += 1; }
+    // the table entry / prepared buffer of request seq - PIPE_RQ is recycled: its team must be through with it
+    if (seq >= PIPE_RQ) {
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      while ((int32_t)(*((volatile uint32_t*)&sm.prep_done[seq % PIPE_PREP_TEAMS]) - (seq - PIPE_RQ)) <= 0) {
+        if (clock64() > deadline) { failed = true; break; }
+        __nanosleep(20);
+      }
+    }
+    if (lane == 0) {
+      sm.rq_cls[seq % PIPE_RQ] = cls; sm.rq_seq[seq % PIPE_RQ] = seq; sm.rq_stamp[seq % PIPE_RQ] = priv_head;
+      c.pipe_requests += 1; c.pairs_scanned += (unsigned long long)S.N;
+      __threadfence_block();
+      *((volatile uint32_t*)&sm.rq_posted) = seq + 1;
+    }
     __syncwarp();
     push_cmd(PCMD_REQ, cls, seq);
     return seq;
@@ -516,79 +646,107 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   while (!c.done && !failed) {
     const uint32_t cls_id = c.cur_class;
     const long long t_v0 = clock64();
+    if (lane == 0) *((volatile uint32_t*)&sm.v_count) = sm.v_count + 1;       // wakes the shadow warp
     // ---------------- visit start: which list ----------------
     uint32_t seq = 0, stamp = 0;
     bool usable = rq_lookup(cls_id, seq, stamp);
     usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor;
     if (!usable) { seq = post_request(cls_id); stamp = priv_head; if (lane == 0) c.pipe_urgent += 1; }
     fresh_floor = 0;
+    const uint32_t pbi = seq % PIPE_RQ;
     {
-      const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
-      uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
-      for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = src[i];
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      while (*((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) {
+        if (clock64() > deadline || *((volatile uint32_t*)&sm.v_err)) { failed = true; break; }
+      }
+      __threadfence_block();
     }
+    if (failed) break;
+    const PrepBuf<NC>& P = sm.pb[pbi];
     // patch set: log entries [stamp, priv_head); of several entries of one node only the latest holds its current record
     const uint32_t npatch = priv_head - stamp;
-    {
+    uint32_t pn = 0xFFFFFFF0u - (uint32_t)lane;
+    if (npatch) {
       const bool pv = (uint32_t)lane < npatch;
-      const uint32_t pn = pv ? sm.hot_node[(stamp + lane) % PIPE_HOT] : (0xFFFFFFF0u - (uint32_t)lane);
+      if (pv) pn = sm.hot_node[(stamp + lane) % PIPE_HOT];
       const unsigned same = __match_any_sync(FULL, pn);
       const bool latest = pv && (same >> (lane + 1)) == 0u;
       const unsigned pvalid = __ballot_sync(FULL, latest);
       sm.pnode[lane] = pn;
       if (lane == 0) {
-        sm.v_slot = seq % PIPE_RING; sm.v_tag = seq + 1; sm.v_stamp = stamp; sm.v_npatch = npatch; sm.v_pvalid = pvalid;
-        if (npatch) { c.pipe_patched += 1; c.pipe_patch_entries += npatch; }
+        sm.v_pb = pbi; sm.v_stamp = stamp; sm.v_npatch = npatch; sm.v_pvalid = pvalid;
+        c.pipe_patched += 1; c.pipe_patch_entries += npatch; c.pairs_replayed += (unsigned long long)__popc(pvalid);
       }
+      __syncwarp();
+      bar_sync(1, (1 + PIPE_DEPTH) * 32);        // go: the patch warps evaluate depths 0..7 of the modified nodes
     }
-    __syncwarp();
-    bar_sync(1, 17 * 32);          // go: the 16 eval warps poll the list, gather, evaluate depths 0..7 of the pool
-    bar_sync(1, 17 * 32);          // done
-    if (*((volatile uint32_t*)&sm.v_err)) { if (lane == 0) { c.error = 3; } failed = true; break; }
+    // ---------------- meanwhile: the prepared list minus the modified nodes, compacted (order is kept) ----------------
+    uint64_t cur_key; uint32_t slot;
+    {
+      const uint64_t lk = P.list[lane];
+      const uint32_t lnode = key_node(lk);
+      bool ok = lk != 0;
+      for (uint32_t i = 0; i < npatch; ++i) ok = ok && (__shfl_sync(FULL, pn, (int)i) != lnode);
+      const uint64_t k0 = ok ? P.key[0][lane] : 0ull;
+      const unsigned am = __ballot_sync(FULL, k0 != 0);
+      const unsigned src = __fns(am, 0, lane + 1);
+      const uint64_t ck = __shfl_sync(FULL, k0, (int)(src & 31u));
+      cur_key = src < 32u ? ck : 0ull;
+      slot = src < 32u ? src : 0u;
+    }
+    const uint64_t f0 = P.list[KTOP - 1];
+    uint64_t dropped = 0;
+    if (npatch) {
+      bar_sync(1, (1 + PIPE_DEPTH) * 32);        // done
+      warp_merge_top32_kv(cur_key, slot, sm.psort_key[lane], sm.psort_slot[lane], dropped, lane);
+    }
     const long long t_v1 = clock64();
     // ---------------- pool -> 32 lane-owned candidates ----------------
-    uint64_t cur_key = sm.lsort_key[lane];
-    uint32_t slot = sm.lsort_slot[lane];
-    uint64_t dropped = 0;
-    warp_merge_top32_kv(cur_key, slot, sm.psort_key[lane], sm.psort_slot[lane], dropped, lane);
-    const uint64_t f0 = sm.v_list[KTOP - 1];
     const uint64_t floor_key = f0 > dropped ? f0 : dropped;
     const bool have = cur_key != 0;
     const uint32_t my_node = key_node(cur_key);
     const uint32_t my_h = slot >> 5, my_l = slot & 31u;
     uint32_t depth = 0;                        // placements made on MY candidate
-    bool cur_fi = have && ((sm.cfi[0][my_h] >> my_l) & 1u);
-    if (lane == 0) { c.scans += 1; c.pairs_scanned += (unsigned long long)S.N; c.pairs_replayed += (unsigned long long)__popc(sm.v_pvalid) ; }
-    // my candidate's base record (state at depth 0), for the final state at write-back time
-    uint64_t rec0[NC];
-    if (have) {
+    bool cur_fi = have && (((my_h ? sm.pfi[0] : P.fi[0]) >> my_l) & 1u);
+    if (lane == 0) c.scans += 1;
+    // key / fits-idle of MY candidate at depth dd (dd >= 1): precomputed chain, else the extension buffer
+    auto chain_has = [&](uint32_t dd) -> bool { return dd < (uint32_t)PIPE_DEPTH || (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u); };
+    auto chain_key = [&](uint32_t dd) -> uint64_t {
+      return dd < (uint32_t)PIPE_DEPTH ? (my_h ? sm.pkey[dd][my_l] : P.key[dd][my_l]) : sm.ext_key[dd - sm.ext_base]; };
+    auto chain_fi = [&](uint32_t dd) -> bool {
+      return dd < (uint32_t)PIPE_DEPTH ? ((((my_h ? sm.pfi[dd] : P.fi[dd]) >> my_l) & 1u) != 0) : (((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0);
+    };
+    // my candidate's base record (state at depth 0): prepared buffer or hot ring
+    auto load_rec0 = [&](uint64_t* r0) {
       if (my_h == 0) {
-        const uint64_t* g = S.tiles + (size_t)(my_node / TILE_NODES) * ((size_t)NC * TILE_NODES) + (my_node % TILE_NODES);
 #pragma unroll
-        for (uint32_t cc = 0; cc < NC; ++cc) rec0[cc] = __ldcg(g + (size_t)cc * TILE_NODES);
+        for (uint32_t cc = 0; cc < NC; ++cc) r0[cc] = P.rec[cc][my_l];
       } else {
         const uint32_t hi = (stamp + my_l) % PIPE_HOT;
 #pragma unroll
-        for (uint32_t cc = 0; cc < NC; ++cc) rec0[cc] = sm.hot_rec[cc][hi];
+        for (uint32_t cc = 0; cc < NC; ++cc) r0[cc] = sm.hot_rec[cc][hi];
       }
-    }
-    // key / fits-idle of MY candidate at depth dd (dd >= 1): precomputed chain, else the extension buffer
-    auto chain_has = [&](uint32_t dd) -> bool { return dd < (uint32_t)PIPE_DEPTH || (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u); };
-    auto chain_key = [&](uint32_t dd) -> uint64_t { return dd < (uint32_t)PIPE_DEPTH ? sm.ckey[dd][slot] : sm.ext_key[dd - sm.ext_base]; };
-    auto chain_fi = [&](uint32_t dd) -> bool {
-      return dd < (uint32_t)PIPE_DEPTH ? (((sm.cfi[dd][my_h] >> my_l) & 1u) != 0) : (((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0);
     };
     // extension: the whole warp evaluates depths base .. base+31 of the owner's candidate
     auto extend = [&](const uint32_t owner) {
       const uint32_t oslot = __shfl_sync(FULL, slot, owner), odepth = __shfl_sync(FULL, depth, owner), onode = __shfl_sync(FULL, my_node, owner);
       uint64_t r2[NC];
+      {
+        const uint32_t oh = oslot >> 5, ol = oslot & 31u;
+        if (oh == 0) {
 #pragma unroll
-      for (uint32_t cc = 0; cc < NC; ++cc) r2[cc] = __shfl_sync(FULL, rec0[cc], owner);
+          for (uint32_t cc = 0; cc < NC; ++cc) r2[cc] = P.rec[cc][ol];
+        } else {
+          const uint32_t hi = (stamp + ol) % PIPE_HOT;
+#pragma unroll
+          for (uint32_t cc = 0; cc < NC; ++cc) r2[cc] = sm.hot_rec[cc][hi];
+        }
+      }
       const uint32_t base = odepth + 1, target = base + (uint32_t)lane;
-      for (uint32_t k = 0; k < target; ++k) advance_rec<RR, WW>(r2, sm.cls);
+      for (uint32_t k = 0; k < target; ++k) advance_rec<RR, WW>(r2, P.cls);
       RegAcc acc{r2, R, W};
       bool f = false;
-      const uint64_t k2 = eval_pair<RR, WW>(S.cf, sm.cls, acc, onode, &f);
+      const uint64_t k2 = eval_pair<RR, WW>(S.cf, P.cls, acc, onode, &f);
       __syncwarp();
       sm.ext_key[lane] = k2;
       const unsigned fm = __ballot_sync(FULL, f);
@@ -613,7 +771,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       ready = __shfl_sync(FULL, ready, 0); min_avail = __shfl_sync(FULL, min_avail, 0);
       double jalloc = 0.0, qalloc = 0.0, my_rq = 0.0;
       if ((uint32_t)lane < R) {
-        my_rq = sm.cls.resreq[lane];
+        my_rq = P.cls.resreq[lane];
         if (S.drf_present) jalloc = S.job_alloc[(size_t)lane * S.J + j];
         if (S.proportion_present) qalloc = S.q_allocated[(size_t)lane * S.Q + q];
       }
@@ -704,7 +862,9 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       // the writer must have written back the ring entries this append overwrites
       while (priv_head + nmod - *((volatile uint32_t*)&sm.pub_head) > PIPE_HOT - PIPE_PATCH) __nanosleep(20);
       if (modified) {
-        for (uint32_t k = 0; k < depth; ++k) advance_rec<RR, WW>(rec0, sm.cls);
+        uint64_t rec0[NC];
+        load_rec0(rec0);
+        for (uint32_t k = 0; k < depth; ++k) advance_rec<RR, WW>(rec0, P.cls);
         const uint32_t hi = (priv_head + (uint32_t)__popc(mm & ((1u << lane) - 1u))) % PIPE_HOT;
 #pragma unroll
         for (uint32_t cc = 0; cc < NC; ++cc) sm.hot_rec[cc][hi] = rec0[cc];
@@ -749,12 +909,12 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   // ---------------- wind down ----------------
   if (lane == 0) { *((volatile uint32_t*)&sm.v_quit) = 1; }
   __syncwarp();
-  bar_sync(1, 17 * 32);                         // releases the eval warps
+  bar_sync(1, (1 + PIPE_DEPTH) * 32);           // releases the patch warps
   push_cmd(PCMD_QUIT, 0, 0);
   while (*((volatile uint32_t*)&sm.cmd_tail) != cmd_head - 1 + 0u && *((volatile uint32_t*)&sm.cmd_tail) != cmd_head) __nanosleep(40);
   if (lane == 0) {
     c.cyc_total += (unsigned long long)(clock64() - t_cycle0);
-    if (failed && !c.error) c.error = 3;
+    if ((failed || *((volatile uint32_t*)&sm.v_err)) && !c.error) c.error = 3;
     const uint32_t perr = ld_relaxed_u32(&pg->error);
     if (perr && !c.error) c.error = perr;
   }
