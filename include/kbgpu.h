@@ -171,6 +171,29 @@ typedef struct kb_plugin_conf {
   const kb_tier* tiers;
 } kb_plugin_conf;
 
+/*
+ * The Running tasks of the session, one by one: what reclaim / preempt walk (`for _, task := range n.Tasks`, reclaim.go:124-138,
+ * preempt.go:195-201) and what the flattened snapshot only carries as aggregates.  Optional: only kb_reclaim / kb_preempt read it.
+ * Every entry is a task with Status == Running that sits on node `node` of the snapshot and belongs to job `job`; the job's
+ * job_ready0 / job_alloc0 and the node's Idle / Used / pod count already include it.
+ */
+#define KB_RUNNING_CRITICAL (1u << 0) /* system-cluster-critical / system-node-critical priority class or kube-system namespace (conformance.go:45-53) */
+typedef struct kb_running {
+  uint32_t n;
+  uint32_t reserved0;
+  const uint32_t* node;         /* [n] node index                                                             */
+  const uint32_t* job;          /* [n] job index                                                              */
+  const double*   resreq;       /* [R][n] TaskInfo.Resreq                                                     */
+  const uint32_t* res_present;  /* [n] bit r (r>=2): scalar r present in Resreq.ScalarResources               */
+  const int32_t*  prio;         /* [n] TaskInfo.Priority                                                      */
+  const int64_t*  ctime;        /* [n] Pod.CreationTimestamp                                                  */
+  const uint32_t* uid_rank;     /* [n] rank of TaskInfo.UID among the running tasks (the reference iterates the Go map n.Tasks;
+                                       the deterministic rule is UID order)                     */
+  const uint32_t* flags;        /* [n] KB_RUNNING_*                                                           */
+  const int32_t*  job_waiting0; /* [J] or NULL (= 0): Pipelined tasks of the job at session open (WaitingTaskNum, job_info.go:396-405);
+                                       non-zero only when an earlier action of the same cycle pipelined tasks  */
+} kb_running;
+
 #define KB_ENGINE_NO_OVERLAP    (1u << 0) /* never run the scan of the next visit concurrently with the replay */
 #define KB_ENGINE_FORCE_OVERLAP (1u << 1) /* always (single GPU); default: only when the scan dominates (large N) */
 #define KB_ENGINE_CHAIN_OFF     (1u << 2) /* one class per launch (visit_kernel); default: chained visits (single GPU, no overlap) */
@@ -236,6 +259,8 @@ typedef struct kb_stats {
   uint32_t pipe_extends;    /*   candidate chains extended beyond the 8 pre-evaluated placement depths       */
   uint32_t pipe_patched;    /*   lists consumed with a non-empty patch set (nodes modified since the scan)   */
   uint32_t pipe_patch_entries; /* log entries re-evaluated by those patches                                  */
+  uint32_t evictions;       /* kb_reclaim / kb_preempt: cache.Evict calls                                            */
+  uint32_t evict_sweeps;    /*   node sweeps executed (identical failing sweeps of one job are skipped)              */
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,
@@ -267,6 +292,26 @@ int kb_allocate(struct kb_engine* e, kb_decision* out, kb_stats* stats);
  * straight after kb_session_load it is the action list "backfill" alone.  kb_allocate restarts from the loaded state.
  * `out` (T entries) is the full decision table; best-effort tasks that found no node change from SKIPPED to NONE. */
 int kb_backfill(struct kb_engine* e, kb_decision* out, kb_stats* stats);
+
+/* Hands the Running tasks of the loaded session to the engine (call after kb_session_load, before kb_reclaim / kb_preempt).
+ * `snap` must be the snapshot the preceding kb_session_load was given (task order keys and job ranges are read from it again).
+ * Replaces nothing in the reference: NodeInfo.Tasks is part of the session there. */
+int kb_session_load_running(struct kb_engine* e, const kb_snapshot* snap, const kb_running* running);
+
+/* Replaces reclaimAction.Execute (actions/reclaim/reclaim.go:41-193): queues by QueueOrderFn, per queue the best job by JobOrderFn
+ * and its first Pending task by TaskOrderFn; the first node (canonical order) on which ssn.PredicateFn passes and the Running tasks
+ * of OTHER queues that ssn.Reclaimable returns (session_plugins.go:80-118) cover InitResreq: those are evicted (ssn.Evict,
+ * session.go:317-353) until InitResreq is covered and the task is pipelined there (ssn.Pipeline).  Runs from the LOADED state.
+ *   out         [T]          kind PIPELINED + node + step for reclaimers, NONE otherwise
+ *   evicted     [running.n]  1 if cache.Evict was called for the running task (may be NULL)
+ *   evict_order [running.n]  0-based order of that call, 0xFFFFFFFF if none (may be NULL)                                  */
+int kb_reclaim(struct kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats);
+
+/* Replaces preemptAction.Execute (actions/preempt/preempt.go:43-270): per queue, preemption between the jobs of the queue under a
+ * framework.Statement (statement.go: Evict / Pipeline, Commit when ssn.JobPipelined, Discard otherwise), then between the tasks
+ * of each job; nodes in util.SortNodes order (best NodeOrderFn score first), victims by ssn.Preemptable, lowest priority first.
+ * Same outputs as kb_reclaim; evictions of discarded statements are not reported (they never reached the cache).            */
+int kb_preempt(struct kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats);
 
 /* Debug / parity: predicate + score of tasks [task_lo, task_hi) against every node in the CURRENT
  * device state (util.PredicateNodes + util.PrioritizeNodes for a task range, scheduler_helper.go:63-171).

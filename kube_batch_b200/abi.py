@@ -194,7 +194,55 @@ class kb_stats(C.Structure):
         ("pipe_extends", C.c_uint32),
         ("pipe_patched", C.c_uint32),
         ("pipe_patch_entries", C.c_uint32),
+        ("evictions", C.c_uint32),
+        ("evict_sweeps", C.c_uint32),
     ]
+
+
+KB_RUNNING_CRITICAL = 1 << 0
+
+
+class kb_running(C.Structure):
+    """Running tasks one by one (include/kbgpu.h kb_running): what reclaim / preempt walk."""
+    _fields_ = [
+        ("n", C.c_uint32),
+        ("reserved0", C.c_uint32),
+        ("node", C.POINTER(C.c_uint32)),
+        ("job", C.POINTER(C.c_uint32)),
+        ("resreq", C.POINTER(C.c_double)),
+        ("res_present", C.POINTER(C.c_uint32)),
+        ("prio", C.POINTER(C.c_int32)),
+        ("ctime", C.POINTER(C.c_int64)),
+        ("uid_rank", C.POINTER(C.c_uint32)),
+        ("flags", C.POINTER(C.c_uint32)),
+        ("job_waiting0", C.POINTER(C.c_int32)),
+    ]
+
+
+def running_to_c(running, R: int, J: int = 0):
+    """dict of arrays (builder.py meta["running"]) -> (kb_running, keep-alive list)."""
+    import numpy as np
+    n = 0 if running is None else len(running["node"])
+    spec = (("node", np.uint32), ("job", np.uint32), ("resreq", np.float64), ("res_present", np.uint32), ("prio", np.int32),
+            ("ctime", np.int64), ("uid_rank", np.uint32), ("flags", np.uint32))
+    arrs = {}
+    for k, dt in spec:
+        a = np.ascontiguousarray(running[k], dtype=dt) if n else np.zeros((R, 1) if k == "resreq" else 1, dtype=dt)
+        arrs[k] = a
+    if n:
+        assert arrs["resreq"].shape == (R, n)
+    r = kb_running()
+    r.n = n
+    ctypes_of = {np.uint32: C.c_uint32, np.float64: C.c_double, np.int32: C.c_int32, np.int64: C.c_int64}
+    for k, dt in spec:
+        setattr(r, k, arrs[k].ctypes.data_as(C.POINTER(ctypes_of[dt])))
+    keep = list(arrs.values())
+    jw = None if running is None else running.get("job_waiting0")
+    if jw is not None:
+        jw = np.ascontiguousarray(jw, dtype=np.int32)
+        r.job_waiting0 = jw.ctypes.data_as(C.POINTER(C.c_int32))
+        keep.append(jw)
+    return r, keep
 
 
 DECISION_DTYPE = [

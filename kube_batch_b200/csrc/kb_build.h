@@ -63,6 +63,10 @@ struct HostConf {
   int w_nodeaff = 1;                // nodeaffinity.weight (nodeorder.go:111-117); only read when the session has preferred terms
   bool task_order_priority = false, queue_order_proportion = false, proportion_present = false, drf_present = false,
        gang_ready = false;
+  // reclaim / preempt (kb_evict.h): EvictFn bits of the first tier with an enabled reclaimableFn / preemptableFn, and whether
+  // gang's JobPipelinedFn is enabled
+  uint32_t reclaim_fns = 0, preempt_fns = 0;
+  bool gang_pipelined = false;
 };
 
 // plugins/factory.go:31-42 by name; OnSessionOpen registrations resolved in tier order (session_plugins.go)
@@ -103,6 +107,21 @@ inline int resolve_conf(BuildErr* e, const kb_plugin_conf* conf, uint32_t R, uin
     // pass 2: dispatch chains in tier / plugin order
     int nj = 0;
     auto in_chain = [&](uint32_t c) { for (int i = 0; i < nj; ++i) if (hc.jobcmp[i] == c) return true; return false; };
+    for (uint32_t t = 0; t < conf->n_tiers; ++t) {
+      // session_plugins.go:80-162: the first tier in which any enabled plugin registered a filter decides (an empty result
+      // stays empty through the later tiers).  Registrations: gang.go:93-94, priority.go:100, drf.go:110, proportion.go:196,
+      // conformance.go:61-62.  EvictFn bit values are spelled out here (kb_evict.h): gang 1, priority 2, drf 4, proportion 8, conformance 16.
+      uint32_t rf = 0, pf = 0;
+      for (uint32_t p = 0; p < conf->tiers[t].n_plugins; ++p) {
+        const kb_plugin_option& o = conf->tiers[t].plugins[p];
+        const int id = id_of(o.name);
+        if (o.enabled_reclaimable) rf |= id == P_GANG ? 1u : id == P_PROPORTION ? 8u : id == P_CONFORMANCE ? 16u : 0u;
+        if (o.enabled_preemptable) pf |= id == P_GANG ? 1u : id == P_PRIORITY ? 2u : id == P_DRF ? 4u : id == P_CONFORMANCE ? 16u : 0u;
+        if (o.enabled_job_pipelined && id == P_GANG) hc.gang_pipelined = true;
+      }
+      if (!hc.reclaim_fns) hc.reclaim_fns = rf;
+      if (!hc.preempt_fns) hc.preempt_fns = pf;
+    }
     for (uint32_t t = 0; t < conf->n_tiers; ++t)
       for (uint32_t p = 0; p < conf->tiers[t].n_plugins; ++p) {
         const kb_plugin_option& o = conf->tiers[t].plugins[p];
@@ -213,6 +232,7 @@ struct BuiltSession {
   std::vector<ClassPref> class_pref; // [C] preferred node-affinity terms per class — HOST ONLY (read by tests/emu's prototype of
   bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
+  std::vector<uint32_t> q_alloc_present;   // [Q] scalar presence of proportion's queueAttr.allocated at session open (kb_evict.h: Resource.Less)
 
   // The BACKFILL VIEW of the same session (backfillAction.Execute, actions/backfill/backfill.go:40-71): same node table,
   // job / queue accounting, decisions and exchange buffers; its own task order (best-effort tasks only), cursors and
@@ -255,6 +275,7 @@ struct BuiltSession {
     D.kchain = kchain; D.ord_chain = (uint32_t*)(ib + oi.ord_chain);
     D.pipe = pipe; D.pipe_S = pipe_S; D.pipe_tpc = pipe_tpc; D.pipe_pad = 0;
     D.pg = (PipeG*)(mb + om.pipe_g); D.modlog = (uint32_t*)(mb + om.modlog); D.pcand = (uint64_t*)(mb + om.pcand);
+    D.dbg = nullptr;
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -608,6 +629,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   for (uint32_t j = 0; j < J; ++j) { if (hc.drf_present) update_job_share(H, j); else H.job_share[j] = 0.0; }
 
   // proportion OnSessionOpen (proportion.go:58-154)
+  B.q_alloc_present.assign(std::max(1u, Q), 0);
   if (hc.proportion_present) {
     struct Attr { bool used = false; int32_t weight = 0; HostRes deserved, allocated, request; };
     std::vector<Attr> qa(Q);
@@ -652,6 +674,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     }
     for (uint32_t q = 0; q < Q; ++q) {
       H.q_deserved_present[q] = qa[q].deserved.present;
+      B.q_alloc_present[q] = qa[q].allocated.present;
       for (uint32_t r = 0; r < R; ++r) {
         H.q_deserved[(size_t)r * Q + q] = (r < 2 || ((qa[q].deserved.present >> r) & 1u)) ? qa[q].deserved.v[r] : 0.0;
         H.q_allocated[(size_t)r * Q + q] = (r < 2 || ((qa[q].allocated.present >> r) & 1u)) ? qa[q].allocated.v[r] : 0.0;

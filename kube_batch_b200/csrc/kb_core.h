@@ -183,6 +183,21 @@ KB_HD uint64_t pack_key(int64_t biased_score, uint32_t node) {
 KB_HD uint32_t key_node(uint64_t key) { return 0xFFFFFFFFu - (uint32_t)(key & 0xFFFFFFFFull); }
 KB_HD int64_t key_score(uint64_t key) { return (int64_t)(key >> 32); }
 
+// K2 alone: the biased weighted sum of the Map priorities for one (class, node) pair (util/scheduler_helper.go:162-168)
+template <class NodeAcc>
+KB_HD int64_t node_score(const EvalConf& cf, const ClassRec& c, const NodeAcc& n) {
+  int64_t score = cf.score_bias;
+  if (cf.nodeorder) {
+    // resource_allocation.go:100-123: req = nodeInfo.NonZeroRequest() + pod non-zero request
+    const int64_t rc = n.nz_cpu() + c.nz_cpu, rm = n.nz_mem() + c.nz_mem;
+    const int64_t ac = n.alloc_cpu(), am = n.alloc_mem();
+    if (cf.w_least)    score += ((least_requested_score(rc, ac) + least_requested_score(rm, am)) / 2) * (int64_t)cf.w_least;
+    if (cf.w_most)     score += ((most_requested_score(rc, ac) + most_requested_score(rm, am)) / 2) * (int64_t)cf.w_most;
+    if (cf.w_balanced) score += balanced_score(rc, ac, rm, am) * (int64_t)cf.w_balanced;
+  }
+  return score;
+}
+
 // NodeAcc concept: idle(r) rel(r) -> double; alloc_cpu() alloc_mem() nz_cpu() nz_mem() -> int64_t;
 // pods() max_pods() -> int32_t; flags() -> uint32_t; labels(w) taints(w) ports(w) -> uint64_t.
 //
@@ -249,16 +264,7 @@ KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n
   if (pred_ok) *pred_ok = pok;
   ok = ok & pok;
 
-  int64_t score = cf.score_bias;
-  if (cf.nodeorder) {
-    // resource_allocation.go:100-123: req = nodeInfo.NonZeroRequest() + pod non-zero request
-    const int64_t rc = n.nz_cpu() + c.nz_cpu, rm = n.nz_mem() + c.nz_mem;
-    const int64_t ac = n.alloc_cpu(), am = n.alloc_mem();
-    if (cf.w_least)    score += ((least_requested_score(rc, ac) + least_requested_score(rm, am)) / 2) * (int64_t)cf.w_least;
-    if (cf.w_most)     score += ((most_requested_score(rc, ac) + most_requested_score(rm, am)) / 2) * (int64_t)cf.w_most;
-    if (cf.w_balanced) score += balanced_score(rc, ac, rm, am) * (int64_t)cf.w_balanced;
-  }
-  return ok ? pack_key(score, node_idx) : 0ull;
+  return ok ? pack_key(node_score(cf, c, n), node_idx) : 0ull;
 }
 
 }  // namespace kb

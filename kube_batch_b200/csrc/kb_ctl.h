@@ -145,6 +145,7 @@ struct DevSession {
   PipeG* pg;
   uint32_t* modlog;       // [To + 64] node ids in modification order (one entry per node a visit chain modified)
   uint64_t* pcand;        // [PIPE_RING][pipe_S][KTOP] per-CTA candidate lists of the requests in flight
+  uint32_t* dbg;          // 64 progress words in mapped host memory (KB_PIPE_DEBUG=1; NULL otherwise): read by the host watchdog when a cycle hangs
 };
 constexpr uint32_t KB_MAX_WORLD = 8;
 constexpr uint32_t P2P_RANK_U64 = (2 + 2 * KB_MAX_R + 6 + 3 * KB_MAX_W) * 32;         // keys + widest record block + flag row

@@ -12,6 +12,7 @@
 // No CPU fallback exists: every decision is produced by the kernels.
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
@@ -24,8 +25,10 @@
 #include <vector>
 
 #include "kb_build.h"
+#include "kb_evict_build.h"
 #include "kb_kernels.cuh"
 #include "kb_pipe.cuh"
+#include "kb_evict.cuh"
 
 using namespace kb;
 
@@ -108,6 +111,15 @@ struct kb_engine {
   bool replicated = false;                  // world > 1 and every rank runs the whole cycle on the full node table
   bool coop_ok = false;                     // device supports cooperative launches
   size_t pipe_smem = 0;
+  // reclaim / preempt (kb_evict.h): the Running tasks and the actions' own state, loaded by kb_session_load_running
+  EvictBuilt ev_built;
+  EvictDev ev{};
+  unsigned char* d_ev_imm = nullptr; unsigned char* d_ev_mut = nullptr; unsigned char* d_ev_pristine = nullptr;
+  size_t ev_cap_imm = 0, ev_cap_mut = 0;
+  bool running_loaded = false;
+  uint32_t* h_dbg = nullptr;                // KB_PIPE_DEBUG=1: 64 progress words of cycle_kernel in mapped host memory
+  uint32_t* d_dbg = nullptr;
+  double watchdog_s = 30.0;                 // a cycle_kernel that has not finished after this long is reported (with the progress words) and the process aborts: a hung cooperative kernel cannot be cancelled
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
   DevSession graph_dev{};              // kernel parameter the graph was captured with
@@ -154,6 +166,10 @@ void free_session(kb_engine* e) {
   if (e->d_pristine) cudaFree(e->d_pristine);
   if (e->d_imm) cudaFree(e->d_imm);
   if (e->h_dec) cudaFreeHost(e->h_dec);
+  if (e->d_ev_imm) cudaFree(e->d_ev_imm);
+  if (e->d_ev_mut) cudaFree(e->d_ev_mut);
+  if (e->d_ev_pristine) cudaFree(e->d_ev_pristine);
+  e->d_ev_imm = e->d_ev_mut = e->d_ev_pristine = nullptr; e->ev_cap_imm = e->ev_cap_mut = 0; e->running_loaded = false;
   e->d_mut = e->d_pristine = e->d_imm = nullptr; e->h_dec = nullptr;
   e->loaded = false;
 }
@@ -254,12 +270,17 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   if (const char* pp = getenv("KB_PIPE")) e->pipe_req = atoi(pp) != 0;
   if (const char* sh = getenv("KB_SHARD")) e->shard_req = atoi(sh) != 0;
   if (const char* pd = getenv("KB_PDL")) e->pdl = atoi(pd) != 0;
+  if (const char* wd = getenv("KB_WATCHDOG_S")) e->watchdog_s = atof(wd);
   if (const char* kc = getenv("KB_CHAIN")) { const int v = atoi(kc); if (v == 1 || v == 2 || v == 4) e->kchain_req = (uint32_t)v; }
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
       (c = cudaEventCreate(&e->ev0)) != cudaSuccess || (c = cudaEventCreate(&e->ev1)) != cudaSuccess ||
       (c = cudaMallocHost(&e->h_ctl, sizeof(Ctl))) != cudaSuccess) {
     g_create_err = std::string("CUDA init failed: ") + cudaGetErrorString(c);
     delete e; return KB_E_CUDA;
+  }
+  if (const char* dbg = getenv("KB_PIPE_DEBUG")) if (atoi(dbg) != 0) {
+    if (cudaHostAlloc(&e->h_dbg, 64 * 4, cudaHostAllocMapped) == cudaSuccess && cudaHostGetDevicePointer(&e->d_dbg, e->h_dbg, 0) == cudaSuccess) memset(e->h_dbg, 0, 64 * 4);
+    else { e->h_dbg = nullptr; e->d_dbg = nullptr; cudaGetLastError(); }
   }
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, e->device) == cudaSuccess) { e->sm_count = prop.multiProcessorCount; e->coop_ok = prop.cooperativeLaunch != 0; }
@@ -283,6 +304,7 @@ void kb_engine_destroy(kb_engine* e) {
   if (e->d_xchg) cudaFree(e->d_xchg);
   if (e->comm) g_nccl.CommDestroy(e->comm);
   if (e->h_ctl) cudaFreeHost(e->h_ctl);
+  if (e->h_dbg) cudaFreeHost(e->h_dbg);
   if (e->ev0) cudaEventDestroy(e->ev0);
   if (e->ev1) cudaEventDestroy(e->ev1);
   if (e->stream) cudaStreamDestroy(e->stream);
@@ -361,6 +383,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   for (int r = 0; r < 8; ++r) e->dev_bf.peer_base[r] = e->p2p_peer[r];
   e->Tb = B.Tb;
   e->allocate_ran = false;
+  e->running_loaded = false;
   e->d_task_class = (uint32_t*)(e->d_imm + oi.task_class);
   e->d_job_ready0 = (int32_t*)(e->d_imm + oi.job_ready0);
   e->R = R; e->W = W; e->N = N; e->T = T; e->J = J; e->Q = Q; e->C = C; e->NT = NT; e->ncols = ncols; e->To = To;
@@ -455,6 +478,8 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
     if (use_pipe) {
       // ONE cooperative launch runs the whole cycle: pipe_S scanner CTAs with resident tiles + the replayer CTA
       DevSession dv = D;
+      dv.dbg = e->d_dbg;
+      if (e->h_dbg) memset(e->h_dbg, 0, 64 * 4);
       void* args[] = {(void*)&dv};
       CUDA_TRY(e, cudaLaunchCooperativeKernel((const void*)cycle_kernel<3, 2>, dim3(D.pipe_S + 1), dim3(PIPE_THREADS), args, e->pipe_smem, e->stream));
       launches += 1;
@@ -481,6 +506,22 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       launches += ((e->world == 1 || D.p2p) ? 1 : 2) * batch;
     }
     CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, D.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    if (use_pipe && e->watchdog_s > 0) {
+      // a persistent cooperative kernel that deadlocks cannot be cancelled from the host: poll instead of blocking, and if the
+      // cycle is still running after watchdog_s say where it stands and abort the process (the driver then resets the context)
+      const auto t0 = std::chrono::steady_clock::now();
+      cudaError_t q;
+      while ((q = cudaStreamQuery(e->stream)) == cudaErrorNotReady) {
+        if (std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > e->watchdog_s) {
+          fprintf(stderr, "libkbgpu: cycle_kernel did not finish within %.0f s — aborting.", e->watchdog_s);
+          if (e->h_dbg) { fprintf(stderr, " progress words:"); for (int i = 0; i < 32; ++i) fprintf(stderr, " %u", e->h_dbg[i]); }
+          fprintf(stderr, "\n");
+          fflush(stderr);
+          _exit(86);
+        }
+      }
+      if (q != cudaSuccess) return fail(e, KB_E_CUDA, "cycle_kernel failed: %s", cudaGetErrorString(q));
+    }
     CUDA_TRY(e, cudaStreamSynchronize(e->stream));
     if (e->h_ctl->done) break;
     if (use_pipe) return fail(e, e->h_ctl->error == 3 ? KB_E_CUDA : KB_E_STATE, "cycle_kernel ended without finishing the cycle (device error %u)", e->h_ctl->error);
@@ -542,6 +583,103 @@ int kb_backfill(kb_engine* e, kb_decision* out, kb_stats* stats) {
   if (!e) return KB_E_BADARG;
   if (!e->loaded) return fail(e, KB_E_STATE, "kb_backfill before kb_session_load");
   return run_action(e, true, out, stats);
+}
+
+int kb_session_load_running(kb_engine* e, const kb_snapshot* s, const kb_running* run) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_session_load_running before kb_session_load");
+  if (!s || s->N != e->N || s->T != e->T || s->J != e->J || s->Q != e->Q || s->R != e->R)
+    return fail(e, KB_E_BADARG, "kb_session_load_running: `snap` is not the snapshot of the loaded session");
+  if (e->world > 1 && !e->replicated) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt run on the full node table: not with KB_ENGINE_SHARD");
+  if (e->built.has_pref) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt with preferred node affinity are outside this build");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  e->running_loaded = false;
+  BuildErr be;
+  DevSession H{};
+  e->built.bind(H, e->built.mut.host.data(), e->built.imm.host.data());      // host view of the as-loaded state: the heaps' comparators read it
+  const int rc = build_evict(s, run, e->built, H, e->ev_built, &be);
+  if (rc) return fail(e, rc, "%s", be.msg.c_str());
+  const size_t ib = e->ev_built.imm.host.size(), mb = e->ev_built.mut.host.size();
+  if (ib > e->ev_cap_imm) {
+    if (e->d_ev_imm) cudaFree(e->d_ev_imm);
+    e->d_ev_imm = nullptr; e->ev_cap_imm = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_ev_imm, ib + ib / 4));
+    e->ev_cap_imm = ib + ib / 4;
+  }
+  if (mb > e->ev_cap_mut) {
+    if (e->d_ev_mut) cudaFree(e->d_ev_mut);
+    if (e->d_ev_pristine) cudaFree(e->d_ev_pristine);
+    e->d_ev_mut = e->d_ev_pristine = nullptr; e->ev_cap_mut = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_ev_mut, mb + mb / 4));
+    CUDA_TRY(e, cudaMalloc(&e->d_ev_pristine, mb + mb / 4));
+    e->ev_cap_mut = mb + mb / 4;
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_ev_imm, e->ev_built.imm.host.data(), ib, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_ev_pristine, e->ev_built.mut.host.data(), mb, cudaMemcpyHostToDevice, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  e->ev_built.bind(e->ev, e->d_ev_imm, e->d_ev_mut);
+  e->running_loaded = true;
+  return KB_OK;
+}
+
+namespace {
+// reclaim / preempt: ONE launch of evict_kernel (one CTA; the node sweep of a preemptor is data-parallel over its threads,
+// the control flow of the action runs uniformly in every thread, kb_evict.h) from the as-loaded state.
+int run_evict(kb_engine* e, const bool preempt, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
+  if (!e->running_loaded) return fail(e, KB_E_STATE, "%s before kb_session_load_running", preempt ? "kb_preempt" : "kb_reclaim");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(e->d_ev_mut, e->d_ev_pristine, e->ev_built.mut.host.size(), cudaMemcpyDeviceToDevice, e->stream));
+  e->allocate_ran = false;
+  if (preempt) evict_kernel<1><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
+  else evict_kernel<0><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
+  CUDA_TRY(e, cudaGetLastError());
+  const uint32_t n = e->ev_built.n_run;
+  std::vector<uint32_t> order(std::max(1u, n)), orig(std::max(1u, n));
+  EvictCtl ctl{};
+  if (e->T) CUDA_TRY(e, cudaMemcpyAsync(e->h_dec, e->dev.dec, (size_t)e->T * sizeof(kb_decision), cudaMemcpyDeviceToHost, e->stream));
+  if (n) CUDA_TRY(e, cudaMemcpyAsync(order.data(), e->ev.evict_order, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaMemcpyAsync(&ctl, e->ev.ctl, sizeof ctl, cudaMemcpyDeviceToHost, e->stream));
+  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
+  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
+  if (ctl.error == 2) return fail(e, KB_E_UNSUPPORTED_FEATURE, "a node hands more than %u victims to one preemptor", KB_EVICT_MAXV);
+  if (ctl.error) return fail(e, KB_E_STATE, "the reference would panic here: Resource.Sub on an insufficient resource (resource_info.go:158)");
+  const uint32_t* r_orig = (const uint32_t*)(e->ev_built.imm.host.data() + e->ev_built.oi.r_orig);
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t i = r_orig[k];
+    if (evicted) evicted[i] = order[k] != 0xFFFFFFFFu ? 1 : 0;
+    if (evict_order) evict_order[i] = order[k];
+  }
+  if (out) for (uint32_t t = 0; t < e->T; ++t) {
+    kb_decision d = e->h_dec[t];
+    if (d.kind != KB_KIND_PIPELINED) { d.node = -1; d.kind = KB_KIND_NONE; d.dispatched = 0; d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu; }
+    out[t] = d;
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->pairs_logical = ctl.pairs_logical; stats->pairs_scanned = (uint64_t)ctl.scans * e->N;
+    stats->tasks_processed = ctl.tasks_processed; stats->tasks_pipelined = ctl.n_pipelined;
+    stats->kernel_launches = 1; stats->n_classes = e->C;
+    stats->evictions = ctl.n_evicted; stats->evict_sweeps = ctl.scans;
+    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
+    stats->gpu_ms = ms; stats->load_ms = e->load_ms;
+    stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)n * 4 + sizeof ctl;
+  }
+  return KB_OK;
+}
+}  // namespace
+
+int kb_reclaim(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_reclaim before kb_session_load");
+  return run_evict(e, false, out, evicted, evict_order, stats);
+}
+
+int kb_preempt(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
+  if (!e) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_preempt before kb_session_load");
+  return run_evict(e, true, out, evicted, evict_order, stats);
 }
 
 int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {

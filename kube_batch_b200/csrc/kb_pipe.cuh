@@ -66,6 +66,8 @@ __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned l
 __device__ __forceinline__ void ld_relaxed_2u64(const unsigned long long* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+// progress word -> mapped host memory (debug builds of a session only; a store, so it never stalls the warp)
+__device__ __forceinline__ void dbg_put(uint32_t* dbg, int i, uint32_t v) { if (dbg) *((volatile uint32_t*)(dbg + i)) = v; }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // record held in registers (column c at r[c]); NC = tile_ncols(R, W) is a compile-time constant here
@@ -233,6 +235,7 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
     }
     bar_sync(bar_id, 128);
     if (G.quit) return;
+    if (cta == 0 && gt == 0) dbg_put(S.dbg, 24 + g, (seq << 4) | 1u);
     const uint32_t cls_id = G.cls_id, stamp = G.stamp;
     {
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
@@ -424,6 +427,7 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
       if (lane == 0) { sm.prep_status[team] = status; if (status == 2) sm.v_err = 1; }
       __threadfence_block();
     }
+    if (w == 0 && lane == 0) dbg_put(S.dbg, 8 + team, (seq << 4) | 1u);
     bar_sync(bar_id, PIPE_PREP_TW * 32);        // P.cls, P.list and the team's status are in place
     if (*((volatile uint32_t*)&sm.prep_status[team]) == 1) return;
     const uint64_t listkey = P.list[lane];
@@ -457,6 +461,7 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
         for (int k = 0; k < PIPE_PREP_TW; ++k) advance_rec<RR, WW>(rec, P.cls);
     }
     __threadfence_block();
+    if (lane == 0) dbg_put(S.dbg, 16 + team * 4 + w, (seq << 4) | 2u);
     bar_sync(bar_id, PIPE_PREP_TW * 32);        // every depth is in place
     if (w == 0 && lane == 0) {
       *((volatile uint32_t*)&sm.pb_ready[idx]) = tag;
@@ -567,7 +572,7 @@ __device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem
     }
     tail += 1;
     __syncwarp();
-    if (lane == 0) *((volatile uint32_t*)&sm.cmd_tail) = tail;
+    if (lane == 0) { *((volatile uint32_t*)&sm.cmd_tail) = tail; dbg_put(S.dbg, 12, tail); }
   }
 }
 
@@ -646,7 +651,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   while (!c.done && !failed) {
     const uint32_t cls_id = c.cur_class;
     const long long t_v0 = clock64();
-    if (lane == 0) *((volatile uint32_t*)&sm.v_count) = sm.v_count + 1;       // wakes the shadow warp
+    if (lane == 0) { *((volatile uint32_t*)&sm.v_count) = sm.v_count + 1; dbg_put(S.dbg, 0, sm.v_count); dbg_put(S.dbg, 1, 1u); dbg_put(S.dbg, 2, cls_id); }       // wakes the shadow warp
     // ---------------- visit start: which list ----------------
     uint32_t seq = 0, stamp = 0;
     bool usable = rq_lookup(cls_id, seq, stamp);
@@ -654,6 +659,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     if (!usable) { seq = post_request(cls_id); stamp = priv_head; if (lane == 0) c.pipe_urgent += 1; }
     fresh_floor = 0;
     const uint32_t pbi = seq % PIPE_RQ;
+    if (lane == 0) { dbg_put(S.dbg, 1, 2u); dbg_put(S.dbg, 3, seq); dbg_put(S.dbg, 4, stamp); dbg_put(S.dbg, 5, priv_head); dbg_put(S.dbg, 6, next_seq); }
     {
       const long long deadline = clock64() + PIPE_DEADLINE;
       while (*((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) {
@@ -678,6 +684,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         c.pipe_patched += 1; c.pipe_patch_entries += npatch; c.pairs_replayed += (unsigned long long)__popc(pvalid);
       }
       __syncwarp();
+      if (lane == 0) dbg_put(S.dbg, 1, 3u);
       bar_sync(1, (1 + PIPE_DEPTH) * 32);        // go: the patch warps evaluate depths 0..7 of the modified nodes
     }
     // ---------------- meanwhile: the prepared list minus the modified nodes, compacted (order is kept) ----------------
@@ -686,7 +693,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       const uint64_t lk = P.list[lane];
       const uint32_t lnode = key_node(lk);
       bool ok = lk != 0;
-      for (uint32_t i = 0; i < npatch; ++i) ok = ok && (__shfl_sync(FULL, pn, (int)i) != lnode);
+      for (uint32_t i = 0; i < npatch; ++i) { const uint32_t o = __shfl_sync(FULL, pn, (int)i); ok = ok & (o != lnode); }   // no short-circuit: every lane takes part in the shuffle
       const uint64_t k0 = ok ? P.key[0][lane] : 0ull;
       const unsigned am = __ballot_sync(FULL, k0 != 0);
       const unsigned src = __fns(am, 0, lane + 1);
@@ -701,6 +708,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       warp_merge_top32_kv(cur_key, slot, sm.psort_key[lane], sm.psort_slot[lane], dropped, lane);
     }
     const long long t_v1 = clock64();
+    if (lane == 0) dbg_put(S.dbg, 1, 4u);
     // ---------------- pool -> 32 lane-owned candidates ----------------
     const uint64_t floor_key = f0 > dropped ? f0 : dropped;
     const bool have = cur_key != 0;
@@ -854,6 +862,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       if (reason == STOP_RESCAN) { rescanned = true; break; }
     }
 
+    if (lane == 0) { dbg_put(S.dbg, 1, 5u); dbg_put(S.dbg, 7, c.rescans); }
     // ---------------- end of the visit chain on this class: modified candidates -> hot ring + log ----------------
     const bool modified = depth > 0;
     const unsigned mm = __ballot_sync(FULL, modified);
@@ -875,6 +884,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       priv_head += nmod;
     }
     if (rescanned) fresh_floor = priv_head;
+    if (lane == 0) dbg_put(S.dbg, 1, 6u);
     // ---------------- planner: scan requests for the classes of the next visits ----------------
     if (!c.done) {
       uint32_t pc[KB_CHAIN_MAX];
@@ -907,6 +917,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   }
 
   // ---------------- wind down ----------------
+  if (lane == 0) dbg_put(S.dbg, 1, 7u);
   if (lane == 0) { *((volatile uint32_t*)&sm.v_quit) = 1; }
   __syncwarp();
   bar_sync(1, (1 + PIPE_DEPTH) * 32);           // releases the patch warps

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
 EXPORTS = [
     "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_backfill", "kb_predicate_score",
     "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
-    "kb_nccl_unique_id", "kb_last_kernel_ms",
+    "kb_nccl_unique_id", "kb_last_kernel_ms", "kb_session_load_running", "kb_reclaim", "kb_preempt",
 ]
 
 
@@ -119,6 +119,31 @@ class Engine:
         st = abi.kb_stats()
         self._check(self.L.kb_backfill(self._h, dec.ctypes.data_as(C.c_void_p), C.byref(st)), "kb_backfill")
         return CycleResult(dec[:T], st)
+
+    def load_running(self, running: Optional[dict]):
+        """Hands the Running tasks (builder.py: snapshot.meta["running"]) to the engine: needed by reclaim() / preempt()."""
+        cs, keep1 = self.snap.to_c()
+        cr, keep2 = abi.running_to_c(running, self.snap.R, self.snap.J)
+        self._check(self.L.kb_session_load_running(self._h, C.byref(cs), C.byref(cr)), "kb_session_load_running")
+        self._n_run = int(cr.n)
+        return self
+
+    def _evict(self, fn, what):
+        T, n = self.snap.T, self._n_run
+        dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+        ev = np.zeros(max(n, 1), dtype=np.uint8)
+        order = np.zeros(max(n, 1), dtype=np.uint32)
+        st = abi.kb_stats()
+        self._check(fn(self._h, dec.ctypes.data_as(C.c_void_p), _p(ev, C.c_uint8), _p(order, C.c_uint32), C.byref(st)), what)
+        return CycleResult(dec[:T], st), ev[:n].astype(bool), order[:n]
+
+    def reclaim(self):
+        """reclaimAction.Execute (actions/reclaim/reclaim.go:41-193) from the loaded state -> (CycleResult, evicted, evict_order)."""
+        return self._evict(self.L.kb_reclaim, "kb_reclaim")
+
+    def preempt(self):
+        """preemptAction.Execute (actions/preempt/preempt.go:43-270) from the loaded state -> (CycleResult, evicted, evict_order)."""
+        return self._evict(self.L.kb_preempt, "kb_preempt")
 
     def predicate_score(self, lo: int, hi: int):
         N = self.snap.N

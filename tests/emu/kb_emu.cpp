@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../kube_batch_b200/csrc/kb_build.h"
+#include "../../kube_batch_b200/csrc/kb_evict_build.h"
 
 using namespace kb;
 
@@ -702,6 +703,68 @@ int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t
                         job_share, job_ready, queue_share, queue_deserved, queue_allocated);
   delete E;
   return rc;
+}
+
+// reclaim (action 0) / preempt (action 1) from the as-loaded state: the product's kb_evict.h run by one CPU thread
+int kbemu_evict(const kb_snapshot* snap, const kb_running* running, const kb_plugin_conf* conf, uint32_t action,
+                kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats,
+                double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
+  Emu* E = (Emu*)kbemu_create2(snap, conf, 0, 1, 1);
+  if (!E) return KB_E_BADARG;
+  EvictBuilt EB;
+  BuildErr be;
+  if (int rc = build_evict(snap, running, E->B, E->S, EB, &be)) { g_err = be.msg; delete E; return rc; }
+  EvictDev D{};
+  EB.bind(D, EB.imm.host.data(), EB.mut.host.data());
+  CpuExec x;
+  if (action) run_preempt(x, E->S, D); else run_reclaim(x, E->S, D);
+  const EvictCtl& ctl = *D.ctl;
+  if (ctl.error) { g_err = ctl.error == 2 ? "victim overflow" : "the reference would panic (Resource.Sub)"; delete E; return KB_E_STATE; }
+  const uint32_t n = EB.n_run, T = E->B.T;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t i = D.r_orig[k];
+    if (evicted) evicted[i] = D.evict_order[k] != 0xFFFFFFFFu ? 1 : 0;
+    if (evict_order) evict_order[i] = D.evict_order[k];
+  }
+  // kbemu_finish without the gang commit (no dispatch in these actions): decisions of non-reclaimers read NONE
+  for (uint32_t t = 0; t < T; ++t) {
+    kb_decision& d = E->S.dec[t];
+    if (d.kind != KB_KIND_PIPELINED) { d.node = -1; d.kind = KB_KIND_NONE; d.dispatched = 0; d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu; }
+  }
+  const BuiltSession& B = E->B; const DevSession& S = E->S;
+  const uint32_t R = B.R, W = B.W, N = B.N, J = B.J, Q = B.Q;
+  if (out) memcpy(out, S.dec, (size_t)T * sizeof(kb_decision));
+  const size_t tile_u64 = (size_t)B.ncols * TILE_NODES;
+  for (uint32_t nn = 0; nn < N; ++nn) {
+    TileAcc a{S.tiles + (size_t)(nn / TILE_NODES) * tile_u64, nn % TILE_NODES, R, W};
+    for (uint32_t r = 0; r < R; ++r) {
+      if (node_idle) node_idle[(size_t)r * N + nn] = a.idle(r);
+      if (node_releasing) node_releasing[(size_t)r * N + nn] = a.rel(r);
+      if (node_used) node_used[(size_t)r * N + nn] = S.node_used[(size_t)r * N + nn];
+    }
+    if (node_pods) node_pods[nn] = a.pods();
+    if (node_nz_cpu) node_nz_cpu[nn] = a.nz_cpu();
+    if (node_nz_mem) node_nz_mem[nn] = a.nz_mem();
+    if (node_ports) for (uint32_t w = 0; w < W; ++w) node_ports[(size_t)w * N + nn] = a.ports(w);
+  }
+  for (uint32_t j = 0; j < J; ++j) { if (job_share) job_share[j] = S.job_share[j]; if (job_ready) job_ready[j] = S.job_ready[j]; }
+  for (uint32_t q = 0; q < Q; ++q) {
+    if (queue_share) queue_share[q] = S.q_share[q];
+    for (uint32_t r = 0; r < R; ++r) {
+      if (queue_deserved) queue_deserved[(size_t)r * Q + q] = S.q_deserved[(size_t)r * Q + q];
+      if (queue_allocated) queue_allocated[(size_t)r * Q + q] = S.q_allocated[(size_t)r * Q + q];
+    }
+  }
+  if (stats) {
+    memset(stats, 0, sizeof *stats);
+    stats->pairs_logical = ctl.pairs_logical; stats->pairs_scanned = (uint64_t)ctl.scans * N;
+    stats->tasks_processed = ctl.tasks_processed; stats->tasks_pipelined = ctl.n_pipelined;
+    stats->evictions = ctl.n_evicted; stats->evict_sweeps = ctl.scans; stats->n_classes = B.C;
+  }
+  delete E;
+  return KB_OK;
 }
 
 }  // extern "C"
