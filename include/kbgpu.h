@@ -313,6 +313,24 @@ int kb_reclaim(struct kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t
  * Same outputs as kb_reclaim; evictions of discarded statements are not reported (they never reached the cache).            */
 int kb_preempt(struct kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats);
 
+/* kb_cycle action ids: the reference's action names (actions/factory.go:28-33) */
+#define KB_ACT_RECLAIM  0
+#define KB_ACT_ALLOCATE 1
+#define KB_ACT_BACKFILL 2
+#define KB_ACT_PREEMPT  3
+
+/* One scheduling cycle on ONE session: the configured actions one after the other from the loaded state, like
+ * scheduler.go:88-101 runs `for _, action := range actions { action.Execute(ssn) }` (shipped configuration: "reclaim,
+ * allocate, backfill, preempt", config/kube-batch-conf.yaml:1).  Every action sees what the previous ones left: node
+ * Idle / Releasing, job / queue accounting of the plugins (drf, proportion, gang), the tasks still Pending, the Running
+ * tasks not yet evicted; each action fills its own queues from that state.  At most one allocate and one backfill per list.
+ *   out         [T]               the final decision table (kind / node / step; dispatched + dispatch_step from the gang commit)
+ *   evicted / evict_order         as kb_reclaim, over the whole cycle (NULL when no kb_running was loaded)
+ *   bounds      [2 * n_actions]   bounds[2i] = first step number NOT produced by actions 0..i, bounds[2i+1] = likewise for the
+ *                                 eviction order: which action made which decision (may be NULL)                              */
+int kb_cycle(struct kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decision* out, uint8_t* evicted,
+             uint32_t* evict_order, uint32_t* bounds, kb_stats* stats);
+
 /* Debug / parity: predicate + score of tasks [task_lo, task_hi) against every node in the CURRENT
  * device state (util.PredicateNodes + util.PrioritizeNodes for a task range, scheduler_helper.go:63-171).
  * fit   [(task_hi-task_lo)][N] uint8 (1 = predicateFn returned nil), may be NULL

@@ -371,6 +371,7 @@ KB_HD void select_next_visit(const DevSession& S, Ctl& c) {
       j = (int32_t)S.q_static[c.bf_cursor];
       c.bf_cursor += 1;
       q = S.job_queue[j];
+      if (S.job_pos[j] >= S.job_ord_off[j + 1]) continue;       // an earlier action of the cycle placed all of its best-effort tasks
     } else {
       if (c.qheap_len == 0) { c.done = 1; return; }                      // :90-92
       q = qheap_pop(S, c);                                                // :94
@@ -421,6 +422,67 @@ KB_HD void after_run(const DevSession& S, Ctl& c, uint32_t reason, uint32_t plac
   if (!end_visit) { setup_run(S, c); return; }
   if (!bf) qheap_push(S, c, c.cur_queue);                               // :192
   select_next_visit<BF>(S, c);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Continuing a cycle on ONE session (scheduler.go:88-101 runs the configured actions one after the other on the same
+// *framework.Session): what an action's own set-up reads from the session as the PREVIOUS actions left it.
+// Single-threaded (one device thread / the host / tests/emu); J is small next to the work of the actions themselves.
+// ---------------------------------------------------------------------------------------------
+// job.TaskStatusIndex[Pending] of view S: tasks an earlier action placed are moved to the front of their job's slot range
+// (order of the others kept) and the cursor starts behind them; run lengths are rebuilt for the rest.
+KB_HD void prep_task_lists(const DevSession& S) {
+  for (uint32_t j = 0; j < S.J; ++j) {
+    const uint32_t lo = S.job_ord_off[j], hi = S.job_ord_off[j + 1];
+    uint32_t front = lo;
+    for (uint32_t i = lo; i < hi; ++i) {
+      const uint8_t k = S.dec[S.ord_task[i]].kind;
+      if (k != KB_KIND_ALLOCATED && k != KB_KIND_PIPELINED) continue;
+      const uint32_t t = S.ord_task[i], c = S.ord_class[i];
+      for (uint32_t m = i; m > front; --m) { S.ord_task[m] = S.ord_task[m - 1]; S.ord_class[m] = S.ord_class[m - 1]; }
+      S.ord_task[front] = t; S.ord_class[front] = c;
+      front += 1;
+    }
+    if (front != lo)
+      for (uint32_t i = hi; i-- > front;) S.ord_run[i] = (i + 1 < hi && S.ord_class[i + 1] == S.ord_class[i]) ? S.ord_run[i + 1] + 1 : 1;
+    S.job_pos[j] = front;
+  }
+}
+
+// allocateAction.Execute's own queues (allocate.go:47-65) on the CURRENT state: JobOrderFn keys may have moved since the
+// per-queue lists were sorted at load (few do: insertion sort), the queue heap is refilled with one push per job, the
+// first visit is selected.  `step0`: the session's next Allocate / Pipeline sequence number.
+KB_HD void prep_allocate(const DevSession& S, Ctl& c, const uint32_t step0) {
+  for (uint32_t q = 0; q < S.Q; ++q) {
+    const uint32_t lo = S.q_static_off[q], hi = S.q_static_off[q + 1];
+    for (uint32_t i = lo + 1; i < hi; ++i) {
+      const uint32_t v = S.q_static[i];
+      uint32_t k = i;
+      while (k > lo && job_before(S, v, S.q_static[k - 1])) { S.q_static[k] = S.q_static[k - 1]; --k; }
+      S.q_static[k] = v;
+    }
+    S.q_static_head[q] = lo;
+  }
+  const uint32_t xe = c.xchg_epoch;
+  c.done = 0; c.cur_job = -1; c.qheap_len = 0; c.dyn_len = 0; c.error = 0;
+  c.step = step0;
+  for (uint32_t j = 0; j < S.J; ++j) qheap_push(S, c, S.job_queue[j]);      // one push PER JOB (allocate.go:52)
+  select_next_visit<0>(S, c);
+  c.scan_class = c.cur_class;
+  c.n_excl = 0; c.list_valid = 0; c.patch_valid = 0;
+  c.xchg_epoch = xe ? xe : 1;
+  publish_chain(S, c);
+}
+
+// backfillAction.Execute's set-up on the current state (backfill.go:45-47 walks ssn.Jobs and their Pending tasks afresh)
+KB_HD void prep_backfill(const DevSession& Sbf, Ctl& cb, const uint32_t step0) {
+  prep_task_lists(Sbf);
+  cb.done = 0; cb.cur_job = -1; cb.bf_cursor = 0; cb.error = 0;
+  cb.step = step0;
+  cb.bf_seeded = 1;
+  select_next_visit<1>(Sbf, cb);
+  cb.scan_class = cb.cur_class;
+  if (!cb.xchg_epoch) cb.xchg_epoch = 1;
 }
 
 }  // namespace kb

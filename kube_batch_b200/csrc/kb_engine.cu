@@ -117,6 +117,10 @@ struct kb_engine {
   unsigned char* d_ev_imm = nullptr; unsigned char* d_ev_mut = nullptr; unsigned char* d_ev_pristine = nullptr;
   size_t ev_cap_imm = 0, ev_cap_mut = 0;
   bool running_loaded = false;
+  bool imm_dirty = false;                   // a kb_cycle rewrote parts of d_imm (job lists / order slots): re-upload before the next action from the loaded state
+  uint32_t last_launches = 0;
+  int32_t* d_ready_start = nullptr;         // [J] ReadyTaskNum of every job when the cycle's allocate / backfill began (gang commit)
+  size_t cap_ready_start = 0;
   uint32_t* h_dbg = nullptr;                // KB_PIPE_DEBUG=1: 64 progress words of cycle_kernel in mapped host memory
   uint32_t* d_dbg = nullptr;
   double watchdog_s = 30.0;                 // a cycle_kernel that has not finished after this long is reported (with the progress words) and the process aborts: a hung cooperative kernel cannot be cancelled
@@ -169,6 +173,8 @@ void free_session(kb_engine* e) {
   if (e->d_ev_imm) cudaFree(e->d_ev_imm);
   if (e->d_ev_mut) cudaFree(e->d_ev_mut);
   if (e->d_ev_pristine) cudaFree(e->d_ev_pristine);
+  if (e->d_ready_start) cudaFree(e->d_ready_start);
+  e->d_ready_start = nullptr; e->cap_ready_start = 0;
   e->d_ev_imm = e->d_ev_mut = e->d_ev_pristine = nullptr; e->ev_cap_imm = e->ev_cap_mut = 0; e->running_loaded = false;
   e->d_mut = e->d_pristine = e->d_imm = nullptr; e->h_dec = nullptr;
   e->loaded = false;
@@ -384,6 +390,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->Tb = B.Tb;
   e->allocate_ran = false;
   e->running_loaded = false;
+  e->imm_dirty = false;
   e->d_task_class = (uint32_t*)(e->d_imm + oi.task_class);
   e->d_job_ready0 = (int32_t*)(e->d_imm + oi.job_ready0);
   e->R = R; e->W = W; e->N = N; e->T = T; e->J = J; e->Q = Q; e->C = C; e->NT = NT; e->ncols = ncols; e->To = To;
@@ -451,15 +458,34 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
 
 namespace {
 
+int finish_cycle(kb_engine* e, const bool backfill, const int32_t* d_ready_start, kb_decision* out, kb_stats* stats, uint32_t launches,
+                 const uint32_t batch, const bool use_pipe);
+
+// back to the as-loaded state: the mutable slab, the evict path's mutable slab, and — when a kb_cycle re-sorted job lists or
+// task order slots in it — the "immutable" slab
+cudaError_t restore_session(kb_engine* e) {
+  cudaError_t c = cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream);
+  if (c == cudaSuccess && e->imm_dirty) {
+    c = cudaMemcpyAsync(e->d_imm, e->built.imm.host.data(), e->imm_bytes, cudaMemcpyHostToDevice, e->stream);
+    e->imm_dirty = false;
+  }
+  if (c == cudaSuccess && e->running_loaded)
+    c = cudaMemcpyAsync(e->d_ev_mut, e->d_ev_pristine, e->ev_built.mut.host.size(), cudaMemcpyDeviceToDevice, e->stream);
+  return c;
+}
+
 // One action of the cycle on view `D`: launches until the view's control block reports done, then the gang commit and
 // the read-back.  allocate (D = e->dev) starts from the pristine tables and pumps the captured graph; backfill
 // (D = e->dev_bf) continues on the current tables with plain launches (there are few best-effort tasks).
-int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* stats) {
+// in_cycle: the action continues kb_cycle's session (no restore, set-up done by the caller, no commit / read-back here)
+int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* stats, const bool in_cycle = false) {
   const DevSession& D = backfill ? e->dev_bf : e->dev;
   CUDA_TRY(e, cudaSetDevice(e->device));
-  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  if (!backfill) CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
-  else seed_backfill_kernel<<<1, 32, 0, e->stream>>>(e->dev.ctl, e->dev_bf.ctl, e->allocate_ran ? 1 : 0);
+  if (!in_cycle) {
+    CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+    if (!backfill) CUDA_TRY(e, restore_session(e));
+    else seed_backfill_kernel<<<1, 32, 0, e->stream>>>(e->dev.ctl, e->dev_bf.ctl, e->allocate_ran ? 1 : 0);
+  }
   if (!backfill) e->allocate_ran = true;
   if (e->world > 1 && D.p2p && !e->replicated) {
     // a new action restarts the exchange sequence at 1: clear my flags, then make sure every rank has done so before
@@ -527,10 +553,23 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
     if (use_pipe) return fail(e, e->h_ctl->error == 3 ? KB_E_CUDA : KB_E_STATE, "cycle_kernel ended without finishing the cycle (device error %u)", e->h_ctl->error);
     if (launches > cap) return fail(e, KB_E_STATE, "%s cycle did not terminate within %llu launches", backfill ? "backfill" : "allocate", (unsigned long long)cap);
   }
+  e->last_launches = launches;
+  if (in_cycle) {
+    if (e->h_ctl->error == 2) return fail(e, KB_E_NCCL, "peer-memory exchange timed out waiting for another rank");
+    if (e->h_ctl->error) return fail(e, KB_E_STATE, "device reported invariant violation %u", e->h_ctl->error);
+    return KB_OK;
+  }
+  return finish_cycle(e, backfill, e->d_job_ready0, out, stats, launches, backfill ? 16u : BATCH, use_pipe);
+}
+
+// gang commit (K4), read-back of the decision table and the statistics of the view that ran last
+int finish_cycle(kb_engine* e, const bool backfill, const int32_t* d_ready_start, kb_decision* out, kb_stats* stats, uint32_t launches,
+                 const uint32_t batch, const bool use_pipe) {
+  const DevSession& D = backfill ? e->dev_bf : e->dev;
   if (e->J) {
     const uint32_t warps_per_block = 4;
     gang_commit_kernel<<<(e->J + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, e->stream>>>(
-        e->dev, e->d_job_ready0, e->dev_bf.ord_task, e->dev_bf.job_ord_off, e->dev_bf.job_pos);
+        e->dev, d_ready_start, e->dev_bf.ord_task, e->dev_bf.job_ord_off, e->dev_bf.job_pos);
     launches += 1;
   }
   CUDA_TRY(e, cudaGetLastError());
@@ -623,63 +662,139 @@ int kb_session_load_running(kb_engine* e, const kb_snapshot* s, const kb_running
 }
 
 namespace {
-// reclaim / preempt: ONE launch of evict_kernel (one CTA; the node sweep of a preemptor is data-parallel over its threads,
-// the control flow of the action runs uniformly in every thread, kb_evict.h) from the as-loaded state.
-int run_evict(kb_engine* e, const bool preempt, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
-  if (!e->running_loaded) return fail(e, KB_E_STATE, "%s before kb_session_load_running", preempt ? "kb_preempt" : "kb_reclaim");
-  CUDA_TRY(e, cudaSetDevice(e->device));
-  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
-  CUDA_TRY(e, cudaMemcpyAsync(e->d_mut, e->d_pristine, e->mut_bytes, cudaMemcpyDeviceToDevice, e->stream));
-  CUDA_TRY(e, cudaMemcpyAsync(e->d_ev_mut, e->d_ev_pristine, e->ev_built.mut.host.size(), cudaMemcpyDeviceToDevice, e->stream));
-  e->allocate_ran = false;
-  if (preempt) evict_kernel<1><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
-  else evict_kernel<0><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
-  CUDA_TRY(e, cudaGetLastError());
-  const uint32_t n = e->ev_built.n_run;
-  std::vector<uint32_t> order(std::max(1u, n)), orig(std::max(1u, n));
-  EvictCtl ctl{};
-  if (e->T) CUDA_TRY(e, cudaMemcpyAsync(e->h_dec, e->dev.dec, (size_t)e->T * sizeof(kb_decision), cudaMemcpyDeviceToHost, e->stream));
-  if (n) CUDA_TRY(e, cudaMemcpyAsync(order.data(), e->ev.evict_order, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(e, cudaMemcpyAsync(&ctl, e->ev.ctl, sizeof ctl, cudaMemcpyDeviceToHost, e->stream));
-  CUDA_TRY(e, cudaEventRecord(e->ev1, e->stream));
-  CUDA_TRY(e, cudaStreamSynchronize(e->stream));
-  if (ctl.error == 2) return fail(e, KB_E_UNSUPPORTED_FEATURE, "a node hands more than %u victims to one preemptor", KB_EVICT_MAXV);
-  if (ctl.error) return fail(e, KB_E_STATE, "the reference would panic here: Resource.Sub on an insufficient resource (resource_info.go:158)");
-  const uint32_t* r_orig = (const uint32_t*)(e->ev_built.imm.host.data() + e->ev_built.oi.r_orig);
-  for (uint32_t k = 0; k < n; ++k) {
-    const uint32_t i = r_orig[k];
-    if (evicted) evicted[i] = order[k] != 0xFFFFFFFFu ? 1 : 0;
-    if (evict_order) evict_order[i] = order[k];
-  }
-  if (out) for (uint32_t t = 0; t < e->T; ++t) {
-    kb_decision d = e->h_dec[t];
-    if (d.kind != KB_KIND_PIPELINED) { d.node = -1; d.kind = KB_KIND_NONE; d.dispatched = 0; d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu; }
-    out[t] = d;
-  }
-  if (stats) {
-    memset(stats, 0, sizeof *stats);
-    stats->pairs_logical = ctl.pairs_logical; stats->pairs_scanned = (uint64_t)ctl.scans * e->N;
-    stats->tasks_processed = ctl.tasks_processed; stats->tasks_pipelined = ctl.n_pipelined;
-    stats->kernel_launches = 1; stats->n_classes = e->C;
-    stats->evictions = ctl.n_evicted; stats->evict_sweeps = ctl.scans;
-    float ms = 0; cudaEventElapsedTime(&ms, e->ev0, e->ev1);
-    stats->gpu_ms = ms; stats->load_ms = e->load_ms;
-    stats->d2h_bytes = (uint64_t)e->T * sizeof(kb_decision) + (uint64_t)n * 4 + sizeof ctl;
-  }
-  return KB_OK;
+__global__ void carry_u32_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst) { if (threadIdx.x == 0 && blockIdx.x == 0) *dst = *src; }
+__global__ void prep_allocate_kernel(const __grid_constant__ DevSession S, const uint32_t* __restrict__ step_src) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  prep_task_lists(S);
+  prep_allocate(S, *S.ctl, step_src ? *step_src : 0u);
+}
+__global__ void prep_backfill_kernel(const __grid_constant__ DevSession Sbf, const uint32_t* __restrict__ step_src) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  prep_backfill(Sbf, *Sbf.ctl, step_src ? *step_src : 0u);
 }
 }  // namespace
 
-int kb_reclaim(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
+// scheduler.go:88-101 on the device: the action list on ONE session
+int kb_cycle(kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decision* out, uint8_t* evicted, uint32_t* evict_order,
+             uint32_t* bounds, kb_stats* stats) {
   if (!e) return KB_E_BADARG;
-  if (!e->loaded) return fail(e, KB_E_STATE, "kb_reclaim before kb_session_load");
-  return run_evict(e, false, out, evicted, evict_order, stats);
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_cycle before kb_session_load");
+  if (!actions && n_actions) return fail(e, KB_E_BADARG, "actions is NULL");
+  uint32_t n_alloc = 0, n_bf = 0;
+  for (uint32_t i = 0; i < n_actions; ++i) {
+    if (actions[i] > KB_ACT_PREEMPT) return fail(e, KB_E_BADARG, "unknown action %u", actions[i]);
+    n_alloc += actions[i] == KB_ACT_ALLOCATE; n_bf += actions[i] == KB_ACT_BACKFILL;
+    if ((actions[i] == KB_ACT_RECLAIM || actions[i] == KB_ACT_PREEMPT) && !e->running_loaded)
+      return fail(e, KB_E_STATE, "%s before kb_session_load_running", actions[i] == KB_ACT_RECLAIM ? "reclaim" : "preempt");
+  }
+  if (n_alloc > 1 || n_bf > 1) return fail(e, KB_E_BADARG, "at most one allocate and one backfill per cycle");
+  // A discarded Statement leaves TaskInfo.NodeName of its un-pipelined tasks behind (statement.go:153-188 never clears it), and
+  // the next ssn.Allocate / ssn.Pipeline of such a task on another node fails in NodeInfo.AddTask AFTER the status changed
+  // (node_info.go:173-176, session.go:241-262).  The shipped action order runs preempt last; other orders are refused
+  // rather than modelled.
+  for (uint32_t i = 0; i + 1 < n_actions; ++i)
+    if (actions[i] == KB_ACT_PREEMPT && actions[i + 1] != KB_ACT_PREEMPT)
+      return fail(e, KB_E_UNSUPPORTED_FEATURE, "an action after preempt: a discarded Statement leaves TaskInfo.NodeName behind (statement.go:153-188), outside this build");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  CUDA_TRY(e, cudaEventRecord(e->ev0, e->stream));
+  CUDA_TRY(e, restore_session(e));
+  e->allocate_ran = false;
+  if ((size_t)e->J * 4 > e->cap_ready_start) {
+    if (e->d_ready_start) cudaFree(e->d_ready_start);
+    e->d_ready_start = nullptr; e->cap_ready_start = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_ready_start, (size_t)std::max(1u, e->J) * 4));
+    e->cap_ready_start = (size_t)std::max(1u, e->J) * 4;
+  }
+  const uint32_t* step_alloc = (const uint32_t*)((const char*)e->dev.ctl + offsetof(Ctl, step));
+  const uint32_t* step_bf = (const uint32_t*)((const char*)e->dev_bf.ctl + offsetof(Ctl, step));
+  uint32_t* step_ev = e->running_loaded ? (uint32_t*)((char*)e->ev.ctl + offsetof(EvictCtl, step)) : nullptr;
+  const uint32_t* nev_ev = e->running_loaded ? (const uint32_t*)((const char*)e->ev.ctl + offsetof(EvictCtl, n_evicted)) : nullptr;
+  const uint32_t* latest = nullptr;          // who holds the session's step counter
+  bool dirty = false;                        // an earlier action of this cycle changed what allocate / backfill set up at load
+  bool ready_taken = false, bf_last = false, placed_ran = false;
+  uint32_t launches = 0;
+  bool use_pipe = false;
+  std::vector<uint32_t> hb(2 * (size_t)std::max(1u, n_actions), 0);
+  uint32_t* d_bounds = nullptr;
+  CUDA_TRY(e, cudaMalloc(&d_bounds, hb.size() * 4));
+  CUDA_TRY(e, cudaMemsetAsync(d_bounds, 0, hb.size() * 4, e->stream));
+  struct Free { uint32_t* p; ~Free() { if (p) cudaFree(p); } } free_bounds{d_bounds};
+  for (uint32_t i = 0; i < n_actions; ++i) {
+    const uint8_t a = actions[i];
+    if (a == KB_ACT_RECLAIM || a == KB_ACT_PREEMPT) {
+      if (latest && latest != step_ev) carry_u32_kernel<<<1, 1, 0, e->stream>>>(latest, step_ev);
+      if (a == KB_ACT_PREEMPT) evict_kernel<1><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
+      else evict_kernel<0><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
+      CUDA_TRY(e, cudaGetLastError());
+      launches += 1;
+      latest = step_ev; dirty = true;
+    } else {
+      const bool bf = a == KB_ACT_BACKFILL;
+      if (!ready_taken) {            // ssn.JobReady inside ssn.Allocate counts from the ReadyTaskNum the placing actions found
+        CUDA_TRY(e, cudaMemcpyAsync(e->d_ready_start, e->dev.job_ready, (size_t)e->J * 4, cudaMemcpyDeviceToDevice, e->stream));
+        ready_taken = true;
+      }
+      if (!bf) {
+        if (dirty || latest) { prep_allocate_kernel<<<1, 1, 0, e->stream>>>(e->dev, latest); e->imm_dirty = true; }
+        use_pipe = e->dev.pipe != 0;
+      } else {
+        if (dirty) { prep_backfill_kernel<<<1, 1, 0, e->stream>>>(e->dev_bf, latest); e->imm_dirty = true; }
+        else seed_backfill_kernel<<<1, 32, 0, e->stream>>>(e->dev.ctl, e->dev_bf.ctl, e->allocate_ran ? 1 : 0);
+      }
+      CUDA_TRY(e, cudaGetLastError());
+      const int rc = run_action(e, bf, nullptr, nullptr, true);
+      if (rc) return rc;
+      launches += e->last_launches;
+      latest = bf ? step_bf : step_alloc;
+      bf_last = bf; placed_ran = true;
+      // a later evicting action must see the placements: they are in the decision table and the node / job tables already
+      dirty = dirty || false;
+    }
+    if (latest) carry_u32_kernel<<<1, 1, 0, e->stream>>>(latest, d_bounds + 2 * i);
+    if (nev_ev) carry_u32_kernel<<<1, 1, 0, e->stream>>>(nev_ev, d_bounds + 2 * i + 1);
+  }
+  CUDA_TRY(e, cudaMemcpyAsync(hb.data(), d_bounds, hb.size() * 4, cudaMemcpyDeviceToHost, e->stream));
+  // evictions
+  const uint32_t n = e->running_loaded ? e->ev_built.n_run : 0;
+  std::vector<uint32_t> order(std::max(1u, n));
+  EvictCtl ectl{};
+  if (n) CUDA_TRY(e, cudaMemcpyAsync(order.data(), e->ev.evict_order, (size_t)n * 4, cudaMemcpyDeviceToHost, e->stream));
+  if (e->running_loaded) CUDA_TRY(e, cudaMemcpyAsync(&ectl, e->ev.ctl, sizeof ectl, cudaMemcpyDeviceToHost, e->stream));
+  if (!placed_ran) {
+    // no placing action ran: the control block the statistics come from is the allocate view's as loaded
+    CUDA_TRY(e, cudaMemcpyAsync(e->h_ctl, e->dev.ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+  }
+  int rc = finish_cycle(e, bf_last, ready_taken ? e->d_ready_start : e->d_job_ready0, out, stats, launches, BATCH, use_pipe);
+  if (rc) return rc;
+  if (ectl.error == 2) return fail(e, KB_E_UNSUPPORTED_FEATURE, "a node hands more than %u victims to one preemptor", KB_EVICT_MAXV);
+  if (ectl.error) return fail(e, KB_E_STATE, "the reference would panic here: Resource.Sub on an insufficient resource (resource_info.go:158)");
+  if (n) {
+    const uint32_t* r_orig = (const uint32_t*)(e->ev_built.imm.host.data() + e->ev_built.oi.r_orig);
+    for (uint32_t k = 0; k < n; ++k) {
+      const uint32_t i = r_orig[k];
+      if (evicted) evicted[i] = order[k] != 0xFFFFFFFFu ? 1 : 0;
+      if (evict_order) evict_order[i] = order[k];
+    }
+  }
+  if (bounds) for (uint32_t i = 0; i < 2 * n_actions; ++i) bounds[i] = hb[i];
+  if (stats) {
+    if (!placed_ran) { stats->pairs_logical = 0; stats->pairs_scanned = 0; stats->tasks_processed = 0; stats->tasks_pipelined = 0; }
+    stats->pairs_logical += ectl.pairs_logical; stats->pairs_scanned += (uint64_t)ectl.scans * e->N;
+    stats->tasks_processed += ectl.tasks_processed; stats->tasks_pipelined += ectl.n_pipelined;
+    stats->evictions = ectl.n_evicted; stats->evict_sweeps = ectl.scans;
+    stats->d2h_bytes += (uint64_t)n * 4 + sizeof ectl;
+  }
+  return KB_OK;
+}
+
+int kb_reclaim(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
+  const uint8_t a = KB_ACT_RECLAIM;
+  return kb_cycle(e, &a, 1, out, evicted, evict_order, nullptr, stats);
 }
 
 int kb_preempt(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
-  if (!e) return KB_E_BADARG;
-  if (!e->loaded) return fail(e, KB_E_STATE, "kb_preempt before kb_session_load");
-  return run_evict(e, true, out, evicted, evict_order, stats);
+  const uint8_t a = KB_ACT_PREEMPT;
+  return kb_cycle(e, &a, 1, out, evicted, evict_order, nullptr, stats);
 }
 
 int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {

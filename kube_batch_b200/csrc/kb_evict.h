@@ -62,7 +62,7 @@ struct EvictDev {
   const uint32_t* pt_off;        // [J+1]
   const uint32_t* task_class;    // [T]
   const uint32_t* task_present;  // [T] scalar presence of the pending task's Resreq
-  const uint32_t* job_has_pending; // unused padding keeps the layout explicit
+  const int32_t*  job_waiting0;  // [J] Pipelined tasks of the job at session open (kb_running.job_waiting0)
   // mutable
   uint8_t*  r_state;             // [n] 0 Running, 1 Releasing (evicted)
   uint32_t* pt_pos;              // [J] tasks popped from preemptorTasks[job]
@@ -108,6 +108,9 @@ KB_HD double drf_share_of(const DevSession& S, const double* alloc) {
   }
   return res;
 }
+
+// job.TaskStatusIndex[Pending] membership: a task an earlier action of the cycle placed (ssn.Allocate / ssn.Pipeline) left it
+KB_HD bool task_pending(const DevSession& S, uint32_t t) { const uint8_t k = S.dec[t].kind; return k != KB_KIND_ALLOCATED && k != KB_KIND_PIPELINED; }
 
 struct Preemptor {
   uint32_t task, job, queue, cls;
@@ -253,7 +256,7 @@ KB_HD void pipeline_apply(const DevSession& S, const EvictDev& E, const Preempto
   if (S.proportion_present) update_queue_share(S, q);
   kb_decision d;
   d.node = undo ? -1 : (int32_t)node;
-  d.kind = undo ? KB_KIND_NONE : KB_KIND_PIPELINED;
+  d.kind = undo ? (res_is_empty(R, [&](uint32_t k) { return c.resreq[k]; }) ? KB_KIND_SKIPPED : KB_KIND_NONE) : KB_KIND_PIPELINED;
   d.dispatched = 0; d.reserved = 0;
   d.step = undo ? 0xFFFFFFFFu : E.ctl->step;
   d.dispatch_step = 0xFFFFFFFFu;
@@ -374,6 +377,55 @@ struct CpuExec {
   KB_HD Preemptor& pre() { return p; }
 };
 
+// Start of an evicting action (reclaim.go:47-81, preempt.go:47-75): the action's own queues are filled from the session as it
+// is NOW — jobs in the canonical job order, Go container/heap pushes with the comparators on the current state; a job
+// enters with the tasks it still has in TaskStatusIndex[Pending].  Thread 0 only (J pushes of O(log J)).
+template <class X>
+KB_HD void evict_init(X& x, const DevSession& S, const EvictDev& E) {
+  EvictCtl& ctl = *E.ctl;
+  x.sync();
+  for (uint32_t j = (uint32_t)x.tid(); j < S.J; j += (uint32_t)x.nthreads()) {
+    int32_t w = E.job_waiting0[j];
+    uint32_t first = 0xFFFFFFFFu;
+    for (uint32_t i = E.pt_off[j]; i < E.pt_off[j + 1]; ++i) {
+      const uint32_t t = E.pt_task[i];
+      if (S.dec[t].kind == KB_KIND_PIPELINED) w += 1;                  // WaitingTaskNum (job_info.go:396-405)
+      if (first == 0xFFFFFFFFu && task_pending(S, t)) first = i - E.pt_off[j];
+    }
+    E.job_waiting[j] = w;
+    E.pt_pos[j] = first == 0xFFFFFFFFu ? E.pt_off[j + 1] - E.pt_off[j] : first;   // cursor on the first Pending task
+  }
+  x.sync();
+  if (x.tid() == 0) {
+    auto qless = [&](uint32_t l, uint32_t r) { return queue_before(S, l, r); };
+    auto jless = [&](uint32_t l, uint32_t r) { return job_before(S, l, r); };
+    ctl.qheap_len = 0; ctl.n_ops = 0; ctl.fail_valid = 0;
+    for (uint32_t q = 0; q < S.Q; ++q) { E.jheap_len[q] = 0; E.scratch[q] = 0; }    // scratch doubles as queueMap (Q <= KB_MAX_Q <= KB_EVICT_MAXV)
+    for (uint32_t j = 0; j < S.J; ++j) {
+      const uint32_t q = S.job_queue[j];
+      if (!E.scratch[q]) { E.scratch[q] = 1; heap_push(E.qheap, ctl.qheap_len, q, qless); }
+      if (E.pt_pos[j] < E.pt_off[j + 1] - E.pt_off[j]) heap_push(E.jheap + S.q_static_off[q], E.jheap_len[q], j, jless);
+    }
+  }
+  x.sync();
+}
+
+// tasks.Pop() of preemptorTasks[job] (thread 0): the next task of the job that is still Pending
+KB_HD uint32_t evict_pop_task(const DevSession& S, const EvictDev& E, uint32_t job) {
+  const uint32_t len = E.pt_off[job + 1] - E.pt_off[job];
+  while (E.pt_pos[job] < len) {
+    const uint32_t t = E.pt_task[E.pt_off[job] + E.pt_pos[job]];
+    E.pt_pos[job] += 1;
+    if (task_pending(S, t)) return t;
+  }
+  return 0xFFFFFFFFu;
+}
+KB_HD bool evict_has_task(const DevSession& S, const EvictDev& E, uint32_t job) {
+  const uint32_t len = E.pt_off[job + 1] - E.pt_off[job];
+  for (uint32_t i = E.pt_pos[job]; i < len; ++i) if (task_pending(S, E.pt_task[E.pt_off[job] + i])) return true;
+  return false;
+}
+
 // One preemptor against all nodes; returns `assigned` (uniform across the block).
 template <class X>
 KB_HD bool try_preemptor(X& x, const DevSession& S, const EvictDev& E, const uint32_t task, const uint32_t job, const uint32_t mode, const bool stmt) {
@@ -425,6 +477,7 @@ KB_HD void run_reclaim(X& x, const DevSession& S, const EvictDev& E) {
   EvictCtl& ctl = *E.ctl;
   auto qless = [&](uint32_t l, uint32_t r) { return queue_before(S, l, r); };
   auto jless = [&](uint32_t l, uint32_t r) { return job_before(S, l, r); };
+  evict_init(x, S, E);
   for (;;) {
     uint32_t task = 0xFFFFFFFFu, job = 0, q = 0, stop = 0;
     if (x.tid() == 0) {
@@ -435,9 +488,8 @@ KB_HD void run_reclaim(X& x, const DevSession& S, const EvictDev& E) {
         uint32_t* jh = E.jheap + S.q_static_off[q];
         if (E.jheap_len[q] == 0) continue;                                         // :99-101
         job = heap_pop(jh, E.jheap_len[q], jless);                                 // :102 (never pushed back)
-        if (E.pt_pos[job] >= E.pt_off[job + 1] - E.pt_off[job]) continue;          // :106-108
-        task = E.pt_task[E.pt_off[job] + E.pt_pos[job]];                           // :109
-        E.pt_pos[job] += 1;
+        task = evict_pop_task(S, E, job);                                          // :106-109
+        if (task == 0xFFFFFFFFu) continue;
         break;
       }
     }
@@ -455,12 +507,8 @@ template <class X>
 KB_HD void run_preempt(X& x, const DevSession& S, const EvictDev& E) {
   EvictCtl& ctl = *E.ctl;
   auto jless = [&](uint32_t l, uint32_t r) { return job_before(S, l, r); };
-  auto pop_task = [&](uint32_t job) -> uint32_t {               // thread 0
-    if (E.pt_pos[job] >= E.pt_off[job + 1] - E.pt_off[job]) return 0xFFFFFFFFu;
-    const uint32_t t = E.pt_task[E.pt_off[job] + E.pt_pos[job]];
-    E.pt_pos[job] += 1;
-    return t;
-  };
+  auto pop_task = [&](uint32_t job) -> uint32_t { return evict_pop_task(S, E, job); };      // thread 0
+  evict_init(x, S, E);
   for (uint32_t q = 0; q < S.Q && !ctl.error; ++q) {            // :78 `queues` is a Go map: ascending QueueID
     if (S.q_static_off[q + 1] == S.q_static_off[q]) continue;   // only queues that some job names
     uint32_t* jh = E.jheap + S.q_static_off[q];

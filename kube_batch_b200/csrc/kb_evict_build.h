@@ -1,7 +1,6 @@
 // kb_evict_build.h — CUDA-free host-side construction of the evict path's data (kb_evict.h) from kb_running + the built
 // session: Running tasks CSR by node (UID order inside a node), every job's Pending tasks in TaskOrderFn order, the job heaps
-// of the queues and reclaim's queue heap exactly as the reference's PriorityQueues are filled (reclaim.go:53-81,
-// preempt.go:54-75: jobs in the canonical job order, Go container/heap pushes with the comparators on the session-open state).
+// of the queues and reclaim's queue heap (filled by evict_init at the start of each action, like reclaim.go:53-81 / preempt.go:54-75).
 // Used by kb_engine.cu (uploads the two slabs) and by tests/emu (runs them on the CPU).
 #ifndef KB_EVICT_BUILD_H_
 #define KB_EVICT_BUILD_H_
@@ -13,7 +12,7 @@ namespace kb {
 
 struct EvictBuilt {
   Slab imm, mut;
-  struct { size_t node_off, r_orig, r_job, r_resreq, r_present, r_prio, r_ctime, r_uid_rank, r_flags, pt_task, pt_off, task_class, task_present; } oi;
+  struct { size_t node_off, r_orig, r_job, r_resreq, r_present, r_prio, r_ctime, r_uid_rank, r_flags, pt_task, pt_off, task_class, task_present, job_waiting0; } oi;
   struct { size_t r_state, pt_pos, job_waiting, jheap, jheap_len, qheap, q_alloc_present, evict_order, ops, scratch, ctl; } om;
   uint32_t n_run = 0, Tall = 0;
   EvictConf ec{};
@@ -24,7 +23,7 @@ struct EvictBuilt {
     E.r_ctime = (const int64_t*)(ib + oi.r_ctime); E.r_uid_rank = (const uint32_t*)(ib + oi.r_uid_rank); E.r_flags = (const uint32_t*)(ib + oi.r_flags);
     E.pt_task = (const uint32_t*)(ib + oi.pt_task); E.pt_off = (const uint32_t*)(ib + oi.pt_off);
     E.task_class = (const uint32_t*)(ib + oi.task_class); E.task_present = (const uint32_t*)(ib + oi.task_present);
-    E.job_has_pending = nullptr;
+    E.job_waiting0 = (const int32_t*)(ib + oi.job_waiting0);
     E.r_state = (uint8_t*)(mb + om.r_state); E.pt_pos = (uint32_t*)(mb + om.pt_pos); E.job_waiting = (int32_t*)(mb + om.job_waiting);
     E.jheap = (uint32_t*)(mb + om.jheap); E.jheap_len = (uint32_t*)(mb + om.jheap_len); E.qheap = (uint32_t*)(mb + om.qheap);
     E.q_alloc_present = (uint32_t*)(mb + om.q_alloc_present); E.evict_order = (uint32_t*)(mb + om.evict_order);
@@ -75,7 +74,7 @@ inline int build_evict(const kb_snapshot* s, const kb_running* run, const BuiltS
   EB.oi.r_resreq = imm.alloc((size_t)R * n1 * 8); EB.oi.r_present = imm.alloc(n1 * 4); EB.oi.r_prio = imm.alloc(n1 * 4);
   EB.oi.r_ctime = imm.alloc(n1 * 8); EB.oi.r_uid_rank = imm.alloc(n1 * 4); EB.oi.r_flags = imm.alloc(n1 * 4);
   EB.oi.pt_task = imm.alloc(T1 * 4); EB.oi.pt_off = imm.alloc(((size_t)J + 1) * 4);
-  EB.oi.task_class = imm.alloc(T1 * 4); EB.oi.task_present = imm.alloc(T1 * 4);
+  EB.oi.task_class = imm.alloc(T1 * 4); EB.oi.task_present = imm.alloc(T1 * 4); EB.oi.job_waiting0 = imm.alloc(J1 * 4);
   EB.om.r_state = mut.alloc(n1); EB.om.pt_pos = mut.alloc(J1 * 4); EB.om.job_waiting = mut.alloc(J1 * 4);
   EB.om.jheap = mut.alloc(J1 * 4); EB.om.jheap_len = mut.alloc(Q1 * 4); EB.om.qheap = mut.alloc(Q1 * 4);
   EB.om.q_alloc_present = mut.alloc(Q1 * 4); EB.om.evict_order = mut.alloc(n1 * 4);
@@ -102,20 +101,11 @@ inline int build_evict(const kb_snapshot* s, const kb_running* run, const BuiltS
   // ---- mutable state as the actions find it ----
   uint32_t* evo = (uint32_t*)(mb + EB.om.evict_order);
   for (uint32_t k = 0; k < n1; ++k) evo[k] = 0xFFFFFFFFu;
-  int32_t* jw = (int32_t*)(mb + EB.om.job_waiting);
-  for (uint32_t j = 0; j < J; ++j) jw[j] = (run && run->job_waiting0) ? run->job_waiting0[j] : 0;
+  int32_t* jw0 = (int32_t*)(ib + EB.oi.job_waiting0);
+  for (uint32_t j = 0; j < J; ++j) jw0[j] = (run && run->job_waiting0) ? run->job_waiting0[j] : 0;
   for (uint32_t q = 0; q < Q; ++q) ((uint32_t*)(mb + EB.om.q_alloc_present))[q] = q < B.q_alloc_present.size() ? B.q_alloc_present[q] : 0u;
-  // preemptorsMap / queues: filled in canonical job order with Go heap pushes (reclaim.go:53-81, preempt.go:54-75)
-  uint32_t* jheap = (uint32_t*)(mb + EB.om.jheap); uint32_t* jlen = (uint32_t*)(mb + EB.om.jheap_len); uint32_t* qheap = (uint32_t*)(mb + EB.om.qheap);
-  EvictCtl* ctl = (EvictCtl*)(mb + EB.om.ctl);
-  std::vector<uint8_t> seen(Q1, 0);
-  auto qless = [&](uint32_t l, uint32_t r) { return queue_before(H, l, r); };
-  auto jless = [&](uint32_t l, uint32_t r) { return job_before(H, l, r); };
-  for (uint32_t j = 0; j < J; ++j) {
-    const uint32_t q = s->job_queue[j];
-    if (!seen[q]) { seen[q] = 1; heap_push(qheap, ctl->qheap_len, q, qless); }
-    if (pt_off[j + 1] > pt_off[j]) heap_push(jheap + H.q_static_off[q], jlen[q], j, jless);
-  }
+  // the actions' own queues (preemptorsMap, queues) are filled at the start of each action, on the state it finds: evict_init
+  (void)H;
   return KB_OK;
 }
 

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
 EXPORTS = [
     "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_backfill", "kb_predicate_score",
     "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
-    "kb_nccl_unique_id", "kb_last_kernel_ms", "kb_session_load_running", "kb_reclaim", "kb_preempt",
+    "kb_nccl_unique_id", "kb_last_kernel_ms", "kb_session_load_running", "kb_reclaim", "kb_preempt", "kb_cycle",
 ]
 
 
@@ -144,6 +144,22 @@ class Engine:
     def preempt(self):
         """preemptAction.Execute (actions/preempt/preempt.go:43-270) from the loaded state -> (CycleResult, evicted, evict_order)."""
         return self._evict(self.L.kb_preempt, "kb_preempt")
+
+    ACTIONS = {"reclaim": 0, "allocate": 1, "backfill": 2, "preempt": 3}      # KB_ACT_*
+
+    def cycle(self, actions=("reclaim", "allocate", "backfill", "preempt")):
+        """One scheduling cycle on ONE session (scheduler.go:88-101): the action list from the loaded state.
+        -> (CycleResult, evicted, evict_order, bounds[n_actions][2])."""
+        T, n = self.snap.T, getattr(self, "_n_run", 0)
+        acts = np.array([self.ACTIONS[a] for a in actions], dtype=np.uint8)
+        dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+        ev = np.zeros(max(n, 1), dtype=np.uint8)
+        order = np.zeros(max(n, 1), dtype=np.uint32)
+        bounds = np.zeros((max(len(acts), 1), 2), dtype=np.uint32)
+        st = abi.kb_stats()
+        self._check(self.L.kb_cycle(self._h, _p(acts, C.c_uint8), C.c_uint32(len(acts)), dec.ctypes.data_as(C.c_void_p), _p(ev, C.c_uint8),
+                                    _p(order, C.c_uint32), _p(bounds, C.c_uint32), C.byref(st)), "kb_cycle")
+        return CycleResult(dec[:T], st), ev[:n].astype(bool), order[:n], bounds[: len(acts)]
 
     def predicate_score(self, lo: int, hi: int):
         N = self.snap.N

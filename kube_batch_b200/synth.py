@@ -231,6 +231,29 @@ def generate(spec: SynthSpec) -> Snapshot:
     return s
 
 
+def running_of(s: Snapshot, preemptable_frac: float = 0.0, seed: int = 1) -> dict:
+    """The Running tasks behind the filler jobs' aggregates, one by one (kb_running): node n carries node_pods[n] bricks of
+    1/64 of the node each (minus its terminating pod, which is Releasing, not Running).  preemptable_frac > 0 lowers MinAvailable
+    of that share of the filler jobs IN PLACE so that gang lets reclaim / preempt take some of their pods (gang.go:70-90)."""
+    Jp, n_fill = s.meta["pending_jobs"], s.meta["filler_jobs"]
+    N, R = s.N, s.R
+    rel = (s.node_releasing[0] > 0).astype(np.int64)
+    k = s.node_pods.astype(np.int64) - rel
+    node = np.repeat(np.arange(N, dtype=np.uint32), k)
+    n = int(k.sum())
+    resreq = np.zeros((R, n))
+    resreq[0] = np.repeat(s.node_allocatable[0] / 64.0, k)
+    resreq[1] = np.repeat(s.node_allocatable[1] / 64.0, k)
+    rng = np.random.Generator(np.random.PCG64(seed))
+    if preemptable_frac > 0:
+        loose = rng.random(n_fill) < preemptable_frac
+        s.job_min_avail[Jp:] = np.where(loose, np.maximum(1, s.job_ready0[Jp:] // 2), s.job_min_avail[Jp:])
+    return {"node": node, "job": (Jp + node % n_fill).astype(np.uint32), "resreq": resreq,
+            "res_present": np.full(n, 1 << 2, dtype=np.uint32), "prio": np.ones(n, dtype=np.int32),
+            "ctime": np.zeros(n, dtype=np.int64), "uid_rank": rng.permutation(n).astype(np.uint32),
+            "flags": np.zeros(n, dtype=np.uint32)}
+
+
 def make(name: str) -> Tuple[Snapshot, PluginConf]:
     spec = CONFIGS[name]
     return generate(spec), (spec.conf or config_conf(name))

@@ -705,6 +705,75 @@ int kbemu_allocate(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_t
   return rc;
 }
 
+// scheduler.go:88-101 on the emulation: the action list on ONE session (kb_cycle).  actions: 0 reclaim, 1 allocate, 2 backfill, 3 preempt.
+int kbemu_cycle(const kb_snapshot* snap, const kb_running* running, const kb_plugin_conf* conf, const uint8_t* actions, uint32_t n_actions, uint32_t mode,
+                kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats,
+                double* node_idle, double* node_releasing, double* node_used, int32_t* node_pods,
+                int64_t* node_nz_cpu, int64_t* node_nz_mem, uint64_t* node_ports,
+                double* job_share, int32_t* job_ready, double* queue_share, double* queue_deserved, double* queue_allocated) {
+  for (uint32_t i = 0; i + 1 < n_actions; ++i)
+    if (actions[i] == 3 && actions[i + 1] != 3) { g_err = "an action after preempt is outside this build (kb_cycle)"; return KB_E_UNSUPPORTED_FEATURE; }
+  Emu* E = (Emu*)kbemu_create2(snap, conf, 0, 1, mode);
+  if (!E) return KB_E_BADARG;
+  EvictBuilt EB;
+  BuildErr be;
+  if (int rc = build_evict(snap, running, E->B, E->S, EB, &be)) { g_err = be.msg; delete E; return rc; }
+  EvictDev D{};
+  EB.bind(D, EB.imm.host.data(), EB.mut.host.data());
+  CpuExec x;
+  std::vector<uint64_t> buf(kbemu_buf_u64(E));
+  const uint64_t guard = 4ull * ((uint64_t)E->B.J + E->B.To + E->B.Tb) + 1024;
+  const uint32_t J = E->B.J;
+  std::vector<int32_t> ready_start((const int32_t*)(E->B.imm.host.data() + E->B.oi.job_ready0), (const int32_t*)(E->B.imm.host.data() + E->B.oi.job_ready0) + J);
+  bool dirty = false, ready_taken = false, have_latest = false, alloc_ran = false;
+  uint32_t latest = 0;
+  auto pump = [&]() -> int {
+    while (!E->cur->ctl->done) {
+      if (E->pipe && !E->cur->backfill) emu_launch_pipe(*E);
+      else if (E->cur->overlap) emu_launch_overlap(*E);
+      else if (E->cur->kchain > 1) emu_launch_chain(*E);
+      else { emu_scan(*E, buf.data()); emu_replay(*E, buf.data()); }
+      if (E->launches > guard) { g_err = "emulated cycle did not terminate"; return KB_E_STATE; }
+    }
+    return KB_OK;
+  };
+  for (uint32_t i = 0; i < n_actions; ++i) {
+    const uint8_t a = actions[i];
+    if (a == 0 || a == 3) {
+      if (have_latest) D.ctl->step = latest;
+      if (a == 3) run_preempt(x, E->S, D); else run_reclaim(x, E->S, D);
+      if (D.ctl->error) { g_err = D.ctl->error == 2 ? "victim overflow" : "the reference would panic (Resource.Sub)"; delete E; return KB_E_STATE; }
+      latest = D.ctl->step; have_latest = true; dirty = true;
+    } else {
+      if (!ready_taken) { for (uint32_t j = 0; j < J; ++j) ready_start[j] = E->S.job_ready[j]; ready_taken = true; }
+      if (a == 1) {
+        if (dirty || have_latest) { prep_task_lists(E->S); prep_allocate(E->S, *E->S.ctl, have_latest ? latest : 0u); }
+        E->cur = &E->S;
+        if (int rc = pump()) { delete E; return rc; }
+        latest = E->S.ctl->step; alloc_ran = true;
+      } else {
+        if (dirty) { prep_backfill(E->Sbf, *E->Sbf.ctl, have_latest ? latest : 0u); E->cur = &E->Sbf; }
+        else emu_begin_backfill(*E, alloc_ran);
+        if (int rc = pump()) { delete E; return rc; }
+        latest = E->Sbf.ctl->step;
+      }
+      have_latest = true;
+    }
+  }
+  const uint32_t n = EB.n_run;
+  for (uint32_t k = 0; k < n; ++k) {
+    const uint32_t i = D.r_orig[k];
+    if (evicted) evicted[i] = D.evict_order[k] != 0xFFFFFFFFu ? 1 : 0;
+    if (evict_order) evict_order[i] = D.evict_order[k];
+  }
+  memcpy(E->B.imm.host.data() + E->B.oi.job_ready0, ready_start.data(), (size_t)J * 4);      // what the gang commit counts from
+  int rc = kbemu_finish(E, out, stats, node_idle, node_releasing, node_used, node_pods, node_nz_cpu, node_nz_mem, node_ports,
+                        job_share, job_ready, queue_share, queue_deserved, queue_allocated);
+  if (stats) { stats->evictions = D.ctl->n_evicted; stats->evict_sweeps = D.ctl->scans; stats->tasks_pipelined += D.ctl->n_pipelined; stats->tasks_processed += D.ctl->tasks_processed; }
+  delete E;
+  return rc;
+}
+
 // reclaim (action 0) / preempt (action 1) from the as-loaded state: the product's kb_evict.h run by one CPU thread
 int kbemu_evict(const kb_snapshot* snap, const kb_running* running, const kb_plugin_conf* conf, uint32_t action,
                 kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats,
@@ -727,11 +796,6 @@ int kbemu_evict(const kb_snapshot* snap, const kb_running* running, const kb_plu
     const uint32_t i = D.r_orig[k];
     if (evicted) evicted[i] = D.evict_order[k] != 0xFFFFFFFFu ? 1 : 0;
     if (evict_order) evict_order[i] = D.evict_order[k];
-  }
-  // kbemu_finish without the gang commit (no dispatch in these actions): decisions of non-reclaimers read NONE
-  for (uint32_t t = 0; t < T; ++t) {
-    kb_decision& d = E->S.dec[t];
-    if (d.kind != KB_KIND_PIPELINED) { d.node = -1; d.kind = KB_KIND_NONE; d.dispatched = 0; d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu; }
   }
   const BuiltSession& B = E->B; const DevSession& S = E->S;
   const uint32_t R = B.R, W = B.W, N = B.N, J = B.J, Q = B.Q;

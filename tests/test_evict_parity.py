@@ -139,7 +139,98 @@ def test_larger_clusters_on_the_emulation(seed):
             compare(f"big seed {seed} {tname} {action}", o, ev, order, g, gev, gorder, util.emu_states(g))
 
 
+FULL_LIST = ("reclaim", "allocate", "backfill", "preempt")            # config/kube-batch-conf.yaml:1
+ACTION_LISTS = (FULL_LIST, ("allocate", "backfill", "preempt"), ("reclaim", "allocate"), ("reclaim", "backfill", "preempt"), ("reclaim", "preempt"),
+                ("allocate", "preempt", "preempt"))
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_action_lists_on_one_session_on_the_emulation(seed):
+    """scheduler.go:88-101: the configured actions one after the other on ONE session — every action's own queues are filled from
+    what the previous ones left (job / queue order keys, tasks still Pending, Running tasks not yet evicted)."""
+    s = random_cluster(seed + 500)
+    for tname, tiers in tier_variants():
+        for acts in (ACTION_LISTS if seed % 3 == 0 else (FULL_LIST,)):
+            for mode in ((1, 5) if seed % 2 else (1,)):
+                o, ev, order = kbo.cycle(s, tiers, actions=acts, running=s.meta["running"])
+                g, gev, gorder = util.emu_cycle(s, tiers, acts, s.meta["running"], mode=mode)
+                what = f"seed {seed} {tname} {acts} mode {mode}"
+                compare(what, o, ev, order, g, gev, gorder, util.emu_states(g))
+                util.assert_same_decisions(o.decisions, g.decisions, what)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_synthetic_cluster_with_a_thousand_evictions_on_the_emulation(seed):
+    """BASELINE-shaped synthetic session (synth.py) + its Running filler pods one by one, 40 % of the filler PodGroups
+    preemptable: the shipped action list evicts ~1000 pods, pipelines ~350 and allocates ~2000 tasks — all of it must match."""
+    from kube_batch_b200 import synth
+    s = synth.random_session(seed, tasks=3000, jobs=300, nodes=600, queues=3, oversub=2.0)
+    run = synth.running_of(s, 0.4)
+    o, ev, order = kbo.cycle(s, PluginConf.default(), actions=FULL_LIST, running=run)
+    assert int(ev.sum()) > 500
+    for mode in (1, 5):
+        g, gev, gorder = util.emu_cycle(s, PluginConf.default(), FULL_LIST, run, mode=mode)
+        compare(f"synthetic {seed} mode {mode}", o, ev, order, g, gev, gorder, util.emu_states(g))
+        util.assert_same_decisions(o.decisions, g.decisions, f"synthetic {seed} mode {mode}")
+
+
+def test_an_action_after_preempt_is_refused():
+    """A discarded Statement leaves TaskInfo.NodeName behind (statement.go:153-188); a later ssn.Allocate of that task on another
+    node fails in AddTask after the status change (node_info.go:173-176) — the oracle reproduces it, the engine refuses such
+    action orders (the shipped order runs preempt last)."""
+    s = random_cluster(518)
+    with pytest.raises(RuntimeError, match="after preempt"):
+        util.emu_cycle(s, PluginConf.default(), ("preempt", "allocate", "backfill"), s.meta["running"])
+
+
+@pytest.mark.parametrize("seed", range(2))
+def test_action_list_on_a_larger_cluster_on_the_emulation(seed):
+    s = random_cluster(300 + seed, big=True)
+    o, ev, order = kbo.cycle(s, PluginConf.default(), actions=FULL_LIST, running=s.meta["running"])
+    g, gev, gorder = util.emu_cycle(s, PluginConf.default(), FULL_LIST, s.meta["running"], mode=5)
+    compare(f"big {seed}", o, ev, order, g, gev, gorder, util.emu_states(g))
+    util.assert_same_decisions(o.decisions, g.decisions, f"big {seed}")
+
+
 # ------------------------------------------------------------------------------------------------ GPU, through the C ABI
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(2))
+def test_synthetic_cluster_with_a_thousand_evictions_on_the_gpu(seed):
+    from kube_batch_b200 import engine, synth
+    s = synth.random_session(seed, tasks=3000, jobs=300, nodes=600, queues=3, oversub=2.0)
+    run = synth.running_of(s, 0.4)
+    o, ev, order = kbo.cycle(s, PluginConf.default(), actions=FULL_LIST, running=run)
+    eng = engine.Engine(0)
+    eng.load(s, PluginConf.default()).load_running(run)
+    for rep in range(2):                                                    # repeatable from the loaded state
+        res, gev, gorder, bounds = eng.cycle(FULL_LIST)
+        compare(f"gpu synthetic {seed}", o, ev, order, res, gev, gorder, (eng.node_state(), eng.order_state()))
+        util.assert_same_decisions(o.decisions, res.decisions, f"gpu synthetic {seed}")
+    eng.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(8))
+def test_action_lists_on_one_session_on_the_gpu(seed):
+    from kube_batch_b200 import engine
+    s = random_cluster(seed + 500, big=(seed % 4 == 3))
+    eng = engine.Engine(0)
+    for tname, tiers in tier_variants():
+        eng.load(s, tiers).load_running(s.meta["running"])
+        for acts in (ACTION_LISTS if seed % 2 == 0 else (FULL_LIST,)):
+            o, ev, order = kbo.cycle(s, tiers, actions=acts, running=s.meta["running"])
+            res, gev, gorder, bounds = eng.cycle(acts)
+            what = f"gpu seed {seed} {tname} {acts}"
+            compare(what, o, ev, order, res, gev, gorder, (eng.node_state(), eng.order_state()))
+            util.assert_same_decisions(o.decisions, res.decisions, what)
+            assert int(bounds[-1][1]) == int(ev.sum()) and (np.diff(bounds[:, 0].astype(np.int64)) >= 0).all()
+        # kb_allocate from the loaded state is unaffected by the cycles before it (job lists / order slots restored)
+        o1 = kbo.allocate(s, tiers)
+        r1 = eng.allocate()
+        util.assert_same_decisions(o1.decisions, r1.decisions, f"gpu seed {seed} {tname} allocate after cycles")
+    eng.close()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", list(golden_sessions()), ids=lambda c: c[0])
 def test_reference_action_tests_on_the_gpu(case):

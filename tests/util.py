@@ -91,6 +91,38 @@ def emu_evict(snap: Snapshot, conf: PluginConf, action: str, running):
     return out, ev[:n].astype(bool), order[:n]
 
 
+def emu_cycle(snap: Snapshot, conf: PluginConf, actions, running, mode: int = 1):
+    """kb_cycle on the CPU emulation: the action list on ONE session -> (OracleOut, evicted, evict_order)."""
+    L = emu_lib()
+    cs, k1 = snap.to_c()
+    cc, k2 = conf.to_c()
+    cr, k3 = abi.running_to_c(running, snap.R, snap.J)
+    R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
+    n = int(cr.n)
+    dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
+    ev = np.zeros(max(n, 1), dtype=np.uint8)
+    order = np.zeros(max(n, 1), dtype=np.uint32)
+    st = abi.kb_stats()
+    acts = np.array([kbo.ACTIONS[a] for a in actions], dtype=np.uint8)
+    out = kbo.OracleOut(
+        decisions=dec, result=st,
+        node_idle=np.zeros((R, N)), node_releasing=np.zeros((R, N)), node_used=np.zeros((R, N)),
+        node_pods=np.zeros(N, dtype=np.int32), node_nz_cpu=np.zeros(N, dtype=np.int64),
+        node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
+        job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
+        queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
+    rc = L.kbemu_cycle(C.byref(cs), C.byref(cr), C.byref(cc), _p(acts, C.c_uint8), C.c_uint32(len(acts)), C.c_uint32(mode),
+                       dec.ctypes.data_as(C.c_void_p), _p(ev, C.c_uint8), _p(order, C.c_uint32), C.byref(st),
+                       _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
+                       _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
+                       _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
+                       _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double), _p(out.queue_allocated, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"kbemu_cycle rc={rc}: {L.kbemu_last_error().decode()}")
+    out.decisions = dec[:T]
+    return out, ev[:n].astype(bool), order[:n]
+
+
 def assert_same_decisions(ref: np.ndarray, got: np.ndarray, what: str = ""):
     """Bit-exact placement parity: node, kind, dispatched, step and dispatch_step of every task."""
     assert ref.shape == got.shape, (what, ref.shape, got.shape)
