@@ -213,9 +213,9 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf,
-                bf_job_pos, bf_ctl, pipe_g, modlog, pcand; };
+                bf_job_pos, bf_ctl, pipe_g, modlog, pcand, ppref; };
 struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0,
-                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes, ord_chain; };
+                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes, ord_chain, class_pref; };
 
 struct BuiltSession {
   Slab mut, imm;
@@ -276,6 +276,9 @@ struct BuiltSession {
     D.pipe = pipe; D.pipe_S = pipe_S; D.pipe_tpc = pipe_tpc; D.pipe_pad = 0;
     D.pg = (PipeG*)(mb + om.pipe_g); D.modlog = (uint32_t*)(mb + om.modlog); D.pcand = (uint64_t*)(mb + om.pcand);
     D.dbg = nullptr;
+    D.ppref = (unsigned long long*)(mb + om.ppref);
+    D.class_pref = has_pref ? (const ClassPref*)(ib + oi.class_pref) : nullptr;
+    D.w_nodeaff = hc.w_nodeaff;
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -376,8 +379,10 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         task_class[t] = prev_class; task_empty[t] = task_empty[t - 1];
         continue;
       }
-      if ((s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY) || ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && !allow_pref))
-        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod / preferred node affinity terms: outside this build (no CPU fallback)", t);
+      if (s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY)
+        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod affinity terms: outside this build (no CPU fallback)", t);
+      if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && !allow_pref && pipe_mode <= 0)
+        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries preferred node-affinity terms: only the persistent pipeline (cycle_kernel) evaluates them", t);
       ClassPref cp = pref_of(t);
       if (cp.n) {
         if (cp.n > KB_MAX_PREF_TERMS) return bfail(e, KB_E_BADARG, "task %u: preferred node-affinity arrays missing or n_pref_terms > KB_MAX_PREF_TERMS", t);
@@ -430,7 +435,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); ClassPref cp; memset(&cp, 0, sizeof cp); class_pref.push_back(cp); }
   static_assert(sizeof(ClassPref) % 8 == 0, "ClassPref is hashed as 64-bit words");
-  if (B.has_pref && (kchain > 1 || overlap_mode > 0))
+  if (B.has_pref && !pipe_mode && (kchain > 1 || overlap_mode > 0))
     return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node affinity: only the plain launch mode is prototyped");
   if (B.has_pref) hc.cf.score_bias += 10ll * (hc.w_nodeaff < 0 ? -(int64_t)hc.w_nodeaff : 0);
   const uint32_t C = (uint32_t)classes.size();
@@ -497,16 +502,20 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   // persistent pipeline: scanner CTAs keep their tiles resident in shared memory; built for the common record geometry
   // (R = 3, W = 2: cpu, memory, one scalar; 128 label / taint / port atoms) on one GPU (or replicated on every rank)
   B.pipe = 0; B.pipe_S = 0; B.pipe_tpc = 0;
-  if (pipe_mode > 0 && world <= 1 && !B.has_pref && NT > 0 && R == 3 && W == 2 && GMAX >= 2) {
+  if (pipe_mode > 0 && world <= 1 && NT > 0 && R == 3 && W == 2 && GMAX >= 2) {
     const size_t tile_bytes = (size_t)ncols * TILE_NODES * 8;
     const uint32_t max_tpc = (uint32_t)((227 * 1024 - 8 * 1024) / tile_bytes);
     const uint32_t smax = GMAX - 1;
     const uint32_t tpc = (NT + smax - 1) / smax;
     if (tpc <= max_tpc) { B.pipe = 1; B.pipe_tpc = tpc; B.pipe_S = (NT + tpc - 1) / tpc; }
   }
+  if (B.has_pref && !B.pipe && !allow_pref)
+    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node-affinity terms need the persistent pipeline (cycle_kernel): this session's geometry "
+                 "(R = %u, W = %u, %u nodes) runs on the per-launch kernels, which do not evaluate NodeAffinityPriority", R, W, N);
   om.pipe_g = mut.alloc(sizeof(PipeG));
   om.modlog = mut.alloc(((size_t)To + 64) * 4);
   om.pcand = mut.alloc((size_t)PIPE_RING * std::max(1u, B.pipe_S) * KTOP * 8);
+  om.ppref = mut.alloc((size_t)PIPE_RING * std::max(1u, B.pipe_S) * 8);
   om.tiles = mut.alloc(std::max<size_t>(1, NT) * tile_u64 * 8);
   om.used = mut.alloc((size_t)R * std::max(1u, N) * 8);
   om.job_pos = mut.alloc((size_t)std::max(1u, J) * 4);
@@ -552,6 +561,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.bf_jobs_off = imm.alloc(2 * 4);
   oi.bf_classes = imm.alloc((size_t)(Tb ? C : 1) * sizeof(ClassRec));
   oi.ord_chain = imm.alloc((size_t)std::max(1u, To) * (KB_CHAIN_MAX - 1) * 4);
+  oi.class_pref = imm.alloc((size_t)(B.has_pref ? C : 1) * sizeof(ClassPref));
   mut.commit(); imm.commit();
 
   B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.Tb = Tb;
@@ -587,6 +597,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
 
   // ---------------- immutable job / queue / class tables ----------------
   memcpy(H.classes, classes.data(), (size_t)C * sizeof(ClassRec));
+  if (B.has_pref) memcpy(imm.host.data() + oi.class_pref, class_pref.data(), (size_t)C * sizeof(ClassPref));
   if (To) { memcpy(H.ord_task, ord_task.data(), (size_t)To * 4); memcpy(H.ord_class, ord_class.data(), (size_t)To * 4); }
   for (uint32_t j = 0; j < J; ++j)                     // run lengths, right to left inside each job
     for (uint32_t i = job_ord_off[j + 1]; i-- > job_ord_off[j];)

@@ -90,8 +90,8 @@ struct ClassRec {
 };
 
 // Preferred node-affinity terms of a class (NodeAffinityPriority, vendor/.../priorities/node_affinity.go:34-77): requirement
-// atoms that must ALL hold on the node + the term's weight.  Host-side only so far (the emulation prototypes the two-pass scan
-// that the kernels get next).
+// atoms that must ALL hold on the node + the term's weight.  Evaluated by cycle_kernel (two-pass scan, kb_pipe.cuh) and by
+// the emulation; the per-launch kernels still refuse sessions with preferred terms.
 struct ClassPref {
   uint64_t term[KB_MAX_PREF_TERMS][KB_MAX_W];
   int32_t  weight[KB_MAX_PREF_TERMS];
@@ -173,6 +173,27 @@ KB_HD int64_t balanced_score(int64_t req_cpu, int64_t cap_cpu, int64_t req_mem, 
   if (cf >= 1.0 || mf >= 1.0) return 0;
   double diff = KB_FABS(KB_DSUB(cf, mf));
   return (int64_t)KB_D2LL(KB_DMUL(KB_DSUB(1.0, diff), 10.0));
+}
+
+// NodeAffinityPriority Map (node_affinity.go:34-77): count = sum of the weights of the preferred terms whose requirement
+// atoms ALL hold on the node (weight 0 terms are skipped)
+template <class NodeAcc>
+KB_HD int32_t pref_count(const ClassPref& cp, const NodeAcc& n, uint32_t W) {
+  int32_t count = 0;
+  for (uint32_t p = 0; p < cp.n && p < KB_MAX_PREF_TERMS; ++p) {
+    if (cp.weight[p] == 0) continue;
+    bool match = true;
+    for (uint32_t w = 0; w < W; ++w) match = match && ((n.labels(w) & cp.term[p][w]) == cp.term[p][w]);
+    if (match) count += cp.weight[p];
+  }
+  return count;
+}
+// ... and its Reduce, NormalizeReduce(MaxPriority = 10, reverse = false) (reduce.go:28-63) over the FEASIBLE nodes, times the
+// nodeaffinity.weight: what the node's packed key gains.  max_count == 0: every score stays 0.
+KB_HD uint64_t add_pref_term(uint64_t key, int64_t w_nodeaff, int64_t count, int64_t max_count) {
+  if (!key || max_count <= 0) return key;
+  const int64_t hi = (int64_t)(key >> 32) + w_nodeaff * (10 * count / max_count);
+  return ((uint64_t)hi << 32) | (key & 0xFFFFFFFFull);
 }
 
 // Packed candidate key: (biased score << 32) | (0xFFFFFFFF - node).  max over keys == highest score,

@@ -72,6 +72,8 @@ struct PipeG {
   unsigned long long req[PIPE_RING][2];  // NCCL-LL style words (tag << 32 | payload): class, stamp; tag = seq + 1
   uint32_t ticket[PIPE_RING];            // scanner CTAs that delivered their list for the slot
   unsigned long long list[PIPE_RING][2 * KTOP];   // merged top-32 of a request: two LL words (low / high half) per key
+  uint32_t ticket_pref[PIPE_RING];       // scanner CTAs that delivered pass 1 (preferred node affinity) for the slot
+  unsigned long long pref[PIPE_RING][2]; // LL words of a request for a class with preferred terms: max count over the feasible nodes, nodes reaching it
 };
 
 struct DevSession {
@@ -145,6 +147,10 @@ struct DevSession {
   PipeG* pg;
   uint32_t* modlog;       // [To + 64] node ids in modification order (one entry per node a visit chain modified)
   uint64_t* pcand;        // [PIPE_RING][pipe_S][KTOP] per-CTA candidate lists of the requests in flight
+  unsigned long long* ppref;   // [PIPE_RING][pipe_S] pass 1 of a scan for a class with preferred node-affinity terms: (max count << 32 | nodes reaching it) per CTA
+  const ClassPref* class_pref; // [C] preferred terms of the classes, NULL when the session has none
+  int32_t w_nodeaff;           // nodeaffinity.weight (nodeorder.go:111-117)
+  uint32_t pad_pref;
   uint32_t* dbg;          // 64 progress words in mapped host memory (KB_PIPE_DEBUG=1; NULL otherwise): read by the host watchdog when a cycle hangs
 };
 constexpr uint32_t KB_MAX_WORLD = 8;

@@ -149,7 +149,9 @@ __device__ __forceinline__ void warp_merge_top32_kv(uint64_t& a, uint32_t& ap, u
 // ---------------------------------------------------------------------------------------------
 struct ScanGroup {
   ClassRec cls;
+  ClassPref pref;                        // preferred node-affinity terms of the class (a12), n == 0: none
   uint32_t cls_id, stamp, quit, is_last;
+  uint32_t pmax, pnmax, wmax[4], wn[4];  // pass 1: max count over the feasible nodes, nodes reaching it
   uint64_t wl[4][KTOP];
 };
 struct ScanSmem {
@@ -241,6 +243,11 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&G.cls);
       for (uint32_t i = gt; i < sizeof(ClassRec) / 4; i += 128) dst[i] = src[i];
+      if (S.class_pref) {
+        const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[cls_id]);
+        uint32_t* pd = reinterpret_cast<uint32_t*>(&G.pref);
+        for (uint32_t i = gt; i < sizeof(ClassPref) / 4; i += 128) pd[i] = ps[i];
+      } else if (gt == 0) G.pref.n = 0;
     }
     {
       // the resident tiles must reflect every log entry below the request's stamp (entries at or above it are the replayer's patch)
@@ -252,6 +259,51 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
       __threadfence_block();
     }
     bar_sync(bar_id, 128);
+    // NodeAffinityPriority (a12): NormalizeReduce needs the max count over the FEASIBLE nodes of the whole table before a
+    // single key can be built -> pass 1 over the resident tiles, one exchange between the scanner CTAs, then the keys
+    const bool is_pref = S.cf.nodeorder && G.pref.n != 0;
+    int64_t pmax = 0;
+    if (is_pref) {
+      uint32_t mymax = 0, myn = 0;
+      for (uint32_t i = 0; i < ntl; ++i) {
+        const uint32_t node = (t0 + i) * TILE_NODES + gt;
+        if (node >= S.N) continue;
+        ColAcc acc{tiles + (size_t)i * tile_u64, (uint32_t)gt, TILE_NODES, R, W};
+        if (!eval_pair<RR, WW>(S.cf, G.cls, acc, node, nullptr)) continue;
+        const uint32_t cnt = (uint32_t)pref_count(G.pref, acc, W);
+        if (cnt > mymax) { mymax = cnt; myn = 1; } else if (cnt == mymax) myn += 1;
+      }
+      const uint32_t wm = __reduce_max_sync(FULL, mymax);
+      const uint32_t wnn = __reduce_add_sync(FULL, mymax == wm ? myn : 0u);
+      if (lane == 0) { G.wmax[wg] = wm; G.wn[wg] = wnn; }
+      bar_sync(bar_id, 128);
+      if (wg == 0) {
+        uint32_t gm = 0, gn = 0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) { if (G.wmax[w] > gm) { gm = G.wmax[w]; gn = G.wn[w]; } else if (G.wmax[w] == gm) gn += G.wn[w]; }
+        if (lane == 0) {
+          st_relaxed_u64(&S.ppref[(size_t)slot * nS + cta], ((unsigned long long)gm << 32) | gn);
+          __threadfence();
+          atomicAdd(&pg->ticket_pref[slot], 1u);
+        }
+        const long long deadline = clock64() + PIPE_DEADLINE;
+        while (ld_acquire_u32(&pg->ticket_pref[slot]) < nS) {
+          if (clock64() > deadline) { pg->error = 3; st_release_u32(&pg->quit, 1u); break; }
+          __nanosleep(32);
+        }
+        uint32_t am = 0, an = 0;
+        for (uint32_t c2 = (uint32_t)lane; c2 < nS; c2 += 32) {
+          const unsigned long long v = __ldcg(&S.ppref[(size_t)slot * nS + c2]);
+          const uint32_t m2 = (uint32_t)(v >> 32), n2 = (uint32_t)v;
+          if (m2 > am) { am = m2; an = n2; } else if (m2 == am) an += n2;
+        }
+        const uint32_t tm = __reduce_max_sync(FULL, am);
+        const uint32_t tn = __reduce_add_sync(FULL, am == tm ? an : 0u);
+        if (lane == 0) { G.pmax = tm; G.pnmax = tn; }
+      }
+      bar_sync(bar_id, 128);
+      pmax = (int64_t)G.pmax;
+    }
     uint64_t mylist = 0;
     for (uint32_t i = 0; i < ntl; ++i) {
       const uint32_t node = (t0 + i) * TILE_NODES + gt;
@@ -259,6 +311,7 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
       if (node < S.N) {
         ColAcc acc{tiles + (size_t)i * tile_u64, (uint32_t)gt, TILE_NODES, R, W};
         key = eval_pair<RR, WW>(S.cf, G.cls, acc, node, nullptr);
+        if (is_pref && key) key = add_pref_term(key, (int64_t)S.w_nodeaff, (int64_t)pref_count(G.pref, acc, W), pmax);
       }
       const uint64_t thr = __shfl_sync(FULL, mylist, 31);
       if (__any_sync(FULL, key > thr)) {
@@ -295,7 +348,14 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
       if (wg == 0) {
 #pragma unroll
         for (int w = 1; w < 4; ++w) acc = warp_merge_top32(acc, G.wl[w][lane], lane);
-        if (lane == 0) pg->ticket[slot] = 0;
+        if (lane == 0) {
+          pg->ticket[slot] = 0;
+          if (is_pref) {      // every CTA has left pass 1 (it delivered its list): the slot's pass-1 counter can be recycled
+            pg->ticket_pref[slot] = 0;
+            st_relaxed_u64(&pg->pref[slot][0], ((unsigned long long)tag << 32) | G.pmax);
+            st_relaxed_u64(&pg->pref[slot][1], ((unsigned long long)tag << 32) | G.pnmax);
+          }
+        }
         __threadfence();
         st_relaxed_u64(&pg->list[slot][2 * lane], ((unsigned long long)tag << 32) | (acc & 0xFFFFFFFFull));
         st_relaxed_u64(&pg->list[slot][2 * lane + 1], ((unsigned long long)tag << 32) | (acc >> 32));
@@ -320,6 +380,11 @@ struct PrepBuf {
   uint64_t key[PIPE_DEPTH][KTOP];              // key of entry l after d more placements of the class
   uint32_t fi[PIPE_DEPTH];                     // fits-idle ballots of the same states
   uint64_t rec[NC][KTOP];                      // entry l's record (state at depth 0)
+  // NodeAffinityPriority (a12): the class's preferred terms, the request's normalisation (max count over the feasible
+  // nodes at the stamp, nodes reaching it) and entry l's own count.  Lists of such classes are only used fresh.
+  ClassPref pref;
+  uint32_t is_pref, pmax, pnmax, pad_pref;
+  int32_t cnt[KTOP];
 };
 
 template <int NC>
@@ -411,6 +476,11 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[sm.rq_cls[idx]]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&P.cls);
         for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = __ldg(src + i);
+        if (S.class_pref) {
+          const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[sm.rq_cls[idx]]);
+          uint32_t* pd = reinterpret_cast<uint32_t*>(&P.pref);
+          for (uint32_t i = lane; i < sizeof(ClassPref) / 4; i += 32) pd[i] = __ldg(ps + i);
+        } else if (lane == 0) P.pref.n = 0;
         // the request's list: lane l polls its own two LL words (payload + tag in one 8-byte word each)
         const long long deadline = clock64() + PIPE_DEADLINE;
         for (;;) {
@@ -424,7 +494,22 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
         }
       }
       P.list[lane] = status ? 0ull : ((w0 & 0xFFFFFFFFull) | (w1 << 32));
-      if (lane == 0) { sm.prep_status[team] = status; if (status == 2) sm.v_err = 1; }
+      __syncwarp();
+      if (lane == 0) {
+        const bool isp = !status && S.cf.nodeorder && P.pref.n != 0;
+        P.is_pref = isp ? 1u : 0u; P.pmax = 0; P.pnmax = 0;
+        if (isp) {          // written before the list words (fence in between): present once the list is
+          unsigned long long a = 0, b = 0;
+          const long long deadline = clock64() + PIPE_DEADLINE;
+          for (;;) {
+            ld_relaxed_2u64(&pg->pref[slot][0], a, b);
+            if ((uint32_t)(a >> 32) == tag && (uint32_t)(b >> 32) == tag) break;
+            if (clock64() > deadline) { status = 2; break; }
+          }
+          P.pmax = (uint32_t)a; P.pnmax = (uint32_t)b;
+        }
+        sm.prep_status[team] = status; if (status == 2) sm.v_err = 1;
+      }
       __threadfence_block();
     }
     if (w == 0 && lane == 0) dbg_put(S.dbg, 8 + team, (seq << 4) | 1u);
@@ -441,9 +526,13 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
 #pragma unroll
       for (uint32_t c = 0; c < NC; ++c) rec[c] = __ldcg(g + (size_t)c * TILE_NODES);
     }
+    const bool is_pref = P.is_pref != 0;
+    int32_t pcnt = 0;
+    if (is_pref && have) { RegAcc a0{rec, R, W}; pcnt = pref_count(P.pref, a0, W); }      // labels do not change with placements
     if (w == 0) {
 #pragma unroll
       for (uint32_t c = 0; c < NC; ++c) P.rec[c][lane] = rec[c];
+      P.cnt[lane] = pcnt;
     }
     for (int k = 0; k < w; ++k) advance_rec<RR, WW>(rec, P.cls);
 #pragma unroll 1
@@ -453,6 +542,7 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
       if (have) {
         RegAcc acc{rec, R, W};
         key = eval_pair<RR, WW>(S.cf, P.cls, acc, node, &fi);
+        if (is_pref) key = add_pref_term(key, (int64_t)S.w_nodeaff, (int64_t)pcnt, (int64_t)P.pmax);
       }
       P.key[d][lane] = key;
       const unsigned fim = __ballot_sync(FULL, have && fi);
@@ -654,8 +744,11 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     if (lane == 0) { *((volatile uint32_t*)&sm.v_count) = sm.v_count + 1; dbg_put(S.dbg, 0, sm.v_count); dbg_put(S.dbg, 1, 1u); dbg_put(S.dbg, 2, cls_id); }       // wakes the shadow warp
     // ---------------- visit start: which list ----------------
     uint32_t seq = 0, stamp = 0;
+    // a class with preferred node-affinity terms: its keys are normalised by the max count over the nodes feasible AT THE STAMP,
+    // so only a list of the current table state will do (the replay then tracks the feasible max-count nodes itself)
+    const bool pref_cls = S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[cls_id].n != 0;
     bool usable = rq_lookup(cls_id, seq, stamp);
-    usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor;
+    usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor && (!pref_cls || stamp == priv_head);
     if (!usable) { seq = post_request(cls_id); stamp = priv_head; if (lane == 0) c.pipe_urgent += 1; }
     fresh_floor = 0;
     const uint32_t pbi = seq % PIPE_RQ;
@@ -754,7 +847,8 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       for (uint32_t k = 0; k < target; ++k) advance_rec<RR, WW>(r2, P.cls);
       RegAcc acc{r2, R, W};
       bool f = false;
-      const uint64_t k2 = eval_pair<RR, WW>(S.cf, P.cls, acc, onode, &f);
+      uint64_t k2 = eval_pair<RR, WW>(S.cf, P.cls, acc, onode, &f);
+      if (P.is_pref) k2 = add_pref_term(k2, (int64_t)S.w_nodeaff, (int64_t)pref_count(P.pref, acc, W), (int64_t)P.pmax);
       __syncwarp();
       sm.ext_key[lane] = k2;
       const unsigned fm = __ballot_sync(FULL, f);
@@ -763,10 +857,15 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     };
     if (lane == 0) sm.ext_slot = 0xFFFFFFFFu;
     __syncwarp();
+    // a12 countdown: feasible nodes that reach the max count; when the last one fills up every key of this list is stale
+    const bool is_pref = P.is_pref != 0 && P.pmax > 0;
+    const int32_t my_cnt = (is_pref && have && my_h == 0) ? P.cnt[my_l] : -1;
+    uint32_t nmax_live = P.pnmax;
+    bool pref_stale = false;
 
     bool rescanned = false;
     for (;;) {              // runs of this class (consecutive visits of one class share the pool)
-      if (c.done || c.cur_class != cls_id) break;
+      if (c.done || c.cur_class != cls_id || pref_stale) break;
       const uint32_t j = (uint32_t)c.cur_job;
       const uint32_t q = c.cur_queue;
       const uint32_t jend = S.job_ord_off[j + 1];
@@ -799,10 +898,12 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         const unsigned ownbits = __shfl_sync(FULL, (chain_has(depth + 1) ? 1u : 0u) | (cur_fi ? 2u : 0u), owner);
         if (!(ownbits & 1u)) extend(owner);
         const bool fits_idle = (ownbits & 2u) != 0;
+        bool left_max = false;
         if ((uint32_t)lane == owner) {             // ssn.Allocate / ssn.Pipeline: my candidate moves to its next state
           depth += 1;
           cur_key = chain_key(depth);
           cur_fi = chain_fi(depth);
+          left_max = is_pref && cur_key == 0 && my_cnt == (int32_t)P.pmax;      // a max-count node left the feasible set
         }
         jalloc = KB_DADD(jalloc, my_rq);
         qalloc = KB_DADD(qalloc, my_rq);
@@ -817,8 +918,10 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         }
         placed += 1;
         n_alloc += fits_idle ? 1u : 0u;
+        if (is_pref && __any_sync(FULL, left_max)) { nmax_live -= 1; pref_stale = nmax_live == 0; }
         const bool jr = !S.gang_ready || (ready + (int32_t)n_alloc) >= min_avail;     // ssn.JobReady
         if (jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }                   // allocate.go:185-188
+        if (pref_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
       }
       if (lane == 0) {
         S.job_pos[j] = pos0 + popped;
@@ -900,6 +1003,13 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         const uint32_t pcls = pc[k];
         if (pcls == 0xFFFFFFFFu) continue;
         if (k == 0 && rescanned) continue;                      // the visit start posts the fresh request itself
+        if (S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[pcls].n != 0) {
+          // preferred terms: only a list of the table state at its use will do — request the next visit's now, nothing further ahead
+          if (k != 0) continue;
+          uint32_t s3 = 0, st3 = 0;
+          if (!(rq_lookup(pcls, s3, st3) && st3 == priv_head)) post_request(pcls);
+          continue;
+        }
         uint32_t s2 = 0, st2 = 0;
         const bool f = rq_lookup(pcls, s2, st2);
         const uint32_t age = priv_head - st2;

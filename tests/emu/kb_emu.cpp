@@ -63,25 +63,11 @@ struct Emu {
   uint32_t next() { rng = rng * 6364136223846793005ull + 1442695040888963407ull; return (uint32_t)(rng >> 33); }
 };
 
-// NodeAffinityPriority of one (class, node): count = sum of the weights of the matching preferred terms (weight 0 skipped)
-template <class Acc>
-int64_t pref_count(const ClassPref& cp, const Acc& acc, uint32_t W) {
-  int64_t count = 0;
-  for (uint32_t p = 0; p < cp.n; ++p) {
-    if (cp.weight[p] == 0) continue;
-    bool match = true;
-    for (uint32_t w = 0; w < W; ++w) if ((acc.labels(w) & cp.term[p][w]) != cp.term[p][w]) { match = false; break; }
-    if (match) count += cp.weight[p];
-  }
-  return count;
-}
 struct PrefCtx { const ClassPref* cp; int64_t w_nodeaff; int64_t max; uint32_t* nmax; };
-// key of a feasible node with the NormalizeReduce(10) term added to the (biased) score half
+// key of a feasible node with the NormalizeReduce(10) term added to the (biased) score half (kb_core.h add_pref_term)
 inline uint64_t add_pref_term(uint64_t key, const PrefCtx* pc, int64_t count) {
-  if (!key || !pc || pc->max <= 0) return key;
-  const int64_t term = pc->w_nodeaff * (10 * count / pc->max);
-  const int64_t hi = (int64_t)(key >> 32) + term;
-  return ((uint64_t)hi << 32) | (key & 0xFFFFFFFFull);
+  if (!pc) return key;
+  return kb::add_pref_term(key, pc->w_nodeaff, count, pc->max);
 }
 
 // visit_kernel, scan + merge + (sharded) pack: keys[32] then columns [ncols][32]
@@ -457,7 +443,9 @@ void emu_launch_pipe(Emu& E) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t head = (uint32_t)E.log_node.size();
   if (E.view.empty()) { E.view.assign(S.tiles, S.tiles + (size_t)std::max(1u, S.NT) * tile_u64); E.view_pos = head; }
-  uint32_t lag = E.need_fresh ? 0u : E.next() % (PIPE_PATCH + 1);
+  // a12: a class with preferred node-affinity terms only ever uses a list of the CURRENT table state (kb_pipe.cuh)
+  const ClassPref* cp = (E.B.has_pref && S.cf.nodeorder && E.B.class_pref[cls_id].n) ? &E.B.class_pref[cls_id] : nullptr;
+  uint32_t lag = (E.need_fresh || cp) ? 0u : E.next() % (PIPE_PATCH + 1);
   if (E.next() % 4 == 0) lag = 0;
   uint32_t stamp = head > lag ? head - lag : 0;
   if (stamp < E.view_pos) stamp = E.view_pos;                  // the applier never goes back
@@ -471,6 +459,17 @@ void emu_launch_pipe(Emu& E) {
   std::vector<uint32_t> inflight;                              // distinct nodes of log[stamp, head)
   for (uint32_t i = stamp; i < head; ++i) if (std::find(inflight.begin(), inflight.end(), E.log_node[i]) == inflight.end()) inflight.push_back(E.log_node[i]);
   // ---- scanners ----
+  // pass 1 (preferred terms): max count over the feasible nodes, nodes reaching it
+  E.pref_max = 0; E.pref_nmax = 0;
+  if (cp)
+    for (uint32_t n = 0; n < S.N; ++n) {
+      TileAcc acc{E.view.data() + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+      if (!eval_pair(S.cf, cls, acc, n, nullptr)) continue;
+      const int64_t cnt = pref_count(*cp, acc, W);
+      if (cnt > E.pref_max) { E.pref_max = cnt; E.pref_nmax = 1; }
+      else if (cnt == E.pref_max) E.pref_nmax += 1;
+    }
+  PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &E.pref_nmax};
   std::vector<uint64_t> keys;
   for (uint32_t n = 0; n < S.N; ++n) {
     uint64_t k;
@@ -483,6 +482,7 @@ void emu_launch_pipe(Emu& E) {
     } else {
       TileAcc acc{E.view.data() + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
       k = eval_pair(S.cf, cls, acc, n, nullptr);
+      if (k && cp) k = add_pref_term(k, &pc, pref_count(*cp, acc, W));
     }
     if (k) keys.push_back(k);
   }
@@ -510,8 +510,9 @@ void emu_launch_pipe(Emu& E) {
     for (uint32_t cc = 0; cc < ncols; ++cc) cd.st[0].col[cc] = gt[(size_t)cc * TILE_NODES];
     SlotAcc acc{&cd.st[0], R, W};
     cd.cur_fi = res_less_equal(R, [&](uint32_t k) { return cls.initreq[k]; }, [&](uint32_t k) { return acc.idle(k); });
+    if (cp) cd.pref = pref_count(*cp, acc, W);
   }
-  E.need_fresh = replay_core(S, c, cls_id, cand, fl);
+  E.need_fresh = replay_core(S, c, cls_id, cand, fl, cp ? &pc : nullptr);
   write_back(S, cls, cand);
   for (auto& cd : cand) {
     if (!cd.modified) continue;

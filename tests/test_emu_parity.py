@@ -366,15 +366,18 @@ def test_phantom_corner_random_clusters(seed):
 
 
 # ---------------- a12 NodeAffinityPriority: prototype of the engine algorithm (emulation only; the kernels follow next round) ----------------
-def _pref_cluster(seed):
+def _pref_cluster(seed, pipe_geometry=False, nodes=None):
+    """pipe_geometry: R = 3 (one scalar resource) and W = 2 atom words — the record geometry cycle_kernel is built for."""
     rng = np.random.default_rng(seed)
     b = B.SessionBuilder()
     b.add_queue(B.Queue("q", 1))
-    nn = int(rng.integers(2, 7))
+    nn = int(rng.integers(2, 7)) if nodes is None else nodes
     zones = ["a", "b", "c"]
     for n in range(nn):
-        b.add_node(B.Node(f"n{n}", {"cpu": float(rng.choice([2, 4, 8])), "memory": 64e9, "pods": int(rng.choice([3, 6, 110]))},
-                          labels={"zone": zones[n % 3], "rank": str(n)}))
+        alloc = {"cpu": float(rng.choice([2, 4, 8])), "memory": 64e9, "pods": int(rng.choice([3, 6, 110]))}
+        if pipe_geometry:
+            alloc["nvidia.com/gpu"] = 4
+        b.add_node(B.Node(f"n{n:03d}", alloc, labels={"zone": zones[n % 3], "rank": str(n)}))
     for g in range(int(rng.integers(1, 4))):
         b.add_pod_group(B.PodGroup("ns", f"g{g}", "q", min_member=int(rng.integers(0, 3))))
         pref = [(int(rng.choice([0, 1, 20, 50, 100])), [("zone", "In", [str(rng.choice(zones))])]) for _ in range(int(rng.integers(1, 4)))]
@@ -382,7 +385,7 @@ def _pref_cluster(seed):
         for k in range(int(rng.integers(3, 14))):
             b.add_pod(B.Pod("ns", f"g{g}-p{k:02d}", "", "Pending", {"cpu": cpu, "memory": 1e9}, group=f"g{g}", creation=k,
                             preferred_terms=pref if rng.random() < 0.9 else []))
-    return b.flatten()
+    return b.flatten(W=2 if pipe_geometry else 1)
 
 
 @pytest.mark.parametrize("seed", range(40))
@@ -399,6 +402,24 @@ def test_preferred_node_affinity_two_pass_scan_prototype(seed):
         o, e = check(s, conf, f"pref seed{seed}", mode=1)
         rescans += e.result.rescans
     assert rescans >= 0
+
+
+PREF_CONFS = (PluginConf.default(),
+              PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "5"}}),
+              PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "-3"}}),
+              PluginConf.from_names([["gang", "priority"], ["predicates"]]))
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_preferred_node_affinity_in_the_pipeline_protocol(seed):
+    """cycle_kernel's treatment (emulated): a class with preferred terms only ever uses a list of the current table state;
+    the scanners run pass 1 (max count over the feasible nodes), exchange, then build the keys; the replayer counts the
+    feasible max-count nodes down."""
+    s = _pref_cluster(6100 + seed, pipe_geometry=True, nodes=(None if seed % 4 else 150))
+    assert s.R == 3 and s.W == 2
+    for conf in PREF_CONFS:
+        check(s, conf, f"pref pipe seed{seed}", mode=5)
+        check(s, conf, f"pref pipe seed{seed} plain", mode=1)
 
 
 def test_preferred_node_affinity_normalisation_goes_stale_exactly_when_the_last_max_node_fills():

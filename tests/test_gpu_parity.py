@@ -192,6 +192,26 @@ def test_unknown_plugin_and_unsupported_feature_fail_loudly(eng):
     assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
 
 
+# ---------------- a12 NodeAffinityPriority (node_affinity.go:34-77 + reduce.go:28-63) in cycle_kernel ----------------
+@pytest.mark.parametrize("seed", range(12))
+def test_preferred_node_affinity_on_the_gpu(eng, seed):
+    """Preferred node-affinity terms: the scanner CTAs find the max count over the feasible nodes (pass 1 + one exchange between
+    the CTAs), build the keys with weight * (10 * count / max), and the replayer counts the feasible max-count nodes down."""
+    from test_emu_parity import _pref_cluster, PREF_CONFS
+    s = _pref_cluster(6100 + seed, pipe_geometry=True, nodes=(None if seed % 3 else 400))
+    for conf in PREF_CONFS:
+        run_and_check(eng, s, conf, f"pref seed{seed}")
+
+
+def test_preferred_node_affinity_outside_the_pipeline_geometry_is_refused(eng):
+    from test_emu_parity import _pref_cluster
+    s = _pref_cluster(6000)                       # R = 2, W = 1: the per-launch kernels would run it, and they have no a12
+    assert s.R == 2
+    with pytest.raises(engine.KbError) as ei:
+        eng.load(s, PluginConf.default())
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+
+
 # ---------------- kb_backfill (actions/backfill/backfill.go:40-71) ----------------
 def run_backfill_and_check(eng, snap, conf, what, actions):
     o = kbo.allocate(snap, conf, actions=actions)
