@@ -28,7 +28,7 @@
 #include "kb_evict_build.h"
 #include "kb_kernels.cuh"
 #include "kb_pipe.cuh"
-#include "kb_evict.cuh"
+#include "kb_evict_launch.h"
 
 using namespace kb;
 
@@ -415,9 +415,10 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   if (e->dev.pipe) {
     const size_t scan_b = pipe_scan_header() + (size_t)e->dev.pipe_tpc * e->tile_smem;
     e->pipe_smem = std::max(scan_b, sizeof(ReplaySmem<18>));
-    CUDA_TRY(e, cudaFuncSetAttribute(cycle_kernel<3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pipe_smem));
+    CUDA_TRY(e, cudaFuncSetAttribute(cycle_kernel<3, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pipe_smem));
+    CUDA_TRY(e, cudaFuncSetAttribute(cycle_kernel<3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->pipe_smem));
     int occ = 0;
-    CUDA_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cycle_kernel<3, 2>, PIPE_THREADS, e->pipe_smem));
+    CUDA_TRY(e, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, cycle_kernel<3, 2, 1>, PIPE_THREADS, e->pipe_smem));
     if (occ < 1 || (int)e->dev.pipe_S + 1 > e->sm_count * occ)
       return fail(e, KB_E_CUDA, "cycle_kernel: %u CTAs cannot be co-resident (occupancy %d x %d SMs)", e->dev.pipe_S + 1, occ, e->sm_count);
   }
@@ -507,7 +508,8 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       dv.dbg = e->d_dbg;
       if (e->h_dbg) memset(e->h_dbg, 0, 64 * 4);
       void* args[] = {(void*)&dv};
-      CUDA_TRY(e, cudaLaunchCooperativeKernel((const void*)cycle_kernel<3, 2>, dim3(D.pipe_S + 1), dim3(PIPE_THREADS), args, e->pipe_smem, e->stream));
+      const void* kfn = D.class_pref ? (const void*)cycle_kernel<3, 2, 1> : (const void*)cycle_kernel<3, 2, 0>;
+      CUDA_TRY(e, cudaLaunchCooperativeKernel(kfn, dim3(D.pipe_S + 1), dim3(PIPE_THREADS), args, e->pipe_smem, e->stream));
       launches += 1;
     } else if (use_graph) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
@@ -723,9 +725,7 @@ int kb_cycle(kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decisi
     const uint8_t a = actions[i];
     if (a == KB_ACT_RECLAIM || a == KB_ACT_PREEMPT) {
       if (latest && latest != step_ev) carry_u32_kernel<<<1, 1, 0, e->stream>>>(latest, step_ev);
-      if (a == KB_ACT_PREEMPT) evict_kernel<1><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
-      else evict_kernel<0><<<1, EVICT_THREADS, 0, e->stream>>>(e->dev, e->ev);
-      CUDA_TRY(e, cudaGetLastError());
+      CUDA_TRY(e, launch_evict(a == KB_ACT_PREEMPT, e->dev, e->ev, e->coop_ok ? e->sm_count : 1, e->stream));
       launches += 1;
       latest = step_ev; dirty = true;
     } else {

@@ -29,6 +29,12 @@ struct EvictConf {
   uint32_t task_order_priority;
 };
 
+struct Preemptor {
+  uint32_t task, job, queue, cls;
+  uint32_t mode;           // 0 reclaim: Running tasks of OTHER queues; 1 preempt between jobs: same queue, other job; 2 preempt in job
+  double ls;               // drf: share of the preemptor's job with the preemptor added (drf.go:87-89)
+};
+
 struct EvictCtl {
   uint32_t error;              // 1: the reference would panic (Resource.Sub on insufficient resource), 2: victim overflow
   uint32_t step;               // next Pipeline sequence number
@@ -41,6 +47,12 @@ struct EvictCtl {
   uint32_t qheap_len;
   uint32_t fail_valid, fail_cls, fail_mode, fail_key, fail_version;   // the last sweep that found no node
   unsigned long long pairs_logical;
+  // device plumbing of the multi-CTA kernel (kb_evict_kernels.cu): grid barrier, broadcast slot, arg-max slot, the
+  // preemptor being swept and its class (written by thread 0 of the grid, read by every CTA after a barrier)
+  uint32_t bar_count, bar_gen, bc, pad0;
+  unsigned long long red;
+  Preemptor pre;
+  ClassRec cls;
 };
 
 // Device view of the evict path's own data (everything else — node tiles, job / queue accounting, classes — is the
@@ -111,12 +123,6 @@ KB_HD double drf_share_of(const DevSession& S, const double* alloc) {
 
 // job.TaskStatusIndex[Pending] membership: a task an earlier action of the cycle placed (ssn.Allocate / ssn.Pipeline) left it
 KB_HD bool task_pending(const DevSession& S, uint32_t t) { const uint8_t k = S.dec[t].kind; return k != KB_KIND_ALLOCATED && k != KB_KIND_PIPELINED; }
-
-struct Preemptor {
-  uint32_t task, job, queue, cls;
-  uint32_t mode;           // 0 reclaim: Running tasks of OTHER queues; 1 preempt between jobs: same queue, other job; 2 preempt in job
-  double ls;               // drf: share of the preemptor's job with the preemptor added (drf.go:87-89)
-};
 
 KB_HD bool evict_candidate(const DevSession& S, const EvictDev& E, const Preemptor& P, uint32_t slot) {
   if (E.r_state[slot] != 0) return false;                       // "Ignore non running task" (reclaim.go:127, preempt.go:105)
@@ -373,6 +379,7 @@ struct CpuExec {
   KB_HD void sync() {}
   KB_HD uint32_t bcast(uint32_t v) { return v; }
   KB_HD uint64_t block_max(uint64_t v) { return v; }
+  KB_HD void clear_max() {}
   KB_HD ClassRec& cls() { return c; }
   KB_HD Preemptor& pre() { return p; }
 };
@@ -443,6 +450,7 @@ KB_HD bool try_preemptor(X& x, const DevSession& S, const EvictDev& E, const uin
     }
     ctl.tasks_processed += 1;
     ctl.pairs_logical += (unsigned long long)S.N;
+    x.clear_max();
   }
   x.sync();
   const Preemptor& P = x.pre();

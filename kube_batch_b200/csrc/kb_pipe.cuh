@@ -163,7 +163,7 @@ struct ScanSmem {
 };
 __host__ __device__ constexpr size_t pipe_scan_header() { return ((sizeof(ScanSmem) + 127) / 128) * 128; }
 
-template <int RR, int WW>
+template <int RR, int WW, int PREF>
 __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char* smem_raw) {
   constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
   ScanSmem& sm = *reinterpret_cast<ScanSmem*>(smem_raw);
@@ -243,7 +243,7 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
       const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
       uint32_t* dst = reinterpret_cast<uint32_t*>(&G.cls);
       for (uint32_t i = gt; i < sizeof(ClassRec) / 4; i += 128) dst[i] = src[i];
-      if (S.class_pref) {
+      if (PREF && S.class_pref) {
         const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[cls_id]);
         uint32_t* pd = reinterpret_cast<uint32_t*>(&G.pref);
         for (uint32_t i = gt; i < sizeof(ClassPref) / 4; i += 128) pd[i] = ps[i];
@@ -261,7 +261,7 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
     bar_sync(bar_id, 128);
     // NodeAffinityPriority (a12): NormalizeReduce needs the max count over the FEASIBLE nodes of the whole table before a
     // single key can be built -> pass 1 over the resident tiles, one exchange between the scanner CTAs, then the keys
-    const bool is_pref = S.cf.nodeorder && G.pref.n != 0;
+    const bool is_pref = PREF && S.cf.nodeorder && G.pref.n != 0;
     int64_t pmax = 0;
     if (is_pref) {
       uint32_t mymax = 0, myn = 0;
@@ -451,7 +451,7 @@ __device__ __forceinline__ void pipe_patch_warp(const DevSession& S, ReplaySmem<
 
 // prep team (PIPE_PREP_TW warps): requests seq = team, team + PIPE_PREP_TEAMS, ...  Waits for the scanners' answer, gathers the
 // 32 records, evaluates the depth chain (warp w: depths w, w + TW, ...) and publishes pb[seq % PIPE_RQ].
-template <int RR, int WW>
+template <int RR, int WW, int PREF>
 __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int team, const int w, const int lane) {
   constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
   PipeG* pg = S.pg;
@@ -476,7 +476,7 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
         const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[sm.rq_cls[idx]]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&P.cls);
         for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = __ldg(src + i);
-        if (S.class_pref) {
+        if (PREF && S.class_pref) {
           const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[sm.rq_cls[idx]]);
           uint32_t* pd = reinterpret_cast<uint32_t*>(&P.pref);
           for (uint32_t i = lane; i < sizeof(ClassPref) / 4; i += 32) pd[i] = __ldg(ps + i);
@@ -496,7 +496,7 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
       P.list[lane] = status ? 0ull : ((w0 & 0xFFFFFFFFull) | (w1 << 32));
       __syncwarp();
       if (lane == 0) {
-        const bool isp = !status && S.cf.nodeorder && P.pref.n != 0;
+        const bool isp = PREF && !status && S.cf.nodeorder && P.pref.n != 0;
         P.is_pref = isp ? 1u : 0u; P.pmax = 0; P.pnmax = 0;
         if (isp) {          // written before the list words (fence in between): present once the list is
           unsigned long long a = 0, b = 0;
@@ -526,7 +526,7 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
 #pragma unroll
       for (uint32_t c = 0; c < NC; ++c) rec[c] = __ldcg(g + (size_t)c * TILE_NODES);
     }
-    const bool is_pref = P.is_pref != 0;
+    const bool is_pref = PREF && P.is_pref != 0;
     int32_t pcnt = 0;
     if (is_pref && have) { RegAcc a0{rec, R, W}; pcnt = pref_count(P.pref, a0, W); }      // labels do not change with placements
     if (w == 0) {
@@ -666,7 +666,7 @@ __device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem
   }
 }
 
-template <int RR, int WW>
+template <int RR, int WW, int PREF>
 __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char* smem_raw) {
   constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
   using RS = ReplaySmem<NC>;
@@ -683,7 +683,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   __syncthreads();
   if (warp >= PIPE_W_PATCH0 && warp < PIPE_W_PATCH0 + PIPE_DEPTH) { pipe_patch_warp<RR, WW>(S, sm, warp - PIPE_W_PATCH0, lane); return; }
   if (warp >= PIPE_W_PREP0 && warp < PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW) {
-    pipe_prep_warp<RR, WW>(S, sm, (warp - PIPE_W_PREP0) / PIPE_PREP_TW, (warp - PIPE_W_PREP0) % PIPE_PREP_TW, lane); return; }
+    pipe_prep_warp<RR, WW, PREF>(S, sm, (warp - PIPE_W_PREP0) / PIPE_PREP_TW, (warp - PIPE_W_PREP0) % PIPE_PREP_TW, lane); return; }
   if (warp == PIPE_W_WRITER) { pipe_writer_warp<RR, WW>(S, sm, lane); return; }
   if (warp == PIPE_W_SHADOW) { pipe_shadow_warp<NC>(S, sm, lane); return; }
   if (warp != 0) return;
@@ -746,7 +746,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     uint32_t seq = 0, stamp = 0;
     // a class with preferred node-affinity terms: its keys are normalised by the max count over the nodes feasible AT THE STAMP,
     // so only a list of the current table state will do (the replay then tracks the feasible max-count nodes itself)
-    const bool pref_cls = S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[cls_id].n != 0;
+    const bool pref_cls = PREF && S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[cls_id].n != 0;
     bool usable = rq_lookup(cls_id, seq, stamp);
     usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor && (!pref_cls || stamp == priv_head);
     if (!usable) { seq = post_request(cls_id); stamp = priv_head; if (lane == 0) c.pipe_urgent += 1; }
@@ -848,7 +848,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       RegAcc acc{r2, R, W};
       bool f = false;
       uint64_t k2 = eval_pair<RR, WW>(S.cf, P.cls, acc, onode, &f);
-      if (P.is_pref) k2 = add_pref_term(k2, (int64_t)S.w_nodeaff, (int64_t)pref_count(P.pref, acc, W), (int64_t)P.pmax);
+      if (PREF && P.is_pref) k2 = add_pref_term(k2, (int64_t)S.w_nodeaff, (int64_t)pref_count(P.pref, acc, W), (int64_t)P.pmax);
       __syncwarp();
       sm.ext_key[lane] = k2;
       const unsigned fm = __ballot_sync(FULL, f);
@@ -858,14 +858,14 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     if (lane == 0) sm.ext_slot = 0xFFFFFFFFu;
     __syncwarp();
     // a12 countdown: feasible nodes that reach the max count; when the last one fills up every key of this list is stale
-    const bool is_pref = P.is_pref != 0 && P.pmax > 0;
+    const bool is_pref = PREF && P.is_pref != 0 && P.pmax > 0;
     const int32_t my_cnt = (is_pref && have && my_h == 0) ? P.cnt[my_l] : -1;
     uint32_t nmax_live = P.pnmax;
     bool pref_stale = false;
 
     bool rescanned = false;
     for (;;) {              // runs of this class (consecutive visits of one class share the pool)
-      if (c.done || c.cur_class != cls_id || pref_stale) break;
+      if (c.done || c.cur_class != cls_id || (PREF && pref_stale)) break;
       const uint32_t j = (uint32_t)c.cur_job;
       const uint32_t q = c.cur_queue;
       const uint32_t jend = S.job_ord_off[j + 1];
@@ -903,7 +903,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
           depth += 1;
           cur_key = chain_key(depth);
           cur_fi = chain_fi(depth);
-          left_max = is_pref && cur_key == 0 && my_cnt == (int32_t)P.pmax;      // a max-count node left the feasible set
+          if (PREF) left_max = is_pref && cur_key == 0 && my_cnt == (int32_t)P.pmax;      // a max-count node left the feasible set
         }
         jalloc = KB_DADD(jalloc, my_rq);
         qalloc = KB_DADD(qalloc, my_rq);
@@ -918,10 +918,10 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         }
         placed += 1;
         n_alloc += fits_idle ? 1u : 0u;
-        if (is_pref && __any_sync(FULL, left_max)) { nmax_live -= 1; pref_stale = nmax_live == 0; }
+        if (PREF && is_pref && __any_sync(FULL, left_max)) { nmax_live -= 1; pref_stale = nmax_live == 0; }
         const bool jr = !S.gang_ready || (ready + (int32_t)n_alloc) >= min_avail;     // ssn.JobReady
         if (jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }                   // allocate.go:185-188
-        if (pref_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
+        if (PREF && pref_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
       }
       if (lane == 0) {
         S.job_pos[j] = pos0 + popped;
@@ -1003,7 +1003,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         const uint32_t pcls = pc[k];
         if (pcls == 0xFFFFFFFFu) continue;
         if (k == 0 && rescanned) continue;                      // the visit start posts the fresh request itself
-        if (S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[pcls].n != 0) {
+        if (PREF && S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[pcls].n != 0) {
           // preferred terms: only a list of the table state at its use will do — request the next visit's now, nothing further ahead
           if (k != 0) continue;
           uint32_t s3 = 0, st3 = 0;
@@ -1043,12 +1043,14 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   store_ctl(gctl, c, lane);
 }
 
-template <int RR, int WW>
+// PREF: the session has classes with preferred node-affinity terms (a12); 0 compiles the two-pass scan, the fresh-list rule and
+// the max-count countdown out of the hot paths
+template <int RR, int WW, int PREF>
 __global__ void __launch_bounds__(PIPE_THREADS, 1)
 cycle_kernel(const __grid_constant__ DevSession S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  if (blockIdx.x == gridDim.x - 1) pipe_replayer<RR, WW>(S, smem_raw);
-  else pipe_scanner<RR, WW>(S, smem_raw);
+  if (blockIdx.x == gridDim.x - 1) pipe_replayer<RR, WW, PREF>(S, smem_raw);
+  else pipe_scanner<RR, WW, PREF>(S, smem_raw);
 }
 
 }  // namespace kb

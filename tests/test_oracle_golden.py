@@ -266,13 +266,15 @@ def test_node_affinity_priority_normalises_over_feasible_nodes_only():
     assert score[[0, 2, 3]].tolist() == [17.0, 17.0, 17.0]
 
 
-def test_engine_side_still_refuses_preferred_node_affinity():
+def test_per_launch_kernels_refuse_preferred_node_affinity():
+    """NodeAffinityPriority runs in cycle_kernel (two-pass scan); a session the per-launch kernels would run — here R = 2, W = 1,
+    outside the pipeline's record geometry — is refused by the engine's host build, which is what the emulation runs too."""
     import util
     from kube_batch_b200 import builder as B
     from kube_batch_b200.snapshot import PluginConf
     s = _pref_session([B.Pod("ns", "p", "", "Pending", {"cpu": 1}, group="g", preferred_terms=[(1, [("zone", "In", ["a"])])])])
-    with pytest.raises(RuntimeError, match="preferred node affinity"):
-        util.emu_allocate(s, PluginConf.default())       # the engine's host build (kb_build.h) is what the emulation runs
+    with pytest.raises(RuntimeError, match="preferred node-affinity"):
+        util.emu_allocate(s, PluginConf.default())
 
 
 # ---------------- preempt / reclaim (SURVEY §8f-2): ORACLE ONLY so far; pinned on the reference's own action tests ----------------

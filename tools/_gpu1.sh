@@ -2,5 +2,7 @@ set -x
 cd /root/repo
 mkdir -p gpurun_out
 export KB_WATCHDOG_S=30
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "preferred or unsupported or baseline or reference_allocate" 2>&1 | tail -15
 timeout 100 python tools/quick_time.py c3 2 2>&1 | tail -6
+timeout 900 python -m pytest tests/test_evict_parity.py tests/test_gpu_parity.py -x -q -m gpu 2>&1 | tail -8
+timeout 600 python tools/cycle_time.py c3 0.3 0 > gpurun_out/r02b_cycle_c3.json 2> gpurun_out/r02b_cycle_c3.err; python -c "
+import json;d=json.load(open('gpurun_out/r02b_cycle_c3.json'));print(d['workload']);print({k:v for k,v in d['rep1'].items() if 'bounds' not in k})"; tail -3 gpurun_out/r02b_cycle_c3.err
