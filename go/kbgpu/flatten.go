@@ -714,6 +714,7 @@ func (a *arena) u64(s []uint64) *C.uint64_t { return (*C.uint64_t)(a.put(unsafe.
 // after kb_session_load returns: the library copies everything it needs before returning.
 func (f *Flat) cSnapshot(s *C.kb_snapshot, a *arena) {
 	s.abi_version = C.KB_ABI_VERSION
+	s.flags = 0 // Flatten refuses sessions that would need KB_SNAPSHOT_PLACED_POD_AFFINITY before it gets here
 	s.R, s.W, s.N, s.T, s.J, s.Q = C.uint32_t(f.R), C.uint32_t(f.W), C.uint32_t(f.N), C.uint32_t(f.T), C.uint32_t(f.J), C.uint32_t(f.Q)
 	s.node_idle, s.node_releasing, s.node_used, s.node_allocatable = a.f64(f.nodeIdle), a.f64(f.nodeReleasing), a.f64(f.nodeUsed), a.f64(f.nodeAllocatable)
 	s.node_alloc_present, s.node_flags = a.u32(f.nodeAllocPresent), a.u32(f.nodeFlags)

@@ -59,6 +59,12 @@ typedef enum kb_status {
 #define KB_TASK_HAS_POD_AFFINITY (1u << 1) /* pod (anti)affinity terms present -> KB_E_UNSUPPORTED_FEATURE        */
 #define KB_TASK_HAS_PREFERRED_NODE_AFFINITY (1u << 2) /* -> KB_E_UNSUPPORTED_FEATURE                               */
 
+/* kb_snapshot.flags */
+#define KB_SNAPSHOT_PLACED_POD_AFFINITY (1u << 0) /* some task that is NOT pending (running / bound / allocated on a node) carries
+                                                      inter-pod affinity or anti-affinity terms: the reference's predicate step 10 lets such
+                                                      pods reject nodes for OTHER pods (predicates.go:1261-1288 satisfiesExistingPodsAntiAffinity)
+                                                      and scores them (interpod_affinity.go:150-170) -> KB_E_UNSUPPORTED_FEATURE            */
+
 /* kb_decision.kind */
 #define KB_KIND_NONE      0 /* task was never placed this cycle                                   */
 #define KB_KIND_ALLOCATED 1 /* ssn.Allocate (framework/session.go:235)  — consumed node.Idle       */
@@ -83,7 +89,7 @@ typedef struct kb_snapshot {
   uint32_t R;               /* 2..KB_MAX_R */
   uint32_t W;               /* 1..KB_MAX_W */
   uint32_t N, T, J, Q;
-  uint32_t reserved0;       /* 0 */
+  uint32_t flags;           /* KB_SNAPSHOT_* */
 
   /* ---- nodes (api.NodeInfo, api/node_info.go:28-47) ---- */
   const double*   node_idle;          /* [R][N] NodeInfo.Idle; >= -epsilon (the cache never over-commits a node), else KB_E_BADARG */

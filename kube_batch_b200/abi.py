@@ -38,6 +38,7 @@ KB_NODE_PID_PRESSURE = 1 << 5
 
 KB_TASK_BEST_EFFORT_QOS = 1 << 0
 KB_TASK_HAS_POD_AFFINITY = 1 << 1
+KB_SNAPSHOT_PLACED_POD_AFFINITY = 1 << 0
 KB_TASK_HAS_PREFERRED_NODE_AFFINITY = 1 << 2
 
 KB_KIND_NONE = 0
@@ -108,7 +109,7 @@ class kb_snapshot(C.Structure):
         ("T", C.c_uint32),
         ("J", C.c_uint32),
         ("Q", C.c_uint32),
-        ("reserved0", C.c_uint32),
+        ("flags", C.c_uint32),
     ] + [(name, ptr) for name, ptr, _, _ in SNAPSHOT_ARRAYS]
 
 

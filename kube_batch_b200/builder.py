@@ -16,6 +16,8 @@ executable specification of what the Go shim's flattening must compute (INTEGRAT
 """
 from __future__ import annotations
 
+import math
+
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -194,19 +196,24 @@ class SessionBuilder:
 
     # ---- api.NewResource (api/resource_info.go:73-90): cpu -> milli, memory -> bytes, scalars -> milli ----
     @staticmethod
+    def _milli(q: float) -> int:
+        """resource.Quantity.MilliValue(): rounds UP (apimachinery resource/quantity.go ScaledValue), e.g. cpu 0.0005 -> 1."""
+        return int(math.ceil(q * 1000.0 - 1e-9))
+
+    @staticmethod
     def _resource(rl: Dict[str, float], dims: List[str]):
         v = np.zeros(len(dims))
         present = 0
         for k, q in rl.items():
             if k == "cpu":
-                v[0] += round(q * 1000.0)
+                v[0] += SessionBuilder._milli(q)
             elif k == "memory":
                 v[1] += q
             elif k == "pods":
                 continue
             else:
                 r = dims.index(k)
-                v[r] += round(q * 1000.0)
+                v[r] += SessionBuilder._milli(q)
                 present |= 1 << r
         return v, present
 
@@ -334,7 +341,7 @@ class SessionBuilder:
             return self._resource(p.requests, dims)
 
         def pod_nz(p: Pod):
-            cpu = round(p.requests["cpu"] * 1000.0) if "cpu" in p.requests else DEFAULT_MILLI_CPU_REQUEST
+            cpu = self._milli(p.requests["cpu"]) if "cpu" in p.requests else DEFAULT_MILLI_CPU_REQUEST
             mem = int(p.requests["memory"]) if "memory" in p.requests else DEFAULT_MEMORY_REQUEST
             return int(cpu), int(mem)
 

@@ -294,6 +294,10 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
                          int pipe_mode = 0 /* persistent pipeline (cycle_kernel): 0 off, 1 when the geometry allows it */) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
+  if (s->flags & KB_SNAPSHOT_PLACED_POD_AFFINITY)
+    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "a placed pod carries inter-pod (anti)affinity terms: the reference lets it reject nodes for other pods "
+                 "(predicates.go:1261-1288), which this build does not model (no CPU fallback)");
+  if (s->flags & ~KB_SNAPSHOT_PLACED_POD_AFFINITY) return bfail(e, KB_E_BADARG, "unknown kb_snapshot.flags bits 0x%x", s->flags);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
   if (s->Q > KB_MAX_Q) return bfail(e, KB_E_BADARG, "Q=%u > KB_MAX_Q", s->Q);
   if (s->N >= 0xFFFFFFF0u) return bfail(e, KB_E_BADARG, "N too large for the packed key");

@@ -47,9 +47,9 @@ struct EvictCtl {
   uint32_t qheap_len;
   uint32_t fail_valid, fail_cls, fail_mode, fail_key, fail_version;   // the last sweep that found no node
   unsigned long long pairs_logical;
-  // device plumbing of the multi-CTA kernel (kb_evict_kernels.cu): grid barrier, broadcast slot, arg-max slot, the
-  // preemptor being swept and its class (written by thread 0 of the grid, read by every CTA after a barrier)
-  uint32_t bar_count, bar_gen, bc, pad0;
+  // device plumbing of the master / worker kernel (kb_evict_kernels.cu): sweep mailbox, arg-max slot, the preemptor being
+  // swept and its class (written by the master thread before it posts the command)
+  uint32_t cmd_seq, arrived, n_workers, pad0;      // master -> workers: sweep command counter (~0u = exit); workers -> master: CTAs done
   unsigned long long red;
   Preemptor pre;
   ClassRec cls;
@@ -380,6 +380,13 @@ struct CpuExec {
   KB_HD uint32_t bcast(uint32_t v) { return v; }
   KB_HD uint64_t block_max(uint64_t v) { return v; }
   KB_HD void clear_max() {}
+  uint64_t sweep(const DevSession& S, const EvictDev& E, const Preemptor& P, const ClassRec& c) {      // the node axis, serially
+    uint64_t best = 0;
+    uint32_t err = 0;
+    for (uint32_t n = 0; n < S.N; ++n) { const uint64_t k = evict_node_key(S, E, P, c, n, &err); best = k > best ? k : best; }
+    if (err) E.ctl->error = err;
+    return best;
+  }
   KB_HD ClassRec& cls() { return c; }
   KB_HD Preemptor& pre() { return p; }
 };
@@ -459,15 +466,7 @@ KB_HD bool try_preemptor(X& x, const DevSession& S, const EvictDev& E, const uin
   const uint32_t fkey = mode == 0 ? P.queue : job;
   const bool known_fail = ctl.fail_valid && ctl.fail_cls == P.cls && ctl.fail_mode == mode && ctl.fail_key == fkey && ctl.fail_version == ctl.version;
   uint64_t best = 0;
-  uint32_t err = 0;
-  if (!known_fail) {
-    for (uint32_t n = (uint32_t)x.tid(); n < S.N; n += (uint32_t)x.nthreads()) {
-      const uint64_t k = evict_node_key(S, E, P, c, n, &err);
-      best = k > best ? k : best;
-    }
-    best = x.block_max(best);
-    if (err) ctl.error = err;                                   // benign race: every writer stores the same kind of value
-  }
+  if (!known_fail) best = x.sweep(S, E, P, c);      // all nodes: K1 (+K2) + the victim walk, arg-max of the packed keys
   x.sync();
   if (x.tid() == 0) {
     if (!known_fail) ctl.scans += 1;

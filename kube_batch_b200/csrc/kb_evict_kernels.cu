@@ -1,14 +1,18 @@
 // kb_evict_kernels.cu — reclaim / preempt on the device (kb_evict.h holds the algorithm, shared with the CPU emulation).
 //
-// evict_kernel<PREEMPT>   cooperative grid of up to one CTA per SM.  Per preemptor task ALL CTAs sweep the node table together
-//                         (one node per thread per iteration: K1 predicate, K2 score for preempt, the serial victim walk of
-//                         the node), a grid-wide arg-max picks the node, thread 0 of the grid commits (evictions, Pipeline,
-//                         Statement log) and runs the action's control flow; grid barriers in between.
+// evict_kernel<PREEMPT>   cooperative grid: W worker CTAs + 1 master CTA.
+//   master  ONE thread runs the action exactly as written in kb_evict.h (queue / job heaps with Go's container/heap semantics,
+//           Statement commit / discard, the serial commit on the chosen node).  Whenever a preemptor needs its pass over the
+//           node table it writes the preemptor + its class into the mailbox, posts a command word (release) and waits for the
+//           workers' arrival counter; preemptors whose sweep is known to fail (same class, same filter, unchanged state) never
+//           leave the master thread.
+//   worker  CTAs poll the command word (acquire), sweep their share of the nodes — one node per thread per iteration: K1
+//           predicate, K2 score for preempt, the serial victim walk of the node's Running tasks — reduce the packed keys
+//           (warp REDUX, one 64-bit atomicMax per CTA) and arrive.
 //
-// This translation unit is compiled with -Xptxas -dlcm=cg: every global load goes to L2.  The action mutates node records,
-// job / queue accounting and the Running tasks' states from ONE thread while 147 other SMs read them in the next sweep; with
-// L1-cached loads those SMs could see stale lines.  (The allocate kernels keep L1 caching: their mutable tables are only
-// read by the SM that writes them.)
+// This translation unit is compiled with -Xptxas -dlcm=cg: every global load goes to L2.  The master mutates node records,
+// job / queue accounting and the Running tasks' states between two sweeps; with L1-cached loads the workers' SMs could see
+// stale lines.  (The allocate kernels keep L1 caching: their mutable tables are only read by the SM that writes them.)
 #include <cuda_runtime.h>
 
 #include "kb_evict.h"
@@ -17,80 +21,122 @@
 namespace kb {
 
 constexpr int EVICT_THREADS = 512;
+constexpr uint32_t EVICT_EXIT = 0xFFFFFFFFu;
 
 __device__ __forceinline__ uint32_t ev_ld_acquire(const uint32_t* p) {
   uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
 }
+__device__ __forceinline__ void ev_st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-struct GridExec {
-  EvictCtl* g;               // barrier / broadcast / arg-max slots + the preemptor and its class
-  uint64_t* red_smem;        // [32] per-CTA reduction scratch
-  __device__ __forceinline__ int tid() const { return (int)(blockIdx.x * blockDim.x + threadIdx.x); }
-  __device__ __forceinline__ int nthreads() const { return (int)(gridDim.x * blockDim.x); }
-  // sense-reversing grid barrier (all CTAs are co-resident: cooperative launch)
-  __device__ __forceinline__ void sync() {
-    __syncthreads();
-    if (threadIdx.x == 0 && gridDim.x > 1) {
-      const uint32_t gen = ev_ld_acquire(&g->bar_gen);
-      __threadfence();
-      if (atomicAdd(&g->bar_count, 1u) == gridDim.x - 1) {
-        g->bar_count = 0;
-        __threadfence();
-        atomicAdd(&g->bar_gen, 1u);
-      } else {
-        while (ev_ld_acquire(&g->bar_gen) == gen) __nanosleep(20);
-      }
-    }
-    __syncthreads();
-  }
-  __device__ __forceinline__ uint32_t bcast(uint32_t v) {
-    if (tid() == 0) g->bc = v;
-    sync();
-    const uint32_t r = *((volatile uint32_t*)&g->bc);
-    sync();
-    return r;
-  }
-  // arg-max over the grid: thread 0 cleared g->red before the barrier that precedes the sweep (try_preemptor)
-  __device__ __forceinline__ uint64_t block_max(uint64_t v) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
-    const unsigned mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
-    const unsigned mlo = __reduce_max_sync(0xFFFFFFFFu, hi == mhi ? lo : 0u);
-    if (lane == 0) red_smem[warp] = ((uint64_t)mhi << 32) | mlo;
-    __syncthreads();
-    if (warp == 0) {
-      uint64_t r = lane < (int)(blockDim.x >> 5) ? red_smem[lane] : 0ull;
-      const unsigned rh = (unsigned)(r >> 32), rl = (unsigned)r;
-      const unsigned xh = __reduce_max_sync(0xFFFFFFFFu, rh);
-      const unsigned xl = __reduce_max_sync(0xFFFFFFFFu, rh == xh ? rl : 0u);
-      if (lane == 0 && (xh | xl)) atomicMax(&g->red, ((unsigned long long)xh << 32) | xl);
-    }
-    sync();
-    const uint64_t r = *((volatile unsigned long long*)&g->red);
-    return r;
-  }
-  __device__ __forceinline__ void clear_max() { g->red = 0ull; }
+// the master thread's Exec: single-threaded control, the sweep is farmed out
+struct MasterExec {
+  EvictCtl* g;
+  uint32_t seq;
+  __device__ __forceinline__ int tid() const { return 0; }
+  __device__ __forceinline__ int nthreads() const { return 1; }
+  __device__ __forceinline__ void sync() {}
+  __device__ __forceinline__ uint32_t bcast(uint32_t v) { return v; }
+  __device__ __forceinline__ void clear_max() {}
   __device__ __forceinline__ ClassRec& cls() { return g->cls; }
   __device__ __forceinline__ Preemptor& pre() { return g->pre; }
+  __device__ __forceinline__ uint64_t sweep(const DevSession&, const EvictDev&, const Preemptor&, const ClassRec&) {
+    g->red = 0ull;
+    g->arrived = 0u;
+    __threadfence();                                 // the mailbox (pre, cls) and every table write of earlier commits are visible first
+    seq += 1;
+    ev_st_release(&g->cmd_seq, seq);
+    const uint32_t nw = g->n_workers;
+    while (ev_ld_acquire(&g->arrived) < nw) __nanosleep(40);
+    return *((volatile unsigned long long*)&g->red);
+  }
 };
 
 template <int PREEMPT>
 __global__ void __launch_bounds__(EVICT_THREADS, 1)
 evict_kernel(const __grid_constant__ DevSession S, const __grid_constant__ EvictDev E) {
-  __shared__ uint64_t s_red[32];
-  GridExec x{E.ctl, s_red};
-  if (PREEMPT) run_preempt(x, S, E);
-  else run_reclaim(x, S, E);
+  EvictCtl* g = E.ctl;
+  if (blockIdx.x == gridDim.x - 1) {
+    // ---------------- master ----------------
+    if (threadIdx.x != 0) return;
+    MasterExec x{g, 0u};
+    if (PREEMPT) run_preempt(x, S, E);
+    else run_reclaim(x, S, E);
+    __threadfence();
+    ev_st_release(&g->cmd_seq, EVICT_EXIT);
+    return;
+  }
+  // ---------------- workers ----------------
+  __shared__ ClassRec s_cls;
+  __shared__ Preemptor s_pre;
+  __shared__ uint64_t s_red[EVICT_THREADS / 32];
+  __shared__ uint32_t s_cmd, s_err;
+  const uint32_t nw = gridDim.x - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t seen = 0;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      uint32_t v;
+      while ((v = ev_ld_acquire(&g->cmd_seq)) == seen) __nanosleep(40);
+      s_cmd = v; s_err = 0;
+    }
+    __syncthreads();
+    const uint32_t cmd = s_cmd;
+    if (cmd == EVICT_EXIT) return;
+    seen = cmd;
+    {
+      const uint32_t* src = reinterpret_cast<const uint32_t*>(&g->cls);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(&s_cls);
+      for (uint32_t i = threadIdx.x; i < sizeof(ClassRec) / 4; i += EVICT_THREADS) dst[i] = src[i];
+      const uint32_t* ps = reinterpret_cast<const uint32_t*>(&g->pre);
+      uint32_t* pd = reinterpret_cast<uint32_t*>(&s_pre);
+      for (uint32_t i = threadIdx.x; i < sizeof(Preemptor) / 4; i += EVICT_THREADS) pd[i] = ps[i];
+    }
+    __syncthreads();
+    uint64_t best = 0;
+    uint32_t err = 0;
+    for (uint32_t n = blockIdx.x * EVICT_THREADS + threadIdx.x; n < S.N; n += nw * EVICT_THREADS) {
+      const uint64_t k = evict_node_key(S, E, s_pre, s_cls, n, &err);
+      best = k > best ? k : best;
+    }
+    if (err) s_err = err;
+    {
+      const unsigned hi = (unsigned)(best >> 32), lo = (unsigned)best;
+      const unsigned mhi = __reduce_max_sync(0xFFFFFFFFu, hi);
+      const unsigned mlo = __reduce_max_sync(0xFFFFFFFFu, hi == mhi ? lo : 0u);
+      if (lane == 0) s_red[warp] = ((uint64_t)mhi << 32) | mlo;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      const uint64_t r = lane < EVICT_THREADS / 32 ? s_red[lane] : 0ull;
+      const unsigned rh = (unsigned)(r >> 32), rl = (unsigned)r;
+      const unsigned xh = __reduce_max_sync(0xFFFFFFFFu, rh);
+      const unsigned xl = __reduce_max_sync(0xFFFFFFFFu, rh == xh ? rl : 0u);
+      if (lane == 0) {
+        if (xh | xl) atomicMax(&g->red, ((unsigned long long)xh << 32) | xl);
+        if (s_err) g->error = s_err;
+        __threadfence();
+        atomicAdd(&g->arrived, 1u);
+      }
+    }
+    __syncthreads();      // s_cls / s_pre / s_red are reused by the next command
+  }
 }
 
 cudaError_t launch_evict(const bool preempt, const DevSession& S, const EvictDev& E, const int sm_count, cudaStream_t stream) {
-  // enough CTAs for one node per thread per sweep iteration, at most one CTA per SM (co-residency of the grid barrier)
-  int grid = (int)((S.N + EVICT_THREADS - 1) / EVICT_THREADS);
-  grid = grid < 1 ? 1 : (grid > sm_count ? sm_count : grid);
+  // workers: one node per thread per sweep iteration, at most one CTA per SM next to the master's (co-residency: they spin)
+  int workers = (int)((S.N + EVICT_THREADS - 1) / EVICT_THREADS);
+  workers = workers < 1 ? 1 : (workers > sm_count - 1 ? sm_count - 1 : workers);
+  if (workers < 1) workers = 1;
+  cudaError_t c = cudaMemcpyAsync(reinterpret_cast<char*>(E.ctl) + offsetof(EvictCtl, n_workers), &workers, 4, cudaMemcpyHostToDevice, stream);
+  if (c != cudaSuccess) return c;
+  c = cudaMemsetAsync(reinterpret_cast<char*>(E.ctl) + offsetof(EvictCtl, cmd_seq), 0, 8, stream);      // cmd_seq, arrived
+  if (c != cudaSuccess) return c;
   DevSession s = S; EvictDev ev = E;
   void* args[] = {(void*)&s, (void*)&ev};
   const void* fn = preempt ? (const void*)evict_kernel<1> : (const void*)evict_kernel<0>;
-  return cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(EVICT_THREADS), args, 0, stream);
+  return cudaLaunchCooperativeKernel(fn, dim3(workers + 1), dim3(EVICT_THREADS), args, 0, stream);
 }
 
 }  // namespace kb

@@ -32,15 +32,17 @@
 
 namespace kb {
 
-constexpr int PIPE_DEPTH = 8;              // placement depths evaluated up front per candidate
-// replayer CTA warp roles: 0 main, 1..8 patch warps (one per depth), 9..16 prep teams, 17 writer, 18 shadow prefetch.
-// scanner CTAs: 0..15 scan groups, 16 applier, the rest exit.
+constexpr int PIPE_DEPTH = 8;              // placement depths a prep team evaluates per list entry (ahead of the visit)
+constexpr int PIPE_PDEPTH = 4;             // ... and the patch warps per patch entry (on the visit's critical path: kept short;
+                                           //     deeper states of a candidate come from the chain extension)
+// replayer CTA warp roles: 0 main, 1..4 patch warps (one per depth), then the prep teams, the writer, the shadow prefetch;
+// the remaining warps exit.  scanner CTAs: 0..15 scan groups, 16 applier.
 constexpr int PIPE_W_PATCH0 = 1;
 constexpr int PIPE_PREP_TEAMS = 2, PIPE_PREP_TW = 4;
-constexpr int PIPE_W_PREP0 = PIPE_W_PATCH0 + PIPE_DEPTH;
+constexpr int PIPE_W_PREP0 = PIPE_W_PATCH0 + PIPE_PDEPTH;
 constexpr int PIPE_W_WRITER = PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW;
 constexpr int PIPE_W_SHADOW = PIPE_W_WRITER + 1;
-constexpr int PIPE_WARPS = PIPE_W_SHADOW + 1;
+constexpr int PIPE_WARPS = (PIPE_W_SHADOW + 1) > 17 ? (PIPE_W_SHADOW + 1) : 17;      // the scanner CTAs need 16 scan warps + the applier
 constexpr int PIPE_THREADS = PIPE_WARPS * 32;
 static_assert(PIPE_DEPTH % PIPE_PREP_TW == 0, "a prep warp owns depths w, w + TW, ...");
 constexpr uint32_t PIPE_HOT = 128;         // hot ring: records of the most recent log entries (replayer shared memory)
@@ -393,8 +395,9 @@ struct ReplaySmem {
   // visit descriptor (main warp -> patch warps)
   uint32_t v_pb, v_stamp, v_npatch, v_pvalid, v_quit, v_err, v_count, v_pad;
   uint32_t pnode[32];                          // patch entry i: node of log entry v_stamp + i (valid bit in v_pvalid: latest entry of its node)
-  uint64_t pkey[PIPE_DEPTH][KTOP];             // patch entry i after d more placements
-  uint32_t pfi[PIPE_DEPTH];
+  uint64_t pkey[PIPE_PDEPTH][KTOP];            // patch entry i after d more placements
+  uint32_t pfi[PIPE_PDEPTH];
+  uint64_t cmp_key[KTOP]; uint32_t cmp_slot[KTOP];       // compaction scratch of the main warp
   uint64_t psort_key[KTOP]; uint32_t psort_slot[KTOP];   // patch entries' fresh keys, sorted (descending); slot = 32 + i
   // chain extension of ONE pool slot beyond PIPE_DEPTH
   uint64_t ext_key[32]; uint32_t ext_fi, ext_slot, ext_base, ext_pad;
@@ -421,7 +424,7 @@ template <int RR, int WW>
 __device__ __forceinline__ void pipe_patch_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int d, const int lane) {
   constexpr uint32_t R = RR, W = WW, NC = 2 * RR + 6 + 3 * WW;
   for (;;) {
-    bar_sync(1, (1 + PIPE_DEPTH) * 32);         // go
+    bar_sync(1, (1 + PIPE_PDEPTH) * 32);         // go
     if (*((volatile uint32_t*)&sm.v_quit)) return;
     const ClassRec& cls = sm.pb[sm.v_pb].cls;
     const bool have = ((sm.v_pvalid >> lane) & 1u) != 0;
@@ -445,7 +448,7 @@ __device__ __forceinline__ void pipe_patch_warp(const DevSession& S, ReplaySmem<
       warp_sort_desc_kv(k2, sl, lane);
       sm.psort_key[lane] = k2; sm.psort_slot[lane] = sl;
     }
-    bar_sync(1, (1 + PIPE_DEPTH) * 32);         // done
+    bar_sync(1, (1 + PIPE_PDEPTH) * 32);         // done
   }
 }
 
@@ -681,7 +684,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     if (lane == 0) { sm.cmd_head = 0; sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.v_count = 0; sm.rq_posted = 0; sm.ext_slot = 0xFFFFFFFFu; }
   }
   __syncthreads();
-  if (warp >= PIPE_W_PATCH0 && warp < PIPE_W_PATCH0 + PIPE_DEPTH) { pipe_patch_warp<RR, WW>(S, sm, warp - PIPE_W_PATCH0, lane); return; }
+  if (warp >= PIPE_W_PATCH0 && warp < PIPE_W_PATCH0 + PIPE_PDEPTH) { pipe_patch_warp<RR, WW>(S, sm, warp - PIPE_W_PATCH0, lane); return; }
   if (warp >= PIPE_W_PREP0 && warp < PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW) {
     pipe_prep_warp<RR, WW, PREF>(S, sm, (warp - PIPE_W_PREP0) / PIPE_PREP_TW, (warp - PIPE_W_PREP0) % PIPE_PREP_TW, lane); return; }
   if (warp == PIPE_W_WRITER) { pipe_writer_warp<RR, WW>(S, sm, lane); return; }
@@ -737,10 +740,11 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     return seq;
   };
 
+  const bool timing = (S.pipe_pad & 1u) != 0;       // KB_PIPE_TIMING=1: clock64 phase timers of the main warp (kb_stats.cyc_*)
   const long long t_cycle0 = clock64();
   while (!c.done && !failed) {
     const uint32_t cls_id = c.cur_class;
-    const long long t_v0 = clock64();
+    const long long t_v0 = timing ? clock64() : 0;
     if (lane == 0) { *((volatile uint32_t*)&sm.v_count) = sm.v_count + 1; dbg_put(S.dbg, 0, sm.v_count); dbg_put(S.dbg, 1, 1u); dbg_put(S.dbg, 2, cls_id); }       // wakes the shadow warp
     // ---------------- visit start: which list ----------------
     uint32_t seq = 0, stamp = 0;
@@ -778,7 +782,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       }
       __syncwarp();
       if (lane == 0) dbg_put(S.dbg, 1, 3u);
-      bar_sync(1, (1 + PIPE_DEPTH) * 32);        // go: the patch warps evaluate depths 0..7 of the modified nodes
+      bar_sync(1, (1 + PIPE_PDEPTH) * 32);        // go: the patch warps evaluate depths 0..7 of the modified nodes
     }
     // ---------------- meanwhile: the prepared list minus the modified nodes, compacted (order is kept) ----------------
     uint64_t cur_key; uint32_t slot;
@@ -789,18 +793,20 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       for (uint32_t i = 0; i < npatch; ++i) { const uint32_t o = __shfl_sync(FULL, pn, (int)i); ok = ok & (o != lnode); }   // no short-circuit: every lane takes part in the shuffle
       const uint64_t k0 = ok ? P.key[0][lane] : 0ull;
       const unsigned am = __ballot_sync(FULL, k0 != 0);
-      const unsigned src = __fns(am, 0, lane + 1);
-      const uint64_t ck = __shfl_sync(FULL, k0, (int)(src & 31u));
-      cur_key = src < 32u ? ck : 0ull;
-      slot = src < 32u ? src : 0u;
+      if (k0) { const uint32_t rank = (uint32_t)__popc(am & ((1u << lane) - 1u)); sm.cmp_key[rank] = k0; sm.cmp_slot[rank] = (uint32_t)lane; }
+      __syncwarp();
+      const bool in = (uint32_t)lane < (uint32_t)__popc(am);
+      cur_key = in ? sm.cmp_key[lane] : 0ull;
+      slot = in ? sm.cmp_slot[lane] : 0u;
+      __syncwarp();
     }
     const uint64_t f0 = P.list[KTOP - 1];
     uint64_t dropped = 0;
     if (npatch) {
-      bar_sync(1, (1 + PIPE_DEPTH) * 32);        // done
+      bar_sync(1, (1 + PIPE_PDEPTH) * 32);        // done
       warp_merge_top32_kv(cur_key, slot, sm.psort_key[lane], sm.psort_slot[lane], dropped, lane);
     }
-    const long long t_v1 = clock64();
+    const long long t_v1 = timing ? clock64() : 0;
     if (lane == 0) dbg_put(S.dbg, 1, 4u);
     // ---------------- pool -> 32 lane-owned candidates ----------------
     const uint64_t floor_key = f0 > dropped ? f0 : dropped;
@@ -811,11 +817,12 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     bool cur_fi = have && (((my_h ? sm.pfi[0] : P.fi[0]) >> my_l) & 1u);
     if (lane == 0) c.scans += 1;
     // key / fits-idle of MY candidate at depth dd (dd >= 1): precomputed chain, else the extension buffer
-    auto chain_has = [&](uint32_t dd) -> bool { return dd < (uint32_t)PIPE_DEPTH || (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u); };
+    const uint32_t my_lim = my_h ? (uint32_t)PIPE_PDEPTH : (uint32_t)PIPE_DEPTH;      // depths evaluated up front for MY candidate
+    auto chain_has = [&](uint32_t dd) -> bool { return dd < my_lim || (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u); };
     auto chain_key = [&](uint32_t dd) -> uint64_t {
-      return dd < (uint32_t)PIPE_DEPTH ? (my_h ? sm.pkey[dd][my_l] : P.key[dd][my_l]) : sm.ext_key[dd - sm.ext_base]; };
+      return dd < my_lim ? (my_h ? sm.pkey[dd][my_l] : P.key[dd][my_l]) : sm.ext_key[dd - sm.ext_base]; };
     auto chain_fi = [&](uint32_t dd) -> bool {
-      return dd < (uint32_t)PIPE_DEPTH ? ((((my_h ? sm.pfi[dd] : P.fi[dd]) >> my_l) & 1u) != 0) : (((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0);
+      return dd < my_lim ? ((((my_h ? sm.pfi[dd] : P.fi[dd]) >> my_l) & 1u) != 0) : (((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0);
     };
     // my candidate's base record (state at depth 0): prepared buffer or hot ring
     auto load_rec0 = [&](uint64_t* r0) {
@@ -884,7 +891,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       }
       const uint32_t step0 = c.step;
       uint32_t my_task = 0;
-      const long long t_run0 = clock64();
+      const long long t_run0 = timing ? clock64() : 0;
       while (run_left > 0) {      // steps: one pending task each (allocate.go:129-189)
         const uint64_t best = warp_max_u64(cur_key);
         if (best < floor_key) { reason = STOP_RESCAN; break; }
@@ -937,29 +944,35 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (S.drf_present) S.job_alloc[(size_t)lane * S.J + j] = jalloc;
         if (S.proportion_present) S.q_allocated[(size_t)lane * S.Q + q] = qalloc;
       }
-      if (placed) {        // drf.calculateShare / proportion.updateShare: one FP64 division per dimension, in parallel lanes
-        if (S.drf_present) {
-          double v = 0.0;
-          if ((uint32_t)lane < R && ((S.total_dims_mask >> lane) & 1u)) v = share_of(jalloc, S.total[lane]);
-          const uint64_t m = warp_max_u64(double_as_u64(v));
-          if (lane == 0) S.job_share[j] = u64_as_double(m);
+      if (placed) {        // drf.calculateShare (lanes 0..R-1) and proportion.updateShare (lanes 8..8+R-1): all divisions side by side
+        const int k8 = lane & 7;
+        const double qa = __shfl_sync(FULL, qalloc, k8);
+        double v = 0.0;
+        if (lane < 8) {
+          if (S.drf_present && (uint32_t)lane < R && ((S.total_dims_mask >> lane) & 1u)) v = share_of(jalloc, S.total[lane]);
+        } else if (lane < 16) {
+          if (S.proportion_present && (uint32_t)k8 < R) {
+            const uint32_t present = S.q_deserved_present[q] | 3u;
+            if ((present >> k8) & 1u) v = share_of(qa, S.q_deserved[(size_t)k8 * S.Q + q]);
+          }
         }
-        if (S.proportion_present) {
-          double v = 0.0;
-          const uint32_t present = S.q_deserved_present[q] | 3u;
-          if ((uint32_t)lane < R && ((present >> lane) & 1u)) v = share_of(qalloc, S.q_deserved[(size_t)lane * S.Q + q]);
-          const uint64_t m = warp_max_u64(double_as_u64(v));
-          if (lane == 0) S.q_share[q] = u64_as_double(m);
+        const uint64_t m1 = warp_max_u64(lane < 8 ? double_as_u64(v) : 0ull);
+        const uint64_t m2 = warp_max_u64((lane >= 8 && lane < 16) ? double_as_u64(v) : 0ull);
+        if (lane == 0) {
+          if (S.drf_present) S.job_share[j] = u64_as_double(m1);
+          if (S.proportion_present) S.q_share[q] = u64_as_double(m2);
         }
       }
       __syncwarp();
-      const long long t_run1 = clock64();
+      const long long t_run1 = timing ? clock64() : 0;
       if (lane == 0) {
         if (reason == STOP_RESCAN) c.rescans += 1;
         after_run<0>(S, c, reason, placed, true);
-        const long long t_run2 = clock64();
-        c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
-        c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
+        if (timing) {
+          const long long t_run2 = clock64();
+          c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
+          c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
+        }
       }
       __syncwarp();
       if (reason == STOP_RESCAN) { rescanned = true; break; }
@@ -1017,7 +1030,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (!ok) post_request(pcls);
       }
     }
-    if (lane == 0) {
+    if (lane == 0 && timing) {
       const long long t_end = clock64();
       c.cyc_wait += (unsigned long long)(t_v1 - t_v0);
       c.cyc_scan += (unsigned long long)(t_v1 - t_v0);
@@ -1030,7 +1043,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   if (lane == 0) dbg_put(S.dbg, 1, 7u);
   if (lane == 0) { *((volatile uint32_t*)&sm.v_quit) = 1; }
   __syncwarp();
-  bar_sync(1, (1 + PIPE_DEPTH) * 32);           // releases the patch warps
+  bar_sync(1, (1 + PIPE_PDEPTH) * 32);           // releases the patch warps
   push_cmd(PCMD_QUIT, 0, 0);
   while (*((volatile uint32_t*)&sm.cmd_tail) != cmd_head - 1 + 0u && *((volatile uint32_t*)&sm.cmd_tail) != cmd_head) __nanosleep(40);
   if (lane == 0) {

@@ -43,10 +43,10 @@ struct Resource {                                     // api/resource_info.go:28
   static Resource New(const ResourceList& rl) {       // NewResource, resource_info.go:73-90
     Resource r;
     for (auto& kv : rl) {
-      if (kv.first == "cpu") r.MilliCPU += std::llround(kv.second * 1000.0);
+      if (kv.first == "cpu") r.MilliCPU += std::ceil(kv.second * 1000.0 - 1e-9);      // Quantity.MilliValue rounds up
       else if (kv.first == "memory") r.Memory += kv.second;
       else if (kv.first == "pods") r.MaxTaskNum += (int)kv.second;
-      else r.ScalarResources[kv.first] += std::llround(kv.second * 1000.0);
+      else r.ScalarResources[kv.first] += std::ceil(kv.second * 1000.0 - 1e-9);
     }
     return r;
   }
@@ -460,7 +460,7 @@ inline Flat Flatten(const framework::Session& ssn) {
     f.node_flags[i] = fl;
     for (auto& kv : n.Tasks) {                         // nonzero requests + used ports of every task on the node
       auto& p = *kv.second->pod;
-      f.node_nz_cpu[i] += p.Requests.count("cpu") ? (int64_t)std::llround(p.Requests.at("cpu") * 1000.0) : 100;           // non_zero.go:36
+      f.node_nz_cpu[i] += p.Requests.count("cpu") ? (int64_t)std::ceil(p.Requests.at("cpu") * 1000.0 - 1e-9) : 100;           // non_zero.go:36
       f.node_nz_mem[i] += p.Requests.count("memory") ? (int64_t)p.Requests.at("memory") : 200ll * 1024 * 1024;             // non_zero.go:38
       for (auto& h : p.HostPorts) if (h.Port > 0) setbit(f.node_ports, N, i, portAtoms.at(san(h)));
     }
@@ -476,7 +476,7 @@ inline Flat Flatten(const framework::Session& ssn) {
   for (uint32_t t = 0; t < T; ++t) {
     auto& ti = *f.tasks[t]; auto& p = *ti.pod;
     resourceVec(ti.Resreq, f.dims, &f.task_resreq[t], T, &f.task_res_present[t]); resourceVec(ti.InitResreq, f.dims, &f.task_initreq[t], T, nullptr);
-    f.task_nz_cpu[t] = p.Requests.count("cpu") ? (int64_t)std::llround(p.Requests.at("cpu") * 1000.0) : 100;
+    f.task_nz_cpu[t] = p.Requests.count("cpu") ? (int64_t)std::ceil(p.Requests.at("cpu") * 1000.0 - 1e-9) : 100;
     f.task_nz_mem[t] = p.Requests.count("memory") ? (int64_t)p.Requests.at("memory") : 200ll * 1024 * 1024;
     for (auto& kv : p.NodeSelector) setbit(f.task_sel_req, T, t, labelAtoms.at({kv.first, kv.second}));
     for (auto& ta : taintAtoms) for (auto& tol : p.Tolerations) {                // Toleration.ToleratesTaint, toleration.go:37-56

@@ -68,7 +68,7 @@ class Snapshot:
         s = abi.kb_snapshot()
         s.abi_version = abi.KB_ABI_VERSION
         s.R, s.W, s.N, s.T, s.J, s.Q = self.R, self.W, self.N, self.T, self.J, self.Q
-        s.reserved0 = 0
+        s.flags = int(getattr(self, "flags", 0))      # KB_SNAPSHOT_*
         keep = []
         for name, ptr, _, _ in abi.SNAPSHOT_ARRAYS:
             a = getattr(self, name)

@@ -404,6 +404,15 @@ def test_preferred_node_affinity_two_pass_scan_prototype(seed):
     assert rescans >= 0
 
 
+def test_a_placed_pod_with_inter_pod_affinity_terms_is_refused():
+    """predicates.go:1261-1288: pods already on a node can reject it for OTHER pods through their anti-affinity terms.  The ABI
+    carries that as a snapshot flag; the engine's host build (which the emulation runs) refuses such a session loudly."""
+    s = synth.random_session(3)
+    s.flags = abi.KB_SNAPSHOT_PLACED_POD_AFFINITY
+    with pytest.raises(RuntimeError, match="placed pod carries inter-pod"):
+        util.emu_allocate(s, PluginConf.default())
+
+
 PREF_CONFS = (PluginConf.default(),
               PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "5"}}),
               PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "-3"}}),

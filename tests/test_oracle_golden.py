@@ -266,6 +266,15 @@ def test_node_affinity_priority_normalises_over_feasible_nodes_only():
     assert score[[0, 2, 3]].tolist() == [17.0, 17.0, 17.0]
 
 
+def test_sub_milli_quantities_round_up_like_milli_value():
+    """resource.Quantity.MilliValue() rounds up: cpu 0.0005 is 1 milli (api.NewResource, resource_info.go:73-90, and
+    GetNonzeroRequests), not 0 as half-to-even rounding would give."""
+    from kube_batch_b200 import builder as B
+    v, _ = B.SessionBuilder._resource({"cpu": 0.0005, "memory": 1.0}, ["cpu", "memory"])
+    assert v.tolist() == [1.0, 1.0]
+    assert B.SessionBuilder._milli(0.5) == 500 and B.SessionBuilder._milli(2.5e-3) == 3 and B.SessionBuilder._milli(1.0) == 1000
+
+
 def test_per_launch_kernels_refuse_preferred_node_affinity():
     """NodeAffinityPriority runs in cycle_kernel (two-pass scan); a session the per-launch kernels would run — here R = 2, W = 1,
     outside the pipeline's record geometry — is refused by the engine's host build, which is what the emulation runs too."""
