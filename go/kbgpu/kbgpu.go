@@ -93,3 +93,27 @@ func (e *Engine) action(nTasks int, backfill bool) ([]Decision, error) {
 	}
 	return out, nil
 }
+
+// Bind is one entry of the bind fan-out list.
+type Bind struct {
+	Task uint32 // index into Flat.Tasks
+	Node int32  // index into Flat.NodeNames
+}
+
+// BindList returns the (task, node) pairs that reach cache.Bind in the cycle just run, in ssn.dispatch order
+// (framework/session.go:277-314), compacted and sorted on the device.  A batched Binder (one API round trip for the whole list
+// instead of cache.Bind's goroutine per task, cache/cache.go:491-535) consumes it; the per-task replay through ssn.Allocate
+// keeps the session state, the list replaces only the fan-out.
+func (e *Engine) BindList(nTasks int) ([]Bind, error) {
+	tasks := make([]C.uint32_t, nTasks+1)
+	nodes := make([]C.int32_t, nTasks+1)
+	var n C.uint32_t
+	if rc := C.kb_bind_list(e.h, &tasks[0], &nodes[0], &n); rc != 0 {
+		return nil, e.err("kb_bind_list", rc)
+	}
+	out := make([]Bind, int(n))
+	for i := range out {
+		out[i] = Bind{Task: uint32(tasks[i]), Node: int32(nodes[i])}
+	}
+	return out, nil
+}

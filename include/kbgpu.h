@@ -337,6 +337,13 @@ int kb_preempt(struct kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t
 int kb_cycle(struct kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decision* out, uint8_t* evicted,
              uint32_t* evict_order, uint32_t* bounds, kb_stats* stats);
 
+/* Bind fan-out: the (task, node) pairs that reach cache.Bind in the cycle just run (kb_allocate / kb_backfill /
+ * kb_cycle), in the order ssn.dispatch issues them (framework/session.go:277-314; among the tasks one ssn.JobReady releases at
+ * once — a Go map iteration in the reference — Allocate order).  Compacted and radix-sorted on the device.  A shim hands the list
+ * to ONE batched Binder call instead of a goroutine + API call per task (cache/cache.go:491-535).
+ *   task, node  [T] caller-allocated; *n receives the number of binds                                                        */
+int kb_bind_list(struct kb_engine* e, uint32_t* task, int32_t* node, uint32_t* n);
+
 /* Debug / parity: predicate + score of tasks [task_lo, task_hi) against every node in the CURRENT
  * device state (util.PredicateNodes + util.PrioritizeNodes for a task range, scheduler_helper.go:63-171).
  * fit   [(task_hi-task_lo)][N] uint8 (1 = predicateFn returned nil), may be NULL

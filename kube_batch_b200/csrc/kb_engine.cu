@@ -29,6 +29,7 @@
 #include "kb_kernels.cuh"
 #include "kb_pipe.cuh"
 #include "kb_evict_launch.h"
+#include "kb_bind.h"
 
 using namespace kb;
 
@@ -119,6 +120,8 @@ struct kb_engine {
   bool running_loaded = false;
   bool imm_dirty = false;                   // a kb_cycle rewrote parts of d_imm (job lists / order slots): re-upload before the next action from the loaded state
   uint32_t last_launches = 0;
+  unsigned char* d_bind_scratch = nullptr;  // kb_bind_list: CUB temp storage + key / value double buffers
+  size_t cap_bind_scratch = 0;
   int32_t* d_ready_start = nullptr;         // [J] ReadyTaskNum of every job when the cycle's allocate / backfill began (gang commit)
   size_t cap_ready_start = 0;
   uint32_t* h_dbg = nullptr;                // KB_PIPE_DEBUG=1: 64 progress words of cycle_kernel in mapped host memory
@@ -175,6 +178,8 @@ void free_session(kb_engine* e) {
   if (e->d_ev_mut) cudaFree(e->d_ev_mut);
   if (e->d_ev_pristine) cudaFree(e->d_ev_pristine);
   if (e->d_ready_start) cudaFree(e->d_ready_start);
+  if (e->d_bind_scratch) cudaFree(e->d_bind_scratch);
+  e->d_bind_scratch = nullptr; e->cap_bind_scratch = 0;
   e->d_ready_start = nullptr; e->cap_ready_start = 0;
   e->d_ev_imm = e->d_ev_mut = e->d_ev_pristine = nullptr; e->ev_cap_imm = e->ev_cap_mut = 0; e->running_loaded = false;
   e->d_mut = e->d_pristine = e->d_imm = nullptr; e->h_dec = nullptr;
@@ -706,6 +711,8 @@ int kb_cycle(kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decisi
   e->allocate_ran = false;
   if ((size_t)e->J * 4 > e->cap_ready_start) {
     if (e->d_ready_start) cudaFree(e->d_ready_start);
+  if (e->d_bind_scratch) cudaFree(e->d_bind_scratch);
+  e->d_bind_scratch = nullptr; e->cap_bind_scratch = 0;
     e->d_ready_start = nullptr; e->cap_ready_start = 0;
     CUDA_TRY(e, cudaMalloc(&e->d_ready_start, (size_t)std::max(1u, e->J) * 4));
     e->cap_ready_start = (size_t)std::max(1u, e->J) * 4;
@@ -798,6 +805,29 @@ int kb_reclaim(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict
 int kb_preempt(kb_engine* e, kb_decision* out, uint8_t* evicted, uint32_t* evict_order, kb_stats* stats) {
   const uint8_t a = KB_ACT_PREEMPT;
   return kb_cycle(e, &a, 1, out, evicted, evict_order, nullptr, stats);
+}
+
+int kb_bind_list(kb_engine* e, uint32_t* task, int32_t* node, uint32_t* n) {
+  if (!e || !n) return KB_E_BADARG;
+  if (!e->loaded) return fail(e, KB_E_STATE, "kb_bind_list before kb_session_load");
+  *n = 0;
+  if (e->T == 0) return KB_OK;
+  if (!task || !node) return fail(e, KB_E_BADARG, "kb_bind_list: NULL output");
+  CUDA_TRY(e, cudaSetDevice(e->device));
+  const size_t need = bind_scratch_bytes(e->T);
+  if (need > e->cap_bind_scratch) {
+    if (e->d_bind_scratch) cudaFree(e->d_bind_scratch);
+    e->d_bind_scratch = nullptr; e->cap_bind_scratch = 0;
+    CUDA_TRY(e, cudaMalloc(&e->d_bind_scratch, need + need / 4));
+    e->cap_bind_scratch = need + need / 4;
+  }
+  cudaEventRecord(e->ev0, e->stream);
+  const cudaError_t c = bind_list(e->dev.dec, e->T, e->d_bind_scratch, e->cap_bind_scratch, task, node, n, e->stream);
+  cudaEventRecord(e->ev1, e->stream);
+  if (c != cudaSuccess) return fail(e, KB_E_CUDA, "kb_bind_list: %s", cudaGetErrorString(c));
+  cudaEventSynchronize(e->ev1);
+  cudaEventElapsedTime(&e->last_kernel_ms, e->ev0, e->ev1);
+  return KB_OK;
 }
 
 int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {

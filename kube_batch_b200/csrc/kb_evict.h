@@ -49,7 +49,8 @@ struct EvictCtl {
   unsigned long long pairs_logical;
   // device plumbing of the master / worker kernel (kb_evict_kernels.cu): sweep mailbox, arg-max slot, the preemptor being
   // swept and its class (written by the master thread before it posts the command)
-  uint32_t cmd_seq, arrived, n_workers, pad0;      // master -> workers: sweep command counter (~0u = exit); workers -> master: CTAs done
+  uint32_t cmd_seq, arrived, n_workers, pad0;
+  uint32_t cls_valid, cls_id;      // class record currently in `cls`      // master -> workers: sweep command counter (~0u = exit); workers -> master: CTAs done
   unsigned long long red;
   Preemptor pre;
   ClassRec cls;
@@ -379,6 +380,7 @@ struct CpuExec {
   KB_HD void sync() {}
   KB_HD uint32_t bcast(uint32_t v) { return v; }
   KB_HD uint64_t block_max(uint64_t v) { return v; }
+  KB_HD bool jobs_scanned() const { return false; }
   KB_HD void clear_max() {}
   uint64_t sweep(const DevSession& S, const EvictDev& E, const Preemptor& P, const ClassRec& c) {      // the node axis, serially
     uint64_t best = 0;
@@ -394,20 +396,25 @@ struct CpuExec {
 // Start of an evicting action (reclaim.go:47-81, preempt.go:47-75): the action's own queues are filled from the session as it
 // is NOW — jobs in the canonical job order, Go container/heap pushes with the comparators on the current state; a job
 // enters with the tasks it still has in TaskStatusIndex[Pending].  Thread 0 only (J pushes of O(log J)).
+// WaitingTaskNum and the cursor on the first Pending task of job j, from the decision table as the earlier actions left it
+KB_HD void evict_scan_job(const DevSession& S, const EvictDev& E, const uint32_t j) {
+  int32_t w = E.job_waiting0[j];
+  uint32_t first = 0xFFFFFFFFu;
+  for (uint32_t i = E.pt_off[j]; i < E.pt_off[j + 1]; ++i) {
+    const uint32_t t = E.pt_task[i];
+    if (S.dec[t].kind == KB_KIND_PIPELINED) w += 1;                  // WaitingTaskNum (job_info.go:396-405)
+    if (first == 0xFFFFFFFFu && task_pending(S, t)) first = i - E.pt_off[j];
+  }
+  E.job_waiting[j] = w;
+  E.pt_pos[j] = first == 0xFFFFFFFFu ? E.pt_off[j + 1] - E.pt_off[j] : first;   // cursor on the first Pending task
+}
+
 template <class X>
 KB_HD void evict_init(X& x, const DevSession& S, const EvictDev& E) {
   EvictCtl& ctl = *E.ctl;
   x.sync();
-  for (uint32_t j = (uint32_t)x.tid(); j < S.J; j += (uint32_t)x.nthreads()) {
-    int32_t w = E.job_waiting0[j];
-    uint32_t first = 0xFFFFFFFFu;
-    for (uint32_t i = E.pt_off[j]; i < E.pt_off[j + 1]; ++i) {
-      const uint32_t t = E.pt_task[i];
-      if (S.dec[t].kind == KB_KIND_PIPELINED) w += 1;                  // WaitingTaskNum (job_info.go:396-405)
-      if (first == 0xFFFFFFFFu && task_pending(S, t)) first = i - E.pt_off[j];
-    }
-    E.job_waiting[j] = w;
-    E.pt_pos[j] = first == 0xFFFFFFFFu ? E.pt_off[j + 1] - E.pt_off[j] : first;   // cursor on the first Pending task
+  for (uint32_t j = (uint32_t)x.tid(); j < S.J && !x.jobs_scanned(); j += (uint32_t)x.nthreads()) {
+    evict_scan_job(S, E, j);
   }
   x.sync();
   if (x.tid() == 0) {
@@ -448,7 +455,7 @@ KB_HD bool try_preemptor(X& x, const DevSession& S, const EvictDev& E, const uin
   if (x.tid() == 0) {
     Preemptor& P = x.pre();
     P.task = task; P.job = job; P.queue = S.job_queue[job]; P.cls = E.task_class[task]; P.mode = mode;
-    x.cls() = S.classes[P.cls];
+    if (!ctl.cls_valid || ctl.cls_id != P.cls) { x.cls() = S.classes[P.cls]; ctl.cls_id = P.cls; ctl.cls_valid = 1; }      // 408 B: only when it changes
     P.ls = 0.0;
     if (mode != 0 && (E.ec.preempt_fns & EVF_DRF)) {
       double la[KB_MAX_R];

@@ -10,9 +10,11 @@
 //           predicate, K2 score for preempt, the serial victim walk of the node's Running tasks — reduce the packed keys
 //           (warp REDUX, one 64-bit atomicMax per CTA) and arrive.
 //
-// This translation unit is compiled with -Xptxas -dlcm=cg: every global load goes to L2.  The master mutates node records,
-// job / queue accounting and the Running tasks' states between two sweeps; with L1-cached loads the workers' SMs could see
-// stale lines.  (The allocate kernels keep L1 caching: their mutable tables are only read by the SM that writes them.)
+// Coherence: the master mutates node records, job / queue accounting and the Running tasks' states between two sweeps.  It
+// publishes them with a release store of the command word; thread 0 of every worker CTA reads that word with ld.acquire.gpu —
+// which invalidates the SM's L1 — before the CTA barrier that starts the sweep, so the workers' ordinary (L1-cached) loads see
+// the current tables, and nothing changes while a sweep runs.  The master's own acquire on the arrival counter does the same
+// for the workers' error word.
 #include <cuda_runtime.h>
 
 #include "kb_evict.h"
@@ -38,6 +40,7 @@ struct MasterExec {
   __device__ __forceinline__ int nthreads() const { return 1; }
   __device__ __forceinline__ void sync() {}
   __device__ __forceinline__ uint32_t bcast(uint32_t v) { return v; }
+  __device__ __forceinline__ bool jobs_scanned() const { return true; }      // evict_scan_kernel ran before this kernel
   __device__ __forceinline__ void clear_max() {}
   __device__ __forceinline__ ClassRec& cls() { return g->cls; }
   __device__ __forceinline__ Preemptor& pre() { return g->pre; }
@@ -124,6 +127,12 @@ evict_kernel(const __grid_constant__ DevSession S, const __grid_constant__ Evict
   }
 }
 
+// evict_init's per-job scan (WaitingTaskNum, first Pending task), one thread per job
+__global__ void evict_scan_kernel(const __grid_constant__ DevSession S, const __grid_constant__ EvictDev E) {
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < S.J) evict_scan_job(S, E, j);
+}
+
 cudaError_t launch_evict(const bool preempt, const DevSession& S, const EvictDev& E, const int sm_count, cudaStream_t stream) {
   // workers: one node per thread per sweep iteration, at most one CTA per SM next to the master's (co-residency: they spin)
   int workers = (int)((S.N + EVICT_THREADS - 1) / EVICT_THREADS);
@@ -133,6 +142,9 @@ cudaError_t launch_evict(const bool preempt, const DevSession& S, const EvictDev
   if (c != cudaSuccess) return c;
   c = cudaMemsetAsync(reinterpret_cast<char*>(E.ctl) + offsetof(EvictCtl, cmd_seq), 0, 8, stream);      // cmd_seq, arrived
   if (c != cudaSuccess) return c;
+  c = cudaMemsetAsync(reinterpret_cast<char*>(E.ctl) + offsetof(EvictCtl, cls_valid), 0, 4, stream);
+  if (c != cudaSuccess) return c;
+  if (S.J) evict_scan_kernel<<<(S.J + 255) / 256, 256, 0, stream>>>(S, E);
   DevSession s = S; EvictDev ev = E;
   void* args[] = {(void*)&s, (void*)&ev};
   const void* fn = preempt ? (const void*)evict_kernel<1> : (const void*)evict_kernel<0>;

@@ -18,7 +18,7 @@ LIB_PATH = os.path.join(_HERE, "libkbgpu.so")
 EXPORTS = [
     "kb_engine_create", "kb_engine_destroy", "kb_session_load", "kb_allocate", "kb_backfill", "kb_predicate_score",
     "kb_best_nodes", "kb_node_state", "kb_order_state", "kb_last_error", "kb_status_str", "kb_version",
-    "kb_nccl_unique_id", "kb_last_kernel_ms", "kb_session_load_running", "kb_reclaim", "kb_preempt", "kb_cycle",
+    "kb_nccl_unique_id", "kb_last_kernel_ms", "kb_session_load_running", "kb_reclaim", "kb_preempt", "kb_cycle", "kb_bind_list",
 ]
 
 
@@ -160,6 +160,15 @@ class Engine:
         self._check(self.L.kb_cycle(self._h, _p(acts, C.c_uint8), C.c_uint32(len(acts)), dec.ctypes.data_as(C.c_void_p), _p(ev, C.c_uint8),
                                     _p(order, C.c_uint32), _p(bounds, C.c_uint32), C.byref(st)), "kb_cycle")
         return CycleResult(dec[:T], st), ev[:n].astype(bool), order[:n], bounds[: len(acts)]
+
+    def bind_list(self):
+        """The (task, node) pairs that reach cache.Bind, in ssn.dispatch order (device-side compaction + radix sort)."""
+        T = self.snap.T
+        task = np.zeros(max(T, 1), dtype=np.uint32)
+        node = np.zeros(max(T, 1), dtype=np.int32)
+        n = C.c_uint32(0)
+        self._check(self.L.kb_bind_list(self._h, _p(task, C.c_uint32), _p(node, C.c_int32), C.byref(n)), "kb_bind_list")
+        return task[: n.value], node[: n.value]
 
     def predicate_score(self, lo: int, hi: int):
         N = self.snap.N

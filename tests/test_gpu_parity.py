@@ -192,6 +192,22 @@ def test_unknown_plugin_and_unsupported_feature_fail_loudly(eng):
     assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
 
 
+# ---------------- bind fan-out list (framework/session.go:277-314 -> cache.Bind) ----------------
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_bind_list_is_the_dispatch_order_of_the_oracle(eng, name):
+    s, conf = synth.make(name)
+    o = kbo.allocate(s, conf)
+    eng.load(s, conf)
+    eng.allocate()
+    task, node = eng.bind_list()
+    d = o.decisions
+    disp = np.nonzero(d["dispatched"] & (d["node"] >= 0))[0]
+    order = disp[np.lexsort((d["step"][disp], d["dispatch_step"][disp]))]          # by dispatch step, then Allocate order
+    np.testing.assert_array_equal(task, order.astype(np.uint32))
+    np.testing.assert_array_equal(node, d["node"][order])
+    assert len(task) == int(d["dispatched"].sum()) > 0
+
+
 # ---------------- a12 NodeAffinityPriority (node_affinity.go:34-77 + reduce.go:28-63) in cycle_kernel ----------------
 @pytest.mark.parametrize("seed", range(12))
 def test_preferred_node_affinity_on_the_gpu(eng, seed):
