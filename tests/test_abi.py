@@ -35,8 +35,8 @@ def test_struct_sizes_match_c():
 #include <stdio.h>
 #include "kbgpu.h"
 int main(void) {
-  printf("%zu %zu %zu %zu %zu %zu %zu\n", sizeof(kb_snapshot), sizeof(kb_plugin_option), sizeof(kb_tier),
-         sizeof(kb_plugin_conf), sizeof(kb_engine_opts), sizeof(kb_decision), sizeof(kb_stats));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(kb_snapshot), sizeof(kb_plugin_option), sizeof(kb_tier),
+         sizeof(kb_plugin_conf), sizeof(kb_engine_opts), sizeof(kb_decision), sizeof(kb_stats), sizeof(kb_running));
   return 0;
 }'''
     with tempfile.TemporaryDirectory() as d:
@@ -46,7 +46,7 @@ int main(void) {
         subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         sizes = [int(x) for x in subprocess.check_output([exe]).split()]
     mirrors = [abi.kb_snapshot, abi.kb_plugin_option, abi.kb_tier, abi.kb_plugin_conf, abi.kb_engine_opts,
-               abi.kb_decision, abi.kb_stats]
+               abi.kb_decision, abi.kb_stats, abi.kb_running]
     assert sizes == [C.sizeof(m) for m in mirrors]
     import numpy as np
     assert np.dtype(abi.DECISION_DTYPE).itemsize == C.sizeof(abi.kb_decision) == 16
