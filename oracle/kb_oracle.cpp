@@ -1432,6 +1432,10 @@ struct Executor {
 // actions/allocate/allocate.go:43-194
 void Execute(Session& ssn, const kbo_opts& opts, kbo_result& res) {
   auto t0 = std::chrono::steady_clock::now();
+  const int64_t warm = opts.warm_tasks > 0 ? opts.warm_tasks : 0;     // timing samples: see kbo_opts.warm_tasks
+  const int timed_mode = ssn.mode;
+  bool warming = warm > 0;
+  if (warming) ssn.mode = KBO_MODE_OPTIMISED;
   Executor ex(ssn, opts.threads);
   PriorityQueue<uint32_t> queues([&](const uint32_t& l, const uint32_t& r) { return ssn.QueueOrderFn(ssn.Queues[l], ssn.Queues[r]); });
   std::map<uint32_t, PriorityQueue<uint32_t>> jobsMap;
@@ -1471,8 +1475,9 @@ void Execute(Session& ssn, const kbo_opts& opts, kbo_result& res) {
     PriorityQueue<uint32_t>& tasks = pendingTasks.at(j);
 
     while (!tasks.Empty()) {                           // :129
-      if (opts.max_tasks > 0 && (int64_t)res.tasks_processed >= opts.max_tasks) { stop = true; res.truncated = 1; break; }
-      if (opts.max_seconds > 0) {
+      if (warming && (int64_t)res.tasks_processed >= warm) { warming = false; ssn.mode = timed_mode; t0 = std::chrono::steady_clock::now(); }
+      if (!warming && opts.max_tasks > 0 && (int64_t)res.tasks_processed - warm >= opts.max_tasks) { stop = true; res.truncated = 1; break; }
+      if (!warming && opts.max_seconds > 0) {
         double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         if (el >= opts.max_seconds) { stop = true; res.truncated = 1; break; }
       }
@@ -1503,6 +1508,8 @@ void Execute(Session& ssn, const kbo_opts& opts, kbo_result& res) {
   res.tasks_allocated = ssn.n_allocated;
   res.tasks_pipelined = ssn.n_pipelined;
   res.seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  res.timed_tasks = warming ? 0u : (uint32_t)((int64_t)res.tasks_processed - warm);
+  ssn.mode = timed_mode;
 }
 
 // actions/backfill/backfill.go:40-71.  Deterministic rules: jobs in ascending JobID, a job's Pending tasks in ascending

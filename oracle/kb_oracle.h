@@ -41,7 +41,9 @@ typedef struct kbo_opts {
   double  max_seconds;   /* >0: stop once this much wall time has elapsed (bounded timing sample)  */
   int32_t actions;       /* bit 0 allocate (default when 0), bit 1 backfill afterwards on the same session
                             ("allocate, backfill" = the default action list, pkg/scheduler/util.go:31-42)  */
-  int32_t reserved;
+  int32_t warm_tasks;    /* timing samples only: the first warm_tasks tasks run with cached aggregates (mode B), then the
+                            session switches to `mode`, the clock starts and max_tasks / max_seconds count from there — a
+                            sample of the reference's cost pattern at a later point of the cycle (more allocated pods)   */
 } kbo_opts;
 #define KBO_ACTION_ALLOCATE 1
 #define KBO_ACTION_BACKFILL 2
@@ -74,8 +76,8 @@ typedef struct kbo_result {
   uint32_t visits;
   uint32_t truncated;        /* 1 if max_tasks / max_seconds stopped the cycle early               */
   uint32_t evictions;        /* cache.Evict calls (util.FakeEvictor.Evicts)                        */
-  uint32_t reserved;
-  double   seconds;          /* wall time of Execute                                               */
+  uint32_t timed_tasks;      /* tasks processed after the warm-up (== tasks_processed when warm_tasks == 0)     */
+  double   seconds;          /* wall time of Execute (after the warm-up)                           */
 } kbo_result;
 
 /* allocateAction.Execute on the flattened snapshot.  out: T decisions.  Optional final state outputs

@@ -25,14 +25,14 @@ KBO_MODE_FAITHFUL = 1
 
 class kbo_opts(C.Structure):
     _fields_ = [("mode", C.c_int32), ("threads", C.c_int32), ("max_tasks", C.c_int64), ("max_seconds", C.c_double),
-                ("actions", C.c_int32), ("reserved", C.c_int32)]
+                ("actions", C.c_int32), ("warm_tasks", C.c_int32)]
 
 
 class kbo_result(C.Structure):
     _fields_ = [
         ("pairs_logical", C.c_uint64), ("tasks_processed", C.c_uint32), ("tasks_allocated", C.c_uint32),
         ("tasks_pipelined", C.c_uint32), ("jobs_ready", C.c_uint32), ("visits", C.c_uint32),
-        ("truncated", C.c_uint32), ("evictions", C.c_uint32), ("reserved", C.c_uint32), ("seconds", C.c_double),
+        ("truncated", C.c_uint32), ("evictions", C.c_uint32), ("timed_tasks", C.c_uint32), ("seconds", C.c_double),
     ]
 
 
@@ -105,11 +105,12 @@ KBO_ACTION_BACKFILL = 2
 
 
 def allocate(snap: Snapshot, conf: PluginConf, mode: int = KBO_MODE_OPTIMISED, threads: int = 1,
-             max_tasks: int = 0, max_seconds: float = 0.0, actions: int = KBO_ACTION_ALLOCATE) -> OracleOut:
+             max_tasks: int = 0, max_seconds: float = 0.0, actions: int = KBO_ACTION_ALLOCATE, warm_tasks: int = 0) -> OracleOut:
+    """warm_tasks (timing samples): run that many tasks with cached aggregates first, then switch to `mode` and start the clock."""
     L = lib()
     cs, keep1 = snap.to_c()
     cc, keep2 = conf.to_c()
-    o = kbo_opts(mode, threads, max_tasks, max_seconds, actions, 0)
+    o = kbo_opts(mode, threads, max_tasks, max_seconds, actions, warm_tasks)
     R, W, N, T, J, Q = snap.R, snap.W, snap.N, snap.T, snap.J, snap.Q
     dec = np.zeros(max(T, 1), dtype=np.dtype(abi.DECISION_DTYPE))
     res = kbo_result()
