@@ -824,14 +824,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     uint32_t depth = 0;                        // placements made on MY candidate
     bool cur_fi = have && (((my_h ? sm.pfi[0] : P.fi[0]) >> my_l) & 1u);
     if (lane == 0) c.scans += 1;
-    // key / fits-idle of MY candidate at depth dd (dd >= 1): precomputed chain, else the extension buffer
     const uint32_t my_lim = my_h ? (uint32_t)PIPE_PDEPTH : (uint32_t)PIPE_DEPTH;      // depths evaluated up front for MY candidate
-    auto chain_has = [&](uint32_t dd) -> bool { return dd < my_lim || (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u); };
-    auto chain_key = [&](uint32_t dd) -> uint64_t {
-      return dd < my_lim ? (my_h ? sm.pkey[dd][my_l] : P.key[dd][my_l]) : sm.ext_key[dd - sm.ext_base]; };
-    auto chain_fi = [&](uint32_t dd) -> bool {
-      return dd < my_lim ? ((((my_h ? sm.pfi[dd] : P.fi[dd]) >> my_l) & 1u) != 0) : (((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0);
-    };
     // my candidate's base record (state at depth 0): prepared buffer or hot ring
     auto load_rec0 = [&](uint64_t* r0) {
       if (my_h == 0) {
@@ -877,6 +870,21 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     const int32_t my_cnt = (is_pref && have && my_h == 0) ? P.cnt[my_l] : -1;
     uint32_t nmax_live = P.pnmax;
     bool pref_stale = false;
+
+    // Look-ahead of MY candidate: key / fits-idle of its NEXT state, kept in registers so that the owner of a pick moves on
+    // without touching memory; the refill (a shared-memory read) is off the loop's dependency chain.
+    const uint64_t* my_chain = my_h ? &sm.pkey[0][my_l] : &P.key[0][my_l];      // + d * KTOP: depth d
+    const uint32_t* my_fiw = my_h ? &sm.pfi[0] : &P.fi[0];
+    uint64_t next_key = 0;
+    bool next_fi = false, have_next = false;
+    auto refill = [&]() {                      // state at depth + 1, from the chain evaluated up front or the extension buffer
+      const uint32_t dd = depth + 1;
+      if (dd < my_lim) { next_key = my_chain[(size_t)dd * KTOP]; next_fi = ((my_fiw[dd] >> my_l) & 1u) != 0; have_next = true; }
+      else if (sm.ext_slot == slot && dd >= sm.ext_base && dd < sm.ext_base + 32u) {
+        next_key = sm.ext_key[dd - sm.ext_base]; next_fi = ((sm.ext_fi >> (dd - sm.ext_base)) & 1u) != 0; have_next = true;
+      } else have_next = false;
+    };
+    refill();
 
     bool rescanned = false;
     for (;;) {              // runs of this class (consecutive visits of one class share the pool)
@@ -928,13 +936,14 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         const uint32_t owner = (uint32_t)__ffs(__ballot_sync(FULL, cur_key == best)) - 1u;
         const bool fits_idle = ((__ballot_sync(FULL, cur_fi) >> owner) & 1u) != 0;
         const bool own = (uint32_t)lane == owner;
-        if (__any_sync(FULL, own && !chain_has(depth + 1))) extend(owner);
+        if (__any_sync(FULL, own && !have_next)) { extend(owner); if (own) refill(); }      // rare: chain exhausted
         bool left_max = false;
         if (own) {                                 // ssn.Allocate / ssn.Pipeline: my candidate moves to its next state
           depth += 1;
-          cur_key = chain_key(depth);
-          cur_fi = chain_fi(depth);
+          cur_key = next_key;
+          cur_fi = next_fi;
           if (PREF) left_max = is_pref && cur_key == 0 && my_cnt == (int32_t)P.pmax;      // a max-count node left the feasible set
+          refill();
         }
         if (lane == 0) sm.step_rec[placed & 31u] = owner | (fits_idle ? 32u : 0u);
         placed += 1;
@@ -945,6 +954,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (jr && (pos0 + popped < jend)) { reason = STOP_YIELD; break; }             // allocate.go:185-188
         if (PREF && pref_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
       }
+      const long long t_loop1 = timing ? clock64() : 0;
       __syncwarp();
       if (flushed < placed) flush(placed);
       for (uint32_t z = 0; z < placed; ++z) { jalloc = KB_DADD(jalloc, my_rq); qalloc = KB_DADD(qalloc, my_rq); }      // AllocateFunc handlers, in order
@@ -989,6 +999,8 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (timing) {
           const long long t_run2 = clock64();
           c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
+          c.cyc_merge += (unsigned long long)(t_loop1 - t_run0);      // the step loop alone
+          c.predictions += 1; c.mispredictions += popped;               // runs, step iterations (timing mode only)
           c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
         }
       }
