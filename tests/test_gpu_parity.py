@@ -330,6 +330,17 @@ def check_committed_digest(eng, name, r):
     assert digest.state_digest(ns["idle"], ns["releasing"], osr["job_ready"], osr["job_share"]) == g["state"], name + ": state digest"
 
 
+def test_c5_shaped_session_at_one_fiftieth_scale(eng):
+    """BASELINE config 5 (1M tasks x 100k nodes, one node shape) is too large for the CPU oracle; its SHAPE is not: the same
+    generator at 1/50 scale (20k tasks / 2k PodGroups / 2k homogeneous nodes, gang + drf + predicates + nodeorder) with full
+    oracle parity, and at 12 500 nodes (several resident tiles per scanner CTA... 98 tiles on 98 SMs) as well."""
+    for scale, nodes in ((50, 2_000), (8, 12_500)):
+        spec = synth.SynthSpec(f"c5/{scale}", tasks=1_000_000 // scale, jobs=100_000 // scale, nodes=nodes, homogeneous_nodes=True, seed=0xB200 + 5)
+        s = synth.generate(spec)
+        conf = synth.config_conf("c5")
+        run_and_check(eng, s, conf, f"c5 shape 1/{scale}")
+
+
 def test_c4_multiqueue_full_size_parity(eng):
     """BASELINE config 4 (200k tasks x 20k nodes, 8 queues with proportion): exact Go-heap replay with stale keys at scale.
     The oracle runs here as well (about a minute on 16 host threads)."""
