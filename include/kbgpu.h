@@ -267,6 +267,8 @@ typedef struct kb_stats {
   uint32_t pipe_patch_entries; /* log entries re-evaluated by those patches                                  */
   uint32_t evictions;       /* kb_reclaim / kb_preempt: cache.Evict calls                                            */
   uint32_t evict_sweeps;    /*   node sweeps executed (identical failing sweeps of one job are skipped)              */
+  uint64_t cyc_ring;        /* cycle_kernel, KB_PIPE_TIMING=1: main-warp cycles from the end of the runs to the write-back command (hot ring) */
+  uint64_t cyc_plan;        /*   ... and in the planner (scan requests for the next visits)                           */
 } kb_stats;
 
 /* Replaces nothing in the reference (process start-up): binds a CUDA device, creates the stream,

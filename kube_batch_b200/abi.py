@@ -197,6 +197,8 @@ class kb_stats(C.Structure):
         ("pipe_patch_entries", C.c_uint32),
         ("evictions", C.c_uint32),
         ("evict_sweeps", C.c_uint32),
+        ("cyc_ring", C.c_uint64),
+        ("cyc_plan", C.c_uint64),
     ]
 
 

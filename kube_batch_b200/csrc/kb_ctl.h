@@ -59,6 +59,7 @@ struct Ctl {
   uint32_t pipe_requests, pipe_urgent, pipe_extends, pipe_patched, pipe_patch_entries;
   uint32_t phantoms;      // backfill: tasks left Allocated on no node (ssn.Allocate sets the status before node.AddTask refuses, session.go:241-262)
   unsigned long long cyc_wait;     // replayer cycles spent between posting the visit and the eval warps' results (list wait + eval)
+  unsigned long long cyc_ring, cyc_plan;      // timing mode: hot-ring append + write-back command; planner
 };
 
 // ---- persistent pipeline: global mailboxes between the replayer CTA and the scanner CTAs (kb_pipe.cuh) ----

@@ -1009,6 +1009,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     }
 
     if (lane == 0) { dbg_put(S.dbg, 1, 5u); dbg_put(S.dbg, 7, c.rescans); }
+    const long long t_r0 = timing ? clock64() : 0;
     // ---------------- end of the visit chain on this class: modified candidates -> hot ring + log ----------------
     const bool modified = depth > 0;
     const unsigned mm = __ballot_sync(FULL, modified);
@@ -1030,6 +1031,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       priv_head += nmod;
     }
     if (rescanned) fresh_floor = priv_head;
+    const long long t_r1 = timing ? clock64() : 0;
     if (lane == 0) dbg_put(S.dbg, 1, 6u);
     // ---------------- planner: scan requests for the classes of the next visits ----------------
     if (!c.done) {
@@ -1065,6 +1067,8 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       c.cyc_wait += (unsigned long long)(t_v1 - t_v0);
       c.cyc_scan += (unsigned long long)(t_v1 - t_v0);
       c.cyc_replay += (unsigned long long)(t_end - t_v1);
+      c.cyc_ring += (unsigned long long)(t_r1 - t_r0);
+      c.cyc_plan += (unsigned long long)(t_end - t_r1);
     }
     __syncwarp();
   }
