@@ -70,6 +70,27 @@ __device__ __forceinline__ void ld_relaxed_2u64(const unsigned long long* p, uns
 }
 // progress word -> mapped host memory (debug builds of a session only; a store, so it never stalls the warp)
 __device__ __forceinline__ void dbg_put(uint32_t* dbg, int i, uint32_t v) { if (dbg) *((volatile uint32_t*)(dbg + i)) = v; }
+// Shared-memory mailboxes of the replayer CTA: ONE 8- or 16-byte word carries tag + payload, written / read by a single thread
+// with a single access, so producer and consumer need no fence (a MEMBAR.SC.CTA on the main warp also waits for its
+// outstanding global stores: hundreds of cycles per command).  Data a mailbox word announces (hot ring entries) was stored by
+// the same warp before it; shared-memory accesses of one warp are performed in issue order.
+__device__ __forceinline__ void sts_v4(void* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+  asm volatile("st.volatile.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ uint4 lds_v4(const void* p) {
+  uint4 v;
+  asm volatile("ld.volatile.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u64(void* p, unsigned long long v) {
+  asm volatile("st.volatile.shared.u64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(p)), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_u64(const void* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.shared.u64 %0, [%1];" : "=l"(v) : "r"((uint32_t)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void compiler_fence() { asm volatile("" ::: "memory"); }
 __device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 // record held in registers (column c at r[c]); NC = tile_ncols(R, W) is a compile-time constant here
@@ -407,13 +428,13 @@ struct ReplaySmem {
   uint64_t hot_rec[NC][PIPE_HOT];
   // requested table (request seq lives at seq % PIPE_RQ, and so does its prepared list)
   uint32_t rq_cls[PIPE_RQ], rq_seq[PIPE_RQ], rq_stamp[PIPE_RQ];
-  uint32_t rq_posted;                          // requests entered into the table (volatile: main -> prep teams)
+  unsigned long long rq_word[PIPE_RQ];         // (seq + 1) << 32 | class: request seq exists (one word, main -> prep teams)
   uint32_t pb_ready[PIPE_RQ];                  // seq + 1 once pb[seq % PIPE_RQ] holds request seq (volatile: prep -> main)
   uint32_t prep_done[PIPE_PREP_TEAMS];         // requests a team has finished (its next seq; volatile)
   uint32_t prep_status[PIPE_PREP_TEAMS];       // warp 0 of a team -> its other warps
   // main -> writer command ring
-  uint32_t cmd_kind[PIPE_CMDS], cmd_a[PIPE_CMDS], cmd_b[PIPE_CMDS];
-  uint32_t cmd_head, cmd_tail;                 // volatile: written by main / by the writer
+  uint4 cmd[PIPE_CMDS];                        // {index + 1, kind, a, b}: one 16-byte word per command
+  uint32_t cmd_tail;                           // commands the writer has finished (volatile)
   uint32_t pub_head;                           // log entries the writer has published (volatile)
   uint32_t sink;
   PrepBuf<NC> pb[PIPE_RQ];
@@ -474,21 +495,24 @@ __device__ __forceinline__ void pipe_prep_warp(const DevSession& S, ReplaySmem<2
       // warp 0 of the team waits (for the request to exist, then for the scanners' answer) and decides for the team, so that
       // all four warps leave together when the cycle ends
       uint32_t status = 0;                      // 0 ok, 1 quit, 2 timeout (kept warp-uniform)
+      uint32_t rcls = 0;
       if (lane == 0) {
-        while ((int32_t)(*((volatile uint32_t*)&sm.rq_posted) - seq) <= 0) {
+        unsigned long long rw;
+        while ((uint32_t)((rw = lds_u64(&sm.rq_word[idx])) >> 32) != tag) {
           if (*((volatile uint32_t*)&sm.v_quit)) { status = 1; break; }
           __nanosleep(40);
         }
+        rcls = (uint32_t)rw;
       }
       status = __shfl_sync(FULL, status, 0);
+      rcls = __shfl_sync(FULL, rcls, 0);
       unsigned long long w0 = 0, w1 = 0;
       if (status == 0) {
-        __threadfence_block();
-        const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[sm.rq_cls[idx]]);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[rcls]);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&P.cls);
         for (uint32_t i = lane; i < sizeof(ClassRec) / 4; i += 32) dst[i] = __ldg(src + i);
         if (PREF && S.class_pref) {
-          const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[sm.rq_cls[idx]]);
+          const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[rcls]);
           uint32_t* pd = reinterpret_cast<uint32_t*>(&P.pref);
           for (uint32_t i = lane; i < sizeof(ClassPref) / 4; i += 32) pd[i] = __ldg(ps + i);
         } else if (lane == 0) P.pref.n = 0;
@@ -632,9 +656,9 @@ __device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem
   PipeG* pg = S.pg;
   uint32_t tail = 0;
   for (;;) {
-    while (*((volatile uint32_t*)&sm.cmd_head) == tail) __nanosleep(40);
-    __threadfence_block();
-    const uint32_t kind = sm.cmd_kind[tail % PIPE_CMDS], a = sm.cmd_a[tail % PIPE_CMDS], b = sm.cmd_b[tail % PIPE_CMDS];
+    uint4 cw;
+    while ((cw = lds_v4(&sm.cmd[tail % PIPE_CMDS])).x != tail + 1) __nanosleep(40);
+    const uint32_t kind = cw.y, a = cw.z, b = cw.w;
     if (kind == PCMD_WB) {
       // log entries [a, b): record -> global table, Used += cnt x Resreq (node_info.go:203), node id -> modlog
       for (uint32_t base = a; base < b; base += 32) {
@@ -687,9 +711,10 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   Ctl* gctl = S.ctl;
   if (warp == 0) {
     load_ctl(sm.ctl, gctl, lane);
-    if (lane < (int)PIPE_RQ) { sm.rq_cls[lane] = 0xFFFFFFFFu; sm.rq_seq[lane] = 0; sm.rq_stamp[lane] = 0; sm.pb_ready[lane] = 0; }
+    if (lane < (int)PIPE_RQ) { sm.rq_cls[lane] = 0xFFFFFFFFu; sm.rq_seq[lane] = 0; sm.rq_stamp[lane] = 0; sm.pb_ready[lane] = 0; sm.rq_word[lane] = 0ull; }
+    for (uint32_t i = lane; i < PIPE_CMDS; i += 32) sm.cmd[i] = make_uint4(0u, 0u, 0u, 0u);
     if (lane < PIPE_PREP_TEAMS) sm.prep_done[lane] = (uint32_t)lane;
-    if (lane == 0) { sm.cmd_head = 0; sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.v_count = 0; sm.rq_posted = 0; sm.ext_slot = 0xFFFFFFFFu; }
+    if (lane == 0) { sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.v_count = 0; sm.ext_slot = 0xFFFFFFFFu; }
   }
   __syncthreads();
   if (warp >= PIPE_W_PATCH0 && warp < PIPE_W_PATCH0 + PIPE_PDEPTH) { pipe_patch_warp<RR, WW>(S, sm, warp - PIPE_W_PATCH0, lane); return; }
@@ -706,15 +731,11 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   uint32_t cmd_head = 0;
   uint32_t fresh_floor = 0;      // after a rescan stop: only a list requested at or after this log position will do
   bool failed = false;
+  uint32_t n_requests = 0;       // lane 0: requests posted, added to the statistics at the end
   auto push_cmd = [&](uint32_t kind, uint32_t a, uint32_t b) {       // whole warp calls it
     while (cmd_head - *((volatile uint32_t*)&sm.cmd_tail) >= PIPE_CMDS) __nanosleep(20);
-    if (lane == 0) {
-      sm.cmd_kind[cmd_head % PIPE_CMDS] = kind; sm.cmd_a[cmd_head % PIPE_CMDS] = a; sm.cmd_b[cmd_head % PIPE_CMDS] = b;
-      __threadfence_block();
-      *((volatile uint32_t*)&sm.cmd_head) = cmd_head + 1;
-    }
+    if (lane == 0) sts_v4(&sm.cmd[cmd_head % PIPE_CMDS], cmd_head + 1, kind, a, b);
     cmd_head += 1;
-    __syncwarp();
   };
   // newest request for class `cls` in the requested table: returns found; seq / stamp by reference
   auto rq_lookup = [&](uint32_t cls, uint32_t& seq, uint32_t& stamp) -> bool {
@@ -727,28 +748,30 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     stamp = __shfl_sync(FULL, m ? sm.rq_stamp[lane] : 0u, src);
     return true;
   };
+  const bool timing = (S.pipe_pad & 1u) != 0;       // KB_PIPE_TIMING=1: clock64 phase timers of the main warp (kb_stats.cyc_*)
   auto post_request = [&](uint32_t cls) -> uint32_t {
+    const long long t_p0 = timing ? clock64() : 0;
     const uint32_t seq = next_seq++;
     // the table entry / prepared buffer of request seq - PIPE_RQ is recycled: its team must be through with it
-    if (seq >= PIPE_RQ) {
-      const long long deadline = clock64() + PIPE_DEADLINE;
+    if (seq >= PIPE_RQ && (int32_t)(*((volatile uint32_t*)&sm.prep_done[seq % PIPE_PREP_TEAMS]) - (seq - PIPE_RQ)) <= 0) {
+      const long long t_w0 = clock64(), deadline = t_w0 + PIPE_DEADLINE;
       while ((int32_t)(*((volatile uint32_t*)&sm.prep_done[seq % PIPE_PREP_TEAMS]) - (seq - PIPE_RQ)) <= 0) {
         if (clock64() > deadline) { failed = true; break; }
         __nanosleep(20);
       }
+      if (timing && lane == 0) { c.cyc_merge += (unsigned long long)(clock64() - t_w0); c.mispredictions += 1; }
     }
     if (lane == 0) {
       sm.rq_cls[seq % PIPE_RQ] = cls; sm.rq_seq[seq % PIPE_RQ] = seq; sm.rq_stamp[seq % PIPE_RQ] = priv_head;
-      c.pipe_requests += 1; c.pairs_scanned += (unsigned long long)S.N;
-      __threadfence_block();
-      *((volatile uint32_t*)&sm.rq_posted) = seq + 1;
+      n_requests += 1;
+      sts_u64(&sm.rq_word[seq % PIPE_RQ], ((unsigned long long)(seq + 1) << 32) | cls);
     }
-    __syncwarp();
+    const long long t_p1 = timing ? clock64() : 0;
     push_cmd(PCMD_REQ, cls, seq);
+    if (timing && lane == 0) { c.cyc_total += (unsigned long long)(t_p1 - t_p0); c.chain_hits += 1; }
     return seq;
   };
 
-  const bool timing = (S.pipe_pad & 1u) != 0;       // KB_PIPE_TIMING=1: clock64 phase timers of the main warp (kb_stats.cyc_*)
   const long long t_cycle0 = clock64();
   while (!c.done && !failed) {
     const uint32_t cls_id = c.cur_class;
@@ -766,11 +789,13 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     const uint32_t pbi = seq % PIPE_RQ;
     if (lane == 0) { dbg_put(S.dbg, 1, 2u); dbg_put(S.dbg, 3, seq); dbg_put(S.dbg, 4, stamp); dbg_put(S.dbg, 5, priv_head); dbg_put(S.dbg, 6, next_seq); }
     {
-      const long long deadline = clock64() + PIPE_DEADLINE;
+      const long long t_b0 = clock64(), deadline = t_b0 + PIPE_DEADLINE;
+      if (timing && lane == 0 && *((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) c.predictions += 1;
       while (*((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) {
         if (clock64() > deadline || *((volatile uint32_t*)&sm.v_err)) { failed = true; break; }
       }
-      __threadfence_block();
+      compiler_fence();          // pb[pbi] was stored before pb_ready by its team (fence + barrier on their side)
+      if (timing && lane == 0) c.cyc_ctl += (unsigned long long)(clock64() - t_b0);
     }
     if (failed) break;
     const PrepBuf<NC>& P = sm.pb[pbi];
@@ -999,9 +1024,7 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (timing) {
           const long long t_run2 = clock64();
           c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
-          c.cyc_merge += (unsigned long long)(t_loop1 - t_run0);      // the step loop alone
-          c.predictions += 1; c.mispredictions += popped;               // runs, step iterations (timing mode only)
-          c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
+          c.predictions += 1;               // runs, step iterations (timing mode only)
         }
       }
       __syncwarp();
@@ -1010,6 +1033,16 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
 
     if (lane == 0) { dbg_put(S.dbg, 1, 5u); dbg_put(S.dbg, 7, c.rescans); }
     const long long t_r0 = timing ? clock64() : 0;
+    // the planner's inputs (static-order classes of the runs after the next visit): loads issued now, used after the ring append
+    uint32_t pc[KB_CHAIN_MAX];
+    pc[0] = c.cur_class;
+#pragma unroll
+    for (uint32_t k = 1; k < KB_CHAIN_MAX; ++k) pc[k] = 0xFFFFFFFFu;
+    if (!c.done) {
+      const uint32_t s1 = S.job_pos[(uint32_t)c.cur_job];
+#pragma unroll
+      for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX; ++k) pc[k + 1] = S.ord_chain[(size_t)s1 * (KB_CHAIN_MAX - 1) + k];
+    }
     // ---------------- end of the visit chain on this class: modified candidates -> hot ring + log ----------------
     const bool modified = depth > 0;
     const unsigned mm = __ballot_sync(FULL, modified);
@@ -1035,14 +1068,10 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     if (lane == 0) dbg_put(S.dbg, 1, 6u);
     // ---------------- planner: scan requests for the classes of the next visits ----------------
     if (!c.done) {
-      uint32_t pc[KB_CHAIN_MAX];
-      pc[0] = c.cur_class;
-      {
-        const uint32_t s0 = lane == 0 ? S.job_pos[(uint32_t)c.cur_job] : 0u;
-        const uint32_t s1 = __shfl_sync(FULL, s0, 0);
+      // the chain's classes are distinct, so no post below changes a later lookup: all lookups first (they overlap), then the posts
+      uint32_t ls[KB_CHAIN_MAX], lst[KB_CHAIN_MAX]; bool lf[KB_CHAIN_MAX];
 #pragma unroll
-        for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX; ++k) pc[k + 1] = S.ord_chain[(size_t)s1 * (KB_CHAIN_MAX - 1) + k];
-      }
+      for (uint32_t k = 0; k < KB_CHAIN_MAX; ++k) { ls[k] = 0; lst[k] = 0; lf[k] = rq_lookup(pc[k], ls[k], lst[k]); }
 #pragma unroll
       for (uint32_t k = 0; k < KB_CHAIN_MAX; ++k) {
         const uint32_t pcls = pc[k];
@@ -1051,20 +1080,17 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (PREF && S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[pcls].n != 0) {
           // preferred terms: only a list of the table state at its use will do — request the next visit's now, nothing further ahead
           if (k != 0) continue;
-          uint32_t s3 = 0, st3 = 0;
-          if (!(rq_lookup(pcls, s3, st3) && st3 == priv_head)) post_request(pcls);
+          if (!(lf[k] && lst[k] == priv_head)) post_request(pcls);
           continue;
         }
-        uint32_t s2 = 0, st2 = 0;
-        const bool f = rq_lookup(pcls, s2, st2);
-        const uint32_t age = priv_head - st2;
+        const bool f = lf[k];
+        const uint32_t age = priv_head - lst[k];
         const bool ok = f && (k == 0 ? age <= PIPE_PATCH : age + 8u * k <= 24u);
         if (!ok) post_request(pcls);
       }
     }
     if (lane == 0 && timing) {
       const long long t_end = clock64();
-      c.cyc_wait += (unsigned long long)(t_v1 - t_v0);
       c.cyc_scan += (unsigned long long)(t_v1 - t_v0);
       c.cyc_replay += (unsigned long long)(t_end - t_v1);
       c.cyc_ring += (unsigned long long)(t_r1 - t_r0);
@@ -1081,7 +1107,8 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   push_cmd(PCMD_QUIT, 0, 0);
   while (*((volatile uint32_t*)&sm.cmd_tail) != cmd_head - 1 + 0u && *((volatile uint32_t*)&sm.cmd_tail) != cmd_head) __nanosleep(40);
   if (lane == 0) {
-    c.cyc_total += (unsigned long long)(clock64() - t_cycle0);
+    if (!timing) c.cyc_total += (unsigned long long)(clock64() - t_cycle0);
+    c.pipe_requests += n_requests; c.pairs_scanned += (unsigned long long)n_requests * S.N;
     if ((failed || *((volatile uint32_t*)&sm.v_err)) && !c.error) c.error = 3;
     const uint32_t perr = ld_relaxed_u32(&pg->error);
     if (perr && !c.error) c.error = perr;
