@@ -35,22 +35,32 @@ namespace kb {
 constexpr int PIPE_DEPTH = 8;              // placement depths a prep team evaluates per list entry (ahead of the visit)
 constexpr int PIPE_PDEPTH = 4;             // ... and the patch warps per patch entry (on the visit's critical path: kept short;
                                            //     deeper states of a candidate come from the chain extension)
-// replayer CTA warp roles: 0 main, 1..4 patch warps (one per depth), then the prep teams, the writer, the shadow prefetch;
-// the remaining warps exit.  scanner CTAs: 0..15 scan groups, 16 applier.
-constexpr int PIPE_W_PATCH0 = 1;
+// replayer CTA warp roles.  A warp's scheduler (SM sub-partition) is warp % 4: the main warp (0) shares its scheduler only with
+// the patch warps (4, 8, 12, 16), which run while it waits at their barrier; the prep teams, the writer / planner and the shadow
+// prefetch sit on the other three.  scanner CTAs: 0..15 scan groups, 16 applier.
 constexpr int PIPE_PREP_TEAMS = 2, PIPE_PREP_TW = 4;
-constexpr int PIPE_W_PREP0 = PIPE_W_PATCH0 + PIPE_PDEPTH;
-constexpr int PIPE_W_WRITER = PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW;
-constexpr int PIPE_W_SHADOW = PIPE_W_WRITER + 1;
-constexpr int PIPE_WARPS = (PIPE_W_SHADOW + 1) > 17 ? (PIPE_W_SHADOW + 1) : 17;      // the scanner CTAs need 16 scan warps + the applier
+constexpr int PIPE_WARPS = 17;
 constexpr int PIPE_THREADS = PIPE_WARPS * 32;
+enum PipeRole : int { ROLE_MAIN = 0, ROLE_PATCH = 1, ROLE_PREP = 2, ROLE_WRITER = 3, ROLE_SHADOW = 4, ROLE_NONE = 5 };
+__device__ __forceinline__ void pipe_role(const int warp, int& role, int& idx) {
+  idx = 0;
+  if (warp == 0) { role = ROLE_MAIN; return; }
+  if ((warp & 3) == 0) { role = ROLE_PATCH; idx = (warp >> 2) - 1; return; }                // 4, 8, 12, 16 -> depth 0..3
+  const int r = warp - 1 - (warp >> 2);                                                      // 1,2,3,5,6,7,9,10,11,13,14,15 -> 0..11
+  if (r < PIPE_PREP_TEAMS * PIPE_PREP_TW) { role = ROLE_PREP; idx = r; return; }
+  if (r == PIPE_PREP_TEAMS * PIPE_PREP_TW) { role = ROLE_WRITER; return; }
+  if (r == PIPE_PREP_TEAMS * PIPE_PREP_TW + 1) { role = ROLE_SHADOW; return; }
+  role = ROLE_NONE;
+}
+static_assert(PIPE_PDEPTH == 4 && PIPE_PREP_TEAMS * PIPE_PREP_TW + 2 <= 12, "warp roles of the replayer CTA");
 static_assert(PIPE_DEPTH % PIPE_PREP_TW == 0, "a prep warp owns depths w, w + TW, ...");
 constexpr uint32_t PIPE_HOT = 128;         // hot ring: records of the most recent log entries (replayer shared memory)
 constexpr uint32_t PIPE_RQ = 16;           // requested-table entries (most recent scan requests)
 constexpr uint32_t PIPE_CMDS = 64;
 constexpr long long PIPE_DEADLINE = 3000000000ll;     // cycles a wait may take before the cycle is aborted (error 3)
 
-enum PipeCmd : uint32_t { PCMD_WB = 1, PCMD_REQ = 2, PCMD_QUIT = 3 };
+enum PipeCmd : uint32_t { PCMD_WB = 1, PCMD_PLAN = 2, PCMD_QUIT = 3 };
+constexpr uint32_t PLAN_FORCE_BIT = 4u;      // PCMD_PLAN word: kind | PLAN_FORCE_BIT (request the next visit's class whatever the table holds) | job << 3
 
 // ---- memory-model helpers ----
 __device__ __forceinline__ uint32_t ld_relaxed_u32(const uint32_t* p) {
@@ -427,7 +437,11 @@ struct ReplaySmem {
   uint32_t hot_node[PIPE_HOT], hot_cnt[PIPE_HOT], hot_cls[PIPE_HOT];
   uint64_t hot_rec[NC][PIPE_HOT];
   // requested table (request seq lives at seq % PIPE_RQ, and so does its prepared list)
-  uint32_t rq_cls[PIPE_RQ], rq_seq[PIPE_RQ], rq_stamp[PIPE_RQ];
+  // {class, seq + 1 (0 = empty), stamp, 0}: one 16-byte word per entry, written by the planner (writer warp), read by main
+  uint4 rq_ent[PIPE_RQ];
+  uint32_t in_use;                             // seq + 1 of the prepared list the main warp is replaying (volatile: main -> planner)
+  uint32_t posting;                            // seq + 1 of the request the planner is entering (volatile: planner -> main)
+  uint32_t n_requests;                         // planner -> main at PCMD_QUIT
   unsigned long long rq_word[PIPE_RQ];         // (seq + 1) << 32 | class: request seq exists (one word, main -> prep teams)
   uint32_t pb_ready[PIPE_RQ];                  // seq + 1 once pb[seq % PIPE_RQ] holds request seq (volatile: prep -> main)
   uint32_t prep_done[PIPE_PREP_TEAMS];         // requests a team has finished (its next seq; volatile)
@@ -650,15 +664,61 @@ __device__ __forceinline__ void pipe_shadow_warp(const DevSession& S, ReplaySmem
 }
 
 // writer / planner warp: write-backs, log, requests — everything that needs a membar, off the replay's critical path
-template <int RR, int WW>
+// newest request for class `cls` in the requested table (whole warp): found; seq / stamp by reference
+template <int NC>
+__device__ __forceinline__ bool rq_find(const ReplaySmem<NC>& sm, const int lane, const uint32_t cls, uint32_t& seq, uint32_t& stamp) {
+  uint4 e = make_uint4(0u, 0u, 0u, 0u);
+  if (lane < (int)PIPE_RQ) e = lds_v4(&sm.rq_ent[lane]);
+  const bool m = e.y != 0u && e.x == cls;
+  const uint32_t s1 = m ? e.y : 0u;
+  const uint32_t best = __reduce_max_sync(FULL, s1);
+  if (best == 0) return false;
+  const int src = __ffs(__ballot_sync(FULL, m && s1 == best)) - 1;
+  seq = best - 1u;
+  stamp = __shfl_sync(FULL, e.z, src);
+  return true;
+}
+
+template <int RR, int WW, int PREF>
 __device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem<2 * RR + 6 + 3 * WW>& sm, const int lane) {
   constexpr uint32_t R = RR, NC = 2 * RR + 6 + 3 * WW;
   PipeG* pg = S.pg;
   uint32_t tail = 0;
+  uint32_t next_seq = 0;         // scan requests posted
+  // Enter request next_seq for class `cls`: table entry, the prep team's word, the scanners' slot.  The prepared buffer and the
+  // table entry of request seq - PIPE_RQ are recycled: its team must be through with it, and the main warp must not be replaying
+  // it.  Both sides write their word, fence, then read the other's (main: in_use then posting + entry; here: posting then in_use),
+  // so at least one of them sees the other and steps back; a request that steps back is simply not made (a later plan repeats it).
+  auto post = [&](const uint32_t cls, const uint32_t head) {
+    const uint32_t seq = next_seq;
+    if (seq >= PIPE_RQ) {
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      while ((int32_t)(*((volatile uint32_t*)&sm.prep_done[seq % PIPE_PREP_TEAMS]) - (seq - PIPE_RQ)) <= 0) {
+        if (clock64() > deadline) { *((volatile uint32_t*)&sm.v_err) = 1; return; }
+        __nanosleep(20);
+      }
+    }
+    uint32_t ok = 1;
+    if (lane == 0) {
+      *((volatile uint32_t*)&sm.posting) = seq + 1;
+      __threadfence_block();
+      if (seq >= PIPE_RQ && *((volatile uint32_t*)&sm.in_use) == seq + 1 - PIPE_RQ) { *((volatile uint32_t*)&sm.posting) = 0; ok = 0; }
+      else {
+        sts_v4(&sm.rq_ent[seq % PIPE_RQ], cls, seq + 1, head, 0u);
+        sts_u64(&sm.rq_word[seq % PIPE_RQ], ((unsigned long long)(seq + 1) << 32) | cls);
+        // the slot's previous request (seq - PIPE_RING) was consumed by its prep team long ago (PIPE_RQ <= PIPE_RING)
+        const unsigned long long tag = (unsigned long long)(seq + 1) << 32;
+        st_relaxed_u64(&pg->req[seq % PIPE_RING][1], tag | head);
+        st_relaxed_u64(&pg->req[seq % PIPE_RING][0], tag | cls);
+        *((volatile uint32_t*)&sm.posting) = 0;
+      }
+    }
+    if (__shfl_sync(FULL, ok, 0)) next_seq = seq + 1;
+  };
   for (;;) {
     uint4 cw;
     while ((cw = lds_v4(&sm.cmd[tail % PIPE_CMDS])).x != tail + 1) __nanosleep(40);
-    const uint32_t kind = cw.y, a = cw.z, b = cw.w;
+    const uint32_t kind = cw.y & 3u, a = cw.z, b = cw.w;
     if (kind == PCMD_WB) {
       // log entries [a, b): record -> global table, Used += cnt x Resreq (node_info.go:203), node id -> modlog
       for (uint32_t base = a; base < b; base += 32) {
@@ -681,18 +741,36 @@ __device__ __forceinline__ void pipe_writer_warp(const DevSession& S, ReplaySmem
       }
       __syncwarp();
       if (lane == 0) { st_release_u32(&pg->log_head, b); *((volatile uint32_t*)&sm.pub_head) = b; }
-    } else if (kind == PCMD_REQ) {
-      // a = class, b = seq.  The slot's previous request (seq - PIPE_RING) was consumed by its prep team long ago: main does
-      // not enter request seq into the table before the team has finished seq - PIPE_RQ (PIPE_RQ <= PIPE_RING).
-      const uint32_t slot = b % PIPE_RING;
-      if (lane == 0) {
-        const unsigned long long tag = (unsigned long long)(b + 1) << 32;
-        const uint32_t stamp = *((volatile uint32_t*)&sm.pub_head);
-        st_relaxed_u64(&pg->req[slot][1], tag | stamp);
-        st_relaxed_u64(&pg->req[slot][0], tag | a);
+    } else if (kind == PCMD_PLAN) {
+      // planner: scan requests for the class of the next visit (a; PLAN_FORCE = whatever the table holds) and for the classes
+      // of the runs after it in the static order of the next job's queue.  b = the log position the next visit starts from
+      // (published: the visit's write-back command precedes this one).
+      const uint32_t force = cw.y & PLAN_FORCE_BIT, head = b;
+      uint32_t pc[KB_CHAIN_MAX];
+      pc[0] = a;
+      {
+        const uint32_t s1 = S.job_pos[cw.y >> 3];
+#pragma unroll
+        for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX; ++k) pc[k + 1] = S.ord_chain[(size_t)s1 * (KB_CHAIN_MAX - 1) + k];
+      }
+#pragma unroll
+      for (uint32_t k = 0; k < KB_CHAIN_MAX; ++k) {
+        const uint32_t pcls = pc[k];
+        if (pcls == 0xFFFFFFFFu) continue;
+        if (k == 0 && force) { post(pcls, head); continue; }
+        const uint32_t amax = k == 0 ? PIPE_PATCH : ((S.pipe_pad >> (8u * k)) & 255u);
+        if (amax == 255u) continue;
+        uint32_t s2 = 0, st2 = 0;
+        const bool f = rq_find<NC>(sm, lane, pcls, s2, st2);
+        if (PREF && S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[pcls].n != 0) {
+          // preferred terms: only a list of the table state at its use will do — request the next visit's now, nothing further ahead
+          if (k == 0 && !(f && st2 == head)) post(pcls, head);
+          continue;
+        }
+        if (!(f && head - st2 <= amax)) post(pcls, head);
       }
     } else {   // PCMD_QUIT
-      if (lane == 0) st_release_u32(&pg->quit, 1u);
+      if (lane == 0) { st_release_u32(&pg->quit, 1u); sm.n_requests = next_seq; __threadfence_block(); *((volatile uint32_t*)&sm.cmd_tail) = tail + 1; }
       return;
     }
     tail += 1;
@@ -711,66 +789,47 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   Ctl* gctl = S.ctl;
   if (warp == 0) {
     load_ctl(sm.ctl, gctl, lane);
-    if (lane < (int)PIPE_RQ) { sm.rq_cls[lane] = 0xFFFFFFFFu; sm.rq_seq[lane] = 0; sm.rq_stamp[lane] = 0; sm.pb_ready[lane] = 0; sm.rq_word[lane] = 0ull; }
+    if (lane < (int)PIPE_RQ) { sm.rq_ent[lane] = make_uint4(0u, 0u, 0u, 0u); sm.pb_ready[lane] = 0; sm.rq_word[lane] = 0ull; }
     for (uint32_t i = lane; i < PIPE_CMDS; i += 32) sm.cmd[i] = make_uint4(0u, 0u, 0u, 0u);
     if (lane < PIPE_PREP_TEAMS) sm.prep_done[lane] = (uint32_t)lane;
-    if (lane == 0) { sm.cmd_tail = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.v_count = 0; sm.ext_slot = 0xFFFFFFFFu; }
+    if (lane == 0) { sm.cmd_tail = 0; sm.in_use = 0; sm.posting = 0; sm.n_requests = 0; sm.pub_head = 0; sm.v_quit = 0; sm.v_err = 0; sm.v_count = 0; sm.ext_slot = 0xFFFFFFFFu; }
   }
   __syncthreads();
-  if (warp >= PIPE_W_PATCH0 && warp < PIPE_W_PATCH0 + PIPE_PDEPTH) { pipe_patch_warp<RR, WW>(S, sm, warp - PIPE_W_PATCH0, lane); return; }
-  if (warp >= PIPE_W_PREP0 && warp < PIPE_W_PREP0 + PIPE_PREP_TEAMS * PIPE_PREP_TW) {
-    pipe_prep_warp<RR, WW, PREF>(S, sm, (warp - PIPE_W_PREP0) / PIPE_PREP_TW, (warp - PIPE_W_PREP0) % PIPE_PREP_TW, lane); return; }
-  if (warp == PIPE_W_WRITER) { pipe_writer_warp<RR, WW>(S, sm, lane); return; }
-  if (warp == PIPE_W_SHADOW) { pipe_shadow_warp<NC>(S, sm, lane); return; }
-  if (warp != 0) return;
+  int role, ridx;
+  pipe_role(warp, role, ridx);
+  if (role == ROLE_PATCH) { pipe_patch_warp<RR, WW>(S, sm, ridx, lane); return; }
+  if (role == ROLE_PREP) { pipe_prep_warp<RR, WW, PREF>(S, sm, ridx / PIPE_PREP_TW, ridx % PIPE_PREP_TW, lane); return; }
+  if (role == ROLE_WRITER) { pipe_writer_warp<RR, WW, PREF>(S, sm, lane); return; }
+  if (role == ROLE_SHADOW) { pipe_shadow_warp<NC>(S, sm, lane); return; }
+  if (role != ROLE_MAIN) return;
 
   // ---------------- main warp ----------------
   Ctl& c = sm.ctl;
   uint32_t priv_head = 0;        // log entries appended (the writer publishes them a little later)
-  uint32_t next_seq = 0;         // scan requests posted
   uint32_t cmd_head = 0;
   uint32_t fresh_floor = 0;      // after a rescan stop: only a list requested at or after this log position will do
   bool failed = false;
-  uint32_t n_requests = 0;       // lane 0: requests posted, added to the statistics at the end
   auto push_cmd = [&](uint32_t kind, uint32_t a, uint32_t b) {       // whole warp calls it
     while (cmd_head - *((volatile uint32_t*)&sm.cmd_tail) >= PIPE_CMDS) __nanosleep(20);
     if (lane == 0) sts_v4(&sm.cmd[cmd_head % PIPE_CMDS], cmd_head + 1, kind, a, b);
     cmd_head += 1;
   };
-  // newest request for class `cls` in the requested table: returns found; seq / stamp by reference
-  auto rq_lookup = [&](uint32_t cls, uint32_t& seq, uint32_t& stamp) -> bool {
-    const bool m = lane < (int)PIPE_RQ && sm.rq_cls[lane] == cls;
-    const uint32_t s1 = m ? sm.rq_seq[lane] + 1u : 0u;
-    const uint32_t best = __reduce_max_sync(FULL, s1);
-    if (best == 0) return false;
-    const int src = __ffs(__ballot_sync(FULL, m && s1 == best)) - 1;
-    seq = best - 1u;
-    stamp = __shfl_sync(FULL, m ? sm.rq_stamp[lane] : 0u, src);
-    return true;
-  };
   const bool timing = (S.pipe_pad & 1u) != 0;       // KB_PIPE_TIMING=1: clock64 phase timers of the main warp (kb_stats.cyc_*)
-  auto post_request = [&](uint32_t cls) -> uint32_t {
-    const long long t_p0 = timing ? clock64() : 0;
-    const uint32_t seq = next_seq++;
-    // the table entry / prepared buffer of request seq - PIPE_RQ is recycled: its team must be through with it
-    if (seq >= PIPE_RQ && (int32_t)(*((volatile uint32_t*)&sm.prep_done[seq % PIPE_PREP_TEAMS]) - (seq - PIPE_RQ)) <= 0) {
-      const long long t_w0 = clock64(), deadline = t_w0 + PIPE_DEADLINE;
-      while ((int32_t)(*((volatile uint32_t*)&sm.prep_done[seq % PIPE_PREP_TEAMS]) - (seq - PIPE_RQ)) <= 0) {
-        if (clock64() > deadline) { failed = true; break; }
-        __nanosleep(20);
-      }
-      if (timing && lane == 0) { c.cyc_merge += (unsigned long long)(clock64() - t_w0); c.mispredictions += 1; }
-    }
+  // claim prepared list `seq` for this visit against the planner recycling its buffer (see `post` in the writer warp)
+  auto claim = [&](const uint32_t seq) -> bool {
+    uint32_t ok = 1;
     if (lane == 0) {
-      sm.rq_cls[seq % PIPE_RQ] = cls; sm.rq_seq[seq % PIPE_RQ] = seq; sm.rq_stamp[seq % PIPE_RQ] = priv_head;
-      n_requests += 1;
-      sts_u64(&sm.rq_word[seq % PIPE_RQ], ((unsigned long long)(seq + 1) << 32) | cls);
+      *((volatile uint32_t*)&sm.in_use) = seq + 1;
+      __threadfence_block();
+      const uint32_t po = *((volatile uint32_t*)&sm.posting);
+      const uint4 e = lds_v4(&sm.rq_ent[seq % PIPE_RQ]);
+      if (po == seq + 1 + PIPE_RQ || e.y != seq + 1) { *((volatile uint32_t*)&sm.in_use) = 0; ok = 0; }
     }
-    const long long t_p1 = timing ? clock64() : 0;
-    push_cmd(PCMD_REQ, cls, seq);
-    if (timing && lane == 0) { c.cyc_total += (unsigned long long)(t_p1 - t_p0); c.chain_hits += 1; }
-    return seq;
+    return __shfl_sync(FULL, ok, 0) != 0;
   };
+  // the first visit's list
+  if (!c.done) push_cmd(PCMD_PLAN | PLAN_FORCE_BIT | ((uint32_t)c.cur_job << 3), c.cur_class, 0u);
+  uint32_t plan_idx = cmd_head;       // commands pushed up to and including the latest PCMD_PLAN
 
   const long long t_cycle0 = clock64();
   while (!c.done && !failed) {
@@ -782,20 +841,34 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
     // a class with preferred node-affinity terms: its keys are normalised by the max count over the nodes feasible AT THE STAMP,
     // so only a list of the current table state will do (the replay then tracks the feasible max-count nodes itself)
     const bool pref_cls = PREF && S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[cls_id].n != 0;
-    bool usable = rq_lookup(cls_id, seq, stamp);
-    usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor && (!pref_cls || stamp == priv_head);
-    if (!usable) { seq = post_request(cls_id); stamp = priv_head; if (lane == 0) c.pipe_urgent += 1; }
+    // The planner judged the table by the same rule when it handled this visit's PCMD_PLAN, or will in a moment: if nothing
+    // usable is there yet, wait for it to get that far and look again.
+    for (bool waited = false;;) {
+      bool usable = rq_find<NC>(sm, lane, cls_id, seq, stamp);
+      usable = usable && (priv_head - stamp) <= PIPE_PATCH && stamp >= fresh_floor && (!pref_cls || stamp == priv_head);
+      if (usable && claim(seq)) break;
+      if (waited) push_cmd(PCMD_PLAN | PLAN_FORCE_BIT | ((uint32_t)c.cur_job << 3), cls_id, priv_head), plan_idx = cmd_head;      // its request stepped back: ask again
+      else if (lane == 0) c.pipe_urgent += 1;
+      const long long deadline = clock64() + PIPE_DEADLINE;
+      while ((int32_t)(*((volatile uint32_t*)&sm.cmd_tail) - plan_idx) < 0) {
+        if (clock64() > deadline || *((volatile uint32_t*)&sm.v_err)) { failed = true; break; }
+        __nanosleep(20);
+      }
+      if (failed) break;
+      waited = true;
+    }
+    if (failed) break;
     fresh_floor = 0;
     const uint32_t pbi = seq % PIPE_RQ;
-    if (lane == 0) { dbg_put(S.dbg, 1, 2u); dbg_put(S.dbg, 3, seq); dbg_put(S.dbg, 4, stamp); dbg_put(S.dbg, 5, priv_head); dbg_put(S.dbg, 6, next_seq); }
+    if (lane == 0) { dbg_put(S.dbg, 1, 2u); dbg_put(S.dbg, 3, seq); dbg_put(S.dbg, 4, stamp); dbg_put(S.dbg, 5, priv_head); dbg_put(S.dbg, 6, cmd_head); }
     {
       const long long t_b0 = clock64(), deadline = t_b0 + PIPE_DEADLINE;
-      if (timing && lane == 0 && *((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) c.predictions += 1;
+      if (timing && lane == 0 && *((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) c.mispredictions += 1;      // visits that waited for their list (timing mode only)
       while (*((volatile uint32_t*)&sm.pb_ready[pbi]) != seq + 1) {
         if (clock64() > deadline || *((volatile uint32_t*)&sm.v_err)) { failed = true; break; }
       }
       compiler_fence();          // pb[pbi] was stored before pb_ready by its team (fence + barrier on their side)
-      if (timing && lane == 0) c.cyc_ctl += (unsigned long long)(clock64() - t_b0);
+      if (timing && lane == 0) c.cyc_total += (unsigned long long)(clock64() - t_b0);      // timing mode: the wait for the prepared list
     }
     if (failed) break;
     const PrepBuf<NC>& P = sm.pb[pbi];
@@ -1024,7 +1097,9 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
         if (timing) {
           const long long t_run2 = clock64();
           c.cyc_steps += (unsigned long long)(t_run1 - t_run0);
-          c.predictions += 1;               // runs, step iterations (timing mode only)
+          c.cyc_merge += (unsigned long long)(t_loop1 - t_run0);      // the step loop alone
+          c.cyc_ctl += (unsigned long long)(t_run2 - t_run1);
+          c.predictions += 1;               // runs (timing mode only)
         }
       }
       __syncwarp();
@@ -1033,16 +1108,6 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
 
     if (lane == 0) { dbg_put(S.dbg, 1, 5u); dbg_put(S.dbg, 7, c.rescans); }
     const long long t_r0 = timing ? clock64() : 0;
-    // the planner's inputs (static-order classes of the runs after the next visit): loads issued now, used after the ring append
-    uint32_t pc[KB_CHAIN_MAX];
-    pc[0] = c.cur_class;
-#pragma unroll
-    for (uint32_t k = 1; k < KB_CHAIN_MAX; ++k) pc[k] = 0xFFFFFFFFu;
-    if (!c.done) {
-      const uint32_t s1 = S.job_pos[(uint32_t)c.cur_job];
-#pragma unroll
-      for (uint32_t k = 0; k + 1 < KB_CHAIN_MAX; ++k) pc[k + 1] = S.ord_chain[(size_t)s1 * (KB_CHAIN_MAX - 1) + k];
-    }
     // ---------------- end of the visit chain on this class: modified candidates -> hot ring + log ----------------
     const bool modified = depth > 0;
     const unsigned mm = __ballot_sync(FULL, modified);
@@ -1064,31 +1129,12 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
       priv_head += nmod;
     }
     if (rescanned) fresh_floor = priv_head;
+    if (lane == 0) *((volatile uint32_t*)&sm.in_use) = 0;          // P is not read past this point
+    // the planner (writer warp) requests the lists of the next visits, stamped with the log position this visit ended at
+    // (measured: pushing this before the write-back command, with the stamp ahead of the published log, is 0.3 ms slower on C3)
+    if (!c.done) { push_cmd(PCMD_PLAN | (rescanned ? PLAN_FORCE_BIT : 0u) | ((uint32_t)c.cur_job << 3), c.cur_class, priv_head); plan_idx = cmd_head; }
     const long long t_r1 = timing ? clock64() : 0;
     if (lane == 0) dbg_put(S.dbg, 1, 6u);
-    // ---------------- planner: scan requests for the classes of the next visits ----------------
-    if (!c.done) {
-      // the chain's classes are distinct, so no post below changes a later lookup: all lookups first (they overlap), then the posts
-      uint32_t ls[KB_CHAIN_MAX], lst[KB_CHAIN_MAX]; bool lf[KB_CHAIN_MAX];
-#pragma unroll
-      for (uint32_t k = 0; k < KB_CHAIN_MAX; ++k) { ls[k] = 0; lst[k] = 0; lf[k] = rq_lookup(pc[k], ls[k], lst[k]); }
-#pragma unroll
-      for (uint32_t k = 0; k < KB_CHAIN_MAX; ++k) {
-        const uint32_t pcls = pc[k];
-        if (pcls == 0xFFFFFFFFu) continue;
-        if (k == 0 && rescanned) continue;                      // the visit start posts the fresh request itself
-        if (PREF && S.class_pref != nullptr && S.cf.nodeorder && S.class_pref[pcls].n != 0) {
-          // preferred terms: only a list of the table state at its use will do — request the next visit's now, nothing further ahead
-          if (k != 0) continue;
-          if (!(lf[k] && lst[k] == priv_head)) post_request(pcls);
-          continue;
-        }
-        const bool f = lf[k];
-        const uint32_t age = priv_head - lst[k];
-        const bool ok = f && (k == 0 ? age <= PIPE_PATCH : age + 8u * k <= 24u);
-        if (!ok) post_request(pcls);
-      }
-    }
     if (lane == 0 && timing) {
       const long long t_end = clock64();
       c.cyc_scan += (unsigned long long)(t_v1 - t_v0);
@@ -1105,9 +1151,13 @@ __device__ __forceinline__ void pipe_replayer(const DevSession& S, unsigned char
   __syncwarp();
   bar_sync(1, (1 + PIPE_PDEPTH) * 32);           // releases the patch warps
   push_cmd(PCMD_QUIT, 0, 0);
-  while (*((volatile uint32_t*)&sm.cmd_tail) != cmd_head - 1 + 0u && *((volatile uint32_t*)&sm.cmd_tail) != cmd_head) __nanosleep(40);
+  {
+    const long long deadline = clock64() + PIPE_DEADLINE;
+    while (*((volatile uint32_t*)&sm.cmd_tail) != cmd_head) { if (clock64() > deadline) { failed = true; break; } __nanosleep(40); }
+  }
   if (lane == 0) {
     if (!timing) c.cyc_total += (unsigned long long)(clock64() - t_cycle0);
+    const uint32_t n_requests = *((volatile uint32_t*)&sm.n_requests);
     c.pipe_requests += n_requests; c.pairs_scanned += (unsigned long long)n_requests * S.N;
     if ((failed || *((volatile uint32_t*)&sm.v_err)) && !c.error) c.error = 3;
     const uint32_t perr = ld_relaxed_u32(&pg->error);

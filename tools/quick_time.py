@@ -20,8 +20,7 @@ for i in range(reps):
           f"        predictions {s.predictions} mispredictions {s.mispredictions}\n"
           f"        scans {s.scans} rescans {s.rescans} per-launch cycles: scan {s.cyc_scan / max(1, s.scans):.0f} merge {s.cyc_merge / max(1, s.scans):.0f} "
           f"replay+ctl {s.cyc_replay / max(1, s.scans):.0f} (steps {s.cyc_steps / max(1, s.scans):.0f} ctl {s.cyc_ctl / max(1, s.scans):.0f}) total {s.cyc_total / max(1, s.scans):.0f}; us/launch {1e3 * s.gpu_ms / max(1, s.kernel_launches):.2f}\n"
-          f"        timing mode: step loop {s.cyc_merge / max(1, s.scans):.0f} hot ring {s.cyc_ring / max(1, s.scans):.0f} planner {s.cyc_plan / max(1, s.scans):.0f} "
-          f"pb_ready: {s.predictions} visits waited, {s.cyc_ctl / max(1, s.scans):.0f} cycles per visit chain in the wait block; post_request: {s.chain_hits} calls, {s.cyc_total / max(1, s.chain_hits):.0f} cycles before push_cmd "
-          f"(incl. the prep_done wait: {s.mispredictions} waits, {s.cyc_merge / max(1, s.mispredictions):.0f} cycles each)\n"
+          f"        timing mode (KB_PIPE_TIMING=1): step loop {s.cyc_merge / max(1, s.scans):.0f} hot ring {s.cyc_ring / max(1, s.scans):.0f} plan command {s.cyc_plan / max(1, s.scans):.0f} "
+          f"runs {s.predictions}; list wait {s.cyc_total / max(1, s.scans):.0f} cycles per visit chain, {s.mispredictions} visits waited\n"
           f"        pipeline {s.pipeline}: requests {s.pipe_requests} urgent {s.pipe_urgent} extends {s.pipe_extends} patched lists {s.pipe_patched} "
           f"patch entries {s.pipe_patch_entries}; us/visit-chain {1e3 * s.gpu_ms / max(1, s.scans):.2f}")
