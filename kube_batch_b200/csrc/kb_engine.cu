@@ -127,7 +127,11 @@ struct kb_engine {
   uint32_t* h_dbg = nullptr;                // KB_PIPE_DEBUG=1: 64 progress words of cycle_kernel in mapped host memory
   uint32_t* d_dbg = nullptr;
   bool pipe_timing = false;                 // KB_PIPE_TIMING=1: phase timers inside cycle_kernel (kb_stats.cyc_*)
-  uint32_t pipe_plan = (28u << 8) | (16u << 16) | (255u << 24);   // planner: oldest list (log entries) accepted 1 / 2 / 3 visits ahead (KB_PIPE_PLAN=a1,a2,a3; 255 = no request that far ahead)
+  // planner: oldest list (log entries since its stamp) accepted for the class 1 / 2 / 3 runs ahead in the queue's static order,
+  // 255 = no request that far ahead (KB_PIPE_PLAN=a1,a2,a3).  0 = by session: measured on B200, 28,16,off is best with one
+  // queue (C3 49.3 ms; 16,8,off 51 ms), 16,8,off with several (C4, 8 queues: 280 ms; 28,16,off 340 ms — the static order of ONE
+  // queue predicts the visit after next badly when the queues take turns)
+  uint32_t pipe_plan = 0;
   double watchdog_s = 30.0;                 // a cycle_kernel that has not finished after this long is reported (with the progress words) and the process aborts: a hung cooperative kernel cannot be cancelled
   cudaGraph_t graph = nullptr;         // BATCH visit_kernel launches, captured once per distinct DevSession
   cudaGraphExec_t graph_exec = nullptr;
@@ -287,7 +291,7 @@ int kb_engine_create(const kb_engine_opts* opts, kb_engine** out) {
   if (const char* pt = getenv("KB_PIPE_TIMING")) e->pipe_timing = atoi(pt) != 0;
   if (const char* pp = getenv("KB_PIPE_PLAN")) {
     unsigned a1 = 28, a2 = 16, a3 = 255;
-    if (sscanf(pp, "%u,%u,%u", &a1, &a2, &a3) == 3 && a1 < 256 && a2 < 256 && a3 < 256) e->pipe_plan = (a1 << 8) | (a2 << 16) | (a3 << 24);
+    if (sscanf(pp, "%u,%u,%u", &a1, &a2, &a3) == 3 && a1 >= 1 && a1 < 256 && a2 < 256 && a3 < 256) e->pipe_plan = (a1 << 8) | (a2 << 16) | (a3 << 24);
   }
   if (const char* kc = getenv("KB_CHAIN")) { const int v = atoi(kc); if (v == 1 || v == 2 || v == 4) e->kchain_req = (uint32_t)v; }
   if ((c = cudaSetDevice(e->device)) != cudaSuccess || (c = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking)) != cudaSuccess ||
@@ -518,7 +522,8 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       // ONE cooperative launch runs the whole cycle: pipe_S scanner CTAs with resident tiles + the replayer CTA
       DevSession dv = D;
       dv.dbg = e->d_dbg;
-      dv.pipe_pad = (e->pipe_timing ? 1u : 0u) | e->pipe_plan;
+      const uint32_t plan = e->pipe_plan ? e->pipe_plan : (D.Q > 1 ? ((16u << 8) | (8u << 16) | (255u << 24)) : ((28u << 8) | (16u << 16) | (255u << 24)));
+      dv.pipe_pad = (e->pipe_timing ? 1u : 0u) | plan;
       if (e->h_dbg) memset(e->h_dbg, 0, 64 * 4);
       void* args[] = {(void*)&dv};
       const void* kfn = D.class_pref ? (const void*)cycle_kernel<3, 2, 1> : (const void*)cycle_kernel<3, 2, 0>;

@@ -3,20 +3,22 @@
 // cycle_kernel<R, W>   grid = pipe_S scanner CTAs + 1 replayer CTA, all co-resident, one launch per kb_allocate.
 //
 //   scanner CTA   keeps pipe_tpc node tiles (TMA bulk copy at start) RESIDENT in shared memory for the whole cycle.
-//                 Four warp groups (4 warps = 128 threads = one node per thread per tile) serve scan requests
-//                 seq = g, g+4, ... concurrently: K1 predicate bitmask + K2 fused score (eval_pair) for the request's
+//                 Three warp groups (4 warps = 128 threads = one node per thread per tile) serve scan requests
+//                 seq = g, g+3, ... concurrently: K1 predicate bitmask + K2 fused score (eval_pair) for the request's
 //                 class over the CTA's nodes, warp bitonic top-32 (K3), group fold, list -> global; the LAST group to
 //                 deliver (ticket) merges the pipe_S lists and publishes the request's top-32 (NCCL-LL style words:
 //                 the payload carries its own sequence tag, no separate flag, no fence on the reader).
-//                 A 17th warp (applier) follows the modification log and refreshes the resident tiles.
-//   replayer CTA  warp 0 walks the visits exactly like allocate.go:89-193: for the class of the next run it takes the
-//                 look-ahead list that was requested a few visits earlier (stamp = log position at the request),
+//                 Warp 12 (applier) follows the modification log and refreshes the resident tiles.
+//   replayer CTA  warp 0 (main) walks the visits exactly like allocate.go:89-193: for the class of the next run it takes
+//                 the look-ahead list that was requested a few visits earlier (stamp = log position at the request),
 //                 PATCHES it — every node modified since the stamp is dropped from the list and re-evaluated from the
-//                 replayer's own copy (hot ring) — and replays.  16 eval warps evaluate, in ONE round, the candidate
-//                 pool (<= 32 list entries + <= 32 patch entries) at placement depths 0..7 (the state after k more
-//                 placements of this class is a pure function of the record), so a step of the run is a warp arg-max
-//                 plus a shared-memory read.  Warp 17 (writer) writes modified records back, appends the log, publishes
-//                 its head (st.release: no L1 invalidation on this SM) and posts scan requests for the predicted classes.
+//                 replayer's own copy (hot ring) by the four patch warps — and replays: the prep teams (2 x 4 warps) have
+//                 evaluated the list's candidates at placement depths 0..7 ahead of the visit (the state after k more
+//                 placements of this class is a pure function of the record), so a step of the run is a warp arg-max plus
+//                 a shared-memory read.  The writer warp writes modified records back, appends the log, publishes its
+//                 head (st.release: no L1 invalidation on this SM) and, as the planner, owns the requested table: it posts
+//                 the scan requests for the classes of the next visits from a PLAN command the main warp pushes per visit.
+//                 The shadow warp pulls the job / queue rows of the next visits into L1.
 //
 // Exactness (same argument as the per-launch kernels, generalised to a stale list): let L be the exact top-32 of class c
 // for the table state at log position s, floor = its 32nd key, M = nodes in log[s, now).  A node outside L and outside M
@@ -35,24 +37,30 @@ namespace kb {
 constexpr int PIPE_DEPTH = 8;              // placement depths a prep team evaluates per list entry (ahead of the visit)
 constexpr int PIPE_PDEPTH = 4;             // ... and the patch warps per patch entry (on the visit's critical path: kept short;
                                            //     deeper states of a candidate come from the chain extension)
-// replayer CTA warp roles.  A warp's scheduler (SM sub-partition) is warp % 4: the main warp (0) shares its scheduler only with
-// the patch warps (4, 8, 12, 16), which run while it waits at their barrier; the prep teams, the writer / planner and the shadow
-// prefetch sit on the other three.  scanner CTAs: 0..15 scan groups, 16 applier.
+// 16 warps per CTA: four per scheduler (SM sub-partition, warp % 4), so ptxas may use 128 registers per thread (a 17th warp
+// would put five on one scheduler: 96 registers and spills in the step loop).
+// replayer CTA warp roles: the main warp (0) shares its scheduler only with patch warps (4, 8, 12), which run while it waits at
+// their barrier; the prep teams, the writer / planner, the shadow prefetch and the fourth patch warp sit on the other three.
+// scanner CTAs: PIPE_SCAN_GROUPS scan groups of 4 warps, then the applier warp.
 constexpr int PIPE_PREP_TEAMS = 2, PIPE_PREP_TW = 4;
-constexpr int PIPE_WARPS = 17;
+constexpr int PIPE_WARPS = 16;
 constexpr int PIPE_THREADS = PIPE_WARPS * 32;
+constexpr int PIPE_SCAN_GROUPS = 3;
+constexpr int PIPE_W_APPLIER = 4 * PIPE_SCAN_GROUPS;
+static_assert(PIPE_W_APPLIER < PIPE_WARPS, "scanner CTA: scan groups + applier");
 enum PipeRole : int { ROLE_MAIN = 0, ROLE_PATCH = 1, ROLE_PREP = 2, ROLE_WRITER = 3, ROLE_SHADOW = 4, ROLE_NONE = 5 };
 __device__ __forceinline__ void pipe_role(const int warp, int& role, int& idx) {
   idx = 0;
   if (warp == 0) { role = ROLE_MAIN; return; }
-  if ((warp & 3) == 0) { role = ROLE_PATCH; idx = (warp >> 2) - 1; return; }                // 4, 8, 12, 16 -> depth 0..3
+  if ((warp & 3) == 0) { role = ROLE_PATCH; idx = (warp >> 2) - 1; return; }                // 4, 8, 12 -> depth 0..2
   const int r = warp - 1 - (warp >> 2);                                                      // 1,2,3,5,6,7,9,10,11,13,14,15 -> 0..11
   if (r < PIPE_PREP_TEAMS * PIPE_PREP_TW) { role = ROLE_PREP; idx = r; return; }
   if (r == PIPE_PREP_TEAMS * PIPE_PREP_TW) { role = ROLE_WRITER; return; }
   if (r == PIPE_PREP_TEAMS * PIPE_PREP_TW + 1) { role = ROLE_SHADOW; return; }
+  if (r == PIPE_PREP_TEAMS * PIPE_PREP_TW + 2) { role = ROLE_PATCH; idx = 3; return; }       // warp 15 -> depth 3
   role = ROLE_NONE;
 }
-static_assert(PIPE_PDEPTH == 4 && PIPE_PREP_TEAMS * PIPE_PREP_TW + 2 <= 12, "warp roles of the replayer CTA");
+static_assert(PIPE_PDEPTH == 4 && PIPE_PREP_TEAMS * PIPE_PREP_TW + 3 <= 12, "warp roles of the replayer CTA");
 static_assert(PIPE_DEPTH % PIPE_PREP_TW == 0, "a prep warp owns depths w, w + TW, ...");
 constexpr uint32_t PIPE_HOT = 128;         // hot ring: records of the most recent log entries (replayer shared memory)
 constexpr uint32_t PIPE_RQ = 16;           // requested-table entries (most recent scan requests)
@@ -192,7 +200,7 @@ struct ScanSmem {
   uint32_t pad[3];
   uint64_t mbar;
   uint64_t pad2;
-  ScanGroup grp[4];
+  ScanGroup grp[PIPE_SCAN_GROUPS];
 };
 __host__ __device__ constexpr size_t pipe_scan_header() { return ((sizeof(ScanSmem) + 127) / 128) * 128; }
 
@@ -215,8 +223,8 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
   __syncthreads();
   mbar_wait(&sm.mbar, 0);
 
-  if (warp > 16) return;
-  if (warp == 16) {
+  if (warp > PIPE_W_APPLIER) return;
+  if (warp == PIPE_W_APPLIER) {
     // ---------------- applier: follow the modification log, refresh the resident copies of MY nodes ----------------
     uint32_t cursor = 0;
     for (;;) {
@@ -253,7 +261,7 @@ __device__ __forceinline__ void pipe_scanner(const DevSession& S, unsigned char*
   const int g = warp >> 2, wg = warp & 3, gt = tid & 127;
   ScanGroup& G = sm.grp[g];
   const int bar_id = 1 + g;
-  for (uint32_t seq = (uint32_t)g;; seq += 4) {
+  for (uint32_t seq = (uint32_t)g;; seq += PIPE_SCAN_GROUPS) {
     const uint32_t slot = seq % PIPE_RING, tag = seq + 1;
     if (wg == 0) {
       unsigned long long w0 = 0, w1 = 0;
