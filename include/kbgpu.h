@@ -56,20 +56,79 @@ typedef enum kb_status {
 
 /* task_flags bits */
 #define KB_TASK_BEST_EFFORT_QOS  (1u << 0) /* v1qos.GetPodQOS(pod) == BestEffort (memory-pressure predicate only) */
-#define KB_TASK_HAS_POD_AFFINITY (1u << 1) /* pod (anti)affinity terms present -> KB_E_UNSUPPORTED_FEATURE        */
-#define KB_TASK_HAS_PREFERRED_NODE_AFFINITY (1u << 2) /* -> KB_E_UNSUPPORTED_FEATURE                               */
+#define KB_TASK_HAS_POD_AFFINITY (1u << 1) /* pod (anti)affinity terms present: needs kb_snapshot.pod_affinity, else KB_E_UNSUPPORTED_FEATURE */
+#define KB_TASK_HAS_PREFERRED_NODE_AFFINITY (1u << 2) /* preferred node-affinity terms (task_pref_*)                */
+#define KB_TASK_AFF_SELF_MATCH   (1u << 3) /* targetPodMatchesAffinityOfPod(pod, pod): the pod matches the namespaces + selectors of ALL its own
+                                              required pod-affinity terms (vendor/.../predicates/metadata.go:767-778) — the "first pod of a
+                                              series" escape of predicates.go:1545-1560                                                  */
 
 /* kb_snapshot.flags */
 #define KB_SNAPSHOT_PLACED_POD_AFFINITY (1u << 0) /* some task that is NOT pending (running / bound / allocated on a node) carries
                                                       inter-pod affinity or anti-affinity terms: the reference's predicate step 10 lets such
                                                       pods reject nodes for OTHER pods (predicates.go:1261-1288 satisfiesExistingPodsAntiAffinity)
-                                                      and scores them (interpod_affinity.go:150-170) -> KB_E_UNSUPPORTED_FEATURE            */
+                                                      and scores them (interpod_affinity.go:150-170): needs kb_snapshot.pod_affinity, else
+                                                      KB_E_UNSUPPORTED_FEATURE                                                              */
 
 /* kb_decision.kind */
 #define KB_KIND_NONE      0 /* task was never placed this cycle                                   */
 #define KB_KIND_ALLOCATED 1 /* ssn.Allocate (framework/session.go:235)  — consumed node.Idle       */
 #define KB_KIND_PIPELINED 2 /* ssn.Pipeline (framework/session.go:194)  — consumed node.Releasing  */
 #define KB_KIND_SKIPPED   3 /* Resreq.IsEmpty(): skipped by allocate (allocate.go:113-118)         */
+
+/*
+ * Inter-pod (anti)affinity, flattened (SURVEY.md 8a a5 step 10 + a13).  The flattener does the string work once per snapshot:
+ * it interns the topology keys the terms use, the label selectors / namespaces of the terms, and matches every pod against
+ * them; the engine only counts.  Two families of counters, because the reference reads two different pod sets:
+ *
+ *  (P) predicate InterPodAffinityMatches (vendor/.../predicates/predicates.go:1261-1572, slow path: meta == nil) walks
+ *      util.PodLister (plugins/util/util.go:37-85) = the tasks with AllocatedStatus (Bound, Binding, Running, Allocated) of the
+ *      session's jobs, located by TaskInfo.NodeName.  A counter GROUP g counts such pods per topology DOMAIN of its key set:
+ *        - one group per distinct required anti-affinity term an existing / pending pod owns (members: the pods owning it;
+ *          key set = {term.topologyKey}); an incoming pod that matches the term's namespaces + selector FORBIDS the group
+ *          (satisfiesExistingPodsAntiAffinity, :1400-1439);
+ *        - one group per distinct required anti-affinity term LIST of a pending pod (members: the pods matching the namespaces +
+ *          selector of ALL terms of the list, podMatchesPodAffinityTerms :1296-1320; key set = the list's topology keys — a
+ *          domain is the tuple of label values): the pod FORBIDS it (:1526-1533);
+ *        - one group per distinct required affinity term list of a pending pod, likewise: the pod NEEDS it — a node passes
+ *          iff the group's counter of the node's domain is > 0, or no member exists anywhere and the pod matches its own terms
+ *          (KB_TASK_AFF_SELF_MATCH, :1536-1560).
+ *      A node whose labels lack a key of the set has domain -1 (NodesHaveSameTopologyKey is false).
+ *  (S) priority CalculateInterPodAffinityPriority (vendor/.../priorities/interpod_affinity.go:99-235) walks nodeInfo.Pods() of
+ *      the FEASIBLE nodes = every task in NodeInfo.Tasks whatever its status.  Pods are grouped into KINDS (same weights against
+ *      every pending pod); per pending task a list of (kind, key set, weight): sum over the task's preferred (anti)affinity terms
+ *      the kind matches (+-weight), the kind's required affinity terms the task matches (+1 each,
+ *      v1.DefaultHardPodAffinitySymmetricWeight, nodeorder.go:159) and the kind's preferred terms the task matches (+-weight),
+ *      all with that topology key.  count(n) = sum over feasible nodes m, pods on m: weight if the "pod's node" and n share the
+ *      key's label value.  The "pod's node" is m for a pod whose Spec.NodeName is set; for one placed in this or an earlier
+ *      session and not yet bound (Spec.NodeName == "") the reference's cachedNodeInfo.GetNodeInfo (plugins/nodeorder/nodeorder.go:
+ *      49-63) returns the first node it finds holding ANY such pod — a Go map iteration; deterministic rule:
+ *      the lowest node index holding one (`first_unbound_node`, kept current by the engine).
+ *      score = int(10 * (count - min) / (max - min)) over the feasible nodes, min and max starting at 0.
+ */
+#define KB_MAX_AFF_GROUPS 64
+typedef struct kb_pod_affinity {
+  uint32_t n_keysets;             /* distinct topology key sets                                                              */
+  uint32_t n_groups;              /* <= KB_MAX_AFF_GROUPS                                                                     */
+  uint32_t n_kinds;
+  uint32_t n_weights;
+  int32_t  first_unbound_node;    /* -1: no pod with an empty Spec.NodeName sits on a node at session open                    */
+  uint32_t reserved;
+  const int32_t*  node_domain;    /* [n_keysets][N] domain of node n under key set s, -1 = a key of the set is not a label of n */
+  const uint32_t* keyset_domains; /* [n_keysets] number of domains                                                            */
+  const uint32_t* group_keyset;   /* [n_groups]                                                                               */
+  const int32_t*  group_count0;   /* groups back to back, keyset_domains[group_keyset[g]] counters each: members per domain at open */
+  const int32_t*  group_total0;   /* [n_groups] members anywhere (also on nodes with domain -1)                               */
+  const uint64_t* task_forbid;    /* [T] bit g: a member of g in the node's domain rejects the node for this task             */
+  const int32_t*  task_need;      /* [T] group the task's required pod-affinity terms need, -1 none                          */
+  const uint64_t* task_contrib;   /* [T] bit g: the task becomes a member of g once it is Allocated (not when Pipelined)      */
+  const int32_t*  task_kind;      /* [T] kind the task's pod has once it sits on a node (Allocated or Pipelined), -1 = no weight anywhere */
+  const int32_t*  node_kind_count0; /* [n_kinds][N] pods of kind k in NodeInfo.Tasks of node n at open                       */
+  const uint8_t*  kind_unbound;   /* [n_kinds] 1: pods of the kind have an empty Spec.NodeName                                */
+  const uint32_t* task_weight_off;/* [T+1] the task's entries in the three arrays below                                       */
+  const int32_t*  weight_kind;    /* [n_weights]                                                                              */
+  const int32_t*  weight_keyset;  /* [n_weights] a single-key key set                                                         */
+  const int64_t*  weight_value;   /* [n_weights]                                                                              */
+} kb_pod_affinity;
 
 /*
  * Flattened Session snapshot (SoA).  Replaces the Go maps ssn.Jobs / ssn.Nodes / ssn.Queues
@@ -142,10 +201,15 @@ typedef struct kb_snapshot {
   /* ---- preferred node affinity (NodeAffinityPriority, vendor/.../priorities/node_affinity.go:34-77) ----
    * Only read for tasks that carry KB_TASK_HAS_PREFERRED_NODE_AFFINITY; all three may be NULL otherwise.  The CPU oracle
    * evaluates them (count = sum of the weights of the matching terms, NormalizeReduce(10) over the feasible nodes);
-   * this build of the engine still refuses such tasks (KB_E_UNSUPPORTED_FEATURE). */
+   * the engine evaluates them in cycle_kernel (sessions on the per-visit kernels are refused, KB_E_UNSUPPORTED_FEATURE). */
   const uint32_t* task_n_pref_terms;  /* [T] 0..KB_MAX_PREF_TERMS                                    */
   const uint64_t* task_pref_terms;    /* [KB_MAX_PREF_TERMS][W][T] requirement atoms of term p: ALL must hold on the node */
   const int32_t*  task_pref_weights;  /* [KB_MAX_PREF_TERMS][T] PreferredSchedulingTerm.Weight (0 = term skipped) */
+
+  /* ---- inter-pod (anti)affinity (predicate step 10 + InterPodAffinityPriority), NULL = no pod of the session carries terms.
+   * With it the cycle runs on the per-visit kernels (fresh scan per task for the classes that read the counters); kb_reclaim /
+   * kb_preempt refuse such sessions (KB_E_UNSUPPORTED_FEATURE). ---- */
+  const kb_pod_affinity* pod_affinity;
 } kb_snapshot;
 
 /* Mirrors conf.PluginOption (pkg/scheduler/conf/scheduler_conf.go:33-56).  The Enabled* tri-states

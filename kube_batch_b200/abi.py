@@ -40,6 +40,8 @@ KB_TASK_BEST_EFFORT_QOS = 1 << 0
 KB_TASK_HAS_POD_AFFINITY = 1 << 1
 KB_SNAPSHOT_PLACED_POD_AFFINITY = 1 << 0
 KB_TASK_HAS_PREFERRED_NODE_AFFINITY = 1 << 2
+KB_TASK_AFF_SELF_MATCH = 1 << 3
+KB_MAX_AFF_GROUPS = 64
 
 KB_KIND_NONE = 0
 KB_KIND_ALLOCATED = 1
@@ -100,6 +102,54 @@ SNAPSHOT_ARRAYS = [
 ]
 
 
+# kb_pod_affinity arrays: (field, ctypes element type, numpy dtype)
+POD_AFFINITY_ARRAYS = [
+    ("node_domain", C.c_int32, "i4"),
+    ("keyset_domains", C.c_uint32, "u4"),
+    ("group_keyset", C.c_uint32, "u4"),
+    ("group_count0", C.c_int32, "i4"),
+    ("group_total0", C.c_int32, "i4"),
+    ("task_forbid", C.c_uint64, "u8"),
+    ("task_need", C.c_int32, "i4"),
+    ("task_contrib", C.c_uint64, "u8"),
+    ("task_kind", C.c_int32, "i4"),
+    ("node_kind_count0", C.c_int32, "i4"),
+    ("kind_unbound", C.c_uint8, "u1"),
+    ("task_weight_off", C.c_uint32, "u4"),
+    ("weight_kind", C.c_int32, "i4"),
+    ("weight_keyset", C.c_int32, "i4"),
+    ("weight_value", C.c_int64, "i8"),
+]
+
+
+class kb_pod_affinity(C.Structure):
+    """include/kbgpu.h kb_pod_affinity: inter-pod (anti)affinity, flattened by builder.py."""
+    _fields_ = [
+        ("n_keysets", C.c_uint32),
+        ("n_groups", C.c_uint32),
+        ("n_kinds", C.c_uint32),
+        ("n_weights", C.c_uint32),
+        ("first_unbound_node", C.c_int32),
+        ("reserved", C.c_uint32),
+    ] + [(name, C.POINTER(ct)) for name, ct, _ in POD_AFFINITY_ARRAYS]
+
+
+def pod_affinity_to_c(pa):
+    """dict (builder.py) -> (kb_pod_affinity, keep-alive list)."""
+    import numpy as np
+    r = kb_pod_affinity()
+    r.n_keysets = int(pa["n_keysets"]); r.n_groups = int(pa["n_groups"]); r.n_kinds = int(pa["n_kinds"])
+    r.n_weights = int(pa["n_weights"]); r.first_unbound_node = int(pa["first_unbound_node"])
+    keep = []
+    for name, ct, dt in POD_AFFINITY_ARRAYS:
+        a = np.ascontiguousarray(pa[name], dtype=np.dtype(dt)).reshape(-1)
+        if a.size == 0:
+            a = np.zeros(1, dtype=np.dtype(dt))
+        keep.append(a)
+        setattr(r, name, a.ctypes.data_as(C.POINTER(ct)))
+    return r, keep
+
+
 class kb_snapshot(C.Structure):
     _fields_ = [
         ("abi_version", C.c_uint32),
@@ -110,7 +160,7 @@ class kb_snapshot(C.Structure):
         ("J", C.c_uint32),
         ("Q", C.c_uint32),
         ("flags", C.c_uint32),
-    ] + [(name, ptr) for name, ptr, _, _ in SNAPSHOT_ARRAYS]
+    ] + [(name, ptr) for name, ptr, _, _ in SNAPSHOT_ARRAYS] + [("pod_affinity", C.POINTER(kb_pod_affinity))]
 
 
 class kb_plugin_option(C.Structure):

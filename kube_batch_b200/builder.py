@@ -68,6 +68,25 @@ class Node:
 
 
 @dataclass
+class PodAffinityTerm:
+    """v1.PodAffinityTerm: labelSelector (matchLabels + matchExpressions; nil_selector = the Go nil *LabelSelector, which
+    LabelSelectorAsSelector turns into labels.Nothing()), namespaces (empty = the owning pod's namespace), topologyKey."""
+    topology_key: str
+    match_labels: Dict[str, str] = field(default_factory=dict)
+    match_expressions: List[Tuple[str, str, Sequence[str]]] = field(default_factory=list)   # In NotIn Exists DoesNotExist
+    namespaces: List[str] = field(default_factory=list)
+    nil_selector: bool = False
+
+
+@dataclass
+class PodAffinity:
+    """v1.PodAffinity / v1.PodAntiAffinity: requiredDuringSchedulingIgnoredDuringExecution and
+    preferredDuringSchedulingIgnoredDuringExecution [(weight, term)]."""
+    required: List[PodAffinityTerm] = field(default_factory=list)
+    preferred: List[Tuple[int, PodAffinityTerm]] = field(default_factory=list)
+
+
+@dataclass
 class Pod:
     namespace: str
     name: str
@@ -89,6 +108,8 @@ class Pod:
     deleting: bool = False
     uid: Optional[str] = None
     limits: Dict[str, float] = field(default_factory=dict)
+    pod_affinity: Optional[PodAffinity] = None          # Spec.Affinity.PodAffinity (None = nil)
+    pod_anti_affinity: Optional[PodAffinity] = None     # Spec.Affinity.PodAntiAffinity
 
 
 @dataclass
@@ -462,7 +483,325 @@ class SessionBuilder:
             v, present = pod_resreq(p)
             rt["resreq"][:, i] = v
             rt["res_present"][i] = present
-        s.meta = {"running": rt, "nodes": [n.name for n in nodes], "tasks": [f"{p.namespace}/{p.name}" for p in pending],
+        pod_objects = None
+        if any(p.pod_affinity is not None or p.pod_anti_affinity is not None for p in self.pods):
+            pend_ids = set(id(p) for p in pending)
+            existing = [p for p in self.pods if id(p) not in pend_ids and p.node_name in nidx and self._task_status(p) != "Pending"]
+            s.pod_affinity, pod_objects = flatten_pod_affinity(nodes, pending, existing, s, on_node,
+                                                               lambda p: self._task_status(p), lambda p: f"{p.namespace}/{p.group}" in jidx)
+        s.meta = {"pod_objects": pod_objects, "running": rt, "nodes": [n.name for n in nodes], "tasks": [f"{p.namespace}/{p.name}" for p in pending],
                   "jobs": list(jidx.keys()), "queues": [q.name for q in queues], "dims": dims}
         s.validate()
         return s
+
+
+# ----------------------------------------------------------------------------------------------
+# inter-pod (anti)affinity: the string work of predicate step 10 and InterPodAffinityPriority, done once per snapshot
+# (include/kbgpu.h kb_pod_affinity).  Reference: vendor/k8s.io/kubernetes/pkg/scheduler/algorithm/predicates/predicates.go:
+# 1261-1572, .../priorities/interpod_affinity.go:99-235, .../priorities/util/topologies.go:25-70,
+# vendor/k8s.io/apimachinery/pkg/apis/meta/v1/helpers.go (LabelSelectorAsSelector), pkg/scheduler/plugins/util/util.go:37-85.
+# ----------------------------------------------------------------------------------------------
+def _term_props(owner: Pod, term: PodAffinityTerm):
+    """(namespaces, selector) of a term: GetNamespacesFromPodAffinityTerm + LabelSelectorAsSelector, canonical + hashable."""
+    ns = frozenset(term.namespaces) if term.namespaces else frozenset([owner.namespace])
+    if term.nil_selector:
+        return (ns, None)
+    reqs = [(k, "In", (v,)) for k, v in sorted(term.match_labels.items())]
+    for (k, op, vals) in term.match_expressions:
+        assert op in ("In", "NotIn", "Exists", "DoesNotExist"), f"label selector operator {op}"
+        if op in ("In", "NotIn"):
+            assert len(vals) > 0, "In / NotIn need values (LabelSelectorAsSelector returns an error otherwise)"
+        else:
+            assert len(vals) == 0
+        reqs.append((k, op, tuple(sorted(vals))))
+    return (ns, tuple(reqs))
+
+
+def _props_match(pod: Pod, props) -> bool:
+    """priorityutil.PodMatchesTermsNamespaceAndSelector (topologies.go:38-49)."""
+    ns, reqs = props
+    if pod.namespace not in ns:
+        return False
+    if reqs is None:            # labels.Nothing()
+        return False
+    return all(_match_requirement(pod.labels, k, op, vals) for (k, op, vals) in reqs)
+
+
+def _aff_sig(p: Pod):
+    def spec(a):
+        if a is None:
+            return None
+        def term(t):
+            return (t.topology_key, tuple(sorted(t.match_labels.items())), tuple((k, op, tuple(v)) for (k, op, v) in t.match_expressions),
+                    tuple(t.namespaces), t.nil_selector)
+        return (tuple(term(t) for t in a.required), tuple((w, term(t)) for (w, t) in a.preferred))
+    return (p.namespace, tuple(sorted(p.labels.items())), spec(p.pod_affinity), spec(p.pod_anti_affinity))
+
+
+def flatten_pod_affinity(nodes, pending, existing, s, on_node, status_of, in_session_job):
+    """-> (dict mirroring kb_pod_affinity, dict of the raw objects for the oracle).  `pending`: the snapshot's tasks in task
+    order; `existing`: pods with a node of the session that are not Pending; on_node: ids of pods node.AddTask accepted."""
+    N, T = len(nodes), len(pending)
+    nidx = {n.name: i for i, n in enumerate(nodes)}
+    listed = [p for p in existing if status_of(p) in ("Bound", "Binding", "Running", "Allocated") and in_session_job(p)]
+    for p in listed:
+        assert id(p) in on_node, "a listed pod that its node refused (over-committed node): nodeInfo.Filter would hide it from its own node only"
+    in_tasks = [p for p in existing if id(p) in on_node]
+
+    # ---- key sets / domains ----
+    keysets: Dict[Tuple[str, ...], int] = {}
+    dom_rows: List[np.ndarray] = []
+    dom_count: List[int] = []
+
+    def keyset_of(keys) -> int:
+        ks = tuple(sorted(set(keys)))
+        assert all(ks), "an empty topologyKey in a required term is an error in the reference (predicates.go:1311-1313); preferred terms with one never match"
+        if ks not in keysets:
+            keysets[ks] = len(keysets)
+            vals: Dict[Tuple[str, ...], int] = {}
+            row = np.full(N, -1, dtype=np.int32)
+            for i, n in enumerate(nodes):
+                if all(k in n.labels for k in ks):
+                    v = tuple(n.labels[k] for k in ks)
+                    row[i] = vals.setdefault(v, len(vals))
+            dom_rows.append(row)
+            dom_count.append(len(vals))
+        return keysets[ks]
+
+    # ---- pod types (namespace, labels, affinity spec): all matching is done between types ----
+    types: Dict[Tuple, int] = {}
+    reps: List[Pod] = []
+
+    def type_of(p: Pod) -> int:
+        sg = _aff_sig(p)
+        if sg not in types:
+            types[sg] = len(types)
+            reps.append(p)
+        return types[sg]
+
+    ptype = [type_of(p) for p in pending]
+    ltype = [type_of(p) for p in listed]
+    ttype = [type_of(p) for p in in_tasks]
+    NTY = len(reps)
+
+    def req_terms(p, anti):
+        a = p.pod_anti_affinity if anti else p.pod_affinity
+        return list(a.required) if a is not None else []
+
+    # ---- predicate groups ----
+    groups: Dict[Tuple, int] = {}
+    g_keyset: List[int] = []
+    g_member = []                  # per group: function(type id) -> bool, cached as a list over types
+    pend_types = sorted(set(ptype))
+
+    def group_of(key, ks, member_fn):
+        if key not in groups:
+            groups[key] = len(groups)
+            g_keyset.append(ks)
+            g_member.append([bool(member_fn(reps[ty])) for ty in range(NTY)])
+        return groups[key]
+
+    forbid_ty = {ty: 0 for ty in pend_types}
+    need_ty = {ty: -1 for ty in pend_types}
+    self_ty = {ty: False for ty in pend_types}
+    # (A) required anti-affinity terms pods own: symmetric check (satisfiesExistingPodsAntiAffinity, predicates.go:1400-1439)
+    owner_types = sorted(set(ltype) | set(ptype))
+    for oty in owner_types:
+        owner = reps[oty]
+        for term in req_terms(owner, True):
+            if not term.topology_key:
+                continue            # node.Labels[""] never exists: the term can reject nothing (:1366)
+            props = _term_props(owner, term)
+            victims = [ty for ty in pend_types if _props_match(reps[ty], props)]
+            if not victims:
+                continue
+            akey = ("A", props, term.topology_key)
+            def owns(x, props=props, key=term.topology_key):
+                return any(_term_props(x, t) == props and t.topology_key == key for t in req_terms(x, True))
+            g = group_of(akey, keyset_of([term.topology_key]), owns)
+            for ty in victims:
+                forbid_ty[ty] |= 1 << g
+    # (B) the pending pods' own required terms (satisfiesPodsAffinityAntiAffinity slow path, :1516-1562)
+    for ty in pend_types:
+        p = reps[ty]
+        for anti in (False, True):
+            terms = req_terms(p, anti)
+            if not terms:
+                continue
+            props = frozenset(_term_props(p, t) for t in terms)
+            ks = keyset_of([t.topology_key for t in terms])
+            g = group_of(("B", props, ks), ks, lambda x, props=props: all(_props_match(x, pr) for pr in props))
+            if anti:
+                forbid_ty[ty] |= 1 << g
+            else:
+                need_ty[ty] = g
+                self_ty[ty] = all(_props_match(p, pr) for pr in props)      # targetPodMatchesAffinityOfPod(pod, pod)
+    NG = len(groups)
+    assert NG <= abi.KB_MAX_AFF_GROUPS, "more than 64 inter-pod affinity counter groups"
+    g_off = np.zeros(NG + 1, dtype=np.int64)
+    for g in range(NG):
+        g_off[g + 1] = g_off[g] + dom_count[g_keyset[g]]
+    count0 = np.zeros(int(g_off[NG]), dtype=np.int32)
+    total0 = np.zeros(NG, dtype=np.int32)
+    for p, ty in zip(listed, ltype):
+        n = nidx[p.node_name]
+        for g in range(NG):
+            if g_member[g][ty]:
+                total0[g] += 1
+                d = dom_rows[g_keyset[g]][n]
+                if d >= 0:
+                    count0[g_off[g] + d] += 1
+    contrib_ty = {ty: sum((1 << g) for g in range(NG) if g_member[g][ty]) for ty in pend_types}
+
+    # ---- priority kinds + weights (interpod_affinity.go:119-171) ----
+    def pref_terms(p, anti):
+        a = p.pod_anti_affinity if anti else p.pod_affinity
+        return list(a.preferred) if a is not None else []
+
+    def weights(P: Pod, X: Pod) -> Dict[str, int]:
+        """incoming pod P, existing pod X -> {topologyKey: weight} (processPod)."""
+        w: Dict[str, int] = {}
+        def add(key, v):
+            if key and v:
+                w[key] = w.get(key, 0) + v
+        for (wt, t) in pref_terms(P, False):
+            if _props_match(X, _term_props(P, t)):
+                add(t.topology_key, wt)
+        for (wt, t) in pref_terms(P, True):
+            if _props_match(X, _term_props(P, t)):
+                add(t.topology_key, -wt)
+        if X.pod_affinity is not None:
+            for t in X.pod_affinity.required:                       # hardPodAffinityWeight = 1 (nodeorder.go:159)
+                if _props_match(P, _term_props(X, t)):
+                    add(t.topology_key, 1)
+            for (wt, t) in X.pod_affinity.preferred:
+                if _props_match(P, _term_props(X, t)):
+                    add(t.topology_key, wt)
+        if X.pod_anti_affinity is not None:
+            for (wt, t) in X.pod_anti_affinity.preferred:
+                if _props_match(P, _term_props(X, t)):
+                    add(t.topology_key, -wt)
+        return {k: v for k, v in w.items() if v}
+
+    wtab = {(pt, xt): weights(reps[pt], reps[xt]) for pt in pend_types for xt in range(NTY)}
+    kinds: Dict[Tuple, int] = {}
+    kind_unbound: List[int] = []
+
+    def kind_of(xt: int, unbound: bool) -> int:
+        vec = tuple(tuple(sorted(wtab[(pt, xt)].items())) for pt in pend_types)
+        if not any(vec):
+            return -1
+        k = (vec, unbound)
+        if k not in kinds:
+            kinds[k] = len(kinds)
+            kind_unbound.append(1 if unbound else 0)
+        return kinds[k]
+
+    xkind = [kind_of(ty, False) for ty in ttype]                    # pods already on nodes: Spec.NodeName is set
+    pkind_ty = {ty: kind_of(ty, True) for ty in pend_types}          # a task placed this session: Spec.NodeName stays ""
+    NK = len(kinds)
+    kc0 = np.zeros((max(1, NK), N), dtype=np.int32)
+    for p, k in zip(in_tasks, xkind):
+        if k >= 0:
+            kc0[k, nidx[p.node_name]] += 1
+    kind_rep: Dict[int, int] = {}
+    for ty, k in list(zip(ttype, xkind)) + [(ty, pkind_ty[ty]) for ty in pend_types]:
+        if k >= 0:
+            kind_rep.setdefault(k, ty)
+    wlist_ty = {}
+    for pt in pend_types:
+        lst = []
+        for k in range(NK):
+            for key, v in sorted(wtab[(pt, kind_rep[k])].items()):
+                lst.append((k, keyset_of([key]), v))
+        wlist_ty[pt] = lst
+    w_off = np.zeros(T + 1, dtype=np.uint32)
+    wk, wks, wv = [], [], []
+    for t in range(T):
+        for (k, ks, v) in wlist_ty[ptype[t]]:
+            wk.append(k); wks.append(ks); wv.append(v)
+        w_off[t + 1] = len(wk)
+
+    for t in range(T):
+        ty = ptype[t]
+        p = pending[t]
+        if p.pod_affinity is not None or p.pod_anti_affinity is not None:
+            s.task_flags[t] |= abi.KB_TASK_HAS_POD_AFFINITY
+        if self_ty[ty]:
+            s.task_flags[t] |= abi.KB_TASK_AFF_SELF_MATCH
+    if any(p.pod_affinity is not None or p.pod_anti_affinity is not None for p in existing):
+        s.flags = int(getattr(s, "flags", 0)) | abi.KB_SNAPSHOT_PLACED_POD_AFFINITY
+
+    NKS = len(keysets)
+    pa = {
+        "n_keysets": NKS, "n_groups": NG, "n_kinds": NK, "n_weights": len(wk), "first_unbound_node": -1,
+        "node_domain": np.stack(dom_rows).astype(np.int32) if NKS else np.zeros((1, max(1, N)), dtype=np.int32),
+        "keyset_domains": np.array(dom_count if NKS else [0], dtype=np.uint32),
+        "group_keyset": np.array(g_keyset if NG else [0], dtype=np.uint32),
+        "group_count0": count0 if count0.size else np.zeros(1, dtype=np.int32),
+        "group_total0": total0 if NG else np.zeros(1, dtype=np.int32),
+        "task_forbid": np.array([forbid_ty[ty] for ty in ptype] or [0], dtype=np.uint64),
+        "task_need": np.array([need_ty[ty] for ty in ptype] or [-1], dtype=np.int32),
+        "task_contrib": np.array([contrib_ty[ty] for ty in ptype] or [0], dtype=np.uint64),
+        "task_kind": np.array([pkind_ty[ty] for ty in ptype] or [-1], dtype=np.int32),
+        "node_kind_count0": kc0,
+        "kind_unbound": np.array(kind_unbound or [0], dtype=np.uint8),
+        "task_weight_off": w_off,
+        "weight_kind": np.array(wk or [0], dtype=np.int32),
+        "weight_keyset": np.array(wks or [0], dtype=np.int32),
+        "weight_value": np.array(wv or [0], dtype=np.int64),
+    }
+
+    # ---- the raw objects, for the oracle (oracle/kb_oracle.h kbo_pod_objects): pods = pending tasks, then the existing pods ----
+    strs: Dict[str, int] = {}
+    def sid(x: str) -> int:
+        return strs.setdefault(x, len(strs))
+    allpods = list(pending) + list(existing)
+    topo_keys: Dict[str, int] = {}
+    ob = {"P": len(allpods), "T": T, "pod_ns": [], "lab_off": [0], "lab_key": [], "lab_val": [], "has_aff": [], "has_anti": [],
+          "term_off": [0], "term_kind": [], "term_weight": [], "term_topo": [], "term_nil": [], "term_ns_off": [0], "term_ns": [],
+          "term_req_off": [0], "req_key": [], "req_op": [], "req_val_off": [0], "req_val": [],
+          "pod_node": [], "pod_listed": [], "pod_in_tasks": [], "pod_unbound": []}
+    opn = {"In": 0, "NotIn": 1, "Exists": 2, "DoesNotExist": 3}
+    lset, tset = set(id(p) for p in listed), set(id(p) for p in in_tasks)
+    for p in allpods:
+        ob["pod_ns"].append(sid(p.namespace))
+        for k, v in sorted(p.labels.items()):
+            ob["lab_key"].append(sid(k)); ob["lab_val"].append(sid(v))
+        ob["lab_off"].append(len(ob["lab_key"]))
+        ob["has_aff"].append(1 if p.pod_affinity is not None else 0)
+        ob["has_anti"].append(1 if p.pod_anti_affinity is not None else 0)
+        for kind, a in ((0, p.pod_affinity), (1, p.pod_anti_affinity)):
+            if a is None:
+                continue
+            for (wt, term) in [(0, t) for t in a.required] + [(w, t) for (w, t) in a.preferred]:
+                pref = not any(term is t for t in a.required)
+                ob["term_kind"].append(kind + (2 if pref else 0))
+                ob["term_weight"].append(wt)
+                ob["term_topo"].append(topo_keys.setdefault(term.topology_key, len(topo_keys)) if term.topology_key else -1)
+                ob["term_nil"].append(1 if term.nil_selector else 0)
+                for ns in term.namespaces:
+                    ob["term_ns"].append(sid(ns))
+                ob["term_ns_off"].append(len(ob["term_ns"]))
+                for k, v in sorted(term.match_labels.items()):
+                    ob["req_key"].append(sid(k)); ob["req_op"].append(0); ob["req_val"].append(sid(v)); ob["req_val_off"].append(len(ob["req_val"]))
+                for (k, op, vals) in term.match_expressions:
+                    ob["req_key"].append(sid(k)); ob["req_op"].append(opn[op])
+                    for v in vals:
+                        ob["req_val"].append(sid(v))
+                    ob["req_val_off"].append(len(ob["req_val"]))
+                ob["term_req_off"].append(len(ob["req_key"]))
+        ob["term_off"].append(len(ob["term_kind"]))
+    for p in existing:
+        ob["pod_node"].append(nidx[p.node_name])
+        ob["pod_listed"].append(1 if id(p) in lset else 0)
+        ob["pod_in_tasks"].append(1 if id(p) in tset else 0)
+        ob["pod_unbound"].append(0)
+    ob["n_topo"] = len(topo_keys)
+    nt = np.full((max(1, len(topo_keys)), max(1, N)), -1, dtype=np.int32)
+    for key, ki in topo_keys.items():
+        for i, n in enumerate(nodes):
+            if key in n.labels:
+                nt[ki, i] = sid("\0v:" + n.labels[key])
+    ob["node_topo"] = nt
+    return pa, ob

@@ -1,0 +1,152 @@
+// kb_aff.h — inter-pod (anti)affinity on the device: predicate step 10 (InterPodAffinityMatches) and InterPodAffinityPriority
+// over the counters of include/kbgpu.h kb_pod_affinity.  Host/device shared (KB_HD): the kernels (kb_kernels.cuh), the host
+// build (kb_build.h) and tests/emu compile the same functions.
+//
+// Reference (paths relative to /root/reference):
+//   predicate   vendor/k8s.io/kubernetes/pkg/scheduler/algorithm/predicates/predicates.go:1261-1572 (slow path, meta == nil),
+//               pods from pkg/scheduler/plugins/util/util.go:37-85 (AllocatedStatus tasks of the session's jobs)
+//   priority    vendor/k8s.io/kubernetes/pkg/scheduler/algorithm/priorities/interpod_affinity.go:99-235 over the FEASIBLE nodes,
+//               pods from NodeInfo.Tasks; pkg/scheduler/plugins/nodeorder/nodeorder.go:49-63 (node of a not-yet-bound pod)
+//
+// What moves during a cycle (all of it written by the ONE replaying thread, read by the scans of later launches):
+//   cnt[g][domain], total[g]   members of counter group g — a task joins when ssn.Allocate places it (status Allocated is an
+//                              AllocatedStatus; Pipelined is not, so ssn.Pipeline does not count)
+//   kind_count[kind][node]     pods per kind in NodeInfo.Tasks — Allocate and Pipeline both call node.AddTask
+//   first_unbound              lowest node index holding a pod with an empty Spec.NodeName — every pod placed in the session
+// A placement can change the feasibility / score of EVERY node of a topology domain, so the "one node column changes per
+// placement" rule behind the candidate lists does not hold for a class whose keys read these counters: such a
+// class (ClassAff.reads) gets a fresh scan per task — the replay stops after one placement.
+#ifndef KB_AFF_H_
+#define KB_AFF_H_
+
+#include "kb_core.h"
+
+namespace kb {
+
+struct ClassAff {
+  uint64_t forbid;        // groups whose members in the node's domain reject the node
+  uint64_t contrib;       // groups the task joins once Allocated
+  uint64_t w_keysets;     // key sets that appear in the class's weight list
+  int32_t  need;          // group the required pod-affinity terms need, -1 none
+  int32_t  kind;          // kind of the placed pod, -1 none
+  uint32_t w_off, w_cnt;  // weight list (AffDev.w_*)
+  uint32_t self_match;    // KB_TASK_AFF_SELF_MATCH
+  uint32_t reads;         // forbid | need | weights: this class's keys depend on the counters
+};
+
+struct AffDev {
+  uint32_t on;                    // the session carries kb_pod_affinity
+  uint32_t n_keysets, n_groups, n_kinds;
+  uint32_t has_weights;           // some class has a weight list: the priority passes run before every visit
+  int32_t  w_podaff;              // podaffinity.weight (nodeorder.go:111-117)
+  uint32_t dom_total;             // sum of the key sets' domain counts (size of dom_sum)
+  uint32_t pad0;
+  const int32_t*  node_domain;    // [n_keysets][N]
+  const uint32_t* keyset_off;     // [n_keysets + 1] offsets into dom_sum
+  const uint32_t* group_keyset;   // [n_groups]
+  const uint32_t* group_off;      // [n_groups] offsets into cnt
+  const ClassAff* cls;            // [C]
+  const int32_t*  w_kind;
+  const int32_t*  w_keyset;
+  const int64_t*  w_value;
+  const uint8_t*  kind_unbound;   // [n_kinds]
+  int32_t*   cnt;                 // mutable: group counters
+  int32_t*   total;               // [n_groups]
+  int32_t*   kind_count;          // [n_kinds][N]
+  int32_t*   first_unbound;       // [1], -1 none
+  long long* dom_sum;             // [dom_total] scratch of the priority: weight per domain over the feasible nodes (pass 1)
+  long long* minmax;              // [2] min / max count over the feasible nodes (pass 2)
+};
+
+// does a view (allocate: nodeorder as configured; backfill: off) read the counters for this class?
+KB_HD bool aff_reads(const ClassAff& ca, const bool nodeorder) { return ca.forbid != 0 || ca.need >= 0 || (ca.w_cnt != 0 && nodeorder); }
+
+// predicate step 10 for a pod of class `ca` on node n (the predicates plugin must be enabled; the caller checks)
+KB_HD bool aff_pred(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t n) {
+  bool ok = true;
+  uint64_t f = ca.forbid;
+  while (f) {                                    // satisfiesExistingPodsAntiAffinity (:1400-1439) + the pod's own anti-affinity (:1526-1533)
+#if defined(__CUDA_ARCH__)
+    const uint32_t g = (uint32_t)__ffsll((long long)f) - 1u;
+#else
+    const uint32_t g = (uint32_t)__builtin_ctzll(f);
+#endif
+    f &= f - 1;
+    const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
+    if (d >= 0 && A.cnt[A.group_off[g] + (uint32_t)d] > 0) ok = false;
+  }
+  if (ca.need >= 0) {                            // the pod's required affinity terms (:1516-1560)
+    const uint32_t g = (uint32_t)ca.need;
+    const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
+    const bool match = d >= 0 && A.cnt[A.group_off[g] + (uint32_t)d] > 0;
+    const bool first_of_series = A.total[g] == 0 && ca.self_match;
+    ok = ok && (match || first_of_series);
+  }
+  return ok;
+}
+
+// priority pass 1, one FEASIBLE node m: the weight its pods contribute, added to the domain of the "pod's node" per key set.
+// `add(slot, value)` accumulates into dom_sum (atomicAdd on the device).
+template <class Add>
+KB_HD void aff_pass1_node(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t m, Add add) {
+  const int32_t fu = *A.first_unbound;
+  for (uint32_t i = ca.w_off; i < ca.w_off + ca.w_cnt; ++i) {
+    const uint32_t e = (uint32_t)A.w_kind[i], ks = (uint32_t)A.w_keyset[i];
+    const int32_t c = A.kind_count[(size_t)e * N + m];
+    if (!c) continue;
+    const uint32_t fixed = A.kind_unbound[e] ? (uint32_t)fu : m;     // cachedNodeInfo.GetNodeInfo (nodeorder.go:49-63)
+    const int32_t d = A.node_domain[(size_t)ks * N + fixed];
+    if (d >= 0) add(A.keyset_off[ks] + (uint32_t)d, (long long)A.w_value[i] * (long long)c);
+  }
+}
+// pass 2 / 3, one feasible node n: pm.counts[n]
+KB_HD long long aff_count_node(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t n) {
+  long long count = 0;
+  uint64_t k = ca.w_keysets;
+  while (k) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t ks = (uint32_t)__ffsll((long long)k) - 1u;
+#else
+    const uint32_t ks = (uint32_t)__builtin_ctzll(k);
+#endif
+    k &= k - 1;
+    const int32_t d = A.node_domain[(size_t)ks * N + n];
+    if (d >= 0) count += A.dom_sum[A.keyset_off[ks] + (uint32_t)d];
+  }
+  return count;
+}
+// interpod_affinity.go:222-228: fScore = MaxPriority * (float64(count - min) / float64(max - min)); int(fScore); 0 if max == min
+KB_HD int64_t aff_score(const long long count, const long long mn, const long long mx) {
+  if (mx - mn <= 0) return 0;
+  return (int64_t)KB_D2LL(KB_DMUL(10.0, KB_DDIV(KB_LL2D(count - mn), KB_LL2D(mx - mn))));
+}
+KB_HD uint64_t aff_add_score(const uint64_t key, const int32_t w_podaff, const int64_t score) {
+  if (!key) return key;
+  const int64_t hi = (int64_t)(key >> 32) + (int64_t)w_podaff * score;
+  return ((uint64_t)hi << 32) | (key & 0xFFFFFFFFull);
+}
+
+// One placement of a task of class `ca` on node n (single thread): what ssn.Allocate / ssn.Pipeline change for the pods that
+// come after it.
+KB_HD void aff_commit(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t n, const bool allocated) {
+  if (allocated) {
+    uint64_t c = ca.contrib;
+    while (c) {
+#if defined(__CUDA_ARCH__)
+      const uint32_t g = (uint32_t)__ffsll((long long)c) - 1u;
+#else
+      const uint32_t g = (uint32_t)__builtin_ctzll(c);
+#endif
+      c &= c - 1;
+      A.total[g] += 1;
+      const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
+      if (d >= 0) A.cnt[A.group_off[g] + (uint32_t)d] += 1;
+    }
+  }
+  if (ca.kind >= 0) A.kind_count[(size_t)ca.kind * N + n] += 1;
+  const int32_t fu = *A.first_unbound;
+  if (fu < 0 || (int32_t)n < fu) *A.first_unbound = (int32_t)n;
+}
+
+}  // namespace kb
+#endif  // KB_AFF_H_

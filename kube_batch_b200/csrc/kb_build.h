@@ -13,6 +13,7 @@
 #include <cstring>
 #include <string>
 #include <unordered_map>
+#include <map>
 #include <vector>
 
 #include "kb_ctl.h"
@@ -61,6 +62,7 @@ struct HostConf {
   EvalConf cf{};
   uint32_t jobcmp[4] = {0, 0, 0, 0};
   int w_nodeaff = 1;                // nodeaffinity.weight (nodeorder.go:111-117); only read when the session has preferred terms
+  int w_podaff = 1;                 // podaffinity.weight; only read when the session carries kb_pod_affinity
   bool task_order_priority = false, queue_order_proportion = false, proportion_present = false, drf_present = false,
        gang_ready = false;
   // reclaim / preempt (kb_evict.h): EvictFn bits of the first tier with an enabled reclaimableFn / preemptableFn, and whether
@@ -142,7 +144,7 @@ inline int resolve_conf(BuildErr* e, const kb_plugin_conf* conf, uint32_t R, uin
   hc.cf.mem_pressure = memp; hc.cf.disk_pressure = diskp; hc.cf.pid_pressure = pidp;
   hc.cf.w_least = w_least; hc.cf.w_most = w_most; hc.cf.w_balanced = w_bal;
   hc.w_nodeaff = w_nodeaff;           // NodeAffinityPriority is identically 0 without preferred terms
-  (void)w_podaff;                     // InterPodAffinityPriority: tasks with such terms are refused
+  hc.w_podaff = w_podaff;             // InterPodAffinityPriority is identically 0 without inter-pod terms (kb_pod_affinity)
   const long lim = 1 << 20;
   if (labs(w_least) > lim || labs(w_most) > lim || labs(w_bal) > lim) return bfail(e, KB_E_BADARG, "nodeorder weight out of range");
   hc.cf.score_bias = 10ll * ((w_least < 0 ? -w_least : 0) + (w_most < 0 ? -w_most : 0) + (w_bal < 0 ? -w_bal : 0));
@@ -213,9 +215,10 @@ inline bool hr_is_empty(uint32_t R, const HostRes& r) {                    // :9
 
 
 struct OffMut { size_t tiles, used, job_pos, job_ready, job_alloc, job_share, job_placed, q_head, dyn, q_alloc, q_share, qheap, dec, cand, ctl, sendbuf, recvbuf,
-                bf_job_pos, bf_ctl, pipe_g, modlog, pcand, ppref; };
+                bf_job_pos, bf_ctl, pipe_g, modlog, pcand, ppref, aff_cnt, aff_total, aff_kind_count, aff_first_unbound, aff_dom_sum, aff_minmax; };
 struct OffImm { size_t classes, ord_task, ord_class, ord_run, ord_peek, job_ord_off, job_min, job_queue, job_prio, job_tb, q_static, q_static_off, q_des, q_des_p, q_ctime, task_class, job_ready0,
-                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes, ord_chain, class_pref; };
+                bf_ord_task, bf_ord_class, bf_ord_run, bf_ord_peek, bf_job_ord_off, bf_jobs, bf_jobs_off, bf_classes, ord_chain, class_pref,
+                aff_node_domain, aff_keyset_off, aff_group_keyset, aff_group_off, aff_cls, aff_w_kind, aff_w_keyset, aff_w_value, aff_kind_unbound; };
 
 struct BuiltSession {
   Slab mut, imm;
@@ -231,6 +234,7 @@ struct BuiltSession {
   uint32_t pipe = 0, pipe_S = 0, pipe_tpc = 0;   // persistent pipeline (cycle_kernel): scanner CTAs, resident tiles per scanner CTA
   std::vector<ClassPref> class_pref; // [C] preferred node-affinity terms per class — HOST ONLY (read by tests/emu's prototype of
   bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
+  AffDev aff{};                      // inter-pod (anti)affinity: sizes and flags (pointers are set by bind())
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
   std::vector<uint32_t> q_alloc_present;   // [Q] scalar presence of proportion's queueAttr.allocated at session open (kb_evict.h: Resource.Less)
 
@@ -279,6 +283,17 @@ struct BuiltSession {
     D.ppref = (unsigned long long*)(mb + om.ppref);
     D.class_pref = has_pref ? (const ClassPref*)(ib + oi.class_pref) : nullptr;
     D.w_nodeaff = hc.w_nodeaff;
+    D.aff = aff;
+    if (aff.on) {
+      D.aff.node_domain = (const int32_t*)(ib + oi.aff_node_domain); D.aff.keyset_off = (const uint32_t*)(ib + oi.aff_keyset_off);
+      D.aff.group_keyset = (const uint32_t*)(ib + oi.aff_group_keyset); D.aff.group_off = (const uint32_t*)(ib + oi.aff_group_off);
+      D.aff.cls = (const ClassAff*)(ib + oi.aff_cls);
+      D.aff.w_kind = (const int32_t*)(ib + oi.aff_w_kind); D.aff.w_keyset = (const int32_t*)(ib + oi.aff_w_keyset);
+      D.aff.w_value = (const int64_t*)(ib + oi.aff_w_value); D.aff.kind_unbound = (const uint8_t*)(ib + oi.aff_kind_unbound);
+      D.aff.cnt = (int32_t*)(mb + om.aff_cnt); D.aff.total = (int32_t*)(mb + om.aff_total);
+      D.aff.kind_count = (int32_t*)(mb + om.aff_kind_count); D.aff.first_unbound = (int32_t*)(mb + om.aff_first_unbound);
+      D.aff.dom_sum = (long long*)(mb + om.aff_dom_sum); D.aff.minmax = (long long*)(mb + om.aff_minmax);
+    }
     D.job_ord_off = (uint32_t*)(ib + oi.job_ord_off); D.job_min_avail = (int32_t*)(ib + oi.job_min);
     D.job_queue = (uint32_t*)(ib + oi.job_queue); D.job_prio = (int32_t*)(ib + oi.job_prio); D.job_tb_rank = (uint32_t*)(ib + oi.job_tb);
     D.q_static = (uint32_t*)(ib + oi.q_static); D.q_static_off = (uint32_t*)(ib + oi.q_static_off);
@@ -294,9 +309,17 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
                          int pipe_mode = 0 /* persistent pipeline (cycle_kernel): 0 off, 1 when the geometry allows it */) {
   if (!s) return bfail(e, KB_E_BADARG, "snapshot is NULL");
   if (s->abi_version != KB_ABI_VERSION) return bfail(e, KB_E_BADARG, "snapshot abi_version %u != %u", s->abi_version, KB_ABI_VERSION);
-  if (s->flags & KB_SNAPSHOT_PLACED_POD_AFFINITY)
+  const kb_pod_affinity* pa = s->pod_affinity;
+  if ((s->flags & KB_SNAPSHOT_PLACED_POD_AFFINITY) && !pa)
     return bfail(e, KB_E_UNSUPPORTED_FEATURE, "a placed pod carries inter-pod (anti)affinity terms: the reference lets it reject nodes for other pods "
-                 "(predicates.go:1261-1288), which this build does not model (no CPU fallback)");
+                 "(predicates.go:1261-1288); the flattener must hand over kb_snapshot.pod_affinity (no CPU fallback)");
+  if (pa) {
+    // the counters of a topology domain change the keys of many nodes at once: per-visit kernels, fresh scan per task for the
+    // classes that read them (kb_aff.h); no look-ahead lists, no overlap, no node sharding
+    if (pa->n_groups > KB_MAX_AFF_GROUPS || pa->n_keysets > 64) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "kb_pod_affinity: more than 64 counter groups / key sets");
+    if (world > 1) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "inter-pod affinity: not with a sharded node axis (KB_ENGINE_SHARD)");
+    pipe_mode = 0; overlap_mode = 0; kchain = 1;
+  }
   if (s->flags & ~KB_SNAPSHOT_PLACED_POD_AFFINITY) return bfail(e, KB_E_BADARG, "unknown kb_snapshot.flags bits 0x%x", s->flags);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
   if (s->Q > KB_MAX_Q) return bfail(e, KB_E_BADARG, "Q=%u > KB_MAX_Q", s->Q);
@@ -337,6 +360,40 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     }
     return cp;
   };
+  // inter-pod affinity: tasks with the same masks / kind / weight list share an "aff id", which is part of the class identity
+  std::vector<uint32_t> aff_id(pa ? T : 0, 0);
+  std::vector<ClassAff> aff_tab;                  // by aff id; w_off / w_cnt index the packed lists below
+  std::vector<int32_t> aff_wk, aff_wks; std::vector<int64_t> aff_wv;
+  if (pa) {
+    std::map<std::vector<int64_t>, uint32_t> ids;
+    for (uint32_t t = 0; t < T; ++t) {
+      std::vector<int64_t> key = {(int64_t)pa->task_forbid[t], (int64_t)pa->task_contrib[t], (int64_t)pa->task_need[t], (int64_t)pa->task_kind[t],
+                                  (int64_t)((s->task_flags[t] & KB_TASK_AFF_SELF_MATCH) ? 1 : 0)};
+      const uint32_t w0 = pa->task_weight_off[t], w1 = pa->task_weight_off[t + 1];
+      if (w1 < w0 || w1 > pa->n_weights) return bfail(e, KB_E_BADARG, "kb_pod_affinity: task_weight_off is not monotone at task %u", t);
+      for (uint32_t i = w0; i < w1; ++i) { key.push_back(pa->weight_kind[i]); key.push_back(pa->weight_keyset[i]); key.push_back(pa->weight_value[i]); }
+      auto it = ids.find(key);
+      if (it == ids.end()) {
+        if (pa->task_need[t] >= (int32_t)pa->n_groups || pa->task_kind[t] >= (int32_t)pa->n_kinds) return bfail(e, KB_E_BADARG, "kb_pod_affinity: task %u names a group / kind out of range", t);
+        if (pa->n_groups < 64 && ((pa->task_forbid[t] | pa->task_contrib[t]) >> pa->n_groups)) return bfail(e, KB_E_BADARG, "kb_pod_affinity: task %u names a group out of range", t);
+        ClassAff ca; memset(&ca, 0, sizeof ca);
+        ca.forbid = pa->task_forbid[t]; ca.contrib = pa->task_contrib[t]; ca.need = pa->task_need[t]; ca.kind = pa->task_kind[t];
+        ca.self_match = (s->task_flags[t] & KB_TASK_AFF_SELF_MATCH) ? 1u : 0u;
+        ca.w_off = (uint32_t)aff_wk.size(); ca.w_cnt = w1 - w0;
+        for (uint32_t i = w0; i < w1; ++i) {
+          if (pa->weight_kind[i] < 0 || pa->weight_kind[i] >= (int32_t)pa->n_kinds || pa->weight_keyset[i] < 0 || pa->weight_keyset[i] >= (int32_t)pa->n_keysets)
+            return bfail(e, KB_E_BADARG, "kb_pod_affinity: weight entry %u names a kind / key set out of range", i);
+          aff_wk.push_back(pa->weight_kind[i]); aff_wks.push_back(pa->weight_keyset[i]); aff_wv.push_back(pa->weight_value[i]);
+          ca.w_keysets |= 1ull << pa->weight_keyset[i];
+        }
+        ca.reads = (ca.forbid != 0 || ca.need >= 0 || ca.w_cnt > 0) ? 1u : 0u;
+        it = ids.emplace(key, (uint32_t)aff_tab.size()).first;
+        aff_tab.push_back(ca);
+      }
+      aff_id[t] = it->second;
+    }
+    if (aff_tab.size() >= (1u << 24)) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "kb_pod_affinity: too many distinct affinity signatures");
+  }
   std::vector<uint32_t> task_class(T, 0);
   std::vector<uint8_t> task_empty(T, 0);
   {
@@ -356,6 +413,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     // t and t-1 (bit patterns, like the memcmp of the records below) is far cheaper than building and hashing a record.
     auto bits = [](const double* a, size_t i) { uint64_t u; memcpy(&u, a + i, 8); return u; };
     auto same_as_prev = [&](uint32_t t) {
+      if (pa && aff_id[t] != aff_id[t - 1]) return false;
       if (s->task_flags[t] != s->task_flags[t - 1] || s->task_n_aff_terms[t] != s->task_n_aff_terms[t - 1] ||
           s->task_nz_cpu[t] != s->task_nz_cpu[t - 1] || s->task_nz_mem[t] != s->task_nz_mem[t - 1]) return false;
       if (s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) {
@@ -383,8 +441,10 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         task_class[t] = prev_class; task_empty[t] = task_empty[t - 1];
         continue;
       }
-      if (s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY)
-        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod affinity terms: outside this build (no CPU fallback)", t);
+      if ((s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY) && !pa)
+        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod affinity terms but the snapshot has no kb_pod_affinity (no CPU fallback)", t);
+      if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && pa)
+        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u: preferred node-affinity terms in a session with inter-pod affinity (per-visit kernels do not evaluate NodeAffinityPriority)", t);
       if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && !allow_pref && pipe_mode <= 0)
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries preferred node-affinity terms: only the persistent pipeline (cycle_kernel) evaluates them", t);
       ClassPref cp = pref_of(t);
@@ -402,7 +462,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
       }
       c.nz_cpu = s->task_nz_cpu[t]; c.nz_mem = s->task_nz_mem[t];
       c.n_aff = s->task_n_aff_terms[t];
-      c.flags = s->task_flags[t] & KB_TASK_BEST_EFFORT_QOS;
+      c.flags = (s->task_flags[t] & KB_TASK_BEST_EFFORT_QOS) | (pa ? (aff_id[t] << 8) : 0u);      // bits 8.. = aff id: part of the class identity
       for (uint32_t w = 0; w < W; ++w) {
         c.sel_req[w] = s->task_sel_req[(size_t)w * T + t];
         c.tol[w] = s->task_tol[(size_t)w * T + t];
@@ -443,6 +503,32 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node affinity: only the plain launch mode is prototyped");
   if (B.has_pref) hc.cf.score_bias += 10ll * (hc.w_nodeaff < 0 ? -(int64_t)hc.w_nodeaff : 0);
   const uint32_t C = (uint32_t)classes.size();
+  B.aff = AffDev{};
+  std::vector<uint32_t> aff_keyset_off, aff_group_off;
+  if (pa) {
+    AffDev& A = B.aff;
+    A.on = 1; A.n_keysets = pa->n_keysets; A.n_groups = pa->n_groups; A.n_kinds = pa->n_kinds; A.w_podaff = hc.w_podaff;
+    for (const ClassAff& ca : aff_tab) if (ca.w_cnt) A.has_weights = 1;
+    if (!hc.cf.nodeorder || hc.w_podaff == 0) A.has_weights = 0;          // the priority is not registered / weighs nothing
+    if (A.has_weights) hc.cf.score_bias += 10ll * (hc.w_podaff < 0 ? -(int64_t)hc.w_podaff : 0);
+    aff_keyset_off.assign(pa->n_keysets + 1, 0);
+    for (uint32_t k = 0; k < pa->n_keysets; ++k) {
+      if (pa->keyset_domains[k] > N) return bfail(e, KB_E_BADARG, "kb_pod_affinity: key set %u has more domains than nodes", k);
+      aff_keyset_off[k + 1] = aff_keyset_off[k] + pa->keyset_domains[k];
+    }
+    A.dom_total = aff_keyset_off[pa->n_keysets];
+    aff_group_off.assign(pa->n_groups + 1, 0);
+    for (uint32_t g = 0; g < pa->n_groups; ++g) {
+      if (pa->group_keyset[g] >= pa->n_keysets) return bfail(e, KB_E_BADARG, "kb_pod_affinity: group %u names a key set out of range", g);
+      aff_group_off[g + 1] = aff_group_off[g] + pa->keyset_domains[pa->group_keyset[g]];
+    }
+    for (uint32_t k = 0; k < pa->n_keysets; ++k)
+      for (uint32_t n = 0; n < N; ++n) {
+        const int32_t d = pa->node_domain[(size_t)k * N + n];
+        if (d < -1 || d >= (int32_t)pa->keyset_domains[k]) return bfail(e, KB_E_BADARG, "kb_pod_affinity: node %u has domain %d under key set %u", n, d, k);
+      }
+    if (pa->first_unbound_node < -1 || pa->first_unbound_node >= (int32_t)N) return bfail(e, KB_E_BADARG, "kb_pod_affinity: first_unbound_node out of range");
+  }
 
   // ---------------- per-job TaskOrderFn order (session_plugins.go:318-331, priority.go:40-56) ----------------
   std::vector<uint32_t> ord_task, ord_class, job_ord_off(J + 1, 0);
@@ -566,6 +652,23 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   oi.bf_classes = imm.alloc((size_t)(Tb ? C : 1) * sizeof(ClassRec));
   oi.ord_chain = imm.alloc((size_t)std::max(1u, To) * (KB_CHAIN_MAX - 1) * 4);
   oi.class_pref = imm.alloc((size_t)(B.has_pref ? C : 1) * sizeof(ClassPref));
+  if (pa) {
+    oi.aff_node_domain = imm.alloc((size_t)std::max(1u, pa->n_keysets) * std::max(1u, N) * 4);
+    oi.aff_keyset_off = imm.alloc((size_t)(pa->n_keysets + 1) * 4);
+    oi.aff_group_keyset = imm.alloc((size_t)std::max(1u, pa->n_groups) * 4);
+    oi.aff_group_off = imm.alloc((size_t)(pa->n_groups + 1) * 4);
+    oi.aff_cls = imm.alloc((size_t)C * sizeof(ClassAff));
+    oi.aff_w_kind = imm.alloc(std::max<size_t>(1, aff_wk.size()) * 4);
+    oi.aff_w_keyset = imm.alloc(std::max<size_t>(1, aff_wk.size()) * 4);
+    oi.aff_w_value = imm.alloc(std::max<size_t>(1, aff_wk.size()) * 8);
+    oi.aff_kind_unbound = imm.alloc(std::max(1u, pa->n_kinds));
+    om.aff_cnt = mut.alloc((size_t)std::max(1u, aff_group_off[pa->n_groups]) * 4);
+    om.aff_total = mut.alloc((size_t)std::max(1u, pa->n_groups) * 4);
+    om.aff_kind_count = mut.alloc((size_t)std::max(1u, pa->n_kinds) * std::max(1u, N) * 4);
+    om.aff_first_unbound = mut.alloc(8);
+    om.aff_dom_sum = mut.alloc((size_t)std::max(1u, B.aff.dom_total) * 8);
+    om.aff_minmax = mut.alloc(16);
+  }
   mut.commit(); imm.commit();
 
   B.R = R; B.W = W; B.N = N; B.T = T; B.J = J; B.Q = Q; B.C = C; B.NT = NT; B.ncols = ncols; B.To = To; B.Tb = Tb;
@@ -602,6 +705,29 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   // ---------------- immutable job / queue / class tables ----------------
   memcpy(H.classes, classes.data(), (size_t)C * sizeof(ClassRec));
   if (B.has_pref) memcpy(imm.host.data() + oi.class_pref, class_pref.data(), (size_t)C * sizeof(ClassPref));
+  if (pa) {
+    unsigned char* ib = imm.host.data(); unsigned char* mb = mut.host.data();
+    if (pa->n_keysets && N) memcpy(ib + oi.aff_node_domain, pa->node_domain, (size_t)pa->n_keysets * N * 4);
+    memcpy(ib + oi.aff_keyset_off, aff_keyset_off.data(), aff_keyset_off.size() * 4);
+    if (pa->n_groups) memcpy(ib + oi.aff_group_keyset, pa->group_keyset, (size_t)pa->n_groups * 4);
+    memcpy(ib + oi.aff_group_off, aff_group_off.data(), aff_group_off.size() * 4);
+    ClassAff* hca = (ClassAff*)(ib + oi.aff_cls);
+    for (uint32_t k = 0; k < C; ++k) {
+      const uint32_t id = classes[k].flags >> 8;
+      if (id < aff_tab.size()) hca[k] = aff_tab[id]; else { memset(&hca[k], 0, sizeof(ClassAff)); hca[k].need = -1; hca[k].kind = -1; }
+      if (!B.aff.has_weights) { hca[k].w_cnt = 0; hca[k].w_keysets = 0; hca[k].reads = (hca[k].forbid != 0 || hca[k].need >= 0) ? 1u : 0u; }
+      if (!hc.cf.predicates) { hca[k].forbid = 0; hca[k].need = -1; hca[k].reads = hca[k].w_cnt ? 1u : 0u; }      // step 10 belongs to the predicates plugin
+    }
+    if (!aff_wk.empty()) {
+      memcpy(ib + oi.aff_w_kind, aff_wk.data(), aff_wk.size() * 4); memcpy(ib + oi.aff_w_keyset, aff_wks.data(), aff_wks.size() * 4);
+      memcpy(ib + oi.aff_w_value, aff_wv.data(), aff_wv.size() * 8);
+    }
+    if (pa->n_kinds) memcpy(ib + oi.aff_kind_unbound, pa->kind_unbound, pa->n_kinds);
+    if (aff_group_off[pa->n_groups]) memcpy(mb + om.aff_cnt, pa->group_count0, (size_t)aff_group_off[pa->n_groups] * 4);
+    if (pa->n_groups) memcpy(mb + om.aff_total, pa->group_total0, (size_t)pa->n_groups * 4);
+    if (pa->n_kinds && N) memcpy(mb + om.aff_kind_count, pa->node_kind_count0, (size_t)pa->n_kinds * N * 4);
+    *(int32_t*)(mb + om.aff_first_unbound) = pa->first_unbound_node;
+  }
   if (To) { memcpy(H.ord_task, ord_task.data(), (size_t)To * 4); memcpy(H.ord_class, ord_class.data(), (size_t)To * 4); }
   for (uint32_t j = 0; j < J; ++j)                     // run lengths, right to left inside each job
     for (uint32_t i = job_ord_off[j + 1]; i-- > job_ord_off[j];)

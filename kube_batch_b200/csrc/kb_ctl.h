@@ -14,6 +14,7 @@
 #define KB_CTL_H_
 
 #include "kb_core.h"
+#include "kb_aff.h"
 
 namespace kb {
 
@@ -153,6 +154,7 @@ struct DevSession {
   int32_t w_nodeaff;           // nodeaffinity.weight (nodeorder.go:111-117)
   uint32_t pad_pref;
   uint32_t* dbg;          // 64 progress words in mapped host memory (KB_PIPE_DEBUG=1; NULL otherwise): read by the host watchdog when a cycle hangs
+  AffDev aff;             // inter-pod (anti)affinity tables and counters (kb_aff.h); aff.on == 0: the session carries none
 };
 constexpr uint32_t KB_MAX_WORLD = 8;
 constexpr uint32_t P2P_RANK_U64 = (2 + 2 * KB_MAX_R + 6 + 3 * KB_MAX_W) * 32;         // keys + widest record block + flag row

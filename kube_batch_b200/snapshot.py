@@ -41,6 +41,7 @@ class Snapshot:
         for name, _, dt, shp in abi.SNAPSHOT_ARRAYS:
             setattr(self, name, np.zeros(_shape(shp, dims), dtype=np.dtype(dt)))
         self.meta: Dict[str, object] = {}
+        self.pod_affinity = None       # dict mirroring kb_pod_affinity (builder.py), None = no pod carries inter-pod terms
 
     def dims(self) -> Dict[str, int]:
         return {"R": self.R, "W": self.W, "N": self.N, "T": self.T, "J": self.J, "Q": self.Q, "A": abi.KB_MAX_AFF_TERMS,
@@ -76,6 +77,10 @@ class Snapshot:
                 a = np.zeros(1, dtype=a.dtype)
             keep.append(a)
             setattr(s, name, a.ctypes.data_as(ptr))
+        if getattr(self, "pod_affinity", None) is not None:
+            pa, k2 = abi.pod_affinity_to_c(self.pod_affinity)
+            keep += [pa, k2]
+            s.pod_affinity = C.pointer(pa)
         return s, keep
 
     def invalidate(self) -> None:

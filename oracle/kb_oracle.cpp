@@ -445,6 +445,51 @@ inline std::function<void(std::vector<int64_t>&)> NormalizeReduce(int64_t maxPri
   };
 }
 
+// ---------------------------------------------------------------------------------------------
+// inter-pod (anti)affinity on the raw pod objects (kbo_pod_objects)
+// ---------------------------------------------------------------------------------------------
+struct LabelReq { int key, op; std::vector<int> vals; };
+struct AffTerm { int kind, weight, topo; bool nil; std::vector<int> ns; std::vector<LabelReq> reqs; };
+struct PodObj { int ns = 0; std::vector<std::pair<int, int>> labels; bool has_aff = false, has_anti = false; std::vector<AffTerm> terms; };
+struct ExistingPod { uint32_t pod; int node; bool listed, in_tasks, unbound; };
+struct PodWorld {
+  uint32_t T = 0, N = 0, n_topo = 0;
+  std::vector<PodObj> pods;
+  std::vector<ExistingPod> existing;
+  std::vector<int32_t> node_topo;      // [n_topo][N]
+  std::vector<std::vector<uint32_t>> existing_on;   // per node: indices into `existing` with in_tasks
+  int topo(int key, uint32_t node) const { return key < 0 ? -1 : node_topo[(size_t)key * N + node]; }
+  // labels.Requirement.Matches (vendor/k8s.io/apimachinery/pkg/labels/selector.go:193-230)
+  static bool req_matches(const LabelReq& r, const PodObj& p) {
+    const int* val = nullptr;
+    for (auto& kv : p.labels) if (kv.first == r.key) { val = &kv.second; break; }
+    switch (r.op) {
+      case 0: if (!val) return false; for (int v : r.vals) if (v == *val) return true; return false;        // In
+      case 1: if (!val) return true; for (int v : r.vals) if (v == *val) return false; return true;         // NotIn
+      case 2: return val != nullptr;                                                                        // Exists
+      default: return val == nullptr;                                                                       // DoesNotExist
+    }
+  }
+  // priorityutil.PodMatchesTermsNamespaceAndSelector (vendor/.../priorities/util/topologies.go:38-49) with
+  // GetNamespacesFromPodAffinityTerm (:25-36) and metav1.LabelSelectorAsSelector (nil -> Nothing, empty -> Everything)
+  bool matches(const PodObj& owner, const AffTerm& t, const PodObj& pod) const {
+    bool ns_ok = false;
+    if (t.ns.empty()) ns_ok = pod.ns == owner.ns;
+    else for (int n : t.ns) if (n == pod.ns) { ns_ok = true; break; }
+    if (!ns_ok) return false;
+    if (t.nil) return false;
+    for (auto& r : t.reqs) if (!req_matches(r, pod)) return false;
+    return true;
+  }
+  // NodesHaveSameTopologyKey (topologies.go:51-70)
+  bool same_topology(uint32_t a, uint32_t b, int key) const {
+    if (key < 0) return false;
+    const int va = topo(key, a), vb = topo(key, b);
+    return va >= 0 && vb >= 0 && va == vb;
+  }
+};
+thread_local std::shared_ptr<PodWorld> g_pod_world;
+
 struct Session;
 struct Plugin {
   virtual ~Plugin() = default;
@@ -488,6 +533,137 @@ struct Session {
   std::vector<std::vector<uint32_t>> placeholder_alloc;
   std::unordered_map<std::string, uint32_t> nodeByName;   // ssn.Nodes map[string]*NodeInfo, mode A only
   std::vector<std::string> nodeNames;
+
+  std::shared_ptr<PodWorld> pw;         // raw pod objects: inter-pod (anti)affinity is evaluated iff present
+
+  // util.PodLister.FilteredList (plugins/util/util.go:62-85): every AllocatedStatus task of every session job, with the node
+  // TaskInfo.NodeName names.  nodeInfo.Filter passes everything here (a listed pod is in its node's NodeInfo).  fn(pod, node);
+  // returns false if fn did, or if a listed task has no node: a task ssn.Allocate left Allocated although node.AddTask refused it
+  // (session.go:241-262) keeps NodeName "" and CachedNodeInfo.GetNodeInfo("") is an error that fails the predicate (:1386-1393).
+  template <class F>
+  bool for_each_listed_pod(F fn) const {
+    for (const ExistingPod& e : pw->existing) if (e.listed) if (!fn(pw->pods[e.pod], (uint32_t)e.node)) return false;
+    for (const JobInfo& job : Jobs)
+      for (auto& kv : job.TaskStatusIndex) {
+        if (!AllocatedStatus(kv.first)) continue;
+        for (uint32_t id : kv.second) {
+          if (id >= pw->T) continue;                       // Running tasks of kbo_running are the `existing` pods above
+          const TaskInfo& t = Tasks[id];
+          if (t.NodeName < 0) return false;
+          if (!fn(pw->pods[id], (uint32_t)t.NodeName)) return false;
+        }
+      }
+    return true;
+  }
+
+  // PodAffinityChecker.InterPodAffinityMatches (vendor/.../predicates/predicates.go:1261-1288), meta == nil
+  bool InterPodAffinityMatches(const TaskInfo& task, const NodeInfo& node) const {
+    const PodWorld& W_ = *pw;
+    const PodObj& pod = W_.pods[task.idx];
+    const uint32_t n = node.idx;
+    // satisfiesExistingPodsAntiAffinity (:1400-1439): topology pairs of the existing pods' anti-affinity terms that match `pod`
+    // (getMatchingAntiAffinityTopologyPairsOfPod :1354-1376), then any label of the node among them rejects it
+    bool bad = false;
+    bool ok = for_each_listed_pod([&](const PodObj& e, uint32_t en) {
+      if (!e.has_anti) return true;
+      for (const AffTerm& t : e.terms) {
+        if (t.kind != 1) continue;
+        if (!W_.matches(e, t, pod)) continue;
+        const int v = W_.topo(t.topo, en);
+        if (v >= 0 && W_.topo(t.topo, n) == v) bad = true;          // the node carries the pair (key, value)
+      }
+      return true;
+    });
+    if (!ok || bad) return false;
+    if (!pod.has_aff && !pod.has_anti) return true;                   // :1274-1277
+    // satisfiesPodsAffinityAntiAffinity, slow path (:1516-1562)
+    std::vector<const AffTerm*> affinityTerms, antiAffinityTerms;
+    for (const AffTerm& t : pod.terms) { if (t.kind == 0) affinityTerms.push_back(&t); else if (t.kind == 1) antiAffinityTerms.push_back(&t); }
+    // podMatchesPodAffinityTerms (:1296-1320): (matches all terms + topologies, matches all term properties)
+    auto podMatches = [&](const PodObj& target, uint32_t tn, const std::vector<const AffTerm*>& terms, bool* props) {
+      *props = false;
+      for (const AffTerm* t : terms) if (!W_.matches(pod, *t, target)) return false;   // podMatchesAllAffinityTermProperties
+      *props = true;
+      for (const AffTerm* t : terms) if (!W_.same_topology(n, tn, t->topo)) return false;
+      return true;
+    };
+    bool matchFound = false, termsSelectorMatchFound = false, rejected = false;
+    ok = for_each_listed_pod([&](const PodObj& target, uint32_t tn) {
+      if (!matchFound && !affinityTerms.empty()) {
+        bool props = false;
+        const bool m = podMatches(target, tn, affinityTerms, &props);
+        if (props) termsSelectorMatchFound = true;
+        if (m) matchFound = true;
+      }
+      if (!antiAffinityTerms.empty()) {
+        bool props = false;
+        if (podMatches(target, tn, antiAffinityTerms, &props)) { rejected = true; return false; }
+      }
+      return true;
+    });
+    if (rejected) return false;
+    if (!ok) return false;
+    if (!matchFound && !affinityTerms.empty()) {
+      if (termsSelectorMatchFound) return false;
+      // targetPodMatchesAffinityOfPod(pod, pod) (metadata.go:767-778): the first pod of a self-affine series
+      if (!pod.has_aff) return false;
+      for (const AffTerm* t : affinityTerms) if (!W_.matches(pod, *t, pod)) return false;
+    }
+    return true;
+  }
+
+  // InterPodAffinity.CalculateInterPodAffinityPriority (vendor/.../priorities/interpod_affinity.go:99-235) over the feasible
+  // nodes; hardPodAffinityWeight = v1.DefaultHardPodAffinitySymmetricWeight = 1 (nodeorder.go:159).  Returns the scores 0..10.
+  std::vector<int64_t> InterPodAffinityPriority(const TaskInfo& task, const std::vector<uint32_t>& nodes) const {
+    const PodWorld& W_ = *pw;
+    const PodObj& pod = W_.pods[task.idx];
+    std::vector<int64_t> counts(nodes.size(), 0);
+    // cachedNodeInfo.GetNodeInfo (plugins/nodeorder/nodeorder.go:49-63) for a pod whose Spec.NodeName is "": the first node of
+    // the session holding ANY pod with an empty Spec.NodeName (a Go map walk there; ascending node order here)
+    int first_unbound = -1;
+    for (const NodeInfo& ni : Nodes) {
+      bool any = false;
+      for (auto& kv : ni.Tasks) if (kv.first < W_.T) { any = true; break; }      // placed this session: the pod object is unchanged
+      if (!any) for (uint32_t ei : W_.existing_on[ni.idx]) if (W_.existing[ei].unbound) { any = true; break; }
+      if (any) { first_unbound = (int)ni.idx; break; }
+    }
+    auto processTerm = [&](const AffTerm& term, const PodObj& defining, const PodObj& toCheck, uint32_t fixedNode, int64_t weight) {
+      if (!W_.matches(defining, term, toCheck)) return;
+      for (size_t i = 0; i < nodes.size(); ++i) if (W_.same_topology(nodes[i], fixedNode, term.topo)) counts[i] += weight;
+    };
+    auto processPod = [&](const PodObj& existing, bool unbound, uint32_t host) {
+      const uint32_t existingPodNode = unbound ? (uint32_t)first_unbound : host;
+      if (pod.has_aff) for (const AffTerm& t : pod.terms) if (t.kind == 2) processTerm(t, pod, existing, existingPodNode, t.weight);
+      if (pod.has_anti) for (const AffTerm& t : pod.terms) if (t.kind == 3) processTerm(t, pod, existing, existingPodNode, -(int64_t)t.weight);
+      if (existing.has_aff) {
+        for (const AffTerm& t : existing.terms) if (t.kind == 0) processTerm(t, existing, pod, existingPodNode, 1);
+        for (const AffTerm& t : existing.terms) if (t.kind == 2) processTerm(t, existing, pod, existingPodNode, t.weight);
+      }
+      if (existing.has_anti) for (const AffTerm& t : existing.terms) if (t.kind == 3) processTerm(t, existing, pod, existingPodNode, -(int64_t)t.weight);
+    };
+    const bool all = pod.has_aff || pod.has_anti;             // else only nodeInfo.PodsWithAffinity()
+    for (uint32_t m : nodes) {                                 // nodeNameToInfo holds the feasible nodes only (scheduler_helper.go:219-230)
+      for (uint32_t ei : W_.existing_on[m]) {
+        const ExistingPod& e = W_.existing[ei];
+        const PodObj& x = W_.pods[e.pod];
+        if (all || x.has_aff || x.has_anti) processPod(x, e.unbound, m);
+      }
+      for (auto& kv : Nodes[m].Tasks) {
+        if (kv.first >= W_.T) continue;
+        const PodObj& x = W_.pods[kv.first];
+        if (all || x.has_aff || x.has_anti) processPod(x, true, m);
+      }
+    }
+    int64_t maxCount = 0, minCount = 0;
+    for (int64_t c : counts) { if (c > maxCount) maxCount = c; if (c < minCount) minCount = c; }
+    std::vector<int64_t> result(nodes.size(), 0);
+    if (maxCount - minCount > 0)
+      for (size_t i = 0; i < nodes.size(); ++i) {
+        const double fScore = 10.0 * ((double)(counts[i] - minCount) / (double)(maxCount - minCount));
+        result[i] = (int64_t)fScore;
+      }
+    return result;
+  }
 
   Session(uint32_t r, uint32_t w) : A(r), R(r), W(w) {}
 
@@ -1056,8 +1232,9 @@ struct predicatesPlugin : Plugin {
         if ((task.flags & KB_TASK_BEST_EFFORT_QOS) && (node.flags & KB_NODE_MEM_PRESSURE)) return false;
       if (diskPressureEnable && (node.flags & KB_NODE_DISK_PRESSURE)) return false;    // :1654-1660
       if (pidPressureEnable && (node.flags & KB_NODE_PID_PRESSURE)) return false;      // :1664-1671
-      // InterPodAffinityMatches :1261-1288 — no pod in the snapshot carries (anti)affinity terms
-      // (kbo rejects KB_TASK_HAS_POD_AFFINITY), so it is identically true.
+      // InterPodAffinityMatches :1261-1288 — identically true when no pod of the session carries (anti)affinity terms
+      // (no raw pod objects were handed over: kbo_set_pod_objects)
+      if (ssn->pw) return ssn->InterPodAffinityMatches(task, node);
       return true;
     };
   }
@@ -1231,7 +1408,7 @@ int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, st
       ti.Priority = s->task_prio[t]; ti.ctime = s->task_ctime[t]; ti.uid_rank = s->task_uid_rank[t];
       ti.nz_cpu = s->task_nz_cpu[t]; ti.nz_mem = s->task_nz_mem[t];
       ti.flags = s->task_flags[t];
-      if (ti.flags & KB_TASK_HAS_POD_AFFINITY) { g_err = "inter-pod affinity is outside this build"; return KB_E_UNSUPPORTED_FEATURE; }
+      if ((ti.flags & KB_TASK_HAS_POD_AFFINITY) && !g_pod_world) { g_err = "inter-pod affinity terms without the raw pod objects (kbo_set_pod_objects)"; return KB_E_UNSUPPORTED_FEATURE; }
       ti.n_pref = 0;
       for (auto& pw : ti.pref_w) pw = 0;
       for (auto& pr : ti.pref) for (uint32_t w = 0; w < KB_MAX_W; ++w) pr[w] = 0;
@@ -1308,6 +1485,10 @@ int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, st
       if (!pb) { g_err = "Failed to get plugin " + po.Name; return KB_E_UNSUPPORTED_PLUGIN; }
       ssn->plugins[pb->Name()] = std::move(pb);   // later option of the same name overrides, like the Go map
     }
+  if (g_pod_world) {
+    if (g_pod_world->T != T || g_pod_world->N != N) { g_err = "kbo_set_pod_objects: pod objects do not belong to this snapshot"; return KB_E_BADARG; }
+    ssn->pw = g_pod_world;
+  }
   for (auto& kv : ssn->plugins) kv.second->OnSessionOpen(ssn.get());
   ssn->resolvePredicates();
   out = std::move(ssn);
@@ -1417,6 +1598,13 @@ struct Executor {
       c.Reduce(col);
       for (size_t i = 0; i < nodes.size(); ++i) result[i] += (double)(col[i] * (int64_t)c.Weight);
     }
+    // the one `Function` config (scheduler_helper.go:112-124): InterPodAffinityPriority over the whole feasible list
+    if (ssn.pw)
+      for (auto& c : cfgs) {
+        if (c.Name != "InterPodAffinityPriority") continue;
+        const std::vector<int64_t> col = ssn.InterPodAffinityPriority(task, nodes);
+        for (size_t i = 0; i < nodes.size(); ++i) result[i] += (double)(col[i] * (int64_t)c.Weight);
+      }
   }
 
   // util.SelectBestNode (util/scheduler_helper.go:188-208) with rule (3): first max
@@ -1723,6 +1911,38 @@ void putres(uint32_t R, const Resource& r, double* v, uint32_t* present) {
 extern "C" {
 
 const char* kbo_last_error(void) { return g_err.c_str(); }
+
+void kbo_set_pod_objects(const kbo_pod_objects* po, uint32_t N) {
+  if (!po) { g_pod_world.reset(); return; }
+  auto w = std::make_shared<PodWorld>();
+  w->T = po->T; w->N = N; w->n_topo = po->n_topo;
+  w->pods.resize(po->P);
+  for (uint32_t p = 0; p < po->P; ++p) {
+    PodObj& o = w->pods[p];
+    o.ns = po->pod_ns[p]; o.has_aff = po->has_aff[p] != 0; o.has_anti = po->has_anti[p] != 0;
+    for (uint32_t i = po->lab_off[p]; i < po->lab_off[p + 1]; ++i) o.labels.push_back({po->lab_key[i], po->lab_val[i]});
+    for (uint32_t t = po->term_off[p]; t < po->term_off[p + 1]; ++t) {
+      AffTerm a;
+      a.kind = po->term_kind[t]; a.weight = po->term_weight[t]; a.topo = po->term_topo[t]; a.nil = po->term_nil[t] != 0;
+      for (uint32_t i = po->term_ns_off[t]; i < po->term_ns_off[t + 1]; ++i) a.ns.push_back(po->term_ns[i]);
+      for (uint32_t r = po->term_req_off[t]; r < po->term_req_off[t + 1]; ++r) {
+        LabelReq q; q.key = po->req_key[r]; q.op = po->req_op[r];
+        for (uint32_t i = po->req_val_off[r]; i < po->req_val_off[r + 1]; ++i) q.vals.push_back(po->req_val[i]);
+        a.reqs.push_back(q);
+      }
+      o.terms.push_back(a);
+    }
+  }
+  w->existing_on.resize(N);
+  for (uint32_t p = po->T; p < po->P; ++p) {
+    const uint32_t e = p - po->T;
+    ExistingPod x{p, po->pod_node[e], po->pod_listed[e] != 0, po->pod_in_tasks[e] != 0, po->pod_unbound[e] != 0};
+    if (x.in_tasks && x.node >= 0 && (uint32_t)x.node < N) w->existing_on[(uint32_t)x.node].push_back((uint32_t)w->existing.size());
+    w->existing.push_back(x);
+  }
+  w->node_topo.assign(po->node_topo, po->node_topo + (size_t)std::max(1u, po->n_topo) * std::max(1u, N));
+  g_pod_world = w;
+}
 
 int kbo_cycle(const kb_snapshot* snap, const kbo_running* running, const kb_plugin_conf* conf, const kbo_opts* opts_in,
               const uint8_t* action_list, uint32_t n_actions,

@@ -130,6 +130,41 @@ uint32_t kbo_select_best_node(const double* scores, uint32_t n);
 /* framework.Arguments.GetInt (framework/arguments.go:29-46): `value` NULL = key absent; returns the resulting *ptr */
 int kbo_arguments_get_int(const char* value, int base);
 
+/* ---- inter-pod (anti)affinity on the RAW objects (labels, namespaces, selectors, terms) — the oracle does NOT read
+ * kb_snapshot.pod_affinity (the flattener's aggregated form, which the engine consumes); it walks the pods like the reference:
+ * predicate InterPodAffinityMatches (vendor/.../predicates/predicates.go:1261-1572, slow path) over util.PodLister
+ * (plugins/util/util.go:37-85), priority CalculateInterPodAffinityPriority (vendor/.../priorities/interpod_affinity.go:99-235)
+ * over nodeInfo.Pods() of the feasible nodes.  Strings are interned to ints by the caller (equal strings <=> equal ints).
+ * Pods [0, T) are the snapshot's pending tasks (same index), pods [T, P) the existing pods. ---- */
+typedef struct kbo_pod_objects {
+  uint32_t P, T;
+  const int32_t* pod_ns;          /* [P]                                                          */
+  const uint32_t* lab_off;        /* [P+1] -> lab_key / lab_val                                    */
+  const int32_t* lab_key; const int32_t* lab_val;
+  const uint8_t* has_aff;         /* [P] Spec.Affinity.PodAffinity != nil                          */
+  const uint8_t* has_anti;        /* [P] Spec.Affinity.PodAntiAffinity != nil                      */
+  const uint32_t* term_off;       /* [P+1] -> terms                                                */
+  const int32_t* term_kind;       /* 0 required affinity, 1 required anti-affinity, 2 preferred affinity, 3 preferred anti-affinity */
+  const int32_t* term_weight;     /* preferred terms                                               */
+  const int32_t* term_topo;       /* topology key id, -1 = ""                                      */
+  const uint8_t* term_nil;        /* LabelSelector == nil -> labels.Nothing()                      */
+  const uint32_t* term_ns_off;    /* [terms+1] -> term_ns (empty = the owner's namespace)          */
+  const int32_t* term_ns;
+  const uint32_t* term_req_off;   /* [terms+1] -> requirements                                     */
+  const int32_t* req_key; const int32_t* req_op;   /* 0 In, 1 NotIn, 2 Exists, 3 DoesNotExist     */
+  const uint32_t* req_val_off;    /* [reqs+1] -> req_val                                           */
+  const int32_t* req_val;
+  /* existing pods (index p - T) */
+  const int32_t* pod_node;        /* node index                                                    */
+  const uint8_t* pod_listed;      /* AllocatedStatus task of a session job: util.PodLister lists it */
+  const uint8_t* pod_in_tasks;    /* in NodeInfo.Tasks of its node                                 */
+  const uint8_t* pod_unbound;     /* Spec.NodeName == ""                                           */
+  uint32_t n_topo;
+  const int32_t* node_topo;       /* [n_topo][N] value id of the node's label, -1 absent           */
+} kbo_pod_objects;
+/* Deep-copied; used by the kbo_allocate / kbo_cycle / kbo_predicate_score calls of this thread until cleared with NULL. */
+void kbo_set_pod_objects(const kbo_pod_objects* po, uint32_t N);
+
 const char* kbo_last_error(void);
 
 #ifdef __cplusplus

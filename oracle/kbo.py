@@ -103,6 +103,50 @@ def _p(a, t):
 KBO_ACTION_ALLOCATE = 1
 KBO_ACTION_BACKFILL = 2
 
+_PO_FIELDS = [("pod_ns", C.c_int32), ("lab_off", C.c_uint32), ("lab_key", C.c_int32), ("lab_val", C.c_int32), ("has_aff", C.c_uint8),
+              ("has_anti", C.c_uint8), ("term_off", C.c_uint32), ("term_kind", C.c_int32), ("term_weight", C.c_int32),
+              ("term_topo", C.c_int32), ("term_nil", C.c_uint8), ("term_ns_off", C.c_uint32), ("term_ns", C.c_int32),
+              ("term_req_off", C.c_uint32), ("req_key", C.c_int32), ("req_op", C.c_int32), ("req_val_off", C.c_uint32),
+              ("req_val", C.c_int32), ("pod_node", C.c_int32), ("pod_listed", C.c_uint8), ("pod_in_tasks", C.c_uint8),
+              ("pod_unbound", C.c_uint8)]
+
+
+class kbo_pod_objects(C.Structure):
+    _fields_ = [("P", C.c_uint32), ("T", C.c_uint32)] + [(n, C.POINTER(t)) for n, t in _PO_FIELDS] + \
+               [("n_topo", C.c_uint32), ("node_topo", C.POINTER(C.c_int32))]
+
+
+class _PodObjects:
+    """Hands the raw pod objects of a snapshot (builder.py: snap.meta["pod_objects"]) to the oracle for the duration of a call."""
+
+    def __init__(self, snap: Snapshot):
+        self.ob = (snap.meta or {}).get("pod_objects")
+        self.N = snap.N
+
+    def __enter__(self):
+        if self.ob is None:
+            return self
+        ob = self.ob
+        po = kbo_pod_objects()
+        po.P, po.T, po.n_topo = int(ob["P"]), int(ob["T"]), int(ob["n_topo"])
+        keep = []
+        for n, t in _PO_FIELDS:
+            a = np.ascontiguousarray(ob[n], dtype=np.dtype(t))
+            if a.size == 0:
+                a = np.zeros(1, dtype=np.dtype(t))
+            keep.append(a)
+            setattr(po, n, _p(a, t))
+        nt = np.ascontiguousarray(ob["node_topo"], dtype=np.int32)
+        keep.append(nt)
+        po.node_topo = _p(nt, C.c_int32)
+        lib().kbo_set_pod_objects(C.byref(po), C.c_uint32(self.N))
+        return self
+
+    def __exit__(self, *a):
+        if self.ob is not None:
+            lib().kbo_set_pod_objects(None, C.c_uint32(0))
+        return False
+
 
 def allocate(snap: Snapshot, conf: PluginConf, mode: int = KBO_MODE_OPTIMISED, threads: int = 1,
              max_tasks: int = 0, max_seconds: float = 0.0, actions: int = KBO_ACTION_ALLOCATE, warm_tasks: int = 0) -> OracleOut:
@@ -121,12 +165,13 @@ def allocate(snap: Snapshot, conf: PluginConf, mode: int = KBO_MODE_OPTIMISED, t
         node_nz_mem=np.zeros(N, dtype=np.int64), node_ports=np.zeros((W, N), dtype=np.uint64),
         job_share=np.zeros(J), job_ready=np.zeros(J, dtype=np.int32), queue_share=np.zeros(Q),
         queue_deserved=np.zeros((R, Q)), queue_allocated=np.zeros((R, Q)))
-    rc = L.kbo_allocate(C.byref(cs), C.byref(cc), C.byref(o), dec.ctypes.data_as(C.c_void_p), C.byref(res),
-                        _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
-                        _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
-                        _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
-                        _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double),
-                        _p(out.queue_allocated, C.c_double))
+    with _PodObjects(snap):
+        rc = L.kbo_allocate(C.byref(cs), C.byref(cc), C.byref(o), dec.ctypes.data_as(C.c_void_p), C.byref(res),
+                            _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
+                            _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
+                            _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
+                            _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double),
+                            _p(out.queue_allocated, C.c_double))
     if rc != 0:
         raise RuntimeError(f"kbo_allocate rc={rc}: {L.kbo_last_error().decode()}")
     out.decisions = dec[:T]
@@ -175,13 +220,14 @@ def cycle(snap: Snapshot, conf: PluginConf, actions=("allocate",), running: Opti
     evicted = np.zeros(max(nrun, 1), dtype=np.uint8)
     order = np.zeros(max(nrun, 1), dtype=np.uint32)
     acts = np.array([ACTIONS[a] for a in actions], dtype=np.uint8)
-    rc = L.kbo_cycle(C.byref(cs), C.byref(run) if run is not None else None, C.byref(cc), C.byref(o),
-                     _p(acts, C.c_uint8), C.c_uint32(len(acts)), dec.ctypes.data_as(C.c_void_p), _p(evicted, C.c_uint8), _p(order, C.c_uint32),
-                     C.byref(res),
-                     _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
-                     _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
-                     _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
-                     _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double), _p(out.queue_allocated, C.c_double))
+    with _PodObjects(snap):
+        rc = L.kbo_cycle(C.byref(cs), C.byref(run) if run is not None else None, C.byref(cc), C.byref(o),
+                         _p(acts, C.c_uint8), C.c_uint32(len(acts)), dec.ctypes.data_as(C.c_void_p), _p(evicted, C.c_uint8), _p(order, C.c_uint32),
+                         C.byref(res),
+                         _p(out.node_idle, C.c_double), _p(out.node_releasing, C.c_double), _p(out.node_used, C.c_double),
+                         _p(out.node_pods, C.c_int32), _p(out.node_nz_cpu, C.c_int64), _p(out.node_nz_mem, C.c_int64),
+                         _p(out.node_ports, C.c_uint64), _p(out.job_share, C.c_double), _p(out.job_ready, C.c_int32),
+                         _p(out.queue_share, C.c_double), _p(out.queue_deserved, C.c_double), _p(out.queue_allocated, C.c_double))
     if rc != 0:
         raise RuntimeError(f"kbo_cycle rc={rc}: {L.kbo_last_error().decode()}")
     out.decisions = dec[:T]
@@ -195,7 +241,8 @@ def predicate_score(snap: Snapshot, conf: PluginConf, task: int):
     cc, keep2 = conf.to_c()
     fit = np.zeros(snap.N, dtype=np.uint8)
     score = np.zeros(snap.N, dtype=np.float64)
-    rc = L.kbo_predicate_score(C.byref(cs), C.byref(cc), C.c_uint32(task), _p(fit, C.c_uint8), _p(score, C.c_double))
+    with _PodObjects(snap):
+        rc = L.kbo_predicate_score(C.byref(cs), C.byref(cc), C.c_uint32(task), _p(fit, C.c_uint8), _p(score, C.c_double))
     if rc != 0:
         raise RuntimeError(f"kbo_predicate_score rc={rc}: {L.kbo_last_error().decode()}")
     return fit, score

@@ -93,6 +93,29 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
     }
   uint32_t nmax_dummy = 0;
   PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &nmax_dummy};
+  // inter-pod affinity (kb_aff.h): step 10 joins the plugin predicates; a class with a weight list gets the priority's passes
+  // first (aff_prepass_kernel): pass 1 = weight per topology domain over the FEASIBLE nodes, pass 2 = min / max count
+  const AffDev& A = S.aff;
+  const ClassAff* ca = A.on ? &A.cls[c.cur_class] : nullptr;
+  const bool ipa = ca && ca->w_cnt && S.cf.nodeorder;
+  auto feasible_key = [&](uint32_t n, bool* pok) {
+    TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+    uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr, pok);
+    if (ca && S.cf.predicates && !aff_pred(A, *ca, S.N, n)) { k = 0; if (pok) *pok = false; }
+    return k;
+  };
+  if (ipa) {
+    for (uint32_t i = 0; i < A.dom_total; ++i) A.dom_sum[i] = 0;
+    A.minmax[0] = 0; A.minmax[1] = 0;
+    for (uint32_t n = 0; n < S.N; ++n)
+      if (feasible_key(n, nullptr)) aff_pass1_node(A, *ca, S.N, n, [&](uint32_t slot, long long v) { A.dom_sum[slot] += v; });
+    for (uint32_t n = 0; n < S.N; ++n)
+      if (feasible_key(n, nullptr)) {
+        const long long cnt = aff_count_node(A, *ca, S.N, n);
+        if (cnt < A.minmax[0]) A.minmax[0] = cnt;
+        if (cnt > A.minmax[1]) A.minmax[1] = cnt;
+      }
+  }
   std::vector<uint64_t> keys;
   for (uint32_t t = S.tile_lo; t < S.tile_hi; ++t)
     for (uint32_t i = 0; i < TILE_NODES; ++i) {
@@ -100,9 +123,10 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
       if (n >= S.N) break;
       TileAcc acc{S.tiles + (size_t)t * tile_u64, i, R, W};
       bool pok = false;
-      uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr, &pok);
+      uint64_t k = feasible_key(n, &pok);
       if (S.backfill && pok && !k) sendbuf[(size_t)(1 + S.ncols) * 32] = 1;      // flag row: passes ssn.PredicateFn, no Idle for Resreq
       if (k && cp) k = add_pref_term(k, &pc, pref_count(*cp, acc, W));
+      if (k && ipa) k = aff_add_score(k, A.w_podaff, aff_score(aff_count_node(A, *ca, S.N, n), A.minmax[0], A.minmax[1]));
       if (k) keys.push_back(k);
     }
   std::sort(keys.begin(), keys.end(), [](uint64_t a, uint64_t b) { return a > b; });
@@ -122,6 +146,9 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
                  const PrefCtx* pc = nullptr, const bool pred_any_outside = false) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
+  const ClassAff* ca = S.aff.on ? &S.aff.cls[cls_id] : nullptr;
+  const bool ca_reads = ca && aff_reads(*ca, S.cf.nodeorder != 0);
+  bool aff_stale = false;       // a placement of a class whose keys read the inter-pod counters: the list is used once
   auto refresh = [&]() {
     for (auto& cd : cand) {
       if (!(cd.have && cd.cur_key != 0 && !cd.next_valid)) continue;
@@ -144,7 +171,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
   refresh();
   bool pref_stale = false;      // the last feasible max-count node filled up: every key of this launch used a stale normalisation
   for (;;) {
-    if (c.done || c.cur_class != cls_id || pref_stale) break;
+    if (c.done || c.cur_class != cls_id || pref_stale || aff_stale) break;
     const uint32_t j = (uint32_t)c.cur_job;
     const uint32_t jend = S.job_ord_off[j + 1];
     uint32_t run_left = c.cur_run, placed = 0, reason = STOP_RUN_DONE;
@@ -165,6 +192,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
             SlotAcc acc{&cd.st[cd.which], R, W};
             bool pok = false;
             eval_pair(S.cf, cls, acc, cd.node, nullptr, &pok);
+            if (ca && S.cf.predicates && !aff_pred(S.aff, *ca, S.N, cd.node)) pok = false;
             any = any || pok;
           }
           if (any) {
@@ -190,13 +218,14 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       if (fits_idle) { c.tasks_allocated += 1; S.job_ready[j] += 1; } else c.tasks_pipelined += 1;
       S.job_placed[j] += 1;
       on_allocate_event(S, j, cls);
+      if (ca) { aff_commit(S.aff, *ca, S.N, cd.node, fits_idle); aff_stale = ca_reads; }
       placed += 1;
       if (pc && pc->max > 0 && cd.cur_key == 0 && cd.pref == pc->max) {            // a max-count node left the feasible set
         *pc->nmax -= 1;
         if (*pc->nmax == 0) pref_stale = true;
       }
       if (ssn_job_ready(S, j) && (pos + 1 < jend) && !S.backfill) { reason = STOP_YIELD; break; }
-      if (pref_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
+      if (pref_stale || aff_stale) { if (run_left > 0) reason = STOP_RESCAN; break; }
     }
     if (reason == STOP_RESCAN) c.rescans += 1;
     after_run(S, c, reason, placed);
@@ -589,7 +618,7 @@ void* kbemu_create2(const kb_snapshot* snap, const kb_plugin_conf* conf, uint32_
   BuildErr be;
   // mode 1 (plain launches) also accepts preferred node-affinity terms: the emulation prototypes the two-pass scan (a12)
   if (build_session(snap, conf, 148, E->B, &be, rank, world, mode == 0 ? 1 : 0, (mode == 2 || mode == 4) ? mode : 1, mode == 1, mode == 5 ? 1 : 0)) { g_err = be.msg; delete E; return nullptr; }
-  E->pipe = mode == 5;
+  E->pipe = mode == 5 && E->B.pipe;
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
   E->cur = &E->S;
@@ -602,7 +631,7 @@ int kbemu_reload(void* h, const kb_snapshot* snap, const kb_plugin_conf* conf, u
   Emu* E = (Emu*)h;
   BuildErr be;
   if (int rc = build_session(snap, conf, 148, E->B, &be, 0, 1, mode == 0 ? 1 : 0, (mode == 2 || mode == 4) ? mode : 1, false, mode == 5 ? 1 : 0)) { g_err = be.msg; return rc; }
-  E->pipe = mode == 5; E->log_node.clear(); E->log_rec.clear(); E->view.clear(); E->view_pos = 0; E->need_fresh = false;
+  E->pipe = mode == 5 && E->B.pipe; E->log_node.clear(); E->log_rec.clear(); E->view.clear(); E->view_pos = 0; E->need_fresh = false;
   E->B.bind(E->S, E->B.mut.host.data(), E->B.imm.host.data());
   E->B.bind_backfill(E->Sbf, E->B.mut.host.data(), E->B.imm.host.data());
   E->cur = &E->S;
