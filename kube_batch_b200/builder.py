@@ -539,7 +539,7 @@ def _aff_sig(p: Pod):
 
 
 def flatten_pod_affinity(nodes, pending, existing, s, on_node, status_of, in_session_job):
-    """-> (dict mirroring kb_pod_affinity, dict of the raw objects for the oracle).  `pending`: the snapshot's tasks in task
+    """-> (dict mirroring kb_pod_affinity, dict of the raw objects for object-level checkers).  `pending`: the snapshot's tasks in task
     order; `existing`: pods with a node of the session that are not Pending; on_node: ids of pods node.AddTask accepted."""
     N, T = len(nodes), len(pending)
     nidx = {n.name: i for i, n in enumerate(nodes)}
@@ -752,56 +752,8 @@ def flatten_pod_affinity(nodes, pending, existing, s, on_node, status_of, in_ses
         "weight_value": np.array(wv or [0], dtype=np.int64),
     }
 
-    # ---- the raw objects, for the oracle (oracle/kb_oracle.h kbo_pod_objects): pods = pending tasks, then the existing pods ----
-    strs: Dict[str, int] = {}
-    def sid(x: str) -> int:
-        return strs.setdefault(x, len(strs))
-    allpods = list(pending) + list(existing)
-    topo_keys: Dict[str, int] = {}
-    ob = {"P": len(allpods), "T": T, "pod_ns": [], "lab_off": [0], "lab_key": [], "lab_val": [], "has_aff": [], "has_anti": [],
-          "term_off": [0], "term_kind": [], "term_weight": [], "term_topo": [], "term_nil": [], "term_ns_off": [0], "term_ns": [],
-          "term_req_off": [0], "req_key": [], "req_op": [], "req_val_off": [0], "req_val": [],
-          "pod_node": [], "pod_listed": [], "pod_in_tasks": [], "pod_unbound": []}
-    opn = {"In": 0, "NotIn": 1, "Exists": 2, "DoesNotExist": 3}
+    # ---- the raw objects (what a checker that walks the pods one by one needs): pending pods in task order, then the others ----
     lset, tset = set(id(p) for p in listed), set(id(p) for p in in_tasks)
-    for p in allpods:
-        ob["pod_ns"].append(sid(p.namespace))
-        for k, v in sorted(p.labels.items()):
-            ob["lab_key"].append(sid(k)); ob["lab_val"].append(sid(v))
-        ob["lab_off"].append(len(ob["lab_key"]))
-        ob["has_aff"].append(1 if p.pod_affinity is not None else 0)
-        ob["has_anti"].append(1 if p.pod_anti_affinity is not None else 0)
-        for kind, a in ((0, p.pod_affinity), (1, p.pod_anti_affinity)):
-            if a is None:
-                continue
-            for (wt, term) in [(0, t) for t in a.required] + [(w, t) for (w, t) in a.preferred]:
-                pref = not any(term is t for t in a.required)
-                ob["term_kind"].append(kind + (2 if pref else 0))
-                ob["term_weight"].append(wt)
-                ob["term_topo"].append(topo_keys.setdefault(term.topology_key, len(topo_keys)) if term.topology_key else -1)
-                ob["term_nil"].append(1 if term.nil_selector else 0)
-                for ns in term.namespaces:
-                    ob["term_ns"].append(sid(ns))
-                ob["term_ns_off"].append(len(ob["term_ns"]))
-                for k, v in sorted(term.match_labels.items()):
-                    ob["req_key"].append(sid(k)); ob["req_op"].append(0); ob["req_val"].append(sid(v)); ob["req_val_off"].append(len(ob["req_val"]))
-                for (k, op, vals) in term.match_expressions:
-                    ob["req_key"].append(sid(k)); ob["req_op"].append(opn[op])
-                    for v in vals:
-                        ob["req_val"].append(sid(v))
-                    ob["req_val_off"].append(len(ob["req_val"]))
-                ob["term_req_off"].append(len(ob["req_key"]))
-        ob["term_off"].append(len(ob["term_kind"]))
-    for p in existing:
-        ob["pod_node"].append(nidx[p.node_name])
-        ob["pod_listed"].append(1 if id(p) in lset else 0)
-        ob["pod_in_tasks"].append(1 if id(p) in tset else 0)
-        ob["pod_unbound"].append(0)
-    ob["n_topo"] = len(topo_keys)
-    nt = np.full((max(1, len(topo_keys)), max(1, N)), -1, dtype=np.int32)
-    for key, ki in topo_keys.items():
-        for i, n in enumerate(nodes):
-            if key in n.labels:
-                nt[ki, i] = sid("\0v:" + n.labels[key])
-    ob["node_topo"] = nt
+    ob = {"nodes": nodes, "pending": list(pending), "existing": list(existing), "node_index": nidx,
+          "listed": [id(p) in lset for p in existing], "in_tasks": [id(p) in tset for p in existing]}
     return pa, ob

@@ -21,6 +21,15 @@
 
 #include "kb_core.h"
 
+// The counters are written by one launch and read by the next; visit_kernel may be scheduled (programmatic dependent launch)
+// while its predecessor still runs, so an SM's L1 can hold a line the predecessor's scan read before its replay changed it:
+// every read of MUTABLE affinity data goes to L2 (ld.global.cg), like the control block and the candidate lists.
+#if defined(__CUDA_ARCH__)
+#define KB_LDM(p) __ldcg(p)
+#else
+#define KB_LDM(p) (*(p))
+#endif
+
 namespace kb {
 
 struct ClassAff {
@@ -73,13 +82,13 @@ KB_HD bool aff_pred(const AffDev& A, const ClassAff& ca, const uint32_t N, const
 #endif
     f &= f - 1;
     const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
-    if (d >= 0 && A.cnt[A.group_off[g] + (uint32_t)d] > 0) ok = false;
+    if (d >= 0 && KB_LDM(&A.cnt[A.group_off[g] + (uint32_t)d]) > 0) ok = false;
   }
   if (ca.need >= 0) {                            // the pod's required affinity terms (:1516-1560)
     const uint32_t g = (uint32_t)ca.need;
     const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
-    const bool match = d >= 0 && A.cnt[A.group_off[g] + (uint32_t)d] > 0;
-    const bool first_of_series = A.total[g] == 0 && ca.self_match;
+    const bool match = d >= 0 && KB_LDM(&A.cnt[A.group_off[g] + (uint32_t)d]) > 0;
+    const bool first_of_series = KB_LDM(&A.total[g]) == 0 && ca.self_match;
     ok = ok && (match || first_of_series);
   }
   return ok;
@@ -89,10 +98,10 @@ KB_HD bool aff_pred(const AffDev& A, const ClassAff& ca, const uint32_t N, const
 // `add(slot, value)` accumulates into dom_sum (atomicAdd on the device).
 template <class Add>
 KB_HD void aff_pass1_node(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t m, Add add) {
-  const int32_t fu = *A.first_unbound;
+  const int32_t fu = KB_LDM(A.first_unbound);
   for (uint32_t i = ca.w_off; i < ca.w_off + ca.w_cnt; ++i) {
     const uint32_t e = (uint32_t)A.w_kind[i], ks = (uint32_t)A.w_keyset[i];
-    const int32_t c = A.kind_count[(size_t)e * N + m];
+    const int32_t c = KB_LDM(&A.kind_count[(size_t)e * N + m]);
     if (!c) continue;
     const uint32_t fixed = A.kind_unbound[e] ? (uint32_t)fu : m;     // cachedNodeInfo.GetNodeInfo (nodeorder.go:49-63)
     const int32_t d = A.node_domain[(size_t)ks * N + fixed];
@@ -111,7 +120,7 @@ KB_HD long long aff_count_node(const AffDev& A, const ClassAff& ca, const uint32
 #endif
     k &= k - 1;
     const int32_t d = A.node_domain[(size_t)ks * N + n];
-    if (d >= 0) count += A.dom_sum[A.keyset_off[ks] + (uint32_t)d];
+    if (d >= 0) count += KB_LDM(&A.dom_sum[A.keyset_off[ks] + (uint32_t)d]);
   }
   return count;
 }
@@ -138,13 +147,13 @@ KB_HD void aff_commit(const AffDev& A, const ClassAff& ca, const uint32_t N, con
       const uint32_t g = (uint32_t)__builtin_ctzll(c);
 #endif
       c &= c - 1;
-      A.total[g] += 1;
+      A.total[g] = KB_LDM(&A.total[g]) + 1;
       const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
-      if (d >= 0) A.cnt[A.group_off[g] + (uint32_t)d] += 1;
+      if (d >= 0) A.cnt[A.group_off[g] + (uint32_t)d] = KB_LDM(&A.cnt[A.group_off[g] + (uint32_t)d]) + 1;
     }
   }
-  if (ca.kind >= 0) A.kind_count[(size_t)ca.kind * N + n] += 1;
-  const int32_t fu = *A.first_unbound;
+  if (ca.kind >= 0) A.kind_count[(size_t)ca.kind * N + n] = KB_LDM(&A.kind_count[(size_t)ca.kind * N + n]) + 1;
+  const int32_t fu = KB_LDM(A.first_unbound);
   if (fu < 0 || (int32_t)n < fu) *A.first_unbound = (int32_t)n;
 }
 

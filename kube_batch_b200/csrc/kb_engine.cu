@@ -354,10 +354,13 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   // world > 1: by default every rank runs the whole cycle on the full (replicated) node table — the cycle is bound by the
   // serial replay, not by the scan, so sharding the scan only adds an exchange per visit; KB_ENGINE_SHARD
   // selects the node-sharded per-launch path instead.
-  const bool pipe_try = e->pipe_req && e->coop_ok && (e->world == 1 || !e->shard_req);
+  // inter-pod affinity (kb_pod_affinity): per-visit kernels on the full table; with world > 1 every rank runs the whole cycle
+  // (replicated) unless KB_ENGINE_SHARD asks for the sharded path, which such sessions refuse
+  const bool aff_session = s && s->pod_affinity != nullptr;
+  const bool pipe_try = (e->pipe_req && e->coop_ok && (e->world == 1 || !e->shard_req)) || (aff_session && !e->shard_req);
   int rc_build = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, pipe_try ? 0u : (uint32_t)e->rank,
                                pipe_try ? 1u : (uint32_t)e->world, e->overlap_mode, kchain, false, pipe_try ? 1 : 0);
-  if (rc_build == KB_OK && pipe_try && !B.pipe && e->world > 1)       // geometry outside the pipeline: fall back to the sharded path
+  if (rc_build == KB_OK && pipe_try && !B.pipe && e->world > 1 && !aff_session)       // geometry outside the pipeline: fall back to the sharded path
     rc_build = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode, kchain);
   if (rc_build) return fail(e, rc_build, "%s", be.msg.c_str());
   e->replicated = e->world > 1 && B.world == 1;
@@ -417,6 +420,8 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   e->visit_smem = ((sizeof(VisitSmem) + 127) / 128) * 128 + 2 * (size_t)B.tpi * e->tile_smem;
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
+  CUDA_TRY(e, cudaFuncSetAttribute(visit_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   CUDA_TRY(e, cudaFuncSetAttribute(visit_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->visit_smem));
   e->chain_smem = 0;
   if (B.kchain == 2) { e->chain_smem = chain_smem_header<2>() + 2 * (size_t)B.tpi * e->tile_smem; CUDA_TRY(e, cudaFuncSetAttribute(visit_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)e->chain_smem)); }
@@ -446,8 +451,19 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
     cudaError_t ce = cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal);
     bool ok = ce == cudaSuccess;
     for (uint32_t i = 0; ok && i < BATCH; ++i) {
-      const bool pdl = e->pdl && e->world == 1;
-      if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
+      const bool pdl = e->pdl && (e->world == 1 || e->replicated);
+      if (e->dev.aff.on) {
+        // inter-pod affinity: the priority's passes over the feasible nodes (they return at once for a class without a weight
+        // list), then the visit with predicate step 10 / the score term in its scan
+        if (e->dev.aff.has_weights) {
+          const uint32_t ag = std::max(1u, std::min((e->N + AFF_THREADS - 1) / AFF_THREADS, (uint32_t)e->sm_count * 4u));
+          aff_prepass_kernel<0><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
+          aff_prepass_kernel<1><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
+          aff_prepass_kernel<2><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
+        }
+        ok = launch_visit(visit_kernel<0, 1>, e->scan_grid, e->visit_smem, e->stream, e->dev, pdl) == cudaSuccess;
+      }
+      else if (e->dev.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(e->dev);
       else if (e->dev.kchain == 2) ok = launch_visit(visit_chain_kernel<2>, e->scan_grid, e->chain_smem, e->stream, e->dev, pdl) == cudaSuccess;
       else if (e->dev.kchain == 4) ok = launch_visit(visit_chain_kernel<4>, e->scan_grid, e->chain_smem, e->stream, e->dev, pdl) == cudaSuccess;
       else ok = launch_visit(visit_kernel<0>, e->scan_grid, e->visit_smem, e->stream, e->dev, pdl) == cudaSuccess;
@@ -513,7 +529,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
   }
   uint32_t launches = 0;
   // every visit pops one queue entry or consumes >= 1 task; rescans are bounded by tasks as well
-  const uint64_t cap = 4ull * ((uint64_t)e->J + e->To + e->Tb) + 1024;
+  const uint64_t cap = (D.aff.on ? 4ull : 1ull) * (4ull * ((uint64_t)e->J + e->To + e->Tb) + 1024);
   const bool use_pipe = !backfill && D.pipe;
   const bool use_graph = !backfill && !use_pipe && e->graph_exec;
   const uint32_t batch = backfill ? 16u : BATCH;
@@ -531,12 +547,25 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       launches += 1;
     } else if (use_graph) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
-      launches += ((e->world == 1 || D.p2p) ? 1 : 2) * BATCH;
+      launches += ((D.aff.on && D.aff.has_weights) ? 4 : (e->world == 1 || D.p2p || e->replicated) ? 1 : 2) * BATCH;
     } else {
       // sharded node axis without peer memory: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
       const size_t cnt = (size_t)xchg_u64(e->ncols);
       for (uint32_t i = 0; i < batch; ++i) {
-        if (backfill) visit_kernel<1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
+        if (D.aff.on) {
+          if (backfill) visit_kernel<1, 1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);      // nodeorder is off in backfill: no passes
+          else {
+            if (D.aff.has_weights) {
+              const uint32_t ag = std::max(1u, std::min((e->N + AFF_THREADS - 1) / AFF_THREADS, (uint32_t)e->sm_count * 4u));
+              aff_prepass_kernel<0><<<ag, AFF_THREADS, 0, e->stream>>>(D);
+              aff_prepass_kernel<1><<<ag, AFF_THREADS, 0, e->stream>>>(D);
+              aff_prepass_kernel<2><<<ag, AFF_THREADS, 0, e->stream>>>(D);
+              launches += 3;
+            }
+            visit_kernel<0, 1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
+          }
+        }
+        else if (backfill) visit_kernel<1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
         else if (D.overlap) visit_overlap_kernel<<<e->scan_grid + 1, SCAN_THREADS, e->visit_smem, e->stream>>>(D);
         else if (D.kchain == 2) visit_chain_kernel<2><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(D);
         else if (D.kchain == 4) visit_chain_kernel<4><<<e->scan_grid, SCAN_THREADS, e->chain_smem, e->stream>>>(D);
@@ -651,6 +680,7 @@ int kb_session_load_running(kb_engine* e, const kb_snapshot* s, const kb_running
     return fail(e, KB_E_BADARG, "kb_session_load_running: `snap` is not the snapshot of the loaded session");
   if (e->world > 1 && !e->replicated) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt run on the full node table: not with KB_ENGINE_SHARD");
   if (e->built.has_pref) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt with preferred node affinity are outside this build");
+  if (e->built.aff.on) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt in a session with inter-pod affinity are outside this build (the victim walk does not update the affinity counters)");
   CUDA_TRY(e, cudaSetDevice(e->device));
   e->running_loaded = false;
   BuildErr be;
@@ -843,6 +873,7 @@ int kb_bind_list(kb_engine* e, uint32_t* task, int32_t* node, uint32_t* n) {
 int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {
   if (!e) return KB_E_BADARG;
   if (!e->loaded) return fail(e, KB_E_STATE, "kb_predicate_score before kb_session_load");
+  if (e->built.aff.on) return fail(e, KB_E_UNSUPPORTED_FEATURE, "kb_predicate_score: the matrix kernels do not evaluate inter-pod affinity");
   if (task_lo > task_hi || task_hi > e->T) return fail(e, KB_E_BADARG, "task range [%u,%u) outside [0,%u)", task_lo, task_hi, e->T);
   const size_t n = (size_t)(task_hi - task_lo) * e->N;
   if (n == 0 || e->NT == 0) return KB_OK;
@@ -868,6 +899,7 @@ int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t
 int kb_best_nodes(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint64_t* best_key) {
   if (!e) return KB_E_BADARG;
   if (!e->loaded) return fail(e, KB_E_STATE, "kb_best_nodes before kb_session_load");
+  if (e->built.aff.on) return fail(e, KB_E_UNSUPPORTED_FEATURE, "kb_best_nodes: the matrix kernels do not evaluate inter-pod affinity");
   if (task_lo > task_hi || task_hi > e->T || !best_key) return fail(e, KB_E_BADARG, "bad task range or NULL output");
   const uint32_t n = task_hi - task_lo;
   if (n == 0) return KB_OK;

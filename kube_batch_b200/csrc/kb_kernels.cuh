@@ -136,6 +136,7 @@ __device__ __forceinline__ uint64_t cta_fold_lists(uint64_t mine, uint64_t (*wli
 
 struct VisitSmem {
   ClassRec cls;
+  ClassAff cls_aff;                          // inter-pod affinity record of the class (AFF instantiations only)
   Ctl ctl;
   uint64_t keys[KTOP];                       // merged candidate list of the scan (K3 result)
   uint64_t wlist[SCAN_WARPS][KTOP];          // per-warp lists exchanged through shared memory
@@ -177,7 +178,7 @@ __device__ __forceinline__ void store_ctl(Ctl* g, const Ctl& c, int lane) {
 // evaluates ITS candidate's current state for it and the sorted keys go to c.patch (see Ctl).  The caller stores c.
 // CH = 1 (visit_chain_kernel): the floor comes from sm.chain_floor (a patched list's floor is not its 32nd key), the nodes
 // this replay modified are appended to sm.mod and a rescan stop is reported in sm.last_rescan.
-template <int BF, int CH = 0>
+template <int BF, int CH = 0, int AFF = 0>
 __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& sm, const int lane, const uint32_t cls_id,
                                                 const uint64_t* rec_base, const uint32_t rec_stride, const uint32_t patch_class,
                                                 const long long t_start, const long long t_scan) {
@@ -238,8 +239,12 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   const long long t_merge = clock64();
 
   uint32_t my_cnt = 0;        // placements on MY candidate (NodeInfo.Used delta = my_cnt x Resreq, applied at write-back)
+  // inter-pod affinity (kb_aff.h): a class whose keys read the counters uses its list for ONE placement — the placement can
+  // change the feasibility / score of every node of a topology domain
+  const bool aff_rd = AFF && aff_reads(sm.cls_aff, S.cf.nodeorder != 0);
+  bool aff_stop = false;
   for (;;) {              // runs
-    if (c.done || c.cur_class != cls_id) break;
+    if (c.done || c.cur_class != cls_id || (AFF && aff_stop)) break;
     const uint32_t j = (uint32_t)c.cur_job;
     const uint32_t q = c.cur_queue;
     const uint32_t jend = S.job_ord_off[j + 1];
@@ -280,6 +285,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
           if (have) {
             ColAcc acc{&sm.slot[which][0][0], (uint32_t)lane, 32u, R, W};
             eval_pair(S.cf, sm.cls, acc, my_node, nullptr, &pk);
+            if (AFF && pk && S.cf.predicates) pk = aff_pred(S.aff, sm.cls_aff, S.N, my_node);
           }
           if (sm.pred_any_all || __any_sync(FULL, pk)) {
             if (lane == 0) {
@@ -315,12 +321,15 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
         d.step = step0 + placed;
         d.dispatch_step = 0xFFFFFFFFu;
         S.dec[task] = d;
+        if (AFF) aff_commit(S.aff, sm.cls_aff, S.N, key_node(best), fits_idle);
       }
+      if (AFF) aff_stop = aff_rd;
       placed += 1;
       n_alloc += fits_idle ? 1u : 0u;
       // allocate.go:185-188: a ready job yields after every task while tasks remain
       const bool jr = !S.gang_ready || (ready + (int32_t)n_alloc) >= min_avail;     // ssn.JobReady
       if (!BF && jr && (pos + 1 < jend)) { reason = STOP_YIELD; break; }
+      if (AFF && aff_stop) { if (run_left > 0) reason = STOP_RESCAN; break; }
     }
     // write the job-level state back, then run the control plane
     if (lane == 0) {
@@ -446,7 +455,7 @@ __device__ __forceinline__ bool issue_first_group(const DevSession& S, VisitSmem
   return true;
 }
 
-template <bool PH = false>
+template <bool PH = false, int AFF = 0>
 __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx,
                                                const uint32_t n_scanners, const uint32_t cls_id, const int tid, const int lane, const int warp,
                                                const bool first_issued = false) {
@@ -470,8 +479,16 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
     uint32_t* dst = reinterpret_cast<uint32_t*>(&sm.cls);
     for (uint32_t i = tid; i < sizeof(ClassRec) / 4; i += SCAN_THREADS) dst[i] = src[i];
+    if (AFF) {
+      const uint32_t* as = reinterpret_cast<const uint32_t*>(&S.aff.cls[cls_id]);
+      uint32_t* ad = reinterpret_cast<uint32_t*>(&sm.cls_aff);
+      for (uint32_t i = tid; i < sizeof(ClassAff) / 4; i += SCAN_THREADS) ad[i] = as[i];
+    }
   }
   __syncthreads();
+  // InterPodAffinityPriority: the passes of aff_prepass_kernel left the per-domain weights and the min / max count
+  const bool ipa = AFF && sm.cls_aff.w_cnt != 0 && S.cf.nodeorder != 0;
+  const long long ipa_min = ipa ? __ldcg(&S.aff.minmax[0]) : 0ll, ipa_max = ipa ? __ldcg(&S.aff.minmax[1]) : 0ll;
   const uint32_t sub = (uint32_t)warp >> 2, part = (uint32_t)warp & 3u;    // which tile of the group / which 32 nodes of it
   uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
   bool pany = false;                         // PH (backfill): a node that passes the plugin predicates but has no Idle for Resreq
@@ -495,6 +512,10 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
       ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
       bool pok = false;
       key = eval_pair(S.cf, sm.cls, acc, node, nullptr, PH ? &pok : nullptr);
+      if (AFF) {
+        if (S.cf.predicates && !aff_pred(S.aff, sm.cls_aff, S.N, node)) { key = 0; pok = false; }      // predicate step 10
+        if (ipa && key) key = aff_add_score(key, S.aff.w_podaff, aff_score(aff_count_node(S.aff, sm.cls_aff, S.N, node), ipa_min, ipa_max));
+      }
       if (PH) pany = pany | (pok && key == 0);
     }
     // K3, warp level: skip the networks when nothing in this warp can enter its list
@@ -568,7 +589,7 @@ __device__ __forceinline__ void shadow_prefetch(const DevSession& S, const Ctl& 
 // ---------------------------------------------------------------------------------------------
 // visit_kernel
 // ---------------------------------------------------------------------------------------------
-template <int BF>
+template <int BF, int AFF = 0>
 __global__ void __launch_bounds__(SCAN_THREADS)
 visit_kernel(const __grid_constant__ DevSession S) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -594,7 +615,7 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   const long long t_start = clock64();
 
-  uint64_t mylist = scan_phase<BF != 0>(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true);
+  uint64_t mylist = scan_phase<BF != 0, AFF>(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true);
   if (warp == 0) {
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
     if (BF && lane == 0) S.cand[((size_t)gridDim.x + blockIdx.x) * KTOP] = (uint64_t)sm.pred_any;      // second bank of the list area
@@ -745,9 +766,64 @@ visit_kernel(const __grid_constant__ DevSession S) {
   {
     const uint32_t n = key_node(sm.keys[lane]);
     const uint64_t* rec = S.tiles + (size_t)(n / TILE_NODES) * ((size_t)S.ncols * TILE_NODES) + (n % TILE_NODES);
-    replay_epilogue<BF>(S, sm, lane, cls_id, rec, TILE_NODES, 0xFFFFFFFFu, t_start, t_scan);
+    replay_epilogue<BF, 0, AFF>(S, sm, lane, cls_id, rec, TILE_NODES, 0xFFFFFFFFu, t_start, t_scan);
     store_ctl(gctl, sm.ctl, lane);
     if (lane == 0) gctl->arrive = 0;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// aff_prepass_kernel<PHASE>: InterPodAffinityPriority (vendor/.../priorities/interpod_affinity.go:99-235) needs two
+// reductions over the FEASIBLE nodes before a single key of the visit's class exists; three small launches precede the
+// visit_kernel of a session whose classes carry weight lists (they return at once for a class without one):
+//   0  clear the per-domain weights and the min / max count
+//   1  every feasible node adds the weight of its pods to the topology domain of the "pod's node" (kb_aff.h aff_pass1_node)
+//   2  every feasible node's count = sum of its domains' weights -> min / max (both start at 0, :205-214)
+// visit_kernel's scan then adds w * int(10 * (count - min) / (max - min)) to the key (pass 3).  Node records are read from the
+// global tiles (L2 resident); feasible = K1 + predicate step 10, exactly the scan's test.
+// ---------------------------------------------------------------------------------------------
+constexpr int AFF_THREADS = 256;
+template <int PHASE>
+__global__ void __launch_bounds__(AFF_THREADS)
+aff_prepass_kernel(const __grid_constant__ DevSession S) {
+  __shared__ ClassRec scls;
+  __shared__ ClassAff sca;
+  if (__ldcg(&S.ctl->done) || !S.cf.nodeorder) return;
+  const uint32_t cls_id = __ldcg(&S.ctl->cur_class);
+  if (S.aff.cls[cls_id].w_cnt == 0) return;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
+  if (PHASE == 0) {
+    for (uint32_t i = gtid; i < S.aff.dom_total; i += nthr) S.aff.dom_sum[i] = 0;
+    if (gtid == 0) { S.aff.minmax[0] = 0; S.aff.minmax[1] = 0; }
+    return;
+  }
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(&scls);
+    for (uint32_t i = threadIdx.x; i < sizeof(ClassRec) / 4; i += blockDim.x) dst[i] = src[i];
+    const uint32_t* as = reinterpret_cast<const uint32_t*>(&S.aff.cls[cls_id]);
+    uint32_t* ad = reinterpret_cast<uint32_t*>(&sca);
+    for (uint32_t i = threadIdx.x; i < sizeof(ClassAff) / 4; i += blockDim.x) ad[i] = as[i];
+  }
+  __syncthreads();
+  const size_t tile_u64 = (size_t)S.ncols * TILE_NODES;
+  long long mn = 0, mx = 0;
+  for (uint32_t n = gtid; n < S.N; n += nthr) {
+    TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, S.cf.R, S.cf.W};
+    uint64_t key = eval_pair(S.cf, scls, acc, n, nullptr);
+    if (key && S.cf.predicates && !aff_pred(S.aff, sca, S.N, n)) key = 0;
+    if (!key) continue;
+    if (PHASE == 1) {
+      aff_pass1_node(S.aff, sca, S.N, n, [&](uint32_t slot, long long v) {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&S.aff.dom_sum[slot]), (unsigned long long)v); });
+    } else {
+      const long long cnt = aff_count_node(S.aff, sca, S.N, n);
+      mn = cnt < mn ? cnt : mn; mx = cnt > mx ? cnt : mx;
+    }
+  }
+  if (PHASE == 2) {
+    if (mn < 0) atomicMin(&S.aff.minmax[0], mn);
+    if (mx > 0) atomicMax(&S.aff.minmax[1], mx);
   }
 }
 

@@ -116,11 +116,73 @@ class kbo_pod_objects(C.Structure):
                [("n_topo", C.c_uint32), ("node_topo", C.POINTER(C.c_int32))]
 
 
+def _serialize_pod_objects(raw) -> dict:
+    """builder.flatten's raw pod objects (snap.meta["pod_objects"]) -> the interned arrays of kbo_pod_objects."""
+    nodes, pending, existing, nidx = raw["nodes"], raw["pending"], raw["existing"], raw["node_index"]
+    N, T = len(nodes), len(pending)
+    strs = {}
+
+    def sid(x: str) -> int:
+        return strs.setdefault(x, len(strs))
+    allpods = list(pending) + list(existing)
+    topo_keys = {}
+    ob = {"P": len(allpods), "T": T, "pod_ns": [], "lab_off": [0], "lab_key": [], "lab_val": [], "has_aff": [], "has_anti": [],
+          "term_off": [0], "term_kind": [], "term_weight": [], "term_topo": [], "term_nil": [], "term_ns_off": [0], "term_ns": [],
+          "term_req_off": [0], "req_key": [], "req_op": [], "req_val_off": [0], "req_val": [],
+          "pod_node": [], "pod_listed": [], "pod_in_tasks": [], "pod_unbound": []}
+    opn = {"In": 0, "NotIn": 1, "Exists": 2, "DoesNotExist": 3}
+    for p in allpods:
+        ob["pod_ns"].append(sid(p.namespace))
+        for k, v in sorted(p.labels.items()):
+            ob["lab_key"].append(sid(k)); ob["lab_val"].append(sid(v))
+        ob["lab_off"].append(len(ob["lab_key"]))
+        ob["has_aff"].append(1 if p.pod_affinity is not None else 0)
+        ob["has_anti"].append(1 if p.pod_anti_affinity is not None else 0)
+        for kind, a in ((0, p.pod_affinity), (1, p.pod_anti_affinity)):
+            if a is None:
+                continue
+            for (pref, wt, term) in [(0, 0, t) for t in a.required] + [(2, w, t) for (w, t) in a.preferred]:
+                ob["term_kind"].append(kind + pref)
+                ob["term_weight"].append(wt)
+                ob["term_topo"].append(topo_keys.setdefault(term.topology_key, len(topo_keys)) if term.topology_key else -1)
+                ob["term_nil"].append(1 if term.nil_selector else 0)
+                for ns in term.namespaces:
+                    ob["term_ns"].append(sid(ns))
+                ob["term_ns_off"].append(len(ob["term_ns"]))
+                for k, v in sorted(term.match_labels.items()):      # matchLabels: key In (value) (LabelSelectorAsSelector)
+                    ob["req_key"].append(sid(k)); ob["req_op"].append(0); ob["req_val"].append(sid(v)); ob["req_val_off"].append(len(ob["req_val"]))
+                for (k, op, vals) in term.match_expressions:
+                    ob["req_key"].append(sid(k)); ob["req_op"].append(opn[op])
+                    for v in vals:
+                        ob["req_val"].append(sid(v))
+                    ob["req_val_off"].append(len(ob["req_val"]))
+                ob["term_req_off"].append(len(ob["req_key"]))
+        ob["term_off"].append(len(ob["term_kind"]))
+    for p, li, it in zip(existing, raw["listed"], raw["in_tasks"]):
+        ob["pod_node"].append(nidx[p.node_name])
+        ob["pod_listed"].append(1 if li else 0)
+        ob["pod_in_tasks"].append(1 if it else 0)
+        ob["pod_unbound"].append(0)                                   # a pod the cache placed on a node has Spec.NodeName set
+    ob["n_topo"] = len(topo_keys)
+    nt = np.full((max(1, len(topo_keys)), max(1, N)), -1, dtype=np.int32)
+    for key, ki in topo_keys.items():
+        for i, n in enumerate(nodes):
+            if key in n.labels:
+                nt[ki, i] = sid("\0v:" + n.labels[key])
+    ob["node_topo"] = nt
+    return ob
+
+
 class _PodObjects:
     """Hands the raw pod objects of a snapshot (builder.py: snap.meta["pod_objects"]) to the oracle for the duration of a call."""
 
     def __init__(self, snap: Snapshot):
-        self.ob = (snap.meta or {}).get("pod_objects")
+        raw = (snap.meta or {}).get("pod_objects")
+        if raw is not None and "P" not in raw:
+            if "_kbo" not in raw:
+                raw["_kbo"] = _serialize_pod_objects(raw)
+            raw = raw["_kbo"]
+        self.ob = raw
         self.N = snap.N
 
     def __enter__(self):

@@ -46,8 +46,15 @@ def _spec(rng, p_req=0.6, p_pref=0.5):
     return a
 
 
-def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_affine: float = 0.6, besteffort: bool = False) -> B.SessionBuilder:
+def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_affine: float = 0.6, besteffort: bool = False,
+                            spec_pool: int = 0) -> B.SessionBuilder:
+    """spec_pool > 0: the PodGroups draw their (labels, affinity, anti-affinity) from that many templates (large sessions stay
+    within the 64 counter groups of kb_pod_affinity)."""
     rng = np.random.default_rng(seed)
+    pool = []
+    for _ in range(spec_pool):
+        lab = {"app": APPS[int(rng.integers(0, 4))]}
+        pool.append((lab, _spec(rng) if rng.random() < p_affine * 0.6 else None, _spec(rng) if rng.random() < p_affine else None))
     sb = B.SessionBuilder()
     nq = int(rng.integers(1, 3))
     for q in range(nq):
@@ -65,9 +72,14 @@ def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_a
     # pods already running: some belong to session jobs (util.PodLister sees them), some to a group without queue (NodeInfo.Tasks only)
     sb.add_pod_group(B.PodGroup("ns1", "run-a", "q0", min_member=1))
     sb.add_pod_group(B.PodGroup("ns2", "run-b", "nosuchqueue", min_member=1))
+    load = {}
     for i in range(int(rng.integers(0, n_nodes))):
         ns, grp = ("ns1", "run-a") if rng.random() < 0.7 else ("ns2", "run-b")
-        p = B.build_pod(ns, f"r{i}", f"n{int(rng.integers(0, n_nodes)):03d}", "Running", B.build_resource_list("1", "1Gi"), grp,
+        host = int(rng.integers(0, n_nodes))
+        if load.get(host, 0) >= 2:
+            continue                      # never over-commit a node: the cache would refuse the pod (node_info.go:161-167)
+        load[host] = load.get(host, 0) + 1
+        p = B.build_pod(ns, f"r{i}", f"n{host:03d}", "Running", B.build_resource_list("1", "1Gi"), grp,
                         labels={"app": APPS[int(rng.integers(0, 4))]})
         if rng.random() < 0.3:
             p.labels["tier"] = "x"
@@ -87,6 +99,8 @@ def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_a
             labels["tier"] = "x"
         aff = _spec(rng) if rng.random() < p_affine * 0.6 else None
         anti = _spec(rng) if rng.random() < p_affine else None
+        if pool:
+            labels, aff, anti = pool[int(rng.integers(0, len(pool)))]
         req = {} if (besteffort and rng.random() < 0.5) else B.build_resource_list(str(int(rng.choice([1, 2, 3]))), f"{int(rng.choice([1, 2, 4]))}Gi")
         for i in range(ntask):
             p = B.build_pod(ns, f"pg{g}-{i}", "", "Pending", req, f"pg{g}", labels=dict(labels))

@@ -1,0 +1,113 @@
+"""`-m gpu`: inter-pod (anti)affinity on the CUDA path (visit_kernel<BF, AFF = 1> + aff_prepass_kernel) through the C ABI,
+bit-exact against the oracle, which walks the raw pod objects (predicates.go:1261-1572, interpod_affinity.go:99-235)."""
+import numpy as np
+import pytest
+
+from kube_batch_b200 import abi, builder as B, engine
+from kube_batch_b200.snapshot import PluginConf
+from oracle import kbo
+import aff_gen
+import util
+import test_pod_affinity as tpa
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    e = engine.Engine(device=0)
+    yield e
+    e.close()
+
+
+def run_and_check(eng, snap, conf, what, actions=1):
+    o = kbo.allocate(snap, conf, actions=actions)
+    eng.load(snap, conf)
+    r = eng.allocate() if actions & 1 else None
+    if actions & 2:
+        r = eng.backfill()
+    util.assert_same_decisions(o.decisions, r.decisions, what)
+    util.assert_same_state(o, eng.node_state(), eng.order_state(), what)
+    st = r.stats
+    assert (st.tasks_processed, st.tasks_allocated, st.tasks_pipelined, st.jobs_ready, st.pairs_logical) == \
+        (o.result.tasks_processed, o.result.tasks_allocated, o.result.tasks_pipelined, o.result.jobs_ready, o.result.pairs_logical), what
+    assert st.pipeline == 0 and st.kernel_launches > 0
+    return o, r
+
+
+def test_hand_computed_cases_on_the_gpu(eng):
+    # self anti-affinity: one pod per host
+    sb = tpa.cluster(4)
+    for i in range(5):
+        p = tpa.pod(f"p{i}", {"app": "web"}, creation=i)
+        p.pod_anti_affinity = B.PodAffinity(required=[tpa.term(tpa.HOST, app="web")])
+        sb.add_pod(p)
+    o, r = run_and_check(eng, sb.flatten(), PluginConf.default(), "spread")
+    assert sorted(r.decisions["node"][:4].tolist()) == [0, 1, 2, 3] and r.decisions["kind"][4] == abi.KB_KIND_NONE
+    # first pod of a self-affine series, then the zone is fixed
+    sb = tpa.cluster(6, zones=3)
+    for i in range(4):
+        p = tpa.pod(f"p{i}", {"app": "ring"}, creation=i)
+        p.pod_affinity = B.PodAffinity(required=[tpa.term(tpa.ZONE, app="ring")])
+        sb.add_pod(p)
+    o, r = run_and_check(eng, sb.flatten(), PluginConf.default(), "ring")
+    assert len({int(n) % 3 for n in r.decisions["node"]}) == 1
+    # the GetNodeInfo quirk of the priority (nodeorder.go:49-63)
+    sb = tpa.cluster(3, zones=3)
+    sb.add_pod_group(B.PodGroup("ns", "pg0", "q1", min_member=1, creation=0))
+    sb.add_pod_group(B.PodGroup("ns", "pg2", "q1", min_member=1, creation=2))
+    sb.pod_groups[0].creation = 1
+    c0 = tpa.pod("c0", {"app": "c"}, group="pg0"); c0.node_selector = {tpa.HOST: "n0"}
+    a0 = tpa.pod("a0", {"app": "a"}, group="pg1"); a0.node_selector = {tpa.HOST: "n2"}
+    b0 = tpa.pod("b0", {"app": "b"}, group="pg2"); b0.pod_affinity = B.PodAffinity(preferred=[(7, tpa.term(tpa.HOST, app="a"))])
+    for p in (c0, a0, b0):
+        sb.add_pod(p)
+    snap = sb.flatten()
+    o, r = run_and_check(eng, snap, tpa.ONLY_PODAFF, "first unbound node")
+    where = {snap.meta["tasks"][t]: int(r.decisions["node"][t]) for t in range(snap.T)}
+    assert where == {"ns/c0": 0, "ns/a0": 2, "ns/b0": 0}
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_affinity_sessions_on_the_gpu(eng, seed):
+    sb = aff_gen.random_affinity_session(seed, n_nodes=4 + seed % 13, n_groups=3 + seed % 6, besteffort=seed % 4 == 3)
+    snap = sb.flatten()
+    if snap.pod_affinity is None:
+        pytest.skip("no affinity terms drawn")
+    for ci, conf in enumerate(tpa.AFF_CONFS):
+        run_and_check(eng, snap, conf, f"seed {seed} conf {ci}", actions=1)
+        run_and_check(eng, snap, conf, f"seed {seed} conf {ci} +backfill", actions=3)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_larger_affinity_sessions_on_the_gpu(eng, seed):
+    """several node tiles per scan CTA group, hundreds of per-task scans"""
+    sb = aff_gen.random_affinity_session(9000 + seed, n_nodes=700 + 97 * seed, n_groups=60, p_affine=0.5, spec_pool=5)
+    snap = sb.flatten()
+    assert snap.pod_affinity is not None
+    o, r = run_and_check(eng, snap, PluginConf.default(), f"large seed {seed}", actions=3)
+    assert int((r.decisions["kind"] == abi.KB_KIND_ALLOCATED).sum()) > 50
+
+
+def test_cycle_with_the_placing_actions_and_refusals(eng):
+    sb = aff_gen.random_affinity_session(77, n_nodes=20, n_groups=10)
+    snap = sb.flatten()
+    assert snap.pod_affinity is not None
+    conf = PluginConf.default()
+    o = kbo.allocate(snap, conf, actions=3)
+    eng.load(snap, conf)
+    r = eng.cycle(("allocate", "backfill"))
+    res = r[0] if isinstance(r, tuple) else r
+    util.assert_same_decisions(o.decisions, res.decisions, "kb_cycle(allocate, backfill)")
+    # reclaim / preempt do not maintain the affinity counters: refused loudly
+    with pytest.raises(engine.KbError) as ei:
+        eng.load_running(snap.meta["running"])
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+    with pytest.raises(engine.KbError) as ei:
+        eng.predicate_score(0, 1)
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+    # the flags alone, without the flattened tables: refused
+    snap.pod_affinity = None
+    with pytest.raises(engine.KbError) as ei:
+        eng.load(snap, conf)
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
