@@ -89,11 +89,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def parity_verdict(workload, eng, res):
-    """'ok' iff this rank's decisions + node / job state equal the committed oracle digests (tests/golden/cycle_hashes.json)."""
+def parity_verdict(workload, eng, res, replica=0):
+    """'ok' iff this rank's decisions + node / job state equal the committed oracle digests (tests/golden/cycle_hashes.json;
+    `replica` > 0: the digest of that rank's own cluster, synth.make(workload, replica))."""
     from kube_batch_b200 import digest
     hp = os.path.join(ROOT, "tests", "golden", "cycle_hashes.json")
-    g = json.load(open(hp)).get(workload) if os.path.exists(hp) else None
+    g = json.load(open(hp)).get(workload + (f"#{replica}" if replica else "")) if os.path.exists(hp) else None
     if g is None:
         return "no committed digest for this workload"
     ns, osr = eng.node_state(), eng.order_state()
@@ -197,8 +198,17 @@ def run_ours(args, rank, world, local_rank):
         dist.broadcast(uid_t, 0)
         uid = bytes(uid_t.cpu().numpy().tobytes())
 
-    snap, conf = synth.make(args.workload)
-    eng = engine.Engine(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
+    # N > 1: the cycle is one serial replay, so a second GPU cannot shorten it; what N GPUs buy is N SESSIONS
+    # at once.  Default: rank r schedules its OWN cluster of the workload's shape (synth.make(workload, replica=r)) — N
+    # independent sessions, no collective, "weak" scaling; every rank's outcome is checked against the committed oracle digest
+    # of its cluster.  --sessions replicated: every rank runs the SAME session (the engine's world_size > 1 default), "strong".
+    independent = world > 1 and args.sessions == "independent"
+    replica = rank if independent else 0
+    snap, conf = synth.make(args.workload, replica=replica)
+    if independent:
+        eng = engine.Engine(device=local_rank)          # a single-GPU engine per rank: the ranks share nothing
+    else:
+        eng = engine.Engine(device=local_rank, rank=rank, world_size=world, nccl_unique_id=uid)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     def barrier():
@@ -235,14 +245,19 @@ def run_ours(args, rank, world, local_rank):
     pairs = int(st.pairs_logical)
 
     # ---- parity of the timed cycle's outcome, on EVERY rank, against the committed oracle digests (outside the timed region) ----
-    parity = parity_verdict(args.workload, eng, last)
+    parity = parity_verdict(args.workload, eng, last, replica)
     if dist is not None:
         t = torch.tensor([1 if parity == "ok" else 0], dtype=torch.int32, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MIN)
         if int(t.item()) == 0 and parity == "ok":
             parity = "mismatch on another rank"
-    value = pairs * args.steps / (dev_ms * 1e-3)
-    groups_per_s = int(st.jobs_ready) * args.steps / (dev_ms * 1e-3)
+    pairs_all, groups_all = pairs, int(st.jobs_ready)
+    if independent:            # units ALL ranks processed / max-over-ranks time
+        t = torch.tensor([pairs, int(st.jobs_ready)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pairs_all, groups_all = int(t[0].item()), int(t[1].item())
+    value = pairs_all * args.steps / (dev_ms * 1e-3)
+    groups_per_s = groups_all * args.steps / (dev_ms * 1e-3)
 
     # ---- end to end through the C ABI with host buffers: e2e ----
     e2e_steps = max(1, min(args.steps, 5))
@@ -257,7 +272,12 @@ def run_ours(args, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = int(r.stats.pairs_logical) * e2e_steps / e2e_s
+    e2e_pairs = int(r.stats.pairs_logical)
+    if independent:
+        t = torch.tensor([e2e_pairs], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        e2e_pairs = int(t.item())
+    e2e_value = e2e_pairs * e2e_steps / e2e_s
 
     if rank != 0:
         eng.close()
@@ -266,6 +286,10 @@ def run_ours(args, rank, world, local_rank):
         if parity != "ok" and args.workload in ("c2", "c3", "c4"):
             raise SystemExit(f"bench.py rank {rank}: parity check failed: {parity}")
         return
+    workload = workload_desc(args.workload, snap, conf)
+    workload["parallelism"] = ("single GPU" if world == 1 else
+                               f"{world} independent sessions, one cluster of this shape per GPU (seeds +1000 per rank), no collective" if independent else
+                               f"one session replicated on {world} GPUs (every rank runs the whole cycle), no collective")
 
     # ---- roofline of the dominant kernel: algorithmic bytes of its scans / device time ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -292,6 +316,10 @@ def run_ours(args, rank, world, local_rank):
         "kernel": kern, "launches_per_step": n_launch, "scans_per_step": scans,
         "algorithmic_bytes_per_launch": bytes_per_launch,
         "avg_launch_us": 1e3 * st.gpu_ms / max(1, n_launch), "peak_source": peak_src,
+        # SURVEY 8d counts the reference's (task, node) pairs: 128 B each.  The engine scans one CLASS per visit instead of every
+        # task, so `achieved` (pairs really scanned) is the honest kernel figure and this one is the algorithm-level equivalent
+        "achieved_logical_pairs": int(st.pairs_logical) * ALGO_BYTES_PER_PAIR / (st.gpu_ms * 1e-3) / 1e9 * world,
+        "frac_logical_pairs": int(st.pairs_logical) * ALGO_BYTES_PER_PAIR / (st.gpu_ms * 1e-3) / 1e9 / peak,
         "note": "pairs the scans really evaluated x 128 B / device time of the cycle; the node table stays resident in shared memory "
                 "(pipeline) or L2 (per-launch kernels): the cycle is bound by the latency of the sequential replay, not by bandwidth",
     }
@@ -332,9 +360,9 @@ def run_ours(args, rank, world, local_rank):
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak" if independent else "strong", "vs_baseline": None,
         "dtype": "f64 compares + i64 scores + u64 bitmasks", "data": "synthetic",
-        "config": workload_desc(args.workload, snap, conf),
+        "config": workload,
         "podgroups_placed_per_s": groups_per_s,
         "parity": parity,
         "pairs_scanned_per_s": int(st.pairs_scanned) / (st.gpu_ms * 1e-3),
@@ -344,6 +372,7 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": 1e3 * e2e_s / e2e_steps, "steps": e2e_steps,
                 "what": "kb_session_load (host flatten + H2D) + kb_allocate (cycle + decisions D2H), wall clock"},
         "gpu_launches": launches,
+        "sessions": ("independent" if independent else "replicated") if world > 1 else "one",
         "exchange": {0: "none (single GPU)", 1: "ncclAllGather per scan", 2: "fused peer-memory exchange (NVLink stores + flags) inside visit_kernel",
                      3: "none: every rank runs the whole cycle on the full (replicated) node table"}.get(int(st.exchange_mode), "?"),
         "engine_mode": "persistent pipeline (cycle_kernel)" if pipe else "per-visit launches (visit_kernel)",
@@ -370,6 +399,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--sessions", default="independent", choices=["independent", "replicated"],
+                    help="N > 1: one cluster per GPU (weak scaling, default) or the same session on every GPU (strong)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="wall-time bound of each cpu_baseline sample")
     ap.add_argument("--ref-seconds", type=float, default=6.0, help="wall-time bound of one --impl reference step")
     args = ap.parse_args()

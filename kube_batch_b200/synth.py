@@ -254,8 +254,13 @@ def running_of(s: Snapshot, preemptable_frac: float = 0.0, seed: int = 1) -> dic
             "flags": np.zeros(n, dtype=np.uint32)}
 
 
-def make(name: str) -> Tuple[Snapshot, PluginConf]:
+def make(name: str, replica: int = 0) -> Tuple[Snapshot, PluginConf]:
+    """replica > 0: another cluster of the same shape (seed + 1000 * replica) — what rank `replica` schedules when bench.py runs
+    N independent sessions on N GPUs."""
     spec = CONFIGS[name]
+    if replica:
+        from dataclasses import replace
+        spec = replace(spec, seed=(spec.seed if spec.seed is not None else 0xB200) + 1000 * int(replica))
     return generate(spec), (spec.conf or config_conf(name))
 
 

@@ -43,6 +43,15 @@ if __name__ == "__main__":
                         "decisions": digest.decisions_digest(o.decisions),
                         "state": digest.state_digest(o.node_idle, o.node_releasing, o.job_ready, o.job_share)}
         print(name, hashes[name])
+    if "--replicas" in sys.argv:          # the clusters ranks 1..7 schedule when bench.py runs N independent sessions (synth.make(name, replica))
+        for r in range(1, 8):
+            snap, conf = synth.make("c3", replica=r)
+            o = kbo.allocate(snap, conf, threads=os.cpu_count() or 1)
+            hashes[f"c3#{r}"] = {"tasks": int(snap.T), "nodes": int(snap.N), "allocated": int(o.result.tasks_allocated),
+                                 "pipelined": int(o.result.tasks_pipelined), "visits": int(o.result.visits), "jobs_ready": int(o.result.jobs_ready),
+                                 "decisions": digest.decisions_digest(o.decisions),
+                                 "state": digest.state_digest(o.node_idle, o.node_releasing, o.job_ready, o.job_share)}
+            print(f"c3#{r}", hashes[f"c3#{r}"])
     old = {}
     hp = os.path.join(HERE, "cycle_hashes.json")
     if os.path.exists(hp):
