@@ -244,7 +244,7 @@ struct BuiltSession {
   void bind_backfill(DevSession& D, unsigned char* mb, unsigned char* ib) const {
     bind(D, mb, ib);
     D.backfill = 1; D.overlap = 0; D.kchain = 1; D.pipe = 0;
-    D.cf.fit_mode = 1; D.cf.nodeorder = 0; D.cf.score_bias = 0;
+    D.cf.fit_mode = hc.cf.predicates ? 2 : 1; D.cf.nodeorder = 0; D.cf.score_bias = 0;
     D.To = Tb;
     D.classes = (ClassRec*)(ib + oi.bf_classes);        // same ids; `initreq` holds Resreq (EvalConf.fit_mode)
     D.ord_task = (uint32_t*)(ib + oi.bf_ord_task); D.ord_class = (uint32_t*)(ib + oi.bf_ord_class);

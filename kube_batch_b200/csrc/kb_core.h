@@ -71,6 +71,10 @@ struct EvalConf {
                               // 1: backfill — no resource predicate, but NodeInfo.AddTask needs Resreq <= Idle
                               //    (node_info.go:161-167): the backfill view's class table carries Resreq in `initreq`
                               //    and the Releasing alternative is masked off
+                              // 2: backfill with the predicates plugin enabled — the key ignores the resources altogether: the
+                              //    task goes to the FIRST node that passes ssn.PredicateFn, and if node.AddTask refuses it there
+                              //    the task stays Allocated on no node and every later predicate of the session fails
+                              //    (Ctl.pred_dead); `fits_idle` still reports Resreq <= Idle
   uint32_t pad0;
 };
 
@@ -247,7 +251,7 @@ KB_HD uint64_t eval_pair(const EvalConf& cf, const ClassRec& c, const NodeAcc& n
   }
   fr = fr & (cf.fit_mode == 0);                 // backfill only ever allocates from Idle
   if (fits_idle) *fits_idle = fi;
-  bool ok = fi | fr;
+  bool ok = fi | fr | (cf.fit_mode == 2);
   bool pok = true;            // ssn.PredicateFn alone (the predicates plugin), irrespective of the resource fit
 
   if (cf.predicates) {

@@ -59,6 +59,9 @@ struct Ctl {
   //      (no usable look-ahead list), candidate-chain extensions, lists consumed with a non-empty patch set, log entries patched
   uint32_t pipe_requests, pipe_urgent, pipe_extends, pipe_patched, pipe_patch_entries;
   uint32_t phantoms;      // backfill: tasks left Allocated on no node (ssn.Allocate sets the status before node.AddTask refuses, session.go:241-262)
+  uint32_t pred_dead;     // ... with the predicates plugin enabled such a task makes InterPodAffinityMatches return an error for every later
+                          // pair (PodLister lists it, GetNodeInfo("") fails: plugins/util/util.go:93-100, vendor/.../predicates.go:1381-1393):
+                          // no node passes ssn.PredicateFn for the rest of the session
   unsigned long long cyc_wait;     // replayer cycles spent between posting the visit and the eval warps' results (list wait + eval)
   unsigned long long cyc_ring, cyc_plan;      // timing mode: hot-ring append + write-back command; planner
 };

@@ -771,8 +771,14 @@ int kb_cycle(kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decisi
   CUDA_TRY(e, cudaMalloc(&d_bounds, hb.size() * 4));
   CUDA_TRY(e, cudaMemsetAsync(d_bounds, 0, hb.size() * 4, e->stream));
   struct Free { uint32_t* p; ~Free() { if (p) cudaFree(p); } } free_bounds{d_bounds};
+  bool session_dead = false;                 // Ctl.pred_dead after a backfill: every later ssn.PredicateFn of the session fails
   for (uint32_t i = 0; i < n_actions; ++i) {
     const uint8_t a = actions[i];
+    if (session_dead) {                      // the remaining actions find no node for anybody: nothing to launch
+      if (latest) carry_u32_kernel<<<1, 1, 0, e->stream>>>(latest, d_bounds + 2 * i);
+      if (nev_ev) carry_u32_kernel<<<1, 1, 0, e->stream>>>(nev_ev, d_bounds + 2 * i + 1);
+      continue;
+    }
     if (a == KB_ACT_RECLAIM || a == KB_ACT_PREEMPT) {
       if (latest && latest != step_ev) carry_u32_kernel<<<1, 1, 0, e->stream>>>(latest, step_ev);
       CUDA_TRY(e, launch_evict(a == KB_ACT_PREEMPT, e->dev, e->ev, e->coop_ok ? e->sm_count : 1, e->stream));
@@ -795,6 +801,7 @@ int kb_cycle(kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decisi
       const int rc = run_action(e, bf, nullptr, nullptr, true);
       if (rc) return rc;
       launches += e->last_launches;
+      if (bf && e->h_ctl->pred_dead) session_dead = true;
       latest = bf ? step_bf : step_alloc;
       bf_last = bf; placed_ran = true;
       // a later evicting action must see the placements: they are in the decision table and the node / job tables already

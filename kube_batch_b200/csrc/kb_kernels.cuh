@@ -287,7 +287,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
             eval_pair(S.cf, sm.cls, acc, my_node, nullptr, &pk);
             if (AFF && pk && S.cf.predicates) pk = aff_pred(S.aff, sm.cls_aff, S.N, my_node);
           }
-          if (sm.pred_any_all || __any_sync(FULL, pk)) {
+          if (S.cf.fit_mode != 2 && (sm.pred_any_all || __any_sync(FULL, pk))) {      // fit_mode 2: a node that passes the predicates is IN the list
             if (lane == 0) {
               kb_decision d;
               d.node = -1; d.kind = KB_KIND_ALLOCATED; d.dispatched = 0; d.reserved = 0;
@@ -301,6 +301,21 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       }
       const uint32_t owner = (uint32_t)__ffs(__ballot_sync(FULL, cur_key == best)) - 1u;
       const unsigned ownbits = __shfl_sync(FULL, (next_valid ? 1u : 0u) | (cur_fi ? 2u : 0u), owner);
+      if (BF && S.cf.fit_mode == 2 && !(ownbits & 2u)) {
+        // backfill with the predicates plugin (EvalConf.fit_mode 2): the FIRST node that passes ssn.PredicateFn is tried and
+        // node.AddTask refuses it (Resreq > Idle): ssn.Allocate has already made the task Allocated (session.go:241-262), it
+        // has no node, and from now on InterPodAffinityMatches returns an error for every pair of the session (Ctl.pred_dead)
+        if (lane == 0) {
+          kb_decision d;
+          d.node = -1; d.kind = KB_KIND_ALLOCATED; d.dispatched = 0; d.reserved = 0;
+          d.step = 0xFFFFFFFFu; d.dispatch_step = 0xFFFFFFFFu;
+          S.dec[task] = d;
+          c.pred_dead = 1;
+        }
+        n_phantom += 1;
+        cur_key = 0; next_key = 0; next_valid = true;
+        reason = STOP_NOFIT; break;
+      }
       if (!(ownbits & 1u)) refresh();
       const bool fits_idle = (ownbits & 2u) != 0;
       // commit: ssn.Allocate (session.go:235) or ssn.Pipeline (session.go:194) -> NodeInfo.AddTask (node_info.go:172-212):
@@ -458,7 +473,7 @@ __device__ __forceinline__ bool issue_first_group(const DevSession& S, VisitSmem
 template <bool PH = false, int AFF = 0>
 __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& sm, uint64_t* tilebuf, const uint32_t scanner_idx,
                                                const uint32_t n_scanners, const uint32_t cls_id, const int tid, const int lane, const int warp,
-                                               const bool first_issued = false) {
+                                               const bool first_issued = false, const bool pred_dead = false) {
   const uint32_t tile_u64 = S.ncols * TILE_NODES;
   const uint32_t tile_bytes = tile_u64 * 8u;
   // ---------------- scan: tile GROUPS blockIdx.x, +gridDim.x, ...: S.tpi tiles per iteration, double-buffered TMA ----------------
@@ -512,6 +527,7 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
       ColAcc acc{tilebuf + ((size_t)b * tpi + sub) * tile_u64, part * 32u + lane, TILE_NODES, S.cf.R, S.cf.W};
       bool pok = false;
       key = eval_pair(S.cf, sm.cls, acc, node, nullptr, PH ? &pok : nullptr);
+      if (PH && pred_dead) { key = 0; pok = false; }        // a task Allocated on no node: InterPodAffinityMatches errors for every pair (Ctl.pred_dead)
       if (AFF) {
         if (S.cf.predicates && !aff_pred(S.aff, sm.cls_aff, S.N, node)) { key = 0; pok = false; }      // predicate step 10
         if (ipa && key) key = aff_add_score(key, S.aff.w_podaff, aff_score(aff_count_node(S.aff, sm.cls_aff, S.N, node), ipa_min, ipa_max));
@@ -615,7 +631,8 @@ visit_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   const long long t_start = clock64();
 
-  uint64_t mylist = scan_phase<BF != 0, AFF>(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true);
+  const bool pred_dead = BF && *((volatile uint32_t*)&gctl->pred_dead) != 0;
+  uint64_t mylist = scan_phase<BF != 0, AFF>(S, sm, tilebuf, blockIdx.x, gridDim.x, cls_id, tid, lane, warp, true, pred_dead);
   if (warp == 0) {
     S.cand[(size_t)blockIdx.x * KTOP + lane] = mylist;
     if (BF && lane == 0) S.cand[((size_t)gridDim.x + blockIdx.x) * KTOP] = (uint64_t)sm.pred_any;      // second bank of the list area

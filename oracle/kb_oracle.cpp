@@ -521,6 +521,7 @@ struct Session {
   std::map<std::string, VictimFn> preemptableFns, reclaimableFns;
   std::map<std::string, std::function<bool(const JobInfo&)>> jobPipelinedFns;
   uint32_t n_evicted = 0;               // cache.Evict calls (util.FakeEvictor.Evicts)
+  uint32_t n_allocated_nowhere = 0;     // tasks ssn.Allocate left Allocated on no node (see Allocate): the predicates plugin fails from then on
 
   // resolved once after OnSessionOpen: the (tier, plugin) walk of PredicateFn with its map lookups hoisted
   std::vector<const std::function<bool(const TaskInfo&, const NodeInfo&, int32_t, const uint64_t*)>*> resolvedPredicates;
@@ -821,7 +822,14 @@ struct Session {
   bool Allocate(TaskInfo& task, NodeInfo& node) {
     JobInfo& job = Jobs[task.Job];
     UpdateTaskStatus(job, task, Allocated);
-    if (!AddTask(node, task)) return false;
+    if (!AddTask(node, task)) {
+      // the status changed before node.AddTask refused (session.go:241-262): the task stays Allocated with NodeName "".
+      // util.PodLister lists it from now on, and CachedNodeInfo.GetNodeInfo("") (plugins/util/util.go:93-100) is an error that is
+      // not apierrors.IsNotFound: getMatchingAntiAffinityTopologyPairsOfPods (vendor/.../predicates.go:1381-1393) returns it and
+      // InterPodAffinityMatches fails — for EVERY later (pod, node) pair of the session, affinity terms or not.
+      if (task.NodeName < 0) ++n_allocated_nowhere;
+      return false;
+    }
     task.step = step_counter++;
     ++n_allocated;
     for (auto& eh : allocateHandlers) eh(task);
@@ -1206,6 +1214,8 @@ struct predicatesPlugin : Plugin {
     ssn->predicateFns[Name()] = [=](const TaskInfo& task, const NodeInfo& node, int32_t pods, const uint64_t* ports) {
       // :127  node.Allocatable.MaxTaskNum <= len(nodeInfo.Pods())
       if (node.max_pods <= pods) return false;
+      // InterPodAffinityMatches (:1261-1288, the plugin's last step) returns an error once a listed pod has no node: see Session::Allocate
+      if (ssn->n_allocated_nowhere) return false;
       // CheckNodeConditionPredicate, vendor/.../predicates.go:1675-1698 (incl. Spec.Unschedulable)
       if (node.flags & (KB_NODE_NOT_READY | KB_NODE_NET_UNAVAILABLE | KB_NODE_UNSCHEDULABLE)) return false;
       // CheckNodeUnschedulablePredicate :1576-1593 — subsumed: an unschedulable node already failed above

@@ -102,6 +102,7 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
     TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
     uint64_t k = eval_pair(S.cf, cls, acc, n, nullptr, pok);
     if (ca && S.cf.predicates && !aff_pred(A, *ca, S.N, n)) { k = 0; if (pok) *pok = false; }
+    if (S.backfill && c.pred_dead) { k = 0; if (pok) *pok = false; }      // Ctl.pred_dead: every predicate fails once a task is Allocated on no node
     return k;
   };
   if (ipa) {
@@ -195,7 +196,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
             if (ca && S.cf.predicates && !aff_pred(S.aff, *ca, S.N, cd.node)) pok = false;
             any = any || pok;
           }
-          if (any) {
+          if (any && S.cf.fit_mode != 2) {
             kb_decision dd;
             dd.node = -1; dd.kind = KB_KIND_ALLOCATED; dd.dispatched = 0; dd.reserved = 0; dd.step = 0xFFFFFFFFu; dd.dispatch_step = 0xFFFFFFFFu;
             S.dec[S.ord_task[pos]] = dd;
@@ -206,6 +207,18 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
         reason = STOP_NOFIT; break;
       }
       Cand& cd = cand[owner];
+      if (S.cf.fit_mode == 2 && !cd.cur_fi) {
+        // backfill with the predicates plugin: the FIRST node that passes ssn.PredicateFn is tried; node.AddTask refuses
+        // (Resreq > Idle) -> the task stays Allocated on no node and every later predicate fails (Ctl.pred_dead)
+        kb_decision dd;
+        dd.node = -1; dd.kind = KB_KIND_ALLOCATED; dd.dispatched = 0; dd.reserved = 0; dd.step = 0xFFFFFFFFu; dd.dispatch_step = 0xFFFFFFFFu;
+        S.dec[S.ord_task[pos]] = dd;
+        S.job_ready[j] += 1;
+        c.phantoms += 1;
+        c.pred_dead = 1;
+        for (auto& x : cand) { x.cur_key = 0; x.next_key = 0; x.next_valid = true; }
+        reason = STOP_NOFIT; break;
+      }
       if (!cd.next_valid) refresh();
       const bool fits_idle = cd.cur_fi;
       cd.cnt += 1;
@@ -769,6 +782,9 @@ int kbemu_cycle(const kb_snapshot* snap, const kb_running* running, const kb_plu
   };
   for (uint32_t i = 0; i < n_actions; ++i) {
     const uint8_t a = actions[i];
+    // Ctl.pred_dead: backfill left a task Allocated on no node, ssn.PredicateFn fails for every pair from then on — the
+    // remaining actions find no node for anybody (kb_cycle skips them the same way)
+    if (E->Sbf.ctl->pred_dead) continue;
     if (a == 0 || a == 3) {
       if (have_latest) D.ctl->step = latest;
       if (a == 3) run_preempt(x, E->S, D); else run_reclaim(x, E->S, D);

@@ -325,7 +325,30 @@ def test_phantom_allocated_best_effort_task_matches_the_reference_order():
     assert o.decisions["kind"].tolist() == [abi.KB_KIND_ALLOCATED, abi.KB_KIND_ALLOCATED] and o.decisions["node"].tolist() == [0, -1]
     for mode in (0, 1, 5):
         check(s, conf, f"phantom mode{mode}", actions=3, mode=mode)
-    # a phantom that completes the gang is dispatched, together with the rest, by the job's NEXT successful Allocate
+    # With the predicates plugin the phantom poisons the session: util.PodLister lists it, CachedNodeInfo.GetNodeInfo("") is an
+    # error (plugins/util/util.go:93-100) that InterPodAffinityMatches returns for EVERY later pair (vendor/.../predicates.go:
+    # 1381-1393, 1261-1270).  So (a) the task is lost on the FIRST node that passes the predicates — backfill.go:50-65 moves on to
+    # the next node, whose predicate now fails — and (b) nobody is placed afterwards.
+    b = B.SessionBuilder()
+    b.add_queue(B.Queue("q", 1))
+    b.add_pod_group(B.PodGroup("ns", "g", "q", min_member=1))
+    b.add_node(B.Node("n0", {"cpu": 1, "memory": 4e9, "pods": 10}))
+    b.add_node(B.Node("n1", {"cpu": 1, "memory": 4e9, "pods": 10}))                                # plenty of room, and never reached
+    b.add_pod(B.Pod("ns", "full", "n0", "Running", {"cpu": 1, "memory": 1e9}, group="g"))
+    for k, nm in enumerate(["a", "b", "c"]):
+        b.add_pod(B.Pod("ns", "tiny-" + nm, "", "Pending", {"cpu": 0.005}, group="g", creation=k + 1))
+    s = b.flatten()
+    o = kbo.allocate(s, conf, actions=3)
+    assert o.decisions["node"].tolist() == [0, -1, -1]
+    assert o.decisions["kind"].tolist() == [abi.KB_KIND_ALLOCATED, abi.KB_KIND_ALLOCATED, abi.KB_KIND_NONE]
+    for mode in (0, 1, 5):
+        check(s, conf, f"poisoned session mode{mode}", actions=3, mode=mode)
+    # without the predicates plugin nothing evaluates InterPodAffinityMatches: the loop simply tries the next node
+    o = kbo.allocate(s, PluginConf.from_names([["gang"]]), actions=3)
+    assert o.decisions["node"].tolist() == [0, 1, 1] and (o.decisions["kind"] == abi.KB_KIND_ALLOCATED).all()
+    for mode in (0, 1, 5):
+        check(s, PluginConf.from_names([["gang"]]), f"no predicates plugin mode{mode}", actions=3, mode=mode)
+    # a phantom counts towards JobReady (gang), on one node and on several
     b = B.SessionBuilder()
     b.add_queue(B.Queue("q", 1))
     b.add_pod_group(B.PodGroup("ns", "g", "q", min_member=3))
