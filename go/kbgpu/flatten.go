@@ -58,6 +58,9 @@ type Flat struct {
 	jobCtime, queueCtime                   []int64
 	queueWeight                            []int32
 
+	snapFlags uint32  // KB_SNAPSHOT_*
+	podAff    *podAff // inter-pod (anti)affinity tables (podaffinity.go), nil when no pod of the session carries terms
+
 	// C-side copy of the tier configuration (strings, option and tier arrays), released by Free
 	cstrings []*C.char
 	cTiers   *C.kb_tier
@@ -282,20 +285,8 @@ func Flatten(ssn *framework.Session) (*Flat, error) {
 		return nil, fmt.Errorf("kbgpu: duplicate task UIDs in the session")
 	}
 
-	// ---- inter-pod (anti)affinity: predicate step 10 / InterPodAffinityPriority are outside this build.  The reference
-	//      also rejects nodes because of ANTI-affinity terms of pods already placed (predicates.go:1261-1288
-	//      satisfiesExistingPodsAntiAffinity) and scores required affinity terms of existing pods
-	//      (interpod_affinity.go:150-170): any such term anywhere in the session makes the cycle unsupported. ----
-	for _, job := range ssn.Jobs {
-		for _, t := range job.Tasks {
-			if t.Pod == nil {
-				continue
-			}
-			if aff := t.Pod.Spec.Affinity; aff != nil && (aff.PodAffinity != nil || aff.PodAntiAffinity != nil) {
-				return nil, &ErrUnsupported{fmt.Sprintf("pod %s/%s carries inter-pod (anti)affinity terms", t.Namespace, t.Name)}
-			}
-		}
-	}
+	// ---- inter-pod (anti)affinity (predicate step 10 / InterPodAffinityPriority): flattened at the end of this function into
+	//      kb_pod_affinity (podaffinity.go) once the task flags exist ----
 
 	// ---- resource dims ----
 	scalars := map[v1.ResourceName]bool{}
@@ -616,6 +607,15 @@ func Flatten(ssn *framework.Session) (*Flat, error) {
 		}
 	}
 	f.buildTiers(ssn.Tiers)
+	nidx := make(map[string]int, N)
+	for i, name := range f.NodeNames {
+		nidx[name] = i
+	}
+	pa, err := flattenPodAffinity(ssn, f, nidx, &f.snapFlags)
+	if err != nil {
+		return nil, err
+	}
+	f.podAff = pa
 	return f, nil
 }
 
@@ -714,7 +714,11 @@ func (a *arena) u64(s []uint64) *C.uint64_t { return (*C.uint64_t)(a.put(unsafe.
 // after kb_session_load returns: the library copies everything it needs before returning.
 func (f *Flat) cSnapshot(s *C.kb_snapshot, a *arena) {
 	s.abi_version = C.KB_ABI_VERSION
-	s.flags = 0 // Flatten refuses sessions that would need KB_SNAPSHOT_PLACED_POD_AFFINITY before it gets here
+	s.flags = C.uint32_t(f.snapFlags)
+	s.pod_affinity = nil
+	if f.podAff != nil {
+		s.pod_affinity = f.podAff.cPodAffinity(a)
+	}
 	s.R, s.W, s.N, s.T, s.J, s.Q = C.uint32_t(f.R), C.uint32_t(f.W), C.uint32_t(f.N), C.uint32_t(f.T), C.uint32_t(f.J), C.uint32_t(f.Q)
 	s.node_idle, s.node_releasing, s.node_used, s.node_allocatable = a.f64(f.nodeIdle), a.f64(f.nodeReleasing), a.f64(f.nodeUsed), a.f64(f.nodeAllocatable)
 	s.node_alloc_present, s.node_flags = a.u32(f.nodeAllocPresent), a.u32(f.nodeFlags)

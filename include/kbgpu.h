@@ -69,6 +69,13 @@ typedef enum kb_status {
                                                       and scores them (interpod_affinity.go:150-170): needs kb_snapshot.pod_affinity, else
                                                       KB_E_UNSUPPORTED_FEATURE                                                              */
 
+#define KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE (1u << 1) /* an AllocatedStatus task (Bound / Binding / Running / Allocated) of a session job names a
+                                                      node that is NOT in ssn.Nodes (cache.Snapshot drops NotReady nodes, cache.go:633-640; the
+                                                      job keeps its tasks).  util.PodLister lists the pod, CachedNodeInfo.GetNodeInfo fails
+                                                      (plugins/util/util.go:93-100), and InterPodAffinityMatches returns that error for EVERY
+                                                      (pod, node) pair (vendor/.../predicates.go:1381-1393): with the predicates plugin enabled
+                                                      no node passes ssn.PredicateFn in this session.  The engine reproduces exactly that.      */
+
 /* kb_decision.kind */
 #define KB_KIND_NONE      0 /* task was never placed this cycle                                   */
 #define KB_KIND_ALLOCATED 1 /* ssn.Allocate (framework/session.go:235)  — consumed node.Idle       */

@@ -39,6 +39,7 @@ KB_NODE_PID_PRESSURE = 1 << 5
 KB_TASK_BEST_EFFORT_QOS = 1 << 0
 KB_TASK_HAS_POD_AFFINITY = 1 << 1
 KB_SNAPSHOT_PLACED_POD_AFFINITY = 1 << 0
+KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE = 1 << 1
 KB_TASK_HAS_PREFERRED_NODE_AFFINITY = 1 << 2
 KB_TASK_AFF_SELF_MATCH = 1 << 3
 KB_MAX_AFF_GROUPS = 64

@@ -379,6 +379,10 @@ class SessionBuilder:
                     s.job_ready0[j] += 1
                 elif st == "Succeeded":
                     s.job_ready0[j] += 1
+            if p.node_name and p.node_name not in nidx and key in jidx and st in ("Bound", "Binding", "Running", "Allocated"):
+                # the job lists the task, its node is not part of the session (cache.Snapshot drops NotReady nodes, cache.go:633-640):
+                # util.PodLister + CachedNodeInfo.GetNodeInfo make every InterPodAffinityMatches call fail (kbgpu.h)
+                s.flags = int(getattr(s, "flags", 0)) | abi.KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE
             if p.node_name and p.node_name in nidx and st != "Pending":
                 i = nidx[p.node_name]
                 # cache.addTask: the job has the task (above); node.AddTask refuses what does not fit into Idle

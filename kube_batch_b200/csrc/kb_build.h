@@ -320,7 +320,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     if (world > 1) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "inter-pod affinity: not with a sharded node axis (KB_ENGINE_SHARD)");
     pipe_mode = 0; overlap_mode = 0; kchain = 1;
   }
-  if (s->flags & ~KB_SNAPSHOT_PLACED_POD_AFFINITY) return bfail(e, KB_E_BADARG, "unknown kb_snapshot.flags bits 0x%x", s->flags);
+  if (s->flags & ~(KB_SNAPSHOT_PLACED_POD_AFFINITY | KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE)) return bfail(e, KB_E_BADARG, "unknown kb_snapshot.flags bits 0x%x", s->flags);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
   if (s->Q > KB_MAX_Q) return bfail(e, KB_E_BADARG, "Q=%u > KB_MAX_Q", s->Q);
   if (s->N >= 0xFFFFFFF0u) return bfail(e, KB_E_BADARG, "N too large for the packed key");
@@ -689,7 +689,9 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         put(col_alloc_cpu(R), (uint64_t)s->node_alloc_cpu[n]); put(col_alloc_mem(R), (uint64_t)s->node_alloc_mem[n]);
         put(col_nz_cpu(R), (uint64_t)s->node_nz_cpu[n]); put(col_nz_mem(R), (uint64_t)s->node_nz_mem[n]);
         put(col_pods(R), (uint64_t)(uint32_t)s->node_pods[n] | ((uint64_t)(uint32_t)s->node_max_pods[n] << 32));
-        put(col_flags(R), (uint64_t)s->node_flags[n]);
+        // KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE: InterPodAffinityMatches errors for every pair, i.e. the predicates plugin rejects
+        // every node; K1 reads that as a node condition that fails (only evaluated when the plugin's predicate is enabled)
+        put(col_flags(R), (uint64_t)s->node_flags[n] | ((s->flags & KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE) ? (uint64_t)KB_NODE_NOT_READY : 0ull));
         for (uint32_t w = 0; w < W; ++w) {
           put(col_labels(R, W, w), s->node_labels[(size_t)w * N + n]);
           put(col_taints(R, W, w), s->node_taints[(size_t)w * N + n]);

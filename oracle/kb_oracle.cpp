@@ -1495,6 +1495,7 @@ int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, int mode, st
       if (!pb) { g_err = "Failed to get plugin " + po.Name; return KB_E_UNSUPPORTED_PLUGIN; }
       ssn->plugins[pb->Name()] = std::move(pb);   // later option of the same name overrides, like the Go map
     }
+  if (s->flags & KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE) ssn->n_allocated_nowhere = 1;   // PodLister -> GetNodeInfo error for every pair (see Session::Allocate)
   if (g_pod_world) {
     if (g_pod_world->T != T || g_pod_world->N != N) { g_err = "kbo_set_pod_objects: pod objects do not belong to this snapshot"; return KB_E_BADARG; }
     ssn->pw = g_pod_world;

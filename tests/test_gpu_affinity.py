@@ -111,3 +111,29 @@ def test_cycle_with_the_placing_actions_and_refusals(eng):
     with pytest.raises(engine.KbError) as ei:
         eng.load(snap, conf)
     assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+
+
+def test_big_affinity_session_matches_the_emulation_and_is_timed(eng):
+    """2 000 nodes / ~3 000 pending pods, a third of the PodGroups with (anti)affinity terms: hundreds of fresh scans, every one with
+    predicate step 10, many with the three priority passes.  The object-level oracle is O(pods) per pair (the reference's cost), so at
+    this size the engine is compared with the emulation of the device algorithm (itself pinned on the oracle at small sizes)."""
+    import json, os, time
+    sb = aff_gen.random_affinity_session(4242, n_nodes=2000, n_groups=1000, p_affine=0.35, spec_pool=6)
+    snap = sb.flatten()
+    assert snap.pod_affinity is not None
+    conf = PluginConf.default()
+    e = util.emu_allocate(snap, conf, actions=1, mode=1)
+    eng.load(snap, conf)
+    eng.allocate()
+    t0 = time.perf_counter()
+    r = eng.allocate()
+    wall = time.perf_counter() - t0
+    util.assert_same_decisions(e.decisions, r.decisions, "big affinity session vs emulation")
+    st = r.stats
+    rec = {"nodes": int(snap.N), "tasks": int(snap.T), "groups": int(snap.pod_affinity["n_groups"]), "kinds": int(snap.pod_affinity["n_kinds"]),
+           "allocated": int(st.tasks_allocated), "scans": int(st.scans), "kernel_launches": int(st.kernel_launches), "gpu_ms": float(st.gpu_ms),
+           "wall_ms": 1e3 * wall, "pairs_logical": int(st.pairs_logical)}
+    print("affinity timing:", json.dumps(rec))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(rec, open(os.path.join(out, "affinity_big_session.json"), "w"))

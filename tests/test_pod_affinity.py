@@ -256,3 +256,23 @@ def test_affinity_terms_without_the_flattened_tables_are_refused():
     snap.pod_affinity = None
     with pytest.raises(RuntimeError, match="no kb_pod_affinity"):
         util.emu_allocate(snap, PluginConf.default(), mode=1)
+
+
+def test_a_listed_pod_on_a_node_outside_the_session_fails_every_predicate():
+    """cache.Snapshot drops NotReady nodes (cache/cache.go:633-640) but the jobs keep their tasks: util.PodLister hands the pod to
+    InterPodAffinityMatches, CachedNodeInfo.GetNodeInfo does not find its node (plugins/util/util.go:93-100) and the error fails the
+    predicate for every (pod, node) pair (vendor/.../predicates.go:1381-1393) — no affinity term anywhere.  KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE."""
+    sb = cluster(3)
+    sb.add_pod(pod("lost", {"app": "db"}, node="gone-node", phase="Running", group="run"))
+    for i in range(3):
+        sb.add_pod(pod(f"p{i}", {"app": "web"}, creation=i))
+    snap = sb.flatten()
+    assert snap.flags & abi.KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE and snap.pod_affinity is None
+    o = both(snap, PluginConf.default(), actions=3)
+    assert (o.decisions["kind"] == abi.KB_KIND_NONE).all()
+    for mode in (0, 5):
+        e = util.emu_allocate(snap, PluginConf.default(), actions=3, mode=mode)
+        util.assert_same_decisions(o.decisions, e.decisions, f"mode {mode}")
+    # without the predicates plugin nobody calls InterPodAffinityMatches
+    o = both(snap, PluginConf.from_names([["gang", "priority"], ["drf", "nodeorder"]]), actions=3)
+    assert (o.decisions["kind"] == abi.KB_KIND_ALLOCATED).all()
