@@ -70,19 +70,41 @@ struct AffDev {
 // does a view (allocate: nodeorder as configured; backfill: off) read the counters for this class?
 KB_HD bool aff_reads(const ClassAff& ca, const bool nodeorder) { return ca.forbid != 0 || ca.need >= 0 || (ca.w_cnt != 0 && nodeorder); }
 
-// predicate step 10 for a pod of class `ca` on node n (the predicates plugin must be enabled; the caller checks)
+KB_HD uint32_t aff_lowest_bit(const uint64_t m) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__ffsll((long long)m) - 1u;
+#else
+  return (uint32_t)__builtin_ctzll(m);
+#endif
+}
+
+// predicate step 10 for a pod of class `ca` on node n (the predicates plugin must be enabled; the caller checks).
+// The counter reads of up to four groups are issued together: each is a chain node_domain -> cnt (an L2 round trip each), and a
+// lone thread only overlaps what it has in flight at once (ncu, r02h: a class forbidden by 35 groups cost 35 serial round trips).
 KB_HD bool aff_pred(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t n) {
   bool ok = true;
   uint64_t f = ca.forbid;
   while (f) {                                    // satisfiesExistingPodsAntiAffinity (:1400-1439) + the pod's own anti-affinity (:1526-1533)
+    int32_t d[4];
+    uint32_t off[4];
 #if defined(__CUDA_ARCH__)
-    const uint32_t g = (uint32_t)__ffsll((long long)f) - 1u;
-#else
-    const uint32_t g = (uint32_t)__builtin_ctzll(f);
+#pragma unroll
 #endif
-    f &= f - 1;
-    const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];
-    if (d >= 0 && KB_LDM(&A.cnt[A.group_off[g] + (uint32_t)d]) > 0) ok = false;
+    for (int k = 0; k < 4; ++k) {
+      d[k] = -1; off[k] = 0;
+      if (f) {
+        const uint32_t g = aff_lowest_bit(f);
+        f &= f - 1;
+        d[k] = A.node_domain[(size_t)A.group_keyset[g] * N + n];
+        off[k] = A.group_off[g];
+      }
+    }
+    int32_t v[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < 4; ++k) v[k] = d[k] >= 0 ? KB_LDM(&A.cnt[off[k] + (uint32_t)d[k]]) : 0;
+    ok = ok && ((v[0] | v[1] | v[2] | v[3]) <= 0);          // counters are never negative
   }
   if (ca.need >= 0) {                            // the pod's required affinity terms (:1516-1560)
     const uint32_t g = (uint32_t)ca.need;
@@ -95,11 +117,13 @@ KB_HD bool aff_pred(const AffDev& A, const ClassAff& ca, const uint32_t N, const
 }
 
 // priority pass 1, one FEASIBLE node m: the weight its pods contribute, added to the domain of the "pod's node" per key set.
-// `add(slot, value)` accumulates into dom_sum (atomicAdd on the device).
+// `add(slot, value)` accumulates into dom_sum (atomicAdd on the device).  (i0, stride): the device gives a node to a whole warp
+// and lane l the entries l, l + 32, ... — a class can weigh hundreds of pod kinds, and each test is an L2 read.
 template <class Add>
-KB_HD void aff_pass1_node(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t m, Add add) {
+KB_HD void aff_pass1_node(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t m, Add add,
+                          const uint32_t i0 = 0, const uint32_t stride = 1) {
   const int32_t fu = KB_LDM(A.first_unbound);
-  for (uint32_t i = ca.w_off; i < ca.w_off + ca.w_cnt; ++i) {
+  for (uint32_t i = ca.w_off + i0; i < ca.w_off + ca.w_cnt; i += stride) {
     const uint32_t e = (uint32_t)A.w_kind[i], ks = (uint32_t)A.w_keyset[i];
     const int32_t c = KB_LDM(&A.kind_count[(size_t)e * N + m]);
     if (!c) continue;
@@ -113,11 +137,7 @@ KB_HD long long aff_count_node(const AffDev& A, const ClassAff& ca, const uint32
   long long count = 0;
   uint64_t k = ca.w_keysets;
   while (k) {
-#if defined(__CUDA_ARCH__)
-    const uint32_t ks = (uint32_t)__ffsll((long long)k) - 1u;
-#else
-    const uint32_t ks = (uint32_t)__builtin_ctzll(k);
-#endif
+    const uint32_t ks = aff_lowest_bit(k);
     k &= k - 1;
     const int32_t d = A.node_domain[(size_t)ks * N + n];
     if (d >= 0) count += KB_LDM(&A.dom_sum[A.keyset_off[ks] + (uint32_t)d]);
@@ -141,11 +161,7 @@ KB_HD void aff_commit(const AffDev& A, const ClassAff& ca, const uint32_t N, con
   if (allocated) {
     uint64_t c = ca.contrib;
     while (c) {
-#if defined(__CUDA_ARCH__)
-      const uint32_t g = (uint32_t)__ffsll((long long)c) - 1u;
-#else
-      const uint32_t g = (uint32_t)__builtin_ctzll(c);
-#endif
+      const uint32_t g = aff_lowest_bit(c);
       c &= c - 1;
       A.total[g] = KB_LDM(&A.total[g]) + 1;
       const int32_t d = A.node_domain[(size_t)A.group_keyset[g] * N + n];

@@ -457,8 +457,9 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
         // list), then the visit with predicate step 10 / the score term in its scan
         if (e->dev.aff.has_weights) {
           const uint32_t ag = std::max(1u, std::min((e->N + AFF_THREADS - 1) / AFF_THREADS, (uint32_t)e->sm_count * 4u));
+          const uint32_t ag1 = std::max(1u, std::min((e->N + AFF_THREADS / 32 - 1) / (AFF_THREADS / 32), (uint32_t)e->sm_count * 8u));   // pass 1: a warp per node
           aff_prepass_kernel<0><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
-          aff_prepass_kernel<1><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
+          aff_prepass_kernel<1><<<ag1, AFF_THREADS, 0, e->stream>>>(e->dev);
           aff_prepass_kernel<2><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
         }
         ok = launch_visit(visit_kernel<0, 1>, e->scan_grid, e->visit_smem, e->stream, e->dev, pdl) == cudaSuccess;
@@ -557,8 +558,9 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
           else {
             if (D.aff.has_weights) {
               const uint32_t ag = std::max(1u, std::min((e->N + AFF_THREADS - 1) / AFF_THREADS, (uint32_t)e->sm_count * 4u));
+              const uint32_t ag1 = std::max(1u, std::min((e->N + AFF_THREADS / 32 - 1) / (AFF_THREADS / 32), (uint32_t)e->sm_count * 8u));
               aff_prepass_kernel<0><<<ag, AFF_THREADS, 0, e->stream>>>(D);
-              aff_prepass_kernel<1><<<ag, AFF_THREADS, 0, e->stream>>>(D);
+              aff_prepass_kernel<1><<<ag1, AFF_THREADS, 0, e->stream>>>(D);
               aff_prepass_kernel<2><<<ag, AFF_THREADS, 0, e->stream>>>(D);
               launches += 3;
             }

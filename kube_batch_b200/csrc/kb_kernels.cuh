@@ -825,15 +825,24 @@ aff_prepass_kernel(const __grid_constant__ DevSession S) {
   __syncthreads();
   const size_t tile_u64 = (size_t)S.ncols * TILE_NODES;
   long long mn = 0, mx = 0;
-  for (uint32_t n = gtid; n < S.N; n += nthr) {
+  auto feasible = [&](const uint32_t n) {
     TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, S.cf.R, S.cf.W};
     uint64_t key = eval_pair(S.cf, scls, acc, n, nullptr);
     if (key && S.cf.predicates && !aff_pred(S.aff, sca, S.N, n)) key = 0;
-    if (!key) continue;
-    if (PHASE == 1) {
+    return key != 0;
+  };
+  if (PHASE == 1) {
+    // one WARP per node: lane 0 decides feasibility, then the lanes share the class's weight list
+    const uint32_t lane = threadIdx.x & 31u, gw = gtid >> 5, nw = nthr >> 5;
+    for (uint32_t n = gw; n < S.N; n += nw) {
+      const bool ok = __shfl_sync(0xFFFFFFFFu, (lane == 0 && feasible(n)) ? 1 : 0, 0) != 0;
+      if (!ok) continue;
       aff_pass1_node(S.aff, sca, S.N, n, [&](uint32_t slot, long long v) {
-        atomicAdd(reinterpret_cast<unsigned long long*>(&S.aff.dom_sum[slot]), (unsigned long long)v); });
-    } else {
+        atomicAdd(reinterpret_cast<unsigned long long*>(&S.aff.dom_sum[slot]), (unsigned long long)v); }, lane, 32u);
+    }
+  } else {
+    for (uint32_t n = gtid; n < S.N; n += nthr) {
+      if (!feasible(n)) continue;
       const long long cnt = aff_count_node(S.aff, sca, S.N, n);
       mn = cnt < mn ? cnt : mn; mx = cnt > mx ? cnt : mx;
     }
