@@ -15,7 +15,8 @@
 //   first_unbound              lowest node index holding a pod with an empty Spec.NodeName — every pod placed in the session
 // A placement can change the feasibility / score of EVERY node of a topology domain, so the "one node column changes per
 // placement" rule behind the candidate lists does not hold for a class whose keys read these counters: such a
-// class (ClassAff.reads) gets a fresh scan per task — the replay stops after one placement.
+// class (aff_stop_each) gets a fresh scan per task — the replay stops after one placement.  Exception: a class whose own
+// placements only touch single-node domains (one replica per host) keeps its multi-task runs (ClassAff.pred_multi_ok).
 #ifndef KB_AFF_H_
 #define KB_AFF_H_
 
@@ -39,8 +40,11 @@ struct ClassAff {
   int32_t  need;          // group the required pod-affinity terms need, -1 none
   int32_t  kind;          // kind of the placed pod, -1 none
   uint32_t w_off, w_cnt;  // weight list (AffDev.w_*)
-  uint32_t self_match;    // KB_TASK_AFF_SELF_MATCH
-  uint32_t reads;         // forbid | need | weights: this class's keys depend on the counters
+  uint16_t self_match;    // KB_TASK_AFF_SELF_MATCH
+  uint16_t self_block;    // a placement of this class makes the chosen node infeasible for the class itself (one replica per host)
+  uint32_t pred_multi_ok; // the predicate part of the class survives its OWN placements: the only counters it both joins and reads
+                          // belong to key sets whose domains are single nodes (kubernetes.io/hostname), so a placement changes
+                          // nothing but the chosen node — the candidate list stays exact and a run may place several tasks
 };
 
 struct AffDev {
@@ -67,8 +71,13 @@ struct AffDev {
   long long* minmax;              // [2] min / max count over the feasible nodes (pass 2)
 };
 
-// does a view (allocate: nodeorder as configured; backfill: off) read the counters for this class?
-KB_HD bool aff_reads(const ClassAff& ca, const bool nodeorder) { return ca.forbid != 0 || ca.need >= 0 || (ca.w_cnt != 0 && nodeorder); }
+// Must the replay stop after ONE placement of this class (fresh scan per task)?  Yes when its keys read counters that its own
+// placement changes beyond the chosen node: a weight list (allocate view: nodeorder on), or predicate groups over multi-node domains.
+KB_HD bool aff_stop_each(const ClassAff& ca, const bool nodeorder) {
+  if (ca.w_cnt != 0 && nodeorder) return true;
+  if (ca.forbid == 0 && ca.need < 0) return false;
+  return ca.pred_multi_ok == 0;
+}
 
 KB_HD uint32_t aff_lowest_bit(const uint64_t m) {
 #if defined(__CUDA_ARCH__)
@@ -114,6 +123,18 @@ KB_HD bool aff_pred(const AffDev& A, const ClassAff& ca, const uint32_t N, const
     ok = ok && (match || first_of_series);
   }
   return ok;
+}
+
+// ClassAff.self_block: does an ALLOCATED pod of the class forbid node n for the next pod of the class?  Only through a group it both
+// joins and is forbidden by, and only if the node has a domain under the group's key set (a node without the label is never matched).
+KB_HD bool aff_self_blocks(const AffDev& A, const ClassAff& ca, const uint32_t N, const uint32_t n) {
+  uint64_t m = ca.self_block ? (ca.contrib & ca.forbid) : 0ull;
+  while (m) {
+    const uint32_t g = aff_lowest_bit(m);
+    m &= m - 1;
+    if (A.node_domain[(size_t)A.group_keyset[g] * N + n] >= 0) return true;
+  }
+  return false;
 }
 
 // priority pass 1, one FEASIBLE node m: the weight its pods contribute, added to the domain of the "pod's node" per key set.

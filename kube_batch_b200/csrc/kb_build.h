@@ -386,7 +386,6 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
           aff_wk.push_back(pa->weight_kind[i]); aff_wks.push_back(pa->weight_keyset[i]); aff_wv.push_back(pa->weight_value[i]);
           ca.w_keysets |= 1ull << pa->weight_keyset[i];
         }
-        ca.reads = (ca.forbid != 0 || ca.need >= 0 || ca.w_cnt > 0) ? 1u : 0u;
         it = ids.emplace(key, (uint32_t)aff_tab.size()).first;
         aff_tab.push_back(ca);
       }
@@ -713,12 +712,29 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     memcpy(ib + oi.aff_keyset_off, aff_keyset_off.data(), aff_keyset_off.size() * 4);
     if (pa->n_groups) memcpy(ib + oi.aff_group_keyset, pa->group_keyset, (size_t)pa->n_groups * 4);
     memcpy(ib + oi.aff_group_off, aff_group_off.data(), aff_group_off.size() * 4);
+    std::vector<uint8_t> keyset_single(std::max(1u, pa->n_keysets), 1);      // every domain of the key set is ONE node
+    for (uint32_t k = 0; k < pa->n_keysets; ++k) {
+      std::vector<uint32_t> size(std::max(1u, pa->keyset_domains[k]), 0);
+      for (uint32_t n = 0; n < N; ++n) { const int32_t d = pa->node_domain[(size_t)k * N + n]; if (d >= 0 && ++size[d] > 1) keyset_single[k] = 0; }
+    }
     ClassAff* hca = (ClassAff*)(ib + oi.aff_cls);
     for (uint32_t k = 0; k < C; ++k) {
       const uint32_t id = classes[k].flags >> 8;
       if (id < aff_tab.size()) hca[k] = aff_tab[id]; else { memset(&hca[k], 0, sizeof(ClassAff)); hca[k].need = -1; hca[k].kind = -1; }
-      if (!B.aff.has_weights) { hca[k].w_cnt = 0; hca[k].w_keysets = 0; hca[k].reads = (hca[k].forbid != 0 || hca[k].need >= 0) ? 1u : 0u; }
-      if (!hc.cf.predicates) { hca[k].forbid = 0; hca[k].need = -1; hca[k].reads = hca[k].w_cnt ? 1u : 0u; }      // step 10 belongs to the predicates plugin
+      if (!B.aff.has_weights) { hca[k].w_cnt = 0; hca[k].w_keysets = 0; }
+      if (!hc.cf.predicates) { hca[k].forbid = 0; hca[k].need = -1; }      // step 10 belongs to the predicates plugin
+      // groups the class both joins and reads: if all of them live on single-node domains (and the needed group is not among
+      // them: its `total` would end the first-of-series escape for every node), its own placements only change the chosen node
+      const uint64_t needbit = hca[k].need >= 0 ? (1ull << hca[k].need) : 0ull;
+      uint64_t m = hca[k].contrib & (hca[k].forbid | needbit);
+      bool multi = (hca[k].contrib & needbit) == 0;
+      while (m && multi) {
+        const uint32_t g = (uint32_t)__builtin_ctzll(m);
+        m &= m - 1;
+        multi = keyset_single[pa->group_keyset[g]] != 0;
+      }
+      hca[k].pred_multi_ok = multi ? 1u : 0u;
+      hca[k].self_block = (multi && (hca[k].contrib & hca[k].forbid) != 0) ? 1 : 0;
     }
     if (!aff_wk.empty()) {
       memcpy(ib + oi.aff_w_kind, aff_wk.data(), aff_wk.size() * 4); memcpy(ib + oi.aff_w_keyset, aff_wks.data(), aff_wks.size() * 4);

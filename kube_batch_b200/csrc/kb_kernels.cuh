@@ -230,6 +230,8 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       for (uint32_t w = 0; w < W; ++w) dst[col_ports(R, W, w)][lane] = src[col_ports(R, W, w)][lane] | sm.cls.port_own[w];
       ColAcc acc{&dst[0][0], (uint32_t)lane, 32u, R, W};
       next_key = eval_pair(S.cf, sm.cls, acc, my_node, &next_fi);
+      if (AFF && cur_fi && aff_self_blocks(S.aff, sm.cls_aff, S.N, my_node)) next_key = 0;   // one replica per host: the class's own pod, once ALLOCATED (a Pipelined
+                                                                  // pod is not listed by util.PodLister), forbids the node (kb_aff.h)
       next_valid = true;
     }
     if (lane == 0) c.pairs_replayed += (unsigned long long)__popc(todo);
@@ -239,9 +241,9 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   const long long t_merge = clock64();
 
   uint32_t my_cnt = 0;        // placements on MY candidate (NodeInfo.Used delta = my_cnt x Resreq, applied at write-back)
-  // inter-pod affinity (kb_aff.h): a class whose keys read the counters uses its list for ONE placement — the placement can
-  // change the feasibility / score of every node of a topology domain
-  const bool aff_rd = AFF && aff_reads(sm.cls_aff, S.cf.nodeorder != 0);
+  // inter-pod affinity (kb_aff.h): a class whose keys read counters that its own placement changes beyond the chosen node uses
+  // its list for ONE placement — the placement can change the feasibility / score of every node of a topology domain
+  const bool aff_rd = AFF && aff_stop_each(sm.cls_aff, S.cf.nodeorder != 0);
   bool aff_stop = false;
   for (;;) {              // runs
     if (c.done || c.cur_class != cls_id || (AFF && aff_stop)) break;

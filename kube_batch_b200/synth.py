@@ -264,6 +264,38 @@ def make(name: str, replica: int = 0) -> Tuple[Snapshot, PluginConf]:
     return generate(spec), (spec.conf or config_conf(name))
 
 
+def add_host_spread(s: Snapshot, frac: float = 0.1, labels: int = 8, seed: int = 7) -> Snapshot:
+    """Gives `frac` of the PodGroups the most common inter-pod constraint — "one replica per host": every pod of the group carries the
+    label app=<L> (L = one of `labels` values) and a required anti-affinity term {app=<L>, topologyKey kubernetes.io/hostname}.  Fills
+    kb_pod_affinity (include/kbgpu.h) exactly as builder.flatten_pod_affinity would for such pods: per label one counter group for
+    the term the pods OWN (satisfiesExistingPodsAntiAffinity) and one for the pods that MATCH the term list (the pod's own check) —
+    same members, both forbidden to and joined by the label's pods; one key set (hostname: a domain per node); no pod kinds (required
+    anti-affinity terms carry no priority weight).  Pods already running carry no labels here."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    T, N, J = s.T, s.N, s.J
+    forbid = np.zeros(max(T, 1), dtype=np.uint64)
+    for j in range(J):
+        lo, hi = int(s.job_task_off[j]), int(s.job_task_off[j + 1])
+        if hi > lo and rng.random() < frac:
+            lab = int(rng.integers(0, labels))
+            forbid[lo:hi] = np.uint64(3 << (2 * lab))
+            s.task_flags[lo:hi] |= abi.KB_TASK_HAS_POD_AFFINITY
+    G = 2 * labels
+    s.pod_affinity = {
+        "n_keysets": 1, "n_groups": G, "n_kinds": 0, "n_weights": 0, "first_unbound_node": -1,
+        "node_domain": np.arange(max(N, 1), dtype=np.int32).reshape(1, -1), "keyset_domains": np.array([N], dtype=np.uint32),
+        "group_keyset": np.zeros(G, dtype=np.uint32), "group_count0": np.zeros(max(1, G * N), dtype=np.int32),
+        "group_total0": np.zeros(G, dtype=np.int32), "task_forbid": forbid, "task_need": np.full(max(T, 1), -1, dtype=np.int32),
+        "task_contrib": forbid.copy(), "task_kind": np.full(max(T, 1), -1, dtype=np.int32),
+        "node_kind_count0": np.zeros((1, max(N, 1)), dtype=np.int32), "kind_unbound": np.zeros(1, dtype=np.uint8),
+        "task_weight_off": np.zeros(T + 1, dtype=np.uint32), "weight_kind": np.zeros(1, dtype=np.int32),
+        "weight_keyset": np.zeros(1, dtype=np.int32), "weight_value": np.zeros(1, dtype=np.int64),
+    }
+    s.meta["spread_tasks"] = int((forbid != 0).sum())
+    s.invalidate()
+    return s
+
+
 # ------------------------------------------------------------------------------------------------
 # small randomised sessions for property / parity tests: every feature of the path at once
 # ------------------------------------------------------------------------------------------------

@@ -148,7 +148,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   const ClassAff* ca = S.aff.on ? &S.aff.cls[cls_id] : nullptr;
-  const bool ca_reads = ca && aff_reads(*ca, S.cf.nodeorder != 0);
+  const bool ca_reads = ca && aff_stop_each(*ca, S.cf.nodeorder != 0);
   bool aff_stale = false;       // a placement of a class whose keys read the inter-pod counters: the list is used once
   auto refresh = [&]() {
     for (auto& cd : cand) {
@@ -165,6 +165,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       SlotAcc acc{&dst, R, W};
       bool f = false;
       cd.next_key = add_pref_term(eval_pair(S.cf, cls, acc, cd.node, &f), pc, cd.pref);
+      if (ca && cd.cur_fi && aff_self_blocks(S.aff, *ca, S.N, cd.node)) cd.next_key = 0;       // one replica per host: the class's own pod, once ALLOCATED, forbids the node
       cd.next_fi = f; cd.next_valid = true;
       c.pairs_replayed += 1;
     }

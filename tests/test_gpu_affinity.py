@@ -137,3 +137,31 @@ def test_big_affinity_session_matches_the_emulation_and_is_timed(eng):
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         json.dump(rec, open(os.path.join(out, "affinity_big_session.json"), "w"))
+
+
+@pytest.mark.parametrize("name", ["c2", "c3"])
+def test_one_replica_per_host_at_baseline_size(eng, name):
+    """BASELINE configs 2 / 3 with a tenth of the PodGroups under "one replica per host" (required anti-affinity on
+    kubernetes.io/hostname against their own label, synth.add_host_spread).  Their own placements only touch single-node domains, so
+    the replay keeps multi-task runs (ClassAff.pred_multi_ok).  Engine vs the emulation (the object-level oracle is O(pods) per pair)."""
+    import json, os
+    from kube_batch_b200 import synth
+    s, conf = synth.make(name)
+    synth.add_host_spread(s, 0.1)
+    e = util.emu_allocate(s, conf, mode=1)
+    eng.load(s, conf)
+    eng.allocate()
+    r = eng.allocate()
+    util.assert_same_decisions(e.decisions, r.decisions, f"{name} + host spread vs emulation")
+    d = r.decisions
+    fb = s.pod_affinity["task_forbid"][:s.T]
+    for lab in range(8):
+        nodes = d["node"][(fb == np.uint64(3 << (2 * lab))) & (d["kind"] == abi.KB_KIND_ALLOCATED)]
+        assert len(nodes) == len(set(nodes.tolist())), "two replicas of one label on a host"
+    st = r.stats
+    rec = {"workload": name, "spread_tasks": int(s.meta["spread_tasks"]), "gpu_ms": float(st.gpu_ms), "kernel_launches": int(st.kernel_launches),
+           "allocated": int(st.tasks_allocated), "pairs_logical": int(st.pairs_logical), "pairs_per_s": float(st.pairs_logical) / (st.gpu_ms * 1e-3)}
+    print("host spread timing:", json.dumps(rec))
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        json.dump(rec, open(os.path.join(out, f"affinity_host_spread_{name}.json"), "w"))

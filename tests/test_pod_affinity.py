@@ -276,3 +276,25 @@ def test_a_listed_pod_on_a_node_outside_the_session_fails_every_predicate():
     # without the predicates plugin nobody calls InterPodAffinityMatches
     o = both(snap, PluginConf.from_names([["gang", "priority"], ["drf", "nodeorder"]]), actions=3)
     assert (o.decisions["kind"] == abi.KB_KIND_ALLOCATED).all()
+
+
+def test_synthetic_host_spread_tables_are_what_the_flattener_produces():
+    """synth.add_host_spread writes kb_pod_affinity directly (BASELINE-size sessions are not built from objects): same structure as
+    builder.flatten_pod_affinity gives for pods that carry {app=L} + required anti-affinity {app=L, hostname}."""
+    from kube_batch_b200 import synth
+    sb = cluster(4)
+    for i in range(3):
+        p = pod(f"p{i}", {"app": "web"}, creation=i)
+        p.pod_anti_affinity = B.PodAffinity(required=[term(HOST, app="web")])
+        sb.add_pod(p)
+    a = sb.flatten().pod_affinity
+    s, _ = synth.make("c1")
+    b = synth.add_host_spread(s, frac=1.0, labels=1).pod_affinity
+    assert (a["n_groups"], a["n_keysets"], a["n_kinds"]) == (b["n_groups"], b["n_keysets"], b["n_kinds"]) == (2, 1, 0)
+    assert a["task_forbid"].tolist() == [3, 3, 3] and set(b["task_forbid"][: s.T].tolist()) == {3}
+    assert a["task_contrib"].tolist() == [3, 3, 3] and np.array_equal(b["task_contrib"], b["task_forbid"])
+    assert a["node_domain"].tolist() == [[0, 1, 2, 3]] and b["node_domain"].tolist() == [list(range(s.N))]
+    e = util.emu_allocate(s, PluginConf.default(), mode=1)
+    d = e.decisions
+    placed = d["node"][d["kind"] == abi.KB_KIND_ALLOCATED]
+    assert len(placed) == len(set(placed.tolist())) > 0
