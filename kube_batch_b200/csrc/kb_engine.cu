@@ -889,7 +889,10 @@ int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t
   CUDA_TRY(e, cudaSetDevice(e->device));
   uint8_t* d_fit = nullptr; double* d_score = nullptr;
   if (fit) CUDA_TRY(e, cudaMalloc(&d_fit, n));
-  if (score) CUDA_TRY(e, cudaMalloc(&d_score, n * 8));
+  if (score) {
+    const cudaError_t ca = cudaMalloc(&d_score, n * 8);
+    if (ca != cudaSuccess) { if (d_fit) cudaFree(d_fit); return fail(e, KB_E_CUDA, "cudaMalloc(score) failed: %s", cudaGetErrorString(ca)); }   // no leak of d_fit
+  }
   dim3 grid(e->NT, (task_hi - task_lo + MATRIX_TASKS_PER_CTA - 1) / MATRIX_TASKS_PER_CTA);
   cudaEventRecord(e->ev0, e->stream);
   matrix_kernel<<<grid, MATRIX_THREADS, e->tile_smem, e->stream>>>(e->dev, e->d_task_class, task_lo, task_hi, d_fit, d_score);
