@@ -235,6 +235,8 @@ struct BuiltSession {
   std::vector<ClassPref> class_pref; // [C] preferred node-affinity terms per class — HOST ONLY (read by tests/emu's prototype of
   bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
   AffDev aff{};                      // inter-pod (anti)affinity: sizes and flags (pointers are set by bind())
+  bool aff_session = false;          // the snapshot carries kb_pod_affinity (counter path OR atoms): reclaim / preempt are refused
+  uint64_t aff_atom_mask[KB_MAX_W] = {0};   // port-word bits that encode host-level anti-affinity groups (hidden from kb_node_state)
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
   std::vector<uint32_t> q_alloc_present;   // [Q] scalar presence of proportion's queueAttr.allocated at session open (kb_evict.h: Resource.Less)
 
@@ -313,13 +315,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   if ((s->flags & KB_SNAPSHOT_PLACED_POD_AFFINITY) && !pa)
     return bfail(e, KB_E_UNSUPPORTED_FEATURE, "a placed pod carries inter-pod (anti)affinity terms: the reference lets it reject nodes for other pods "
                  "(predicates.go:1261-1288); the flattener must hand over kb_snapshot.pod_affinity (no CPU fallback)");
-  if (pa) {
-    // the counters of a topology domain change the keys of many nodes at once: per-visit kernels, fresh scan per task for the
-    // classes that read them (kb_aff.h); no look-ahead lists, no overlap, no node sharding
-    if (pa->n_groups > KB_MAX_AFF_GROUPS || pa->n_keysets > 64) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "kb_pod_affinity: more than 64 counter groups / key sets");
-    if (world > 1) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "inter-pod affinity: not with a sharded node axis (KB_ENGINE_SHARD)");
-    pipe_mode = 0; overlap_mode = 0; kchain = 1;
-  }
+  if (pa && (pa->n_groups > KB_MAX_AFF_GROUPS || pa->n_keysets > 64))
+    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "kb_pod_affinity: more than 64 counter groups / key sets");
   if (s->flags & ~(KB_SNAPSHOT_PLACED_POD_AFFINITY | KB_SNAPSHOT_LISTED_POD_WITHOUT_NODE)) return bfail(e, KB_E_BADARG, "unknown kb_snapshot.flags bits 0x%x", s->flags);
   if (s->R < 2 || s->R > KB_MAX_R || s->W < 1 || s->W > KB_MAX_W) return bfail(e, KB_E_BADARG, "R=%u / W=%u out of range", s->R, s->W);
   if (s->Q > KB_MAX_Q) return bfail(e, KB_E_BADARG, "Q=%u > KB_MAX_Q", s->Q);
@@ -329,6 +326,84 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   HostConf& hc = B.hc;
   int rc = resolve_conf(e, conf, R, W, hc);
   if (rc) return rc;
+  B.aff_session = pa != nullptr;
+  for (uint32_t w = 0; w < KB_MAX_W; ++w) B.aff_atom_mask[w] = 0;
+  // Host-level inter-pod anti-affinity as ATOMS.  When every counter the session's tasks read or join lives on a key set whose
+  // domains are exactly the nodes (kubernetes.io/hostname), "a member of group g sits in the node's domain" is a per-node bit,
+  // set by an Allocate of a contributing task and tested like a host-port conflict (predicates.go:1153-1173 has the same shape):
+  // group g becomes a spare bit of the port words, ClassRec.port_conflict gets the forbidden groups, ClassRec.aff_own the joined
+  // ones (applied by Allocate only: a Pipelined pod is not listed by util.PodLister).  The placement then changes ONE node record
+  // again, every invariant of the candidate lists holds and the session runs on the persistent pipeline at full
+  // speed.  Not convertible (-> per-visit kernels with counters, kb_aff.h): required pod AFFINITY, live priority weights, multi-node
+  // domains, nodes without the topology label, no spare bits.  KB_AFF_ATOMS=0 forces the counter path.
+  std::vector<int32_t> aff_atom_of_group;               // group -> atom index, -1
+  std::vector<uint64_t> node_aff_bits;                  // [W][N] initial member bits
+  std::vector<uint32_t> aff_group_off0;
+  bool aff_as_atoms = false;
+  if (pa) {
+    aff_group_off0.assign(pa->n_groups + 1, 0);
+    for (uint32_t g = 0; g < pa->n_groups; ++g) {
+      if (pa->group_keyset[g] >= pa->n_keysets) return bfail(e, KB_E_BADARG, "kb_pod_affinity: group %u names a key set out of range", g);
+      aff_group_off0[g + 1] = aff_group_off0[g] + pa->keyset_domains[pa->group_keyset[g]];
+    }
+    const char* sw = getenv("KB_AFF_ATOMS");
+    bool ok = !(sw && atoi(sw) == 0);
+    const bool weights_live = hc.cf.nodeorder && hc.w_podaff != 0;
+    uint64_t used = 0;
+    for (uint32_t t = 0; t < T && ok; ++t) {
+      if (hc.cf.predicates && pa->task_need[t] >= 0) ok = false;
+      if (weights_live && pa->task_weight_off[t + 1] > pa->task_weight_off[t]) ok = false;
+      used |= pa->task_contrib[t] | pa->task_forbid[t];
+    }
+    if (!hc.cf.predicates) used = 0;                    // step 10 is not evaluated: nothing reads the counters
+    if (pa->n_groups < 64 && (used >> pa->n_groups)) return bfail(e, KB_E_BADARG, "kb_pod_affinity: a task names a group out of range");
+    for (uint32_t g = 0; g < pa->n_groups && ok; ++g) {
+      if (!((used >> g) & 1ull)) continue;
+      const uint32_t ks = pa->group_keyset[g];
+      if (pa->keyset_domains[ks] != N) { ok = false; break; }
+      std::vector<uint8_t> seen(N, 0);
+      for (uint32_t n = 0; n < N; ++n) {
+        const int32_t d = pa->node_domain[(size_t)ks * N + n];
+        if (d < 0 || d >= (int32_t)N || seen[d]) { ok = false; break; }
+        seen[d] = 1;
+      }
+    }
+    int hb = -1;                                        // highest port atom in use
+    if (ok && used) {
+      for (uint32_t w = 0; w < W; ++w) {
+        uint64_t acc = 0;
+        for (uint32_t n = 0; n < N; ++n) acc |= s->node_ports[(size_t)w * N + n];
+        for (uint32_t t = 0; t < T; ++t) acc |= s->task_port_own[(size_t)w * T + t] | s->task_port_conflict[(size_t)w * T + t];
+        if (acc) hb = (int)(w * 64 + 63 - (uint32_t)__builtin_clzll(acc));
+      }
+      if ((uint32_t)(hb + 1) + (uint32_t)__builtin_popcountll(used) > 64u * W) ok = false;
+    }
+    if (ok) {
+      aff_as_atoms = true;
+      aff_atom_of_group.assign(pa->n_groups, -1);
+      node_aff_bits.assign((size_t)W * std::max(1u, N), 0);
+      int next = hb + 1;
+      for (uint32_t g = 0; g < pa->n_groups; ++g) {
+        if (!((used >> g) & 1ull)) continue;
+        const int a = next++;
+        aff_atom_of_group[g] = a;
+        B.aff_atom_mask[a / 64] |= 1ull << (a % 64);
+        const uint32_t ks = pa->group_keyset[g];
+        for (uint32_t n = 0; n < N; ++n)
+          if (pa->group_count0[aff_group_off0[g] + (uint32_t)pa->node_domain[(size_t)ks * N + n]] > 0) node_aff_bits[(size_t)(a / 64) * N + n] |= 1ull << (a % 64);
+      }
+    } else {
+      // the counters of a topology domain change the keys of many nodes at once: per-visit kernels, fresh scan per task for
+      // the classes that read them (kb_aff.h); no look-ahead lists, no overlap, no node sharding
+      if (world > 1) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "inter-pod affinity beyond host-level anti-affinity: not with a sharded node axis (KB_ENGINE_SHARD)");
+      pipe_mode = 0; overlap_mode = 0; kchain = 1;
+    }
+  }
+  const kb_pod_affinity* pa_full = pa;                  // the snapshot's tables (class identity below)
+  if (aff_as_atoms) pa = nullptr;                       // from here on `pa` = what the counter path (AffDev) consumes
+  auto atoms_of = [&](uint64_t groups, uint64_t* out) {
+    while (groups) { const uint32_t g = (uint32_t)__builtin_ctzll(groups); groups &= groups - 1; const int a = aff_atom_of_group[g]; if (a >= 0) out[a / 64] |= 1ull << (a % 64); }
+  };
 
   // ---------------- validate + task classes ----------------
   for (uint32_t j = 0; j < J; ++j) {
@@ -413,6 +488,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     auto bits = [](const double* a, size_t i) { uint64_t u; memcpy(&u, a + i, 8); return u; };
     auto same_as_prev = [&](uint32_t t) {
       if (pa && aff_id[t] != aff_id[t - 1]) return false;
+      if (aff_as_atoms && (pa_full->task_forbid[t] != pa_full->task_forbid[t - 1] || pa_full->task_contrib[t] != pa_full->task_contrib[t - 1])) return false;
       if (s->task_flags[t] != s->task_flags[t - 1] || s->task_n_aff_terms[t] != s->task_n_aff_terms[t - 1] ||
           s->task_nz_cpu[t] != s->task_nz_cpu[t - 1] || s->task_nz_mem[t] != s->task_nz_mem[t - 1]) return false;
       if (s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) {
@@ -440,7 +516,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         task_class[t] = prev_class; task_empty[t] = task_empty[t - 1];
         continue;
       }
-      if ((s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY) && !pa)
+      if ((s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY) && !pa_full)
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod affinity terms but the snapshot has no kb_pod_affinity (no CPU fallback)", t);
       if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && pa)
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u: preferred node-affinity terms in a session with inter-pod affinity (per-visit kernels do not evaluate NodeAffinityPriority)", t);
@@ -468,6 +544,10 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         c.port_own[w] = s->task_port_own[(size_t)w * T + t];
         c.port_conflict[w] = s->task_port_conflict[(size_t)w * T + t];
         for (uint32_t a = 0; a < c.n_aff; ++a) c.aff[a][w] = s->task_aff_terms[((size_t)a * W + w) * T + t];
+      }
+      if (aff_as_atoms) {                 // host-level anti-affinity as atoms: forbidden groups conflict, joined groups are set by Allocate
+        if (hc.cf.predicates) atoms_of(pa_full->task_forbid[t], c.port_conflict);
+        atoms_of(pa_full->task_contrib[t], c.aff_own);
       }
       task_empty[t] = res_is_empty(R, [&](uint32_t k) { return c.resreq[k]; }) ? 1 : 0;   // allocate.go:113-118
       if (prev_class != 0xFFFFFFFFu && memcmp(&classes[prev_class], &c, sizeof c) == 0 && memcmp(&class_pref[prev_class], &cp, sizeof cp) == 0) {
@@ -694,7 +774,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         for (uint32_t w = 0; w < W; ++w) {
           put(col_labels(R, W, w), s->node_labels[(size_t)w * N + n]);
           put(col_taints(R, W, w), s->node_taints[(size_t)w * N + n]);
-          put(col_ports(R, W, w), s->node_ports[(size_t)w * N + n]);
+          put(col_ports(R, W, w), s->node_ports[(size_t)w * N + n] | (aff_as_atoms ? node_aff_bits[(size_t)w * N + n] : 0ull));
         }
       } else {                                   // padding node: can never fit (kernels also test node < N)
         for (uint32_t r = 0; r < R; ++r) { put(col_idle(R, r), double_as_u64(-1e300)); put(col_rel(R, r), double_as_u64(-1e300)); }

@@ -89,6 +89,8 @@ struct ClassRec {
   uint64_t tol[KB_MAX_W];
   uint64_t port_own[KB_MAX_W];
   uint64_t port_conflict[KB_MAX_W];
+  uint64_t aff_own[KB_MAX_W];     // bits an ALLOCATE placement (not a Pipeline) adds to the node's port words: host-level inter-pod
+                                  // anti-affinity encoded as atoms (kb_build.h affinity_as_atoms); all zero otherwise
   uint32_t n_aff;
   uint32_t flags;             // KB_TASK_BEST_EFFORT_QOS only
 };

@@ -357,9 +357,10 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
   // inter-pod affinity (kb_pod_affinity): per-visit kernels on the full table; with world > 1 every rank runs the whole cycle
   // (replicated) unless KB_ENGINE_SHARD asks for the sharded path, which such sessions refuse
   const bool aff_session = s && s->pod_affinity != nullptr;
-  const bool pipe_try = (e->pipe_req && e->coop_ok && (e->world == 1 || !e->shard_req)) || (aff_session && !e->shard_req);
+  const bool pipe_ok = e->pipe_req && e->coop_ok;
+  const bool pipe_try = (pipe_ok && (e->world == 1 || !e->shard_req)) || (aff_session && !e->shard_req);      // = the full table on this rank
   int rc_build = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, pipe_try ? 0u : (uint32_t)e->rank,
-                               pipe_try ? 1u : (uint32_t)e->world, e->overlap_mode, kchain, false, pipe_try ? 1 : 0);
+                               pipe_try ? 1u : (uint32_t)e->world, e->overlap_mode, kchain, false, (pipe_try && pipe_ok) ? 1 : 0);
   if (rc_build == KB_OK && pipe_try && !B.pipe && e->world > 1 && !aff_session)       // geometry outside the pipeline: fall back to the sharded path
     rc_build = build_session(s, conf, (uint32_t)std::max(1, e->sm_count), B, &be, (uint32_t)e->rank, (uint32_t)e->world, e->overlap_mode, kchain);
   if (rc_build) return fail(e, rc_build, "%s", be.msg.c_str());
@@ -682,7 +683,7 @@ int kb_session_load_running(kb_engine* e, const kb_snapshot* s, const kb_running
     return fail(e, KB_E_BADARG, "kb_session_load_running: `snap` is not the snapshot of the loaded session");
   if (e->world > 1 && !e->replicated) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt run on the full node table: not with KB_ENGINE_SHARD");
   if (e->built.has_pref) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt with preferred node affinity are outside this build");
-  if (e->built.aff.on) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt in a session with inter-pod affinity are outside this build (the victim walk does not update the affinity counters)");
+  if (e->built.aff_session) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt in a session with inter-pod affinity are outside this build (the victim walk does not update the affinity counters / member bits)");
   CUDA_TRY(e, cudaSetDevice(e->device));
   e->running_loaded = false;
   BuildErr be;
@@ -963,7 +964,7 @@ int kb_node_state(kb_engine* e, double* idle, double* releasing, double* used, i
     if (pods) pods[n] = a.pods();
     if (nz_cpu) nz_cpu[n] = a.nz_cpu();
     if (nz_mem) nz_mem[n] = a.nz_mem();
-    if (ports) for (uint32_t w = 0; w < W; ++w) ports[(size_t)w * N + n] = a.ports(w);
+    if (ports) for (uint32_t w = 0; w < W; ++w) ports[(size_t)w * N + n] = a.ports(w) & ~e->built.aff_atom_mask[w];      // host-level anti-affinity bits are not ports
   }
   return KB_OK;
 }

@@ -227,7 +227,7 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
       dst[col_nz_cpu(R)][lane] = (uint64_t)((int64_t)src[col_nz_cpu(R)][lane] + sm.cls.nz_cpu);
       dst[col_nz_mem(R)][lane] = (uint64_t)((int64_t)src[col_nz_mem(R)][lane] + sm.cls.nz_mem);
       dst[col_pods(R)][lane] = src[col_pods(R)][lane] + 1ull;          // pods live in the low 32 bits
-      for (uint32_t w = 0; w < W; ++w) dst[col_ports(R, W, w)][lane] = src[col_ports(R, W, w)][lane] | sm.cls.port_own[w];
+      for (uint32_t w = 0; w < W; ++w) dst[col_ports(R, W, w)][lane] = src[col_ports(R, W, w)][lane] | sm.cls.port_own[w] | (cur_fi ? sm.cls.aff_own[w] : 0ull);
       ColAcc acc{&dst[0][0], (uint32_t)lane, 32u, R, W};
       next_key = eval_pair(S.cf, sm.cls, acc, my_node, &next_fi);
       if (AFF && cur_fi && aff_self_blocks(S.aff, sm.cls_aff, S.N, my_node)) next_key = 0;   // one replica per host: the class's own pod, once ALLOCATED (a Pipelined

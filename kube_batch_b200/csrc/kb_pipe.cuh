@@ -147,7 +147,7 @@ __device__ __forceinline__ bool advance_rec(uint64_t* rec, const ClassRec& c) {
   rec[col_nz_mem(R)] = (uint64_t)((int64_t)rec[col_nz_mem(R)] + c.nz_mem);
   rec[col_pods(R)] = rec[col_pods(R)] + 1ull;
 #pragma unroll
-  for (uint32_t w = 0; w < W; ++w) rec[col_ports(R, W, w)] |= c.port_own[w];
+  for (uint32_t w = 0; w < W; ++w) rec[col_ports(R, W, w)] |= c.port_own[w] | (fi ? c.aff_own[w] : 0ull);      // aff_own: ClassRec
   return fi;
 }
 

@@ -46,6 +46,63 @@ def _spec(rng, p_req=0.6, p_pref=0.5):
     return a
 
 
+def host_spread_session(seed: int, n_nodes: int = 12, n_groups: int = 8, pipe_geometry: bool = False, ports: bool = False) -> B.SessionBuilder:
+    """Only the commonest constraint: required anti-affinity on kubernetes.io/hostname (against the pod's own or another label),
+    also on pods already running; no preferred terms, no required affinity.  The engine encodes such sessions as atoms in the
+    node's port words and runs them on the persistent pipeline.  pipe_geometry: R = 3 (a scalar resource), for flatten(W=2)."""
+    rng = np.random.default_rng(seed)
+    sb = B.SessionBuilder()
+    nq = int(rng.integers(1, 3))
+    for q in range(nq):
+        sb.add_queue(B.Queue(f"q{q}", weight=int(rng.integers(1, 4)), creation=q))
+    for i in range(n_nodes):
+        cpu = int(rng.choice([2, 4, 8]))
+        alloc = B.build_resource_list(str(cpu), f"{cpu * 2}Gi")
+        if pipe_geometry:
+            alloc[B.GPU] = 4.0
+        else:
+            alloc.pop(B.GPU, None)
+        sb.add_node(B.build_node(f"n{i:03d}", alloc, labels={HOST: f"n{i:03d}", ZONE: f"z{i % 3}"}, pods=int(rng.choice([3, 110]))))
+
+    def anti(label):
+        t = B.PodAffinityTerm(HOST, match_labels={"app": label})
+        if rng.random() < 0.2:
+            t.namespaces = ["ns1", "ns2"]
+        return B.PodAffinity(required=[t] if rng.random() < 0.85 else [t, B.PodAffinityTerm(HOST, match_expressions=[("app", "Exists", [])])])
+    uid = 0
+    sb.add_pod_group(B.PodGroup("ns1", "run-a", "q0", min_member=1))
+    load = {}
+    for i in range(int(rng.integers(0, n_nodes))):
+        host = int(rng.integers(0, n_nodes))
+        if load.get(host, 0) >= 1:
+            continue
+        load[host] = 1
+        lab = APPS[int(rng.integers(0, 4))]
+        p = B.build_pod("ns1", f"r{i}", f"n{host:03d}", "Running", {"cpu": 1.0, "memory": 1e9}, "run-a", labels={"app": lab})
+        if rng.random() < 0.5:
+            p.pod_anti_affinity = anti(APPS[int(rng.integers(0, 4))])
+        p.uid = f"u{uid:05d}"; uid += 1
+        sb.add_pod(p)
+    for g in range(n_groups):
+        ns = "ns1" if rng.random() < 0.8 else "ns2"
+        ntask = int(rng.integers(1, 7))
+        sb.add_pod_group(B.PodGroup(ns, f"pg{g}", f"q{int(rng.integers(0, nq))}", min_member=int(rng.integers(1, ntask + 1)), creation=g))
+        lab = APPS[int(rng.integers(0, 4))]
+        spec = anti(lab if rng.random() < 0.7 else APPS[int(rng.integers(0, 4))]) if rng.random() < 0.6 else None
+        req = {"cpu": float(rng.choice([0.5, 1, 2])), "memory": float(rng.choice([1, 2])) * 1e9}
+        if pipe_geometry and rng.random() < 0.3:
+            req[B.GPU] = 1.0
+        hp = [("", "TCP", 8000 + int(rng.integers(0, 3)))] if ports and rng.random() < 0.3 else []
+        for i in range(ntask):
+            p = B.build_pod(ns, f"pg{g}-{i}", "", "Pending", dict(req), f"pg{g}", labels={"app": lab})
+            p.pod_anti_affinity = spec
+            p.host_ports = list(hp)
+            p.creation = int(rng.integers(0, 3))
+            p.uid = f"u{uid:05d}"; uid += 1
+            sb.add_pod(p)
+    return sb
+
+
 def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_affine: float = 0.6, besteffort: bool = False,
                             spec_pool: int = 0) -> B.SessionBuilder:
     """spec_pool > 0: the PodGroups draw their (labels, affinity, anti-affinity) from that many templates (large sessions stay

@@ -161,7 +161,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       dst.col[col_nz_cpu(R)] = (uint64_t)((int64_t)src.col[col_nz_cpu(R)] + cls.nz_cpu);
       dst.col[col_nz_mem(R)] = (uint64_t)((int64_t)src.col[col_nz_mem(R)] + cls.nz_mem);
       dst.col[col_pods(R)] = src.col[col_pods(R)] + 1ull;
-      for (uint32_t w = 0; w < W; ++w) dst.col[col_ports(R, W, w)] = src.col[col_ports(R, W, w)] | cls.port_own[w];
+      for (uint32_t w = 0; w < W; ++w) dst.col[col_ports(R, W, w)] = src.col[col_ports(R, W, w)] | cls.port_own[w] | (cd.cur_fi ? cls.aff_own[w] : 0ull);
       SlotAcc acc{&dst, R, W};
       bool f = false;
       cd.next_key = add_pref_term(eval_pair(S.cf, cls, acc, cd.node, &f), pc, cd.pref);
@@ -697,7 +697,7 @@ int kbemu_finish(void* h, kb_decision* out, kb_stats* stats,
     if (node_pods) node_pods[n] = a.pods();
     if (node_nz_cpu) node_nz_cpu[n] = a.nz_cpu();
     if (node_nz_mem) node_nz_mem[n] = a.nz_mem();
-    if (node_ports) for (uint32_t w = 0; w < W; ++w) node_ports[(size_t)w * N + n] = a.ports(w);
+    if (node_ports) for (uint32_t w = 0; w < W; ++w) node_ports[(size_t)w * N + n] = a.ports(w) & ~E.B.aff_atom_mask[w];
   }
   for (uint32_t j = 0; j < J; ++j) { if (job_share) job_share[j] = S.job_share[j]; if (job_ready) job_ready[j] = S.job_ready[j]; }
   for (uint32_t q = 0; q < Q; ++q) {

@@ -139,19 +139,46 @@ def test_big_affinity_session_matches_the_emulation_and_is_timed(eng):
         json.dump(rec, open(os.path.join(out, "affinity_big_session.json"), "w"))
 
 
-@pytest.mark.parametrize("name", ["c2", "c3"])
-def test_one_replica_per_host_at_baseline_size(eng, name):
+@pytest.mark.parametrize("seed", range(24))
+def test_host_level_anti_affinity_runs_on_the_pipeline(eng, seed):
+    """Required anti-affinity on kubernetes.io/hostname only (pending and running pods): the host build turns the counter groups into
+    atoms of the node's port words (kb_build.h), so the session runs on cycle_kernel when the record geometry allows — bit-exact
+    against the object-level oracle, allocate and allocate + backfill."""
+    pg = seed % 3 != 2
+    snap = aff_gen.host_spread_session(700 + seed, n_nodes=3 + seed % 14, n_groups=3 + seed % 9, pipe_geometry=pg, ports=seed % 4 == 0).flatten(W=2 if pg else 1)
+    if snap.pod_affinity is None:
+        pytest.skip("no affinity terms drawn")
+    for ci, conf in enumerate((PluginConf.default(), PluginConf.from_names([["gang"], ["predicates"]]))):
+        for actions in (1, 3):
+            o = kbo.allocate(snap, conf, actions=actions)
+            eng.load(snap, conf)
+            r = eng.allocate()
+            assert r.stats.pipeline == (1 if pg else 0)
+            if actions & 2:
+                r = eng.backfill()
+            util.assert_same_decisions(o.decisions, r.decisions, f"seed {seed} conf {ci} actions {actions}")
+            util.assert_same_state(o, eng.node_state(), eng.order_state(), f"seed {seed} conf {ci} actions {actions}")
+
+
+@pytest.mark.parametrize("name,atoms", [("c2", 1), ("c2", 0), ("c3", 1), ("c3", 0)])
+def test_one_replica_per_host_at_baseline_size(eng, name, atoms):
     """BASELINE configs 2 / 3 with a tenth of the PodGroups under "one replica per host" (required anti-affinity on
-    kubernetes.io/hostname against their own label, synth.add_host_spread).  Their own placements only touch single-node domains, so
-    the replay keeps multi-task runs (ClassAff.pred_multi_ok).  Engine vs the emulation (the object-level oracle is O(pods) per pair)."""
+    kubernetes.io/hostname against their own label, synth.add_host_spread).  atoms = 1: the groups become atoms of the port words and
+    the cycle runs on cycle_kernel; atoms = 0 (KB_AFF_ATOMS=0): the counter path on the per-visit kernels, where such classes keep
+    multi-task runs (ClassAff.pred_multi_ok).  Engine vs the emulation (the object-level oracle is O(pods) per pair)."""
     import json, os
     from kube_batch_b200 import synth
     s, conf = synth.make(name)
     synth.add_host_spread(s, 0.1)
     e = util.emu_allocate(s, conf, mode=1)
-    eng.load(s, conf)
+    os.environ["KB_AFF_ATOMS"] = str(atoms)
+    try:
+        eng.load(s, conf)
+    finally:
+        os.environ.pop("KB_AFF_ATOMS", None)
     eng.allocate()
     r = eng.allocate()
+    assert r.stats.pipeline == atoms
     util.assert_same_decisions(e.decisions, r.decisions, f"{name} + host spread vs emulation")
     d = r.decisions
     fb = s.pod_affinity["task_forbid"][:s.T]
@@ -159,9 +186,10 @@ def test_one_replica_per_host_at_baseline_size(eng, name):
         nodes = d["node"][(fb == np.uint64(3 << (2 * lab))) & (d["kind"] == abi.KB_KIND_ALLOCATED)]
         assert len(nodes) == len(set(nodes.tolist())), "two replicas of one label on a host"
     st = r.stats
-    rec = {"workload": name, "spread_tasks": int(s.meta["spread_tasks"]), "gpu_ms": float(st.gpu_ms), "kernel_launches": int(st.kernel_launches),
+    rec = {"workload": name, "path": "cycle_kernel (groups as port-word atoms)" if atoms else "visit_kernel<0,1> (counters)",
+           "spread_tasks": int(s.meta["spread_tasks"]), "gpu_ms": float(st.gpu_ms), "kernel_launches": int(st.kernel_launches),
            "allocated": int(st.tasks_allocated), "pairs_logical": int(st.pairs_logical), "pairs_per_s": float(st.pairs_logical) / (st.gpu_ms * 1e-3)}
     print("host spread timing:", json.dumps(rec))
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
-        json.dump(rec, open(os.path.join(out, f"affinity_host_spread_{name}.json"), "w"))
+        json.dump(rec, open(os.path.join(out, f"affinity_host_spread_{name}_{'atoms' if atoms else 'counters'}.json"), "w"))

@@ -298,3 +298,30 @@ def test_synthetic_host_spread_tables_are_what_the_flattener_produces():
     d = e.decisions
     placed = d["node"][d["kind"] == abi.KB_KIND_ALLOCATED]
     assert len(placed) == len(set(placed.tolist())) > 0
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_host_level_anti_affinity_as_atoms_in_every_launch_mode(seed):
+    """Sessions whose only inter-pod constraint is required anti-affinity on kubernetes.io/hostname: kb_build.h encodes the counter
+    groups as atoms of the node's port words (ClassRec.port_conflict / aff_own), so they run in EVERY launch mode — overlap (0),
+    plain (1), the persistent pipeline's stale-list + patch protocol (5) — and must still equal the object-level oracle.
+    KB_AFF_ATOMS=0 keeps them on the counter path; both must agree."""
+    import os
+    pg = seed % 2 == 0
+    snap = aff_gen.host_spread_session(seed, n_nodes=3 + seed % 14, n_groups=3 + seed % 9, pipe_geometry=pg, ports=seed % 3 == 0).flatten(W=2 if pg else 1)
+    if snap.pod_affinity is None:
+        pytest.skip("no affinity terms drawn")
+    for ci, conf in enumerate((PluginConf.default(), PluginConf.from_names([["gang"], ["predicates"]]),
+                               PluginConf.from_names([["priority", "gang"], ["drf", "predicates", "proportion", "nodeorder"]], {"nodeorder": {"podaffinity.weight": "0"}}))):
+        o = kbo.allocate(snap, conf, actions=3)
+        for mode in (0, 1, 5):
+            e = util.emu_allocate(snap, conf, actions=3, mode=mode)
+            util.assert_same_decisions(o.decisions, e.decisions, f"seed {seed} conf {ci} mode {mode}")
+            st = util.emu_states(e)
+            util.assert_same_state(o, st[0], st[1], f"seed {seed} conf {ci} mode {mode}")
+        os.environ["KB_AFF_ATOMS"] = "0"
+        try:
+            e = util.emu_allocate(snap, conf, actions=3, mode=1)
+        finally:
+            os.environ.pop("KB_AFF_ATOMS", None)
+        util.assert_same_decisions(o.decisions, e.decisions, f"seed {seed} conf {ci} counter path")
