@@ -561,3 +561,19 @@ def test_committed_cycle_digests_match_a_fresh_oracle_run():
         assert digest.decisions_digest(o.decisions) == g[name]["decisions"], name
         assert digest.state_digest(o.node_idle, o.node_releasing, o.job_ready, o.job_share) == g[name]["state"], name
         assert int(o.result.tasks_allocated) == g[name]["allocated"]
+
+
+@pytest.mark.parametrize("replica", [2, 7])
+def test_replica_digests_match_the_pipeline_emulation(replica):
+    """bench.py --gpus N: rank r schedules synth.make("c3", replica=r) and checks itself against tests/golden/cycle_hashes.json
+    "c3#r" (made by the oracle).  Here: the emulation of cycle_kernel's protocol (mode 5) reproduces those digests on the CPU."""
+    import json
+    import os
+    import util
+    from kube_batch_b200 import digest, synth
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "cycle_hashes.json")))[f"c3#{replica}"]
+    s, conf = synth.make("c3", replica=replica)
+    e = util.emu_allocate(s, conf, mode=5)
+    assert digest.decisions_digest(e.decisions) == g["decisions"]
+    ns, os_ = util.emu_states(e)
+    assert digest.state_digest(ns["idle"], ns["releasing"], os_["job_ready"], os_["job_share"]) == g["state"]
