@@ -208,7 +208,8 @@ typedef struct kb_snapshot {
   /* ---- preferred node affinity (NodeAffinityPriority, vendor/.../priorities/node_affinity.go:34-77) ----
    * Only read for tasks that carry KB_TASK_HAS_PREFERRED_NODE_AFFINITY; all three may be NULL otherwise.  The CPU oracle
    * evaluates them (count = sum of the weights of the matching terms, NormalizeReduce(10) over the feasible nodes);
-   * the engine evaluates them in cycle_kernel (sessions on the per-visit kernels are refused, KB_E_UNSUPPORTED_FEATURE). */
+   * the engine evaluates them in cycle_kernel, and on the per-visit kernels (other record geometries, sessions with inter-pod terms)
+   * with a pass over the feasible nodes before every visit of such a class; refused only on a sharded node axis. */
   const uint32_t* task_n_pref_terms;  /* [T] 0..KB_MAX_PREF_TERMS                                    */
   const uint64_t* task_pref_terms;    /* [KB_MAX_PREF_TERMS][W][T] requirement atoms of term p: ALL must hold on the node */
   const int32_t*  task_pref_weights;  /* [KB_MAX_PREF_TERMS][T] PreferredSchedulingTerm.Weight (0 = term skipped) */

@@ -53,7 +53,8 @@ struct AffDev {
   uint32_t has_weights;           // some class has a weight list: the priority passes run before every visit
   int32_t  w_podaff;              // podaffinity.weight (nodeorder.go:111-117)
   uint32_t dom_total;             // sum of the key sets' domain counts (size of dom_sum)
-  uint32_t pad0;
+  uint32_t has_pref;              // some class carries preferred NODE-affinity terms and the session runs on the per-visit kernels:
+                                  // pass 2 also reduces the max count over the feasible nodes (NodeAffinityPriority, minmax[2])
   const int32_t*  node_domain;    // [n_keysets][N]
   const uint32_t* keyset_off;     // [n_keysets + 1] offsets into dom_sum
   const uint32_t* group_keyset;   // [n_groups]
@@ -68,7 +69,7 @@ struct AffDev {
   int32_t*   kind_count;          // [n_kinds][N]
   int32_t*   first_unbound;       // [1], -1 none
   long long* dom_sum;             // [dom_total] scratch of the priority: weight per domain over the feasible nodes (pass 1)
-  long long* minmax;              // [2] min / max count over the feasible nodes (pass 2)
+  long long* minmax;              // [3] min / max count over the feasible nodes (pass 2); [2] = max preferred node-affinity count
 };
 
 // Must the replay stop after ONE placement of this class (fresh scan per task)?  Yes when its keys read counters that its own

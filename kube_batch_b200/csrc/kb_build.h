@@ -303,6 +303,11 @@ struct BuiltSession {
   }
 };
 
+// tests/emu's first a12 prototype (plain launches + a countdown of the feasible max-count nodes in the replay) only survives for the
+// SHARDED emulation (world > 1: pass 1 on every rank's replicated table, no second exchange); on one rank the plain path now
+// evaluates preferred node affinity like the kernels do (counter path)
+inline bool allow_pref_legacy(bool allow_pref, uint32_t world) { return allow_pref && world > 1; }
+
 // Everything kb_session_load does before touching the device.  `max_grid` = scan CTAs (SM count).
 inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint32_t max_grid, BuiltSession& B, BuildErr* e,
                          uint32_t rank = 0, uint32_t world = 1, int overlap_mode = -1 /* -1 auto, 0 off, 1 on */,
@@ -401,6 +406,44 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   const kb_pod_affinity* pa_full = pa;                  // the snapshot's tables (class identity below)
   if (aff_as_atoms) pa = nullptr;                       // from here on `pa` = what the counter path (AffDev) consumes
+  // Preferred NODE affinity (a12) outside cycle_kernel: the per-visit kernels evaluate it with the same machinery as the inter-pod
+  // priority — a pass over the feasible nodes before the visit (max count, aff_prepass_kernel<2>), the term in the scan, a fresh
+  // scan per task of such a class.  Without inter-pod tables the counter path runs on empty ones.
+  bool any_pref = false;
+  for (uint32_t t = 0; t < T && !any_pref; ++t) any_pref = (s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) != 0;
+  bool will_pipe = false;
+  if (pipe_mode > 0 && world <= 1 && N > 0 && R == 3 && W == 2 && std::max(1u, max_grid) >= 2) {
+    const uint32_t nt = (N + TILE_NODES - 1) / TILE_NODES, smax = std::max(1u, max_grid) - 1;
+    const size_t tile_bytes = (size_t)tile_ncols(R, W) * TILE_NODES * 8;
+    will_pipe = (nt + smax - 1) / smax <= (uint32_t)((227 * 1024 - 8 * 1024) / tile_bytes);
+  }
+  static const int32_t kz32[2] = {-1, -1};
+  static const uint32_t kzu32[2] = {0, 0};
+  static const uint64_t kzu64[2] = {0, 0};
+  static const int64_t kz64[2] = {0, 0};
+  static const uint8_t kzu8[2] = {0, 0};
+  std::vector<uint64_t> empty_u64;
+  std::vector<int32_t> empty_i32;
+  std::vector<uint32_t> empty_off;
+  kb_pod_affinity empty_pa;
+  const bool pref_legacy = any_pref && allow_pref_legacy(allow_pref, world);
+  const bool pref_on_counters = any_pref && !will_pipe && !pref_legacy;
+  if (pref_on_counters || (pa && any_pref)) {
+    if (world > 1) return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node-affinity terms outside the persistent pipeline: not with a sharded node axis");
+    pipe_mode = 0; overlap_mode = 0; kchain = 1;
+    if (!pa) {
+      memset(&empty_pa, 0, sizeof empty_pa);
+      empty_u64.assign(std::max(1u, T), 0); empty_i32.assign(std::max(1u, T), -1); empty_off.assign((size_t)T + 1, 0);
+      empty_pa.first_unbound_node = -1;
+      empty_pa.node_domain = kz32; empty_pa.keyset_domains = kzu32; empty_pa.group_keyset = kzu32; empty_pa.group_count0 = kz32 + 0;
+      empty_pa.group_total0 = kz32; empty_pa.task_forbid = empty_u64.data(); empty_pa.task_need = empty_i32.data();
+      empty_pa.task_contrib = empty_u64.data(); empty_pa.task_kind = empty_i32.data(); empty_pa.node_kind_count0 = kz32;
+      empty_pa.kind_unbound = kzu8; empty_pa.task_weight_off = empty_off.data(); empty_pa.weight_kind = kz32; empty_pa.weight_keyset = kz32;
+      empty_pa.weight_value = kz64;
+      (void)kzu64;
+      pa = &empty_pa;
+    }
+  }
   auto atoms_of = [&](uint64_t groups, uint64_t* out) {
     while (groups) { const uint32_t g = (uint32_t)__builtin_ctzll(groups); groups &= groups - 1; const int a = aff_atom_of_group[g]; if (a >= 0) out[a / 64] |= 1ull << (a % 64); }
   };
@@ -518,10 +561,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
       }
       if ((s->task_flags[t] & KB_TASK_HAS_POD_AFFINITY) && !pa_full)
         return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries inter-pod affinity terms but the snapshot has no kb_pod_affinity (no CPU fallback)", t);
-      if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && pa)
-        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u: preferred node-affinity terms in a session with inter-pod affinity (per-visit kernels do not evaluate NodeAffinityPriority)", t);
-      if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && !allow_pref && pipe_mode <= 0)
-        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries preferred node-affinity terms: only the persistent pipeline (cycle_kernel) evaluates them", t);
+      if ((s->task_flags[t] & KB_TASK_HAS_PREFERRED_NODE_AFFINITY) && !pa && !will_pipe && !pref_legacy)
+        return bfail(e, KB_E_UNSUPPORTED_FEATURE, "task %u carries preferred node-affinity terms: neither the persistent pipeline nor the counter path is available", t);
       ClassPref cp = pref_of(t);
       if (cp.n) {
         if (cp.n > KB_MAX_PREF_TERMS) return bfail(e, KB_E_BADARG, "task %u: preferred node-affinity arrays missing or n_pref_terms > KB_MAX_PREF_TERMS", t);
@@ -578,8 +619,6 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   }
   if (classes.empty()) { ClassRec c; memset(&c, 0, sizeof c); classes.push_back(c); ClassPref cp; memset(&cp, 0, sizeof cp); class_pref.push_back(cp); }
   static_assert(sizeof(ClassPref) % 8 == 0, "ClassPref is hashed as 64-bit words");
-  if (B.has_pref && !pipe_mode && (kchain > 1 || overlap_mode > 0))
-    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node affinity: only the plain launch mode is prototyped");
   if (B.has_pref) hc.cf.score_bias += 10ll * (hc.w_nodeaff < 0 ? -(int64_t)hc.w_nodeaff : 0);
   const uint32_t C = (uint32_t)classes.size();
   B.aff = AffDev{};
@@ -590,6 +629,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     for (const ClassAff& ca : aff_tab) if (ca.w_cnt) A.has_weights = 1;
     if (!hc.cf.nodeorder || hc.w_podaff == 0) A.has_weights = 0;          // the priority is not registered / weighs nothing
     if (A.has_weights) hc.cf.score_bias += 10ll * (hc.w_podaff < 0 ? -(int64_t)hc.w_podaff : 0);
+    A.has_pref = (B.has_pref && hc.cf.nodeorder) ? 1u : 0u;
     aff_keyset_off.assign(pa->n_keysets + 1, 0);
     for (uint32_t k = 0; k < pa->n_keysets; ++k) {
       if (pa->keyset_domains[k] > N) return bfail(e, KB_E_BADARG, "kb_pod_affinity: key set %u has more domains than nodes", k);
@@ -678,9 +718,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     const uint32_t tpc = (NT + smax - 1) / smax;
     if (tpc <= max_tpc) { B.pipe = 1; B.pipe_tpc = tpc; B.pipe_S = (NT + tpc - 1) / tpc; }
   }
-  if (B.has_pref && !B.pipe && !allow_pref)
-    return bfail(e, KB_E_UNSUPPORTED_FEATURE, "preferred node-affinity terms need the persistent pipeline (cycle_kernel): this session's geometry "
-                 "(R = %u, W = %u, %u nodes) runs on the per-launch kernels, which do not evaluate NodeAffinityPriority", R, W, N);
+  if (B.has_pref && !B.pipe && !B.aff.on && !pref_legacy)
+    return bfail(e, KB_E_STATE, "preferred node-affinity terms: the session ended up on the per-launch kernels without the counter path (R = %u, W = %u, %u nodes)", R, W, N);
   om.pipe_g = mut.alloc(sizeof(PipeG));
   om.modlog = mut.alloc(((size_t)To + 64) * 4);
   om.pcand = mut.alloc((size_t)PIPE_RING * std::max(1u, B.pipe_S) * KTOP * 8);
@@ -746,7 +785,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
     om.aff_kind_count = mut.alloc((size_t)std::max(1u, pa->n_kinds) * std::max(1u, N) * 4);
     om.aff_first_unbound = mut.alloc(8);
     om.aff_dom_sum = mut.alloc((size_t)std::max(1u, B.aff.dom_total) * 8);
-    om.aff_minmax = mut.alloc(16);
+    om.aff_minmax = mut.alloc(32);
   }
   mut.commit(); imm.commit();
 

@@ -456,7 +456,7 @@ int kb_session_load(kb_engine* e, const kb_snapshot* s, const kb_plugin_conf* co
       if (e->dev.aff.on) {
         // inter-pod affinity: the priority's passes over the feasible nodes (they return at once for a class without a weight
         // list), then the visit with predicate step 10 / the score term in its scan
-        if (e->dev.aff.has_weights) {
+        if (e->dev.aff.has_weights || e->dev.aff.has_pref) {
           const uint32_t ag = std::max(1u, std::min((e->N + AFF_THREADS - 1) / AFF_THREADS, (uint32_t)e->sm_count * 4u));
           const uint32_t ag1 = std::max(1u, std::min((e->N + AFF_THREADS / 32 - 1) / (AFF_THREADS / 32), (uint32_t)e->sm_count * 8u));   // pass 1: a warp per node
           aff_prepass_kernel<0><<<ag, AFF_THREADS, 0, e->stream>>>(e->dev);
@@ -549,7 +549,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
       launches += 1;
     } else if (use_graph) {
       CUDA_TRY(e, cudaGraphLaunch(e->graph_exec, e->stream));
-      launches += ((D.aff.on && D.aff.has_weights) ? 4 : (e->world == 1 || D.p2p || e->replicated) ? 1 : 2) * BATCH;
+      launches += ((D.aff.on && (D.aff.has_weights || D.aff.has_pref)) ? 4 : (e->world == 1 || D.p2p || e->replicated) ? 1 : 2) * BATCH;
     } else {
       // sharded node axis without peer memory: scan shard -> all-gather (top-32 keys + node records per rank) -> identical replay
       const size_t cnt = (size_t)xchg_u64(e->ncols);
@@ -557,7 +557,7 @@ int run_action(kb_engine* e, const bool backfill, kb_decision* out, kb_stats* st
         if (D.aff.on) {
           if (backfill) visit_kernel<1, 1><<<e->scan_grid, SCAN_THREADS, e->visit_smem, e->stream>>>(D);      // nodeorder is off in backfill: no passes
           else {
-            if (D.aff.has_weights) {
+            if (D.aff.has_weights || D.aff.has_pref) {
               const uint32_t ag = std::max(1u, std::min((e->N + AFF_THREADS - 1) / AFF_THREADS, (uint32_t)e->sm_count * 4u));
               const uint32_t ag1 = std::max(1u, std::min((e->N + AFF_THREADS / 32 - 1) / (AFF_THREADS / 32), (uint32_t)e->sm_count * 8u));
               aff_prepass_kernel<0><<<ag, AFF_THREADS, 0, e->stream>>>(D);

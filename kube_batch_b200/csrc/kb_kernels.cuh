@@ -137,6 +137,7 @@ __device__ __forceinline__ uint64_t cta_fold_lists(uint64_t mine, uint64_t (*wli
 struct VisitSmem {
   ClassRec cls;
   ClassAff cls_aff;                          // inter-pod affinity record of the class (AFF instantiations only)
+  ClassPref cls_pref;                        // preferred node-affinity terms of the class (AFF instantiations, AffDev.has_pref)
   Ctl ctl;
   uint64_t keys[KTOP];                       // merged candidate list of the scan (K3 result)
   uint64_t wlist[SCAN_WARPS][KTOP];          // per-warp lists exchanged through shared memory
@@ -243,7 +244,8 @@ __device__ __forceinline__ void replay_epilogue(const DevSession& S, VisitSmem& 
   uint32_t my_cnt = 0;        // placements on MY candidate (NodeInfo.Used delta = my_cnt x Resreq, applied at write-back)
   // inter-pod affinity (kb_aff.h): a class whose keys read counters that its own placement changes beyond the chosen node uses
   // its list for ONE placement — the placement can change the feasibility / score of every node of a topology domain
-  const bool aff_rd = AFF && aff_stop_each(sm.cls_aff, S.cf.nodeorder != 0);
+  const bool aff_rd = AFF && (aff_stop_each(sm.cls_aff, S.cf.nodeorder != 0) ||
+                              (S.aff.has_pref && sm.cls_pref.n != 0 && S.cf.nodeorder != 0));      // the normalisation (max count) can move with every placement
   bool aff_stop = false;
   for (;;) {              // runs
     if (c.done || c.cur_class != cls_id || (AFF && aff_stop)) break;
@@ -500,12 +502,20 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
       const uint32_t* as = reinterpret_cast<const uint32_t*>(&S.aff.cls[cls_id]);
       uint32_t* ad = reinterpret_cast<uint32_t*>(&sm.cls_aff);
       for (uint32_t i = tid; i < sizeof(ClassAff) / 4; i += SCAN_THREADS) ad[i] = as[i];
+      uint32_t* pd = reinterpret_cast<uint32_t*>(&sm.cls_pref);
+      if (S.aff.has_pref) {
+        const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[cls_id]);
+        for (uint32_t i = tid; i < sizeof(ClassPref) / 4; i += SCAN_THREADS) pd[i] = ps[i];
+      } else if (tid == 0) sm.cls_pref.n = 0;
     }
   }
   __syncthreads();
   // InterPodAffinityPriority: the passes of aff_prepass_kernel left the per-domain weights and the min / max count
   const bool ipa = AFF && sm.cls_aff.w_cnt != 0 && S.cf.nodeorder != 0;
   const long long ipa_min = ipa ? __ldcg(&S.aff.minmax[0]) : 0ll, ipa_max = ipa ? __ldcg(&S.aff.minmax[1]) : 0ll;
+  // NodeAffinityPriority on the per-visit kernels: pass 2 left the max count over the feasible nodes (NormalizeReduce, reduce.go:28-63)
+  const bool prf = AFF && S.aff.has_pref && sm.cls_pref.n != 0 && S.cf.nodeorder != 0;
+  const long long prf_max = prf ? __ldcg(&S.aff.minmax[2]) : 0ll;
   const uint32_t sub = (uint32_t)warp >> 2, part = (uint32_t)warp & 3u;    // which tile of the group / which 32 nodes of it
   uint64_t mylist = 0;                       // this warp's running top-32 (lane l holds the l-th best)
   bool pany = false;                         // PH (backfill): a node that passes the plugin predicates but has no Idle for Resreq
@@ -533,6 +543,7 @@ __device__ __forceinline__ uint64_t scan_phase(const DevSession& S, VisitSmem& s
       if (AFF) {
         if (S.cf.predicates && !aff_pred(S.aff, sm.cls_aff, S.N, node)) { key = 0; pok = false; }      // predicate step 10
         if (ipa && key) key = aff_add_score(key, S.aff.w_podaff, aff_score(aff_count_node(S.aff, sm.cls_aff, S.N, node), ipa_min, ipa_max));
+        if (prf && key) key = add_pref_term(key, (int64_t)S.w_nodeaff, (int64_t)pref_count(sm.cls_pref, acc, S.cf.W), (int64_t)prf_max);
       }
       if (PH) pany = pany | (pok && key == 0);
     }
@@ -809,12 +820,21 @@ aff_prepass_kernel(const __grid_constant__ DevSession S) {
   __shared__ ClassAff sca;
   if (__ldcg(&S.ctl->done) || !S.cf.nodeorder) return;
   const uint32_t cls_id = __ldcg(&S.ctl->cur_class);
-  if (S.aff.cls[cls_id].w_cnt == 0) return;
+  const bool wts = S.aff.cls[cls_id].w_cnt != 0;
+  const bool prf = S.aff.has_pref && S.class_pref[cls_id].n != 0;        // NodeAffinityPriority: max count over the feasible nodes
+  if (!wts && !prf) return;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, nthr = gridDim.x * blockDim.x;
   if (PHASE == 0) {
-    for (uint32_t i = gtid; i < S.aff.dom_total; i += nthr) S.aff.dom_sum[i] = 0;
-    if (gtid == 0) { S.aff.minmax[0] = 0; S.aff.minmax[1] = 0; }
+    if (wts) for (uint32_t i = gtid; i < S.aff.dom_total; i += nthr) S.aff.dom_sum[i] = 0;
+    if (gtid == 0) { S.aff.minmax[0] = 0; S.aff.minmax[1] = 0; S.aff.minmax[2] = 0; }
     return;
+  }
+  if (PHASE == 1 && !wts) return;
+  __shared__ ClassPref scp;
+  if (prf) {
+    const uint32_t* ps = reinterpret_cast<const uint32_t*>(&S.class_pref[cls_id]);
+    uint32_t* pd = reinterpret_cast<uint32_t*>(&scp);
+    for (uint32_t i = threadIdx.x; i < sizeof(ClassPref) / 4; i += blockDim.x) pd[i] = ps[i];
   }
   {
     const uint32_t* src = reinterpret_cast<const uint32_t*>(&S.classes[cls_id]);
@@ -843,11 +863,20 @@ aff_prepass_kernel(const __grid_constant__ DevSession S) {
         atomicAdd(reinterpret_cast<unsigned long long*>(&S.aff.dom_sum[slot]), (unsigned long long)v); }, lane, 32u);
     }
   } else {
+    long long pmx = 0;
     for (uint32_t n = gtid; n < S.N; n += nthr) {
       if (!feasible(n)) continue;
-      const long long cnt = aff_count_node(S.aff, sca, S.N, n);
-      mn = cnt < mn ? cnt : mn; mx = cnt > mx ? cnt : mx;
+      if (wts) {
+        const long long cnt = aff_count_node(S.aff, sca, S.N, n);
+        mn = cnt < mn ? cnt : mn; mx = cnt > mx ? cnt : mx;
+      }
+      if (prf) {
+        TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, S.cf.R, S.cf.W};
+        const long long pc = (long long)pref_count(scp, acc, S.cf.W);
+        pmx = pc > pmx ? pc : pmx;
+      }
     }
+    if (pmx > 0) atomicMax(&S.aff.minmax[2], pmx);
   }
   if (PHASE == 2) {
     if (mn < 0) atomicMin(&S.aff.minmax[0], mn);

@@ -104,7 +104,7 @@ def host_spread_session(seed: int, n_nodes: int = 12, n_groups: int = 8, pipe_ge
 
 
 def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_affine: float = 0.6, besteffort: bool = False,
-                            spec_pool: int = 0) -> B.SessionBuilder:
+                            spec_pool: int = 0, node_pref: bool = False) -> B.SessionBuilder:
     """spec_pool > 0: the PodGroups draw their (labels, affinity, anti-affinity) from that many templates (large sessions stay
     within the 64 counter groups of kb_pod_affinity)."""
     rng = np.random.default_rng(seed)
@@ -159,9 +159,13 @@ def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_a
         if pool:
             labels, aff, anti = pool[int(rng.integers(0, len(pool)))]
         req = {} if (besteffort and rng.random() < 0.5) else B.build_resource_list(str(int(rng.choice([1, 2, 3]))), f"{int(rng.choice([1, 2, 4]))}Gi")
+        npref = []
+        if node_pref and rng.random() < 0.5:      # preferred NODE affinity (NodeAffinityPriority) next to the inter-pod terms
+            npref = [(int(rng.choice([1, 10, 50, 100])), [(ZONE, "In", [f"z{int(rng.integers(0, 3))}"])]) for _ in range(int(rng.integers(1, 3)))]
         for i in range(ntask):
             p = B.build_pod(ns, f"pg{g}-{i}", "", "Pending", req, f"pg{g}", labels=dict(labels))
             p.pod_affinity, p.pod_anti_affinity = aff, anti
+            p.preferred_terms = list(npref)
             p.creation = int(rng.integers(0, 4))
             p.uid = f"u{uid:05d}"; uid += 1
             if besteffort and not req and rng.random() < 0.3:

@@ -83,16 +83,6 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
   // pass 1 (only for a class with preferred terms): max count over the FEASIBLE nodes + how many feasible nodes reach it
   const ClassPref* cp = (E.B.has_pref && S.cf.nodeorder && !S.backfill && E.B.class_pref[c.cur_class].n) ? &E.B.class_pref[c.cur_class] : nullptr;
   E.pref_max = 0; E.pref_nmax = 0;
-  if (cp)
-    for (uint32_t n = 0; n < S.N; ++n) {
-      TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
-      if (!eval_pair(S.cf, cls, acc, n, nullptr)) continue;
-      const int64_t cnt = pref_count(*cp, acc, W);
-      if (cnt > E.pref_max) { E.pref_max = cnt; E.pref_nmax = 1; }
-      else if (cnt == E.pref_max) E.pref_nmax += 1;
-    }
-  uint32_t nmax_dummy = 0;
-  PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &nmax_dummy};
   // inter-pod affinity (kb_aff.h): step 10 joins the plugin predicates; a class with a weight list gets the priority's passes
   // first (aff_prepass_kernel): pass 1 = weight per topology domain over the FEASIBLE nodes, pass 2 = min / max count
   const AffDev& A = S.aff;
@@ -105,6 +95,16 @@ void emu_scan(Emu& E, uint64_t* sendbuf) {
     if (S.backfill && c.pred_dead) { k = 0; if (pok) *pok = false; }      // Ctl.pred_dead: every predicate fails once a task is Allocated on no node
     return k;
   };
+  if (cp)                       // aff_prepass_kernel<2>: max preferred count over the FEASIBLE nodes (incl. predicate step 10)
+    for (uint32_t n = 0; n < S.N; ++n) {
+      if (!feasible_key(n, nullptr)) continue;
+      TileAcc acc{S.tiles + (size_t)(n / TILE_NODES) * tile_u64, n % TILE_NODES, R, W};
+      const int64_t cnt = pref_count(*cp, acc, W);
+      if (cnt > E.pref_max) { E.pref_max = cnt; E.pref_nmax = 1; }
+      else if (cnt == E.pref_max) E.pref_nmax += 1;
+    }
+  uint32_t nmax_dummy = 0;
+  PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &nmax_dummy};
   if (ipa) {
     for (uint32_t i = 0; i < A.dom_total; ++i) A.dom_sum[i] = 0;
     A.minmax[0] = 0; A.minmax[1] = 0;
@@ -144,7 +144,7 @@ struct Cand { bool have = false, cur_fi = false, next_fi = false, next_valid = f
 
 // replay_epilogue's core: look-ahead refresh + certified steps + control plane, for candidates already loaded
 bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector<Cand>& cand, const uint64_t floor_key,
-                 const PrefCtx* pc = nullptr, const bool pred_any_outside = false) {
+                 const PrefCtx* pc = nullptr, const bool pred_any_outside = false, const bool pref_stop_each = false) {
   const ClassRec& cls = S.classes[cls_id];
   const uint32_t R = S.cf.R, W = S.cf.W, ncols = S.ncols;
   const ClassAff* ca = S.aff.on ? &S.aff.cls[cls_id] : nullptr;
@@ -233,6 +233,7 @@ bool replay_core(const DevSession& S, Ctl& c, const uint32_t cls_id, std::vector
       S.job_placed[j] += 1;
       on_allocate_event(S, j, cls);
       if (ca) { aff_commit(S.aff, *ca, S.N, cd.node, fits_idle); aff_stale = ca_reads; }
+      if (pc && pref_stop_each) aff_stale = true;       // visit_kernel<.,1>: a class with preferred node-affinity terms is scanned afresh per task
       placed += 1;
       if (pc && pc->max > 0 && cd.cur_key == 0 && cd.pref == pc->max) {            // a max-count node left the feasible set
         *pc->nmax -= 1;
@@ -298,7 +299,7 @@ void emu_replay(Emu& E, const uint64_t* recvbuf) {
   const ClassPref* cp = (E.B.has_pref && S.cf.nodeorder && !S.backfill && E.B.class_pref[cls_id].n) ? &E.B.class_pref[cls_id] : nullptr;
   PrefCtx pc{cp, E.B.hc.w_nodeaff, E.pref_max, &E.pref_nmax};
   if (cp) for (auto& cd : cand) if (cd.have) { SlotAcc acc{&cd.st[0], R, W}; cd.pref = pref_count(*cp, acc, W); }
-  replay_core(S, c, cls_id, cand, floor_key, cp ? &pc : nullptr, pred_any);
+  replay_core(S, c, cls_id, cand, floor_key, cp ? &pc : nullptr, pred_any, S.aff.on != 0);      // sharded prototype (no counter path): countdown rule
   write_back(S, cls, cand);          // every replica writes every modified candidate back
 }
 

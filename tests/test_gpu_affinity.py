@@ -193,3 +193,14 @@ def test_one_replica_per_host_at_baseline_size(eng, name, atoms):
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
     if os.path.isdir(out):
         json.dump(rec, open(os.path.join(out, f"affinity_host_spread_{name}_{'atoms' if atoms else 'counters'}.json"), "w"))
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_inter_pod_terms_together_with_preferred_node_affinity(eng, seed):
+    """both priorities with a cross-node reduction in one session: InterPodAffinityPriority (min / max of the counts) and
+    NodeAffinityPriority (max count) share the passes of aff_prepass_kernel"""
+    sb = aff_gen.random_affinity_session(300 + seed, n_nodes=4 + seed % 13, n_groups=3 + seed % 6, node_pref=True, p_affine=0.6 if seed % 3 else 0.0)
+    snap = sb.flatten()
+    confs = tpa.AFF_CONFS + [PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "-3", "podaffinity.weight": "2"}})]
+    for ci, conf in enumerate(confs):
+        run_and_check(eng, snap, conf, f"seed {seed} conf {ci}", actions=3)

@@ -219,13 +219,16 @@ def test_preferred_node_affinity_on_the_gpu(eng, seed):
         run_and_check(eng, s, conf, f"pref seed{seed}")
 
 
-def test_preferred_node_affinity_outside_the_pipeline_geometry_is_refused(eng):
-    from test_emu_parity import _pref_cluster
-    s = _pref_cluster(6000)                       # R = 2, W = 1: the per-launch kernels would run it, and they have no a12
-    assert s.R == 2
-    with pytest.raises(engine.KbError) as ei:
-        eng.load(s, PluginConf.default())
-    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+def test_preferred_node_affinity_outside_the_pipeline_geometry(eng):
+    """R = 2, W = 1: the per-visit kernels run it (visit_kernel<0,1> + aff_prepass_kernel: max count over the feasible nodes before the
+    visit, a fresh scan per task of a class with preferred terms)."""
+    from test_emu_parity import _pref_cluster, PREF_CONFS
+    for seed in range(6):
+        s = _pref_cluster(6000 + seed)
+        assert s.R == 2
+        for conf in PREF_CONFS:
+            o, r = run_and_check(eng, s, conf, f"pref outside the pipeline geometry seed{seed}")
+            assert r.stats.pipeline == 0
 
 
 # ---------------- kb_backfill (actions/backfill/backfill.go:40-71) ----------------

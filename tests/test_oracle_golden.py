@@ -275,15 +275,20 @@ def test_sub_milli_quantities_round_up_like_milli_value():
     assert B.SessionBuilder._milli(0.5) == 500 and B.SessionBuilder._milli(2.5e-3) == 3 and B.SessionBuilder._milli(1.0) == 1000
 
 
-def test_per_launch_kernels_refuse_preferred_node_affinity():
-    """NodeAffinityPriority runs in cycle_kernel (two-pass scan); a session the per-launch kernels would run — here R = 2, W = 1,
-    outside the pipeline's record geometry — is refused by the engine's host build, which is what the emulation runs too."""
+def test_per_launch_kernels_evaluate_preferred_node_affinity_on_the_counter_path():
+    """NodeAffinityPriority runs in cycle_kernel (two-pass scan); a session outside the pipeline's record geometry — here R = 2,
+    W = 1 — runs on the per-visit kernels, which evaluate it with the inter-pod machinery (a pass over the feasible nodes before the
+    visit for the max count, a fresh scan per task of such a class).  Round 1 / early round 2 refused such sessions."""
     import util
     from kube_batch_b200 import builder as B
     from kube_batch_b200.snapshot import PluginConf
+    from oracle import kbo
     s = _pref_session([B.Pod("ns", "p", "", "Pending", {"cpu": 1}, group="g", preferred_terms=[(1, [("zone", "In", ["a"])])])])
-    with pytest.raises(RuntimeError, match="preferred node-affinity"):
-        util.emu_allocate(s, PluginConf.default())
+    assert s.R == 2
+    o = kbo.allocate(s, PluginConf.default())
+    for mode in (0, 1, 5):
+        e = util.emu_allocate(s, PluginConf.default(), mode=mode)
+        util.assert_same_decisions(o.decisions, e.decisions, f"mode {mode}")
 
 
 # ---------------- preempt / reclaim (SURVEY §8f-2): ORACLE ONLY so far; pinned on the reference's own action tests ----------------

@@ -325,3 +325,14 @@ def test_host_level_anti_affinity_as_atoms_in_every_launch_mode(seed):
         finally:
             os.environ.pop("KB_AFF_ATOMS", None)
         util.assert_same_decisions(o.decisions, e.decisions, f"seed {seed} conf {ci} counter path")
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_inter_pod_terms_together_with_preferred_node_affinity(seed):
+    sb = aff_gen.random_affinity_session(300 + seed, n_nodes=4 + seed % 13, n_groups=3 + seed % 6, node_pref=True, p_affine=0.6 if seed % 3 else 0.0)
+    snap = sb.flatten()
+    confs = AFF_CONFS + [PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "-3", "podaffinity.weight": "2"}})]
+    for ci, conf in enumerate(confs):
+        o = kbo.allocate(snap, conf, actions=3)
+        e = util.emu_allocate(snap, conf, actions=3, mode=1)
+        util.assert_same_decisions(o.decisions, e.decisions, f"seed {seed} conf {ci}")
