@@ -883,7 +883,9 @@ int kb_bind_list(kb_engine* e, uint32_t* task, int32_t* node, uint32_t* n) {
 int kb_predicate_score(kb_engine* e, uint32_t task_lo, uint32_t task_hi, uint8_t* fit, double* score) {
   if (!e) return KB_E_BADARG;
   if (!e->loaded) return fail(e, KB_E_STATE, "kb_predicate_score before kb_session_load");
-  if (e->built.aff.on) return fail(e, KB_E_UNSUPPORTED_FEATURE, "kb_predicate_score: the matrix kernels do not evaluate inter-pod affinity");
+  if (e->built.aff.on && score && (e->built.aff.has_weights || e->built.aff.has_pref))
+    return fail(e, KB_E_UNSUPPORTED_FEATURE, "kb_predicate_score: InterPodAffinityPriority / NodeAffinityPriority need reductions over the feasible nodes; "
+                "ask for `fit` only (predicate step 10 is evaluated against the current counters)");
   if (task_lo > task_hi || task_hi > e->T) return fail(e, KB_E_BADARG, "task range [%u,%u) outside [0,%u)", task_lo, task_hi, e->T);
   const size_t n = (size_t)(task_hi - task_lo) * e->N;
   if (n == 0 || e->NT == 0) return KB_OK;

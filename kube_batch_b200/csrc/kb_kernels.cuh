@@ -1483,7 +1483,10 @@ matrix_kernel(const __grid_constant__ DevSession S, const uint32_t* __restrict__
     }
     __syncthreads();
     if (node < S.N) {
-      const uint64_t key = eval_pair(S.cf, cls, acc, node, nullptr);
+      uint64_t key = eval_pair(S.cf, cls, acc, node, nullptr);
+      // inter-pod affinity sessions on the counter path: predicate step 10 against the CURRENT counters (the priority terms need
+      // reductions over the feasible nodes: kb_predicate_score returns fit only for such classes)
+      if (key && S.aff.on && S.cf.predicates && !aff_pred(S.aff, S.aff.cls[task_class[t]], S.N, node)) key = 0;
       const size_t o = (size_t)(t - task_lo) * S.N + node;
       if (fit) fit[o] = key != 0;
       if (score) score[o] = key ? (double)(key_score(key) - S.cf.score_bias) : 0.0;

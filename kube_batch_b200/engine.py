@@ -170,12 +170,14 @@ class Engine:
         self._check(self.L.kb_bind_list(self._h, _p(task, C.c_uint32), _p(node, C.c_int32), C.byref(n)), "kb_bind_list")
         return task[: n.value], node[: n.value]
 
-    def predicate_score(self, lo: int, hi: int):
+    def predicate_score(self, lo: int, hi: int, want_score: bool = True):
+        """kb_predicate_score for tasks [lo, hi) against the current device state.  want_score=False: fit only (sessions whose
+        priorities need a reduction over the feasible nodes — inter-pod / preferred node affinity on the counter path)."""
         N = self.snap.N
         fit = np.zeros((hi - lo, N), dtype=np.uint8)
-        score = np.zeros((hi - lo, N), dtype=np.float64)
-        self._check(self.L.kb_predicate_score(self._h, C.c_uint32(lo), C.c_uint32(hi), _p(fit, C.c_uint8), _p(score, C.c_double)),
-                    "kb_predicate_score")
+        score = np.zeros((hi - lo, N), dtype=np.float64) if want_score else None
+        self._check(self.L.kb_predicate_score(self._h, C.c_uint32(lo), C.c_uint32(hi), _p(fit, C.c_uint8),
+                                              _p(score, C.c_double) if want_score else None), "kb_predicate_score")
         return fit, score
 
     def best_nodes(self, lo: int, hi: int) -> np.ndarray:

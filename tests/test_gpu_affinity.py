@@ -104,7 +104,7 @@ def test_cycle_with_the_placing_actions_and_refusals(eng):
         eng.load_running(snap.meta["running"])
     assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
     with pytest.raises(engine.KbError) as ei:
-        eng.predicate_score(0, 1)
+        eng.predicate_score(0, 1)                  # the priority terms need reductions: only `fit` is offered for such sessions
     assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
     # the flags alone, without the flattened tables: refused
     snap.pod_affinity = None
@@ -204,3 +204,19 @@ def test_inter_pod_terms_together_with_preferred_node_affinity(eng, seed):
     confs = tpa.AFF_CONFS + [PluginConf.from_names([["gang"], ["predicates", "nodeorder"]], {"nodeorder": {"nodeaffinity.weight": "-3", "podaffinity.weight": "2"}})]
     for ci, conf in enumerate(confs):
         run_and_check(eng, snap, conf, f"seed {seed} conf {ci}", actions=3)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_predicate_step_10_fit_matrix_on_the_gpu(eng, seed):
+    """kb_predicate_score (fit only) against the loaded state: the engine's counters + aff_pred vs the oracle's walk over the pods,
+    every pending task x every node — predicate step 10 in isolation (predicates.go:1261-1572)."""
+    sb = aff_gen.random_affinity_session(800 + seed, n_nodes=6 + seed % 11, n_groups=4 + seed % 5)
+    snap = sb.flatten()
+    if snap.pod_affinity is None:
+        pytest.skip("no affinity terms drawn")
+    conf = PluginConf.default()
+    eng.load(snap, conf)
+    fit, _ = eng.predicate_score(0, snap.T, want_score=False)
+    for t in range(snap.T):
+        ofit, _ = kbo.predicate_score(snap, conf, t)
+        np.testing.assert_array_equal(fit[t], ofit, err_msg=f"seed {seed} task {t}")
