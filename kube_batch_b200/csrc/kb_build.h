@@ -235,7 +235,10 @@ struct BuiltSession {
   std::vector<ClassPref> class_pref; // [C] preferred node-affinity terms per class — HOST ONLY (read by tests/emu's prototype of
   bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
   AffDev aff{};                      // inter-pod (anti)affinity: sizes and flags (pointers are set by bind())
-  bool aff_session = false;          // the snapshot carries kb_pod_affinity (counter path OR atoms): reclaim / preempt are refused
+  bool aff_session = false;          // the snapshot carries kb_pod_affinity (counter path OR atoms)
+  bool aff_evict_ok = true;          // reclaim / preempt may run: no affinity tables, or host-level atoms with NO member among the pods
+                                     // already placed — then a victim (a Running pod) is never a member, an eviction changes no bit, and
+                                     // the preemptors are Pipelined (never members): the bits stay exact through the whole action list
   uint64_t aff_atom_mask[KB_MAX_W] = {0};   // port-word bits that encode host-level anti-affinity groups (hidden from kb_node_state)
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
   std::vector<uint32_t> q_alloc_present;   // [Q] scalar presence of proportion's queueAttr.allocated at session open (kb_evict.h: Resource.Less)
@@ -332,6 +335,7 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
   int rc = resolve_conf(e, conf, R, W, hc);
   if (rc) return rc;
   B.aff_session = pa != nullptr;
+  B.aff_evict_ok = pa == nullptr;
   for (uint32_t w = 0; w < KB_MAX_W; ++w) B.aff_atom_mask[w] = 0;
   // Host-level inter-pod anti-affinity as ATOMS.  When every counter the session's tasks read or join lives on a key set whose
   // domains are exactly the nodes (kubernetes.io/hostname), "a member of group g sits in the node's domain" is a per-node bit,
@@ -397,6 +401,8 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
         for (uint32_t n = 0; n < N; ++n)
           if (pa->group_count0[aff_group_off0[g] + (uint32_t)pa->node_domain[(size_t)ks * N + n]] > 0) node_aff_bits[(size_t)(a / 64) * N + n] |= 1ull << (a % 64);
       }
+      B.aff_evict_ok = true;
+      for (uint64_t b : node_aff_bits) if (b) { B.aff_evict_ok = false; break; }
     } else {
       // the counters of a topology domain change the keys of many nodes at once: per-visit kernels, fresh scan per task for
       // the classes that read them (kb_aff.h); no look-ahead lists, no overlap, no node sharding

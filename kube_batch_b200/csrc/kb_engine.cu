@@ -683,7 +683,9 @@ int kb_session_load_running(kb_engine* e, const kb_snapshot* s, const kb_running
     return fail(e, KB_E_BADARG, "kb_session_load_running: `snap` is not the snapshot of the loaded session");
   if (e->world > 1 && !e->replicated) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt run on the full node table: not with KB_ENGINE_SHARD");
   if (e->built.has_pref) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt with preferred node affinity are outside this build");
-  if (e->built.aff_session) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt in a session with inter-pod affinity are outside this build (the victim walk does not update the affinity counters / member bits)");
+  if (e->built.aff_session && !e->built.aff_evict_ok)
+    return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt in this session with inter-pod affinity are outside this build: the victim walk does not "
+                "update the affinity counters / member bits (only host-level anti-affinity whose groups have no member among the placed pods is safe)");
   CUDA_TRY(e, cudaSetDevice(e->device));
   e->running_loaded = false;
   BuildErr be;

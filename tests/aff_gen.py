@@ -172,3 +172,44 @@ def random_affinity_session(seed: int, n_nodes: int = 12, n_groups: int = 6, p_a
                 p.requests = {}
             sb.add_pod(p)
     return sb
+
+
+def evict_spread_cluster(seed: int, members_running: bool = False):
+    """Clusters that make reclaim / preempt evict (several queues, priorities, Running / terminating / Pending pods like
+    tests/test_evict_parity.random_cluster) whose PENDING pods partly carry "one replica per host"; members_running: the pods already
+    running carry the labels + terms too (then a victim can be a member of a counter group and the engine refuses the evicting actions)."""
+    rng = np.random.default_rng(7000 + seed)
+    b = B.SessionBuilder()
+    nq = int(rng.integers(1, 4))
+    for q in range(nq):
+        b.add_queue(B.Queue(f"q{q}", int(rng.integers(1, 4)), creation=int(rng.integers(0, 3))))
+    nn = int(rng.integers(2, 9))
+    for n in range(nn):
+        b.add_node(B.Node(f"n{n:04d}", {"cpu": 8, "memory": 32e9, "pods": int(rng.integers(6, 14))}, labels={HOST: f"n{n:04d}"}))
+    cap = {f"n{n:04d}": 8.0 for n in range(nn)}
+    k = 0
+    for g in range(int(rng.integers(2, 9))):
+        b.add_pod_group(B.PodGroup("ns", f"g{g}", f"q{int(rng.integers(0, nq))}", min_member=int(rng.integers(0, 4)),
+                                   priority=int(rng.integers(0, 3)), creation=int(rng.integers(0, 4))))
+        cpu = float(rng.choice([0.5, 1, 2, 3]))
+        req = {"cpu": cpu, "memory": cpu * 1e9}
+        lab = APPS[int(rng.integers(0, 3))]
+        spread = rng.random() < 0.6
+        for i in range(int(rng.integers(1, 7))):
+            state = rng.choice(["Running", "Running", "Pending", "Pending", "Deleting"])
+            node = ""
+            if state != "Pending":
+                free = [n for n, c in cap.items() if c >= cpu]
+                if not free:
+                    state = "Pending"
+                else:
+                    node = str(rng.choice(free))
+                    cap[node] -= cpu
+            p = B.Pod("ns", f"g{g}-p{i}", node, "Pending" if state == "Pending" else "Running", dict(req), group=f"g{g}",
+                      priority=int(rng.integers(0, 3)), creation=int(rng.integers(0, 5)) if rng.random() < 0.5 else k, deleting=(state == "Deleting"))
+            if spread and (state == "Pending" or members_running):
+                p.labels = {"app": lab}
+                p.pod_anti_affinity = B.PodAffinity(required=[B.PodAffinityTerm(HOST, match_labels={"app": lab})])
+            b.add_pod(p)
+            k += 1
+    return b.flatten()

@@ -760,6 +760,9 @@ int kbemu_cycle(const kb_snapshot* snap, const kb_running* running, const kb_plu
     if (actions[i] == 3 && actions[i + 1] != 3) { g_err = "an action after preempt is outside this build (kb_cycle)"; return KB_E_UNSUPPORTED_FEATURE; }
   Emu* E = (Emu*)kbemu_create2(snap, conf, 0, 1, mode);
   if (!E) return KB_E_BADARG;
+  if (E->B.aff_session && !E->B.aff_evict_ok && running && running->n)
+    for (uint32_t i = 0; i < n_actions; ++i)
+      if (actions[i] == 0 || actions[i] == 3) { g_err = "reclaim / preempt in this session with inter-pod affinity are outside this build"; delete E; return KB_E_UNSUPPORTED_FEATURE; }
   EvictBuilt EB;
   BuildErr be;
   if (int rc = build_evict(snap, running, E->B, E->S, EB, &be)) { g_err = be.msg; delete E; return rc; }

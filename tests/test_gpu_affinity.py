@@ -220,3 +220,28 @@ def test_predicate_step_10_fit_matrix_on_the_gpu(eng, seed):
     for t in range(snap.T):
         ofit, _ = kbo.predicate_score(snap, conf, t)
         np.testing.assert_array_equal(fit[t], ofit, err_msg=f"seed {seed} task {t}")
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_the_shipped_action_list_with_host_level_anti_affinity_on_the_gpu(eng, seed):
+    """kb_cycle("reclaim, allocate, backfill, preempt") through the C ABI on sessions whose pending pods carry "one replica per host"
+    (no placed pod is a member): evict kernels + cycle_kernel / visit_kernel read the member bits from the node records."""
+    from test_evict_parity import tier_variants
+    s = aff_gen.evict_spread_cluster(40 + seed)
+    if s.pod_affinity is None:
+        pytest.skip("no spread group drawn")
+    acts = ("reclaim", "allocate", "backfill", "preempt")
+    for tname, tiers in tier_variants():
+        o, ev, order = kbo.cycle(s, tiers, actions=acts, running=s.meta["running"])
+        eng.load(s, tiers)
+        eng.load_running(s.meta["running"])
+        r, gev, gorder, _ = eng.cycle(acts)
+        np.testing.assert_array_equal(ev, gev, err_msg=f"seed {seed} {tname}: evicted set")
+        np.testing.assert_array_equal(order, gorder, err_msg=f"seed {seed} {tname}: eviction order")
+        util.assert_same_decisions(o.decisions, r.decisions, f"seed {seed} {tname}")
+        util.assert_same_state(o, eng.node_state(), eng.order_state(), f"seed {seed} {tname}")
+    s = aff_gen.evict_spread_cluster(0, members_running=True)
+    eng.load(s, PluginConf.default())
+    with pytest.raises(engine.KbError) as ei:
+        eng.load_running(s.meta["running"])
+    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE

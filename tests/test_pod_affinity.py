@@ -336,3 +336,26 @@ def test_inter_pod_terms_together_with_preferred_node_affinity(seed):
         o = kbo.allocate(snap, conf, actions=3)
         e = util.emu_allocate(snap, conf, actions=3, mode=1)
         util.assert_same_decisions(o.decisions, e.decisions, f"seed {seed} conf {ci}")
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_reclaim_and_preempt_with_host_level_anti_affinity_on_pending_pods(seed):
+    """The shipped action list on sessions whose PENDING pods carry "one replica per host" while no placed pod is a member of a counter
+    group: a victim (a Running pod) is then never a member, an eviction changes no member bit, the preemptors are Pipelined (not
+    listed by util.PodLister) — the atoms stay exact through reclaim / allocate / backfill / preempt.  Emulation vs the oracle (whose
+    PodLister follows every status change)."""
+    from test_evict_parity import compare, tier_variants
+    s = aff_gen.evict_spread_cluster(seed)
+    if s.pod_affinity is None:
+        pytest.skip("no spread group drawn")
+    for tname, tiers in tier_variants():
+        for acts in (("reclaim", "allocate", "backfill", "preempt"), ("reclaim",), ("allocate", "preempt")):
+            o, ev, order = kbo.cycle(s, tiers, actions=acts, running=s.meta["running"])
+            g, gev, gorder = util.emu_cycle(s, tiers, acts, s.meta["running"], mode=1)
+            compare(f"seed {seed} {tname} {acts}", o, ev, order, g, gev, gorder, util.emu_states(g))
+
+
+def test_evicting_actions_are_refused_when_a_placed_pod_is_a_member():
+    s = aff_gen.evict_spread_cluster(0, members_running=True)
+    with pytest.raises(RuntimeError, match="reclaim / preempt in this session"):
+        util.emu_cycle(s, PluginConf.default(), ("reclaim", "allocate", "backfill", "preempt"), s.meta["running"], mode=1)
