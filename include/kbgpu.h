@@ -215,8 +215,10 @@ typedef struct kb_snapshot {
   const int32_t*  task_pref_weights;  /* [KB_MAX_PREF_TERMS][T] PreferredSchedulingTerm.Weight (0 = term skipped) */
 
   /* ---- inter-pod (anti)affinity (predicate step 10 + InterPodAffinityPriority), NULL = no pod of the session carries terms.
-   * With it the cycle runs on the per-visit kernels (fresh scan per task for the classes that read the counters); kb_reclaim /
-   * kb_preempt refuse such sessions (KB_E_UNSUPPORTED_FEATURE). ---- */
+   * Host-level anti-affinity (every group on a key set whose domains are the nodes, no required affinity, no live weights) is folded
+   * into the node records and costs nothing; anything else runs on the per-visit kernels (fresh scan per task for the classes that
+   * read the counters).  kb_session_load_running (reclaim / preempt) refuses such sessions (KB_E_UNSUPPORTED_FEATURE) unless they are
+   * of the first kind and no pod already placed is a member of a group. ---- */
   const kb_pod_affinity* pod_affinity;
 } kb_snapshot;
 
