@@ -111,6 +111,9 @@ func (c *Cycle) flattenRunning(ssn *framework.Session, f *Flat) *runningFlat {
 			if cn == scheduling.SystemClusterCritical || cn == scheduling.SystemNodeCritical || t.Namespace == v1.NamespaceSystem {
 				r.flags[i] |= uint32(C.KB_RUNNING_CRITICAL)
 			}
+			if f.podAff != nil && f.podAff.members[t.Pod] { // its eviction takes it out of util.PodLister: kbgpu.h KB_RUNNING_AFF_MEMBER
+				r.flags[i] |= uint32(C.KB_RUNNING_AFF_MEMBER)
+			}
 		}
 	}
 	for j, id := range f.JobIDs { // WaitingTaskNum (job_info.go:396-405): 0 unless an earlier action pipelined tasks

@@ -41,6 +41,7 @@ type podAff struct {
 	taskWeightOff             []uint32
 	weightKind, weightKeyset  []int32
 	weightValue               []int64
+	members                   map[*v1.Pod]bool // listed pods that are members of a counter group: KB_RUNNING_AFF_MEMBER for the Running ones
 }
 
 // termProps is what a term selects: GetNamespacesFromPodAffinityTerm + LabelSelectorAsSelector (topologies.go:25-49)
@@ -389,11 +390,13 @@ func flattenPodAffinity(ssn *framework.Session, f *Flat, nidx map[string]int, sn
 	}
 	pa.groupCount0 = make([]int32, max1(gOff[len(groups)]))
 	pa.groupTotal0 = make([]int32, max1(len(groups)))
+	pa.members = map[*v1.Pod]bool{}
 	for i, p := range listed {
 		for g, gr := range groups {
 			if !gr.member[ltype[i]] {
 				continue
 			}
+			pa.members[p.pod] = true
 			pa.groupTotal0[g]++
 			if d := pa.nodeDomain[gr.keyset*N+p.node]; d >= 0 {
 				pa.groupCount0[gOff[g]+int(d)]++

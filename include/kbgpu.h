@@ -258,6 +258,11 @@ typedef struct kb_plugin_conf {
  * job_ready0 / job_alloc0 and the node's Idle / Used / pod count already include it.
  */
 #define KB_RUNNING_CRITICAL (1u << 0) /* system-cluster-critical / system-node-critical priority class or kube-system namespace (conformance.go:45-53) */
+#define KB_RUNNING_AFF_MEMBER (1u << 1) /* the pod is a member of an inter-pod affinity counter group (kb_pod_affinity): evicting it takes it out of
+                                            util.PodLister and can open its topology domain for other pods.  The engine keeps host-level groups as
+                                            bits of the node records and does not clear them: when such a pod IS evicted (even inside a Statement that is
+                                            discarded later) kb_cycle / kb_reclaim / kb_preempt return KB_E_UNSUPPORTED_FEATURE instead of a result — the
+                                            shim reruns that cycle with the original actions.  Flatteners MUST set it for every Running member. */
 typedef struct kb_running {
   uint32_t n;
   uint32_t reserved0;

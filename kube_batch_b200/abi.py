@@ -254,6 +254,7 @@ class kb_stats(C.Structure):
 
 
 KB_RUNNING_CRITICAL = 1 << 0
+KB_RUNNING_AFF_MEMBER = 1 << 1
 
 
 class kb_running(C.Structure):

@@ -493,6 +493,10 @@ class SessionBuilder:
             existing = [p for p in self.pods if id(p) not in pend_ids and p.node_name in nidx and self._task_status(p) != "Pending"]
             s.pod_affinity, pod_objects = flatten_pod_affinity(nodes, pending, existing, s, on_node,
                                                                lambda p: self._task_status(p), lambda p: f"{p.namespace}/{p.group}" in jidx)
+            members = s.pod_affinity.pop("member_pod_ids")
+            for i, p in enumerate(running):
+                if id(p) in members:
+                    rt["flags"][i] |= abi.KB_RUNNING_AFF_MEMBER      # its eviction would take it out of util.PodLister (kbgpu.h)
         s.meta = {"pod_objects": pod_objects, "running": rt, "nodes": [n.name for n in nodes], "tasks": [f"{p.namespace}/{p.name}" for p in pending],
                   "jobs": list(jidx.keys()), "queues": [q.name for q in queues], "dims": dims}
         s.validate()
@@ -758,6 +762,7 @@ def flatten_pod_affinity(nodes, pending, existing, s, on_node, status_of, in_ses
 
     # ---- the raw objects (what a checker that walks the pods one by one needs): pending pods in task order, then the others ----
     lset, tset = set(id(p) for p in listed), set(id(p) for p in in_tasks)
+    pa["member_pod_ids"] = set(id(p) for p, ty in zip(listed, ltype) if any(g_member[g][ty] for g in range(NG)))   # -> KB_RUNNING_AFF_MEMBER
     ob = {"nodes": nodes, "pending": list(pending), "existing": list(existing), "node_index": nidx,
           "listed": [id(p) in lset for p in existing], "in_tasks": [id(p) in tset for p in existing]}
     return pa, ob

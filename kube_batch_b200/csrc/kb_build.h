@@ -236,9 +236,9 @@ struct BuiltSession {
   bool has_pref = false;             // the two-pass scan); the device slabs do not carry them yet
   AffDev aff{};                      // inter-pod (anti)affinity: sizes and flags (pointers are set by bind())
   bool aff_session = false;          // the snapshot carries kb_pod_affinity (counter path OR atoms)
-  bool aff_evict_ok = true;          // reclaim / preempt may run: no affinity tables, or host-level atoms with NO member among the pods
-                                     // already placed — then a victim (a Running pod) is never a member, an eviction changes no bit, and
-                                     // the preemptors are Pipelined (never members): the bits stay exact through the whole action list
+  bool aff_evict_ok = true;          // reclaim / preempt may run: no affinity tables, or host-level anti-affinity as atoms.  The bits stay
+                                     // exact as long as no MEMBER is evicted (a victim that is no member changes nothing, preemptors are
+                                     // Pipelined: never members); the eviction of a member (KB_RUNNING_AFF_MEMBER) withholds the outcome
   uint64_t aff_atom_mask[KB_MAX_W] = {0};   // port-word bits that encode host-level anti-affinity groups (hidden from kb_node_state)
   uint32_t Tb = 0;                   // backfill order slots: Pending tasks with InitResreq.IsEmpty() (backfill.go:47)
   std::vector<uint32_t> q_alloc_present;   // [Q] scalar presence of proportion's queueAttr.allocated at session open (kb_evict.h: Resource.Less)
@@ -402,7 +402,6 @@ inline int build_session(const kb_snapshot* s, const kb_plugin_conf* conf, uint3
           if (pa->group_count0[aff_group_off0[g] + (uint32_t)pa->node_domain[(size_t)ks * N + n]] > 0) node_aff_bits[(size_t)(a / 64) * N + n] |= 1ull << (a % 64);
       }
       B.aff_evict_ok = true;
-      for (uint64_t b : node_aff_bits) if (b) { B.aff_evict_ok = false; break; }
     } else {
       // the counters of a topology domain change the keys of many nodes at once: per-visit kernels, fresh scan per task for
       // the classes that read them (kb_aff.h); no look-ahead lists, no overlap, no node sharding

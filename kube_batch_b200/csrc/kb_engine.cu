@@ -685,7 +685,7 @@ int kb_session_load_running(kb_engine* e, const kb_snapshot* s, const kb_running
   if (e->built.has_pref) return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt with preferred node affinity are outside this build");
   if (e->built.aff_session && !e->built.aff_evict_ok)
     return fail(e, KB_E_UNSUPPORTED_FEATURE, "reclaim / preempt in this session with inter-pod affinity are outside this build: the victim walk does not "
-                "update the affinity counters / member bits (only host-level anti-affinity whose groups have no member among the placed pods is safe)");
+                "update the affinity counters (only host-level anti-affinity, kept as bits of the node records, runs the evicting actions)");
   CUDA_TRY(e, cudaSetDevice(e->device));
   e->running_loaded = false;
   BuildErr be;
@@ -829,6 +829,8 @@ int kb_cycle(kb_engine* e, const uint8_t* actions, uint32_t n_actions, kb_decisi
   int rc = finish_cycle(e, bf_last, ready_taken ? e->d_ready_start : e->d_job_ready0, out, stats, launches, BATCH, use_pipe);
   if (rc) return rc;
   if (ectl.error == 2) return fail(e, KB_E_UNSUPPORTED_FEATURE, "a node hands more than %u victims to one preemptor", KB_EVICT_MAXV);
+  if (ectl.error == 3) return fail(e, KB_E_UNSUPPORTED_FEATURE, "a member of an inter-pod affinity counter group was evicted (KB_RUNNING_AFF_MEMBER): the member bits "
+                                   "of the node records are stale from that point on, the outcome of this cycle is withheld");
   if (ectl.error) return fail(e, KB_E_STATE, "the reference would panic here: Resource.Sub on an insufficient resource (resource_info.go:158)");
   if (n) {
     const uint32_t* r_orig = (const uint32_t*)(e->ev_built.imm.host.data() + e->ev_built.oi.r_orig);

@@ -213,6 +213,9 @@ KB_HD void evict_apply(const DevSession& S, const EvictDev& E, const uint32_t no
   const size_t tile_u64 = (size_t)S.ncols * TILE_NODES;
   uint64_t* t = S.tiles + (size_t)(node / TILE_NODES) * tile_u64 + (node % TILE_NODES);
   E.r_state[slot] = undo ? 0 : 1;
+  // KB_RUNNING_AFF_MEMBER: the victim leaves util.PodLister — the member bits of the node records (host-level inter-pod
+  // anti-affinity as atoms, kb_build.h) would have to change with it.  They do not: the cycle's outcome is withheld (error 3).
+  if (!undo && (E.r_flags[slot] & KB_RUNNING_AFF_MEMBER) && E.ctl->error == 0) E.ctl->error = 3;
   S.job_ready[j] += undo ? 1 : -1;                                         // Running counts as ready, Releasing does not (job_info.go:383-393)
   for (uint32_t k = 0; k < R; ++k) {
     const double r = E.r_resreq[(size_t)k * n + slot];

@@ -793,6 +793,7 @@ int kbemu_cycle(const kb_snapshot* snap, const kb_running* running, const kb_plu
     if (a == 0 || a == 3) {
       if (have_latest) D.ctl->step = latest;
       if (a == 3) run_preempt(x, E->S, D); else run_reclaim(x, E->S, D);
+      if (D.ctl->error == 3) { g_err = "a member of an inter-pod affinity counter group was evicted: the outcome of this cycle is withheld"; delete E; return KB_E_UNSUPPORTED_FEATURE; }
       if (D.ctl->error) { g_err = D.ctl->error == 2 ? "victim overflow" : "the reference would panic (Resource.Sub)"; delete E; return KB_E_STATE; }
       latest = D.ctl->step; have_latest = true; dirty = true;
     } else {
@@ -841,6 +842,7 @@ int kbemu_evict(const kb_snapshot* snap, const kb_running* running, const kb_plu
   CpuExec x;
   if (action) run_preempt(x, E->S, D); else run_reclaim(x, E->S, D);
   const EvictCtl& ctl = *D.ctl;
+  if (ctl.error == 3) { g_err = "a member of an inter-pod affinity counter group was evicted: the outcome of this action is withheld"; delete E; return KB_E_UNSUPPORTED_FEATURE; }
   if (ctl.error) { g_err = ctl.error == 2 ? "victim overflow" : "the reference would panic (Resource.Sub)"; delete E; return KB_E_STATE; }
   const uint32_t n = EB.n_run, T = E->B.T;
   for (uint32_t k = 0; k < n; ++k) {

@@ -240,8 +240,20 @@ def test_the_shipped_action_list_with_host_level_anti_affinity_on_the_gpu(eng, s
         np.testing.assert_array_equal(order, gorder, err_msg=f"seed {seed} {tname}: eviction order")
         util.assert_same_decisions(o.decisions, r.decisions, f"seed {seed} {tname}")
         util.assert_same_state(o, eng.node_state(), eng.order_state(), f"seed {seed} {tname}")
-    s = aff_gen.evict_spread_cluster(0, members_running=True)
-    eng.load(s, PluginConf.default())
-    with pytest.raises(engine.KbError) as ei:
+    # pods already running are members of the groups: the outcome is withheld iff a member gets evicted (KB_RUNNING_AFF_MEMBER)
+    s = aff_gen.evict_spread_cluster(seed, members_running=True)
+    if s.pod_affinity is None:
+        return
+    member = (s.meta["running"]["flags"] & abi.KB_RUNNING_AFF_MEMBER) != 0
+    for tname, tiers in tier_variants():
+        o, ev, order = kbo.cycle(s, tiers, actions=acts, running=s.meta["running"])
+        eng.load(s, tiers)
         eng.load_running(s.meta["running"])
-    assert ei.value.code == abi.KB_E_UNSUPPORTED_FEATURE
+        try:
+            r, gev, gorder, _ = eng.cycle(acts)
+        except engine.KbError as ex:
+            assert ex.code == abi.KB_E_UNSUPPORTED_FEATURE and "withheld" in str(ex)
+            continue
+        np.testing.assert_array_equal(ev, gev, err_msg=f"members seed {seed} {tname}: evicted set")
+        util.assert_same_decisions(o.decisions, r.decisions, f"members seed {seed} {tname}")
+        assert not (gev & member).any()
