@@ -217,8 +217,8 @@ typedef struct kb_snapshot {
   /* ---- inter-pod (anti)affinity (predicate step 10 + InterPodAffinityPriority), NULL = no pod of the session carries terms.
    * Host-level anti-affinity (every group on a key set whose domains are the nodes, no required affinity, no live weights) is folded
    * into the node records and costs nothing; anything else runs on the per-visit kernels (fresh scan per task for the classes that
-   * read the counters).  kb_session_load_running (reclaim / preempt) refuses such sessions (KB_E_UNSUPPORTED_FEATURE) unless they are
-   * of the first kind and no pod already placed is a member of a group. ---- */
+   * read the counters).  kb_session_load_running (reclaim / preempt) refuses sessions of the second kind (KB_E_UNSUPPORTED_FEATURE);
+   * in the first kind the evicting actions run and only the eviction of a group MEMBER (KB_RUNNING_AFF_MEMBER) withholds the outcome. ---- */
   const kb_pod_affinity* pod_affinity;
 } kb_snapshot;
 
