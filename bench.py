@@ -164,7 +164,9 @@ def run_reference(args, rank, world):
               f"whole cycle really executed in {opt['seconds']:.1f} s) shown as value_mode_b")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True, "scaling": "strong",
+        "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, len(vals)), "higher_is_better": True,
+        # same label as our arm at this N (N > 1: one cluster per GPU there); the CPU rate itself does not depend on N
+        "scaling": "weak" if (world > 1 and args.sessions == "independent") else "strong",
         "vs_baseline": None, "dtype": "f64/i64 (CPU)", "data": "synthetic", "config": workload_desc(args.workload, snap, conf),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
                          "value_mode_b": opt["pairs_per_s"], "host_cores": cores, "samples": last[0], "estimated_cycle_seconds": last[2]},
